@@ -1,0 +1,132 @@
+"""Pin the oracle restatement against outputs of the UNMODIFIED reference (tests/golden, made by
+oracle/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+import dsdiff_oracle as O
+from _util import golden, synth_sd, maxabs
+
+TOL = 2e-5      # fp32 CPU, different op fusion/order inside torch kernels only
+
+
+def test_unet_small_matches_reference():
+    hp, sd = synth_sd("unet_small")
+    g = golden("unet_small")
+    y = O.unet_forward(sd, hp, g["x"], g["t"])
+    assert y.shape == g["y"].shape
+    assert g["y"].abs().max() > 0.05            # fixture is not degenerate
+    assert maxabs(y, g["y"]) < TOL * max(1.0, float(g["y"].abs().max()))
+
+
+def test_unet_legacy_attention_film_float_t():
+    hp, sd = synth_sd("unet_legacy_film")
+    g = golden("unet_legacy_film")
+    y = O.unet_forward(sd, hp, g["x"], g["t"])
+    assert maxabs(y, g["y"]) < TOL * max(1.0, float(g["y"].abs().max()))
+
+
+def test_dsunet_matches_reference_including_feature_dict():
+    hp, sd = synth_sd("ds_small")
+    g = golden("ds_small")
+    y, f = O.dsunet_forward(sd, hp, g["x"], g["t"])
+    s = max(1.0, float(g["y"].abs().max()))
+    assert maxabs(y, g["y"]) < TOL * s
+    assert maxabs(f["style"][0], g["style0"]) < TOL * s
+    assert maxabs(f["content"][2], g["content2"]) < TOL * s
+    assert maxabs(f["anatomy"][1], g["anatomy1"]) < TOL * s
+    assert maxabs(f["lesion"][0], g["lesion0"]) < TOL * s
+    for i in range(4):
+        assert maxabs(f["n_style_content"][i], g[f"nsc{i}"]) < TOL * s
+
+
+def test_dsunet_two_channel_input_zero_fills_streams():
+    hp, sd = synth_sd("ds_small")
+    g = golden("ds_small_2ch")
+    y, _ = O.dsunet_forward(sd, hp, g["x"], g["t"])
+    assert maxabs(y, g["y"]) < TOL * max(1.0, float(g["y"].abs().max()))
+
+
+def test_ldm_tables_bit_exact():
+    g = golden("tables_ldm_T2000_S50")
+    sch = O.LdmSchedule(2000, "linear", 1e-4, 2e-2)
+    for name, ref in (("betas", "betas"), ("alphas_cumprod", "alphas_cumprod"),
+                      ("sqrt_alphas_cumprod", "sqrt_ac"), ("sqrt_one_minus_alphas_cumprod", "sqrt_1mac"),
+                      ("posterior_log_variance_clipped", "post_logvar"),
+                      ("posterior_mean_coef1", "coef1"), ("posterior_mean_coef2", "coef2")):
+        assert np.array_equal(getattr(sch, name), g[ref].numpy()), name
+    tab = O.LdmDdimTables(sch, 50, eta=0.3)
+    assert np.array_equal(tab.timesteps, g["ddim_timesteps"].numpy())
+    assert tab.timesteps[0] == 1 and tab.timesteps[-1] == 1961
+    assert np.array_equal(tab.alphas, g["ddim_alphas"].numpy())
+    assert np.array_equal(tab.alphas_prev, g["ddim_alphas_prev"].numpy())
+    assert np.array_equal(tab.sqrt_one_minus_alphas, g["ddim_s1m"].numpy())
+    assert np.array_equal(tab.sigmas, g["ddim_sigmas"].numpy())
+
+
+@pytest.mark.parametrize("resp", ["50", "20"])
+def test_gd_tables_bit_exact(resp):
+    g = golden(f"tables_gd_T1000_S{resp}")
+    sch = O.GdSchedule(1000, "linear", resp, True)
+    assert sch.timestep_map == g["timestep_map"].tolist()
+    assert np.array_equal(sch.betas, g["betas"].numpy())
+    assert np.array_equal(sch.alphas_cumprod, g["alphas_cumprod"].numpy())
+    assert np.array_equal(sch.posterior_log_variance_clipped, g["post_logvar"].numpy())
+    assert np.array_equal(sch.posterior_mean_coef1, g["coef1"].numpy())
+    assert np.array_equal(sch.posterior_mean_coef2, g["coef2"].numpy())
+    assert np.array_equal(sch.sqrt_recipm1_alphas_cumprod, g["sqrt_recipm1"].numpy())
+
+
+@pytest.mark.parametrize("param", ["v", "eps"])
+@pytest.mark.parametrize("eta", [0.0, 0.7])
+def test_v1_ldm_ddim_steps_and_loop(param, eta):
+    g = golden(f"v1_ddim_{param}_eta{eta}")
+    sch = O.LdmSchedule(2000, "linear", 1e-4, 2e-2)
+    S = g["S"]
+    tab = O.LdmDdimTables(sch, S, eta)
+    # (1) update kernel alone: feed the reference's own model outputs, compare every step
+    x = g["x_T"]
+    for i in range(S):
+        index = S - 1 - i
+        x_prev, x0 = O.ldm_ddim_step(sch, tab, x, g["model_out"][i], index, g["noises"][i], param, True)
+        assert maxabs(x_prev, g["x_inter"][i]) < 2e-6
+        assert maxabs(x0, g["pred_x0"][i]) < 2e-6
+        x = g["x_inter"][i]
+    # (2) full loop with the oracle network
+    hp, sd = synth_sd("unet_small")
+    rec = []
+    final = O.ldm_ddim_loop(lambda xc, t: O.unet_forward(sd, hp, xc, t), sch, S, g["x_T"], g["cond"],
+                            g["noises"], eta, param, True, record=rec)
+    assert maxabs(final, g["final"]) < 1e-4
+    assert maxabs(rec[0]["model_out"], g["model_out"][0]) < 1e-4
+
+
+@pytest.mark.parametrize("param", ["v", "eps", "x0"])
+def test_v2_ldm_ancestral(param):
+    g = golden(f"v2_ddpm_{param}")
+    T = g["T"]
+    sch = O.LdmSchedule(T, "linear", 1e-4, 2e-2)
+    hp, sd = synth_sd("unet_small")
+    rec = []
+    final = O.ldm_ddpm_loop(lambda xc, t: O.unet_forward(sd, hp, xc, t), sch, g["x_T"], g["cond"],
+                            g["noises"], param, True, record=rec)
+    for i in range(T):
+        assert maxabs(rec[i]["x_prev"], g["x_inter"][i]) < 1e-4, i
+    assert maxabs(final, g["final"]) < 1e-4
+
+
+@pytest.mark.parametrize("mode,eta", [("ddim", 0.0), ("ddim", 0.5), ("ddpm", 0.0)])
+@pytest.mark.parametrize("tag", ["ls", "fixed"])
+def test_v3_v4_guided_diffusion(mode, eta, tag):
+    g = golden(f"v34_{mode}_{tag}_eta{eta}")
+    sch = O.GdSchedule(1000, "linear", "5", True)
+    assert sch.timestep_map == g["timestep_map"].tolist()
+    hp, sd = synth_sd("ds_film2" if tag == "ls" else "ds_small")
+    rec = []
+    final = O.gd_loop(lambda xc, t: O.dsunet_forward(sd, hp, xc, t), sch, g["x_T"], g["cond"], g["noises"],
+                      mode=mode, eta=eta, record=rec, parameterization="v", learn_sigma=(tag == "ls"),
+                      clip_denoised=True)
+    for i in range(g["S"]):
+        assert maxabs(rec[i]["pred_x0"], g["pred_x0"][i]) < 1e-4, i
+        assert maxabs(rec[i]["x_prev"], g["x_inter"][i]) < 1e-4, i
+    assert maxabs(final, g["final"]) < 1e-4
