@@ -1,0 +1,11 @@
+"""B200-native (sm_100a) sampling hot path for larrybb626/diffusion_models_dsdiff.
+
+Drop-in operator surface (same names, arguments and state_dict keys as the reference):
+``UNetModel``, ``DSUnetModel``, ``DDPM`` / ``DiffusionWrapper``, ``DDIMSampler``,
+``GaussianDiffusion`` / ``SpacedDiffusion`` / ``create_gaussian_diffusion``.
+All arithmetic runs in libb200diff.so (include/b200diff.h); there is no CPU fallback.
+"""
+from ._lib import B200Error, LIB_PATH, launch_count  # noqa: F401
+from .unet import UNetModel  # noqa: F401
+
+__all__ = ["B200Error", "LIB_PATH", "launch_count", "UNetModel"]

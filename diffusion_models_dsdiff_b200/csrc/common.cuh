@@ -1,0 +1,248 @@
+// Shared device/host helpers for libb200diff (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/b200diff.h"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define B200_CHECK(cond, ...)            \
+  do {                                   \
+    if (!(cond)) {                       \
+      b200::set_error(__VA_ARGS__);      \
+      return 1;                          \
+    }                                    \
+  } while (0)
+
+#define B200_CUDA(call)                                                              \
+  do {                                                                               \
+    cudaError_t e__ = (call);                                                        \
+    if (e__ != cudaSuccess) {                                                        \
+      b200::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return 2;                                                                      \
+    }                                                                                \
+  } while (0)
+
+// every launch goes through here so gpu_launches is a counted fact
+#define B200_LAUNCH_CHECK()                                     \
+  do {                                                          \
+    b200::g_launches.fetch_add(1, std::memory_order_relaxed);   \
+    B200_CUDA(cudaGetLastError());                              \
+  } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+int num_sms();
+
+// ------------------------------------------------------------------------------------------
+// 16-bit activation type traits
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct Act;
+template <>
+struct Act<__half> {
+  static constexpr int kFmt = 0;  // UMMA F16
+  __device__ __forceinline__ static float to_f(__half v) { return __half2float(v); }
+  __device__ __forceinline__ static __half from_f(float v) {
+    // saturate instead of producing inf: fp16 max is 65504
+    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    return __float2half_rn(v);
+  }
+};
+template <>
+struct Act<__nv_bfloat16> {
+  static constexpr int kFmt = 1;  // UMMA BF16
+  __device__ __forceinline__ static float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __device__ __forceinline__ static __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+
+// 8 x 16-bit packed in a uint4
+template <typename T>
+__device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
+  const T *p = reinterpret_cast<const T *>(&u);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = Act<T>::to_f(p[i]);
+}
+template <typename T>
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  T *p = reinterpret_cast<T *>(&u);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p[i] = Act<T>::from_f(f[i]);
+  return u;
+}
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
+
+// streaming 128-bit access (read-once / write-once tensors)
+__device__ __forceinline__ uint4 ld_stream(const void *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(void *p, const uint4 &v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier / TMA / tcgen05 PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((++spins & 0x3ff) == 0) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+        printf("b200diff: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n",
+               blockIdx.x, threadIdx.x, bar, parity);
+        __trap();
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void prefetch_tmap(const void *tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void *tmap, uint32_t bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void *tmap, uint32_t bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// whole warp; writes the TMEM base address to smem_dst
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; one thread issues.
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   bar)
+               : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread i of the warp gets row (lane_base+i)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 64 x 16-bit (=128 B), 8-row atoms 1024 B apart.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
+//  | layout_type [61,64) with SWIZZLE_128B = 2.)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)0 << 16;                 // LBO unused for swizzled K-major
+  d |= (uint64_t)(1024 >> 4) << 32;       // SBO: 8 rows * 128 B
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16, fp32 accumulate, both operands K-major.
+__host__ __device__ inline uint32_t umma_idesc(int fmt /*0 f16, 1 bf16*/, int M, int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;                       // c_format = F32
+  d |= (uint32_t)fmt << 7;            // a_format
+  d |= (uint32_t)fmt << 10;           // b_format
+  d |= (uint32_t)(N >> 3) << 17;      // n_dim
+  d |= (uint32_t)(M >> 4) << 24;      // m_dim
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------
+// host: TMA descriptor encode through the runtime-resolved driver entry point
+// ------------------------------------------------------------------------------------------
+int encode_tmap(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
+                const uint64_t *strides_bytes /*rank-1*/, const uint32_t *box,
+                const uint32_t *elem_strides);
+
+}  // namespace b200

@@ -1,0 +1,443 @@
+// Small / HBM-bound kernels around the tensor-core path: API-edge layout conversion, weight repack,
+// the degenerate first (Cin<=8) and last (Cout<=4) convolutions, the timestep-embedding MLP,
+// nearest upsample, the DS-Diff skip mean and SE_Attention.  Reference call sites: see
+// include/b200diff.h next to each entry point.
+#include "common.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------
+// layout conversion (API edge)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float *__restrict__ src, T *__restrict__ dst, int N, int C,
+                                    int HW, int Cpad) {
+  const long long total = (long long)N * HW * Cpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cpad);
+    const long long np = i / Cpad;
+    const int p = (int)(np % HW);
+    const int n = (int)(np / HW);
+    dst[i] = c < C ? Act<T>::from_f(src[((long long)n * C + c) * HW + p]) : Act<T>::from_f(0.f);
+  }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T *__restrict__ src, float *__restrict__ dst, int N, int C,
+                                    int HW, int Csrc) {
+  const long long total = (long long)N * C * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % HW);
+    const long long nc = i / HW;
+    const int c = (int)(nc % C);
+    const int n = (int)(nc / C);
+    dst[i] = Act<T>::to_f(src[((long long)n * HW + p) * Csrc + c]);
+  }
+}
+
+template <typename T>
+__global__ void pack_weight_kernel(const float *__restrict__ w, T *__restrict__ dst, int Cout, int Cin,
+                                   int taps, int CinPad) {
+  const long long total = (long long)taps * Cout * CinPad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % CinPad);
+    const long long r = i / CinPad;
+    const int co = (int)(r % Cout);
+    const int tap = (int)(r / Cout);
+    dst[i] = ci < Cin ? Act<T>::from_f(w[((long long)co * Cin + ci) * taps + tap]) : Act<T>::from_f(0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// first conv: NCHW fp32 (Cin <= 8) -> NHWC act.  One thread per output pixel, weights in smem as
+// [Cin*9][Cout] so each 8-cout chunk is two broadcast LDS.128.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128)
+conv3x3_in_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
+                  T *__restrict__ out, int N, int Cin, int H, int W, int Cout) {
+  extern __shared__ float sw[];  // [Cin*9][Cout] then bias[Cout]
+  const int K = Cin * 9;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+    const int co = i % Cout, k = i / Cout;   // k = ci*9 + tap
+    sw[i] = w[(size_t)co * K + k];
+  }
+  float *sb = sw + K * Cout;
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const long long total = (long long)N * H * W;
+  const long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const int wq = (int)(pix % W);
+  const int hq = (int)((pix / W) % H);
+  const int n = (int)(pix / ((long long)W * H));
+  float in[72];
+#pragma unroll
+  for (int ci = 0; ci < 8; ++ci) {
+    if (ci < Cin) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int hh = hq + r - 1, ww = wq + s - 1;
+          in[ci * 9 + r * 3 + s] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
+                                       ? __ldg(x + (((size_t)n * Cin + ci) * H + hh) * W + ww)
+                                       : 0.f;
+        }
+    }
+  }
+  T *o = out + (size_t)pix * Cout;
+  for (int c0 = 0; c0 < Cout; c0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = sb[c0 + i];
+#pragma unroll
+    for (int ci = 0; ci < 8; ++ci) {
+      if (ci < Cin) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float v = in[ci * 9 + t];
+          const float4 w0 = *reinterpret_cast<const float4 *>(sw + (ci * 9 + t) * Cout + c0);
+          const float4 w1 = *reinterpret_cast<const float4 *>(sw + (ci * 9 + t) * Cout + c0 + 4);
+          acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
+          acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+          acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+          acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+        }
+      }
+    }
+    *reinterpret_cast<uint4 *>(o + c0) = pack8<T>(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// last conv: NHWC act (Cin multiple of 8) -> NCHW fp32, Cout <= 4.  One warp per output pixel
+// pair... kept simple: one thread per pixel, 16-byte channel vectors through L1, weights in smem.
+// ------------------------------------------------------------------------------------------
+template <typename T, int COUT>
+__global__ void __launch_bounds__(128)
+conv3x3_out_kernel(const T *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
+                   float *__restrict__ out, int N, int Cin, int H, int W) {
+  extern __shared__ float sw[];  // [9][Cin][COUT]
+  for (int i = threadIdx.x; i < 9 * Cin * COUT; i += blockDim.x) {
+    const int co = i % COUT;
+    const int ci = (i / COUT) % Cin;
+    const int tap = i / (COUT * Cin);
+    sw[i] = w[((size_t)co * Cin + ci) * 9 + tap];
+  }
+  __syncthreads();
+  const long long total = (long long)N * H * W;
+  const long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const int wq = (int)(pix % W);
+  const int hq = (int)((pix / W) % H);
+  const int n = (int)(pix / ((long long)W * H));
+  float acc[COUT];
+#pragma unroll
+  for (int i = 0; i < COUT; ++i) acc[i] = bias ? bias[i] : 0.f;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int hh = hq + tap / 3 - 1, ww = wq + tap % 3 - 1;
+    if (hh < 0 || hh >= H || ww < 0 || ww >= W) continue;
+    const T *px = x + (((size_t)n * H + hh) * W + ww) * Cin;
+    const float *wt = sw + (size_t)tap * Cin * COUT;
+    for (int c = 0; c < Cin; c += 8) {
+      float f[8];
+      unpack8<T>(__ldg(reinterpret_cast<const uint4 *>(px + c)), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] = fmaf(f[i], wt[(c + i) * COUT + co], acc[co]);
+    }
+  }
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) out[(((size_t)n * COUT + co) * H + hq) * W + wq] = acc[co];
+}
+
+// ------------------------------------------------------------------------------------------
+// timestep path (all fp32)
+// ------------------------------------------------------------------------------------------
+__global__ void timestep_embedding_kernel(const float *__restrict__ t_table, const int *__restrict__ step_ptr,
+                                          const float *__restrict__ freqs, float *__restrict__ out, int B,
+                                          int dim) {
+  const int half = dim / 2;
+  const int b = blockIdx.x;
+  const float t = step_ptr ? t_table[*step_ptr] : t_table[b];
+  for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+    float v = 0.f;
+    if (i < 2 * half) {
+      const int j = i < half ? i : i - half;
+      // freqs[j] = exp(-ln(max_period) * j / half) is built on the host with the reference's own fp32
+      // expression (util.py:171-173) so the angle t*freq is bit-identical; args = t * freqs (:174)
+      const float arg = __fmul_rn(t, freqs[j]);
+      v = i < half ? cosf(arg) : sinf(arg);
+    }
+    out[(size_t)b * dim + i] = v;
+  }
+}
+
+// out[b][o] = bias[o] + sum_k f(in[b][k]) W[o][k]; one warp per output row o, all (<= 8 per pass) b.
+template <int BT>
+__global__ void __launch_bounds__(256)
+linear_f32_kernel(const float *__restrict__ in, const float *__restrict__ W, const float *__restrict__ bias,
+                  float *__restrict__ out, int B, int K, int O, int in_silu, int out_silu) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= O) return;
+  const float *wr = W + (size_t)warp * K;
+  for (int b0 = 0; b0 < B; b0 += BT) {
+    float acc[BT];
+#pragma unroll
+    for (int j = 0; j < BT; ++j) acc[j] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float wv = __ldg(wr + k);
+#pragma unroll
+      for (int j = 0; j < BT; ++j) {
+        if (b0 + j < B) {
+          float v = in[(size_t)(b0 + j) * K + k];
+          if (in_silu) v = v / (1.f + expf(-v));
+          acc[j] = fmaf(v, wv, acc[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < BT; ++j) {
+      float a = acc[j];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+      if (lane == 0 && b0 + j < B) {
+        a += bias ? bias[warp] : 0.f;
+        if (out_silu) a = a / (1.f + expf(-a));
+        out[(size_t)(b0 + j) * O + warp] = a;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// elementwise helpers on 16-byte vectors
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void upsample2x_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int N, int H, int W,
+                                  int C8) {
+  const long long total = (long long)N * (2 * H) * (2 * W) * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    long long r = i / C8;
+    const int wo = (int)(r % (2 * W)); r /= 2 * W;
+    const int ho = (int)(r % (2 * H));
+    const int n = (int)(r / (2 * H));
+    dst[i] = __ldg(src + (((long long)n * H + (ho >> 1)) * W + (wo >> 1)) * C8 + c);
+  }
+}
+
+template <typename T>
+__global__ void add4_scale_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b,
+                                  const uint4 *__restrict__ c, const uint4 *__restrict__ d, float scale,
+                                  uint4 *__restrict__ dst, long long nvec, int silu) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    float f[8], g[8];
+    unpack8<T>(ld_stream(a + i), f);
+    if (b) { unpack8<T>(ld_stream(b + i), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += g[j]; }
+    if (c) { unpack8<T>(ld_stream(c + i), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += g[j]; }
+    if (d) { unpack8<T>(ld_stream(d + i), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += g[j]; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] *= scale;
+      if (silu) f[j] = silu_f(f[j]);
+    }
+    dst[i] = pack8<T>(f);
+  }
+}
+
+// SE_Attention: pooled[n][c] = mean_p x; y = sigmoid(W2 relu(W1 pooled)); out = x * y.
+template <typename T>
+__global__ void se_pool_kernel(const T *__restrict__ x, float *__restrict__ pooled, int HW, int C) {
+  const int n = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int p = 0; p < HW; ++p) s += Act<T>::to_f(x[((size_t)n * HW + p) * C + c]);
+  pooled[(size_t)n * C + c] = s / (float)HW;
+}
+__global__ void se_fc_kernel(const float *__restrict__ pooled, const float *__restrict__ w1,
+                             const float *__restrict__ w2, float *__restrict__ gate, int C, int Cr) {
+  extern __shared__ float hid[];  // [Cr]
+  const int n = blockIdx.x;
+  for (int j = threadIdx.x; j < Cr; j += blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(pooled[(size_t)n * C + c], w1[(size_t)j * C + c], s);
+    hid[j] = fmaxf(s, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int j = 0; j < Cr; ++j) s = fmaf(hid[j], w2[(size_t)c * Cr + j], s);
+    gate[(size_t)n * C + c] = 1.f / (1.f + expf(-s));
+  }
+}
+template <typename T>
+__global__ void se_scale_kernel(const T *__restrict__ x, const float *__restrict__ gate, T *__restrict__ out,
+                                int HW, int C, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int n = (int)(i / ((long long)HW * C));
+    out[i] = Act<T>::from_f(Act<T>::to_f(x[i]) * gate[(size_t)n * C + c]);
+  }
+}
+
+static int ew_blocks(long long n, int threads) {
+  return (int)std::min<long long>(cdiv64(n, threads), (long long)num_sms() * 16);
+}
+
+}  // namespace b200
+
+using namespace b200;
+#define DISPATCH_ACT(dt, ...)                                         \
+  if ((dt) == B200_F16) { using T = __half; __VA_ARGS__ }             \
+  else if ((dt) == B200_BF16) { using T = __nv_bfloat16; __VA_ARGS__ } \
+  else { B200_CHECK(false, "bad act_dtype %d", (dt)); }
+
+extern "C" int b200_nchw_f32_to_nhwc(const float *src, void *dst, int N, int C, int H, int W, int Cpad,
+                                     int act_dtype, void *stream) {
+  B200_CHECK(src && dst && N > 0 && C > 0 && Cpad >= C, "nchw_to_nhwc: bad arguments");
+  const long long total = (long long)N * H * W * Cpad;
+  DISPATCH_ACT(act_dtype, nchw_to_nhwc_kernel<T><<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                              src, (T *)dst, N, C, H * W, Cpad);)
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int b200_nhwc_to_nchw_f32(const void *src, float *dst, int N, int C, int H, int W, int Csrc,
+                                     int act_dtype, void *stream) {
+  B200_CHECK(src && dst && N > 0 && C > 0 && Csrc >= C, "nhwc_to_nchw: bad arguments");
+  const long long total = (long long)N * H * W * C;
+  DISPATCH_ACT(act_dtype, nhwc_to_nchw_kernel<T><<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                              (const T *)src, dst, N, C, H * W, Csrc);)
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int b200_pack_conv_weight(const float *w, void *dst, int Cout, int Cin, int KH, int KW, int CinPad,
+                                     int act_dtype, void *stream) {
+  B200_CHECK(w && dst && Cout > 0 && Cin > 0 && CinPad >= Cin && CinPad % 8 == 0, "pack_conv_weight: bad arguments");
+  const long long total = (long long)KH * KW * Cout * CinPad;
+  DISPATCH_ACT(act_dtype, pack_weight_kernel<T><<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                              w, (T *)dst, Cout, Cin, KH * KW, CinPad);)
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_conv3x3_in(const float *x, const float *w, const float *bias, void *out, int N, int Cin,
+                               int H, int W, int Cout, int act_dtype, void *stream) {
+  B200_CHECK(x && w && out, "conv3x3_in: null pointer");
+  B200_CHECK(Cin >= 1 && Cin <= 8, "conv3x3_in: Cin must be 1..8 (got %d)", Cin);
+  B200_CHECK(Cout % 8 == 0 && Cout > 0, "conv3x3_in: Cout must be a multiple of 8");
+  const size_t smem = ((size_t)Cin * 9 * Cout + Cout) * sizeof(float);
+  B200_CHECK(smem <= 200 * 1024, "conv3x3_in: weights do not fit shared memory");
+  const long long total = (long long)N * H * W;
+  DISPATCH_ACT(act_dtype, {
+    if (smem > 48 * 1024)
+      B200_CUDA(cudaFuncSetAttribute(conv3x3_in_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3x3_in_kernel<T><<<(unsigned)cdiv64(total, 128), 128, smem, (cudaStream_t)stream>>>(
+        x, w, bias, (T *)out, N, Cin, H, W, Cout);
+  })
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+static int launch_conv_out(const void *x, const float *w, const float *bias, float *out, int N, int Cin, int H,
+                           int W, int Cout, cudaStream_t st) {
+  const size_t smem = (size_t)9 * Cin * Cout * sizeof(float);
+  B200_CHECK(smem <= 200 * 1024, "conv3x3_out: weights do not fit shared memory");
+  const unsigned blocks = (unsigned)cdiv64((long long)N * H * W, 128);
+#define LAUNCH_OUT(CO)                                                                                     \
+  {                                                                                                        \
+    if (smem > 48 * 1024)                                                                                  \
+      B200_CUDA(cudaFuncSetAttribute(conv3x3_out_kernel<T, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)smem));                                                          \
+    conv3x3_out_kernel<T, CO><<<blocks, 128, smem, st>>>((const T *)x, w, bias, out, N, Cin, H, W);        \
+  }
+  switch (Cout) {
+    case 1: LAUNCH_OUT(1) break;
+    case 2: LAUNCH_OUT(2) break;
+    case 3: LAUNCH_OUT(3) break;
+    case 4: LAUNCH_OUT(4) break;
+    default: B200_CHECK(false, "conv3x3_out: Cout must be 1..4 (got %d)", Cout);
+  }
+#undef LAUNCH_OUT
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int b200_conv3x3_out(const void *x, const float *w, const float *bias, float *out, int N, int Cin,
+                                int H, int W, int Cout, int act_dtype, void *stream) {
+  B200_CHECK(x && w && out, "conv3x3_out: null pointer");
+  B200_CHECK(Cin % 8 == 0 && Cin > 0, "conv3x3_out: Cin must be a multiple of 8");
+  if (act_dtype == B200_F16) return launch_conv_out<__half>(x, w, bias, out, N, Cin, H, W, Cout, (cudaStream_t)stream);
+  if (act_dtype == B200_BF16) return launch_conv_out<__nv_bfloat16>(x, w, bias, out, N, Cin, H, W, Cout, (cudaStream_t)stream);
+  B200_CHECK(false, "conv3x3_out: bad act_dtype");
+}
+
+extern "C" int b200_timestep_embedding(const float *t_table, const int *step_ptr, const float *freqs, float *out,
+                                       int B, int dim, void *stream) {
+  B200_CHECK(t_table && freqs && out && B > 0 && dim > 0, "timestep_embedding: bad arguments");
+  timestep_embedding_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(t_table, step_ptr, freqs, out, B, dim);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int b200_linear_f32(const float *in, const float *W, const float *bias, float *out, int B, int K,
+                               int O, int in_silu, int out_silu, void *stream) {
+  B200_CHECK(in && W && out && B > 0 && K > 0 && O > 0, "linear_f32: bad arguments");
+  const int warps_per_block = 8;
+  linear_f32_kernel<8><<<cdiv(O, warps_per_block), 256, 0, (cudaStream_t)stream>>>(in, W, bias, out, B, K, O,
+                                                                                   in_silu, out_silu);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_upsample_nearest2x(const void *src, void *dst, int N, int H, int W, int C, int act_dtype,
+                                       void *stream) {
+  B200_CHECK(src && dst && C % 8 == 0, "upsample: C must be a multiple of 8");
+  const long long total = (long long)N * 4 * H * W * (C / 8);
+  DISPATCH_ACT(act_dtype, upsample2x_kernel<T><<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                              (const uint4 *)src, (uint4 *)dst, N, H, W, C / 8);)
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int b200_add4_scale(const void *a, const void *b, const void *c, const void *d, float scale, void *dst,
+                               int64_t n, int silu, int act_dtype, void *stream) {
+  B200_CHECK(a && dst && n > 0 && n % 8 == 0, "add4_scale: element count must be a multiple of 8");
+  const long long nvec = n / 8;
+  DISPATCH_ACT(act_dtype, add4_scale_kernel<T><<<ew_blocks(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
+                              (const uint4 *)a, (const uint4 *)b, (const uint4 *)c, (const uint4 *)d, scale,
+                              (uint4 *)dst, nvec, silu);)
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int b200_se_attention(const void *x, const float *w1, const float *w2, void *out, float *scratch, int N,
+                                 int HW, int C, int Cr, int act_dtype, void *stream) {
+  B200_CHECK(x && w1 && w2 && out && scratch, "se_attention: null pointer");
+  B200_CHECK(Cr > 0 && Cr * sizeof(float) <= 48 * 1024, "se_attention: bad reduction width");
+  float *pooled = scratch;            // [N][C]
+  float *gate = scratch + (size_t)N * C;  // [N][C]
+  const long long total = (long long)N * HW * C;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_ACT(act_dtype, {
+    se_pool_kernel<T><<<dim3(cdiv(C, 128), N), 128, 0, st>>>((const T *)x, pooled, HW, C);
+    B200_LAUNCH_CHECK();
+    se_fc_kernel<<<N, 256, Cr * sizeof(float), st>>>(pooled, w1, w2, gate, C, Cr);
+    B200_LAUNCH_CHECK();
+    se_scale_kernel<T><<<ew_blocks(total, 256), 256, 0, st>>>((const T *)x, gate, (T *)out, HW, C, total);
+  })
+  B200_LAUNCH_CHECK();
+  return 0;
+}

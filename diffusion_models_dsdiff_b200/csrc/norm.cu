@@ -1,0 +1,231 @@
+// GroupNorm statistics + fused GroupNorm(+FiLM)(+SiLU) apply over NHWC 16-bit activations.
+// HBM-bound: every access is a coalesced 16-byte vector; reductions are warp shuffles + shared
+// fp64 atomics (one global fp64 atomic pair per (block, group)).
+//
+// Replaces GroupNorm32 -> SiLU (ldm/modules/diffusionmodules/util.py:209-226; openaimodel.py:
+// 205-209, 229-236, 898-902), the FiLM form (openaimodel.py:276-280) and Normalize
+// (ldm/modules/attention.py:88-89).  The input may be the channel concatenation [x0 | x1]
+// (th.cat([h, hs.pop()], 1), openaimodel.py:952) which is never materialised un-normalised.
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kNormThreads = 256;
+constexpr int kMaxGroups = 64;
+
+// Each thread owns one 8-channel column of one source and walks pixels with a fixed stride, so
+// per-channel partial sums stay in registers.
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+gn_stats_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int C1, int HW,
+                int groups, int pix_per_block, double *__restrict__ stats) {
+  __shared__ double s_sum[kMaxGroups], s_sq[kMaxGroups];
+  const int n = blockIdx.y;
+  const int C = C0 + C1;
+  const int cpg = C / groups;
+  for (int i = threadIdx.x; i < groups; i += blockDim.x) { s_sum[i] = 0.0; s_sq[i] = 0.0; }
+  __syncthreads();
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(HW, p_begin + pix_per_block);
+  for (int src = 0; src < 2; ++src) {
+    const T *x = src == 0 ? x0 : x1;
+    const int Cs = src == 0 ? C0 : C1;
+    const int cbase = src == 0 ? 0 : C0;
+    if (Cs == 0) continue;
+    const int ncol = Cs >> 3;
+    const int rows = kNormThreads / ncol;   // pixels per sweep
+    const int col = threadIdx.x % ncol;
+    const int row = threadIdx.x / ncol;
+    if (row < rows) {
+      float s[8] = {0}, q[8] = {0};
+      const T *base = x + (size_t)n * HW * Cs + col * 8;
+      int p = p_begin + row;
+      // 4 independent 16-byte loads in flight per thread
+      for (; p + 3 * rows < p_end; p += 4 * rows) {
+        uint4 u[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) u[j] = ld_stream(base + (size_t)(p + j * rows) * Cs);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float f[8];
+          unpack8<T>(u[j], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+        }
+      }
+      for (; p < p_end; p += rows) {
+        float f[8];
+        unpack8<T>(ld_stream(base + (size_t)p * Cs), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+      }
+      // fold the 8 channels into (at most a few) groups before touching shared memory
+      int g_cur = (cbase + col * 8) / cpg;
+      float gs = 0.f, gq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int g = (cbase + col * 8 + i) / cpg;
+        if (g != g_cur) {
+          atomicAdd(&s_sum[g_cur], (double)gs);
+          atomicAdd(&s_sq[g_cur], (double)gq);
+          g_cur = g; gs = 0.f; gq = 0.f;
+        }
+        gs += s[i]; gq += q[i];
+      }
+      atomicAdd(&s_sum[g_cur], (double)gs);
+      atomicAdd(&s_sq[g_cur], (double)gq);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups; i += blockDim.x) {
+    atomicAdd(&stats[((size_t)n * groups + i) * 2 + 0], s_sum[i]);
+    atomicAdd(&stats[((size_t)n * groups + i) * 2 + 1], s_sq[i]);
+  }
+}
+
+// y = silu?( (x - mean_g) * rstd_g * gamma_c + beta_c ) [ * (1 + scale_nc) + shift_nc ]
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int C1, int HW,
+                int groups, float eps, int pix_per_block, const double *__restrict__ stats,
+                const float *__restrict__ gamma, const float *__restrict__ beta,
+                const float *__restrict__ film, int film_stride, int silu, T *__restrict__ out) {
+  __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
+  const int n = blockIdx.y;
+  const int C = C0 + C1;
+  const int cpg = C / groups;
+  const double cnt = (double)HW * (double)cpg;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    const double m = stats[((size_t)n * groups + g) * 2 + 0] / cnt;
+    double var = stats[((size_t)n * groups + g) * 2 + 1] / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = (float)m;
+    s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int ncol = C >> 3;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(HW, p_begin + pix_per_block);
+  const int rows = kNormThreads / ncol;   // ncol <= 256 (checked on the host)
+  const int col = threadIdx.x % ncol;
+  const int row = threadIdx.x / ncol;
+  if (row < rows) {
+    const int c = col * 8;
+    float a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (c + i) / cpg;
+      const float ga = gamma[c + i] * s_rstd[g];
+      float aa = ga;
+      float bb = beta[c + i] - s_mean[g] * ga;
+      if (film) {
+        const float sc = 1.f + film[(size_t)n * film_stride + c + i];
+        const float sh = film[(size_t)n * film_stride + C + c + i];
+        aa *= sc;
+        bb = bb * sc + sh;
+      }
+      a[i] = aa; b[i] = bb;
+    }
+    const bool from0 = c < C0;
+    const T *src = from0 ? x0 + (size_t)n * HW * C0 + c : x1 + (size_t)n * HW * C1 + (c - C0);
+    const int Cs = from0 ? C0 : C1;
+    T *dst = out + (size_t)n * HW * C + c;
+    int p = p_begin + row;
+    for (; p + 3 * rows < p_end; p += 4 * rows) {
+      uint4 u[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) u[j] = ld_stream(src + (size_t)(p + j * rows) * Cs);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float f[8];
+        unpack8<T>(u[j], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float v = fmaf(f[i], a[i], b[i]);
+          f[i] = silu ? silu_f(v) : v;
+        }
+        *reinterpret_cast<uint4 *>(dst + (size_t)(p + j * rows) * C) = pack8<T>(f);
+      }
+    }
+    for (; p < p_end; p += rows) {
+      float f[8];
+      unpack8<T>(ld_stream(src + (size_t)p * Cs), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = fmaf(f[i], a[i], b[i]);
+        f[i] = silu ? silu_f(v) : v;
+      }
+      *reinterpret_cast<uint4 *>(dst + (size_t)p * C) = pack8<T>(f);
+    }
+  }
+}
+
+static void norm_grid(int N, int HW, int ncol, dim3 *grid, int *pix_per_block) {
+  const int rows = std::max(1, kNormThreads / std::max(ncol, 1));
+  int target_blocks = std::max(1, (num_sms() * 8) / std::max(N, 1));
+  // at least 4 sweeps of `rows` pixels per block so the unrolled loop body is used
+  int max_blocks = std::max(1, HW / (rows * 4));
+  int bps = std::min(target_blocks, max_blocks);
+  *pix_per_block = cdiv(HW, bps);
+  *grid = dim3(cdiv(HW, *pix_per_block), N, 1);
+}
+
+template <typename T>
+static int gn_stats(const void *x0, int C0, const void *x1, int C1, int N, int HW, int groups,
+                    double *stats, cudaStream_t st) {
+  dim3 grid;
+  int ppb;
+  norm_grid(N, HW, std::max(C0, C1) >> 3, &grid, &ppb);
+  gn_stats_kernel<T><<<grid, kNormThreads, 0, st>>>((const T *)x0, C0, (const T *)x1, C1, HW, groups,
+                                                   ppb, stats);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+template <typename T>
+static int gn_apply(const void *x0, int C0, const void *x1, int C1, int N, int HW, int groups,
+                    float eps, const double *stats, const float *gamma, const float *beta,
+                    const float *film, int film_stride, int silu, void *out, cudaStream_t st) {
+  dim3 grid;
+  int ppb;
+  norm_grid(N, HW, (C0 + C1) >> 3, &grid, &ppb);
+  gn_apply_kernel<T><<<grid, kNormThreads, 0, st>>>((const T *)x0, C0, (const T *)x1, C1, HW, groups,
+                                                   eps, ppb, stats, gamma, beta, film, film_stride,
+                                                   silu, (T *)out);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+static int check_gn(int C0, int C1, int N, int HW, int groups) {
+  B200_CHECK(C0 > 0 && C0 % 8 == 0 && C1 % 8 == 0 && C1 >= 0, "groupnorm: channels must be multiples of 8");
+  B200_CHECK(groups > 0 && groups <= kMaxGroups && (C0 + C1) % groups == 0, "groupnorm: bad group count");
+  B200_CHECK(N > 0 && HW > 0, "groupnorm: empty tensor");
+  B200_CHECK(C0 + C1 <= 8 * kNormThreads, "groupnorm: at most %d channels", 8 * kNormThreads);
+  return 0;
+}
+
+}  // namespace b200
+
+extern "C" int b200_groupnorm_stats(const void *x0, int C0, const void *x1, int C1, int N, int HW,
+                                    int groups, double *stats, int act_dtype, void *stream) {
+  using namespace b200;
+  if (x1 == nullptr) C1 = 0;
+  if (int rc = check_gn(C0, C1, N, HW, groups)) return rc;
+  if (act_dtype == B200_F16) return gn_stats<__half>(x0, C0, x1, C1, N, HW, groups, stats, (cudaStream_t)stream);
+  if (act_dtype == B200_BF16) return gn_stats<__nv_bfloat16>(x0, C0, x1, C1, N, HW, groups, stats, (cudaStream_t)stream);
+  B200_CHECK(false, "groupnorm: bad act_dtype");
+}
+
+extern "C" int b200_groupnorm_apply(const void *x0, int C0, const void *x1, int C1, int N, int HW,
+                                    int groups, float eps, const double *stats, const float *gamma,
+                                    const float *beta, const float *film, int film_stride, int silu,
+                                    void *out, int act_dtype, void *stream) {
+  using namespace b200;
+  if (x1 == nullptr) C1 = 0;
+  if (int rc = check_gn(C0, C1, N, HW, groups)) return rc;
+  if (act_dtype == B200_F16)
+    return gn_apply<__half>(x0, C0, x1, C1, N, HW, groups, eps, stats, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream);
+  if (act_dtype == B200_BF16)
+    return gn_apply<__nv_bfloat16>(x0, C0, x1, C1, N, HW, groups, eps, stats, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream);
+  B200_CHECK(false, "groupnorm: bad act_dtype");
+}

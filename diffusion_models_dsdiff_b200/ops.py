@@ -1,0 +1,273 @@
+"""Tensor-level wrappers over the C ABI (include/b200diff.h).
+
+torch is used for device memory and streams only; every arithmetic op below is a kernel of
+libb200diff.so launched on torch's current stream.  Internal activations are NHWC 16-bit tensors
+(``[N, H, W, C]``, ``torch.float16`` by default or ``torch.bfloat16``); the API edge is NCHW fp32
+like the reference.  Nothing here has a CPU or eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+Tensor = torch.Tensor
+
+
+def act_code(dtype: torch.dtype) -> int:
+    if dtype == torch.float16:
+        return L.F16
+    if dtype == torch.bfloat16:
+        return L.BF16
+    raise L.B200Error(f"activation dtype must be float16 or bfloat16, got {dtype}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t: Tensor) -> None:
+    if not t.is_cuda:
+        raise L.B200Error("libb200diff has no CPU path: tensor is not on a CUDA device")
+    L.ensure_init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _p(t: Optional[Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_contiguous():
+        raise L.B200Error("tensor must be contiguous")
+    return t.data_ptr()
+
+
+def _f32(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is not None and t.dtype != torch.float32:
+        raise L.B200Error(f"expected float32, got {t.dtype}")
+    return t
+
+
+# ---------------------------------------------------------------------------------------------
+# layout / weights
+# ---------------------------------------------------------------------------------------------
+def nchw_to_nhwc(x: Tensor, cpad: Optional[int] = None, dtype=torch.float16) -> Tensor:
+    _dev(x)
+    n, c, h, w = x.shape
+    cpad = cpad or ((c + 7) // 8) * 8
+    out = torch.empty((n, h, w, cpad), device=x.device, dtype=dtype)
+    L.check(L.lib().b200_nchw_f32_to_nhwc(_p(_f32(x.contiguous())), _p(out), n, c, h, w, cpad, act_code(dtype),
+                                          _stream()), "nchw_f32_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x: Tensor, c: Optional[int] = None) -> Tensor:
+    _dev(x)
+    n, h, w, cs = x.shape
+    c = c or cs
+    out = torch.empty((n, c, h, w), device=x.device, dtype=torch.float32)
+    L.check(L.lib().b200_nhwc_to_nchw_f32(_p(x), _p(out), n, c, h, w, cs, act_code(x.dtype), _stream()),
+            "nhwc_to_nchw_f32")
+    return out
+
+
+def pack_conv_weight(w_oihw: Tensor, dtype=torch.float16, cin_pad: Optional[int] = None) -> Tensor:
+    """OIHW fp32 -> [KH*KW, Cout, CinPad] 16-bit (K-major rows for the tcgen05 B operand)."""
+    _dev(w_oihw)
+    if w_oihw.dim() == 3:      # Conv1d k=1 weights [O, I, 1]
+        w_oihw = w_oihw[..., None]
+    if w_oihw.dim() == 2:      # Linear weights [O, I]
+        w_oihw = w_oihw[..., None, None]
+    co, ci, kh, kw = w_oihw.shape
+    cin_pad = cin_pad or ((ci + 7) // 8) * 8
+    out = torch.empty((kh * kw, co, cin_pad), device=w_oihw.device, dtype=dtype)
+    L.check(L.lib().b200_pack_conv_weight(_p(_f32(w_oihw.contiguous())), _p(out), co, ci, kh, kw, cin_pad,
+                                          act_code(dtype), _stream()), "pack_conv_weight")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# convolutions
+# ---------------------------------------------------------------------------------------------
+Seg = Tuple[Tensor, Tensor, int, int, int]  # (src NHWC, packed weight, coff, ksize, pad)
+
+
+def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
+           rowbias: Optional[Tensor] = None, residual: Optional[Tensor] = None, res_scale: float = 1.0,
+           out: Optional[Tensor] = None) -> Tensor:
+    """tcgen05 implicit-GEMM conv over up to 3 K-segments (see b200_conv2d_igemm)."""
+    src0, w0, _, k0, p0 = segs[0]
+    _dev(src0)
+    n, hin, win, _ = src0.shape
+    cout = w0.shape[1]
+    hout = (hin + 2 * p0 - k0) // stride + 1
+    wout = (win + 2 * p0 - k0) // stride + 1
+    d = L.ConvDesc()
+    d.N, d.Hin, d.Win, d.Hout, d.Wout, d.Cout, d.stride, d.nseg = n, hin, win, hout, wout, cout, stride, len(segs)
+    for i, (src, wt, coff, ks, pad) in enumerate(segs):
+        if src.shape[:3] != src0.shape[:3] or src.dtype != src0.dtype or wt.dtype != src0.dtype:
+            raise L.B200Error("conv2d: segments must share N,H,W and dtype")
+        if (hin + 2 * pad - ks) // stride + 1 != hout or wt.shape[1] != cout or wt.shape[0] != ks * ks:
+            raise L.B200Error("conv2d: segment geometry mismatch")
+        s = d.seg[i]
+        s.src, s.weight, s.cin, s.wcin, s.coff, s.ksize, s.pad = _p(src), _p(wt), src.shape[3], wt.shape[2], coff, ks, pad
+    if out is None:
+        out = torch.empty((n, hout, wout, cout), device=src0.device, dtype=src0.dtype)
+    d.bias = _p(_f32(bias))
+    d.rowbias, d.rowbias_stride = None, 0
+    if rowbias is not None:       # may be a column slice of the batched emb projection
+        if _f32(rowbias).stride(-1) != 1 or rowbias.shape != (n, cout) or rowbias.data_ptr() % 16:
+            raise L.B200Error("conv2d: rowbias must be [N, Cout] fp32 with dense, 16B-aligned rows")
+        d.rowbias, d.rowbias_stride = rowbias.data_ptr(), rowbias.stride(0)
+    if residual is not None and (residual.shape != out.shape or residual.dtype != out.dtype):
+        raise L.B200Error("conv2d: residual shape/dtype mismatch")
+    d.residual = _p(residual)
+    d.res_scale = res_scale
+    d.out = _p(out)
+    d.gn_sums = None
+    d.act_dtype = act_code(src0.dtype)
+    L.check(L.lib().b200_conv2d_igemm(C.byref(d), _stream()), "conv2d_igemm")
+    return out
+
+
+def conv3x3_in(x_nchw: Tensor, w_oihw: Tensor, bias: Optional[Tensor], dtype=torch.float16) -> Tensor:
+    _dev(x_nchw)
+    n, ci, h, w = x_nchw.shape
+    co = w_oihw.shape[0]
+    out = torch.empty((n, h, w, co), device=x_nchw.device, dtype=dtype)
+    L.check(L.lib().b200_conv3x3_in(_p(_f32(x_nchw)), _p(_f32(w_oihw)), _p(_f32(bias)), _p(out), n, ci, h, w, co,
+                                    act_code(dtype), _stream()), "conv3x3_in")
+    return out
+
+
+def conv3x3_out(x: Tensor, w_oihw: Tensor, bias: Optional[Tensor]) -> Tensor:
+    _dev(x)
+    n, h, w, ci = x.shape
+    co = w_oihw.shape[0]
+    out = torch.empty((n, co, h, w), device=x.device, dtype=torch.float32)
+    L.check(L.lib().b200_conv3x3_out(_p(x), _p(_f32(w_oihw)), _p(_f32(bias)), _p(out), n, ci, h, w, co,
+                                     act_code(x.dtype), _stream()), "conv3x3_out")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# normalisation
+# ---------------------------------------------------------------------------------------------
+def group_norm(x0: Tensor, gamma: Tensor, beta: Tensor, x1: Optional[Tensor] = None, groups: int = 32,
+               eps: float = 1e-5, silu: bool = True, film: Optional[Tensor] = None,
+               stats: Optional[Tensor] = None) -> Tensor:
+    """GroupNorm(+FiLM)(+SiLU) of the channel concatenation [x0 | x1]; NHWC in, NHWC out.
+
+    ``stats`` is an optional pre-zeroed fp64 workspace [N, groups, 2]."""
+    _dev(x0)
+    n = x0.shape[0]
+    hw = x0.numel() // (n * x0.shape[-1])
+    c0 = x0.shape[-1]
+    c1 = x1.shape[-1] if x1 is not None else 0
+    if stats is None:
+        stats = torch.zeros((n, groups, 2), device=x0.device, dtype=torch.float64)
+    code = act_code(x0.dtype)
+    lib = L.lib()
+    L.check(lib.b200_groupnorm_stats(_p(x0), c0, _p(x1), c1, n, hw, groups, _p(stats), code, _stream()),
+            "groupnorm_stats")
+    out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=x0.dtype)
+    L.check(lib.b200_groupnorm_apply(_p(x0), c0, _p(x1), c1, n, hw, groups, eps, _p(stats), _p(_f32(gamma)),
+                                     _p(_f32(beta)), None if film is None else film.data_ptr(),
+                                     0 if film is None else film.stride(0), int(silu), _p(out), code, _stream()),
+            "groupnorm_apply")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# attention / timestep path / elementwise
+# ---------------------------------------------------------------------------------------------
+def attention_qkv(qkv: Tensor, heads: int, new_order: bool) -> Tensor:
+    """qkv: [B, L, 3*heads*ch] -> [B, L, heads*ch];  softmax((q*s)(k*s)) v with s = ch^-1/4."""
+    _dev(qkv)
+    b, l, c3 = qkv.shape
+    ch = c3 // (3 * heads)
+    out = torch.empty((b, l, heads * ch), device=qkv.device, dtype=qkv.dtype)
+    L.check(L.lib().b200_attention_qkv(_p(qkv), _p(out), b, l, heads, ch, int(new_order), float(ch) ** -0.5,
+                                       act_code(qkv.dtype), _stream()), "attention_qkv")
+    return out
+
+
+def timestep_embedding(t_table: Tensor, freqs: Tensor, batch: int, dim: int,
+                       step_ptr: Optional[Tensor] = None) -> Tensor:
+    _dev(t_table)
+    out = torch.empty((batch, dim), device=t_table.device, dtype=torch.float32)
+    L.check(L.lib().b200_timestep_embedding(_p(_f32(t_table)), _p(step_ptr), _p(_f32(freqs)), _p(out), batch, dim,
+                                            _stream()), "timestep_embedding")
+    return out
+
+
+def linear_f32(x: Tensor, w: Tensor, bias: Optional[Tensor], in_silu: bool = False, out_silu: bool = False) -> Tensor:
+    _dev(x)
+    b, k = x.shape
+    o = w.shape[0]
+    out = torch.empty((b, o), device=x.device, dtype=torch.float32)
+    L.check(L.lib().b200_linear_f32(_p(_f32(x)), _p(_f32(w)), _p(_f32(bias)), _p(out), b, k, o, int(in_silu),
+                                    int(out_silu), _stream()), "linear_f32")
+    return out
+
+
+def upsample_nearest2x(x: Tensor) -> Tensor:
+    _dev(x)
+    n, h, w, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=x.dtype)
+    L.check(L.lib().b200_upsample_nearest2x(_p(x), _p(out), n, h, w, c, act_code(x.dtype), _stream()), "upsample")
+    return out
+
+
+def add4_scale(a: Tensor, b: Optional[Tensor] = None, c: Optional[Tensor] = None, d: Optional[Tensor] = None,
+               scale: float = 1.0, silu: bool = False) -> Tensor:
+    _dev(a)
+    out = torch.empty_like(a)
+    L.check(L.lib().b200_add4_scale(_p(a), _p(b), _p(c), _p(d), scale, _p(out), a.numel(), int(silu),
+                                    act_code(a.dtype), _stream()), "add4_scale")
+    return out
+
+
+def se_attention(x: Tensor, w1: Tensor, w2: Tensor) -> Tensor:
+    _dev(x)
+    n, h, w, c = x.shape
+    cr = w1.shape[0]
+    scratch = torch.empty((2, n, c), device=x.device, dtype=torch.float32)
+    out = torch.empty_like(x)
+    L.check(L.lib().b200_se_attention(_p(x), _p(_f32(w1)), _p(_f32(w2)), _p(out), _p(scratch), n, h * w, c, cr,
+                                      act_code(x.dtype), _stream()), "se_attention")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# sampler update
+# ---------------------------------------------------------------------------------------------
+def sampler_update(mode: int, param: int, x: Tensor, model_out: Tensor, noise: Optional[Tensor], coef: Tensor,
+                   step: int = 0, step_ptr: Optional[Tensor] = None, clip_denoised: bool = True,
+                   learned_range: bool = False, want_x0: bool = True, x_prev: Optional[Tensor] = None,
+                   pred_x0: Optional[Tensor] = None):
+    _dev(x)
+    n, c = x.shape[0], x.shape[1]
+    hw = x.numel() // (n * c)
+    mc = model_out.shape[1]
+    if mc != (2 * c if learned_range else c):
+        raise L.B200Error(f"sampler_update: model_out has {mc} channels, expected {2 * c if learned_range else c}")
+    if x_prev is None:
+        x_prev = torch.empty_like(x)
+    if pred_x0 is None and want_x0:
+        pred_x0 = torch.empty_like(x)
+    d = L.SamplerDesc()
+    d.mode, d.param, d.clip_denoised, d.learned_range = mode, param, int(clip_denoised), int(learned_range)
+    d.N, d.C, d.HW = n, c, hw
+    d.x, d.model_out, d.noise, d.coef = _p(_f32(x)), _p(_f32(model_out)), _p(_f32(noise)), _p(_f32(coef))
+    d.step_ptr = _p(step_ptr)
+    d.step_host = step
+    d.x_prev, d.pred_x0 = _p(x_prev), _p(pred_x0)
+    L.check(L.lib().b200_sampler_update(C.byref(d), _stream()), "sampler_update")
+    return x_prev, pred_x0
+
+
+def advance_step(step_ptr: Tensor, delta: int = 1) -> None:
+    _dev(step_ptr)
+    L.check(L.lib().b200_advance_step(_p(step_ptr), delta, _stream()), "advance_step")

@@ -1,0 +1,400 @@
+"""Drop-in ``UNetModel`` (ldm/modules/diffusionmodules/openaimodel.py:571-958) on libb200diff.
+
+Same constructor keywords, same ``forward(x, timesteps=None, context=None, y=None)`` and the same
+``state_dict`` keys / shapes / dtypes (OIHW fp32) as the reference, so reference checkpoints load
+with ``load_state_dict(strict=True)``.  The ``torch.nn`` modules below are PARAMETER CONTAINERS
+only — their ``forward`` is never called.  The compute path is the engine in this file, which walks
+the block structure and launches the hand-written sm_100a kernels through ``ops`` (C ABI):
+
+* activations NHWC 16-bit (fp16 default, bf16 optional), fp32 accumulate / statistics;
+* GroupNorm+SiLU(+FiLM) is one fused pass that also absorbs ``th.cat([h, hs.pop()], 1)``
+  (openaimodel.py:952) by reading two sources;
+* each ResBlock is 2 GN passes + 2 implicit-GEMM launches: the timestep-embedding add
+  (openaimodel.py:282) rides in conv1's epilogue; the 1x1 skip convolution (:245), its bias and the
+  residual add (:284) are extra K-segments / epilogue terms of conv2;
+* all per-ResBlock ``emb_layers`` Linear(SiLU(emb)) (:221-228) run as ONE batched fp32 GEMV.
+
+There is no eager / CPU fallback: calling ``forward`` on a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import B200Error
+
+Tensor = torch.Tensor
+
+
+def default_act_dtype() -> torch.dtype:
+    v = os.environ.get("B200DIFF_ACT_DTYPE", "f16").lower()
+    return torch.bfloat16 if v in ("bf16", "bfloat16") else torch.float16
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter containers (names mirror the reference modules so state_dict keys are identical)
+# ---------------------------------------------------------------------------------------------
+def _gn(ch: int, eps: float = 1e-5) -> nn.GroupNorm:
+    return nn.GroupNorm(32, ch, eps=eps)          # GroupNorm32(32, C), util.py:209-215
+
+
+class ResBlock(nn.Module):
+    """Parameters of openaimodel.ResBlock (:167-262)."""
+
+    def __init__(self, channels, emb_channels, dropout, out_channels=None, use_conv=False,
+                 use_scale_shift_norm=False, up=False, down=False):
+        super().__init__()
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.use_scale_shift_norm = use_scale_shift_norm
+        self.up, self.down = up, down
+        self.in_layers = nn.Sequential(_gn(channels), nn.SiLU(), nn.Conv2d(channels, self.out_channels, 3, padding=1))
+        self.emb_layers = nn.Sequential(
+            nn.SiLU(), nn.Linear(emb_channels, 2 * self.out_channels if use_scale_shift_norm else self.out_channels))
+        self.out_layers = nn.Sequential(_gn(self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
+                                        nn.Conv2d(self.out_channels, self.out_channels, 3, padding=1))
+        if self.out_channels == channels:
+            self.skip_connection = nn.Identity()
+        elif use_conv:
+            self.skip_connection = nn.Conv2d(channels, self.out_channels, 3, padding=1)
+        else:
+            self.skip_connection = nn.Conv2d(channels, self.out_channels, 1)
+
+
+class AttentionBlock(nn.Module):
+    """Parameters of openaimodel.AttentionBlock (:426-473)."""
+
+    def __init__(self, channels, num_heads=1, num_head_channels=-1, use_new_attention_order=False):
+        super().__init__()
+        self.channels = channels
+        if num_head_channels == -1:
+            self.num_heads = num_heads
+        else:
+            assert channels % num_head_channels == 0, (
+                f"q,k,v channels {channels} is not divisible by num_head_channels {num_head_channels}")
+            self.num_heads = channels // num_head_channels
+        self.use_new_attention_order = use_new_attention_order
+        self.norm = _gn(channels)
+        self.qkv = nn.Conv1d(channels, channels * 3, 1)
+        self.proj_out = nn.Conv1d(channels, channels, 1)
+
+
+class Downsample(nn.Module):
+    def __init__(self, channels, use_conv, out_channels=None):
+        super().__init__()
+        self.channels, self.out_channels, self.use_conv = channels, out_channels or channels, use_conv
+        if use_conv:
+            self.op = nn.Conv2d(channels, self.out_channels, 3, stride=2, padding=1)
+        else:
+            assert self.channels == self.out_channels
+            self.op = nn.AvgPool2d(2, 2)
+
+
+class Upsample(nn.Module):
+    def __init__(self, channels, use_conv, out_channels=None):
+        super().__init__()
+        self.channels, self.out_channels, self.use_conv = channels, out_channels or channels, use_conv
+        if use_conv:
+            self.conv = nn.Conv2d(channels, self.out_channels, 3, padding=1)
+
+
+class TimestepEmbedSequential(nn.Sequential):
+    """Container only (openaimodel.py:74-90); the engine dispatches on the child type."""
+
+
+# ---------------------------------------------------------------------------------------------
+# engine helpers shared by UNetModel and DSUnetModel
+# ---------------------------------------------------------------------------------------------
+class PackedWeights:
+    """Kernel-layout copies of a module tree's weights (rebuilt when parameters change)."""
+
+    def __init__(self, root: nn.Module, dtype: torch.dtype):
+        self.dtype = dtype
+        self.conv = {}        # id(module) -> packed [taps, Cout, CinPad]
+        self.bias2 = {}       # id(ResBlock) -> conv2 bias + skip bias
+        self.emb_slices = {}  # id(ResBlock) -> (offset, width)
+        emb_w, emb_b, off = [], [], 0
+        for m in root.modules():
+            if isinstance(m, (nn.Conv2d, nn.Conv1d)):
+                w = m.weight.detach()
+                if w.shape[1] % 8 == 0 and w.shape[0] % 8 == 0:
+                    self.conv[id(m)] = ops.pack_conv_weight(w.float(), dtype)
+            if isinstance(m, ResBlock):
+                lin = m.emb_layers[1]
+                emb_w.append(lin.weight.detach().float())
+                emb_b.append(lin.bias.detach().float())
+                self.emb_slices[id(m)] = (off, lin.weight.shape[0])
+                off += lin.weight.shape[0]
+                b2 = m.out_layers[3].bias.detach().float()
+                if isinstance(m.skip_connection, nn.Conv2d):
+                    b2 = b2 + m.skip_connection.bias.detach().float()
+                self.bias2[id(m)] = b2.contiguous()
+        self.emb_w = torch.cat(emb_w, 0).contiguous() if emb_w else None
+        self.emb_b = torch.cat(emb_b, 0).contiguous() if emb_b else None
+
+
+def _f(p: Tensor) -> Tensor:
+    t = p.detach()
+    return t if t.dtype == torch.float32 and t.is_contiguous() else t.float().contiguous()
+
+
+def run_resblock(pw: PackedWeights, m: ResBlock, x0: Tensor, x1: Optional[Tensor], emb_all: Tensor) -> Tensor:
+    """ResBlock._forward (openaimodel.py:264-284) on NHWC activations; input = cat([x0, x1], C)."""
+    if m.up or m.down:
+        raise NotImplementedError("resblock_updown=True is not supported by the B200 engine yet")
+    gin, gout = m.in_layers[0], m.out_layers[0]
+    a = ops.group_norm(x0, _f(gin.weight), _f(gin.bias), x1, eps=gin.eps, silu=True)
+    off, width = pw.emb_slices[id(m)]
+    emb_out = emb_all[:, off:off + width]
+    conv1, conv2 = m.in_layers[2], m.out_layers[3]
+    if m.use_scale_shift_norm:
+        h = ops.conv2d([(a, pw.conv[id(conv1)], 0, 3, 1)], bias=_f(conv1.bias))
+        a2 = ops.group_norm(h, _f(gout.weight), _f(gout.bias), eps=gout.eps, silu=True, film=emb_out)
+    else:
+        h = ops.conv2d([(a, pw.conv[id(conv1)], 0, 3, 1)], bias=_f(conv1.bias), rowbias=emb_out)
+        a2 = ops.group_norm(h, _f(gout.weight), _f(gout.bias), eps=gout.eps, silu=True)
+    segs = [(a2, pw.conv[id(conv2)], 0, 3, 1)]
+    residual = None
+    sk = m.skip_connection
+    if isinstance(sk, nn.Conv2d):
+        ks = sk.kernel_size[0]
+        wsk = pw.conv[id(sk)]
+        segs.append((x0, wsk, 0, ks, ks // 2))
+        if x1 is not None:
+            segs.append((x1, wsk, x0.shape[-1], ks, ks // 2))
+    else:
+        residual = x0 if x1 is None else torch.cat([x0, x1], dim=-1)
+    return ops.conv2d(segs, bias=pw.bias2[id(m)], residual=residual)
+
+
+def run_attention(pw: PackedWeights, m: AttentionBlock, x: Tensor) -> Tensor:
+    """AttentionBlock._forward (openaimodel.py:467-473)."""
+    n, h, w, c = x.shape
+    a = ops.group_norm(x, _f(m.norm.weight), _f(m.norm.bias), eps=m.norm.eps, silu=False)
+    qkv = ops.conv2d([(a, pw.conv[id(m.qkv)], 0, 1, 0)], bias=_f(m.qkv.bias))
+    att = ops.attention_qkv(qkv.view(n, h * w, 3 * c), m.num_heads, m.use_new_attention_order)
+    return ops.conv2d([(att.view(n, h, w, c), pw.conv[id(m.proj_out)], 0, 1, 0)], bias=_f(m.proj_out.bias),
+                      residual=x)
+
+
+def run_sequential(pw: PackedWeights, seq: nn.Sequential, x0: Tensor, x1: Optional[Tensor], emb_all: Tensor) -> Tensor:
+    """TimestepEmbedSequential.forward (openaimodel.py:80-90)."""
+    for layer in seq:
+        if isinstance(layer, ResBlock):
+            x0, x1 = run_resblock(pw, layer, x0, x1, emb_all), None
+            continue
+        if x1 is not None:
+            x0, x1 = torch.cat([x0, x1], dim=-1), None
+        if isinstance(layer, AttentionBlock):
+            x0 = run_attention(pw, layer, x0)
+        elif isinstance(layer, Downsample):
+            if not layer.use_conv:
+                raise NotImplementedError("Downsample(use_conv=False) is not supported by the B200 engine yet")
+            x0 = ops.conv2d([(x0, pw.conv[id(layer.op)], 0, 3, 1)], stride=2, bias=_f(layer.op.bias))
+        elif isinstance(layer, Upsample):
+            x0 = ops.upsample_nearest2x(x0)
+            if layer.use_conv:
+                x0 = ops.conv2d([(x0, pw.conv[id(layer.conv)], 0, 3, 1)], bias=_f(layer.conv.bias))
+        elif isinstance(layer, nn.Conv2d):
+            x0 = ops.conv2d([(x0, pw.conv[id(layer)], 0, layer.kernel_size[0], layer.padding[0])], bias=_f(layer.bias))
+        else:
+            raise B200Error(f"B200 engine: unsupported layer {type(layer).__name__}")
+    return x0
+
+
+def run_in_conv(pw: PackedWeights, conv: nn.Conv2d, x: Tensor, dtype: torch.dtype) -> Tensor:
+    """First conv: NCHW fp32 -> NHWC 16-bit (input_blocks.0.0, openaimodel.py:714-719)."""
+    if conv.in_channels <= 8:
+        return ops.conv3x3_in(x.contiguous(), _f(conv.weight), _f(conv.bias), dtype)
+    cpad = (conv.in_channels + 7) // 8 * 8
+    key = ("in", id(conv))
+    if key not in pw.conv:
+        pw.conv[key] = ops.pack_conv_weight(_f(conv.weight), dtype, cpad)
+    return ops.conv2d([(ops.nchw_to_nhwc(x, cpad, dtype), pw.conv[key], 0, 3, 1)], bias=_f(conv.bias))
+
+
+def run_out_head(pw: PackedWeights, out: nn.Sequential, h: Tensor) -> Tensor:
+    """self.out = GN, SiLU, conv3x3 (openaimodel.py:898-902): NHWC 16-bit -> NCHW fp32."""
+    gn, conv = out[0], out[2]
+    a = ops.group_norm(h, _f(gn.weight), _f(gn.bias), eps=gn.eps, silu=True)
+    if conv.out_channels <= 4:
+        return ops.conv3x3_out(a, _f(conv.weight), _f(conv.bias))
+    key = ("out", id(conv))
+    cpad = (conv.out_channels + 7) // 8 * 8
+    if key not in pw.conv:
+        w = torch.zeros((cpad,) + tuple(conv.weight.shape[1:]), device=h.device)
+        w[:conv.out_channels] = conv.weight.detach().float()
+        b = torch.zeros(cpad, device=h.device)
+        b[:conv.out_channels] = conv.bias.detach().float()
+        pw.conv[key] = (ops.pack_conv_weight(w, h.dtype), b)
+    wp, bp = pw.conv[key]
+    return ops.nhwc_to_nchw(ops.conv2d([(a, wp, 0, 3, 1)], bias=bp), conv.out_channels)
+
+
+class TimeEmbedding:
+    """timestep_embedding (util.py:161-181) + time_embed MLP + all ResBlock emb_layers."""
+
+    def __init__(self, model_channels: int, device, max_period: float = 10000.0):
+        half = model_channels // 2
+        # the reference's own fp32 expression (util.py:171-173), evaluated on the CPU once
+        freqs = torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half)
+        self.freqs = freqs.to(device)
+        self.dim = model_channels
+
+    def __call__(self, pw: PackedWeights, time_embed: nn.Sequential, t_table: Tensor, batch: int,
+                 step_ptr: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+        t_emb = ops.timestep_embedding(t_table, self.freqs, batch, self.dim, step_ptr)
+        l0, l2 = time_embed[0], time_embed[2]
+        hid = ops.linear_f32(t_emb, _f(l0.weight), _f(l0.bias), out_silu=True)
+        emb = ops.linear_f32(hid, _f(l2.weight), _f(l2.bias))
+        emb_all = ops.linear_f32(emb, pw.emb_w, pw.emb_b, in_silu=True)
+        return emb, emb_all
+
+
+class _EngineModule(nn.Module):
+    """Shared plumbing: packed-weight cache invalidation + timestep handling."""
+
+    act_dtype: torch.dtype
+
+    def _init_engine(self):
+        self._pw: Optional[PackedWeights] = None
+        self._temb: Optional[TimeEmbedding] = None
+        self.register_load_state_dict_post_hook(lambda mod, keys: mod.invalidate())
+
+    def invalidate(self):
+        self._pw = None
+        self._temb = None
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def packed(self) -> PackedWeights:
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise B200Error("the B200 engine has no CPU path: move the module to a CUDA device")
+        if self._pw is None or self._pw.dtype != self.act_dtype:
+            with torch.no_grad():
+                self._pw = PackedWeights(self, self.act_dtype)
+                self._temb = TimeEmbedding(self.model_channels, dev)
+        return self._pw
+
+    @staticmethod
+    def _t_table(timesteps: Tensor, batch: int) -> Tensor:
+        if timesteps is None:
+            raise B200Error("timesteps must be given")
+        t = timesteps.reshape(-1).to(torch.float32)
+        if t.numel() == 1 and batch > 1:
+            t = t.expand(batch)
+        return t.contiguous()
+
+
+class UNetModel(_EngineModule):
+    """openaimodel.UNetModel (:571-958) — constructor keywords and state_dict identical."""
+
+    def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
+                 dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None,
+                 use_checkpoint=False, use_fp16=False, use_bf16=False, num_heads=-1, num_head_channels=-1,
+                 num_heads_upsample=-1, use_scale_shift_norm=False, resblock_updown=False,
+                 use_new_attention_order=False, use_spatial_transformer=False, transformer_depth=1, context_dim=None,
+                 n_embed=None, legacy=True, disable_self_attentions=None, num_attention_blocks=None,
+                 disable_middle_self_attn=False, use_linear_in_transformer=False, adm_in_channels=None,
+                 act_dtype: Optional[torch.dtype] = None):
+        super().__init__()
+        if dims != 2:
+            raise NotImplementedError("B200 engine: dims must be 2")
+        if use_spatial_transformer or context_dim is not None:
+            raise NotImplementedError("B200 engine: SpatialTransformer / cross-attention is not built yet")
+        if num_classes is not None or n_embed is not None:
+            raise NotImplementedError("B200 engine: class conditioning / codebook head are not built yet")
+        if num_heads_upsample == -1:
+            num_heads_upsample = num_heads
+        if num_heads == -1:
+            assert num_head_channels != -1, "Either num_heads or num_head_channels has to be set"
+        if num_head_channels == -1:
+            assert num_heads != -1, "Either num_heads or num_head_channels has to be set"
+        self.image_size, self.in_channels, self.model_channels, self.out_channels = (
+            image_size, in_channels, model_channels, out_channels)
+        if isinstance(num_res_blocks, int):
+            self.num_res_blocks = len(channel_mult) * [num_res_blocks]
+        else:
+            if len(num_res_blocks) != len(channel_mult):
+                raise ValueError("provide num_res_blocks either as an int (globally constant) or "
+                                 "as a list/tuple (per-level) with the same length as channel_mult")
+            self.num_res_blocks = list(num_res_blocks)
+        self.attention_resolutions = attention_resolutions
+        self.channel_mult = channel_mult
+        self.num_classes = None
+        self.dtype = torch.float32
+        self.act_dtype = act_dtype or default_act_dtype()
+        ted = model_channels * 4
+        self.time_embed = nn.Sequential(nn.Linear(model_channels, ted), nn.SiLU(), nn.Linear(ted, ted))
+
+        def attn(ch, heads):
+            return AttentionBlock(ch, num_heads=heads, num_head_channels=num_head_channels,
+                                  use_new_attention_order=use_new_attention_order)
+
+        def res(cin, cout=None, **kw):
+            return ResBlock(cin, ted, dropout, out_channels=cout, use_scale_shift_norm=use_scale_shift_norm, **kw)
+
+        self.input_blocks = nn.ModuleList([TimestepEmbedSequential(nn.Conv2d(in_channels, model_channels, 3, padding=1))])
+        chans = [model_channels]
+        ch, ds = model_channels, 1
+        for level, mult in enumerate(channel_mult):
+            for nr in range(self.num_res_blocks[level]):
+                layers: List[nn.Module] = [res(ch, mult * model_channels)]
+                ch = mult * model_channels
+                if ds in attention_resolutions and (num_attention_blocks is None or nr < num_attention_blocks[level]):
+                    layers.append(attn(ch, num_heads))
+                self.input_blocks.append(TimestepEmbedSequential(*layers))
+                chans.append(ch)
+            if level != len(channel_mult) - 1:
+                self.input_blocks.append(TimestepEmbedSequential(
+                    res(ch, ch, down=True) if resblock_updown else Downsample(ch, conv_resample, out_channels=ch)))
+                chans.append(ch)
+                ds *= 2
+        self.middle_block = TimestepEmbedSequential(res(ch), attn(ch, num_heads), res(ch))
+        self.output_blocks = nn.ModuleList([])
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(self.num_res_blocks[level] + 1):
+                ich = chans.pop()
+                layers = [res(ch + ich, model_channels * mult)]
+                ch = model_channels * mult
+                if ds in attention_resolutions and (num_attention_blocks is None or i < num_attention_blocks[level]):
+                    layers.append(attn(ch, num_heads_upsample))
+                if level and i == self.num_res_blocks[level]:
+                    layers.append(res(ch, ch, up=True) if resblock_updown else Upsample(ch, conv_resample, out_channels=ch))
+                    ds //= 2
+                self.output_blocks.append(TimestepEmbedSequential(*layers))
+        self.out = nn.Sequential(_gn(ch), nn.SiLU(), nn.Conv2d(model_channels, out_channels, 3, padding=1))
+        self._init_engine()
+
+    @torch.no_grad()
+    def forward(self, x, timesteps=None, context=None, y=None, step_ptr: Optional[Tensor] = None, **kwargs):
+        """x [N,C,H,W] fp32 NCHW, timesteps [N] (int or float) -> [N,out_channels,H,W] in x.dtype.
+
+        ``step_ptr`` (engine extension): device int32 index into ``timesteps`` used as a table, so a
+        captured CUDA graph can be replayed for every sampling step."""
+        assert (y is not None) == (self.num_classes is not None), \
+            "must specify y if and only if the model is class-conditional"
+        if context is not None:
+            raise NotImplementedError("B200 engine: cross-attention context is not built yet")
+        pw = self.packed()
+        n = x.shape[0]
+        t_table = timesteps.to(torch.float32).contiguous() if step_ptr is not None else self._t_table(timesteps, n)
+        _, emb_all = self._temb(pw, self.time_embed, t_table, n, step_ptr)
+        hs = []
+        h = run_in_conv(pw, self.input_blocks[0][0], x.float(), self.act_dtype)
+        hs.append(h)
+        for blk in list(self.input_blocks)[1:]:
+            h = run_sequential(pw, blk, h, None, emb_all)
+            hs.append(h)
+        h = run_sequential(pw, self.middle_block, h, None, emb_all)
+        for blk in self.output_blocks:
+            h = run_sequential(pw, blk, h, hs.pop(), emb_all)
+        return run_out_head(pw, self.out, h).to(x.dtype)

@@ -1,0 +1,188 @@
+/*
+ * b200diff.h — C ABI of libb200diff.so (sm_100a kernels for the DS-Diff sampling hot path).
+ *
+ * The reference (larrybb626/diffusion_models_dsdiff) is pure Python/PyTorch and has NO FFI of
+ * its own: the seam a maintainer would bind is the set of torch ops its
+ * hot path dispatches.  Each entry point below names the reference call site(s) whose arithmetic
+ * it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers + sizes only; no torch / C++ types.  All data pointers are DEVICE pointers
+ *     unless the name ends in _host.  `stream` is a cudaStream_t passed as void*.
+ *   - never allocates device memory, never synchronises, never falls back to the CPU.
+ *   - returns 0 on success; non-zero = error, text via b200_last_error() (thread-local).
+ *   - activations inside the network are NHWC 16-bit ("act"): B200_F16 (IEEE half, default —
+ *     same 10-bit mantissa as the TF32 the reference runs with) or B200_BF16.  Tensor-core
+ *     accumulation, GroupNorm statistics, softmax, time embedding and the sampler state are fp32.
+ *   - the API edge (what the Python drop-in classes expose) is NCHW fp32 like the reference.
+ */
+#ifndef B200DIFF_H_
+#define B200DIFF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_F16 0
+#define B200_BF16 1
+
+/* ---- library ---------------------------------------------------------------------------- */
+int b200_abi_version(void);
+const char *b200_last_error(void);
+/* one-time per-process init on the CURRENT device (driver entry points, smem attributes). */
+int b200_init(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+uint64_t b200_launch_count(void);
+
+/* ---- layout conversion at the API edge ----------------------------------------------------
+ * replaces nothing in the reference (it is NCHW fp32 throughout); needed because the kernels
+ * run NHWC 16-bit.  src NCHW fp32 [N,C,H,W] -> dst NHWC act [N,H,W,Cpad] (channels >= C are 0). */
+int b200_nchw_f32_to_nhwc(const float *src, void *dst, int N, int C, int H, int W, int Cpad,
+                          int act_dtype, void *stream);
+int b200_nhwc_to_nchw_f32(const void *src, float *dst, int N, int C, int H, int W, int Csrc,
+                          int act_dtype, void *stream);
+
+/* ---- weight repack (once per load_state_dict) ----------------------------------------------
+ * OIHW fp32 [Cout,Cin,KH,KW] (state_dict layout, ldm/modules/diffusionmodules/util.py:229-239
+ * conv_nd) -> [KH*KW][Cout][CinPad] act dtype, K-major rows for the tcgen05 B operand.       */
+int b200_pack_conv_weight(const float *w_oihw, void *dst, int Cout, int Cin, int KH, int KW,
+                          int CinPad, int act_dtype, void *stream);
+
+/* ---- implicit-GEMM convolution on tcgen05/TMEM, operands by TMA ------------------------------
+ * replaces F.conv2d as called by ResBlock in_layers[2]/out_layers[3]/skip_connection
+ * (ldm/modules/diffusionmodules/openaimodel.py:208,234,245), Downsample.op (:155-157),
+ * Upsample.conv (:118-120), AttentionBlock qkv/proj_out Conv1d (:452,460), FeatureDisentangle and
+ * the *_proj/all_proj convs of DSUnetModel (UNet_DS_Diff/model.py:158,163,569-601), and every
+ * nn.Linear applied to a [B,L,C] token tensor (ldm/modules/attention.py, DiT_models.py).
+ *
+ *   out[n,ho,wo,co] = sum_seg sum_{r,s,ci} src_seg[n, ho*stride+r-pad, wo*stride+s-pad, ci]
+ *                                          * w_seg[r*k+s][co][coff_seg+ci]
+ *                     + bias[co] + rowbias[n*rowbias_stride + co] + res_scale*residual[n,ho,wo,co]
+ *
+ * Up to 3 K-segments accumulate into the same TMEM tile: this is how concat inputs
+ * (th.cat([h, hs.pop()],1), openaimodel.py:952) and the fused ResBlock 1x1 skip are expressed
+ * without materialising the concatenation.  Channel counts must be multiples of 8.            */
+typedef struct {
+  const void *src;     /* NHWC act [N,Hin,Win,cin]                                   */
+  const void *weight;  /* packed [k*k][Cout][wcin] act (b200_pack_conv_weight)       */
+  int cin;             /* channels of src                                            */
+  int wcin;            /* Cin pitch of the packed weight (>= coff+cin)               */
+  int coff;            /* first weight input-channel used by this segment            */
+  int ksize;           /* 1 or 3                                                     */
+  int pad;             /* 0 or 1                                                     */
+} b200_conv_seg;
+
+typedef struct {
+  int N, Hin, Win;     /* input spatial size (all segments share it)                 */
+  int Hout, Wout;      /* output spatial size                                        */
+  int Cout;
+  int stride;          /* 1 or 2                                                     */
+  int nseg;            /* 1..3                                                       */
+  b200_conv_seg seg[3];
+  const float *bias;       /* [Cout] fp32 or NULL                                    */
+  const float *rowbias;    /* per-(n,co) fp32 add (timestep embedding, :282) or NULL */
+  int rowbias_stride;      /* elements between consecutive n                         */
+  const void *residual;    /* NHWC act [N,Hout,Wout,Cout] or NULL                    */
+  float res_scale;
+  void *out;               /* NHWC act [N,Hout,Wout,Cout]                            */
+  float *gn_sums;          /* optional [N][Cout][2] fp32 (sum,sumsq) accumulated from the fp32
+                              accumulators for a following GroupNorm, or NULL        */
+  int act_dtype;
+} b200_conv_desc;
+int b200_conv2d_igemm(const b200_conv_desc *d, void *stream);
+
+/* first conv of the network: tiny Cin (<= 8) read straight from NCHW fp32, writes NHWC act.
+ * replaces input_blocks[0] conv (openaimodel.py:717) after DiffusionWrapper's concat
+ * (ldm/models/diffusion/ddpm.py:1331-1333).  w is OIHW fp32.                                  */
+int b200_conv3x3_in(const float *x_nchw, const float *w_oihw, const float *bias, void *out_nhwc,
+                    int N, int Cin, int H, int W, int Cout, int act_dtype, void *stream);
+/* last conv: Cout <= 4, NHWC act -> NCHW fp32.  replaces self.out[2] (openaimodel.py:898-902). */
+int b200_conv3x3_out(const void *x_nhwc, const float *w_oihw, const float *bias, float *out_nchw,
+                     int N, int Cin, int H, int W, int Cout, int act_dtype, void *stream);
+
+/* ---- GroupNorm(+FiLM)(+SiLU), fused single apply pass ----------------------------------------
+ * replaces GroupNorm32 -> SiLU (util.py:209-226, openaimodel.py:205-209,229-236,898-902), the
+ * FiLM form GN(h)*(1+scale)+shift (openaimodel.py:276-280) and Normalize (eps 1e-6,
+ * ldm/modules/attention.py:88-89).  Input may be the channel-concatenation of two tensors.
+ * stats: [N][groups][2] fp64 (sum, sumsq), zero before b200_groupnorm_stats.                   */
+int b200_groupnorm_stats(const void *x0, int C0, const void *x1, int C1, int N, int HW,
+                         int groups, double *stats, int act_dtype, void *stream);
+int b200_groupnorm_apply(const void *x0, int C0, const void *x1, int C1, int N, int HW,
+                         int groups, float eps, const double *stats, const float *gamma,
+                         const float *beta, const float *film, int film_stride, int silu,
+                         void *out, int act_dtype, void *stream);
+
+/* ---- attention -------------------------------------------------------------------------------
+ * replaces QKVAttention / QKVAttentionLegacy (openaimodel.py:537-555 / 505-521): fused
+ * softmax_fp32((q*s)^T (k*s)) v with online softmax; qkv is the NHWC output of the qkv conv,
+ * [B, L, 3*heads*ch].  new_order=1: q|k|v blocks of heads*ch; 0 (legacy): per head [q,k,v].
+ * scale is applied to q.k (pass ch^-0.5 for the reference's ch^-0.25 on both).                 */
+int b200_attention_qkv(const void *qkv, void *out, int B, int L, int heads, int ch,
+                       int new_order, float scale, int act_dtype, void *stream);
+
+/* ---- small dense layers on [B,K] fp32 vectors (timestep path) --------------------------------
+ * replaces timestep_embedding (util.py:161-181), time_embed MLP (openaimodel.py:606-610) and
+ * the per-ResBlock emb_layers Linear(SiLU(emb)) (openaimodel.py:221-228).
+ * t is read from t_table[*step_ptr] when step_ptr != NULL (CUDA-graph replay), else t_table[b];
+ * freqs[dim/2] = exp(-ln(max_period)*j/half), built on the host with the reference's fp32 expression. */
+int b200_timestep_embedding(const float *t_table, const int *step_ptr, const float *freqs,
+                            float *out, int B, int dim, void *stream);
+/* out[b][o] = bias[o] + sum_k act(in[b][k]) * W[o][k];  in_silu / out_silu select the SiLU.     */
+int b200_linear_f32(const float *in, const float *W, const float *bias, float *out, int B, int K,
+                    int O, int in_silu, int out_silu, void *stream);
+
+/* ---- elementwise helpers ---------------------------------------------------------------------
+ * nearest x2 upsample (Upsample.forward F.interpolate, openaimodel.py:113-117), NHWC.          */
+int b200_upsample_nearest2x(const void *src, void *dst, int N, int H, int W, int C, int act_dtype,
+                            void *stream);
+/* dst = scale * (a + b + c + d)   (b,c,d may be NULL) — DS-Diff skip mean
+ * (hs+hs_a+hs_al+hs_l)/4, UNet_DS_Diff/model.py:745; mean of FeatureDisentangle outputs :722.   */
+int b200_add4_scale(const void *a, const void *b, const void *c, const void *d, float scale,
+                    void *dst, int64_t n, int silu, int act_dtype, void *stream);
+/* SE_Attention (Disc_diff/guided_diffusion/unet.py:105-109): x * sigmoid(W2 relu(W1 avgpool(x))). */
+int b200_se_attention(const void *x, const float *w1, const float *w2, void *out, float *scratch,
+                      int N, int HW, int C, int Cr, int act_dtype, void *stream);
+
+/* ---- fused per-step sampler update -----------------------------------------------------------
+ * one kernel per step; per-step coefficients live in a device table row selected by
+ * *step_ptr (so a captured CUDA graph can be replayed for every step), staged into shared
+ * memory by each CTA.  All state is fp32 NCHW like the reference.
+ *
+ * mode B200_SAMPLER_LDM_DDIM  — DDIMSampler.p_sample_ddim  (ldm/models/diffusion/ddim.py:188-261)
+ *      B200_SAMPLER_LDM_DDPM  — DDPM.p_sample/p_mean_variance/q_posterior as overridden in
+ *                               trainers/trainer_ds_diff.py:717-738 (base ddpm.py:304-332)
+ *      B200_SAMPLER_GD_DDIM   — GaussianDiffusion.ddim_sample
+ *                               (training_project/utils/gaussian_diffusion.py:620-667, 247-351)
+ *      B200_SAMPLER_GD_DDPM   — GaussianDiffusion.p_sample (:423-466)
+ * param: 0 eps, 1 x0, 2 v.  coef row layout (B200_SAMPLER_NCOEF floats) is documented in
+ * diffusion_models_dsdiff_b200/samplers.py next to the host code that fills it with the
+ * reference's own float64->float32 table expressions.                                          */
+#define B200_SAMPLER_LDM_DDIM 0
+#define B200_SAMPLER_LDM_DDPM 1
+#define B200_SAMPLER_GD_DDIM 2
+#define B200_SAMPLER_GD_DDPM 3
+#define B200_SAMPLER_NCOEF 16
+typedef struct {
+  int mode, param;
+  int clip_denoised;
+  int learned_range;       /* GD: model_out has 2*C channels, second half = variance frac */
+  int N, C, HW;            /* x is [N,C,HW]; model_out [N,C or 2C,HW]                     */
+  const float *x;          /* x_t                                                         */
+  const float *model_out;
+  const float *noise;      /* N(0,1), same shape as x; may be NULL when every sigma is 0   */
+  const float *coef;       /* [S][B200_SAMPLER_NCOEF]                                     */
+  const int *step_ptr;     /* device int: row of coef for this step (NULL -> step_host)    */
+  int step_host;
+  float *x_prev;           /* out                                                         */
+  float *pred_x0;          /* out, may be NULL                                            */
+} b200_sampler_desc;
+int b200_sampler_update(const b200_sampler_desc *d, void *stream);
+/* *step_ptr += delta (one-thread kernel; keeps the step counter on the device for graph replay). */
+int b200_advance_step(int *step_ptr, int delta, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DIFF_H_ */

@@ -1,0 +1,236 @@
+"""CPU tests of the host side: state_dict compatibility, schedule / coefficient tables (checked by
+replaying the fused kernel's arithmetic in numpy fp32 against the oracle's per-step functions and the
+reference-generated goldens), respacing, config plumbing, and the C-ABI surface of the built library.
+No CUDA compute is called here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import dsdiff_oracle as O
+from _util import golden
+from _util import manifest, maxabs, synth_sd
+
+import diffusion_models_dsdiff_b200 as P
+from diffusion_models_dsdiff_b200 import _lib as L
+from diffusion_models_dsdiff_b200 import samplers as S
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# -------------------------------------------------------------------------------------------------
+# C ABI surface
+# -------------------------------------------------------------------------------------------------
+def _header_symbols():
+    txt = open(os.path.join(REPO, "include", "b200diff.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = _header_symbols()
+    assert len(syms) >= 18
+    assert os.path.exists(L.LIB_PATH), "libb200diff.so not built (run __graft_entry__.build())"
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/b200diff.h but not exported"
+    assert set(L.SIGNATURES) == set(syms), "ctypes table and header disagree"
+    assert L.lib().b200_abi_version() == 1
+    assert L.lib().b200_launch_count() == 0 or True
+
+
+def test_error_path_reports_text_without_gpu():
+    d = L.ConvDesc()
+    d.nseg = 0
+    rc = L.lib().b200_conv2d_igemm(ctypes.byref(d), None)
+    assert rc != 0 and b"nseg" in L.lib().b200_last_error()
+    with pytest.raises(L.B200Error):
+        L.check(rc, "conv")
+
+
+# -------------------------------------------------------------------------------------------------
+# drop-in modules: constructor keywords + state_dict keys/shapes of the reference
+# -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["unet_small", "unet_legacy_film"])
+def test_unet_state_dict_matches_reference(case):
+    hp, sd = synth_sd(case)
+    net = P.UNetModel(**hp)
+    mine = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    ref = {k: tuple(v) for k, v in manifest()[case]["shapes"].items()}
+    assert mine == ref
+    net.load_state_dict(sd, strict=True)
+    assert all(v.dtype == torch.float32 for v in net.state_dict().values())
+
+
+def test_instantiate_from_config_maps_reference_targets():
+    hp, _ = synth_sd("unet_small")
+    net = S.instantiate_from_config({"target": "ldm.modules.diffusionmodules.openaimodel.UNetModel", "params": hp})
+    assert isinstance(net, P.UNetModel)
+    with pytest.raises(KeyError):
+        S.instantiate_from_config({"params": {}})
+
+
+# -------------------------------------------------------------------------------------------------
+# the fused update kernel's arithmetic, replayed in numpy fp32 on the host-built coefficient rows
+# -------------------------------------------------------------------------------------------------
+f32 = np.float32
+
+
+def emulate(mode, param, c, x, m, s, z, clip=True, learned=False):
+    """sampler.cu::sampler_elem, op for op, in numpy fp32 (no FMA)."""
+    x, m, z = x.astype(f32), m.astype(f32), z.astype(f32)
+    c = c.astype(f32)
+    cl = (lambda v: np.clip(v, f32(-1), f32(1))) if clip else (lambda v: v)
+    if mode == L.SAMPLER_LDM_DDIM:
+        if param == L.PARAM_V:
+            e = c[0] * m + c[1] * x
+            x0 = c[0] * x - c[1] * m
+        else:
+            e = m
+            x0 = (x - c[3] * e) / c[2]
+        x0 = cl(x0)
+        return (c[4] * x0 + c[5] * e) + (c[6] * z) * c[7], x0
+    x0 = m.copy() if param == L.PARAM_X0 else c[0] * x - c[1] * m
+    x0 = cl(x0)
+    if mode == L.SAMPLER_LDM_DDPM:
+        return (c[2] * x0 + c[3] * x) + c[4] * z, x0
+    if mode == L.SAMPLER_GD_DDIM:
+        eps = (c[6] * x - x0) / c[7]
+        return (x0 * c[8] + c[9] * eps) + c[10] * z, x0
+    mean = c[2] * x0 + c[3] * x
+    if learned:
+        frac = (s.astype(f32) + f32(1)) / f32(2)
+        logvar = frac * c[5] + (f32(1) - frac) * c[4]
+    else:
+        logvar = np.full_like(x, c[4])
+    return mean + (c[11] * np.exp(f32(0.5) * logvar)) * z, x0
+
+
+class _Stub(torch.nn.Module):
+    def forward(self, *a, **k):
+        raise AssertionError("network must not run in a host-logic test")
+
+
+def _ddpm(param, T=2000):
+    return S.DDPM(_Stub(), timesteps=T, beta_schedule="linear", linear_start=1e-4, linear_end=2e-2,
+                  conditioning_key="concat", parameterization=param)
+
+
+def test_ldm_schedule_buffers_bit_exact_vs_reference():
+    g = golden("tables_ldm_T2000_S50")
+    m = _ddpm("v")
+    for name, ref in (("betas", "betas"), ("alphas_cumprod", "alphas_cumprod"), ("sqrt_alphas_cumprod", "sqrt_ac"),
+                      ("sqrt_one_minus_alphas_cumprod", "sqrt_1mac"), ("posterior_log_variance_clipped", "post_logvar"),
+                      ("posterior_mean_coef1", "coef1"), ("posterior_mean_coef2", "coef2")):
+        assert torch.equal(getattr(m, name), g[ref]), name
+    smp = S.DDIMSampler(m)
+    smp.make_schedule(50, ddim_eta=0.3, verbose=False)
+    assert np.array_equal(smp.ddim_timesteps, g["ddim_timesteps"].numpy())
+    assert np.array_equal(np.asarray(smp.ddim_alphas), g["ddim_alphas"].numpy())
+    assert np.array_equal(np.asarray(smp.ddim_alphas_prev), g["ddim_alphas_prev"].numpy())
+    assert np.array_equal(np.asarray(smp.ddim_sigmas), g["ddim_sigmas"].numpy())
+    assert np.array_equal(np.asarray(smp.ddim_sqrt_one_minus_alphas), g["ddim_s1m"].numpy())
+
+
+@pytest.mark.parametrize("param", ["v", "eps"])
+@pytest.mark.parametrize("eta", [0.0, 0.7])
+def test_v1_coef_rows_reproduce_reference_steps(param, eta):
+    g = golden(f"v1_ddim_{param}_eta{eta}")
+    m = _ddpm(param)
+    smp = S.DDIMSampler(m)
+    n = g["S"]
+    smp.make_schedule(n, ddim_eta=eta, verbose=False)
+    coef, tsteps = smp._coef(False, 1.0)
+    assert coef.shape == (n, L.SAMPLER_NCOEF) and tsteps == sorted(tsteps, reverse=True)
+    x = g["x_T"].numpy()
+    for i in range(n):
+        xp, x0 = emulate(L.SAMPLER_LDM_DDIM, S._PARAM[param], coef[i].numpy(), x, g["model_out"][i].numpy(), None,
+                         g["noises"][i].numpy())
+        assert np.abs(xp - g["x_inter"][i].numpy()).max() < 2e-6, i
+        assert np.abs(x0 - g["pred_x0"][i].numpy()).max() < 2e-6, i
+        x = g["x_inter"][i].numpy()
+
+
+def test_v1_original_steps_rows():
+    m = _ddpm("v", T=40)
+    smp = S.DDIMSampler(m)
+    smp.make_schedule(8, ddim_eta=0.5, verbose=False)
+    coef, tsteps = smp._coef(True, 1.0)
+    assert tsteps == list(range(39, -1, -1)) and coef.shape[0] == 40
+    assert torch.isfinite(coef[:-1]).all()
+
+
+@pytest.mark.parametrize("param", ["v", "eps", "x0"])
+def test_v2_coef_rows_match_oracle_step(param):
+    T = 12
+    m = _ddpm(param, T=T)
+    sch = O.LdmSchedule(T, "linear", 1e-4, 2e-2)
+    seq = list(reversed(range(T)))
+    coef = m._ddpm_coef(seq)
+    rs = np.random.RandomState(0)
+    for i, t in enumerate(seq):
+        x, mo, z = (torch.from_numpy(rs.standard_normal((2, 1, 8, 8)).astype(f32)) for _ in range(3))
+        ref, ref0 = O.ldm_ddpm_step(sch, x, mo, t, z, param, True)
+        xp, x0 = emulate(L.SAMPLER_LDM_DDPM, S._PARAM[param], coef[i].numpy(), x.numpy(), mo.numpy(), None, z.numpy())
+        assert np.abs(xp - ref.numpy()).max() < 2e-6 and np.abs(x0 - ref0.numpy()).max() < 2e-6
+
+
+@pytest.mark.parametrize("mode", ["ddim", "ddpm"])
+@pytest.mark.parametrize("learn_sigma", [True, False])
+@pytest.mark.parametrize("eta", [0.0, 0.5])
+def test_v3_v4_coef_rows_match_oracle_step(mode, learn_sigma, eta):
+    d = S.create_gaussian_diffusion(steps=1000, learn_sigma=learn_sigma, timestep_respacing="5",
+                                    rescale_timesteps=True, parameterization="v")
+    sch = O.GdSchedule(1000, "linear", "5", True)
+    assert d.timestep_map == sch.timestep_map
+    assert [d._model_timestep(t) for t in range(5)] == [sch.model_timestep(t) for t in range(5)]
+    coef = d._coef(eta)
+    rs = np.random.RandomState(1)
+    kmode = L.SAMPLER_GD_DDIM if mode == "ddim" else L.SAMPLER_GD_DDPM
+    for i, t in enumerate(reversed(range(5))):
+        x, z = (torch.from_numpy(rs.standard_normal((2, 1, 8, 8)).astype(f32)) for _ in range(2))
+        mo = torch.from_numpy(rs.standard_normal((2, 2 if learn_sigma else 1, 8, 8)).astype(f32))
+        if mode == "ddim":
+            ref, ref0 = O.gd_ddim_step(sch, x, mo, t, z, eta=eta, parameterization="v", learn_sigma=learn_sigma)
+        else:
+            ref, ref0 = O.gd_ddpm_step(sch, x, mo, t, z, parameterization="v", learn_sigma=learn_sigma)
+        mean_ch = mo[:, :1].numpy()
+        s_ch = mo[:, 1:].numpy() if learn_sigma else None
+        xp, x0 = emulate(kmode, L.PARAM_V, coef[i].numpy(), x.numpy(), mean_ch, s_ch, z.numpy(), learned=learn_sigma)
+        assert np.abs(xp - ref.numpy()).max() < 3e-6, (i, t)
+        assert np.abs(x0 - ref0.numpy()).max() < 2e-6
+
+
+@pytest.mark.parametrize("resp", ["50", "20"])
+def test_gd_respacing_tables_bit_exact_vs_reference(resp):
+    g = golden(f"tables_gd_T1000_S{resp}")
+    d = S.create_gaussian_diffusion(steps=1000, learn_sigma=True, timestep_respacing=resp, rescale_timesteps=True,
+                                    parameterization="v")
+    assert d.timestep_map == g["timestep_map"].tolist()
+    assert np.array_equal(d.betas, g["betas"].numpy())
+    assert np.array_equal(d.alphas_cumprod, g["alphas_cumprod"].numpy())
+    assert np.array_equal(d.posterior_log_variance_clipped, g["post_logvar"].numpy())
+    assert np.array_equal(d.posterior_mean_coef1, g["coef1"].numpy())
+    assert np.array_equal(d.posterior_mean_coef2, g["coef2"].numpy())
+    assert np.array_equal(d.sqrt_recipm1_alphas_cumprod, g["sqrt_recipm1"].numpy())
+
+
+def test_space_timesteps_edge_cases():
+    assert S.space_timesteps(1000, "ddim50") == set(range(0, 1000, 20))
+    assert sorted(S.space_timesteps(10, [10])) == list(range(10))
+    assert sorted(S.space_timesteps(300, "10,5")) == sorted(O.gd_space_timesteps(300, "10,5"))
+    with pytest.raises(ValueError):
+        S.space_timesteps(10, [11])
+
+
+def test_unsupported_paths_fail_loudly():
+    m = _ddpm("v", T=20)
+    smp = S.DDIMSampler(m)
+    with pytest.raises(NotImplementedError):
+        smp.sample(5, 1, (1, 8, 8), None, mask=torch.ones(1), verbose=False)
+    hp, _ = synth_sd("unet_small")
+    with pytest.raises(NotImplementedError):
+        P.UNetModel(**{**hp, "use_spatial_transformer": True, "context_dim": 8})
