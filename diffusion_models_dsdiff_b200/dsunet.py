@@ -1,0 +1,136 @@
+"""Drop-in ``DSUnetModel`` — the DS-Diff four-stream backbone (UNet_DS_Diff/model.py:171-756).
+
+Same constructor keywords, ``forward(x, timesteps)`` -> ``(out, feature_dict)`` and state_dict keys as
+the reference: four encoders with separate weights (``input_blocks``, ``input_blocks_a``, ``_al``,
+``_l``; :522-524) fed by the four input channels (two-channel input zero-fills the last two streams,
+:654-658), the middle block on the noise stream only (:688), four ``FeatureDisentangle`` heads applied
+12 times (:695-719), SE_Attention + 3x3 projections of the per-family means (:722-725), a 1x1
+``all_proj`` over SiLU of the 5-way concat (:734-738) and a decoder whose skip is the mean of the four
+encoders' skips (:745).
+
+All arithmetic runs through the same sm_100a kernels as ``UNetModel`` (see unet.py): the skip mean is
+one fused 4-input kernel whose output then enters the concat-aware GroupNorm / split-K convolution, so
+``cat([h, skip])`` is never materialised.
+"""
+from __future__ import annotations
+
+import copy
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .unet import (_EngineModule, _f, _gn, build_unet_trunk, run_in_conv, run_out_head, run_sequential)
+
+Tensor = torch.Tensor
+
+
+class SE_Attention(nn.Module):
+    """Parameters of Disc_diff/guided_diffusion/unet.py:82-109 (bias-free squeeze/excite MLP)."""
+
+    def __init__(self, channel=512, reduction=16):
+        super().__init__()
+        self.se = nn.Sequential(nn.Linear(channel, channel // reduction, bias=False), nn.ReLU(inplace=True),
+                                nn.Linear(channel // reduction, channel, bias=False), nn.Sigmoid())
+
+
+class FeatureDisentangle(nn.Module):
+    """Parameters of UNet_DS_Diff/model.py:152-168."""
+
+    def __init__(self, in_channels, half_conv_ch):
+        super().__init__()
+        self.conv_1 = nn.Sequential(_gn(in_channels), nn.SiLU(), nn.Conv2d(in_channels, in_channels, 3, 1, 1))
+        self.conv_2 = nn.Sequential(_gn(in_channels), nn.SiLU(), nn.Conv2d(in_channels, half_conv_ch, 1, 1, 0))
+
+
+class DSUnetModel(_EngineModule):
+    _returns_features = True
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+        build_unet_trunk(self, *args, **kwargs)
+        self.input_blocks_a = nn.ModuleList([copy.deepcopy(m) for m in self.input_blocks])
+        self.input_blocks_al = nn.ModuleList([copy.deepcopy(m) for m in self.input_blocks])
+        self.input_blocks_l = nn.ModuleList([copy.deepcopy(m) for m in self.input_blocks])
+        input_ch = int(self.channel_mult[0] * self.model_channels)
+        conv_ch = input_ch * self.channel_mult[-1]
+        half = int(conv_ch / 2)
+        self.conv_style = FeatureDisentangle(conv_ch, half)
+        self.conv_content = FeatureDisentangle(conv_ch, half)
+        self.conv_anatomy = FeatureDisentangle(conv_ch, half)
+        self.conv_lesion = FeatureDisentangle(conv_ch, half)
+        mk = lambda: nn.Sequential(SE_Attention(half, reduction=8), nn.Conv2d(half, half, 3, 1, 1))
+        self.style_proj, self.share_content_proj = mk(), mk()
+        self.anatomy_proj, self.lesion_proj = mk(), mk()
+        self.all_proj = nn.Sequential(nn.SiLU(), nn.Conv2d(half * 6, conv_ch, 1, 1, 0))
+        self._init_engine()
+
+    # FeatureDisentangle.forward (:165-168): conv_2(conv_1(x) + x)
+    def _fd(self, pw, m: FeatureDisentangle, x: Tensor) -> Tensor:
+        g1, c1, g2, c2 = m.conv_1[0], m.conv_1[2], m.conv_2[0], m.conv_2[2]
+        a = ops.group_norm(x, _f(g1.weight), _f(g1.bias), eps=g1.eps, silu=True)
+        out = ops.conv2d([(a, pw.conv[id(c1)], 0, 3, 1)], bias=_f(c1.bias), residual=x)
+        a2 = ops.group_norm(out, _f(g2.weight), _f(g2.bias), eps=g2.eps, silu=True)
+        return ops.conv2d([(a2, pw.conv[id(c2)], 0, 1, 0)], bias=_f(c2.bias))
+
+    # mean of a feature family -> SE_Attention -> 3x3 conv (:722-725)
+    def _proj(self, pw, seq: nn.Sequential, feats) -> Tensor:
+        mean = ops.add4_scale(*feats, *([None] * (4 - len(feats))), scale=1.0 / len(feats))
+        se, conv = seq[0].se, seq[1]
+        gated = ops.se_attention(mean, _f(se[0].weight), _f(se[2].weight))
+        return ops.conv2d([(gated, pw.conv[id(conv)], 0, 3, 1)], bias=_f(conv.bias))
+
+    @torch.no_grad()
+    def forward(self, x, timesteps=None, context=None, y=None, step_ptr: Optional[Tensor] = None,
+                return_features: bool = True, **kwargs):
+        assert (y is not None) == (self.num_classes is not None), \
+            "must specify y if and only if the model is class-conditional"
+        if context is not None:
+            raise NotImplementedError("B200 engine: cross-attention context is not built yet")
+        pw = self.packed()
+        n = x.shape[0]
+        t_table = timesteps.to(torch.float32).contiguous() if step_ptr is not None else self._t_table(timesteps, n)
+        _, emb_all = self._temb(pw, self.time_embed, t_table, n, step_ptr)
+        x = x.float()
+        if x.shape[1] == 2:       # :654-658
+            zero = torch.zeros_like(x[:, 0:1])
+            inputs = [x[:, 0:1], x[:, 1:2], zero, zero]
+        else:                     # :660-663
+            inputs = [x[:, 0:1], x[:, 1:2], x[:, 2:3], x[:, 3:4]]
+        skips, last = [], []
+        for blocks, xin in zip((self.input_blocks, self.input_blocks_a, self.input_blocks_al, self.input_blocks_l),
+                               inputs):
+            h = run_in_conv(pw, blocks[0][0], xin.contiguous(), self.act_dtype)
+            hs = [h]
+            for blk in list(blocks)[1:]:
+                h = run_sequential(pw, blk, h, None, emb_all)
+                hs.append(h)
+            skips.append(hs)
+            last.append(h)
+        h_n = run_sequential(pw, self.middle_block, last[0], None, emb_all)     # :688
+        h_a, h_al, h_l = last[1], last[2], last[3]
+        fd = lambda m, v: self._fd(pw, m, v)
+        h_n_style, h_n_content = fd(self.conv_style, h_n), fd(self.conv_content, h_n)
+        style = [fd(self.conv_style, v) for v in (h_a, h_al, h_l)]
+        content = [fd(self.conv_content, v) for v in (h_a, h_al, h_l)]
+        anatomy = [fd(self.conv_anatomy, v) for v in (h_a, h_al)]
+        lesion = [fd(self.conv_lesion, v) for v in (h_al, h_l)]
+        h_style = self._proj(pw, self.style_proj, style)
+        h_share = self._proj(pw, self.share_content_proj, content)
+        h_anat = self._proj(pw, self.anatomy_proj, anatomy)
+        h_les = self._proj(pw, self.lesion_proj, lesion)
+        cat = torch.cat([h_n, h_share, h_style, h_anat, h_les], dim=-1)            # :734 (8x8 maps: tiny)
+        ap = self.all_proj[1]
+        h = ops.conv2d([(ops.add4_scale(cat, silu=True), pw.conv[id(ap)], 0, 1, 0)], bias=_f(ap.bias))   # :738
+        for blk in self.output_blocks:
+            skip = ops.add4_scale(skips[0].pop(), skips[1].pop(), skips[2].pop(), skips[3].pop(), scale=0.25)  # :745
+            h = run_sequential(pw, blk, h, skip, emb_all)
+        out = run_out_head(pw, self.out, h).to(x.dtype)
+        if not return_features:
+            return out, None
+        to = ops.nhwc_to_nchw
+        feats = {"style": [to(v) for v in style], "content": [to(v) for v in content],
+                 "anatomy": [to(v) for v in anatomy], "lesion": [to(v) for v in lesion],
+                 "n_style_content": [to(h_style), to(h_n_style), to(h_share), to(h_n_content)]}
+        return out, feats

@@ -17,6 +17,44 @@ from . import _lib as L
 Tensor = torch.Tensor
 
 
+class KernelTimer:
+    """Optional per-launch CUDA-event timing (bench.py's roofline pass).  Events are recorded on the launching
+    stream around each kernel of libb200diff; nothing is recorded unless a timer is installed."""
+
+    def __init__(self):
+        self.records = []      # (name, algorithmic flops, algorithmic bytes, start event, end event)
+
+    def summary(self) -> dict:
+        torch.cuda.synchronize()
+        out = {}
+        for name, fl, by, a, b in self.records:
+            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += a.elapsed_time(b)
+            d["flops"] += fl
+            d["bytes"] += by
+        return out
+
+
+_timer: Optional[KernelTimer] = None
+
+
+def set_timer(t: Optional[KernelTimer]) -> None:
+    global _timer
+    _timer = t
+
+
+def _timed(name: str, flops: float, nbytes: float, launch):
+    if _timer is None:
+        return launch()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    r = launch()
+    b.record()
+    _timer.records.append((name, flops, nbytes, a, b))
+    return r
+
+
 def act_code(dtype: torch.dtype) -> int:
     if dtype == torch.float16:
         return L.F16
@@ -127,7 +165,12 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
     d.out = _p(out)
     d.gn_sums = None
     d.act_dtype = act_code(src0.dtype)
-    L.check(L.lib().b200_conv2d_igemm(C.byref(d), _stream()), "conv2d_igemm")
+    kk = sum(sg[0].shape[3] * sg[3] * sg[3] for sg in segs)
+    flops = 2.0 * n * hout * wout * cout * kk
+    nbytes = 2.0 * (sum(sg[0].numel() for sg in segs) + out.numel() + cout * kk
+                    + (residual.numel() if residual is not None else 0))
+    _timed("conv_igemm", flops, nbytes,
+           lambda: L.check(L.lib().b200_conv2d_igemm(C.byref(d), _stream()), "conv2d_igemm"))
     return out
 
 
@@ -136,8 +179,9 @@ def conv3x3_in(x_nchw: Tensor, w_oihw: Tensor, bias: Optional[Tensor], dtype=tor
     n, ci, h, w = x_nchw.shape
     co = w_oihw.shape[0]
     out = torch.empty((n, h, w, co), device=x_nchw.device, dtype=dtype)
-    L.check(L.lib().b200_conv3x3_in(_p(_f32(x_nchw)), _p(_f32(w_oihw)), _p(_f32(bias)), _p(out), n, ci, h, w, co,
-                                    act_code(dtype), _stream()), "conv3x3_in")
+    _timed("conv3x3_in", 2.0 * n * h * w * co * ci * 9, 4.0 * x_nchw.numel() + 2.0 * out.numel(),
+           lambda: L.check(L.lib().b200_conv3x3_in(_p(_f32(x_nchw)), _p(_f32(w_oihw)), _p(_f32(bias)), _p(out), n, ci,
+                                                   h, w, co, act_code(dtype), _stream()), "conv3x3_in"))
     return out
 
 
@@ -146,8 +190,9 @@ def conv3x3_out(x: Tensor, w_oihw: Tensor, bias: Optional[Tensor]) -> Tensor:
     n, h, w, ci = x.shape
     co = w_oihw.shape[0]
     out = torch.empty((n, co, h, w), device=x.device, dtype=torch.float32)
-    L.check(L.lib().b200_conv3x3_out(_p(x), _p(_f32(w_oihw)), _p(_f32(bias)), _p(out), n, ci, h, w, co,
-                                     act_code(x.dtype), _stream()), "conv3x3_out")
+    _timed("conv3x3_out", 2.0 * n * h * w * co * ci * 9, 2.0 * x.numel() + 4.0 * out.numel(),
+           lambda: L.check(L.lib().b200_conv3x3_out(_p(x), _p(_f32(w_oihw)), _p(_f32(bias)), _p(out), n, ci, h, w, co,
+                                                    act_code(x.dtype), _stream()), "conv3x3_out"))
     return out
 
 
@@ -169,13 +214,19 @@ def group_norm(x0: Tensor, gamma: Tensor, beta: Tensor, x1: Optional[Tensor] = N
         stats = torch.zeros((n, groups, 2), device=x0.device, dtype=torch.float64)
     code = act_code(x0.dtype)
     lib = L.lib()
-    L.check(lib.b200_groupnorm_stats(_p(x0), c0, _p(x1), c1, n, hw, groups, _p(stats), code, _stream()),
-            "groupnorm_stats")
     out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=x0.dtype)
-    L.check(lib.b200_groupnorm_apply(_p(x0), c0, _p(x1), c1, n, hw, groups, eps, _p(stats), _p(_f32(gamma)),
-                                     _p(_f32(beta)), None if film is None else film.data_ptr(),
-                                     0 if film is None else film.stride(0), int(silu), _p(out), code, _stream()),
-            "groupnorm_apply")
+    film_p = None if film is None else film.data_ptr()
+    film_s = 0 if film is None else film.stride(0)
+
+    def launch():
+        L.check(lib.b200_groupnorm_stats(_p(x0), c0, _p(x1), c1, n, hw, groups, _p(stats), code, _stream()),
+                "groupnorm_stats")
+        L.check(lib.b200_groupnorm_apply(_p(x0), c0, _p(x1), c1, n, hw, groups, eps, _p(stats), _p(_f32(gamma)),
+                                         _p(_f32(beta)), film_p, film_s, int(silu), _p(out), code, _stream()),
+                "groupnorm_apply")
+
+    # algorithmic bytes: read the input once, write the output once (16-bit each)
+    _timed("groupnorm_silu", 0.0, 2.0 * 2.0 * out.numel(), launch)
     return out
 
 
@@ -188,8 +239,10 @@ def attention_qkv(qkv: Tensor, heads: int, new_order: bool) -> Tensor:
     b, l, c3 = qkv.shape
     ch = c3 // (3 * heads)
     out = torch.empty((b, l, heads * ch), device=qkv.device, dtype=qkv.dtype)
-    L.check(L.lib().b200_attention_qkv(_p(qkv), _p(out), b, l, heads, ch, int(new_order), float(ch) ** -0.5,
-                                       act_code(qkv.dtype), _stream()), "attention_qkv")
+    _timed("attention", 4.0 * b * heads * l * l * ch, 2.0 * (qkv.numel() + out.numel()),
+           lambda: L.check(L.lib().b200_attention_qkv(_p(qkv), _p(out), b, l, heads, ch, int(new_order),
+                                                      float(ch) ** -0.5, act_code(qkv.dtype), _stream()),
+                           "attention_qkv"))
     return out
 
 
@@ -216,7 +269,9 @@ def upsample_nearest2x(x: Tensor) -> Tensor:
     _dev(x)
     n, h, w, c = x.shape
     out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=x.dtype)
-    L.check(L.lib().b200_upsample_nearest2x(_p(x), _p(out), n, h, w, c, act_code(x.dtype), _stream()), "upsample")
+    _timed("upsample2x", 0.0, 2.0 * (x.numel() + out.numel()),
+           lambda: L.check(L.lib().b200_upsample_nearest2x(_p(x), _p(out), n, h, w, c, act_code(x.dtype), _stream()),
+                           "upsample"))
     return out
 
 
@@ -224,8 +279,10 @@ def add4_scale(a: Tensor, b: Optional[Tensor] = None, c: Optional[Tensor] = None
                scale: float = 1.0, silu: bool = False) -> Tensor:
     _dev(a)
     out = torch.empty_like(a)
-    L.check(L.lib().b200_add4_scale(_p(a), _p(b), _p(c), _p(d), scale, _p(out), a.numel(), int(silu),
-                                    act_code(a.dtype), _stream()), "add4_scale")
+    nin = 1 + (b is not None) + (c is not None) + (d is not None)
+    _timed("add4_scale", 0.0, 2.0 * a.numel() * (nin + 1),
+           lambda: L.check(L.lib().b200_add4_scale(_p(a), _p(b), _p(c), _p(d), scale, _p(out), a.numel(), int(silu),
+                                                   act_code(a.dtype), _stream()), "add4_scale"))
     return out
 
 
@@ -264,7 +321,10 @@ def sampler_update(mode: int, param: int, x: Tensor, model_out: Tensor, noise: O
     d.step_ptr = _p(step_ptr)
     d.step_host = step
     d.x_prev, d.pred_x0 = _p(x_prev), _p(pred_x0)
-    L.check(L.lib().b200_sampler_update(C.byref(d), _stream()), "sampler_update")
+    nb = 4.0 * (x.numel() + model_out.numel() + (noise.numel() if noise is not None else 0) + x_prev.numel()
+                + (pred_x0.numel() if pred_x0 is not None else 0))
+    _timed("sampler_update", 0.0, nb, lambda: L.check(L.lib().b200_sampler_update(C.byref(d), _stream()),
+                                                       "sampler_update"))
     return x_prev, pred_x0
 
 

@@ -1,0 +1,64 @@
+"""Slice sharding across ranks: sampling has NO data-path collective.
+
+The unit of work is one 2D slice (own x_T, noise, conditioning; GroupNorm / attention are per
+sample), so the slice list — a batch, or the 155 slices of a BraTS volume from the reference's
+``get_test_data_dict`` (trainers/trainer_ds_diff.py:256-265) — is partitioned over ranks, the weights
+are replicated, and the only communication is the final gather of finished slices to rank 0, which
+assembles the 2D->3D volume like ``on_predict_end`` (trainer_ds_diff.py:854-875).  Per-SLICE seeds make
+the result independent of the world size.  One process per GPU; ``torch.distributed`` with NCCL over
+NVLink on GPUs (gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+Tensor = torch.Tensor
+
+
+def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) of slice indices for ``rank``; sizes differ by at most one and the first
+    ``n_total % world`` ranks get the extra slice (155 slices on 8 ranks -> 20,20,20,19,...)."""
+    if not (0 <= rank < world) or n_total < 0:
+        raise ValueError(f"bad shard request: n_total={n_total} rank={rank} world={world}")
+    base, extra = divmod(n_total, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def slice_noise(slice_ids: Sequence[int], shape: Sequence[int], base_seed: int, device, stream_id: int = 0) -> Tensor:
+    """N(0,1) tensor [len(slice_ids), *shape] where slice i is drawn from its OWN generator
+    (seed = base_seed + 1000003 * stream_id + slice id): identical for any world size / batch split."""
+    out = torch.empty((len(slice_ids), *shape), dtype=torch.float32, device=device)
+    for j, sid in enumerate(slice_ids):
+        g = torch.Generator(device=device)
+        g.manual_seed(int(base_seed) + 1000003 * int(stream_id) + int(sid))
+        out[j] = torch.randn(tuple(shape), generator=g, device=device, dtype=torch.float32)
+    return out
+
+
+def gather_slices(local: Tensor, n_total: int, group: Optional[dist.ProcessGroup] = None) -> Optional[Tensor]:
+    """Gather every rank's finished slices ``[n_r, ...]`` (ragged n_r allowed) to rank 0 in global slice
+    order.  Returns the full ``[n_total, ...]`` tensor on rank 0, None elsewhere.  Single-process: identity."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if local.shape[0] != n_total:
+            raise ValueError("gather_slices: local slice count does not match n_total")
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nmax = max(shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world))
+    b, e = shard_range(n_total, rank, world)
+    if local.shape[0] != e - b:
+        raise ValueError(f"rank {rank}: expected {e - b} slices, got {local.shape[0]}")
+    pad = torch.zeros((nmax, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: e - b] = local
+    bufs: Optional[List[Tensor]] = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad, bufs, dst=0, group=group)
+    if rank != 0:
+        return None
+    parts = []
+    for r in range(world):
+        rb, re = shard_range(n_total, r, world)
+        parts.append(bufs[r][: re - rb])
+    return torch.cat(parts, dim=0)

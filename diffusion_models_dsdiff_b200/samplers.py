@@ -153,10 +153,15 @@ class StepEngine:
     """
 
     def __init__(self, model_fn: Callable, mode: int, param: int, coef: Tensor, t_table: Tensor,
-                 clip_denoised: bool, learned_range: bool = False):
+                 clip_denoised: bool, learned_range: bool = False, cache: Optional[dict] = None, cache_key=None,
+                 keepalive=None):
         self.model_fn, self.mode, self.param = model_fn, mode, param
         self.coef, self.t_table = coef, t_table
         self.clip, self.learned_range = clip_denoised, learned_range
+        # captured graphs are reused across calls (the reference builds a new DDIMSampler per batch);
+        # cache_key must change whenever the network's packed weights do, keepalive pins them
+        self.cache, self.cache_key, self.keepalive = cache, cache_key, keepalive
+        self.stats: dict = {}
 
     def _one(self, x: Tensor, cond: Optional[Sequence[Tensor]], step_ptr: Tensor, noise: Optional[Tensor],
              pred_x0: Optional[Tensor]):
@@ -187,7 +192,37 @@ class StepEngine:
                 if on_step:
                     on_step(i, x, pred_x0)
             return x
-        # ---- graph path: warm-up on scratch state (does not consume the caller-visible RNG stream or x) ----
+        # ---- graph path ----
+        key = None
+        if self.cache is not None:
+            key = (self.cache_key, self.mode, self.param, self.clip, self.learned_range, tuple(x.shape),
+                   tuple(tuple(c.shape) for c in (cond or [])), steps, want_x0)
+        entry = self.cache.get(key) if key is not None else None
+        if entry is None:
+            entry = self._capture(x, cond, pred_x0, step_ptr, key)
+        else:
+            entry["coef"].copy_(self.coef)
+            entry["t_table"].copy_(self.t_table)
+            entry["x"].copy_(x)
+            for dst, src in zip(entry["cond"], cond or []):
+                dst.copy_(src)
+            entry["step_ptr"].zero_()
+            self.stats = {"graph_launches_per_step": entry["launches"], "graph_reused": True}
+        xs, x0s = entry["x"], entry["pred_x0"]
+        for i in range(steps):
+            entry["graph"].replay()
+            if on_step:
+                on_step(i, xs, x0s)
+        self.stats["replays"] = steps
+        return xs.clone() if key is not None else xs
+
+    def _capture(self, x, cond, pred_x0, step_ptr, key):
+        """Warm-up one step on scratch state (restoring the RNG state so the caller-visible random stream is
+        untouched), then capture one step on static buffers."""
+        dev = x.device
+        coef, t_table = self.coef.clone(), self.t_table.clone()
+        self.coef, self.t_table = coef, t_table           # the captured kernels read these static tables
+        cond = [c.clone().contiguous() for c in (cond or [])]
         gen_state = torch.cuda.get_rng_state(dev)
         scratch = x.clone()
         s = torch.cuda.Stream(device=dev)
@@ -195,17 +230,35 @@ class StepEngine:
         with torch.cuda.stream(s):
             self._one(scratch, cond, step_ptr, None, pred_x0)
         torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
         torch.cuda.set_rng_state(gen_state, dev)
         step_ptr.zero_()
         graph = torch.cuda.CUDAGraph()
+        n0 = L.launch_count()
         with torch.cuda.graph(graph, stream=s):
             self._one(x, cond, step_ptr, None, pred_x0)
-        # capture does not execute: x / step_ptr / RNG are untouched, replay `steps` times
-        for i in range(steps):
-            graph.replay()
-            if on_step:
-                on_step(i, x, pred_x0)
-        return x
+        launches = L.launch_count() - n0
+        # capture does not execute: x / step_ptr / RNG are untouched
+        entry = {"graph": graph, "x": x, "cond": cond, "pred_x0": pred_x0, "step_ptr": step_ptr, "coef": coef,
+                 "t_table": t_table, "launches": launches, "keepalive": self.keepalive}
+        self.stats = {"graph_launches_per_step": launches, "graph_reused": False}
+        if key is not None:
+            if len(self.cache) >= 4:            # bounded: each entry pins a private activation pool
+                self.cache.pop(next(iter(self.cache)))
+            self.cache[key] = entry
+        return entry
+
+
+def _engine_model_fn(net):
+    """model_fn(xc, t_table, step_ptr) for a B200 engine network; the DS-Diff feature dict (discarded by
+    every sampler, trainer_ds_diff.py:752-755 / gaussian_diffusion.py:278-279) is not materialised."""
+    extra = {"return_features": False} if getattr(net, "_returns_features", False) else {}
+    return lambda xc, t_table, step_ptr: net(xc, t_table, step_ptr=step_ptr, **extra)
+
+
+def _graph_cache_args(cache: dict, net) -> dict:
+    pw = net.packed() if hasattr(net, "packed") else None
+    return {"cache": cache, "cache_key": (id(net), id(pw)), "keepalive": pw}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -362,8 +415,10 @@ class DDPM(nn.Module):
         return list(cond) if isinstance(cond, (list, tuple)) else [cond]
 
     def _model_fn(self):
-        net = self.model.diffusion_model
-        return lambda xc, t_table, step_ptr: net(xc, t_table, step_ptr=step_ptr)
+        return _engine_model_fn(self.model.diffusion_model)
+
+    def _graph_cache_args(self):
+        return _graph_cache_args(self.__dict__.setdefault("_graphs", {}), self.model.diffusion_model)
 
     @torch.no_grad()
     def p_sample(self, x, t, cond=None, clip_denoised=True, repeat_noise=False, noise=None, **kw):
@@ -385,7 +440,8 @@ class DDPM(nn.Module):
         coef = self._ddpm_coef(seq).to(device)
         t_table = torch.tensor(seq, dtype=torch.float32, device=device)
         eng = StepEngine(self._model_fn(), L.SAMPLER_LDM_DDPM, _PARAM[self.parameterization], coef, t_table,
-                         self.clip_denoised)
+                         self.clip_denoised, **self._graph_cache_args())
+        self.last_engine = eng
         intermediates = [img]
 
         def on_step(i, x, _x0):
@@ -512,7 +568,8 @@ class DDIMSampler(object):
         print(f"Running DDIM Sampling with {total_steps} timesteps")
         t_table = torch.tensor(tsteps, dtype=torch.float32, device=device)
         eng = StepEngine(self.model._model_fn(), L.SAMPLER_LDM_DDIM, _PARAM[self.model.parameterization],
-                         coef.to(device), t_table, clip_denoised)
+                         coef.to(device), t_table, clip_denoised, **self.model._graph_cache_args())
+        self.last_engine = self.model.last_engine = eng
         intermediates = {"x_inter": [img], "pred_x0": [img]}
 
         def on_step(i, x, x0):
@@ -664,9 +721,10 @@ class GaussianDiffusion:
         if model_kwargs and model_kwargs.get("c_concat") is not None:
             cond = list(model_kwargs["c_concat"])
         net = model.diffusion_model if isinstance(model, DiffusionWrapper) else model
-        model_fn = lambda xc, tt, sp: net(xc, tt, step_ptr=sp)
-        eng = StepEngine(model_fn, mode, self._param(), self._coef(eta).to(device), t_table, clip_denoised,
-                         learned_range=self.model_var_type == "learned_range")
+        eng = StepEngine(_engine_model_fn(net), mode, self._param(), self._coef(eta).to(device), t_table, clip_denoised,
+                         learned_range=self.model_var_type == "learned_range",
+                         **_graph_cache_args(self.__dict__.setdefault("_graphs", {}), net))
+        self.last_engine = eng
         return eng.run(img, cond, T, noises=noises, use_graph=self.use_graph, want_x0=record is not None,
                        record=record)
 

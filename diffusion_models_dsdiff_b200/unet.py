@@ -294,84 +294,90 @@ class _EngineModule(nn.Module):
         return t.contiguous()
 
 
+def build_unet_trunk(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
+                     dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None,
+                     use_checkpoint=False, use_fp16=False, use_bf16=False, num_heads=-1, num_head_channels=-1,
+                     num_heads_upsample=-1, use_scale_shift_norm=False, resblock_updown=False,
+                     use_new_attention_order=False, use_spatial_transformer=False, transformer_depth=1, context_dim=None,
+                     n_embed=None, legacy=True, disable_self_attentions=None, num_attention_blocks=None,
+                     disable_middle_self_attn=False, use_linear_in_transformer=False, adm_in_channels=None,
+                     act_dtype: Optional[torch.dtype] = None):
+    """Builds time_embed / input_blocks / middle_block / output_blocks / out on ``self`` with the block
+    structure of openaimodel.UNetModel.__init__ (:601-908), shared by UNetModel and DSUnetModel."""
+    if dims != 2:
+        raise NotImplementedError("B200 engine: dims must be 2")
+    if use_spatial_transformer or context_dim is not None:
+        raise NotImplementedError("B200 engine: SpatialTransformer / cross-attention is not built yet")
+    if num_classes is not None or n_embed is not None:
+        raise NotImplementedError("B200 engine: class conditioning / codebook head are not built yet")
+    if num_heads_upsample == -1:
+        num_heads_upsample = num_heads
+    if num_heads == -1:
+        assert num_head_channels != -1, "Either num_heads or num_head_channels has to be set"
+    if num_head_channels == -1:
+        assert num_heads != -1, "Either num_heads or num_head_channels has to be set"
+    self.image_size, self.in_channels, self.model_channels, self.out_channels = (
+        image_size, in_channels, model_channels, out_channels)
+    if isinstance(num_res_blocks, int):
+        self.num_res_blocks = len(channel_mult) * [num_res_blocks]
+    else:
+        if len(num_res_blocks) != len(channel_mult):
+            raise ValueError("provide num_res_blocks either as an int (globally constant) or "
+                             "as a list/tuple (per-level) with the same length as channel_mult")
+        self.num_res_blocks = list(num_res_blocks)
+    self.attention_resolutions = attention_resolutions
+    self.channel_mult = channel_mult
+    self.num_classes = None
+    self.dtype = torch.float32
+    self.act_dtype = act_dtype or default_act_dtype()
+    ted = model_channels * 4
+    self.time_embed = nn.Sequential(nn.Linear(model_channels, ted), nn.SiLU(), nn.Linear(ted, ted))
+
+    def attn(ch, heads):
+        return AttentionBlock(ch, num_heads=heads, num_head_channels=num_head_channels,
+                              use_new_attention_order=use_new_attention_order)
+
+    def res(cin, cout=None, **kw):
+        return ResBlock(cin, ted, dropout, out_channels=cout, use_scale_shift_norm=use_scale_shift_norm, **kw)
+
+    self.input_blocks = nn.ModuleList([TimestepEmbedSequential(nn.Conv2d(in_channels, model_channels, 3, padding=1))])
+    chans = [model_channels]
+    ch, ds = model_channels, 1
+    for level, mult in enumerate(channel_mult):
+        for nr in range(self.num_res_blocks[level]):
+            layers: List[nn.Module] = [res(ch, mult * model_channels)]
+            ch = mult * model_channels
+            if ds in attention_resolutions and (num_attention_blocks is None or nr < num_attention_blocks[level]):
+                layers.append(attn(ch, num_heads))
+            self.input_blocks.append(TimestepEmbedSequential(*layers))
+            chans.append(ch)
+        if level != len(channel_mult) - 1:
+            self.input_blocks.append(TimestepEmbedSequential(
+                res(ch, ch, down=True) if resblock_updown else Downsample(ch, conv_resample, out_channels=ch)))
+            chans.append(ch)
+            ds *= 2
+    self.middle_block = TimestepEmbedSequential(res(ch), attn(ch, num_heads), res(ch))
+    self.output_blocks = nn.ModuleList([])
+    for level, mult in list(enumerate(channel_mult))[::-1]:
+        for i in range(self.num_res_blocks[level] + 1):
+            ich = chans.pop()
+            layers = [res(ch + ich, model_channels * mult)]
+            ch = model_channels * mult
+            if ds in attention_resolutions and (num_attention_blocks is None or i < num_attention_blocks[level]):
+                layers.append(attn(ch, num_heads_upsample))
+            if level and i == self.num_res_blocks[level]:
+                layers.append(res(ch, ch, up=True) if resblock_updown else Upsample(ch, conv_resample, out_channels=ch))
+                ds //= 2
+            self.output_blocks.append(TimestepEmbedSequential(*layers))
+    self.out = nn.Sequential(_gn(ch), nn.SiLU(), nn.Conv2d(model_channels, out_channels, 3, padding=1))
+
+
 class UNetModel(_EngineModule):
     """openaimodel.UNetModel (:571-958) — constructor keywords and state_dict identical."""
 
-    def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
-                 dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None,
-                 use_checkpoint=False, use_fp16=False, use_bf16=False, num_heads=-1, num_head_channels=-1,
-                 num_heads_upsample=-1, use_scale_shift_norm=False, resblock_updown=False,
-                 use_new_attention_order=False, use_spatial_transformer=False, transformer_depth=1, context_dim=None,
-                 n_embed=None, legacy=True, disable_self_attentions=None, num_attention_blocks=None,
-                 disable_middle_self_attn=False, use_linear_in_transformer=False, adm_in_channels=None,
-                 act_dtype: Optional[torch.dtype] = None):
+    def __init__(self, *args, **kwargs):
         super().__init__()
-        if dims != 2:
-            raise NotImplementedError("B200 engine: dims must be 2")
-        if use_spatial_transformer or context_dim is not None:
-            raise NotImplementedError("B200 engine: SpatialTransformer / cross-attention is not built yet")
-        if num_classes is not None or n_embed is not None:
-            raise NotImplementedError("B200 engine: class conditioning / codebook head are not built yet")
-        if num_heads_upsample == -1:
-            num_heads_upsample = num_heads
-        if num_heads == -1:
-            assert num_head_channels != -1, "Either num_heads or num_head_channels has to be set"
-        if num_head_channels == -1:
-            assert num_heads != -1, "Either num_heads or num_head_channels has to be set"
-        self.image_size, self.in_channels, self.model_channels, self.out_channels = (
-            image_size, in_channels, model_channels, out_channels)
-        if isinstance(num_res_blocks, int):
-            self.num_res_blocks = len(channel_mult) * [num_res_blocks]
-        else:
-            if len(num_res_blocks) != len(channel_mult):
-                raise ValueError("provide num_res_blocks either as an int (globally constant) or "
-                                 "as a list/tuple (per-level) with the same length as channel_mult")
-            self.num_res_blocks = list(num_res_blocks)
-        self.attention_resolutions = attention_resolutions
-        self.channel_mult = channel_mult
-        self.num_classes = None
-        self.dtype = torch.float32
-        self.act_dtype = act_dtype or default_act_dtype()
-        ted = model_channels * 4
-        self.time_embed = nn.Sequential(nn.Linear(model_channels, ted), nn.SiLU(), nn.Linear(ted, ted))
-
-        def attn(ch, heads):
-            return AttentionBlock(ch, num_heads=heads, num_head_channels=num_head_channels,
-                                  use_new_attention_order=use_new_attention_order)
-
-        def res(cin, cout=None, **kw):
-            return ResBlock(cin, ted, dropout, out_channels=cout, use_scale_shift_norm=use_scale_shift_norm, **kw)
-
-        self.input_blocks = nn.ModuleList([TimestepEmbedSequential(nn.Conv2d(in_channels, model_channels, 3, padding=1))])
-        chans = [model_channels]
-        ch, ds = model_channels, 1
-        for level, mult in enumerate(channel_mult):
-            for nr in range(self.num_res_blocks[level]):
-                layers: List[nn.Module] = [res(ch, mult * model_channels)]
-                ch = mult * model_channels
-                if ds in attention_resolutions and (num_attention_blocks is None or nr < num_attention_blocks[level]):
-                    layers.append(attn(ch, num_heads))
-                self.input_blocks.append(TimestepEmbedSequential(*layers))
-                chans.append(ch)
-            if level != len(channel_mult) - 1:
-                self.input_blocks.append(TimestepEmbedSequential(
-                    res(ch, ch, down=True) if resblock_updown else Downsample(ch, conv_resample, out_channels=ch)))
-                chans.append(ch)
-                ds *= 2
-        self.middle_block = TimestepEmbedSequential(res(ch), attn(ch, num_heads), res(ch))
-        self.output_blocks = nn.ModuleList([])
-        for level, mult in list(enumerate(channel_mult))[::-1]:
-            for i in range(self.num_res_blocks[level] + 1):
-                ich = chans.pop()
-                layers = [res(ch + ich, model_channels * mult)]
-                ch = model_channels * mult
-                if ds in attention_resolutions and (num_attention_blocks is None or i < num_attention_blocks[level]):
-                    layers.append(attn(ch, num_heads_upsample))
-                if level and i == self.num_res_blocks[level]:
-                    layers.append(res(ch, ch, up=True) if resblock_updown else Upsample(ch, conv_resample, out_channels=ch))
-                    ds //= 2
-                self.output_blocks.append(TimestepEmbedSequential(*layers))
-        self.out = nn.Sequential(_gn(ch), nn.SiLU(), nn.Conv2d(model_channels, out_channels, 3, padding=1))
+        build_unet_trunk(self, *args, **kwargs)
         self._init_engine()
 
     @torch.no_grad()

@@ -65,10 +65,25 @@ def test_unet_state_dict_matches_reference(case):
     assert all(v.dtype == torch.float32 for v in net.state_dict().values())
 
 
+@pytest.mark.parametrize("case", ["ds_small", "ds_film2"])
+def test_dsunet_state_dict_matches_reference(case):
+    hp, sd = synth_sd(case)
+    net = P.DSUnetModel(**hp)
+    mine = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    ref = {k: tuple(v) for k, v in manifest()[case]["shapes"].items()}
+    assert mine == ref
+    net.load_state_dict(sd, strict=True)
+    # the three conditioning encoders are separate parameters, not views of the first
+    assert net.input_blocks_a[1][0].in_layers[2].weight.data_ptr() != net.input_blocks[1][0].in_layers[2].weight.data_ptr()
+
+
 def test_instantiate_from_config_maps_reference_targets():
     hp, _ = synth_sd("unet_small")
     net = S.instantiate_from_config({"target": "ldm.modules.diffusionmodules.openaimodel.UNetModel", "params": hp})
     assert isinstance(net, P.UNetModel)
+    hp2, _ = synth_sd("ds_small")
+    assert isinstance(S.instantiate_from_config({"target": "UNet_DS_Diff.model.DSUnetModel", "params": hp2}),
+                      P.DSUnetModel)
     with pytest.raises(KeyError):
         S.instantiate_from_config({"params": {}})
 
