@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py — DDIM-50 256x256 slices/sec of the DS-Diff sampling hot path on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one batch of synthetic input = a full 50-step DDIM sampling
+(ldm DDIMSampler, v-parameterisation, T=2000, eta=0, clip on) of ``--batch`` (default 8) 256x256 slices per
+GPU through ``DSUnetModel`` (BASELINE.json configs[1]: 320-ch DS-Diff backbone, 3 MRI conditioning channels
+concatenated; 64 slices over 8 GPUs = 8 slices per GPU, so the per-GPU work is fixed as N grows: weak
+scaling, no data-path collective — slices are independent units).
+
+Rank 0 prints ONE JSON line.  Keys beyond the base contract:
+  roofline       dominant kernel (tcgen05 implicit-GEMM conv): algorithmic FLOPs / CUDA-event time measured
+                 live in this process (one denoising step with per-launch events), vs MEASURED_PEAKS.json
+  roofline_aux   the same for the HBM-bound fused kernels (GroupNorm+SiLU, sampler update, ...) and attention
+  cpu_baseline   the oracle (CPU restatement of the reference, oracle/dsdiff_oracle.py) timed on the host cores
+                 on a bounded sample (one denoising step of one slice), extrapolated to slices/s
+  e2e            same metric through the public API (DDIMSampler.sample) with HOST (pinned) inputs and a host
+                 result: H2D of cond + x_T and D2H of the finished slices inside the timed region
+  parity         relative L2 error of the CUDA network output vs the oracle on the cpu_baseline sample
+
+``--impl reference`` times the reference's CPU implementation of the path (the oracle port — the reference is
+pure Python/PyTorch and /root/reference does not exist on the GPU box) on all host threads; each step is one
+denoising step of one slice (1/50 of a slice).
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+DDIM_STEPS = 50
+WORKLOADS = {
+    # configs/v2-1-cddpm-ds-disc.yaml:19-38 (DS-Diff, 320-ch) — BASELINE.json configs[1]
+    "cfg2": dict(cls="DSUnetModel", gflop_per_fwd=5544.9, cond_ch=3,
+                 hp=dict(image_size=32, in_channels=1, out_channels=1, model_channels=320,
+                         attention_resolutions=[32, 16, 8], num_res_blocks=2, channel_mult=[1, 1, 2, 2, 3, 3],
+                         num_head_channels=32, use_new_attention_order=True, legacy=False)),
+    # configs/v2-1-cddpm.yaml:19-38 (UNetModel, 160-ch) — BASELINE.json configs[0]
+    "cfg1": dict(cls="UNetModel", gflop_per_fwd=1679.7, cond_ch=3,
+                 hp=dict(image_size=32, in_channels=4, out_channels=1, model_channels=160,
+                         attention_resolutions=[16], num_res_blocks=2, channel_mult=[1, 2, 4, 4],
+                         num_head_channels=32, use_new_attention_order=True, legacy=False)),
+}
+NAMES = {"cfg2": "DSUnetModel 320-ch (configs/v2-1-cddpm-ds-disc.yaml) 256x256 DDIM-50 v-param T=2000 eta=0",
+         "cfg1": "UNetModel 160-ch (configs/v2-1-cddpm.yaml) 256x256 DDIM-50 v-param T=2000 eta=0"}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=8, help="slices per GPU per step")
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--act-dtype", default="f16", choices=["f16", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-pass", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm": float(p["hbm_gbs"]), "tensor_burst": float(p["bf16_tflops"]),
+                "tensor": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "source": "fallback"}
+
+
+def traffic_note(kernel: str):
+    """dram bytes/launch from the committed ncu --set full capture (profiles/roofline_traffic.json), else None."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(kernel)
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of this rank's GPU DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        self.index = vis.split(",")[index] if vis else str(index)
+        self.rows, self.proc = [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.index, f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.th.join(timeout=3)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_inputs(batch, cond_ch, size, rank):
+    """SURVEY.md §8d synthetic inputs; per-rank seeds so ranks sample different slices."""
+    import torch
+    g = torch.Generator().manual_seed(2024 + rank)
+    cond = (torch.randn(batch, cond_ch, size, size, generator=g) * 0.5).clamp_(-1, 1)
+    x_T = torch.randn(batch, 1, size, size, generator=torch.Generator().manual_seed(2025 + rank))
+    return cond, x_T
+
+
+# -------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline (the only places bench.py executes oracle/)
+# -------------------------------------------------------------------------------------------------
+def oracle_step_fn(wl, sd, size):
+    """One denoising step of ONE slice with the CPU oracle: network forward + ldm DDIM update."""
+    import torch
+    import dsdiff_oracle as O
+    sch = O.LdmSchedule(timesteps=2000, beta_schedule="linear", linear_start=1e-4, linear_end=2e-2)
+    tab = O.LdmDdimTables(sch, DDIM_STEPS, 0.0)
+    fwd = O.dsunet_forward if wl["cls"] == "DSUnetModel" else O.unet_forward
+    cond, x_T = synth_inputs(1, wl["cond_ch"], size, 0)
+    index = DDIM_STEPS - 1
+    ts = torch.full((1,), int(tab.timesteps[index]), dtype=torch.long)
+    noise = torch.zeros_like(x_T)
+
+    def step():
+        with torch.no_grad():
+            out = fwd(sd, wl["hp"], torch.cat([x_T, cond], 1), ts)
+            out = out[0] if isinstance(out, tuple) else out
+            xp, _ = O.ldm_ddim_step(sch, tab, x_T, out, index, noise, "v", True)
+        return out, xp
+
+    return step, (cond, x_T, ts)
+
+
+def meta_shapes(wl):
+    import torch
+    import diffusion_models_dsdiff_b200 as P
+    with torch.device("meta"):
+        net = getattr(P, wl["cls"])(**wl["hp"])
+    return {k: tuple(v.shape) for k, v in net.state_dict().items()}
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import dsdiff_oracle as O
+    wl = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.synth_state_dict(meta_shapes(wl))
+    step, _ = oracle_step_fn(wl, sd, args.size)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = 1.0 / (DDIM_STEPS * dt)
+    sample = (f"each step = ONE denoising step (network forward + DDIM update) of ONE {args.size}x{args.size} slice "
+              f"= 1/{DDIM_STEPS} of a slice; slices/s = 1/({DDIM_STEPS} x step time)")
+    print(json.dumps({
+        "impl": "reference", "metric": "DDIM-50 256x256 slices/sec", "value": value, "unit": "slices/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": NAMES[args.workload], "slices_per_step": 1.0 / DDIM_STEPS, "device": "cpu"},
+        "cpu_baseline": {"value": value, "unit": "slices/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# -------------------------------------------------------------------------------------------------
+# B200 arm
+# -------------------------------------------------------------------------------------------------
+def kernel_pass(model_fn, xc, t_table):
+    """One denoising step's network with per-launch CUDA events (the GPU is put to sleep first so the host runs
+    ahead and event pairs bracket device execution only)."""
+    import torch
+    from diffusion_models_dsdiff_b200 import ops
+    step_ptr = torch.zeros(1, dtype=torch.int32, device=xc.device)
+    model_fn(xc, t_table, step_ptr)
+    torch.cuda.synchronize()
+    timer = ops.KernelTimer()
+    ops.set_timer(timer)
+    try:
+        torch.cuda._sleep(int(2e8))
+        model_fn(xc, t_table, step_ptr)
+    finally:
+        ops.set_timer(None)
+    return timer.summary()
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import diffusion_models_dsdiff_b200 as P
+    from diffusion_models_dsdiff_b200 import samplers as S, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS[args.workload]
+    act = torch.float16 if args.act_dtype == "f16" else torch.bfloat16
+    B, size = args.batch, args.size
+
+    torch.manual_seed(0)
+    with torch.device(dev):
+        net = getattr(P, wl["cls"])(**wl["hp"], act_dtype=act)
+    net.eval()
+    model = S.DDPM(net, timesteps=2000, beta_schedule="linear", linear_start=1e-4, linear_end=2e-2,
+                   conditioning_key="concat", parameterization="v", clip_denoised=True).to(dev)
+    cond_h, xT_h = synth_inputs(B, wl["cond_ch"], size, rank)
+    cond_h, xT_h = cond_h.pin_memory(), xT_h.pin_memory()
+    out_h = torch.empty_like(xT_h).pin_memory()
+    cond_d, xT_d = cond_h.to(dev), xT_h.to(dev)
+    quiet = contextlib.redirect_stdout(sys.stderr)
+
+    def sample_resident():
+        smp = S.DDIMSampler(model)
+        out, _ = smp.sample(DDIM_STEPS, B, (1, size, size), cond_d, eta=0.0, x_T=xT_d, verbose=False,
+                            log_every_t=10 ** 9)
+        return out, smp
+
+    def sample_e2e():
+        c = cond_h.to(dev, non_blocking=True)
+        x = xT_h.to(dev, non_blocking=True)
+        smp = S.DDIMSampler(model)
+        out, _ = smp.sample(DDIM_STEPS, B, (1, size, size), c, eta=0.0, x_T=x, verbose=False, log_every_t=10 ** 9)
+        out_h.copy_(out, non_blocking=True)
+        return out, smp
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            _, smp = fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), smp
+
+    with quiet:
+        for _ in range(max(args.warmup, 1)):
+            sample_resident()
+        torch.cuda.synchronize()
+        n0 = P.launch_count()
+        with ClockSampler(local) as clk:
+            ms, smp = timed(sample_resident, args.steps)
+        eng = smp.last_engine
+        per_step = eng.stats.get("graph_launches_per_step", 0)
+        gpu_launches = (P.launch_count() - n0) + per_step * DDIM_STEPS * args.steps
+        sample_e2e()
+        ms_e2e, _ = timed(sample_e2e, args.steps)
+    slices = B * world * args.steps
+    value = slices / (ms / 1e3)
+    e2e_value = slices / (ms_e2e / 1e3)
+    flops_per_step = wl["gflop_per_fwd"] * 1e9 * (size / 256.0) ** 2 * B * DDIM_STEPS
+
+    res = {
+        "metric": "DDIM-50 256x256 slices/sec", "value": value, "unit": "slices/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.act_dtype + " operands, f32 accumulate", "data": "synthetic",
+        "config": {"workload": NAMES[args.workload], "slices_per_gpu_per_step": B, "global_batch": B * world,
+                   "ddim_steps": DDIM_STEPS, "image": [size, size], "cond_channels": wl["cond_ch"],
+                   "parallelism": f"slice-sharded x{world}, no data-path collective",
+                   "l2": "activations per layer exceed the 126 MB L2 (inputs larger than L2; no explicit flush)",
+                   "cuda_graph": True, "graph_kernels_per_denoise_step": per_step},
+        "e2e": {"value": e2e_value, "unit": "slices/s", "h2d_bytes_per_step": int(cond_h.numel() * 4 + xT_h.numel() * 4),
+                "d2h_bytes_per_step": int(out_h.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(gpu_launches),
+        "clocks": clk.summary(),
+        "model_tflops_per_gpu": flops_per_step * args.steps / (ms / 1e3) / 1e12,
+    }
+
+    pk = peaks()
+    if rank == 0 and not args.no_kernel_pass:
+        with quiet:
+            xc = torch.cat([xT_d, cond_d], 1)
+            t_table = torch.full((DDIM_STEPS,), 1961.0, device=dev)
+            ks = kernel_pass(model._model_fn(), xc, t_table)
+            # sampler update at the bench batch (HBM-bound; B*256*256 fp32 elements)
+            timer = ops.KernelTimer()
+            ops.set_timer(timer)
+            coef = torch.rand(DDIM_STEPS, 16, device=dev)
+            mo, z = torch.randn_like(xT_d), torch.randn_like(xT_d)
+            torch.cuda._sleep(int(2e7))
+            for _ in range(5):
+                ops.sampler_update(0, 2, xT_d.clone(), mo, z, coef, step=1, want_x0=True)
+            ops.set_timer(None)
+            ks.update(timer.summary())
+        total_ms = sum(v["ms"] for k, v in ks.items() if k != "sampler_update")
+        aux = []
+        for name, v in sorted(ks.items(), key=lambda kv: -kv[1]["ms"]):
+            tensor = v["flops"] > 0 and name in ("conv_igemm", "attention")
+            ach = (v["flops"] / v["ms"] / 1e9) if tensor else (v["bytes"] / v["ms"] / 1e6)
+            peak = pk["tensor"] if tensor else pk["hbm"]
+            entry = {"kernel": name, "bound": "tensor" if tensor else "hbm", "achieved": ach, "peak": peak,
+                     "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak, "traffic": traffic_note(name),
+                     "launches_per_denoise_step": v["launches"], "ms_per_denoise_step": v["ms"],
+                     "share_of_step": (v["ms"] / total_ms) if name != "sampler_update" else None,
+                     "peak_source": pk["source"] + (" (sustained)" if tensor else " (copy)")}
+            aux.append(entry)
+        dom = next(e for e in aux if e["kernel"] == "conv_igemm")
+        res["roofline"] = {k: dom[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
+        res["roofline"].update({"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM)", "peak_source": dom["peak_source"],
+                                "share_of_step": dom["share_of_step"],
+                                "how": "sum of algorithmic conv FLOPs of one denoising step / sum of per-launch "
+                                       "CUDA-event durations on the launching stream"})
+        res["roofline_aux"] = aux
+        res["kernel_pass_ms_per_denoise_step"] = total_ms
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import dsdiff_oracle as O
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
+        step, (c1, x1, ts) = oracle_step_fn(wl, sd, size)
+        t0 = time.perf_counter()
+        ref_out, _ = step()
+        dt = time.perf_counter() - t0
+        with quiet, torch.no_grad():
+            got = net(torch.cat([x1, c1], 1).to(dev), ts.to(dev))
+            got = (got[0] if isinstance(got, tuple) else got).cpu()
+        res["cpu_baseline"] = {
+            "value": 1.0 / (DDIM_STEPS * dt), "unit": "slices/s", "cores": cores, "kind": "port",
+            "sample": f"one denoising step (oracle network forward + DDIM update) of one {size}x{size} slice, "
+                      f"{dt:.1f} s, un-warmed, x{DDIM_STEPS} extrapolated"}
+        res["parity"] = {"net_out_rel_l2_vs_oracle_fp32": O.rel_err(got, ref_out),
+                         "note": "same weights/input as the cpu_baseline sample; 16-bit operands vs pure fp32"}
+    if rank == 0:
+        print(json.dumps(res))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
