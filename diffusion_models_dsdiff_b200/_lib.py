@@ -42,6 +42,15 @@ class SamplerDesc(C.Structure):
                 ("x_prev", C.c_void_p), ("pred_x0", C.c_void_p)]
 
 
+class AttnDesc(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("out", C.c_void_p),
+                ("B", C.c_int), ("Lq", C.c_int), ("Lk", C.c_int), ("heads", C.c_int), ("d", C.c_int),
+                ("ldq", C.c_int), ("ldk", C.c_int), ("ldv", C.c_int), ("ldo", C.c_int),
+                ("q_off", C.c_int), ("k_off", C.c_int), ("v_off", C.c_int),
+                ("q_hstride", C.c_int), ("k_hstride", C.c_int), ("v_hstride", C.c_int),
+                ("scale", C.c_float), ("act_dtype", C.c_int), ("force_simt", C.c_int)]
+
+
 _P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64
 # name -> argtypes (all return int unless listed in _RESTYPE); mirrors include/b200diff.h
 SIGNATURES = {
@@ -57,7 +66,10 @@ SIGNATURES = {
     "b200_conv3x3_out": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_groupnorm_stats": [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P],
     "b200_groupnorm_apply": [_P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _I, _I, _P, _I, _P],
+    "b200_channel_stats": [_P, _I, _I, _I, _P, _I, _P],
+    "b200_groupnorm_apply_cs": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _I, _I, _P, _I, _P],
     "b200_attention_qkv": [_P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
+    "b200_attention": [C.POINTER(AttnDesc), _P],
     "b200_timestep_embedding": [_P, _P, _P, _P, _I, _I, _P],
     "b200_linear_f32": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "b200_upsample_nearest2x": [_P, _P, _I, _I, _I, _I, _I, _P],

@@ -2,6 +2,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -48,7 +52,7 @@ static int resolve_driver() {
 }
 
 int encode_tmap(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes,
-                const uint32_t *box, const uint32_t *elem_strides) {
+                const uint32_t *box, const uint32_t *elem_strides, bool swizzle128) {
   if (int rc = resolve_driver()) return rc;
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
@@ -56,7 +60,7 @@ int encode_tmap(CUtensorMap *map, const void *base, int rank, const uint64_t *di
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   // 16-bit elements either way (fp16 / bf16): the type only matters for OOB fill, which is zero.
   CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx,
-                        es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (CUresult %d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u] "
@@ -68,6 +72,34 @@ int encode_tmap(CUtensorMap *map, const void *base, int rank, const uint64_t *di
               (unsigned long long)strides_bytes[0], base);
     return 4;
   }
+  return 0;
+}
+
+namespace {
+std::mutex g_tmap_mu;
+std::unordered_map<std::string, CUtensorMap> g_tmap_cache;
+}  // namespace
+
+// Descriptor encoding costs microseconds on the host; layers are launched with the same buffers every step
+// (always under CUDA-graph replay, usually also eagerly), so descriptors are cached by their full definition.
+int cached_tmap(CUtensorMap *out, const void *base, int rank, const uint64_t *dims, const uint64_t *strides,
+                const uint32_t *box, const uint32_t *estr, bool swizzle128) {
+  std::string key(reinterpret_cast<const char *>(&base), sizeof(base));
+  key.append(reinterpret_cast<const char *>(&rank), sizeof(rank));
+  key.append(reinterpret_cast<const char *>(dims), sizeof(uint64_t) * rank);
+  key.append(reinterpret_cast<const char *>(strides), sizeof(uint64_t) * (rank - 1));
+  key.append(reinterpret_cast<const char *>(box), sizeof(uint32_t) * rank);
+  key.append(reinterpret_cast<const char *>(estr), sizeof(uint32_t) * rank);
+  key.push_back(swizzle128 ? 1 : 0);
+  std::lock_guard<std::mutex> lk(g_tmap_mu);
+  auto it = g_tmap_cache.find(key);
+  if (it != g_tmap_cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  if (int rc = encode_tmap(out, base, rank, dims, strides, box, estr, swizzle128)) return rc;
+  if (g_tmap_cache.size() > 200000) g_tmap_cache.clear();
+  g_tmap_cache.emplace(std::move(key), *out);
   return 0;
 }
 

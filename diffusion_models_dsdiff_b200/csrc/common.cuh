@@ -215,6 +215,43 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// make generic-proxy shared-memory writes visible to the async proxy (TMA / tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// Un-swizzled ("interleaved") operand tile made of 8-row x 16-byte core matrices (128 contiguous bytes each).
+// lbo = byte distance between core matrices adjacent along K, sbo = along M/N.  Valid for K-major operands
+// ([row][8 elems] core rows) and MN-major ones ([k][8 mn-elems] core rows) alike.
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo & 0x3FFFF) >> 4) << 16;
+  d |= (uint64_t)((sbo & 0x3FFFF) >> 4) << 32;
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  return d;                               // layout_type 0 = SWIZZLE_NONE
+}
+
 // K-major, 128B-swizzled operand tile: rows of 64 x 16-bit (=128 B), 8-row atoms 1024 B apart.
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48)
 //  | layout_type [61,64) with SWIZZLE_128B = 2.)
@@ -228,8 +265,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 // cute::UMMA::InstrDescriptor for kind::f16, fp32 accumulate, both operands K-major.
-__host__ __device__ inline uint32_t umma_idesc(int fmt /*0 f16, 1 bf16*/, int M, int N) {
+__host__ __device__ inline uint32_t umma_idesc(int fmt /*0 f16, 1 bf16*/, int M, int N, int b_mn_major = 0) {
   uint32_t d = 0;
+  d |= (uint32_t)(b_mn_major & 1) << 16;  // b_major: 0 = K-major, 1 = MN-major
   d |= 1u << 4;                       // c_format = F32
   d |= (uint32_t)fmt << 7;            // a_format
   d |= (uint32_t)fmt << 10;           // b_format
@@ -243,6 +281,9 @@ __host__ __device__ inline uint32_t umma_idesc(int fmt /*0 f16, 1 bf16*/, int M,
 // ------------------------------------------------------------------------------------------
 int encode_tmap(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
                 const uint64_t *strides_bytes /*rank-1*/, const uint32_t *box,
-                const uint32_t *elem_strides);
+                const uint32_t *elem_strides, bool swizzle128 = true);
+int cached_tmap(CUtensorMap *map, const void *base, int rank, const uint64_t *dims,
+                const uint64_t *strides_bytes, const uint32_t *box, const uint32_t *elem_strides,
+                bool swizzle128 = true);
 
 }  // namespace b200

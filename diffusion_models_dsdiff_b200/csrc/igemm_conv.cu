@@ -6,10 +6,6 @@
 //   M = 128 output pixels (a TW x TH x TN box), N = BN output channels (<= 256), K chunk = 64 channels.
 //
 // Replaces F.conv2d at the call sites listed in include/b200diff.h (b200_conv2d_igemm).
-#include <mutex>
-#include <string>
-#include <unordered_map>
-
 #include "common.cuh"
 
 namespace b200 {
@@ -43,9 +39,44 @@ struct ConvKParams {
   const void *residual;
   float res_scale;
   void *out;
-  float *gn_sums;
+  double *gn_sums;
   uint32_t idesc;
 };
+
+// Column sums of a 32 (lanes) x 16 (registers) tile by recursive halving: 16 shuffles instead of 16 x 5.
+// Returns on every lane the total of column (lane >> 1).
+__device__ __forceinline__ float warp_colsum16(const float (&a)[16], int lane) {
+  float b[8];
+  const bool h16 = lane & 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float keep = h16 ? a[i + 8] : a[i];
+    const float send = h16 ? a[i] : a[i + 8];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  float c[4];
+  const bool h8 = lane & 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = h8 ? b[i + 4] : b[i];
+    const float send = h8 ? b[i] : b[i + 4];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float d[2];
+  const bool h4 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = h4 ? c[i + 2] : c[i];
+    const float send = h4 ? c[i] : c[i + 2];
+    d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const bool h2 = lane & 2;
+  const float keep = h2 ? d[1] : d[0];
+  const float send = h2 ? d[0] : d[1];
+  float e = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  e += __shfl_xor_sync(0xffffffffu, e, 1);
+  return e;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -171,7 +202,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       const int w = (pt % p.tiles_w) * p.TW + tw;
       pt /= p.tiles_w;
       const int h = (pt % p.tiles_h) * p.TH + th;
-      const int n = (pt / p.tiles_h) * p.TN + tn;
+      const int n0 = (pt / p.tiles_h) * p.TN;
+      const int n = n0 + tn;
+      const int n_warp = n0 + lane_base / (p.TW * p.TH);
       const bool valid = (w < p.Wout) && (h < p.Hout) && (n < p.N);
       const size_t pix = ((size_t)n * p.Hout + h) * p.Wout + w;
       mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
@@ -182,36 +215,54 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
         tmem_ld16(taddr + c, r);
         tmem_ld_wait();
         const int co = n_tile * p.BN + c;
-        if (valid) {
+        float v[16];
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int cb = co + half * 8;
-            if (cb < p.Cout) {
-              float v[8];
+        for (int half = 0; half < 2; ++half) {
+          const int cb = co + half * 8;
+          float (&vh)[8] = *reinterpret_cast<float (*)[8]>(v + half * 8);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[half * 8 + i]);
-              if (p.bias) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + cb));
-                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + cb + 4));
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
-              if (p.rowbias) {
-                const float *rb = p.rowbias + (size_t)n * p.rowbias_stride + cb;
-                const float4 b0 = __ldg(reinterpret_cast<const float4 *>(rb));
-                const float4 b1 = __ldg(reinterpret_cast<const float4 *>(rb + 4));
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
-              if (res) {
-                const uint4 ru = *reinterpret_cast<const uint4 *>(res + pix * p.Cout + cb);
-                float rf[8];
-                unpack8<T>(ru, rf);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += p.res_scale * rf[i];
-              }
-              *reinterpret_cast<uint4 *>(out + pix * p.Cout + cb) = pack8<T>(v);
+          for (int i = 0; i < 8; ++i) vh[i] = __uint_as_float(r[half * 8 + i]);
+          const bool live = valid && cb < p.Cout;
+          if (live) {
+            if (p.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + cb));
+              const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + cb + 4));
+              vh[0] += b0.x; vh[1] += b0.y; vh[2] += b0.z; vh[3] += b0.w;
+              vh[4] += b1.x; vh[5] += b1.y; vh[6] += b1.z; vh[7] += b1.w;
             }
+            if (p.rowbias) {
+              const float *rb = p.rowbias + (size_t)n * p.rowbias_stride + cb;
+              const float4 b0 = __ldg(reinterpret_cast<const float4 *>(rb));
+              const float4 b1 = __ldg(reinterpret_cast<const float4 *>(rb + 4));
+              vh[0] += b0.x; vh[1] += b0.y; vh[2] += b0.z; vh[3] += b0.w;
+              vh[4] += b1.x; vh[5] += b1.y; vh[6] += b1.z; vh[7] += b1.w;
+            }
+            if (res) {
+              const uint4 ru = *reinterpret_cast<const uint4 *>(res + pix * p.Cout + cb);
+              float rf[8];
+              unpack8<T>(ru, rf);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) vh[i] += p.res_scale * rf[i];
+            }
+            *reinterpret_cast<uint4 *>(out + pix * p.Cout + cb) = pack8<T>(vh);
+          } else if (p.gn_sums) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vh[i] = 0.f;
+          }
+        }
+        if (p.gn_sums) {
+          // per-channel (sum, sum of squares) over this warp's 32 pixels for a following GroupNorm; the 32 rows of a
+          // warp lie in ONE image (the host enables the fused statistics only when TW*TH >= 32)
+          float q[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) q[i] = v[i] * v[i];
+          const float s_tot = warp_colsum16(v, lane);
+          const float q_tot = warp_colsum16(q, lane);
+          const int ch = co + (lane >> 1);
+          if ((lane & 1) == 0 && ch < p.Cout && n_warp < p.N) {
+            double *dst = p.gn_sums + ((size_t)n_warp * p.Cout + ch) * 2;
+            atomicAdd(dst, (double)s_tot);
+            atomicAdd(dst + 1, (double)q_tot);
           }
         }
       }
@@ -233,29 +284,6 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
 // host side
 // ------------------------------------------------------------------------------------------
 namespace {
-std::mutex g_tmap_mu;
-std::unordered_map<std::string, CUtensorMap> g_tmap_cache;
-
-int cached_tmap(CUtensorMap *out, const void *base, int rank, const uint64_t *dims,
-                const uint64_t *strides, const uint32_t *box, const uint32_t *estr) {
-  std::string key(reinterpret_cast<const char *>(&base), sizeof(base));
-  key.append(reinterpret_cast<const char *>(&rank), sizeof(rank));
-  key.append(reinterpret_cast<const char *>(dims), sizeof(uint64_t) * rank);
-  key.append(reinterpret_cast<const char *>(strides), sizeof(uint64_t) * (rank - 1));
-  key.append(reinterpret_cast<const char *>(box), sizeof(uint32_t) * rank);
-  key.append(reinterpret_cast<const char *>(estr), sizeof(uint32_t) * rank);
-  std::lock_guard<std::mutex> lk(g_tmap_mu);
-  auto it = g_tmap_cache.find(key);
-  if (it != g_tmap_cache.end()) {
-    *out = it->second;
-    return 0;
-  }
-  if (int rc = encode_tmap(out, base, rank, dims, strides, box, estr)) return rc;
-  if (g_tmap_cache.size() > 200000) g_tmap_cache.clear();
-  g_tmap_cache.emplace(std::move(key), *out);
-  return 0;
-}
-
 int pow2_ceil(int v) {
   int r = 1;
   while (r < v) r <<= 1;
@@ -279,15 +307,16 @@ static int launch_conv(const b200_conv_desc *d, cudaStream_t stream) {
   p.nseg = d->nseg;
   p.BN = pick_bn(d->Cout);
   p.n_ntiles = cdiv(d->Cout, p.BN);
-  // pixel box: TW x TH x TN == 128, minimise the number of tiles
+  // pixel box: TW x TH x TN == 128.  The box is chosen from (Hout, Wout) ONLY — never from N — so that the result
+  // for one image is bit-identical whatever batch it is part of (slices are independent units):
+  // minimise the padded area of one image, prefer 16-wide boxes on ties (square-ish halo => better L2 locality).
   long best = -1;
   for (int tw = 32; tw >= 1; tw >>= 1) {
     int th = std::min(pow2_ceil(d->Hout), kBM / tw);
     int tn = kBM / (tw * th);
-    long tiles = (long)cdiv(d->Wout, tw) * cdiv(d->Hout, th) * cdiv(d->N, tn);
-    // prefer 16-wide boxes on ties (square-ish halo => better L2 locality)
-    if (best < 0 || tiles < best || (tiles == best && tw == 16)) {
-      best = tiles; p.TW = tw; p.TH = th; p.TN = tn;
+    long area = (long)cdiv(d->Wout, tw) * tw * cdiv(d->Hout, th) * th;
+    if (best < 0 || area < best || (area == best && tw == 16)) {
+      best = area; p.TW = tw; p.TH = th; p.TN = tn;
     }
   }
   p.tiles_w = cdiv(d->Wout, p.TW);
@@ -295,7 +324,10 @@ static int launch_conv(const b200_conv_desc *d, cudaStream_t stream) {
   p.tiles_n = cdiv(d->N, p.TN);
   p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_ntiles;
   p.bias = d->bias; p.rowbias = d->rowbias; p.rowbias_stride = d->rowbias_stride;
-  p.residual = d->residual; p.res_scale = d->res_scale; p.out = d->out; p.gn_sums = d->gn_sums;
+  p.residual = d->residual; p.res_scale = d->res_scale; p.out = d->out;
+  // fused statistics need every epilogue warp (32 consecutive box rows) inside one image; tinier maps (< 32 pixels)
+  // take the standalone kernel below — a choice that depends on the map size only, not on N
+  p.gn_sums = (p.TW * p.TH >= 32) ? d->gn_sums : nullptr;
   p.idesc = umma_idesc(Act<T>::kFmt, kBM, p.BN);
   const size_t stage_bytes = (size_t)kABytes + (size_t)p.BN * 128;
   p.stages = (int)std::min<size_t>(kMaxStages, (200 * 1024) / stage_bytes);
@@ -334,6 +366,8 @@ static int launch_conv(const b200_conv_desc *d, cudaStream_t stream) {
   const int grid = std::min(p.num_tiles, num_sms());
   conv_igemm_kernel<T><<<grid, kConvThreads, smem, stream>>>(maps, p);
   B200_LAUNCH_CHECK();
+  if (d->gn_sums && !p.gn_sums)
+    return b200_channel_stats(d->out, d->N, d->Hout * d->Wout, d->Cout, d->gn_sums, d->act_dtype, stream);
   return 0;
 }
 
@@ -346,7 +380,6 @@ extern "C" int b200_conv2d_igemm(const b200_conv_desc *d, void *stream) {
   B200_CHECK(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2");
   B200_CHECK(d->Cout % 8 == 0, "conv: Cout must be a multiple of 8 (got %d)", d->Cout);
   B200_CHECK(d->N > 0 && d->Hout > 0 && d->Wout > 0, "conv: empty output");
-  B200_CHECK(d->gn_sums == nullptr, "conv: gn_sums epilogue not implemented");
   if (d->act_dtype == B200_F16) return launch_conv<__half>(d, (cudaStream_t)stream);
   if (d->act_dtype == B200_BF16) return launch_conv<__nv_bfloat16>(d, (cudaStream_t)stream);
   B200_CHECK(false, "conv: bad act_dtype %d", d->act_dtype);

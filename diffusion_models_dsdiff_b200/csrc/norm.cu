@@ -83,11 +83,54 @@ gn_stats_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
   }
 }
 
+// Per-(image, channel) sum and sum of squares -> sums[N][C][2] (fp64, accumulated: zero it first).  Same thread
+// mapping as gn_stats_kernel; used for tensors whose producer has no fused statistics epilogue.
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+channel_stats_kernel(const T *__restrict__ x, int C, int HW, int pix_per_block, double *__restrict__ sums) {
+  const int n = blockIdx.y;
+  const int ncol = C >> 3;
+  const int rows = kNormThreads / ncol;
+  const int col = threadIdx.x % ncol;
+  const int row = threadIdx.x / ncol;
+  if (row >= rows) return;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(HW, p_begin + pix_per_block);
+  float s[8] = {0}, q[8] = {0};
+  const T *base = x + (size_t)n * HW * C + col * 8;
+  int p = p_begin + row;
+  for (; p + 3 * rows < p_end; p += 4 * rows) {
+    uint4 u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = ld_stream(base + (size_t)(p + j * rows) * C);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f[8];
+      unpack8<T>(u[j], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+    }
+  }
+  for (; p < p_end; p += rows) {
+    float f[8];
+    unpack8<T>(ld_stream(base + (size_t)p * C), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+  }
+  double *dst = sums + ((size_t)n * C + col * 8) * 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    atomicAdd(dst + 2 * i, (double)s[i]);
+    atomicAdd(dst + 2 * i + 1, (double)q[i]);
+  }
+}
+
 // y = silu?( (x - mean_g) * rstd_g * gamma_c + beta_c ) [ * (1 + scale_nc) + shift_nc ]
 template <typename T>
 __global__ void __launch_bounds__(kNormThreads)
 gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int C1, int HW,
                 int groups, float eps, int pix_per_block, const double *__restrict__ stats,
+                const double *__restrict__ cs0, const double *__restrict__ cs1,
                 const float *__restrict__ gamma, const float *__restrict__ beta,
                 const float *__restrict__ film, int film_stride, int silu, T *__restrict__ out) {
   __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
@@ -96,8 +139,19 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
   const int cpg = C / groups;
   const double cnt = (double)HW * (double)cpg;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    const double m = stats[((size_t)n * groups + g) * 2 + 0] / cnt;
-    double var = stats[((size_t)n * groups + g) * 2 + 1] / cnt - m * m;
+    double sum, sq;
+    if (stats) {
+      sum = stats[((size_t)n * groups + g) * 2 + 0];
+      sq = stats[((size_t)n * groups + g) * 2 + 1];
+    } else {   // per-channel sums written by the producers' epilogues (conv / add4 / channel_stats)
+      sum = 0.0; sq = 0.0;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        const double *src = c < C0 ? cs0 + ((size_t)n * C0 + c) * 2 : cs1 + ((size_t)n * C1 + (c - C0)) * 2;
+        sum += src[0]; sq += src[1];
+      }
+    }
+    const double m = sum / cnt;
+    double var = sq / cnt - m * m;
     if (var < 0.0) var = 0.0;
     s_mean[g] = (float)m;
     s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
@@ -184,13 +238,13 @@ static int gn_stats(const void *x0, int C0, const void *x1, int C1, int N, int H
 
 template <typename T>
 static int gn_apply(const void *x0, int C0, const void *x1, int C1, int N, int HW, int groups,
-                    float eps, const double *stats, const float *gamma, const float *beta,
-                    const float *film, int film_stride, int silu, void *out, cudaStream_t st) {
+                    float eps, const double *stats, const double *cs0, const double *cs1, const float *gamma,
+                    const float *beta, const float *film, int film_stride, int silu, void *out, cudaStream_t st) {
   dim3 grid;
   int ppb;
   norm_grid(N, HW, (C0 + C1) >> 3, &grid, &ppb);
   gn_apply_kernel<T><<<grid, kNormThreads, 0, st>>>((const T *)x0, C0, (const T *)x1, C1, HW, groups,
-                                                   eps, ppb, stats, gamma, beta, film, film_stride,
+                                                   eps, ppb, stats, cs0, cs1, gamma, beta, film, film_stride,
                                                    silu, (T *)out);
   B200_LAUNCH_CHECK();
   return 0;
@@ -224,8 +278,39 @@ extern "C" int b200_groupnorm_apply(const void *x0, int C0, const void *x1, int 
   if (x1 == nullptr) C1 = 0;
   if (int rc = check_gn(C0, C1, N, HW, groups)) return rc;
   if (act_dtype == B200_F16)
-    return gn_apply<__half>(x0, C0, x1, C1, N, HW, groups, eps, stats, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream);
+    return gn_apply<__half>(x0, C0, x1, C1, N, HW, groups, eps, stats, nullptr, nullptr, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream);
   if (act_dtype == B200_BF16)
-    return gn_apply<__nv_bfloat16>(x0, C0, x1, C1, N, HW, groups, eps, stats, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream);
+    return gn_apply<__nv_bfloat16>(x0, C0, x1, C1, N, HW, groups, eps, stats, nullptr, nullptr, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream);
   B200_CHECK(false, "groupnorm: bad act_dtype");
+}
+
+extern "C" int b200_groupnorm_apply_cs(const void *x0, int C0, const double *cs0, const void *x1, int C1,
+                                       const double *cs1, int N, int HW, int groups, float eps, const float *gamma,
+                                       const float *beta, const float *film, int film_stride, int silu, void *out,
+                                       int act_dtype, void *stream) {
+  using namespace b200;
+  if (x1 == nullptr) C1 = 0;
+  if (int rc = check_gn(C0, C1, N, HW, groups)) return rc;
+  B200_CHECK(cs0 != nullptr && (C1 == 0 || cs1 != nullptr), "groupnorm_apply_cs: missing channel sums");
+  if (act_dtype == B200_F16)
+    return gn_apply<__half>(x0, C0, x1, C1, N, HW, groups, eps, nullptr, cs0, cs1, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream);
+  if (act_dtype == B200_BF16)
+    return gn_apply<__nv_bfloat16>(x0, C0, x1, C1, N, HW, groups, eps, nullptr, cs0, cs1, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream);
+  B200_CHECK(false, "groupnorm: bad act_dtype");
+}
+
+extern "C" int b200_channel_stats(const void *x, int N, int HW, int C, double *sums, int act_dtype, void *stream) {
+  using namespace b200;
+  B200_CHECK(x && sums && N > 0 && HW > 0 && C > 0 && C % 8 == 0 && C <= 8 * kNormThreads, "channel_stats: bad arguments");
+  dim3 grid;
+  int ppb;
+  norm_grid(N, HW, C >> 3, &grid, &ppb);
+  if (act_dtype == B200_F16)
+    channel_stats_kernel<__half><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>((const __half *)x, C, HW, ppb, sums);
+  else if (act_dtype == B200_BF16)
+    channel_stats_kernel<__nv_bfloat16><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x, C, HW, ppb, sums);
+  else
+    B200_CHECK(false, "channel_stats: bad act_dtype");
+  B200_LAUNCH_CHECK();
+  return 0;
 }

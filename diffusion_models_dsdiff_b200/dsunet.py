@@ -21,7 +21,8 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .unet import (_EngineModule, _f, _gn, build_unet_trunk, run_in_conv, run_out_head, run_sequential)
+from .unet import (Act, Ctx, _EngineModule, _f, _gn, build_unet_trunk, run_conv, run_gn, run_in_conv, run_out_head,
+                   run_sequential)
 
 Tensor = torch.Tensor
 
@@ -67,19 +68,20 @@ class DSUnetModel(_EngineModule):
         self._init_engine()
 
     # FeatureDisentangle.forward (:165-168): conv_2(conv_1(x) + x)
-    def _fd(self, pw, m: FeatureDisentangle, x: Tensor) -> Tensor:
+    def _fd(self, cx: Ctx, m: FeatureDisentangle, x: Act) -> Tensor:
+        pw = cx.pw
         g1, c1, g2, c2 = m.conv_1[0], m.conv_1[2], m.conv_2[0], m.conv_2[2]
-        a = ops.group_norm(x, _f(g1.weight), _f(g1.bias), eps=g1.eps, silu=True)
-        out = ops.conv2d([(a, pw.conv[id(c1)], 0, 3, 1)], bias=_f(c1.bias), residual=x)
-        a2 = ops.group_norm(out, _f(g2.weight), _f(g2.bias), eps=g2.eps, silu=True)
+        a = run_gn(cx, g1, x)
+        out = run_conv(cx, [(a, pw.conv[id(c1)], 0, 3, 1)], bias=_f(c1.bias), residual=x.t)
+        a2 = run_gn(cx, g2, out)
         return ops.conv2d([(a2, pw.conv[id(c2)], 0, 1, 0)], bias=_f(c2.bias))
 
     # mean of a feature family -> SE_Attention -> 3x3 conv (:722-725)
-    def _proj(self, pw, seq: nn.Sequential, feats) -> Tensor:
+    def _proj(self, cx: Ctx, seq: nn.Sequential, feats) -> Tensor:
         mean = ops.add4_scale(*feats, *([None] * (4 - len(feats))), scale=1.0 / len(feats))
         se, conv = seq[0].se, seq[1]
         gated = ops.se_attention(mean, _f(se[0].weight), _f(se[2].weight))
-        return ops.conv2d([(gated, pw.conv[id(conv)], 0, 3, 1)], bias=_f(conv.bias))
+        return ops.conv2d([(gated, cx.pw.conv[id(conv)], 0, 3, 1)], bias=_f(conv.bias))
 
     @torch.no_grad()
     def forward(self, x, timesteps=None, context=None, y=None, step_ptr: Optional[Tensor] = None,
@@ -92,6 +94,8 @@ class DSUnetModel(_EngineModule):
         n = x.shape[0]
         t_table = timesteps.to(torch.float32).contiguous() if step_ptr is not None else self._t_table(timesteps, n)
         _, emb_all = self._temb(pw, self.time_embed, t_table, n, step_ptr)
+        self._arena.begin(x.device)
+        cx = Ctx(pw, emb_all, self._arena)
         x = x.float()
         if x.shape[1] == 2:       # :654-658
             zero = torch.zeros_like(x[:, 0:1])
@@ -101,32 +105,33 @@ class DSUnetModel(_EngineModule):
         skips, last = [], []
         for blocks, xin in zip((self.input_blocks, self.input_blocks_a, self.input_blocks_al, self.input_blocks_l),
                                inputs):
-            h = run_in_conv(pw, blocks[0][0], xin.contiguous(), self.act_dtype)
+            h = run_in_conv(cx, blocks[0][0], xin.contiguous(), self.act_dtype)
             hs = [h]
             for blk in list(blocks)[1:]:
-                h = run_sequential(pw, blk, h, None, emb_all)
+                h = run_sequential(cx, blk, h, None)
                 hs.append(h)
             skips.append(hs)
             last.append(h)
-        h_n = run_sequential(pw, self.middle_block, last[0], None, emb_all)     # :688
+        h_n = run_sequential(cx, self.middle_block, last[0], None)     # :688
         h_a, h_al, h_l = last[1], last[2], last[3]
-        fd = lambda m, v: self._fd(pw, m, v)
+        fd = lambda m, v: self._fd(cx, m, v)
         h_n_style, h_n_content = fd(self.conv_style, h_n), fd(self.conv_content, h_n)
         style = [fd(self.conv_style, v) for v in (h_a, h_al, h_l)]
         content = [fd(self.conv_content, v) for v in (h_a, h_al, h_l)]
         anatomy = [fd(self.conv_anatomy, v) for v in (h_a, h_al)]
         lesion = [fd(self.conv_lesion, v) for v in (h_al, h_l)]
-        h_style = self._proj(pw, self.style_proj, style)
-        h_share = self._proj(pw, self.share_content_proj, content)
-        h_anat = self._proj(pw, self.anatomy_proj, anatomy)
-        h_les = self._proj(pw, self.lesion_proj, lesion)
-        cat = torch.cat([h_n, h_share, h_style, h_anat, h_les], dim=-1)            # :734 (8x8 maps: tiny)
+        h_style = self._proj(cx, self.style_proj, style)
+        h_share = self._proj(cx, self.share_content_proj, content)
+        h_anat = self._proj(cx, self.anatomy_proj, anatomy)
+        h_les = self._proj(cx, self.lesion_proj, lesion)
+        cat = torch.cat([h_n.t, h_share, h_style, h_anat, h_les], dim=-1)          # :734 (8x8 maps: tiny)
         ap = self.all_proj[1]
-        h = ops.conv2d([(ops.add4_scale(cat, silu=True), pw.conv[id(ap)], 0, 1, 0)], bias=_f(ap.bias))   # :738
+        h = run_conv(cx, [(ops.add4_scale(cat, silu=True), pw.conv[id(ap)], 0, 1, 0)], bias=_f(ap.bias))   # :738
         for blk in self.output_blocks:
-            skip = ops.add4_scale(skips[0].pop(), skips[1].pop(), skips[2].pop(), skips[3].pop(), scale=0.25)  # :745
-            h = run_sequential(pw, blk, h, skip, emb_all)
-        out = run_out_head(pw, self.out, h).to(x.dtype)
+            skip = Act(ops.add4_scale(skips[0].pop().t, skips[1].pop().t, skips[2].pop().t, skips[3].pop().t,
+                                      scale=0.25))                                                       # :745
+            h = run_sequential(cx, blk, h, skip)
+        out = run_out_head(cx, self.out, h).to(x.dtype)
         if not return_features:
             return out, None
         to = ops.nhwc_to_nchw

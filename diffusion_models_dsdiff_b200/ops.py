@@ -133,7 +133,7 @@ Seg = Tuple[Tensor, Tensor, int, int, int]  # (src NHWC, packed weight, coff, ks
 
 def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
            rowbias: Optional[Tensor] = None, residual: Optional[Tensor] = None, res_scale: float = 1.0,
-           out: Optional[Tensor] = None) -> Tensor:
+           out: Optional[Tensor] = None, stats: Optional[Tensor] = None) -> Tensor:
     """tcgen05 implicit-GEMM conv over up to 3 K-segments (see b200_conv2d_igemm)."""
     src0, w0, _, k0, p0 = segs[0]
     _dev(src0)
@@ -163,7 +163,9 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
     d.residual = _p(residual)
     d.res_scale = res_scale
     d.out = _p(out)
-    d.gn_sums = None
+    if stats is not None and (stats.dtype != torch.float64 or stats.numel() != n * cout * 2):
+        raise L.B200Error("conv2d: stats must be a zeroed float64 [N, Cout, 2] tensor")
+    d.gn_sums = _p(stats)
     d.act_dtype = act_code(src0.dtype)
     kk = sum(sg[0].shape[3] * sg[3] * sg[3] for sg in segs)
     flops = 2.0 * n * hout * wout * cout * kk
@@ -199,24 +201,74 @@ def conv3x3_out(x: Tensor, w_oihw: Tensor, bias: Optional[Tensor]) -> Tensor:
 # ---------------------------------------------------------------------------------------------
 # normalisation
 # ---------------------------------------------------------------------------------------------
+class StatsArena:
+    """Bump allocator for the per-(image, channel) fp64 statistics buffers of one network forward: ONE memset at
+    ``begin`` instead of one per GroupNorm.  Buffers that were ever handed out stay alive (captured CUDA graphs keep
+    raw pointers to them)."""
+
+    def __init__(self):
+        self.buf: Optional[Tensor] = None
+        self.off = 0
+        self.retired = []
+
+    def begin(self, device) -> None:
+        if self.buf is None or self.buf.device != device:
+            if self.buf is not None:
+                self.retired.append(self.buf)
+            self.buf = torch.zeros(1 << 18, dtype=torch.float64, device=device)
+        else:
+            self.buf.zero_()
+        self.off = 0
+
+    def take(self, n: int, c: int) -> Tensor:
+        k = n * c * 2
+        if self.off + k > self.buf.numel():
+            self.retired.append(self.buf)
+            self.buf = torch.zeros(max(2 * self.buf.numel(), 4 * k), dtype=torch.float64, device=self.buf.device)
+            self.off = 0
+        v = self.buf[self.off:self.off + k].view(n, c, 2)
+        self.off += k
+        return v
+
+
+def channel_stats(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """sums[N, C, 2] fp64 = per-(image, channel) (sum, sum of squares) of an NHWC activation."""
+    _dev(x)
+    n, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (n * c)
+    if out is None:
+        out = torch.zeros((n, c, 2), device=x.device, dtype=torch.float64)
+    _timed("channel_stats", 0.0, 2.0 * x.numel(),
+           lambda: L.check(L.lib().b200_channel_stats(_p(x), n, hw, c, _p(out), act_code(x.dtype), _stream()),
+                           "channel_stats"))
+    return out
+
+
 def group_norm(x0: Tensor, gamma: Tensor, beta: Tensor, x1: Optional[Tensor] = None, groups: int = 32,
                eps: float = 1e-5, silu: bool = True, film: Optional[Tensor] = None,
-               stats: Optional[Tensor] = None) -> Tensor:
+               stats: Optional[Tensor] = None, cs0: Optional[Tensor] = None, cs1: Optional[Tensor] = None) -> Tensor:
     """GroupNorm(+FiLM)(+SiLU) of the channel concatenation [x0 | x1]; NHWC in, NHWC out.
 
-    ``stats`` is an optional pre-zeroed fp64 workspace [N, groups, 2]."""
+    With ``cs0`` (and ``cs1`` when ``x1`` is given) — the producers' per-channel sums — this is ONE read + ONE write
+    pass; otherwise a statistics pass runs first (``stats``: optional pre-zeroed fp64 workspace [N, groups, 2])."""
     _dev(x0)
     n = x0.shape[0]
     hw = x0.numel() // (n * x0.shape[-1])
     c0 = x0.shape[-1]
     c1 = x1.shape[-1] if x1 is not None else 0
-    if stats is None:
-        stats = torch.zeros((n, groups, 2), device=x0.device, dtype=torch.float64)
     code = act_code(x0.dtype)
     lib = L.lib()
     out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=x0.dtype)
     film_p = None if film is None else film.data_ptr()
     film_s = 0 if film is None else film.stride(0)
+    if cs0 is not None and (x1 is None or cs1 is not None):
+        _timed("groupnorm_silu", 0.0, 2.0 * 2.0 * out.numel(),
+               lambda: L.check(lib.b200_groupnorm_apply_cs(_p(x0), c0, _p(cs0), _p(x1), c1, _p(cs1), n, hw, groups, eps,
+                                                           _p(_f32(gamma)), _p(_f32(beta)), film_p, film_s, int(silu),
+                                                           _p(out), code, _stream()), "groupnorm_apply_cs"))
+        return out
+    if stats is None:
+        stats = torch.zeros((n, groups, 2), device=x0.device, dtype=torch.float64)
 
     def launch():
         L.check(lib.b200_groupnorm_stats(_p(x0), c0, _p(x1), c1, n, hw, groups, _p(stats), code, _stream()),
@@ -243,6 +295,28 @@ def attention_qkv(qkv: Tensor, heads: int, new_order: bool) -> Tensor:
            lambda: L.check(L.lib().b200_attention_qkv(_p(qkv), _p(out), b, l, heads, ch, int(new_order),
                                                       float(ch) ** -0.5, act_code(qkv.dtype), _stream()),
                            "attention_qkv"))
+    return out
+
+
+def attention(q: Tensor, k: Tensor, v: Tensor, heads: int, d: int, scale: float, q_off: int = 0, k_off: int = 0,
+              v_off: int = 0, q_hstride: Optional[int] = None, k_hstride: Optional[int] = None,
+              v_hstride: Optional[int] = None, force_simt: bool = False) -> Tensor:
+    """General fused attention over token tensors q [B,Lq,ldq], k/v [B,Lk,ld*] (heads are channel slices)."""
+    _dev(q)
+    b, lq, ldq = q.shape
+    lk = k.shape[1]
+    out = torch.empty((b, lq, heads * d), device=q.device, dtype=q.dtype)
+    a = L.AttnDesc()
+    a.q, a.k, a.v, a.out = _p(q), _p(k), _p(v), _p(out)
+    a.B, a.Lq, a.Lk, a.heads, a.d = b, lq, lk, heads, d
+    a.ldq, a.ldk, a.ldv, a.ldo = ldq, k.shape[2], v.shape[2], heads * d
+    a.q_off, a.k_off, a.v_off = q_off, k_off, v_off
+    a.q_hstride = d if q_hstride is None else q_hstride
+    a.k_hstride = d if k_hstride is None else k_hstride
+    a.v_hstride = d if v_hstride is None else v_hstride
+    a.scale, a.act_dtype, a.force_simt = scale, act_code(q.dtype), int(force_simt)
+    _timed("attention", 4.0 * b * heads * lq * lk * d, 2.0 * (b * heads * d * (2 * lq + 2 * lk)),
+           lambda: L.check(L.lib().b200_attention(C.byref(a), _stream()), "attention"))
     return out
 
 

@@ -143,95 +143,140 @@ def _f(p: Tensor) -> Tensor:
     return t if t.dtype == torch.float32 and t.is_contiguous() else t.float().contiguous()
 
 
-def run_resblock(pw: PackedWeights, m: ResBlock, x0: Tensor, x1: Optional[Tensor], emb_all: Tensor) -> Tensor:
+class Act:
+    """An NHWC activation travelling through the engine together with its per-(image, channel) statistics
+    (``cs``: fp64 [N, C, 2], filled by the producing kernel's epilogue, or computed on first use)."""
+    __slots__ = ("t", "cs")
+
+    def __init__(self, t: Tensor, cs: Optional[Tensor] = None):
+        self.t, self.cs = t, cs
+
+
+class Ctx:
+    """Per-forward engine state: packed weights, the batched timestep projections, the statistics arena."""
+    __slots__ = ("pw", "emb_all", "arena")
+
+    def __init__(self, pw: PackedWeights, emb_all: Tensor, arena: "ops.StatsArena"):
+        self.pw, self.emb_all, self.arena = pw, emb_all, arena
+
+    def stats_for(self, n: int, c: int) -> Tensor:
+        return self.arena.take(n, c)
+
+
+def _cs(cx: Ctx, a: Act) -> Tensor:
+    if a.cs is None:      # producer without a statistics epilogue (first conv, skip mean): one extra read pass
+        a.cs = ops.channel_stats(a.t, cx.stats_for(a.t.shape[0], a.t.shape[-1]))
+    return a.cs
+
+
+def run_gn(cx: Ctx, gn: nn.GroupNorm, x0: Act, x1: Optional[Act] = None, silu: bool = True,
+           film: Optional[Tensor] = None) -> Tensor:
+    """GroupNorm32 (+SiLU / FiLM) of cat([x0, x1], C) in one read + one write pass."""
+    return ops.group_norm(x0.t, _f(gn.weight), _f(gn.bias), None if x1 is None else x1.t, groups=gn.num_groups,
+                          eps=gn.eps, silu=silu, film=film, cs0=_cs(cx, x0), cs1=None if x1 is None else _cs(cx, x1))
+
+
+def run_conv(cx: Ctx, segs, want_stats: bool = True, **kw) -> Act:
+    src0, w0 = segs[0][0], segs[0][1]
+    st = cx.stats_for(src0.shape[0], w0.shape[1]) if want_stats else None
+    return Act(ops.conv2d(segs, stats=st, **kw), st)
+
+
+def run_resblock(cx: Ctx, m: ResBlock, x0: Act, x1: Optional[Act]) -> Act:
     """ResBlock._forward (openaimodel.py:264-284) on NHWC activations; input = cat([x0, x1], C)."""
     if m.up or m.down:
         raise NotImplementedError("resblock_updown=True is not supported by the B200 engine yet")
+    pw = cx.pw
     gin, gout = m.in_layers[0], m.out_layers[0]
-    a = ops.group_norm(x0, _f(gin.weight), _f(gin.bias), x1, eps=gin.eps, silu=True)
+    a = run_gn(cx, gin, x0, x1)
     off, width = pw.emb_slices[id(m)]
-    emb_out = emb_all[:, off:off + width]
+    emb_out = cx.emb_all[:, off:off + width]
     conv1, conv2 = m.in_layers[2], m.out_layers[3]
     if m.use_scale_shift_norm:
-        h = ops.conv2d([(a, pw.conv[id(conv1)], 0, 3, 1)], bias=_f(conv1.bias))
-        a2 = ops.group_norm(h, _f(gout.weight), _f(gout.bias), eps=gout.eps, silu=True, film=emb_out)
+        h = run_conv(cx, [(a, pw.conv[id(conv1)], 0, 3, 1)], bias=_f(conv1.bias))
+        a2 = run_gn(cx, gout, h, film=emb_out)
     else:
-        h = ops.conv2d([(a, pw.conv[id(conv1)], 0, 3, 1)], bias=_f(conv1.bias), rowbias=emb_out)
-        a2 = ops.group_norm(h, _f(gout.weight), _f(gout.bias), eps=gout.eps, silu=True)
+        h = run_conv(cx, [(a, pw.conv[id(conv1)], 0, 3, 1)], bias=_f(conv1.bias), rowbias=emb_out)
+        a2 = run_gn(cx, gout, h)
     segs = [(a2, pw.conv[id(conv2)], 0, 3, 1)]
     residual = None
     sk = m.skip_connection
     if isinstance(sk, nn.Conv2d):
         ks = sk.kernel_size[0]
         wsk = pw.conv[id(sk)]
-        segs.append((x0, wsk, 0, ks, ks // 2))
+        segs.append((x0.t, wsk, 0, ks, ks // 2))
         if x1 is not None:
-            segs.append((x1, wsk, x0.shape[-1], ks, ks // 2))
+            segs.append((x1.t, wsk, x0.t.shape[-1], ks, ks // 2))
     else:
-        residual = x0 if x1 is None else torch.cat([x0, x1], dim=-1)
-    return ops.conv2d(segs, bias=pw.bias2[id(m)], residual=residual)
+        residual = x0.t if x1 is None else torch.cat([x0.t, x1.t], dim=-1)
+    return run_conv(cx, segs, bias=pw.bias2[id(m)], residual=residual)
 
 
-def run_attention(pw: PackedWeights, m: AttentionBlock, x: Tensor) -> Tensor:
+def run_attention(cx: Ctx, m: AttentionBlock, x: Act) -> Act:
     """AttentionBlock._forward (openaimodel.py:467-473)."""
-    n, h, w, c = x.shape
-    a = ops.group_norm(x, _f(m.norm.weight), _f(m.norm.bias), eps=m.norm.eps, silu=False)
+    pw = cx.pw
+    n, h, w, c = x.t.shape
+    a = run_gn(cx, m.norm, x, silu=False)
     qkv = ops.conv2d([(a, pw.conv[id(m.qkv)], 0, 1, 0)], bias=_f(m.qkv.bias))
     att = ops.attention_qkv(qkv.view(n, h * w, 3 * c), m.num_heads, m.use_new_attention_order)
-    return ops.conv2d([(att.view(n, h, w, c), pw.conv[id(m.proj_out)], 0, 1, 0)], bias=_f(m.proj_out.bias),
-                      residual=x)
+    return run_conv(cx, [(att.view(n, h, w, c), pw.conv[id(m.proj_out)], 0, 1, 0)], bias=_f(m.proj_out.bias),
+                    residual=x.t)
 
 
-def run_sequential(pw: PackedWeights, seq: nn.Sequential, x0: Tensor, x1: Optional[Tensor], emb_all: Tensor) -> Tensor:
+def run_sequential(cx: Ctx, seq: nn.Sequential, x0: Act, x1: Optional[Act]) -> Act:
     """TimestepEmbedSequential.forward (openaimodel.py:80-90)."""
+    pw = cx.pw
     for layer in seq:
         if isinstance(layer, ResBlock):
-            x0, x1 = run_resblock(pw, layer, x0, x1, emb_all), None
+            x0, x1 = run_resblock(cx, layer, x0, x1), None
             continue
         if x1 is not None:
-            x0, x1 = torch.cat([x0, x1], dim=-1), None
+            x0, x1 = Act(torch.cat([x0.t, x1.t], dim=-1)), None
         if isinstance(layer, AttentionBlock):
-            x0 = run_attention(pw, layer, x0)
+            x0 = run_attention(cx, layer, x0)
         elif isinstance(layer, Downsample):
             if not layer.use_conv:
                 raise NotImplementedError("Downsample(use_conv=False) is not supported by the B200 engine yet")
-            x0 = ops.conv2d([(x0, pw.conv[id(layer.op)], 0, 3, 1)], stride=2, bias=_f(layer.op.bias))
+            x0 = run_conv(cx, [(x0.t, pw.conv[id(layer.op)], 0, 3, 1)], stride=2, bias=_f(layer.op.bias))
         elif isinstance(layer, Upsample):
-            x0 = ops.upsample_nearest2x(x0)
+            x0 = Act(ops.upsample_nearest2x(x0.t))
             if layer.use_conv:
-                x0 = ops.conv2d([(x0, pw.conv[id(layer.conv)], 0, 3, 1)], bias=_f(layer.conv.bias))
+                x0 = run_conv(cx, [(x0.t, pw.conv[id(layer.conv)], 0, 3, 1)], bias=_f(layer.conv.bias))
         elif isinstance(layer, nn.Conv2d):
-            x0 = ops.conv2d([(x0, pw.conv[id(layer)], 0, layer.kernel_size[0], layer.padding[0])], bias=_f(layer.bias))
+            x0 = run_conv(cx, [(x0.t, pw.conv[id(layer)], 0, layer.kernel_size[0], layer.padding[0])],
+                          bias=_f(layer.bias))
         else:
             raise B200Error(f"B200 engine: unsupported layer {type(layer).__name__}")
     return x0
 
 
-def run_in_conv(pw: PackedWeights, conv: nn.Conv2d, x: Tensor, dtype: torch.dtype) -> Tensor:
+def run_in_conv(cx: Ctx, conv: nn.Conv2d, x: Tensor, dtype: torch.dtype) -> Act:
     """First conv: NCHW fp32 -> NHWC 16-bit (input_blocks.0.0, openaimodel.py:714-719)."""
+    pw = cx.pw
     if conv.in_channels <= 8:
-        return ops.conv3x3_in(x.contiguous(), _f(conv.weight), _f(conv.bias), dtype)
+        return Act(ops.conv3x3_in(x.contiguous(), _f(conv.weight), _f(conv.bias), dtype))
     cpad = (conv.in_channels + 7) // 8 * 8
     key = ("in", id(conv))
     if key not in pw.conv:
         pw.conv[key] = ops.pack_conv_weight(_f(conv.weight), dtype, cpad)
-    return ops.conv2d([(ops.nchw_to_nhwc(x, cpad, dtype), pw.conv[key], 0, 3, 1)], bias=_f(conv.bias))
+    return run_conv(cx, [(ops.nchw_to_nhwc(x, cpad, dtype), pw.conv[key], 0, 3, 1)], bias=_f(conv.bias))
 
 
-def run_out_head(pw: PackedWeights, out: nn.Sequential, h: Tensor) -> Tensor:
+def run_out_head(cx: Ctx, out: nn.Sequential, h: Act) -> Tensor:
     """self.out = GN, SiLU, conv3x3 (openaimodel.py:898-902): NHWC 16-bit -> NCHW fp32."""
+    pw = cx.pw
     gn, conv = out[0], out[2]
-    a = ops.group_norm(h, _f(gn.weight), _f(gn.bias), eps=gn.eps, silu=True)
+    a = run_gn(cx, gn, h)
     if conv.out_channels <= 4:
         return ops.conv3x3_out(a, _f(conv.weight), _f(conv.bias))
     key = ("out", id(conv))
     cpad = (conv.out_channels + 7) // 8 * 8
     if key not in pw.conv:
-        w = torch.zeros((cpad,) + tuple(conv.weight.shape[1:]), device=h.device)
+        w = torch.zeros((cpad,) + tuple(conv.weight.shape[1:]), device=a.device)
         w[:conv.out_channels] = conv.weight.detach().float()
-        b = torch.zeros(cpad, device=h.device)
+        b = torch.zeros(cpad, device=a.device)
         b[:conv.out_channels] = conv.bias.detach().float()
-        pw.conv[key] = (ops.pack_conv_weight(w, h.dtype), b)
+        pw.conv[key] = (ops.pack_conv_weight(w, a.dtype), b)
     wp, bp = pw.conv[key]
     return ops.nhwc_to_nchw(ops.conv2d([(a, wp, 0, 3, 1)], bias=bp), conv.out_channels)
 
@@ -264,6 +309,7 @@ class _EngineModule(nn.Module):
     def _init_engine(self):
         self._pw: Optional[PackedWeights] = None
         self._temb: Optional[TimeEmbedding] = None
+        self._arena = ops.StatsArena()
         self.register_load_state_dict_post_hook(lambda mod, keys: mod.invalidate())
 
     def invalidate(self):
@@ -394,13 +440,15 @@ class UNetModel(_EngineModule):
         n = x.shape[0]
         t_table = timesteps.to(torch.float32).contiguous() if step_ptr is not None else self._t_table(timesteps, n)
         _, emb_all = self._temb(pw, self.time_embed, t_table, n, step_ptr)
+        self._arena.begin(x.device)
+        cx = Ctx(pw, emb_all, self._arena)
         hs = []
-        h = run_in_conv(pw, self.input_blocks[0][0], x.float(), self.act_dtype)
+        h = run_in_conv(cx, self.input_blocks[0][0], x.float(), self.act_dtype)
         hs.append(h)
         for blk in list(self.input_blocks)[1:]:
-            h = run_sequential(pw, blk, h, None, emb_all)
+            h = run_sequential(cx, blk, h, None)
             hs.append(h)
-        h = run_sequential(pw, self.middle_block, h, None, emb_all)
+        h = run_sequential(cx, self.middle_block, h, None)
         for blk in self.output_blocks:
-            h = run_sequential(pw, blk, h, hs.pop(), emb_all)
-        return run_out_head(pw, self.out, h).to(x.dtype)
+            h = run_sequential(cx, blk, h, hs.pop())
+        return run_out_head(cx, self.out, h).to(x.dtype)

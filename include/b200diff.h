@@ -87,8 +87,9 @@ typedef struct {
   const void *residual;    /* NHWC act [N,Hout,Wout,Cout] or NULL                    */
   float res_scale;
   void *out;               /* NHWC act [N,Hout,Wout,Cout]                            */
-  float *gn_sums;          /* optional [N][Cout][2] fp32 (sum,sumsq) accumulated from the fp32
-                              accumulators for a following GroupNorm, or NULL        */
+  double *gn_sums;         /* optional [N][Cout][2] fp64 (sum, sum of squares per image and channel),
+                              ACCUMULATED from the fp32 epilogue values for a following GroupNorm
+                              (zero it first), or NULL                                */
   int act_dtype;
 } b200_conv_desc;
 int b200_conv2d_igemm(const b200_conv_desc *d, void *stream);
@@ -114,6 +115,15 @@ int b200_groupnorm_apply(const void *x0, int C0, const void *x1, int C1, int N, 
                          const float *beta, const float *film, int film_stride, int silu,
                          void *out, int act_dtype, void *stream);
 
+/* Producer-side statistics: sums[N][C][2] fp64 = per-(image, channel) sum and sum of squares, accumulated (zero first).
+ * b200_conv2d_igemm fills the same layout from its epilogue (gn_sums); b200_groupnorm_apply_cs reduces the channel
+ * sums of the two concatenated sources to group statistics itself, so a GroupNorm is ONE read + ONE write pass. */
+int b200_channel_stats(const void *x, int N, int HW, int C, double *sums, int act_dtype, void *stream);
+int b200_groupnorm_apply_cs(const void *x0, int C0, const double *cs0, const void *x1, int C1,
+                            const double *cs1, int N, int HW, int groups, float eps, const float *gamma,
+                            const float *beta, const float *film, int film_stride, int silu, void *out,
+                            int act_dtype, void *stream);
+
 /* ---- attention -------------------------------------------------------------------------------
  * replaces QKVAttention / QKVAttentionLegacy (openaimodel.py:537-555 / 505-521): fused
  * softmax_fp32((q*s)^T (k*s)) v with online softmax; qkv is the NHWC output of the qkv conv,
@@ -121,6 +131,24 @@ int b200_groupnorm_apply(const void *x0, int C0, const void *x1, int C1, int N, 
  * scale is applied to q.k (pass ch^-0.5 for the reference's ch^-0.25 on both).                 */
 int b200_attention_qkv(const void *qkv, void *out, int B, int L, int heads, int ch,
                        int new_order, float scale, int act_dtype, void *stream);
+/* general form: out[b, i, h*d + :] = softmax_j(scale * <q[b,i,h], k[b,j,h]>) v[b,j,h]   (fp32 softmax, exact max)
+ * q [B,Lq,ldq], k [B,Lk,ldk], v [B,Lk,ldv], out [B,Lq,ldo] act; head h of q starts at channel q_off + h*q_hstride
+ * (same for k, v).  Also replaces CrossAttention.forward's einsum/softmax/einsum
+ * (ldm/modules/attention.py:163-194: scale = dim_head^-0.5, Lk = context length) and timm Attention inside
+ * DiTBlock (UNet_DS_Diff/DiT_models.py:108).  Head dims that are multiples of 16 (32..160) run the tcgen05 flash
+ * kernel; other multiples of 8 (<= 64) run the CUDA-core kernel; force_simt selects the latter for A/B tests.  */
+typedef struct {
+  const void *q, *k, *v;
+  void *out;
+  int B, Lq, Lk, heads, d;
+  int ldq, ldk, ldv, ldo;
+  int q_off, k_off, v_off;
+  int q_hstride, k_hstride, v_hstride;
+  float scale;
+  int act_dtype;
+  int force_simt;
+} b200_attn_desc;
+int b200_attention(const b200_attn_desc *d, void *stream);
 
 /* ---- small dense layers on [B,K] fp32 vectors (timestep path) --------------------------------
  * replaces timestep_embedding (util.py:161-181), time_embed MLP (openaimodel.py:606-610) and

@@ -168,6 +168,45 @@ def test_groupnorm_concat_and_film(dt):
     close(nchw(y), ref, dt, "gn film")
 
 
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("case", [(1, 32, 32, 64, 96, 1), (2, 40, 24, 32, 320, 1), (3, 8, 8, 64, 64, 1), (2, 32, 32, 64, 64, 2)])
+def test_conv_fused_channel_stats_and_single_pass_groupnorm(case, dt):
+    """The conv epilogue's per-(image, channel) sums (tiles inside one image: fused; tiles spanning images: the
+    standalone kernel behind the same ABI field) feed b200_groupnorm_apply_cs = GroupNorm in one read + one write."""
+    ops = _ops()
+    n, h, w, ci, co, stride = case
+    x = q(rnd(1, n, ci, h, w), dt)
+    wt = q(rnd(2, co, ci, 3, 3, scale=1.0 / math.sqrt(ci * 9)), dt)
+    b = rnd(3, co, scale=0.1)
+    ref = F.conv2d(x, wt, b, stride=stride, padding=1)
+    st = torch.zeros(n, co, 2, dtype=torch.float64).cuda()
+    y = ops.conv2d([(nhwc(x, dt), ops.pack_conv_weight(wt.cuda(), dt), 0, 3, 1)], stride=stride, bias=b.cuda(), stats=st)
+    sums = torch.stack([ref.double().sum((2, 3)), (ref.double() ** 2).sum((2, 3))], -1)
+    cnt = ref.shape[2] * ref.shape[3]
+    assert ((st.cpu() - sums).abs() / cnt).max().item() < 1e-5      # fp32 accumulators, before the 16-bit store
+    st2 = ops.channel_stats(y)                                      # standalone kernel on the rounded tensor
+    assert ((st2.cpu() - sums).abs() / cnt).max().item() < STORE_EPS[dt] * 4
+    if co % 32 == 0:
+        g, be = 1 + 0.1 * rnd(4, co), 0.1 * rnd(5, co)
+        yq = nchw(y)
+        refn = F.silu(F.group_norm(yq, 32, g, be, 1e-5))
+        got = ops.group_norm(y, g.cuda(), be.cuda(), silu=True, cs0=st)
+        close(nchw(got), refn, dt, f"single-pass gn {case}")
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_groupnorm_concat_from_channel_sums(dt):
+    ops = _ops()
+    n, c0, c1, h, w = 2, 320, 160, 16, 16
+    x0, x1 = q(rnd(1, n, c0, h, w), dt), q(rnd(2, n, c1, h, w) * 2 + 1, dt)
+    c = c0 + c1
+    g, b = 1 + 0.1 * rnd(3, c), 0.1 * rnd(4, c)
+    ref = F.silu(F.group_norm(torch.cat([x0, x1], 1), 32, g, b, 1e-5))
+    a0, a1 = nhwc(x0, dt), nhwc(x1, dt)
+    y = ops.group_norm(a0, g.cuda(), b.cuda(), a1, silu=True, cs0=ops.channel_stats(a0), cs1=ops.channel_stats(a1))
+    close(nchw(y), ref, dt, "gn concat from channel sums")
+
+
 # -------------------------------------------------------------------------------------------------
 # attention
 # -------------------------------------------------------------------------------------------------
@@ -190,6 +229,26 @@ def test_attention(cfg, dt):
     y = ops.attention_qkv(qkv.permute(0, 2, 1).contiguous().to(dt).cuda(), heads, new_order)
     got = y.float().cpu().permute(0, 2, 1)
     close(got, ref, dt, f"attention {cfg}")
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("cfg", [(1, 128, 128, 1, 32), (2, 200, 77, 8, 64), (1, 256, 300, 2, 160), (1, 1024, 77, 8, 80),
+                                 (2, 320, 320, 3, 48), (1, 64, 64, 2, 40), (3, 130, 257, 2, 96)])
+def test_attention_general(cfg, dt):
+    """b200_attention with separate q / k / v token tensors (cross-attention shapes, Lq != Lk, ragged tiles).
+    Head dims that are multiples of 16 take the tcgen05 flash kernel, 40 the CUDA-core kernel."""
+    ops = _ops()
+    b, lq, lk, heads, d = cfg
+    qq, kk, vv = q(rnd(1, b, lq, heads * d), dt), q(rnd(2, b, lk, heads * d), dt), q(rnd(3, b, lk, heads * d), dt)
+    scale = d ** -0.5
+    sp = lambda t, l: t.view(b, l, heads, d).permute(0, 2, 1, 3)
+    wgt = torch.softmax(sp(qq, lq) @ sp(kk, lk).transpose(-1, -2) * scale, dim=-1)
+    ref = (wgt @ sp(vv, lk)).permute(0, 2, 1, 3).reshape(b, lq, heads * d)
+    y = ops.attention(qq.to(dt).cuda(), kk.to(dt).cuda(), vv.to(dt).cuda(), heads, d, scale)
+    close(y.float().cpu(), ref, dt, f"attention_general {cfg}")
+    if d % 16 == 0 and d <= 64:      # both kernels agree
+        y2 = ops.attention(qq.to(dt).cuda(), kk.to(dt).cuda(), vv.to(dt).cuda(), heads, d, scale, force_simt=True)
+        close(y2.float().cpu(), ref, dt, f"attention_general simt {cfg}")
 
 
 # -------------------------------------------------------------------------------------------------
