@@ -6,6 +6,8 @@
 //   M = 128 output pixels (a TW x TH x TN box), N = BN output channels (<= 256), K chunk = 64 channels.
 //
 // Replaces F.conv2d at the call sites listed in include/b200diff.h (b200_conv2d_igemm).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -30,9 +32,11 @@ struct ConvKParams {
   int tiles_w, tiles_h, tiles_n;
   int num_tiles;
   int stride;
-  int stages;
+  int a_stages, b_stages;   // shared-memory rings: activation tiles / weight tiles
+  int a_bytes;              // bytes of one activation slot (multiple of 1024)
   int nseg;
   int seg_cin[3], seg_coff[3], seg_ks[3], seg_pad[3];
+  int seg_halo[3];          // 3x3 stride-1 segment staged as 3 column-shifted (TH+2)-row boxes reused by the 3 tap rows
   const float *bias;
   const float *rowbias;
   int rowbias_stride;
@@ -78,69 +82,177 @@ __device__ __forceinline__ float warp_colsum16(const float (&a)[16], int lane) {
   return e;
 }
 
-template <typename T>
+// One lane of a fully converged warp (elect.sync): keeps the surrounding control flow warp-uniform so that descriptors,
+// barrier addresses and loop counters live in uniform registers and UTCHMMA / UTMALDG issue without per-lane loops.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// ---- CTA-pair (cta_group::2) PTX: the leader CTA (cluster rank 0) issues the MMAs for both SMs -------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t bar_cluster, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+// TMA loads whose completion is signalled on a barrier that may live in the PEER CTA of the pair
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const void *tmap, uint32_t bar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst), "l"(tmap), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const void *tmap, uint32_t bar_cluster, int c0, int c1, int c2,
+                                                 int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst), "l"(tmap), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+// kCtas == 1: one CTA per 128 x BN tile.  kCtas == 2: a CTA pair (2-CTA cluster on one TPC) per 256 x BN tile — each CTA
+// stages ITS 128 pixels and HALF of the weight tile, the leader's tcgen05.mma.cta_group::2 consumes both halves, so the
+// weight bytes that cross L2 -> SM per FLOP are halved.
+template <typename T, int kCtas>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];      // weight tile (+ the activation box it is first to use)
+  __shared__ __align__(8) uint64_t b_empty[kMaxStages], a_empty[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (kCtas == 2) ? cluster_ctarank() : 0u;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t b_bytes = (uint32_t)p.BN * 128u;
+  const uint32_t b_bytes = (uint32_t)(p.BN / kCtas) * 128u;       // this CTA's share of a weight tile
+  const uint32_t a_bytes = (uint32_t)p.a_bytes;
   const uint32_t smem_a = smem_base;
-  const uint32_t smem_b = smem_base + (uint32_t)p.stages * kABytes;
+  const uint32_t smem_b = smem_base + (uint32_t)p.a_stages * a_bytes;
+  const uint32_t halo_bytes = (uint32_t)(p.TH + 2) * p.TW * 128u;
+  const int tile0 = blockIdx.x / kCtas, tile_step = gridDim.x / kCtas;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nseg; ++s) {
       prefetch_tmap(&maps.a[s]);
       prefetch_tmap(&maps.b[s]);
     }
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), 1);
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), kCtas);     // one arrive.expect_tx per CTA of the pair
+      mbar_init(smem_u32(&b_empty[s]), 1);
+      mbar_init(smem_u32(&a_empty[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[a]), 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&tmem_empty_bar[a]), 4 * kCtas);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), kTmemCols);
+  if (warp == 1) {
+    if (kCtas == 2) tmem_alloc_pair(smem_u32(&tmem_base_smem), kTmemCols);
+    else tmem_alloc(smem_u32(&tmem_base_smem), kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
+  // Work order shared by the producer and the MMA issuer, per tile and segment:
+  //   halo segment : for c0 (64-channel chunk) / for sx (column shift): ONE activation box of (TH+2) rows, consumed
+  //                  by the three weight tiles of taps (r, sx), r = 0..2 - tap row r reads rows [r*TW, r*TW+128) of it;
+  //   otherwise    : for tap / for c0: one 128-pixel activation box per weight tile.
+  // Every weight tile has ONE full barrier; the activation box rides on the barrier of the first weight tile using it.
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    // ===================== TMA producer (one per CTA; whole warp runs the loop, one elected lane issues) ==========
+    {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      // s: segment, (win, hin): box origin or <0,.. ignored when !with_a
+      auto load = [&](int s, int c0, int n_tile, int tap, bool with_a, uint32_t abytes, int win, int hin, int n0) {
+        mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1);
+        if (with_a) mbar_wait(smem_u32(&a_empty[as]), aph ^ 1);
+        const uint32_t fb_local = smem_u32(&full_bar[bs]);
+        const int brow = n_tile * p.BN + (int)rank * (p.BN / kCtas);
+        if (elect_one()) {
+          if (kCtas == 2) {
+            const uint32_t fb = mapa_u32(fb_local, 0);
+            mbar_arrive_expect_tx_cluster(fb, b_bytes + (with_a ? abytes : 0u));
+            if (with_a) tma_load_4d_pair(smem_a + as * a_bytes, &maps.a[s], fb, c0, win, hin, n0);
+            tma_load_3d_pair(smem_b + bs * b_bytes, &maps.b[s], fb, p.seg_coff[s] + c0, brow, tap);
+          } else {
+            mbar_arrive_expect_tx(fb_local, b_bytes + (with_a ? abytes : 0u));
+            if (with_a) tma_load_4d(smem_a + as * a_bytes, &maps.a[s], fb_local, c0, win, hin, n0);
+            tma_load_3d(smem_b + bs * b_bytes, &maps.b[s], fb_local, p.seg_coff[s] + c0, brow, tap);
+          }
+        }
+        __syncwarp();
+        if (with_a && ++as == p.a_stages) { as = 0; aph ^= 1; }
+        if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+      };
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
         const int n_tile = tile % p.n_ntiles;
-        int pt = tile / p.n_ntiles;
+        int pt = (tile / p.n_ntiles) * kCtas + (int)rank;      // this CTA's pixel tile of the pair
         const int w0 = (pt % p.tiles_w) * p.TW;
         pt /= p.tiles_w;
         const int h0 = (pt % p.tiles_h) * p.TH;
-        const int n0 = (pt / p.tiles_h) * p.TN;
+        const int n0 = (pt / p.tiles_h) * p.TN;                // >= N for the odd tile out: all-zero boxes
         for (int s = 0; s < p.nseg; ++s) {
-          const int ks = p.seg_ks[s], pad = p.seg_pad[s], cin = p.seg_cin[s], coff = p.seg_coff[s];
-          for (int tap = 0; tap < ks * ks; ++tap) {
-            const int r = tap / ks, sx = tap - r * ks;
-            const int hin = h0 * p.stride + r - pad;
-            const int win = w0 * p.stride + sx - pad;
-            for (int c0 = 0; c0 < cin; c0 += kBK) {
-              mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-              const uint32_t fb = smem_u32(&full_bar[stage]);
-              mbar_arrive_expect_tx(fb, kABytes + b_bytes);
-              tma_load_4d(smem_a + stage * kABytes, &maps.a[s], fb, c0, win, hin, n0);
-              tma_load_3d(smem_b + stage * b_bytes, &maps.b[s], fb, coff + c0, n_tile * p.BN, tap);
-              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          const int ks = p.seg_ks[s], pad = p.seg_pad[s], cin = p.seg_cin[s];
+          if (p.seg_halo[s]) {
+            for (int c0 = 0; c0 < cin; c0 += kBK)
+              for (int sx = 0; sx < 3; ++sx)
+                for (int r = 0; r < 3; ++r)
+                  load(s, c0, n_tile, r * 3 + sx, r == 0, halo_bytes, w0 + sx - 1, h0 - 1, n0);
+          } else {
+            for (int tap = 0; tap < ks * ks; ++tap) {
+              const int r = tap / ks, sx = tap - r * ks;
+              for (int c0 = 0; c0 < cin; c0 += kBK)
+                load(s, c0, n_tile, tap, true, (uint32_t)kABytes, w0 * p.stride + sx - pad, h0 * p.stride + r - pad, n0);
             }
           }
         }
@@ -148,40 +260,60 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+    // ===================== MMA issuer (leader CTA only; whole warp runs the loop, one elected lane issues) =======
+    if (rank == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccCols;
         uint32_t accumulate = 0;
-        for (int s = 0; s < p.nseg; ++s) {
-          const int taps = p.seg_ks[s] * p.seg_ks[s], cin = p.seg_cin[s];
-          for (int tap = 0; tap < taps; ++tap) {
-            for (int c0 = 0; c0 < cin; c0 += kBK) {
-              const int kk = min(kBK, cin - c0);
-              const int nk = (kk + 15) >> 4;
-              mbar_wait(smem_u32(&full_bar[stage]), phase);
-              tc_fence_after();
-              const uint64_t da = umma_desc_sw128(smem_a + stage * kABytes);
-              const uint64_t db = umma_desc_sw128(smem_b + stage * b_bytes);
-              for (int k = 0; k < nk; ++k) {
-                // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in >>4 units
-                umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, accumulate);
-                accumulate = 1;
-              }
-              umma_commit(smem_u32(&empty_bar[stage]));
-              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        // one weight tile against the activation rows starting a_off bytes into slot `as`
+        auto mma_b = [&](uint32_t a_off, int nk, bool last_use_of_a) {
+          mbar_wait(smem_u32(&full_bar[bs]), bph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da = umma_desc_sw128(smem_a + as * a_bytes + a_off);
+            const uint64_t db = umma_desc_sw128(smem_b + bs * b_bytes);
+            for (int k = 0; k < nk; ++k) {
+              // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in >>4 units
+              if (kCtas == 2) umma_f16_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, accumulate | (uint32_t)k);
+              else umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, accumulate | (uint32_t)k);
+            }
+            if (kCtas == 2) umma_commit_pair(smem_u32(&b_empty[bs])); else umma_commit(smem_u32(&b_empty[bs]));
+            if (last_use_of_a) {
+              if (kCtas == 2) umma_commit_pair(smem_u32(&a_empty[as])); else umma_commit(smem_u32(&a_empty[as]));
             }
           }
+          __syncwarp();
+          accumulate = 1;
+          if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
+          if (last_use_of_a && ++as == p.a_stages) { as = 0; aph ^= 1; }
+        };
+        for (int s = 0; s < p.nseg; ++s) {
+          const int taps = p.seg_ks[s] * p.seg_ks[s], cin = p.seg_cin[s];
+          if (p.seg_halo[s]) {
+            for (int c0 = 0; c0 < cin; c0 += kBK) {
+              const int nk = (min(kBK, cin - c0) + 15) >> 4;
+              for (int sx = 0; sx < 3; ++sx)
+                // tap row r = the 128 box rows starting r*TW pixels (r*TW*128 B, a multiple of the 1024-B swizzle atom)
+                for (int r = 0; r < 3; ++r) mma_b((uint32_t)(r * p.TW) * 128u, nk, r == 2);
+            }
+          } else {
+            for (int tap = 0; tap < taps; ++tap)
+              for (int c0 = 0; c0 < cin; c0 += kBK) mma_b(0u, (min(kBK, cin - c0) + 15) >> 4, true);
+          }
         }
-        umma_commit(smem_u32(&tmem_full_bar[acc]));
+        if (elect_one()) {
+          if (kCtas == 2) umma_commit_pair(smem_u32(&tmem_full_bar[acc])); else umma_commit(smem_u32(&tmem_full_bar[acc]));
+        }
+        __syncwarp();
       }
+      (void)aph;
     }
     __syncwarp();
   } else {
@@ -194,11 +326,12 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
     T *out = reinterpret_cast<T *>(p.out);
     const T *res = reinterpret_cast<const T *>(p.residual);
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    const uint32_t empty_bar_leader0 = (kCtas == 2) ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
+    for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int n_tile = tile % p.n_ntiles;
-      int pt = tile / p.n_ntiles;
+      int pt = (tile / p.n_ntiles) * kCtas + (int)rank;
       const int w = (pt % p.tiles_w) * p.TW + tw;
       pt /= p.tiles_w;
       const int h = (pt % p.tiles_h) * p.TH + th;
@@ -268,15 +401,18 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+      if (lane == 0) {
+        if (kCtas == 2) mbar_arrive_cluster(empty_bar_leader0 + acc * 8u);   // the leader's barrier (8 B apart)
+        else mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (kCtas == 2) tmem_dealloc_pair(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -298,7 +434,7 @@ int pick_bn(int Cout) {
 }
 }  // namespace
 
-template <typename T>
+template <typename T, int kCtas>
 static int launch_conv(const b200_conv_desc *d, cudaStream_t stream) {
   ConvKParams p{};
   ConvMaps maps{};
@@ -322,16 +458,30 @@ static int launch_conv(const b200_conv_desc *d, cudaStream_t stream) {
   p.tiles_w = cdiv(d->Wout, p.TW);
   p.tiles_h = cdiv(d->Hout, p.TH);
   p.tiles_n = cdiv(d->N, p.TN);
-  p.num_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_ntiles;
+  p.num_tiles = cdiv(p.tiles_w * p.tiles_h * p.tiles_n, kCtas) * p.n_ntiles;   // (pairs of) pixel tiles x N tiles
   p.bias = d->bias; p.rowbias = d->rowbias; p.rowbias_stride = d->rowbias_stride;
   p.residual = d->residual; p.res_scale = d->res_scale; p.out = d->out;
   // fused statistics need every epilogue warp (32 consecutive box rows) inside one image; tinier maps (< 32 pixels)
   // take the standalone kernel below — a choice that depends on the map size only, not on N
   p.gn_sums = (p.TW * p.TH >= 32) ? d->gn_sums : nullptr;
-  p.idesc = umma_idesc(Act<T>::kFmt, kBM, p.BN);
-  const size_t stage_bytes = (size_t)kABytes + (size_t)p.BN * 128;
-  p.stages = (int)std::min<size_t>(kMaxStages, (200 * 1024) / stage_bytes);
-  B200_CHECK(p.stages >= 2, "conv: tile too large for shared memory");
+  p.idesc = umma_idesc(Act<T>::kFmt, kBM * kCtas, p.BN);
+  // halo staging: 3x3 stride-1 pad-1 segments whose 128-pixel box lies in one image and is >= 8 pixels wide
+  const bool halo_ok = d->stride == 1 && p.TN == 1 && p.TW >= 8 && !getenv("B200DIFF_NO_HALO");
+  bool any_halo = false;
+  for (int s = 0; s < d->nseg; ++s) {
+    p.seg_halo[s] = halo_ok && d->seg[s].ksize == 3 && d->seg[s].pad == 1;
+    any_halo |= p.seg_halo[s] != 0;
+  }
+  p.a_bytes = any_halo ? kABytes + 2 * p.TW * 128 : kABytes;
+  const size_t b_bytes = (size_t)(p.BN / kCtas) * 128;
+  const size_t budget = 200 * 1024;
+  if (any_halo) {   // one activation box feeds three weight tiles
+    p.a_stages = (kCtas == 2) ? 4 : 3;
+    p.b_stages = (int)std::min<size_t>(kMaxStages, (budget - (size_t)p.a_stages * p.a_bytes) / b_bytes);
+  } else {          // lock-step rings: split the budget evenly
+    p.a_stages = p.b_stages = (int)std::min<size_t>(kMaxStages, budget / (p.a_bytes + b_bytes));
+  }
+  B200_CHECK(p.a_stages >= 2 && p.b_stages >= 2, "conv: tile too large for shared memory");
 
   for (int s = 0; s < d->nseg; ++s) {
     const b200_conv_seg &g = d->seg[s];
@@ -345,26 +495,39 @@ static int launch_conv(const b200_conv_desc *d, cudaStream_t stream) {
       uint64_t str[3] = {(uint64_t)g.cin * 2, (uint64_t)d->Win * g.cin * 2,
                          (uint64_t)d->Hin * d->Win * g.cin * 2};
       uint32_t box[4] = {kBK, (uint32_t)(p.TW * d->stride), (uint32_t)(p.TH * d->stride), (uint32_t)p.TN};
+      if (p.seg_halo[s]) box[2] = (uint32_t)(p.TH + 2);
       uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
       if (int rc = cached_tmap(&maps.a[s], g.src, 4, dims, str, box, es)) return rc;
     }
     {  // weights: (Cin, Cout, taps)
       uint64_t dims[3] = {(uint64_t)g.wcin, (uint64_t)d->Cout, (uint64_t)(g.ksize * g.ksize)};
       uint64_t str[2] = {(uint64_t)g.wcin * 2, (uint64_t)d->Cout * g.wcin * 2};
-      uint32_t box[3] = {kBK, (uint32_t)p.BN, 1};
+      uint32_t box[3] = {kBK, (uint32_t)(p.BN / kCtas), 1};
       uint32_t es[3] = {1, 1, 1};
       if (int rc = cached_tmap(&maps.b[s], g.weight, 3, dims, str, box, es)) return rc;
     }
   }
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[Act<T>::kFmt]) {
-    B200_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  const size_t smem = (size_t)p.a_stages * p.a_bytes + (size_t)p.b_stages * b_bytes + 1024;
+  static bool attr_set = false;     // per (T, kCtas) instantiation
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<T, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    220 * 1024));
-    attr_set[Act<T>::kFmt] = true;
+    attr_set = true;
   }
-  const int grid = std::min(p.num_tiles, num_sms());
-  conv_igemm_kernel<T><<<grid, kConvThreads, smem, stream>>>(maps, p);
+  const int grid = kCtas * std::min(p.num_tiles, num_sms() / kCtas);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(kConvThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<T, kCtas>, maps, p));
   B200_LAUNCH_CHECK();
   if (d->gn_sums && !p.gn_sums)
     return b200_channel_stats(d->out, d->N, d->Hout * d->Wout, d->Cout, d->gn_sums, d->act_dtype, stream);
@@ -380,7 +543,12 @@ extern "C" int b200_conv2d_igemm(const b200_conv_desc *d, void *stream) {
   B200_CHECK(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2");
   B200_CHECK(d->Cout % 8 == 0, "conv: Cout must be a multiple of 8 (got %d)", d->Cout);
   B200_CHECK(d->N > 0 && d->Hout > 0 && d->Wout > 0, "conv: empty output");
-  if (d->act_dtype == B200_F16) return launch_conv<__half>(d, (cudaStream_t)stream);
-  if (d->act_dtype == B200_BF16) return launch_conv<__nv_bfloat16>(d, (cudaStream_t)stream);
+  // CTA pairs need an N tile that splits into two halves of whole 8-row core groups (BN % 16 == 0 always holds)
+  static const bool one_cta = getenv("B200DIFF_CONV_1CTA") != nullptr;
+  if (d->act_dtype == B200_F16)
+    return one_cta ? launch_conv<__half, 1>(d, (cudaStream_t)stream) : launch_conv<__half, 2>(d, (cudaStream_t)stream);
+  if (d->act_dtype == B200_BF16)
+    return one_cta ? launch_conv<__nv_bfloat16, 1>(d, (cudaStream_t)stream)
+                   : launch_conv<__nv_bfloat16, 2>(d, (cudaStream_t)stream);
   B200_CHECK(false, "conv: bad act_dtype %d", d->act_dtype);
 }
