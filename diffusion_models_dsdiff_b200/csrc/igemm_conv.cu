@@ -32,8 +32,8 @@ struct ConvKParams {
   int tiles_w, tiles_h, tiles_n;
   int num_tiles;
   int stride;
-  int a_stages, b_stages;   // shared-memory rings: activation tiles / weight tiles
-  int a_bytes;              // bytes of one activation slot (multiple of 1024)
+  int stages;               // pipeline stages; one stage = [activation box | up to 3 weight tiles]
+  int a_bytes, stage_bytes; // bytes of the activation region / of a whole stage (multiples of 1024)
   int nseg;
   int seg_cin[3], seg_coff[3], seg_ks[3], seg_pad[3];
   int seg_halo[3];          // 3x3 stride-1 segment staged as 3 column-shifted (TH+2)-row boxes reused by the 3 tap rows
@@ -45,6 +45,7 @@ struct ConvKParams {
   void *out;
   double *gn_sums;
   uint32_t idesc;
+  int debug_skip_epilogue;   // B200DIFF_SKIP_EPI: timing experiments only (results are garbage)
 };
 
 // Column sums of a 32 (lanes) x 16 (registers) tile by recursive halving: 16 shuffles instead of 16 x 5.
@@ -160,8 +161,7 @@ template <typename T, int kCtas>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kMaxStages];      // weight tile (+ the activation box it is first to use)
-  __shared__ __align__(8) uint64_t b_empty[kMaxStages], a_empty[kMaxStages];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];   // one pair per pipeline stage
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
@@ -172,8 +172,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t b_bytes = (uint32_t)(p.BN / kCtas) * 128u;       // this CTA's share of a weight tile
   const uint32_t a_bytes = (uint32_t)p.a_bytes;
-  const uint32_t smem_a = smem_base;
-  const uint32_t smem_b = smem_base + (uint32_t)p.a_stages * a_bytes;
+  const uint32_t stage_bytes = (uint32_t)p.stage_bytes;           // [activation box | up to 3 weight tiles]
   const uint32_t halo_bytes = (uint32_t)(p.TH + 2) * p.TW * 128u;
   const int tile0 = blockIdx.x / kCtas, tile_step = gridDim.x / kCtas;
 
@@ -184,8 +183,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
     }
     for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), kCtas);     // one arrive.expect_tx per CTA of the pair
-      mbar_init(smem_u32(&b_empty[s]), 1);
-      mbar_init(smem_u32(&a_empty[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
@@ -202,68 +200,66 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  // Work order shared by the producer and the MMA issuer, per tile and segment:
-  //   halo segment : for c0 (64-channel chunk) / for sx (column shift): ONE activation box of (TH+2) rows, consumed
-  //                  by the three weight tiles of taps (r, sx), r = 0..2 - tap row r reads rows [r*TW, r*TW+128) of it;
-  //   otherwise    : for tap / for c0: one 128-pixel activation box per weight tile.
-  // Every weight tile has ONE full barrier; the activation box rides on the barrier of the first weight tile using it.
+  // A pipeline stage is a GROUP of work, identical for the producer and the MMA issuer, per tile and segment:
+  //   halo segment : for c0 (64-channel chunk) / for sx (column shift): ONE activation box of (TH+2) rows + the THREE
+  //                  weight tiles of taps (r, sx), r = 0..2 — tap row r multiplies box rows [r*TW, r*TW+128): 12 MMAs;
+  //   otherwise    : for tap / for c0: one 128-pixel activation box + one weight tile: 4 MMAs.
+  // One full barrier (expect_tx = all bytes of the group) and one empty barrier per stage: the single-thread issue loops
+  // do one wait per 12 MMAs instead of one per 4.
   if (warp == 0) {
     // ===================== TMA producer (one per CTA; whole warp runs the loop, one elected lane issues) ==========
-    {
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      // s: segment, (win, hin): box origin or <0,.. ignored when !with_a
-      auto load = [&](int s, int c0, int n_tile, int tap, bool with_a, uint32_t abytes, int win, int hin, int n0) {
-        mbar_wait(smem_u32(&b_empty[bs]), bph ^ 1);
-        if (with_a) mbar_wait(smem_u32(&a_empty[as]), aph ^ 1);
-        const uint32_t fb_local = smem_u32(&full_bar[bs]);
-        const int brow = n_tile * p.BN + (int)rank * (p.BN / kCtas);
-        if (elect_one()) {
-          if (kCtas == 2) {
-            const uint32_t fb = mapa_u32(fb_local, 0);
-            mbar_arrive_expect_tx_cluster(fb, b_bytes + (with_a ? abytes : 0u));
-            if (with_a) tma_load_4d_pair(smem_a + as * a_bytes, &maps.a[s], fb, c0, win, hin, n0);
-            tma_load_3d_pair(smem_b + bs * b_bytes, &maps.b[s], fb, p.seg_coff[s] + c0, brow, tap);
-          } else {
-            mbar_arrive_expect_tx(fb_local, b_bytes + (with_a ? abytes : 0u));
-            if (with_a) tma_load_4d(smem_a + as * a_bytes, &maps.a[s], fb_local, c0, win, hin, n0);
-            tma_load_3d(smem_b + bs * b_bytes, &maps.b[s], fb_local, p.seg_coff[s] + c0, brow, tap);
-          }
+    int st = 0;
+    uint32_t ph = 0;
+    auto load_group = [&](int s, int c0, int n_tile, int tap0, int tap_step, int nb, uint32_t abytes, int win, int hin,
+                          int n0) {
+      mbar_wait(smem_u32(&empty_bar[st]), ph ^ 1);
+      const uint32_t fb_local = smem_u32(&full_bar[st]);
+      const uint32_t sa = smem_base + st * stage_bytes;
+      const int brow = n_tile * p.BN + (int)rank * (p.BN / kCtas);
+      if (elect_one()) {
+        if (kCtas == 2) {
+          const uint32_t fb = mapa_u32(fb_local, 0);
+          mbar_arrive_expect_tx_cluster(fb, abytes + nb * b_bytes);
+          tma_load_4d_pair(sa, &maps.a[s], fb, c0, win, hin, n0);
+          for (int j = 0; j < nb; ++j)
+            tma_load_3d_pair(sa + a_bytes + j * b_bytes, &maps.b[s], fb, p.seg_coff[s] + c0, brow, tap0 + j * tap_step);
+        } else {
+          mbar_arrive_expect_tx(fb_local, abytes + nb * b_bytes);
+          tma_load_4d(sa, &maps.a[s], fb_local, c0, win, hin, n0);
+          for (int j = 0; j < nb; ++j)
+            tma_load_3d(sa + a_bytes + j * b_bytes, &maps.b[s], fb_local, p.seg_coff[s] + c0, brow, tap0 + j * tap_step);
         }
-        __syncwarp();
-        if (with_a && ++as == p.a_stages) { as = 0; aph ^= 1; }
-        if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
-      };
-      for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
-        const int n_tile = tile % p.n_ntiles;
-        int pt = (tile / p.n_ntiles) * kCtas + (int)rank;      // this CTA's pixel tile of the pair
-        const int w0 = (pt % p.tiles_w) * p.TW;
-        pt /= p.tiles_w;
-        const int h0 = (pt % p.tiles_h) * p.TH;
-        const int n0 = (pt / p.tiles_h) * p.TN;                // >= N for the odd tile out: all-zero boxes
-        for (int s = 0; s < p.nseg; ++s) {
-          const int ks = p.seg_ks[s], pad = p.seg_pad[s], cin = p.seg_cin[s];
-          if (p.seg_halo[s]) {
+      }
+      __syncwarp();
+      if (++st == p.stages) { st = 0; ph ^= 1; }
+    };
+    for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
+      const int n_tile = tile % p.n_ntiles;
+      int pt = (tile / p.n_ntiles) * kCtas + (int)rank;      // this CTA's pixel tile of the pair
+      const int w0 = (pt % p.tiles_w) * p.TW;
+      pt /= p.tiles_w;
+      const int h0 = (pt % p.tiles_h) * p.TH;
+      const int n0 = (pt / p.tiles_h) * p.TN;                // >= N for the odd tile out: all-zero boxes
+      for (int s = 0; s < p.nseg; ++s) {
+        const int ks = p.seg_ks[s], pad = p.seg_pad[s], cin = p.seg_cin[s];
+        if (p.seg_halo[s]) {
+          for (int c0 = 0; c0 < cin; c0 += kBK)
+            for (int sx = 0; sx < 3; ++sx)
+              load_group(s, c0, n_tile, sx, 3, 3, halo_bytes, w0 + sx - 1, h0 - 1, n0);
+        } else {
+          for (int tap = 0; tap < ks * ks; ++tap) {
+            const int r = tap / ks, sx = tap - r * ks;
             for (int c0 = 0; c0 < cin; c0 += kBK)
-              for (int sx = 0; sx < 3; ++sx)
-                for (int r = 0; r < 3; ++r)
-                  load(s, c0, n_tile, r * 3 + sx, r == 0, halo_bytes, w0 + sx - 1, h0 - 1, n0);
-          } else {
-            for (int tap = 0; tap < ks * ks; ++tap) {
-              const int r = tap / ks, sx = tap - r * ks;
-              for (int c0 = 0; c0 < cin; c0 += kBK)
-                load(s, c0, n_tile, tap, true, (uint32_t)kABytes, w0 * p.stride + sx - pad, h0 * p.stride + r - pad, n0);
-            }
+              load_group(s, c0, n_tile, tap, 0, 1, (uint32_t)kABytes, w0 * p.stride + sx - pad, h0 * p.stride + r - pad, n0);
           }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only; whole warp runs the loop, one elected lane issues) =======
     if (rank == 0) {
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
+      int st = 0;
+      uint32_t ph = 0;
       int it = 0;
       for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
@@ -272,40 +268,37 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * kAccCols;
         uint32_t accumulate = 0;
-        // one weight tile against the activation rows starting a_off bytes into slot `as`
-        auto mma_b = [&](uint32_t a_off, int nk, bool last_use_of_a) {
-          mbar_wait(smem_u32(&full_bar[bs]), bph);
+        // nb weight tiles of the stage; tile j multiplies the activation rows starting j*a_step bytes into the box
+        auto mma_group = [&](int nb, uint32_t a_step, int nk) {
+          mbar_wait(smem_u32(&full_bar[st]), ph);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t da = umma_desc_sw128(smem_a + as * a_bytes + a_off);
-            const uint64_t db = umma_desc_sw128(smem_b + bs * b_bytes);
-            for (int k = 0; k < nk; ++k) {
-              // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in >>4 units
-              if (kCtas == 2) umma_f16_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, accumulate | (uint32_t)k);
-              else umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, accumulate | (uint32_t)k);
+            const uint32_t sa = smem_base + st * stage_bytes;
+            for (int j = 0; j < nb; ++j) {
+              const uint64_t da = umma_desc_sw128(sa + j * a_step);
+              const uint64_t db = umma_desc_sw128(sa + a_bytes + j * b_bytes);
+              for (int k = 0; k < nk; ++k) {
+                // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in >>4 units
+                const uint32_t accf = accumulate | (uint32_t)(j | k);
+                if (kCtas == 2) umma_f16_pair(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, accf);
+                else umma_f16(tmem_d, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), p.idesc, accf);
+              }
             }
-            if (kCtas == 2) umma_commit_pair(smem_u32(&b_empty[bs])); else umma_commit(smem_u32(&b_empty[bs]));
-            if (last_use_of_a) {
-              if (kCtas == 2) umma_commit_pair(smem_u32(&a_empty[as])); else umma_commit(smem_u32(&a_empty[as]));
-            }
+            if (kCtas == 2) umma_commit_pair(smem_u32(&empty_bar[st])); else umma_commit(smem_u32(&empty_bar[st]));
           }
           __syncwarp();
           accumulate = 1;
-          if (++bs == p.b_stages) { bs = 0; bph ^= 1; }
-          if (last_use_of_a && ++as == p.a_stages) { as = 0; aph ^= 1; }
+          if (++st == p.stages) { st = 0; ph ^= 1; }
         };
         for (int s = 0; s < p.nseg; ++s) {
           const int taps = p.seg_ks[s] * p.seg_ks[s], cin = p.seg_cin[s];
           if (p.seg_halo[s]) {
-            for (int c0 = 0; c0 < cin; c0 += kBK) {
-              const int nk = (min(kBK, cin - c0) + 15) >> 4;
-              for (int sx = 0; sx < 3; ++sx)
-                // tap row r = the 128 box rows starting r*TW pixels (r*TW*128 B, a multiple of the 1024-B swizzle atom)
-                for (int r = 0; r < 3; ++r) mma_b((uint32_t)(r * p.TW) * 128u, nk, r == 2);
-            }
+            // tap row r = the 128 box rows starting r*TW pixels (r*TW*128 B, a multiple of the 1024-B swizzle atom)
+            for (int c0 = 0; c0 < cin; c0 += kBK)
+              for (int sx = 0; sx < 3; ++sx) mma_group(3, (uint32_t)p.TW * 128u, (min(kBK, cin - c0) + 15) >> 4);
           } else {
             for (int tap = 0; tap < taps; ++tap)
-              for (int c0 = 0; c0 < cin; c0 += kBK) mma_b(0u, (min(kBK, cin - c0) + 15) >> 4, true);
+              for (int c0 = 0; c0 < cin; c0 += kBK) mma_group(1, 0u, (min(kBK, cin - c0) + 15) >> 4);
           }
         }
         if (elect_one()) {
@@ -313,9 +306,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
         }
         __syncwarp();
       }
-      (void)aph;
     }
-    __syncwarp();
   } else {
     // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
     const int lane_base = 32 * (warp & 3);
@@ -343,7 +334,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + acc * kAccCols;
-      for (int c = 0; c < p.BN; c += 16) {
+      for (int c = 0; c < (p.debug_skip_epilogue ? 0 : p.BN); c += 16) {
         uint32_t r[16];
         tmem_ld16(taddr + c, r);
         tmem_ld_wait();
@@ -465,6 +456,7 @@ static int launch_conv(const b200_conv_desc *d, cudaStream_t stream) {
   // take the standalone kernel below — a choice that depends on the map size only, not on N
   p.gn_sums = (p.TW * p.TH >= 32) ? d->gn_sums : nullptr;
   p.idesc = umma_idesc(Act<T>::kFmt, kBM * kCtas, p.BN);
+  p.debug_skip_epilogue = getenv("B200DIFF_SKIP_EPI") != nullptr;
   // halo staging: 3x3 stride-1 pad-1 segments whose 128-pixel box lies in one image and is >= 8 pixels wide
   const bool halo_ok = d->stride == 1 && p.TN == 1 && p.TW >= 8 && !getenv("B200DIFF_NO_HALO");
   bool any_halo = false;
@@ -474,14 +466,9 @@ static int launch_conv(const b200_conv_desc *d, cudaStream_t stream) {
   }
   p.a_bytes = any_halo ? kABytes + 2 * p.TW * 128 : kABytes;
   const size_t b_bytes = (size_t)(p.BN / kCtas) * 128;
-  const size_t budget = 200 * 1024;
-  if (any_halo) {   // one activation box feeds three weight tiles
-    p.a_stages = (kCtas == 2) ? 4 : 3;
-    p.b_stages = (int)std::min<size_t>(kMaxStages, (budget - (size_t)p.a_stages * p.a_bytes) / b_bytes);
-  } else {          // lock-step rings: split the budget evenly
-    p.a_stages = p.b_stages = (int)std::min<size_t>(kMaxStages, budget / (p.a_bytes + b_bytes));
-  }
-  B200_CHECK(p.a_stages >= 2 && p.b_stages >= 2, "conv: tile too large for shared memory");
+  p.stage_bytes = p.a_bytes + (any_halo ? 3 : 1) * (int)b_bytes;
+  p.stages = (int)std::min<size_t>(kMaxStages, (220 * 1024) / p.stage_bytes);
+  B200_CHECK(p.stages >= 2, "conv: tile too large for shared memory");
 
   for (int s = 0; s < d->nseg; ++s) {
     const b200_conv_seg &g = d->seg[s];
@@ -507,11 +494,11 @@ static int launch_conv(const b200_conv_desc *d, cudaStream_t stream) {
       if (int rc = cached_tmap(&maps.b[s], g.weight, 3, dims, str, box, es)) return rc;
     }
   }
-  const size_t smem = (size_t)p.a_stages * p.a_bytes + (size_t)p.b_stages * b_bytes + 1024;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
   static bool attr_set = false;     // per (T, kCtas) instantiation
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<T, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   220 * 1024));
+                                   226 * 1024));
     attr_set = true;
   }
   const int grid = kCtas * std::min(p.num_tiles, num_sms() / kCtas);
