@@ -45,6 +45,8 @@ struct ConvKParams {
   void *out;
   double *gn_sums;
   uint32_t idesc;
+  float *out_f32;            // NCHW fp32 output of the first cout_real channels (network head) instead of `out`
+  int cout_real;
   int debug_skip_epilogue;   // B200DIFF_SKIP_EPI: timing experiments only (results are garbage)
 };
 
@@ -368,7 +370,14 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) vh[i] += p.res_scale * rf[i];
             }
-            *reinterpret_cast<uint4 *>(out + pix * p.Cout + cb) = pack8<T>(vh);
+            if (p.out_f32) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (cb + i < p.cout_real)
+                  p.out_f32[(((size_t)n * p.cout_real + cb + i) * p.Hout + h) * p.Wout + w] = vh[i];
+            } else {
+              *reinterpret_cast<uint4 *>(out + pix * p.Cout + cb) = pack8<T>(vh);
+            }
           } else if (p.gn_sums) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) vh[i] = 0.f;
@@ -457,6 +466,7 @@ static int launch_conv(const b200_conv_desc *d, cudaStream_t stream) {
   p.gn_sums = (p.TW * p.TH >= 32) ? d->gn_sums : nullptr;
   p.idesc = umma_idesc(Act<T>::kFmt, kBM * kCtas, p.BN);
   p.debug_skip_epilogue = getenv("B200DIFF_SKIP_EPI") != nullptr;
+  p.out_f32 = d->out_nchw_f32; p.cout_real = d->cout_real;
   // halo staging: 3x3 stride-1 pad-1 segments whose 128-pixel box lies in one image and is >= 8 pixels wide
   const bool halo_ok = d->stride == 1 && p.TN == 1 && p.TW >= 8 && !getenv("B200DIFF_NO_HALO");
   bool any_halo = false;
@@ -530,6 +540,9 @@ extern "C" int b200_conv2d_igemm(const b200_conv_desc *d, void *stream) {
   B200_CHECK(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2");
   B200_CHECK(d->Cout % 8 == 0, "conv: Cout must be a multiple of 8 (got %d)", d->Cout);
   B200_CHECK(d->N > 0 && d->Hout > 0 && d->Wout > 0, "conv: empty output");
+  B200_CHECK(d->out != nullptr || d->out_nchw_f32 != nullptr, "conv: no output pointer");
+  B200_CHECK(d->out_nchw_f32 == nullptr || (d->cout_real >= 1 && d->cout_real <= d->Cout && !d->gn_sums),
+             "conv: bad NCHW fp32 head output request");
   // CTA pairs need an N tile that splits into two halves of whole 8-row core groups (BN % 16 == 0 always holds)
   static const bool one_cta = getenv("B200DIFF_CONV_1CTA") != nullptr;
   if (d->act_dtype == B200_F16)

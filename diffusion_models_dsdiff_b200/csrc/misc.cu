@@ -177,6 +177,12 @@ __global__ void timestep_embedding_kernel(const float *__restrict__ t_table, con
   }
 }
 
+__global__ void gather_row_kernel(const float *__restrict__ table, const int *__restrict__ step_ptr,
+                                  float *__restrict__ out, int width) {
+  const float *src = table + (size_t)(*step_ptr) * width;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < width; i += gridDim.x * blockDim.x) out[i] = src[i];
+}
+
 // out[b][o] = bias[o] + sum_k f(in[b][k]) W[o][k]; one warp per output row o, all (<= 8 per pass) b.
 template <int BT>
 __global__ void __launch_bounds__(256)
@@ -391,6 +397,12 @@ extern "C" int b200_timestep_embedding(const float *t_table, const int *step_ptr
                                        int B, int dim, void *stream) {
   B200_CHECK(t_table && freqs && out && B > 0 && dim > 0, "timestep_embedding: bad arguments");
   timestep_embedding_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(t_table, step_ptr, freqs, out, B, dim);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int b200_gather_row_f32(const float *table, const int *step_ptr, float *out, int width, void *stream) {
+  B200_CHECK(table && step_ptr && out && width > 0, "gather_row: bad arguments");
+  gather_row_kernel<<<std::min(cdiv(width, 256), 64), 256, 0, (cudaStream_t)stream>>>(table, step_ptr, out, width);
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -125,6 +125,74 @@ channel_stats_kernel(const T *__restrict__ x, int C, int HW, int pix_per_block, 
   }
 }
 
+// dst = scale * (a + b + c + d) with the per-(image, channel) statistics of dst accumulated on the fly (DS-Diff skip mean,
+// UNet_DS_Diff/model.py:745, whose result feeds the decoder's GroupNorm).  Thread mapping as channel_stats_kernel.
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+add4_stats_kernel(const T *__restrict__ a, const T *__restrict__ b, const T *__restrict__ c, const T *__restrict__ d,
+                  float scale, T *__restrict__ dst, int C, int HW, int pix_per_block, double *__restrict__ sums) {
+  const int n = blockIdx.y;
+  const int ncol = C >> 3;
+  const int rows = kNormThreads / ncol;
+  const int col = threadIdx.x % ncol;
+  const int row = threadIdx.x / ncol;
+  if (row >= rows) return;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(HW, p_begin + pix_per_block);
+  float s[8] = {0}, q[8] = {0};
+  const size_t base = (size_t)n * HW * C + col * 8;
+  const int nin = 1 + (b != nullptr) + (c != nullptr) + (d != nullptr);
+  const T *src[4] = {a, b, c, d};
+  auto finish = [&](float (&f)[8], size_t off) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] *= scale;
+    const uint4 u = pack8_fast<T>(f);     // a mean of stored 16-bit values cannot overflow
+    st_stream(dst + off, u);
+    unpack8<T>(u, f);                     // statistics of the stored (rounded) values, like channel_stats on dst
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
+  };
+  int p = p_begin + row;
+  for (; p + rows < p_end; p += 2 * rows) {      // two pixels per trip: up to 8 independent 16-byte loads in flight
+    const size_t off0 = base + (size_t)p * C, off1 = off0 + (size_t)rows * C;
+    uint4 u0[4], u1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nin) { u0[j] = ld_stream(src[j] + off0); u1[j] = ld_stream(src[j] + off1); }
+    float f0[8] = {0}, f1[8] = {0}, g[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nin) {
+        unpack8<T>(u0[j], g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f0[i] += g[i];
+        unpack8<T>(u1[j], g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f1[i] += g[i];
+      }
+    finish(f0, off0);
+    finish(f1, off1);
+  }
+  for (; p < p_end; p += rows) {
+    const size_t off = base + (size_t)p * C;
+    float f[8] = {0}, g[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nin) {
+        unpack8<T>(ld_stream(src[j] + off), g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] += g[i];
+      }
+    finish(f, off);
+  }
+  double *o = sums + ((size_t)n * C + col * 8) * 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    atomicAdd(o + 2 * i, (double)s[i]);
+    atomicAdd(o + 2 * i + 1, (double)q[i]);
+  }
+}
+
 // y = silu?( (x - mean_g) * rstd_g * gamma_c + beta_c ) [ * (1 + scale_nc) + shift_nc ]
 template <typename T>
 __global__ void __launch_bounds__(kNormThreads)
@@ -198,7 +266,7 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
           float v = fmaf(f[i], a[i], b[i]);
           f[i] = silu ? silu_f(v) : v;
         }
-        *reinterpret_cast<uint4 *>(dst + (size_t)(p + j * rows) * C) = pack8<T>(f);
+        st_stream(dst + (size_t)(p + j * rows) * C, pack8_fast<T>(f));
       }
     }
     for (; p < p_end; p += rows) {
@@ -209,7 +277,7 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
         float v = fmaf(f[i], a[i], b[i]);
         f[i] = silu ? silu_f(v) : v;
       }
-      *reinterpret_cast<uint4 *>(dst + (size_t)p * C) = pack8<T>(f);
+      st_stream(dst + (size_t)p * C, pack8_fast<T>(f));
     }
   }
 }
@@ -297,6 +365,27 @@ extern "C" int b200_groupnorm_apply_cs(const void *x0, int C0, const double *cs0
   if (act_dtype == B200_BF16)
     return gn_apply<__nv_bfloat16>(x0, C0, x1, C1, N, HW, groups, eps, nullptr, cs0, cs1, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream);
   B200_CHECK(false, "groupnorm: bad act_dtype");
+}
+
+extern "C" int b200_add4_scale_stats(const void *a, const void *b, const void *c, const void *d, float scale, void *dst,
+                                     int N, int HW, int C, double *sums, int act_dtype, void *stream) {
+  using namespace b200;
+  B200_CHECK(a && dst && sums && N > 0 && HW > 0 && C > 0 && C % 8 == 0 && C <= 8 * kNormThreads,
+             "add4_scale_stats: bad arguments");
+  dim3 grid;
+  int ppb;
+  norm_grid(N, HW, C >> 3, &grid, &ppb);
+  if (act_dtype == B200_F16)
+    add4_stats_kernel<__half><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(
+        (const __half *)a, (const __half *)b, (const __half *)c, (const __half *)d, scale, (__half *)dst, C, HW, ppb, sums);
+  else if (act_dtype == B200_BF16)
+    add4_stats_kernel<__nv_bfloat16><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16 *)a, (const __nv_bfloat16 *)b, (const __nv_bfloat16 *)c, (const __nv_bfloat16 *)d, scale,
+        (__nv_bfloat16 *)dst, C, HW, ppb, sums);
+  else
+    B200_CHECK(false, "add4_scale_stats: bad act_dtype");
+  B200_LAUNCH_CHECK();
+  return 0;
 }
 
 extern "C" int b200_channel_stats(const void *x, int N, int HW, int C, double *sums, int act_dtype, void *stream) {

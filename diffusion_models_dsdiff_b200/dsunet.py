@@ -92,8 +92,7 @@ class DSUnetModel(_EngineModule):
             raise NotImplementedError("B200 engine: cross-attention context is not built yet")
         pw = self.packed()
         n = x.shape[0]
-        t_table = timesteps.to(torch.float32).contiguous() if step_ptr is not None else self._t_table(timesteps, n)
-        _, emb_all = self._temb(pw, self.time_embed, t_table, n, step_ptr)
+        emb_all = self._emb_all(pw, timesteps, n, step_ptr)
         self._arena.begin(x.device)
         cx = Ctx(pw, emb_all, self._arena)
         x = x.float()
@@ -128,8 +127,9 @@ class DSUnetModel(_EngineModule):
         ap = self.all_proj[1]
         h = run_conv(cx, [(ops.add4_scale(cat, silu=True), pw.conv[id(ap)], 0, 1, 0)], bias=_f(ap.bias))   # :738
         for blk in self.output_blocks:
-            skip = Act(ops.add4_scale(skips[0].pop().t, skips[1].pop().t, skips[2].pop().t, skips[3].pop().t,
-                                      scale=0.25))                                                       # :745
+            s0 = skips[0].pop().t
+            st = cx.stats_for(s0.shape[0], s0.shape[-1])
+            skip = Act(ops.add4_scale_stats(s0, skips[1].pop().t, skips[2].pop().t, skips[3].pop().t, 0.25, st), st)  # :745
             h = run_sequential(cx, blk, h, skip)
         out = run_out_head(cx, self.out, h).to(x.dtype)
         if not return_features:

@@ -133,7 +133,7 @@ Seg = Tuple[Tensor, Tensor, int, int, int]  # (src NHWC, packed weight, coff, ks
 
 def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
            rowbias: Optional[Tensor] = None, residual: Optional[Tensor] = None, res_scale: float = 1.0,
-           out: Optional[Tensor] = None, stats: Optional[Tensor] = None) -> Tensor:
+           out: Optional[Tensor] = None, stats: Optional[Tensor] = None, head_channels: int = 0) -> Tensor:
     """tcgen05 implicit-GEMM conv over up to 3 K-segments (see b200_conv2d_igemm)."""
     src0, w0, _, k0, p0 = segs[0]
     _dev(src0)
@@ -150,19 +150,24 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
             raise L.B200Error("conv2d: segment geometry mismatch")
         s = d.seg[i]
         s.src, s.weight, s.cin, s.wcin, s.coff, s.ksize, s.pad = _p(src), _p(wt), src.shape[3], wt.shape[2], coff, ks, pad
-    if out is None:
+    if head_channels:      # network head: fp32 NCHW output of the first head_channels (zero-padded N tile)
+        out = torch.empty((n, head_channels, hout, wout), device=src0.device, dtype=torch.float32)
+        d.out_nchw_f32, d.cout_real = _p(out), head_channels
+    elif out is None:
         out = torch.empty((n, hout, wout, cout), device=src0.device, dtype=src0.dtype)
     d.bias = _p(_f32(bias))
     d.rowbias, d.rowbias_stride = None, 0
     if rowbias is not None:       # may be a column slice of the batched emb projection
-        if _f32(rowbias).stride(-1) != 1 or rowbias.shape != (n, cout) or rowbias.data_ptr() % 16:
-            raise L.B200Error("conv2d: rowbias must be [N, Cout] fp32 with dense, 16B-aligned rows")
-        d.rowbias, d.rowbias_stride = rowbias.data_ptr(), rowbias.stride(0)
-    if residual is not None and (residual.shape != out.shape or residual.dtype != out.dtype):
+        if (_f32(rowbias).stride(-1) != 1 or rowbias.shape[1] != cout or rowbias.shape[0] not in (1, n)
+                or rowbias.data_ptr() % 16):
+            raise L.B200Error("conv2d: rowbias must be [N or 1, Cout] fp32 with dense, 16B-aligned rows")
+        d.rowbias = rowbias.data_ptr()
+        d.rowbias_stride = rowbias.stride(0) if rowbias.shape[0] == n and n > 1 else 0   # [1, Cout]: shared by the batch
+    if residual is not None and (head_channels or residual.shape != out.shape or residual.dtype != out.dtype):
         raise L.B200Error("conv2d: residual shape/dtype mismatch")
     d.residual = _p(residual)
     d.res_scale = res_scale
-    d.out = _p(out)
+    d.out = None if head_channels else _p(out)
     if stats is not None and (stats.dtype != torch.float64 or stats.numel() != n * cout * 2):
         raise L.B200Error("conv2d: stats must be a zeroed float64 [N, Cout, 2] tensor")
     d.gn_sums = _p(stats)
@@ -260,7 +265,7 @@ def group_norm(x0: Tensor, gamma: Tensor, beta: Tensor, x1: Optional[Tensor] = N
     lib = L.lib()
     out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=x0.dtype)
     film_p = None if film is None else film.data_ptr()
-    film_s = 0 if film is None else film.stride(0)
+    film_s = 0 if film is None or film.shape[0] == 1 else film.stride(0)   # [1, 2C]: shared by the batch
     if cs0 is not None and (x1 is None or cs1 is not None):
         _timed("groupnorm_silu", 0.0, 2.0 * 2.0 * out.numel(),
                lambda: L.check(lib.b200_groupnorm_apply_cs(_p(x0), c0, _p(cs0), _p(x1), c1, _p(cs1), n, hw, groups, eps,
@@ -339,6 +344,14 @@ def linear_f32(x: Tensor, w: Tensor, bias: Optional[Tensor], in_silu: bool = Fal
     return out
 
 
+def gather_row(table: Tensor, step_ptr: Tensor) -> Tensor:
+    """table [S, W] fp32, device int step -> [1, W] (the row of the current sampling step)."""
+    _dev(table)
+    out = torch.empty((1, table.shape[1]), device=table.device, dtype=torch.float32)
+    L.check(L.lib().b200_gather_row_f32(_p(_f32(table)), _p(step_ptr), _p(out), table.shape[1], _stream()), "gather_row")
+    return out
+
+
 def upsample_nearest2x(x: Tensor) -> Tensor:
     _dev(x)
     n, h, w, c = x.shape
@@ -357,6 +370,20 @@ def add4_scale(a: Tensor, b: Optional[Tensor] = None, c: Optional[Tensor] = None
     _timed("add4_scale", 0.0, 2.0 * a.numel() * (nin + 1),
            lambda: L.check(L.lib().b200_add4_scale(_p(a), _p(b), _p(c), _p(d), scale, _p(out), a.numel(), int(silu),
                                                    act_code(a.dtype), _stream()), "add4_scale"))
+    return out
+
+
+def add4_scale_stats(a: Tensor, b: Optional[Tensor], c: Optional[Tensor], d: Optional[Tensor], scale: float,
+                     stats: Tensor) -> Tensor:
+    """scale * (a + b + c + d) over NHWC tensors, accumulating the result's per-(image, channel) sums into ``stats``."""
+    _dev(a)
+    n, ch = a.shape[0], a.shape[-1]
+    hw = a.numel() // (n * ch)
+    out = torch.empty_like(a)
+    nin = 1 + (b is not None) + (c is not None) + (d is not None)
+    _timed("add4_scale", 0.0, 2.0 * a.numel() * (nin + 1),
+           lambda: L.check(L.lib().b200_add4_scale_stats(_p(a), _p(b), _p(c), _p(d), scale, _p(out), n, hw, ch, _p(stats),
+                                                         act_code(a.dtype), _stream()), "add4_scale_stats"))
     return out
 
 

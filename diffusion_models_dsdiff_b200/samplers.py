@@ -154,13 +154,14 @@ class StepEngine:
 
     def __init__(self, model_fn: Callable, mode: int, param: int, coef: Tensor, t_table: Tensor,
                  clip_denoised: bool, learned_range: bool = False, cache: Optional[dict] = None, cache_key=None,
-                 keepalive=None):
+                 keepalive=None, prepare: Optional[Callable] = None):
         self.model_fn, self.mode, self.param = model_fn, mode, param
         self.coef, self.t_table = coef, t_table
         self.clip, self.learned_range = clip_denoised, learned_range
         # captured graphs are reused across calls (the reference builds a new DDIMSampler per batch);
         # cache_key must change whenever the network's packed weights do, keepalive pins them
         self.cache, self.cache_key, self.keepalive = cache, cache_key, keepalive
+        self.prepare = prepare
         self.stats: dict = {}
 
     def _one(self, x: Tensor, cond: Optional[Sequence[Tensor]], step_ptr: Tensor, noise: Optional[Tensor],
@@ -182,6 +183,8 @@ class StepEngine:
         x = x_T.clone().float().contiguous()
         pred_x0 = torch.empty_like(x) if want_x0 else None
         step_ptr = torch.zeros(1, dtype=torch.int32, device=dev)
+        if self.prepare is not None:       # timestep MLP + emb projections for ALL steps, once per loop
+            self.prepare(self.t_table)
         if noises is not None or not use_graph or steps < 3:
             for i in range(steps):
                 out = self._one(x, cond, step_ptr, None if noises is None else noises[i].to(dev).float().contiguous(),
@@ -258,7 +261,8 @@ def _engine_model_fn(net):
 
 def _graph_cache_args(cache: dict, net) -> dict:
     pw = net.packed() if hasattr(net, "packed") else None
-    return {"cache": cache, "cache_key": (id(net), id(pw)), "keepalive": pw}
+    return {"cache": cache, "cache_key": (id(net), id(pw)), "keepalive": pw,
+            "prepare": getattr(net, "prepare_steps", None)}
 
 
 # ---------------------------------------------------------------------------------------------

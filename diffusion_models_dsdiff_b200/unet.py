@@ -267,18 +267,18 @@ def run_out_head(cx: Ctx, out: nn.Sequential, h: Act) -> Tensor:
     pw = cx.pw
     gn, conv = out[0], out[2]
     a = run_gn(cx, gn, h)
-    if conv.out_channels <= 4:
-        return ops.conv3x3_out(a, _f(conv.weight), _f(conv.bias))
+    # tensor-core path with the output channels zero-padded to one 16-wide N tile; the epilogue writes fp32 NCHW
     key = ("out", id(conv))
-    cpad = (conv.out_channels + 7) // 8 * 8
     if key not in pw.conv:
-        w = torch.zeros((cpad,) + tuple(conv.weight.shape[1:]), device=a.device)
+        w = torch.zeros((16,) + tuple(conv.weight.shape[1:]), device=a.device)
         w[:conv.out_channels] = conv.weight.detach().float()
-        b = torch.zeros(cpad, device=a.device)
+        b = torch.zeros(16, device=a.device)
         b[:conv.out_channels] = conv.bias.detach().float()
         pw.conv[key] = (ops.pack_conv_weight(w, a.dtype), b)
+    if conv.out_channels > 16:
+        raise B200Error("B200 engine: output heads wider than 16 channels are not supported")
     wp, bp = pw.conv[key]
-    return ops.nhwc_to_nchw(ops.conv2d([(a, wp, 0, 3, 1)], bias=bp), conv.out_channels)
+    return ops.conv2d([(a, wp, 0, 3, 1)], bias=bp, head_channels=conv.out_channels)
 
 
 class TimeEmbedding:
@@ -299,6 +299,23 @@ class TimeEmbedding:
         emb = ops.linear_f32(hid, _f(l2.weight), _f(l2.bias))
         emb_all = ops.linear_f32(emb, pw.emb_w, pw.emb_b, in_silu=True)
         return emb, emb_all
+
+    def prepare_steps(self, pw: PackedWeights, time_embed: nn.Sequential, t_table: Tensor) -> None:
+        """Sampling loops know every timestep up front and the whole timestep path depends on t only: evaluate it ONCE for
+        all S steps into a persistent [S, total] table (persistent = captured graphs keep pointing at it); each
+        replayed step then just selects its row (ops.gather_row)."""
+        s = int(t_table.numel())
+        _, tab = self(pw, time_embed, t_table, s)
+        if not hasattr(self, "tables"):
+            self.tables = {}
+        if s in self.tables and self.tables[s].shape == tab.shape:
+            self.tables[s].copy_(tab)
+        else:
+            self.tables[s] = tab
+
+    def step_row(self, steps: int, step_ptr: Tensor) -> Optional[Tensor]:
+        tab = getattr(self, "tables", {}).get(steps)
+        return None if tab is None else ops.gather_row(tab, step_ptr)
 
 
 class _EngineModule(nn.Module):
@@ -329,6 +346,23 @@ class _EngineModule(nn.Module):
                 self._pw = PackedWeights(self, self.act_dtype)
                 self._temb = TimeEmbedding(self.model_channels, dev)
         return self._pw
+
+    def prepare_steps(self, t_table: Tensor) -> None:
+        """Called by the sampling loops before (re)playing their step graph; see TimeEmbedding.prepare_steps."""
+        pw = self.packed()
+        with torch.no_grad():
+            self._temb.prepare_steps(pw, self.time_embed, t_table.to(torch.float32).contiguous())
+
+    def _emb_all(self, pw, timesteps: Tensor, n: int, step_ptr: Optional[Tensor]) -> Tensor:
+        """Batched emb_layers projections [N or 1, total] for this call."""
+        if step_ptr is not None:
+            row = self._temb.step_row(int(timesteps.numel()), step_ptr)
+            if row is not None:
+                return row
+            t_table = timesteps.to(torch.float32).contiguous()
+        else:
+            t_table = self._t_table(timesteps, n)
+        return self._temb(pw, self.time_embed, t_table, n, step_ptr)[1]
 
     @staticmethod
     def _t_table(timesteps: Tensor, batch: int) -> Tensor:
@@ -438,8 +472,7 @@ class UNetModel(_EngineModule):
             raise NotImplementedError("B200 engine: cross-attention context is not built yet")
         pw = self.packed()
         n = x.shape[0]
-        t_table = timesteps.to(torch.float32).contiguous() if step_ptr is not None else self._t_table(timesteps, n)
-        _, emb_all = self._temb(pw, self.time_embed, t_table, n, step_ptr)
+        emb_all = self._emb_all(pw, timesteps, n, step_ptr)
         self._arena.begin(x.device)
         cx = Ctx(pw, emb_all, self._arena)
         hs = []

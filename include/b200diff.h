@@ -91,6 +91,10 @@ typedef struct {
                               ACCUMULATED from the fp32 epilogue values for a following GroupNorm
                               (zero it first), or NULL                                */
   int act_dtype;
+  float *out_nchw_f32;     /* optional: write channels [0, cout_real) as NCHW fp32 [N,cout_real,Hout,Wout] INSTEAD of
+                              `out` — the network's last conv (self.out[2], openaimodel.py:898-902) whose 1-2 output
+                              channels are zero-padded to a 16-wide N tile; NULL otherwise                 */
+  int cout_real;
 } b200_conv_desc;
 int b200_conv2d_igemm(const b200_conv_desc *d, void *stream);
 
@@ -161,6 +165,10 @@ int b200_timestep_embedding(const float *t_table, const int *step_ptr, const flo
 int b200_linear_f32(const float *in, const float *W, const float *bias, float *out, int B, int K,
                     int O, int in_silu, int out_silu, void *stream);
 
+/* out[0:width] = table[*step_ptr][0:width]: selects the current step's row of a table precomputed for ALL sampling
+ * steps (the timestep MLP + every ResBlock's emb projection depend on t only), inside a replayed CUDA graph.      */
+int b200_gather_row_f32(const float *table, const int *step_ptr, float *out, int width, void *stream);
+
 /* ---- elementwise helpers ---------------------------------------------------------------------
  * nearest x2 upsample (Upsample.forward F.interpolate, openaimodel.py:113-117), NHWC.          */
 int b200_upsample_nearest2x(const void *src, void *dst, int N, int H, int W, int C, int act_dtype,
@@ -169,6 +177,10 @@ int b200_upsample_nearest2x(const void *src, void *dst, int N, int H, int W, int
  * (hs+hs_a+hs_al+hs_l)/4, UNet_DS_Diff/model.py:745; mean of FeatureDisentangle outputs :722.   */
 int b200_add4_scale(const void *a, const void *b, const void *c, const void *d, float scale,
                     void *dst, int64_t n, int silu, int act_dtype, void *stream);
+/* same, for NHWC [N,HW,C] tensors, also ACCUMULATING the per-(image, channel) statistics of dst (sums[N][C][2] fp64,
+ * zero first) for the GroupNorm that consumes the DS-Diff skip mean.                                             */
+int b200_add4_scale_stats(const void *a, const void *b, const void *c, const void *d, float scale, void *dst,
+                          int N, int HW, int C, double *sums, int act_dtype, void *stream);
 /* SE_Attention (Disc_diff/guided_diffusion/unet.py:105-109): x * sigmoid(W2 relu(W1 avgpool(x))). */
 int b200_se_attention(const void *x, const float *w1, const float *w2, void *out, float *scratch,
                       int N, int HW, int C, int Cr, int act_dtype, void *stream);
