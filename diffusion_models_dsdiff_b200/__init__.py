@@ -8,9 +8,10 @@ All arithmetic runs in libb200diff.so (include/b200diff.h); there is no CPU fall
 from ._lib import B200Error, LIB_PATH, launch_count  # noqa: F401
 from .unet import UNetModel  # noqa: F401
 from .dsunet import DSUnetModel  # noqa: F401
+from .autoencoder import AutoencoderKL, DiagonalGaussianDistribution  # noqa: F401
 from .samplers import (DDPM, DDIMSampler, DiffusionWrapper, GaussianDiffusion, SpacedDiffusion,  # noqa: F401
                        create_gaussian_diffusion, instantiate_from_config, space_timesteps)
 
-__all__ = ["B200Error", "LIB_PATH", "launch_count", "UNetModel", "DSUnetModel", "DDPM", "DDIMSampler",
+__all__ = ["B200Error", "LIB_PATH", "launch_count", "UNetModel", "DSUnetModel", "AutoencoderKL", "DiagonalGaussianDistribution", "DDPM", "DDIMSampler",
            "DiffusionWrapper", "GaussianDiffusion", "SpacedDiffusion", "create_gaussian_diffusion",
            "instantiate_from_config", "space_timesteps"]

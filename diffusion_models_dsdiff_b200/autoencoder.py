@@ -1,0 +1,385 @@
+"""Drop-in ``AutoencoderKL`` (ldm/models/autoencoder.py:26-147) and its ``Encoder`` / ``Decoder``
+(ldm/modules/diffusionmodules/model.py:452-652) on libb200diff.
+
+Same constructor keywords (``ddconfig``, ``embed_dim`` ...), the same ``encode(x) -> DiagonalGaussianDistribution`` /
+``decode(z) -> Tensor`` surface and the same ``state_dict`` keys (``encoder.down.0.block.0.norm1.weight`` ...,
+``decoder.up.2.upsample.conv.weight``, ``quant_conv`` / ``post_quant_conv``) as the reference; keys of the training
+loss (``loss.*``) are ignored on load.  The ``torch.nn`` modules are parameter containers; compute runs through the
+same sm_100a kernels as the UNet (unet.py): GroupNorm(eps 1e-6)+swish in one pass from producer-side statistics,
+tcgen05 implicit-GEMM 3x3 / 1x1 convolutions with the shortcut fused as an extra K-segment, the asymmetric-pad
+stride-2 Downsample (model.py:80-85) as a strided TMA box whose right/bottom overhang is zero-filled, and the
+single-head AttnBlock (model.py:179-202; d = C = 512, L up to 4096) as three tensor-core GEMMs around an fp32 row
+softmax — q k^T is produced in fp32 straight from the accumulators.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import B200Error
+from .unet import Act, Ctx, PackedWeights, _f, default_act_dtype, run_conv, run_gn
+
+Tensor = torch.Tensor
+
+
+def Normalize(in_channels, num_groups=32):
+    return nn.GroupNorm(num_groups=num_groups, num_channels=in_channels, eps=1e-6, affine=True)   # model.py:46-47
+
+
+class Upsample(nn.Module):
+    def __init__(self, in_channels, with_conv):
+        super().__init__()
+        self.with_conv = with_conv
+        if with_conv:
+            self.conv = nn.Conv2d(in_channels, in_channels, 3, 1, 1)
+
+
+class Downsample(nn.Module):
+    def __init__(self, in_channels, with_conv):
+        super().__init__()
+        self.with_conv = with_conv
+        if with_conv:
+            self.conv = nn.Conv2d(in_channels, in_channels, 3, 2, 0)
+
+
+class ResnetBlock(nn.Module):
+    def __init__(self, *, in_channels, out_channels=None, conv_shortcut=False, dropout, temb_channels=512):
+        super().__init__()
+        self.in_channels = in_channels
+        out_channels = in_channels if out_channels is None else out_channels
+        self.out_channels = out_channels
+        self.use_conv_shortcut = conv_shortcut
+        self.norm1 = Normalize(in_channels)
+        self.conv1 = nn.Conv2d(in_channels, out_channels, 3, 1, 1)
+        if temb_channels > 0:
+            self.temb_proj = nn.Linear(temb_channels, out_channels)
+        self.norm2 = Normalize(out_channels)
+        self.dropout = nn.Dropout(dropout)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, 3, 1, 1)
+        if in_channels != out_channels:
+            if conv_shortcut:
+                self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 3, 1, 1)
+            else:
+                self.nin_shortcut = nn.Conv2d(in_channels, out_channels, 1, 1, 0)
+
+
+class AttnBlock(nn.Module):
+    def __init__(self, in_channels):
+        super().__init__()
+        self.in_channels = in_channels
+        self.norm = Normalize(in_channels)
+        self.q = nn.Conv2d(in_channels, in_channels, 1)
+        self.k = nn.Conv2d(in_channels, in_channels, 1)
+        self.v = nn.Conv2d(in_channels, in_channels, 1)
+        self.proj_out = nn.Conv2d(in_channels, in_channels, 1)
+
+
+def make_attn(in_channels, attn_type="vanilla"):
+    if attn_type == "none":
+        return nn.Identity()
+    if attn_type not in ("vanilla", "vanilla-xformers"):
+        raise NotImplementedError(f"B200 engine: attn_type {attn_type!r} is not built")
+    return AttnBlock(in_channels)
+
+
+def _level(block, attn, **extra):
+    m = nn.Module()
+    m.block, m.attn = block, attn
+    for k, v in extra.items():
+        setattr(m, k, v)
+    return m
+
+
+class Encoder(nn.Module):
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0,
+                 resamp_with_conv=True, in_channels, resolution, z_channels, double_z=True, use_linear_attn=False,
+                 attn_type="vanilla", **ignore_kwargs):
+        super().__init__()
+        self.ch, self.temb_ch = ch, 0
+        self.num_resolutions, self.num_res_blocks = len(ch_mult), num_res_blocks
+        self.resolution, self.in_channels = resolution, in_channels
+        self.conv_in = nn.Conv2d(in_channels, ch, 3, 1, 1)
+        curr_res = resolution
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList()
+        for i_level in range(self.num_resolutions):
+            block, attn = nn.ModuleList(), nn.ModuleList()
+            block_in, block_out = ch * in_ch_mult[i_level], ch * ch_mult[i_level]
+            for _ in range(num_res_blocks):
+                block.append(ResnetBlock(in_channels=block_in, out_channels=block_out, temb_channels=0, dropout=dropout))
+                block_in = block_out
+                if curr_res in attn_resolutions:
+                    attn.append(make_attn(block_in, attn_type))
+            down = _level(block, attn)
+            if i_level != self.num_resolutions - 1:
+                down.downsample = Downsample(block_in, resamp_with_conv)
+                curr_res //= 2
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=0, dropout=dropout)
+        self.mid.attn_1 = make_attn(block_in, attn_type)
+        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=0, dropout=dropout)
+        self.norm_out = Normalize(block_in)
+        self.conv_out = nn.Conv2d(block_in, 2 * z_channels if double_z else z_channels, 3, 1, 1)
+
+
+class Decoder(nn.Module):
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0,
+                 resamp_with_conv=True, in_channels, resolution, z_channels, give_pre_end=False, tanh_out=False,
+                 use_linear_attn=False, attn_type="vanilla", **ignorekwargs):
+        super().__init__()
+        self.ch, self.temb_ch = ch, 0
+        self.num_resolutions, self.num_res_blocks = len(ch_mult), num_res_blocks
+        self.resolution, self.in_channels = resolution, in_channels
+        self.give_pre_end, self.tanh_out = give_pre_end, tanh_out
+        block_in = ch * ch_mult[self.num_resolutions - 1]
+        curr_res = resolution // 2 ** (self.num_resolutions - 1)
+        self.z_shape = (1, z_channels, curr_res, curr_res)
+        self.conv_in = nn.Conv2d(z_channels, block_in, 3, 1, 1)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=0, dropout=dropout)
+        self.mid.attn_1 = make_attn(block_in, attn_type)
+        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=0, dropout=dropout)
+        self.up = nn.ModuleList()
+        for i_level in reversed(range(self.num_resolutions)):
+            block, attn = nn.ModuleList(), nn.ModuleList()
+            block_out = ch * ch_mult[i_level]
+            for _ in range(num_res_blocks + 1):
+                block.append(ResnetBlock(in_channels=block_in, out_channels=block_out, temb_channels=0, dropout=dropout))
+                block_in = block_out
+                if curr_res in attn_resolutions:
+                    attn.append(make_attn(block_in, attn_type))
+            up = _level(block, attn)
+            if i_level != 0:
+                up.upsample = Upsample(block_in, resamp_with_conv)
+                curr_res *= 2
+            self.up.insert(0, up)
+        self.norm_out = Normalize(block_in)
+        self.conv_out = nn.Conv2d(block_in, out_ch, 3, 1, 1)
+
+
+class DiagonalGaussianDistribution(object):
+    """ldm/modules/distributions/distributions.py:24-62; ``sample`` / ``mode`` run the fused kernel."""
+
+    def __init__(self, parameters, deterministic=False):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.deterministic = deterministic
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+        if deterministic:
+            self.var = self.std = torch.zeros_like(self.mean)
+
+    def sample(self, noise: Optional[Tensor] = None):
+        if self.deterministic:
+            return self.mode()
+        if noise is None:
+            noise = torch.randn(self.mean.shape, device=self.parameters.device)
+        return ops.gaussian_sample(self.parameters, noise.contiguous())
+
+    def mode(self):
+        return ops.gaussian_sample(self.parameters, None)
+
+    def kl(self, other=None):
+        if self.deterministic:
+            return torch.Tensor([0.])
+        if other is None:
+            return 0.5 * torch.sum(torch.pow(self.mean, 2) + self.var - 1.0 - self.logvar, dim=[1, 2, 3])
+        return 0.5 * torch.sum(torch.pow(self.mean - other.mean, 2) / other.var + self.var / other.var - 1.0
+                               - self.logvar + other.logvar, dim=[1, 2, 3])
+
+
+# ---------------------------------------------------------------------------------------------
+# engine
+# ---------------------------------------------------------------------------------------------
+def _run_resnet(cx: Ctx, m: ResnetBlock, x: Act) -> Act:
+    """ResnetBlock.forward with temb=None (model.py:129-149)."""
+    pw = cx.pw
+    a = run_gn(cx, m.norm1, x)
+    h = run_conv(cx, [(a, pw.conv[id(m.conv1)], 0, 3, 1)], bias=_f(m.conv1.bias))
+    a2 = run_gn(cx, m.norm2, h)
+    segs = [(a2, pw.conv[id(m.conv2)], 0, 3, 1)]
+    bias, residual = _f(m.conv2.bias), None
+    if m.in_channels != m.out_channels:
+        sc = m.conv_shortcut if m.use_conv_shortcut else m.nin_shortcut
+        ks = sc.kernel_size[0]
+        segs.append((x.t, pw.conv[id(sc)], 0, ks, ks // 2))
+        key = ("b2", id(m))
+        if key not in pw.conv:
+            pw.conv[key] = (_f(m.conv2.bias) + _f(sc.bias)).contiguous()
+        bias = pw.conv[key]
+    else:
+        residual = x.t
+    return run_conv(cx, segs, bias=bias, residual=residual)
+
+
+def _run_attn(cx: Ctx, m: nn.Module, x: Act) -> Act:
+    """AttnBlock.forward (model.py:179-202): softmax(q k^T c^-1/2) v, single head of width C."""
+    if isinstance(m, nn.Identity):
+        return x
+    pw = cx.pw
+    n, h, w, c = x.t.shape
+    hw = h * w
+    if hw % 8:
+        raise B200Error("B200 engine: AttnBlock needs H*W to be a multiple of 8")
+    a = run_gn(cx, m.norm, x, silu=False)
+    q = ops.conv2d([(a, pw.conv[id(m.q)], 0, 1, 0)], bias=_f(m.q.bias))
+    k = ops.conv2d([(a, pw.conv[id(m.k)], 0, 1, 0)], bias=_f(m.k.bias))
+    # V^T[c, j] = sum_k Wv[c, k] a[j, k]: the packed weight rows play the pixels, the activations play the weights;
+    # v's bias is added after the attention average (softmax rows sum to one)
+    wv = pw.conv[id(m.v)]                              # [1, C, C] 16-bit
+    wrow = 32 if c % 32 == 0 else 8
+    wv_img = wv.view(1, c // wrow, wrow, c)
+    att = torch.empty_like(x.t)
+    for b in range(n):
+        logits = ops.conv2d([(q[b:b + 1], k[b].reshape(1, hw, c), 0, 1, 0)], out_f32=True)       # [1,h,w,hw] fp32
+        p = ops.softmax_rows(logits, float(int(c) ** (-0.5)), x.t.dtype)
+        vt = ops.conv2d([(wv_img, a[b].reshape(1, hw, c), 0, 1, 0)])                               # [1,c/32,32,hw] = V^T
+        ops.conv2d([(p, vt.view(1, c, hw), 0, 1, 0)], bias=_f(m.v.bias), out=att[b:b + 1])
+    return run_conv(cx, [(att, pw.conv[id(m.proj_out)], 0, 1, 0)], bias=_f(m.proj_out.bias), residual=x.t)
+
+
+def _in_conv(cx: Ctx, conv: nn.Conv2d, x: Tensor, dtype) -> Act:
+    if conv.in_channels > 8:
+        raise B200Error("B200 engine: autoencoder conv_in supports at most 8 input channels")
+    return Act(ops.conv3x3_in(x.float().contiguous(), _f(conv.weight), _f(conv.bias), dtype))
+
+
+def _out_conv(cx: Ctx, norm: nn.GroupNorm, conv: nn.Conv2d, h: Act) -> Tensor:
+    pw = cx.pw
+    a = run_gn(cx, norm, h)
+    if conv.out_channels > 16:
+        raise B200Error("B200 engine: autoencoder conv_out supports at most 16 output channels")
+    key = ("out", id(conv))
+    if key not in pw.conv:
+        wt = torch.zeros((16,) + tuple(conv.weight.shape[1:]), device=a.device)
+        wt[:conv.out_channels] = conv.weight.detach().float()
+        b = torch.zeros(16, device=a.device)
+        b[:conv.out_channels] = conv.bias.detach().float()
+        pw.conv[key] = (ops.pack_conv_weight(wt, a.dtype), b)
+    wp, bp = pw.conv[key]
+    return ops.conv2d([(a, wp, 0, 3, 1)], bias=bp, head_channels=conv.out_channels)
+
+
+def run_encoder(cx: Ctx, enc: Encoder, x: Tensor, dtype) -> Tensor:
+    """Encoder.forward (model.py:518-543): NCHW fp32 image -> NCHW fp32 moments (before quant_conv)."""
+    pw = cx.pw
+    h = _in_conv(cx, enc.conv_in, x, dtype)
+    for i_level in range(enc.num_resolutions):
+        lvl = enc.down[i_level]
+        for i_block in range(enc.num_res_blocks):
+            h = _run_resnet(cx, lvl.block[i_block], h)
+            if len(lvl.attn) > 0:
+                h = _run_attn(cx, lvl.attn[i_block], h)
+        if i_level != enc.num_resolutions - 1:
+            ds = lvl.downsample
+            if not ds.with_conv:
+                raise NotImplementedError("B200 engine: Downsample(with_conv=False) is not built")
+            n, hh, ww, _ = h.t.shape
+            # F.pad(x, (0,1,0,1)) + conv3x3 stride 2 pad 0 (model.py:80-85): the box overhang is zero-filled by TMA
+            h = run_conv(cx, [(h.t, pw.conv[id(ds.conv)], 0, 3, 0)], stride=2, bias=_f(ds.conv.bias),
+                         out_hw=(hh // 2, ww // 2))
+    h = _run_resnet(cx, enc.mid.block_1, h)
+    h = _run_attn(cx, enc.mid.attn_1, h)
+    h = _run_resnet(cx, enc.mid.block_2, h)
+    return _out_conv(cx, enc.norm_out, enc.conv_out, h)
+
+
+def run_decoder(cx: Ctx, dec: Decoder, z: Tensor, dtype) -> Tensor:
+    """Decoder.forward (model.py:619-652): NCHW fp32 latent (after post_quant_conv) -> NCHW fp32 image."""
+    pw = cx.pw
+    if dec.give_pre_end or dec.tanh_out:
+        raise NotImplementedError("B200 engine: give_pre_end / tanh_out are not built")
+    h = _in_conv(cx, dec.conv_in, z, dtype)
+    h = _run_resnet(cx, dec.mid.block_1, h)
+    h = _run_attn(cx, dec.mid.attn_1, h)
+    h = _run_resnet(cx, dec.mid.block_2, h)
+    for i_level in reversed(range(dec.num_resolutions)):
+        lvl = dec.up[i_level]
+        for i_block in range(dec.num_res_blocks + 1):
+            h = _run_resnet(cx, lvl.block[i_block], h)
+            if len(lvl.attn) > 0:
+                h = _run_attn(cx, lvl.attn[i_block], h)
+        if i_level != 0:
+            h = Act(ops.upsample_nearest2x(h.t))
+            if lvl.upsample.with_conv:
+                h = run_conv(cx, [(h.t, pw.conv[id(lvl.upsample.conv)], 0, 3, 1)], bias=_f(lvl.upsample.conv.bias))
+    return _out_conv(cx, dec.norm_out, dec.conv_out, h)
+
+
+class AutoencoderKL(nn.Module):
+    """ldm.models.autoencoder.AutoencoderKL — inference surface (encode / decode / forward)."""
+
+    def __init__(self, ddconfig, lossconfig=None, embed_dim=None, ckpt_path=None, ignore_keys=(), image_key="image",
+                 colorize_nlabels=None, monitor=None, ema_decay=None, learn_logvar=False, train_from_hgf=False,
+                 only_finetune_decoder=False, training_opt=None, act_dtype: Optional[torch.dtype] = None):
+        super().__init__()
+        ddconfig = dict(ddconfig)
+        self.image_key = image_key
+        if not train_from_hgf:                 # autoencoder.py:46-48: single-channel MRI / PET slices
+            ddconfig["in_channels"] = 1
+            ddconfig["out_ch"] = 1
+        assert ddconfig["double_z"]
+        self.encoder = Encoder(**ddconfig)
+        self.decoder = Decoder(**ddconfig)
+        self.quant_conv = nn.Conv2d(2 * ddconfig["z_channels"], 2 * embed_dim, 1)
+        self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
+        self.embed_dim = embed_dim
+        self.act_dtype = act_dtype or default_act_dtype()
+        self._pw: Optional[PackedWeights] = None
+        self._arena = ops.StatsArena()
+        self.register_load_state_dict_post_hook(lambda mod, keys: mod.invalidate())
+        if ckpt_path is not None:
+            self.init_from_ckpt(ckpt_path, ignore_keys=ignore_keys)
+
+    def invalidate(self):
+        self._pw = None
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def init_from_ckpt(self, path, ignore_keys=()):
+        sd = torch.load(path, map_location="cpu")["state_dict"]
+        for k in list(sd.keys()):
+            if any(k.startswith(ik) for ik in ignore_keys):
+                del sd[k]
+        self.load_state_dict(sd, strict=False)
+        print(f"Restored from {path}")
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        # the reference checkpoint also carries the training loss (LPIPS + discriminator): not part of inference
+        sd = {k: v for k, v in state_dict.items() if not k.startswith("loss.")}
+        return super().load_state_dict(sd, strict=strict, **kw)
+
+    def _ctx(self, device) -> Ctx:
+        if device.type != "cuda":
+            raise B200Error("the B200 engine has no CPU path: move the module and its input to a CUDA device")
+        if self._pw is None or self._pw.dtype != self.act_dtype:
+            with torch.no_grad():
+                self._pw = PackedWeights(self, self.act_dtype)
+        self._arena.begin(device)
+        return Ctx(self._pw, None, self._arena)
+
+    @torch.no_grad()
+    def encode(self, x):
+        cx = self._ctx(x.device)
+        h = run_encoder(cx, self.encoder, x, self.act_dtype)
+        moments = ops.conv1x1_f32(h, _f(self.quant_conv.weight), _f(self.quant_conv.bias))
+        return DiagonalGaussianDistribution(moments)
+
+    @torch.no_grad()
+    def decode(self, z):
+        cx = self._ctx(z.device)
+        z = ops.conv1x1_f32(z.float(), _f(self.post_quant_conv.weight), _f(self.post_quant_conv.bias))
+        return run_decoder(cx, self.decoder, z, self.act_dtype)
+
+    @torch.no_grad()
+    def forward(self, input, sample_posterior=True):
+        posterior = self.encode(input)
+        z = posterior.sample() if sample_posterior else posterior.mode()
+        return self.decode(z), posterior

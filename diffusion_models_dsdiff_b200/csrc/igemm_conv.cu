@@ -45,6 +45,7 @@ struct ConvKParams {
   void *out;
   double *gn_sums;
   uint32_t idesc;
+  float *out_f32_nhwc;       // NHWC fp32 output (attention logits) instead of `out`
   float *out_f32;            // NCHW fp32 output of the first cout_real channels (network head) instead of `out`
   int cout_real;
   int debug_skip_epilogue;   // B200DIFF_SKIP_EPI: timing experiments only (results are garbage)
@@ -370,7 +371,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) vh[i] += p.res_scale * rf[i];
             }
-            if (p.out_f32) {
+            if (p.out_f32_nhwc) {
+              float4 *o4 = reinterpret_cast<float4 *>(p.out_f32_nhwc + pix * p.Cout + cb);
+              o4[0] = make_float4(vh[0], vh[1], vh[2], vh[3]);
+              o4[1] = make_float4(vh[4], vh[5], vh[6], vh[7]);
+            } else if (p.out_f32) {
 #pragma unroll
               for (int i = 0; i < 8; ++i)
                 if (cb + i < p.cout_real)
@@ -466,7 +471,7 @@ static int launch_conv(const b200_conv_desc *d, cudaStream_t stream) {
   p.gn_sums = (p.TW * p.TH >= 32) ? d->gn_sums : nullptr;
   p.idesc = umma_idesc(Act<T>::kFmt, kBM * kCtas, p.BN);
   p.debug_skip_epilogue = getenv("B200DIFF_SKIP_EPI") != nullptr;
-  p.out_f32 = d->out_nchw_f32; p.cout_real = d->cout_real;
+  p.out_f32 = d->out_nchw_f32; p.cout_real = d->cout_real; p.out_f32_nhwc = d->out_nhwc_f32;
   // halo staging: 3x3 stride-1 pad-1 segments whose 128-pixel box lies in one image and is >= 8 pixels wide
   const bool halo_ok = d->stride == 1 && p.TN == 1 && p.TW >= 8 && !getenv("B200DIFF_NO_HALO");
   bool any_halo = false;
@@ -540,7 +545,7 @@ extern "C" int b200_conv2d_igemm(const b200_conv_desc *d, void *stream) {
   B200_CHECK(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2");
   B200_CHECK(d->Cout % 8 == 0, "conv: Cout must be a multiple of 8 (got %d)", d->Cout);
   B200_CHECK(d->N > 0 && d->Hout > 0 && d->Wout > 0, "conv: empty output");
-  B200_CHECK(d->out != nullptr || d->out_nchw_f32 != nullptr, "conv: no output pointer");
+  B200_CHECK(d->out != nullptr || d->out_nchw_f32 != nullptr || d->out_nhwc_f32 != nullptr, "conv: no output pointer");
   B200_CHECK(d->out_nchw_f32 == nullptr || (d->cout_real >= 1 && d->cout_real <= d->Cout && !d->gn_sums),
              "conv: bad NCHW fp32 head output request");
   // CTA pairs need an N tile that splits into two halves of whole 8-row core groups (BN % 16 == 0 always holds)

@@ -302,6 +302,81 @@ __global__ void se_scale_kernel(const T *__restrict__ x, const float *__restrict
   }
 }
 
+// row softmax: one block per row, fp32 in, 16-bit out
+template <typename T>
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float *__restrict__ s, T *__restrict__ p, int cols, float scale_log2e) {
+  __shared__ float red[8];
+  const float *row = s + (size_t)blockIdx.x * cols;
+  T *out = p + (size_t)blockIdx.x * cols;
+  float m = -INFINITY;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 v = *reinterpret_cast<const float4 *>(row + c);
+    m = fmaxf(fmaxf(m, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  const float mneg = -m * scale_log2e;
+  float l = 0.f;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 v = *reinterpret_cast<const float4 *>(row + c);
+    l += exp2f(fmaf(v.x, scale_log2e, mneg)) + exp2f(fmaf(v.y, scale_log2e, mneg)) +
+         exp2f(fmaf(v.z, scale_log2e, mneg)) + exp2f(fmaf(v.w, scale_log2e, mneg));
+  }
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l;
+  __syncthreads();
+  l = 0.f;
+  for (int i = 0; i < 8; ++i) l += red[i];
+  const float inv = 1.f / l;
+  for (int c = threadIdx.x * 4; c < cols; c += 1024) {
+    const float4 v = *reinterpret_cast<const float4 *>(row + c);
+    out[c + 0] = Act<T>::from_f(exp2f(fmaf(v.x, scale_log2e, mneg)) * inv);
+    out[c + 1] = Act<T>::from_f(exp2f(fmaf(v.y, scale_log2e, mneg)) * inv);
+    out[c + 2] = Act<T>::from_f(exp2f(fmaf(v.z, scale_log2e, mneg)) * inv);
+    out[c + 3] = Act<T>::from_f(exp2f(fmaf(v.w, scale_log2e, mneg)) * inv);
+  }
+}
+
+// fp32 NCHW pointwise convolution with a handful of channels (weights in registers via constant-size loops)
+__global__ void conv1x1_f32_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                   const float *__restrict__ bias, float *__restrict__ out, int N, int Cin, int Cout,
+                                   int HW) {
+  const long long total = (long long)N * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(i / HW), p = (int)(i % HW);
+    float in[16];
+    for (int c = 0; c < Cin; ++c) in[c] = x[((size_t)n * Cin + c) * HW + p];
+    for (int o = 0; o < Cout; ++o) {
+      float acc = bias ? bias[o] : 0.f;
+      for (int c = 0; c < Cin; ++c) acc = fmaf(in[c], __ldg(w + o * Cin + c), acc);
+      out[((size_t)n * Cout + o) * HW + p] = acc;
+    }
+  }
+}
+
+__global__ void gaussian_sample_kernel(const float *__restrict__ mom, const float *__restrict__ noise,
+                                       float *__restrict__ out, int N, int C, int HW) {
+  const long long total = (long long)N * C * HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long chw = (long long)C * HW;
+    const long long n = i / chw, r = i - n * chw;
+    const float mean = mom[n * 2 * chw + r];
+    float v = mean;
+    if (noise) {
+      const float lv = fminf(fmaxf(mom[n * 2 * chw + chw + r], -30.f), 20.f);
+      v = __fadd_rn(mean, __fmul_rn(expf(__fmul_rn(0.5f, lv)), noise[i]));
+    }
+    out[i] = v;
+  }
+}
+
 static int ew_blocks(long long n, int threads) {
   return (int)std::min<long long>(cdiv64(n, threads), (long long)num_sms() * 16);
 }
@@ -397,6 +472,29 @@ extern "C" int b200_timestep_embedding(const float *t_table, const int *step_ptr
                                        int B, int dim, void *stream) {
   B200_CHECK(t_table && freqs && out && B > 0 && dim > 0, "timestep_embedding: bad arguments");
   timestep_embedding_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(t_table, step_ptr, freqs, out, B, dim);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int b200_softmax_rows(const float *s_, void *p, int64_t rows, int cols, float scale, int act_dtype,
+                                 void *stream) {
+  B200_CHECK(s_ && p && rows > 0 && cols > 0 && cols % 4 == 0, "softmax_rows: cols must be a multiple of 4");
+  const float sl = scale * 1.4426950408889634f;
+  DISPATCH_ACT(act_dtype, softmax_rows_kernel<T><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(s_, (T *)p, cols, sl);)
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int b200_conv1x1_f32_nchw(const float *x, const float *w, const float *bias, float *out, int N, int Cin,
+                                     int Cout, int HW, void *stream) {
+  B200_CHECK(x && w && out && Cin >= 1 && Cin <= 16 && Cout >= 1 && Cout <= 16 && N > 0 && HW > 0,
+             "conv1x1_f32_nchw: 1..16 channels only");
+  conv1x1_f32_kernel<<<ew_blocks((long long)N * HW, 256), 256, 0, (cudaStream_t)stream>>>(x, w, bias, out, N, Cin, Cout, HW);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int b200_gaussian_sample(const float *moments, const float *noise, float *out, int N, int C, int HW,
+                                    void *stream) {
+  B200_CHECK(moments && out && N > 0 && C > 0 && HW > 0, "gaussian_sample: bad arguments");
+  gaussian_sample_kernel<<<ew_blocks((long long)N * C * HW, 256), 256, 0, (cudaStream_t)stream>>>(moments, noise, out, N, C, HW);
   B200_LAUNCH_CHECK();
   return 0;
 }

@@ -133,7 +133,8 @@ Seg = Tuple[Tensor, Tensor, int, int, int]  # (src NHWC, packed weight, coff, ks
 
 def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
            rowbias: Optional[Tensor] = None, residual: Optional[Tensor] = None, res_scale: float = 1.0,
-           out: Optional[Tensor] = None, stats: Optional[Tensor] = None, head_channels: int = 0) -> Tensor:
+           out: Optional[Tensor] = None, stats: Optional[Tensor] = None, head_channels: int = 0,
+           out_hw: Optional[Tuple[int, int]] = None, out_f32: bool = False) -> Tensor:
     """tcgen05 implicit-GEMM conv over up to 3 K-segments (see b200_conv2d_igemm)."""
     src0, w0, _, k0, p0 = segs[0]
     _dev(src0)
@@ -141,18 +142,23 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
     cout = w0.shape[1]
     hout = (hin + 2 * p0 - k0) // stride + 1
     wout = (win + 2 * p0 - k0) // stride + 1
+    if out_hw is not None:     # asymmetric (right/bottom) zero padding: the KL-autoencoder Downsample, model.py:80-85
+        hout, wout = out_hw
     d = L.ConvDesc()
     d.N, d.Hin, d.Win, d.Hout, d.Wout, d.Cout, d.stride, d.nseg = n, hin, win, hout, wout, cout, stride, len(segs)
     for i, (src, wt, coff, ks, pad) in enumerate(segs):
         if src.shape[:3] != src0.shape[:3] or src.dtype != src0.dtype or wt.dtype != src0.dtype:
             raise L.B200Error("conv2d: segments must share N,H,W and dtype")
-        if (hin + 2 * pad - ks) // stride + 1 != hout or wt.shape[1] != cout or wt.shape[0] != ks * ks:
+        if (out_hw is None and (hin + 2 * pad - ks) // stride + 1 != hout) or wt.shape[1] != cout or wt.shape[0] != ks * ks:
             raise L.B200Error("conv2d: segment geometry mismatch")
         s = d.seg[i]
         s.src, s.weight, s.cin, s.wcin, s.coff, s.ksize, s.pad = _p(src), _p(wt), src.shape[3], wt.shape[2], coff, ks, pad
     if head_channels:      # network head: fp32 NCHW output of the first head_channels (zero-padded N tile)
         out = torch.empty((n, head_channels, hout, wout), device=src0.device, dtype=torch.float32)
         d.out_nchw_f32, d.cout_real = _p(out), head_channels
+    elif out_f32:          # fp32 NHWC result (attention logits)
+        out = torch.empty((n, hout, wout, cout), device=src0.device, dtype=torch.float32)
+        d.out_nhwc_f32 = _p(out)
     elif out is None:
         out = torch.empty((n, hout, wout, cout), device=src0.device, dtype=src0.dtype)
     d.bias = _p(_f32(bias))
@@ -163,11 +169,11 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
             raise L.B200Error("conv2d: rowbias must be [N or 1, Cout] fp32 with dense, 16B-aligned rows")
         d.rowbias = rowbias.data_ptr()
         d.rowbias_stride = rowbias.stride(0) if rowbias.shape[0] == n and n > 1 else 0   # [1, Cout]: shared by the batch
-    if residual is not None and (head_channels or residual.shape != out.shape or residual.dtype != out.dtype):
+    if residual is not None and (head_channels or out_f32 or residual.shape != out.shape or residual.dtype != out.dtype):
         raise L.B200Error("conv2d: residual shape/dtype mismatch")
     d.residual = _p(residual)
     d.res_scale = res_scale
-    d.out = None if head_channels else _p(out)
+    d.out = None if (head_channels or out_f32) else _p(out)
     if stats is not None and (stats.dtype != torch.float64 or stats.numel() != n * cout * 2):
         raise L.B200Error("conv2d: stats must be a zeroed float64 [N, Cout, 2] tensor")
     d.gn_sums = _p(stats)
@@ -322,6 +328,38 @@ def attention(q: Tensor, k: Tensor, v: Tensor, heads: int, d: int, scale: float,
     a.scale, a.act_dtype, a.force_simt = scale, act_code(q.dtype), int(force_simt)
     _timed("attention", 4.0 * b * heads * lq * lk * d, 2.0 * (b * heads * d * (2 * lq + 2 * lk)),
            lambda: L.check(L.lib().b200_attention(C.byref(a), _stream()), "attention"))
+    return out
+
+
+def softmax_rows(s: Tensor, scale: float, dtype: torch.dtype) -> Tensor:
+    """softmax(scale * s, dim=-1): fp32 logits [..., cols] -> 16-bit probabilities."""
+    _dev(s)
+    cols = s.shape[-1]
+    out = torch.empty(s.shape, device=s.device, dtype=dtype)
+    _timed("softmax_rows", 0.0, 4.0 * s.numel() + 2.0 * s.numel(),
+           lambda: L.check(L.lib().b200_softmax_rows(_p(_f32(s)), _p(out), s.numel() // cols, cols, scale, act_code(dtype),
+                                                     _stream()), "softmax_rows"))
+    return out
+
+
+def conv1x1_f32(x: Tensor, w: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """fp32 NCHW pointwise conv with <= 16 channels (quant_conv / post_quant_conv)."""
+    _dev(x)
+    n, ci, h, wd = x.shape
+    co = w.shape[0]
+    out = torch.empty((n, co, h, wd), device=x.device, dtype=torch.float32)
+    L.check(L.lib().b200_conv1x1_f32_nchw(_p(_f32(x.contiguous())), _p(_f32(w.reshape(co, ci).contiguous())),
+                                          _p(_f32(bias)), _p(out), n, ci, co, h * wd, _stream()), "conv1x1_f32_nchw")
+    return out
+
+
+def gaussian_sample(moments: Tensor, noise: Optional[Tensor]) -> Tensor:
+    """mean + exp(0.5 * clamp(logvar, -30, 20)) * noise over moments [N, 2C, H, W]; noise None -> the mode."""
+    _dev(moments)
+    n, c2, h, w = moments.shape
+    out = torch.empty((n, c2 // 2, h, w), device=moments.device, dtype=torch.float32)
+    L.check(L.lib().b200_gaussian_sample(_p(_f32(moments.contiguous())), _p(_f32(noise)), _p(out), n, c2 // 2, h * w,
+                                         _stream()), "gaussian_sample")
     return out
 
 

@@ -95,6 +95,9 @@ typedef struct {
                               `out` — the network's last conv (self.out[2], openaimodel.py:898-902) whose 1-2 output
                               channels are zero-padded to a 16-wide N tile; NULL otherwise                 */
   int cout_real;
+  float *out_nhwc_f32;     /* optional: write the result as NHWC fp32 [N,Hout,Wout,Cout] INSTEAD of `out` (attention
+                              logits q k^T of the KL-autoencoder AttnBlock, ldm/modules/diffusionmodules/model.py:186-189,
+                              which must stay fp32 until the softmax); NULL otherwise                       */
 } b200_conv_desc;
 int b200_conv2d_igemm(const b200_conv_desc *d, void *stream);
 
@@ -153,6 +156,18 @@ typedef struct {
   int force_simt;
 } b200_attn_desc;
 int b200_attention(const b200_attn_desc *d, void *stream);
+
+/* p[r][c] = softmax_c(scale * s[r][c]) : fp32 logits [rows][cols] -> act probabilities [rows][cols]
+ * (torch.nn.functional.softmax(w_ * c**-0.5, dim=2), ldm/modules/diffusionmodules/model.py:189-190).              */
+int b200_softmax_rows(const float *s, void *p, int64_t rows, int cols, float scale, int act_dtype, void *stream);
+
+/* ---- KL-autoencoder edge ops (fp32 NCHW, a handful of channels) -------------------------------------------------
+ * 1x1 convolution with Cin, Cout <= 16: quant_conv / post_quant_conv (ldm/models/autoencoder.py:53-54,138-147).   */
+int b200_conv1x1_f32_nchw(const float *x, const float *w, const float *bias, float *out, int N, int Cin, int Cout,
+                          int HW, void *stream);
+/* DiagonalGaussianDistribution (ldm/modules/distributions/distributions.py:24-62) on moments [N,2C,HW]:
+ * mean = first C channels, logvar = clamp(second C, -30, 20); out = mean + exp(0.5*logvar) * noise (noise NULL -> mode). */
+int b200_gaussian_sample(const float *moments, const float *noise, float *out, int N, int C, int HW, void *stream);
 
 /* ---- small dense layers on [B,K] fp32 vectors (timestep path) --------------------------------
  * replaces timestep_embedding (util.py:161-181), time_embed MLP (openaimodel.py:606-610) and

@@ -300,6 +300,94 @@ def dsunet_forward(sd: SD, hp: dict, x: Tensor, t: Tensor, opq=None):
 
 
 # ----------------------------------------------------------------------------
+# KL autoencoder (first stage of the latent path)
+# ----------------------------------------------------------------------------
+def ae_resnet(sd: SD, p: str, x: Tensor, opq=None) -> Tensor:
+    """ResnetBlock.forward with temb=None.  ldm/modules/diffusionmodules/model.py:129-149 (Normalize eps 1e-6 :46-47)."""
+    h = silu(group_norm(x, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], eps=1e-6))
+    h = conv2d(sd, p + ".conv1", h, opq=opq)
+    h = silu(group_norm(h, sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], eps=1e-6))
+    h = conv2d(sd, p + ".conv2", h, opq=opq)
+    if p + ".nin_shortcut.weight" in sd:
+        x = conv2d(sd, p + ".nin_shortcut", x, padding=0, opq=opq)
+    elif p + ".conv_shortcut.weight" in sd:
+        x = conv2d(sd, p + ".conv_shortcut", x, opq=opq)
+    return x + h
+
+
+def ae_attn(sd: SD, p: str, x: Tensor, opq=None) -> Tensor:
+    """AttnBlock.forward (single head of width C).  model.py:179-202."""
+    h_ = group_norm(x, sd[p + ".norm.weight"], sd[p + ".norm.bias"], eps=1e-6)
+    q = conv2d(sd, p + ".q", h_, padding=0, opq=opq)
+    k = conv2d(sd, p + ".k", h_, padding=0, opq=opq)
+    v = conv2d(sd, p + ".v", h_, padding=0, opq=opq)
+    b, c, h, w = q.shape
+    q = q.reshape(b, c, h * w).permute(0, 2, 1)
+    k = k.reshape(b, c, h * w)
+    w_ = torch.bmm(_q(opq, q), _q(opq, k)) * (int(c) ** (-0.5))
+    w_ = F.softmax(w_, dim=2)
+    v = v.reshape(b, c, h * w)
+    h_ = torch.bmm(_q(opq, v), _q(opq, w_.permute(0, 2, 1))).reshape(b, c, h, w)
+    return x + conv2d(sd, p + ".proj_out", h_, padding=0, opq=opq)
+
+
+def ae_encoder(sd: SD, x: Tensor, p: str = "encoder", opq=None) -> Tensor:
+    """Encoder.forward; block structure from the keys.  model.py:518-543 (Downsample :80-85)."""
+    h = conv2d(sd, p + ".conv_in", x.float(), opq=opq)
+    levels = _sub_indices(sd, p + ".down.")
+    for i in levels:
+        for j in _sub_indices(sd, f"{p}.down.{i}.block."):
+            h = ae_resnet(sd, f"{p}.down.{i}.block.{j}", h, opq)
+            if f"{p}.down.{i}.attn.{j}.q.weight" in sd:
+                h = ae_attn(sd, f"{p}.down.{i}.attn.{j}", h, opq)
+        if f"{p}.down.{i}.downsample.conv.weight" in sd:
+            h = F.pad(h, (0, 1, 0, 1), mode="constant", value=0)
+            h = conv2d(sd, f"{p}.down.{i}.downsample.conv", h, stride=2, padding=0, opq=opq)
+    h = ae_resnet(sd, p + ".mid.block_1", h, opq)
+    h = ae_attn(sd, p + ".mid.attn_1", h, opq)
+    h = ae_resnet(sd, p + ".mid.block_2", h, opq)
+    h = silu(group_norm(h, sd[p + ".norm_out.weight"], sd[p + ".norm_out.bias"], eps=1e-6))
+    return conv2d(sd, p + ".conv_out", h, opq=opq)
+
+
+def ae_decoder(sd: SD, z: Tensor, p: str = "decoder", opq=None) -> Tensor:
+    """Decoder.forward.  model.py:619-652."""
+    h = conv2d(sd, p + ".conv_in", z.float(), opq=opq)
+    h = ae_resnet(sd, p + ".mid.block_1", h, opq)
+    h = ae_attn(sd, p + ".mid.attn_1", h, opq)
+    h = ae_resnet(sd, p + ".mid.block_2", h, opq)
+    for i in reversed(_sub_indices(sd, p + ".up.")):
+        for j in _sub_indices(sd, f"{p}.up.{i}.block."):
+            h = ae_resnet(sd, f"{p}.up.{i}.block.{j}", h, opq)
+            if f"{p}.up.{i}.attn.{j}.q.weight" in sd:
+                h = ae_attn(sd, f"{p}.up.{i}.attn.{j}", h, opq)
+        if f"{p}.up.{i}.upsample.conv.weight" in sd:
+            h = F.interpolate(h, scale_factor=2.0, mode="nearest")
+            h = conv2d(sd, f"{p}.up.{i}.upsample.conv", h, opq=opq)
+    h = silu(group_norm(h, sd[p + ".norm_out.weight"], sd[p + ".norm_out.bias"], eps=1e-6))
+    return conv2d(sd, p + ".conv_out", h, opq=opq)
+
+
+def ae_encode_moments(sd: SD, x: Tensor, opq=None) -> Tensor:
+    """AutoencoderKL.encode up to the posterior parameters.  ldm/models/autoencoder.py:138-142."""
+    return conv2d(sd, "quant_conv", ae_encoder(sd, x, opq=opq), padding=0)
+
+
+def ae_posterior_sample(moments: Tensor, noise: Optional[Tensor]) -> Tensor:
+    """DiagonalGaussianDistribution.sample / mode.  ldm/modules/distributions/distributions.py:24-62."""
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    if noise is None:
+        return mean
+    logvar = torch.clamp(logvar, -30.0, 20.0)
+    return mean + torch.exp(0.5 * logvar) * noise
+
+
+def ae_decode(sd: SD, z: Tensor, opq=None) -> Tensor:
+    """AutoencoderKL.decode.  ldm/models/autoencoder.py:144-147."""
+    return ae_decoder(sd, conv2d(sd, "post_quant_conv", z.float(), padding=0), opq=opq)
+
+
+# ----------------------------------------------------------------------------
 # schedules
 # ----------------------------------------------------------------------------
 def ldm_beta_schedule(schedule: str, n: int, linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3):

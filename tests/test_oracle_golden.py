@@ -130,3 +130,18 @@ def test_v3_v4_guided_diffusion(mode, eta, tag):
         assert maxabs(rec[i]["pred_x0"], g["pred_x0"][i]) < 1e-4, i
         assert maxabs(rec[i]["x_prev"], g["x_inter"][i]) < 1e-4, i
     assert maxabs(final, g["final"]) < 1e-4
+
+
+# -------------------------------------------------------------------------------------------------
+# KL autoencoder: oracle restatement vs the reference's AutoencoderKL outputs
+# -------------------------------------------------------------------------------------------------
+def test_autoencoder_oracle_matches_reference():
+    hp, sd = synth_sd("ae_small")
+    g = golden("ae_small")
+    mom = O.ae_encode_moments(sd, g["x"])
+    assert maxabs(mom, g["moments"]) < 2e-5
+    z = O.ae_posterior_sample(g["moments"], g["noise"])
+    assert maxabs(z, g["z"]) < 1e-6
+    assert maxabs(O.ae_posterior_sample(g["moments"], None), g["mode"]) == 0.0
+    dec = O.ae_decode(sd, g["z"])
+    assert maxabs(dec, g["dec"]) < 2e-5
