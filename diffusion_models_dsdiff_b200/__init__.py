@@ -9,9 +9,9 @@ from ._lib import B200Error, LIB_PATH, launch_count  # noqa: F401
 from .unet import UNetModel  # noqa: F401
 from .dsunet import DSUnetModel  # noqa: F401
 from .autoencoder import AutoencoderKL, DiagonalGaussianDistribution  # noqa: F401
-from .samplers import (DDPM, DDIMSampler, DiffusionWrapper, GaussianDiffusion, SpacedDiffusion,  # noqa: F401
+from .samplers import (DDPM, DDIMSampler, DiffusionWrapper, GaussianDiffusion, LatentDiffusion, SpacedDiffusion,  # noqa: F401
                        create_gaussian_diffusion, instantiate_from_config, space_timesteps)
 
-__all__ = ["B200Error", "LIB_PATH", "launch_count", "UNetModel", "DSUnetModel", "AutoencoderKL", "DiagonalGaussianDistribution", "DDPM", "DDIMSampler",
+__all__ = ["B200Error", "LIB_PATH", "launch_count", "UNetModel", "DSUnetModel", "AutoencoderKL", "DiagonalGaussianDistribution", "DDPM", "LatentDiffusion", "DDIMSampler",
            "DiffusionWrapper", "GaussianDiffusion", "SpacedDiffusion", "create_gaussian_diffusion",
            "instantiate_from_config", "space_timesteps"]

@@ -32,7 +32,7 @@ class ConvDesc(C.Structure):
                 ("Cout", C.c_int), ("stride", C.c_int), ("nseg", C.c_int), ("seg", ConvSeg * 3),
                 ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rowbias_stride", C.c_int),
                 ("residual", C.c_void_p), ("res_scale", C.c_float), ("out", C.c_void_p),
-                ("gn_sums", C.c_void_p), ("act_dtype", C.c_int), ("out_nchw_f32", C.c_void_p), ("cout_real", C.c_int), ("out_nhwc_f32", C.c_void_p)]
+                ("gn_sums", C.c_void_p), ("act_dtype", C.c_int), ("out_nchw_f32", C.c_void_p), ("cout_real", C.c_int), ("rowscale", C.c_void_p), ("rowscale_stride", C.c_int), ("epi_act", C.c_int), ("out_nhwc_f32", C.c_void_p)]
 
 
 class SamplerDesc(C.Structure):
@@ -70,6 +70,8 @@ SIGNATURES = {
     "b200_groupnorm_apply_cs": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _I, _I, _P, _I, _P],
     "b200_attention_qkv": [_P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
     "b200_attention": [C.POINTER(AttnDesc), _P],
+    "b200_layernorm": [_P, _P, _P, _P, _P, _I, _I, _L, _I, _F, _P, _I, _P],
+    "b200_geglu": [_P, _P, _L, _I, _I, _P],
     "b200_softmax_rows": [_P, _P, _L, _I, _F, _I, _P],
     "b200_conv1x1_f32_nchw": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "b200_gaussian_sample": [_P, _P, _P, _I, _I, _I, _P],

@@ -45,6 +45,9 @@ struct ConvKParams {
   void *out;
   double *gn_sums;
   uint32_t idesc;
+  const float *rowscale;     // per-(n, co) gate applied before the residual add (adaLN-Zero)
+  int rowscale_stride;
+  int epi_act;               // 1 = GELU(tanh)
   float *out_f32_nhwc;       // NHWC fp32 output (attention logits) instead of `out`
   float *out_f32;            // NCHW fp32 output of the first cout_real channels (network head) instead of `out`
   int cout_real;
@@ -364,6 +367,20 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
               vh[0] += b0.x; vh[1] += b0.y; vh[2] += b0.z; vh[3] += b0.w;
               vh[4] += b1.x; vh[5] += b1.y; vh[6] += b1.z; vh[7] += b1.w;
             }
+            if (p.epi_act == 1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float x = vh[i];
+                vh[i] = 0.5f * x * (1.f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
+              }
+            }
+            if (p.rowscale) {
+              const float *rs = p.rowscale + (size_t)n * p.rowscale_stride + cb;
+              const float4 g0 = __ldg(reinterpret_cast<const float4 *>(rs));
+              const float4 g1 = __ldg(reinterpret_cast<const float4 *>(rs + 4));
+              vh[0] *= g0.x; vh[1] *= g0.y; vh[2] *= g0.z; vh[3] *= g0.w;
+              vh[4] *= g1.x; vh[5] *= g1.y; vh[6] *= g1.z; vh[7] *= g1.w;
+            }
             if (res) {
               const uint4 ru = *reinterpret_cast<const uint4 *>(res + pix * p.Cout + cb);
               float rf[8];
@@ -472,6 +489,7 @@ static int launch_conv(const b200_conv_desc *d, cudaStream_t stream) {
   p.idesc = umma_idesc(Act<T>::kFmt, kBM * kCtas, p.BN);
   p.debug_skip_epilogue = getenv("B200DIFF_SKIP_EPI") != nullptr;
   p.out_f32 = d->out_nchw_f32; p.cout_real = d->cout_real; p.out_f32_nhwc = d->out_nhwc_f32;
+  p.rowscale = d->rowscale; p.rowscale_stride = d->rowscale_stride; p.epi_act = d->epi_act;
   // halo staging: 3x3 stride-1 pad-1 segments whose 128-pixel box lies in one image and is >= 8 pixels wide
   const bool halo_ok = d->stride == 1 && p.TN == 1 && p.TW >= 8 && !getenv("B200DIFF_NO_HALO");
   bool any_halo = false;

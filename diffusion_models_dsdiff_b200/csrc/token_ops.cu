@@ -1,0 +1,122 @@
+// Token-tensor kernels for the transformer blocks (SpatialTransformer, DiT): LayerNorm (+ adaLN modulate) and GEGLU over
+// [rows, C] 16-bit activations.  HBM-bound, one warp per row, 16-byte vector accesses.
+//
+// Replaces nn.LayerNorm in BasicTransformerBlock (ldm/modules/attention.py:319-331), the affine-free LayerNorm +
+// modulate(x, shift, scale) = x * (1 + scale) + shift of DiTBlock / FinalLayer (UNet_DS_Diff/DiT_models.py:19, 107-122,
+// 138-142), and GEGLU.forward x * F.gelu(gate) (ldm/modules/attention.py:49-56).
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kLnMaxVec = 8;   // per-lane 16-byte vectors: C <= 8 * 8 * 32 = 2048
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const T *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
+                 const float *__restrict__ shift, const float *__restrict__ scale, int mod_stride, int rows_per_batch,
+                 long long rows, int C, float eps, T *__restrict__ out) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int nvec = C >> 3;
+  const T *xr = x + row * C;
+  float v[kLnMaxVec][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLnMaxVec; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+      unpack8<T>(ld_stream(xr + vi * 8), v[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += v[j][i];
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < kLnMaxVec; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = v[j][i] - mean; sq += d * d; }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / (float)C + eps);
+  const long long b = row / rows_per_batch;
+  T *orow = out + row * C;
+#pragma unroll
+  for (int j = 0; j < kLnMaxVec; ++j) {
+    const int vi = lane + j * 32;
+    if (vi < nvec) {
+      const int c = vi * 8;
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float y = (v[j][i] - mean) * rstd;
+        if (gamma) y = fmaf(y, gamma[c + i], beta ? beta[c + i] : 0.f);
+        if (scale) y = fmaf(y, 1.f + scale[b * mod_stride + c + i], shift[b * mod_stride + c + i]);
+        f[i] = y;
+      }
+      st_stream(orow + c, pack8<T>(f));
+    }
+  }
+}
+
+__device__ __forceinline__ float gelu_erf(float g) { return 0.5f * g * (1.f + erff(g * 0.70710678118654752f)); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+geglu_kernel(const T *__restrict__ x, T *__restrict__ out, long long rows, int inner) {
+  const int nvec = inner >> 3;
+  const long long total = rows * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nvec;
+    const int c = (int)(i - r * nvec) * 8;
+    float a[8], g[8];
+    unpack8<T>(ld_stream(x + r * 2 * inner + c), a);
+    unpack8<T>(ld_stream(x + r * 2 * inner + inner + c), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] *= gelu_erf(g[k]);
+    st_stream(out + r * inner + c, pack8<T>(a));
+  }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" int b200_layernorm(const void *x, const float *gamma, const float *beta, const float *shift, const float *scale,
+                              int mod_stride, int rows_per_batch, int64_t rows, int C, float eps, void *out, int act_dtype,
+                              void *stream) {
+  B200_CHECK(x && out && rows > 0 && C > 0 && C % 8 == 0 && C <= 8 * 32 * kLnMaxVec, "layernorm: C must be a multiple of 8, <= 2048");
+  B200_CHECK((shift == nullptr) == (scale == nullptr), "layernorm: shift and scale come together");
+  B200_CHECK(rows_per_batch > 0, "layernorm: rows_per_batch must be positive");
+  const unsigned blocks = (unsigned)cdiv64(rows, 8);
+  if (act_dtype == B200_F16)
+    layernorm_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half *)x, gamma, beta, shift, scale, mod_stride,
+                                                                     rows_per_batch, rows, C, eps, (__half *)out);
+  else if (act_dtype == B200_BF16)
+    layernorm_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x, gamma, beta, shift, scale,
+                                                                            mod_stride, rows_per_batch, rows, C, eps,
+                                                                            (__nv_bfloat16 *)out);
+  else
+    B200_CHECK(false, "layernorm: bad act_dtype");
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_geglu(const void *x, void *out, int64_t rows, int inner, int act_dtype, void *stream) {
+  B200_CHECK(x && out && rows > 0 && inner > 0 && inner % 8 == 0, "geglu: inner width must be a multiple of 8");
+  const long long total = rows * (inner / 8);
+  const int blocks = (int)std::min<long long>(cdiv64(total, 256), (long long)num_sms() * 16);
+  if (act_dtype == B200_F16)
+    geglu_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half *)x, (__half *)out, rows, inner);
+  else if (act_dtype == B200_BF16)
+    geglu_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)out, rows, inner);
+  else
+    B200_CHECK(false, "geglu: bad act_dtype");
+  B200_LAUNCH_CHECK();
+  return 0;
+}

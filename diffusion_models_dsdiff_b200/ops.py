@@ -134,7 +134,8 @@ Seg = Tuple[Tensor, Tensor, int, int, int]  # (src NHWC, packed weight, coff, ks
 def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
            rowbias: Optional[Tensor] = None, residual: Optional[Tensor] = None, res_scale: float = 1.0,
            out: Optional[Tensor] = None, stats: Optional[Tensor] = None, head_channels: int = 0,
-           out_hw: Optional[Tuple[int, int]] = None, out_f32: bool = False) -> Tensor:
+           out_hw: Optional[Tuple[int, int]] = None, out_f32: bool = False, rowscale: Optional[Tensor] = None,
+           act: int = 0) -> Tensor:
     """tcgen05 implicit-GEMM conv over up to 3 K-segments (see b200_conv2d_igemm)."""
     src0, w0, _, k0, p0 = segs[0]
     _dev(src0)
@@ -169,6 +170,13 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
             raise L.B200Error("conv2d: rowbias must be [N or 1, Cout] fp32 with dense, 16B-aligned rows")
         d.rowbias = rowbias.data_ptr()
         d.rowbias_stride = rowbias.stride(0) if rowbias.shape[0] == n and n > 1 else 0   # [1, Cout]: shared by the batch
+    d.rowscale, d.rowscale_stride, d.epi_act = None, 0, int(act)
+    if rowscale is not None:      # adaLN-Zero gate, [N or 1, Cout] fp32 (may be a column slice)
+        if (_f32(rowscale).stride(-1) != 1 or rowscale.shape[1] != cout or rowscale.shape[0] not in (1, n)
+                or rowscale.data_ptr() % 16):
+            raise L.B200Error("conv2d: rowscale must be [N or 1, Cout] fp32 with dense, 16B-aligned rows")
+        d.rowscale = rowscale.data_ptr()
+        d.rowscale_stride = rowscale.stride(0) if rowscale.shape[0] == n and n > 1 else 0
     if residual is not None and (head_channels or out_f32 or residual.shape != out.shape or residual.dtype != out.dtype):
         raise L.B200Error("conv2d: residual shape/dtype mismatch")
     d.residual = _p(residual)
@@ -328,6 +336,36 @@ def attention(q: Tensor, k: Tensor, v: Tensor, heads: int, d: int, scale: float,
     a.scale, a.act_dtype, a.force_simt = scale, act_code(q.dtype), int(force_simt)
     _timed("attention", 4.0 * b * heads * lq * lk * d, 2.0 * (b * heads * d * (2 * lq + 2 * lk)),
            lambda: L.check(L.lib().b200_attention(C.byref(a), _stream()), "attention"))
+    return out
+
+
+def layer_norm(x: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], eps: float = 1e-5,
+               shift: Optional[Tensor] = None, scale: Optional[Tensor] = None) -> Tensor:
+    """LayerNorm over the last dim of tokens [B, L, C] (16-bit); optional adaLN modulation with fp32 shift / scale [B, C]
+    (column slices of a wider matrix are fine): y * (1 + scale[b]) + shift[b]."""
+    _dev(x)
+    b, l, c = x.shape
+    out = torch.empty_like(x)
+    ms = 0
+    if shift is not None:
+        if shift.stride(-1) != 1 or scale.stride(-1) != 1 or shift.stride(0) != scale.stride(0):
+            raise L.B200Error("layer_norm: shift / scale must be fp32 rows with the same pitch")
+        ms = shift.stride(0)
+    _timed("layernorm", 0.0, 4.0 * x.numel(),
+           lambda: L.check(L.lib().b200_layernorm(_p(x), _p(_f32(gamma)), _p(_f32(beta)),
+                                                  None if shift is None else _f32(shift).data_ptr(),
+                                                  None if scale is None else _f32(scale).data_ptr(), ms, l, b * l, c, eps,
+                                                  _p(out), act_code(x.dtype), _stream()), "layernorm"))
+    return out
+
+
+def geglu(x: Tensor) -> Tensor:
+    """tokens [B, L, 2I] -> [B, L, I] = x[..., :I] * gelu(x[..., I:])."""
+    _dev(x)
+    b, l, c2 = x.shape
+    out = torch.empty((b, l, c2 // 2), device=x.device, dtype=x.dtype)
+    _timed("geglu", 0.0, 2.0 * (x.numel() + out.numel()),
+           lambda: L.check(L.lib().b200_geglu(_p(x), _p(out), b * l, c2 // 2, act_code(x.dtype), _stream()), "geglu"))
     return out
 
 

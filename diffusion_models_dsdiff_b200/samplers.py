@@ -51,6 +51,7 @@ _PARAM = {"eps": L.PARAM_EPS, "x0": L.PARAM_X0, "v": L.PARAM_V}
 TARGET_ALIASES = {
     "ldm.modules.diffusionmodules.openaimodel.UNetModel": "diffusion_models_dsdiff_b200.unet.UNetModel",
     "UNet_DS_Diff.model.DSUnetModel": "diffusion_models_dsdiff_b200.dsunet.DSUnetModel",
+    "ldm.models.autoencoder.AutoencoderKL": "diffusion_models_dsdiff_b200.autoencoder.AutoencoderKL",
 }
 
 
@@ -154,7 +155,7 @@ class StepEngine:
 
     def __init__(self, model_fn: Callable, mode: int, param: int, coef: Tensor, t_table: Tensor,
                  clip_denoised: bool, learned_range: bool = False, cache: Optional[dict] = None, cache_key=None,
-                 keepalive=None, prepare: Optional[Callable] = None):
+                 keepalive=None, prepare: Optional[Callable] = None, context: Optional[Tensor] = None):
         self.model_fn, self.mode, self.param = model_fn, mode, param
         self.coef, self.t_table = coef, t_table
         self.clip, self.learned_range = clip_denoised, learned_range
@@ -162,12 +163,16 @@ class StepEngine:
         # cache_key must change whenever the network's packed weights do, keepalive pins them
         self.cache, self.cache_key, self.keepalive = cache, cache_key, keepalive
         self.prepare = prepare
+        self.context = context          # cross-attention conditioning [B, Lk, D], constant over the steps
         self.stats: dict = {}
 
     def _one(self, x: Tensor, cond: Optional[Sequence[Tensor]], step_ptr: Tensor, noise: Optional[Tensor],
              pred_x0: Optional[Tensor]):
         xc = x if not cond else torch.cat([x] + list(cond), dim=1)
-        out = self.model_fn(xc, self.t_table, step_ptr)
+        if self.context is not None:
+            out = self.model_fn(xc, self.t_table, step_ptr, context=self.context)
+        else:
+            out = self.model_fn(xc, self.t_table, step_ptr)
         if isinstance(out, tuple):
             out = out[0]
         z = noise if noise is not None else torch.randn_like(x)
@@ -199,7 +204,8 @@ class StepEngine:
         key = None
         if self.cache is not None:
             key = (self.cache_key, self.mode, self.param, self.clip, self.learned_range, tuple(x.shape),
-                   tuple(tuple(c.shape) for c in (cond or [])), steps, want_x0)
+                   tuple(tuple(c.shape) for c in (cond or [])), steps, want_x0,
+                   None if self.context is None else tuple(self.context.shape))
         entry = self.cache.get(key) if key is not None else None
         if entry is None:
             entry = self._capture(x, cond, pred_x0, step_ptr, key)
@@ -209,6 +215,8 @@ class StepEngine:
             entry["x"].copy_(x)
             for dst, src in zip(entry["cond"], cond or []):
                 dst.copy_(src)
+            if self.context is not None:
+                entry["context"].copy_(self.context)
             entry["step_ptr"].zero_()
             self.stats = {"graph_launches_per_step": entry["launches"], "graph_reused": True}
         xs, x0s = entry["x"], entry["pred_x0"]
@@ -226,6 +234,8 @@ class StepEngine:
         coef, t_table = self.coef.clone(), self.t_table.clone()
         self.coef, self.t_table = coef, t_table           # the captured kernels read these static tables
         cond = [c.clone().contiguous() for c in (cond or [])]
+        if self.context is not None:
+            self.context = self.context.clone().contiguous()      # static buffer read by the captured kernels
         gen_state = torch.cuda.get_rng_state(dev)
         scratch = x.clone()
         s = torch.cuda.Stream(device=dev)
@@ -243,7 +253,7 @@ class StepEngine:
         launches = L.launch_count() - n0
         # capture does not execute: x / step_ptr / RNG are untouched
         entry = {"graph": graph, "x": x, "cond": cond, "pred_x0": pred_x0, "step_ptr": step_ptr, "coef": coef,
-                 "t_table": t_table, "launches": launches, "keepalive": self.keepalive}
+                 "t_table": t_table, "launches": launches, "keepalive": self.keepalive, "context": self.context}
         self.stats = {"graph_launches_per_step": launches, "graph_reused": False}
         if key is not None:
             if len(self.cache) >= 4:            # bounded: each entry pins a private activation pool
@@ -256,7 +266,7 @@ def _engine_model_fn(net):
     """model_fn(xc, t_table, step_ptr) for a B200 engine network; the DS-Diff feature dict (discarded by
     every sampler, trainer_ds_diff.py:752-755 / gaussian_diffusion.py:278-279) is not materialised."""
     extra = {"return_features": False} if getattr(net, "_returns_features", False) else {}
-    return lambda xc, t_table, step_ptr: net(xc, t_table, step_ptr=step_ptr, **extra)
+    return lambda xc, t_table, step_ptr, **kw: net(xc, t_table, step_ptr=step_ptr, **extra, **kw)
 
 
 def _graph_cache_args(cache: dict, net) -> dict:
@@ -288,6 +298,11 @@ class DiffusionWrapper(nn.Module):
         if self.conditioning_key == "concat":
             xc = torch.cat([x] + list(c_concat), dim=1)
             return self.diffusion_model(xc, t, **kw)
+        if self.conditioning_key == "crossattn":
+            return self.diffusion_model(x, t, context=torch.cat(list(c_crossattn), 1), **kw)
+        if self.conditioning_key == "hybrid":
+            xc = torch.cat([x] + list(c_concat), dim=1)
+            return self.diffusion_model(xc, t, context=torch.cat(list(c_crossattn), 1), **kw)
         raise NotImplementedError(f"conditioning_key={self.conditioning_key!r} is not built in the B200 path yet")
 
 
@@ -412,11 +427,29 @@ class DDPM(nn.Module):
         return _coef_table({0: ca, 1: cb, 2: g("posterior_mean_coef1"), 3: g("posterior_mean_coef2"), 4: std}, len(t))
 
     def _cond_list(self, cond):
-        if cond is None or self.model.conditioning_key is None:
+        """The tensors DiffusionWrapper concatenates to x on the channel axis (ddpm.py:1331-1333)."""
+        key = self.model.conditioning_key
+        if cond is None or key is None or key == "crossattn":
             return None
         if isinstance(cond, dict):
             cond = cond.get("c_concat")
+            if cond is None:
+                return None
         return list(cond) if isinstance(cond, (list, tuple)) else [cond]
+
+    def _context(self, cond) -> Optional[Tensor]:
+        """The cross-attention context of the 'crossattn' / 'hybrid' keys: cat(c_crossattn, 1) (ddpm.py:1334-1347)."""
+        key = self.model.conditioning_key
+        if cond is None or key not in ("crossattn", "hybrid"):
+            return None
+        if isinstance(cond, dict):
+            cond = cond.get("c_crossattn")
+            if cond is None:
+                return None
+        elif key == "hybrid":
+            return None
+        cond = list(cond) if isinstance(cond, (list, tuple)) else [cond]
+        return torch.cat(cond, 1).float().contiguous()
 
     def _model_fn(self):
         return _engine_model_fn(self.model.diffusion_model)
@@ -444,7 +477,7 @@ class DDPM(nn.Module):
         coef = self._ddpm_coef(seq).to(device)
         t_table = torch.tensor(seq, dtype=torch.float32, device=device)
         eng = StepEngine(self._model_fn(), L.SAMPLER_LDM_DDPM, _PARAM[self.parameterization], coef, t_table,
-                         self.clip_denoised, **self._graph_cache_args())
+                         self.clip_denoised, context=self._context(cond), **self._graph_cache_args())
         self.last_engine = eng
         intermediates = [img]
 
@@ -461,6 +494,66 @@ class DDPM(nn.Module):
     def sample(self, batch_size=16, cond=None, shape=None, return_intermediates=False, *args, **kwargs):
         return self.p_sample_loop((batch_size, shape[0], shape[1], shape[2]), cond,
                                   return_intermediates=return_intermediates, **kwargs)
+
+
+class LatentDiffusion(DDPM):
+    """Sampling half of ldm LatentDiffusion (ldm/models/diffusion/ddpm.py:527-1128): a DDPM over first-stage latents.
+    ``first_stage_config`` is an AutoencoderKL module or an ``instantiate_from_config`` dict; conditioning arrives
+    already encoded (``c_concat`` latents and / or ``c_crossattn`` context), like the trainers pass it."""
+
+    def __init__(self, first_stage_config, cond_stage_config=None, num_timesteps_cond=None, cond_stage_key="image",
+                 cond_stage_trainable=False, concat_mode=True, cond_stage_forward=None, conditioning_key=None,
+                 scale_factor=1.0, scale_by_std=False, force_null_conditioning=False, *args, **kwargs):
+        if conditioning_key is None:
+            conditioning_key = "concat" if concat_mode else "crossattn"
+        if cond_stage_config == "__is_unconditional__" and not force_null_conditioning:
+            conditioning_key = None
+        super().__init__(*args, conditioning_key=conditioning_key, **kwargs)
+        self.scale_factor = scale_factor
+        self.first_stage_model = (first_stage_config if isinstance(first_stage_config, nn.Module)
+                                  else instantiate_from_config(first_stage_config)).eval()
+        for prm in self.first_stage_model.parameters():
+            prm.requires_grad = False
+        self.clip_denoised = False                      # ddpm.py:572
+
+    @torch.no_grad()
+    def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):
+        if predict_cids:
+            raise NotImplementedError("decode_first_stage(predict_cids=True) is not built in the B200 path")
+        return self.first_stage_model.decode(1. / self.scale_factor * z)
+
+    @torch.no_grad()
+    def encode_first_stage(self, x):
+        return self.first_stage_model.encode(x)
+
+    def get_first_stage_encoding(self, encoder_posterior):
+        z = encoder_posterior.sample() if hasattr(encoder_posterior, "sample") else encoder_posterior
+        return self.scale_factor * z
+
+    @torch.no_grad()
+    def p_sample_loop(self, cond, shape, return_intermediates=False, x_T=None, verbose=True, callback=None,
+                      timesteps=None, quantize_denoised=False, mask=None, x0=None, img_callback=None, start_T=None,
+                      log_every_t=None, noises=None, record=None):
+        if self.parameterization == "v":
+            raise NotImplementedError()                 # like LatentDiffusion.p_mean_variance (ddpm.py:941-946)
+        if quantize_denoised or mask is not None:
+            raise NotImplementedError("quantize_denoised / mask are not built in the B200 path")
+        n = self.num_timesteps if timesteps is None else timesteps
+        if start_T is not None:
+            n = min(n, start_T)
+        steps = list(reversed(range(0, n)))
+        if log_every_t:
+            self.log_every_t = log_every_t
+        return DDPM.p_sample_loop(self, shape, cond, return_intermediates=return_intermediates, x_T=x_T, noises=noises,
+                                  steps=steps, record=record)
+
+    @torch.no_grad()
+    def sample(self, cond, batch_size=16, return_intermediates=False, x_T=None, verbose=True, timesteps=None,
+               quantize_denoised=False, mask=None, x0=None, shape=None, **kwargs):
+        if shape is None:
+            shape = (batch_size, self.channels, self.image_size, self.image_size)
+        return self.p_sample_loop(cond, shape, return_intermediates=return_intermediates, x_T=x_T, verbose=verbose,
+                                  timesteps=timesteps, quantize_denoised=quantize_denoised, mask=mask, x0=x0, **kwargs)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -572,7 +665,8 @@ class DDIMSampler(object):
         print(f"Running DDIM Sampling with {total_steps} timesteps")
         t_table = torch.tensor(tsteps, dtype=torch.float32, device=device)
         eng = StepEngine(self.model._model_fn(), L.SAMPLER_LDM_DDIM, _PARAM[self.model.parameterization],
-                         coef.to(device), t_table, clip_denoised, **self.model._graph_cache_args())
+                         coef.to(device), t_table, clip_denoised, context=self.model._context(cond),
+                         **self.model._graph_cache_args())
         self.last_engine = self.model.last_engine = eng
         intermediates = {"x_inter": [img], "pred_x0": [img]}
 

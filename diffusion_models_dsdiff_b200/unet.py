@@ -26,6 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from . import transformer as tfm
 from ._lib import B200Error
 
 Tensor = torch.Tensor
@@ -154,10 +155,10 @@ class Act:
 
 class Ctx:
     """Per-forward engine state: packed weights, the batched timestep projections, the statistics arena."""
-    __slots__ = ("pw", "emb_all", "arena")
+    __slots__ = ("pw", "emb_all", "arena", "context")
 
-    def __init__(self, pw: PackedWeights, emb_all: Tensor, arena: "ops.StatsArena"):
-        self.pw, self.emb_all, self.arena = pw, emb_all, arena
+    def __init__(self, pw: PackedWeights, emb_all: Tensor, arena: "ops.StatsArena", context: Optional[Tensor] = None):
+        self.pw, self.emb_all, self.arena, self.context = pw, emb_all, arena, context
 
     def stats_for(self, n: int, c: int) -> Tensor:
         return self.arena.take(n, c)
@@ -223,6 +224,24 @@ def run_attention(cx: Ctx, m: AttentionBlock, x: Act) -> Act:
                     residual=x.t)
 
 
+def run_spatial_transformer(cx: Ctx, m: "tfm.SpatialTransformer", x: Act) -> Act:
+    """SpatialTransformer.forward (ldm/modules/attention.py:409-428)."""
+    pw = cx.pw
+    n, h, w, c = x.t.shape
+    a = run_gn(cx, m.norm, x, silu=False)
+    dt = a.dtype
+    win = pw.conv.get(id(m.proj_in))        # 1x1 convs are packed with the rest of the network; Linear lazily
+    if win is None:
+        win = tfm._packed(pw, ("st_in", id(m)), lambda: ops.pack_conv_weight(_f(m.proj_in.weight), dt))
+    wout = pw.conv.get(id(m.proj_out))
+    if wout is None:
+        wout = tfm._packed(pw, ("st_out", id(m)), lambda: ops.pack_conv_weight(_f(m.proj_out.weight), dt))
+    t = ops.conv2d([(a, win, 0, 1, 0)], bias=_f(m.proj_in.bias)).view(n, h * w, -1)
+    for blk in m.transformer_blocks:
+        t = tfm.run_basic_block(pw, blk, t, cx.context)
+    return run_conv(cx, [(t.view(n, h, w, -1), wout, 0, 1, 0)], bias=_f(m.proj_out.bias), residual=x.t)
+
+
 def run_sequential(cx: Ctx, seq: nn.Sequential, x0: Act, x1: Optional[Act]) -> Act:
     """TimestepEmbedSequential.forward (openaimodel.py:80-90)."""
     pw = cx.pw
@@ -234,6 +253,8 @@ def run_sequential(cx: Ctx, seq: nn.Sequential, x0: Act, x1: Optional[Act]) -> A
             x0, x1 = Act(torch.cat([x0.t, x1.t], dim=-1)), None
         if isinstance(layer, AttentionBlock):
             x0 = run_attention(cx, layer, x0)
+        elif isinstance(layer, tfm.SpatialTransformer):
+            x0 = run_spatial_transformer(cx, layer, x0)
         elif isinstance(layer, Downsample):
             if not layer.use_conv:
                 raise NotImplementedError("Downsample(use_conv=False) is not supported by the B200 engine yet")
@@ -386,8 +407,14 @@ def build_unet_trunk(self, image_size, in_channels, model_channels, out_channels
     structure of openaimodel.UNetModel.__init__ (:601-908), shared by UNetModel and DSUnetModel."""
     if dims != 2:
         raise NotImplementedError("B200 engine: dims must be 2")
-    if use_spatial_transformer or context_dim is not None:
-        raise NotImplementedError("B200 engine: SpatialTransformer / cross-attention is not built yet")
+    if use_spatial_transformer:
+        assert context_dim is not None, \
+            "Fool!! You forgot to include the dimension of your cross-attention conditioning..."
+    if context_dim is not None:
+        assert use_spatial_transformer, \
+            "Fool!! You forgot to use the spatial transformer for your cross-attention conditioning..."
+        if not isinstance(context_dim, (int, list, tuple)):
+            context_dim = list(context_dim)
     if num_classes is not None or n_embed is not None:
         raise NotImplementedError("B200 engine: class conditioning / codebook head are not built yet")
     if num_heads_upsample == -1:
@@ -413,8 +440,18 @@ def build_unet_trunk(self, image_size, in_channels, model_channels, out_channels
     ted = model_channels * 4
     self.time_embed = nn.Sequential(nn.Linear(model_channels, ted), nn.SiLU(), nn.Linear(ted, ted))
 
-    def attn(ch, heads):
-        return AttentionBlock(ch, num_heads=heads, num_head_channels=num_head_channels,
+    def attn(ch, heads, disabled_sa=False):
+        # head-count resolution of openaimodel.py:739-747 / 795-802
+        if num_head_channels == -1:
+            nh, dim_head = heads, ch // heads
+        else:
+            nh, dim_head = ch // num_head_channels, num_head_channels
+        if legacy:
+            dim_head = ch // nh if use_spatial_transformer else num_head_channels
+        if use_spatial_transformer:
+            return tfm.SpatialTransformer(ch, nh, dim_head, depth=transformer_depth, context_dim=context_dim,
+                                          disable_self_attn=disabled_sa, use_linear=use_linear_in_transformer)
+        return AttentionBlock(ch, num_heads=nh, num_head_channels=dim_head,
                               use_new_attention_order=use_new_attention_order)
 
     def res(cin, cout=None, **kw):
@@ -428,7 +465,7 @@ def build_unet_trunk(self, image_size, in_channels, model_channels, out_channels
             layers: List[nn.Module] = [res(ch, mult * model_channels)]
             ch = mult * model_channels
             if ds in attention_resolutions and (num_attention_blocks is None or nr < num_attention_blocks[level]):
-                layers.append(attn(ch, num_heads))
+                layers.append(attn(ch, num_heads, disable_self_attentions[level] if disable_self_attentions else False))
             self.input_blocks.append(TimestepEmbedSequential(*layers))
             chans.append(ch)
         if level != len(channel_mult) - 1:
@@ -436,7 +473,7 @@ def build_unet_trunk(self, image_size, in_channels, model_channels, out_channels
                 res(ch, ch, down=True) if resblock_updown else Downsample(ch, conv_resample, out_channels=ch)))
             chans.append(ch)
             ds *= 2
-    self.middle_block = TimestepEmbedSequential(res(ch), attn(ch, num_heads), res(ch))
+    self.middle_block = TimestepEmbedSequential(res(ch), attn(ch, num_heads, disable_middle_self_attn), res(ch))
     self.output_blocks = nn.ModuleList([])
     for level, mult in list(enumerate(channel_mult))[::-1]:
         for i in range(self.num_res_blocks[level] + 1):
@@ -444,7 +481,8 @@ def build_unet_trunk(self, image_size, in_channels, model_channels, out_channels
             layers = [res(ch + ich, model_channels * mult)]
             ch = model_channels * mult
             if ds in attention_resolutions and (num_attention_blocks is None or i < num_attention_blocks[level]):
-                layers.append(attn(ch, num_heads_upsample))
+                layers.append(attn(ch, num_heads_upsample,
+                                   disable_self_attentions[level] if disable_self_attentions else False))
             if level and i == self.num_res_blocks[level]:
                 layers.append(res(ch, ch, up=True) if resblock_updown else Upsample(ch, conv_resample, out_channels=ch))
                 ds //= 2
@@ -468,13 +506,11 @@ class UNetModel(_EngineModule):
         captured CUDA graph can be replayed for every sampling step."""
         assert (y is not None) == (self.num_classes is not None), \
             "must specify y if and only if the model is class-conditional"
-        if context is not None:
-            raise NotImplementedError("B200 engine: cross-attention context is not built yet")
         pw = self.packed()
         n = x.shape[0]
         emb_all = self._emb_all(pw, timesteps, n, step_ptr)
         self._arena.begin(x.device)
-        cx = Ctx(pw, emb_all, self._arena)
+        cx = Ctx(pw, emb_all, self._arena, tfm.context_tokens(context, self.act_dtype))
         hs = []
         h = run_in_conv(cx, self.input_blocks[0][0], x.float(), self.act_dtype)
         hs.append(h)

@@ -95,6 +95,10 @@ typedef struct {
                               `out` — the network's last conv (self.out[2], openaimodel.py:898-902) whose 1-2 output
                               channels are zero-padded to a 16-wide N tile; NULL otherwise                 */
   int cout_real;
+  const float *rowscale;   /* optional per-(n,co) fp32 factor applied to (acc + bias + rowbias) BEFORE the residual add:
+                              the adaLN-Zero gate of DiTBlock, x + gate * f(x) (UNet_DS_Diff/DiT_models.py:118-122) */
+  int rowscale_stride;
+  int epi_act;             /* activation on (acc + bias + rowbias): 0 none, 1 GELU(tanh) (timm Mlp in DiT, :111-112) */
   float *out_nhwc_f32;     /* optional: write the result as NHWC fp32 [N,Hout,Wout,Cout] INSTEAD of `out` (attention
                               logits q k^T of the KL-autoencoder AttnBlock, ldm/modules/diffusionmodules/model.py:186-189,
                               which must stay fp32 until the softmax); NULL otherwise                       */
@@ -168,6 +172,16 @@ int b200_conv1x1_f32_nchw(const float *x, const float *w, const float *bias, flo
 /* DiagonalGaussianDistribution (ldm/modules/distributions/distributions.py:24-62) on moments [N,2C,HW]:
  * mean = first C channels, logvar = clamp(second C, -30, 20); out = mean + exp(0.5*logvar) * noise (noise NULL -> mode). */
 int b200_gaussian_sample(const float *moments, const float *noise, float *out, int N, int C, int HW, void *stream);
+
+/* ---- token-tensor ops of the transformer blocks ([rows, C] act) -------------------------------------------------
+ * LayerNorm over C (gamma/beta NULL = no affine) with optional adaLN modulation y*(1+scale[b])+shift[b], b = row /
+ * rows_per_batch, shift/scale fp32 with row pitch mod_stride.  Replaces nn.LayerNorm in BasicTransformerBlock
+ * (ldm/modules/attention.py:319-331) and LayerNorm+modulate in DiTBlock / FinalLayer (DiT_models.py:19,107-142). */
+int b200_layernorm(const void *x, const float *gamma, const float *beta, const float *shift, const float *scale,
+                   int mod_stride, int rows_per_batch, int64_t rows, int C, float eps, void *out, int act_dtype,
+                   void *stream);
+/* out[r, c] = x[r, c] * gelu(x[r, inner + c])  (GEGLU.forward, ldm/modules/attention.py:49-56; exact erf GELU)      */
+int b200_geglu(const void *x, void *out, int64_t rows, int inner, int act_dtype, void *stream);
 
 /* ---- small dense layers on [B,K] fp32 vectors (timestep path) --------------------------------
  * replaces timestep_embedding (util.py:161-181), time_embed MLP (openaimodel.py:606-610) and

@@ -184,13 +184,58 @@ def _heads_for(hp: dict, ch: int) -> int:
     return hp["num_heads"]
 
 
-def timestep_embed_sequential(sd: SD, p: str, x: Tensor, emb: Tensor, hp: dict, opq=None) -> Tensor:
+def cross_attention(sd: SD, p: str, x: Tensor, context: Optional[Tensor], heads: int, opq=None) -> Tensor:
+    """CrossAttention.forward (fp32 sim, scale dim_head^-1/2).  ldm/modules/attention.py:163-194."""
+    ctx = x if context is None else context
+    q, k, v = linear(sd, p + ".to_q", x, opq), linear(sd, p + ".to_k", ctx, opq), linear(sd, p + ".to_v", ctx, opq)
+    b, n, inner = q.shape
+    d = inner // heads
+    sp = lambda t: t.reshape(b, t.shape[1], heads, d).permute(0, 2, 1, 3)
+    sim = torch.einsum("bhid,bhjd->bhij", _q(opq, sp(q)), _q(opq, sp(k))) * (d ** -0.5)
+    out = torch.einsum("bhij,bhjd->bhid", _q(opq, sim.softmax(dim=-1)), _q(opq, sp(v)))
+    return linear(sd, p + ".to_out.0", out.permute(0, 2, 1, 3).reshape(b, n, inner), opq)
+
+
+def basic_transformer_block(sd: SD, p: str, x: Tensor, context: Optional[Tensor], heads: int,
+                            disable_self_attn: bool = False, opq=None) -> Tensor:
+    """BasicTransformerBlock._forward with the GEGLU feed-forward.  attention.py:327-331, 49-76."""
+    ln = lambda name, t: F.layer_norm(t, (t.shape[-1],), sd[f"{p}.{name}.weight"], sd[f"{p}.{name}.bias"], 1e-5)
+    x = cross_attention(sd, p + ".attn1", ln("norm1", x), context if disable_self_attn else None, heads, opq) + x
+    x = cross_attention(sd, p + ".attn2", ln("norm2", x), context, heads, opq) + x
+    h, gate = linear(sd, p + ".ff.net.0.proj", ln("norm3", x), opq).chunk(2, dim=-1)
+    return linear(sd, p + ".ff.net.2", h * F.gelu(gate), opq) + x
+
+
+def spatial_transformer(sd: SD, p: str, x: Tensor, context: Optional[Tensor], heads: int, opq=None) -> Tensor:
+    """SpatialTransformer.forward (conv or linear projections, decided from the weight rank).  attention.py:409-428."""
+    b, c, h, w = x.shape
+    x_in = x
+    x = group_norm(x, sd[p + ".norm.weight"], sd[p + ".norm.bias"], eps=1e-6)
+    use_linear = sd[p + ".proj_in.weight"].dim() == 2
+    if not use_linear:
+        x = conv2d(sd, p + ".proj_in", x, padding=0, opq=opq)
+    x = x.reshape(b, x.shape[1], h * w).permute(0, 2, 1)
+    if use_linear:
+        x = linear(sd, p + ".proj_in", x, opq)
+    for i in _sub_indices(sd, p + ".transformer_blocks."):
+        x = basic_transformer_block(sd, f"{p}.transformer_blocks.{i}", x, context, heads, opq=opq)
+    if use_linear:
+        x = linear(sd, p + ".proj_out", x, opq)
+    x = x.permute(0, 2, 1).reshape(b, -1, h, w)
+    if not use_linear:
+        x = conv2d(sd, p + ".proj_out", x, padding=0, opq=opq)
+    return x + x_in
+
+
+def timestep_embed_sequential(sd: SD, p: str, x: Tensor, emb: Tensor, hp: dict, opq=None, context=None) -> Tensor:
     """TimestepEmbedSequential.forward dispatch, decided from the keys present.
     openaimodel.py:80-90."""
     for j in _sub_indices(sd, p + "."):
         q = f"{p}.{j}"
         if q + ".in_layers.0.weight" in sd:
             x = resblock(sd, q, x, emb, hp.get("use_scale_shift_norm", False), opq=opq)
+        elif q + ".transformer_blocks.0.attn1.to_q.weight" in sd:
+            x = spatial_transformer(sd, q, x, context, _heads_for(hp, x.shape[1]), opq=opq)
         elif q + ".qkv.weight" in sd:
             x = attention_block(sd, q, x, _heads_for(hp, x.shape[1]),
                                 hp.get("use_new_attention_order", False), opq=opq)
@@ -217,19 +262,19 @@ def out_head(sd: SD, h: Tensor, opq=None) -> Tensor:
     return conv2d(sd, "out.2", h, opq=opq)
 
 
-def unet_forward(sd: SD, hp: dict, x: Tensor, t: Tensor, opq=None) -> Tensor:
-    """UNetModel.forward (no class label, no cross-attention context).
+def unet_forward(sd: SD, hp: dict, x: Tensor, t: Tensor, opq=None, context: Optional[Tensor] = None) -> Tensor:
+    """UNetModel.forward (no class label; ``context`` feeds the SpatialTransformer cross-attention).
     openaimodel.py:926-958."""
     emb = time_embed(sd, hp, t, opq)
     hs = []
     h = x.float()
     for i in _sub_indices(sd, "input_blocks."):
-        h = timestep_embed_sequential(sd, f"input_blocks.{i}", h, emb, hp, opq)
+        h = timestep_embed_sequential(sd, f"input_blocks.{i}", h, emb, hp, opq, context)
         hs.append(h)
-    h = timestep_embed_sequential(sd, "middle_block", h, emb, hp, opq)
+    h = timestep_embed_sequential(sd, "middle_block", h, emb, hp, opq, context)
     for i in _sub_indices(sd, "output_blocks."):
         h = torch.cat([h, hs.pop()], dim=1)
-        h = timestep_embed_sequential(sd, f"output_blocks.{i}", h, emb, hp, opq)
+        h = timestep_embed_sequential(sd, f"output_blocks.{i}", h, emb, hp, opq, context)
     return out_head(sd, h, opq)
 
 

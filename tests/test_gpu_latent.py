@@ -94,3 +94,101 @@ def test_autoencoder_cpu_raises():
     ae = P.AutoencoderKL(hp["ddconfig"], None, hp["embed_dim"])
     with pytest.raises(P.B200Error):
         ae.decode(torch.zeros(1, 3, 16, 16))
+
+
+# -------------------------------------------------------------------------------------------------
+# a6: token ops + SpatialTransformer / cross-attention UNet
+# -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_layernorm_geglu_and_gemm_epilogues(dt):
+    from diffusion_models_dsdiff_b200 import ops
+    from diffusion_models_dsdiff_b200 import transformer as tfm
+    g = torch.Generator().manual_seed(9)
+    eps16 = 2.0 ** -10 if dt == torch.float16 else 2.0 ** -7
+    x = (torch.randn(3, 40, 320, generator=g) * 2 + 0.5).to(dt).float()
+    w, b = 1 + 0.1 * torch.randn(320, generator=g), 0.1 * torch.randn(320, generator=g)
+    y = ops.layer_norm(x.to(dt).cuda(), w.cuda(), b.cuda(), 1e-5).float().cpu()
+    ref = F.layer_norm(x, (320,), w, b, 1e-5)
+    assert (y - ref).abs().max().item() < eps16 * 2 * max(1.0, ref.abs().max().item())
+    mod = torch.randn(3, 6 * 320, generator=g) * 0.3                      # adaLN: shift | scale | gate | ...
+    modc = mod.cuda()
+    y = ops.layer_norm(x.to(dt).cuda(), None, None, 1e-6, shift=modc[:, :320], scale=modc[:, 320:640]).float().cpu()
+    ref = F.layer_norm(x, (320,), None, None, 1e-6) * (1 + mod[:, None, 320:640]) + mod[:, None, :320]
+    assert (y - ref).abs().max().item() < eps16 * 2 * max(1.0, ref.abs().max().item())
+    z = torch.randn(2, 24, 2 * 128, generator=g).to(dt).float()
+    got = ops.geglu(z.to(dt).cuda()).float().cpu()
+    ref = z[..., :128] * F.gelu(z[..., 128:])
+    assert (got - ref).abs().max().item() < eps16 * 2 * max(1.0, ref.abs().max().item())
+    # GEMM epilogue: GELU(tanh) then gate then residual  (DiT Mlp fc1 / gated residual)
+    t = torch.randn(2, 64, 96, generator=g).to(dt).float()
+    wt = (torch.randn(160, 96, generator=g) / 10).to(dt).float()
+    bias = 0.1 * torch.randn(160, generator=g)
+    gate = torch.randn(2, 160, generator=g)
+    res = torch.randn(2, 64, 160, generator=g).to(dt).float()
+    wp = ops.pack_conv_weight(wt.cuda(), dt)
+    got = tfm.linear_tokens(t.to(dt).cuda(), wp, bias=bias.cuda(), act=1).float().cpu()
+    ref = F.gelu(F.linear(t, wt, bias), approximate="tanh")
+    assert (got - ref).abs().max().item() < eps16 * 2 * max(1.0, ref.abs().max().item())
+    got = tfm.linear_tokens(t.to(dt).cuda(), wp, bias=bias.cuda(), residual=res.to(dt).cuda(), rowscale=gate.cuda()).float().cpu()
+    ref = res + gate[:, None] * F.linear(t, wt, bias)
+    assert (got - ref).abs().max().item() < eps16 * 2 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("case", ["xattn_small", "xattn_d40"])
+def test_cross_attention_unet_matches_reference(case, dtype):
+    P = _pkg()
+    hp, sd = synth_sd(case)
+    net = P.UNetModel(**hp, act_dtype=dtype)
+    assert set(net.state_dict().keys()) == set(sd.keys())
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    g = golden(case)
+    y = net(g["x"].cuda(), g["t"].cuda(), context=g["context"].cuda()).cpu()
+    assert y.shape == g["y"].shape
+    assert O.rel_err(y, g["y"]) < REL_TOL[dtype], f"{case}: {O.rel_err(y, g['y']):.3e}"
+    yq = O.unet_forward(sd, hp, g["x"], g["t"], opq=lambda v: v.to(dtype).float(), context=g["context"])
+    assert O.rel_err(y, yq) < REL_TOL[dtype]
+
+
+def test_latent_diffusion_ancestral_loop_and_decode():
+    """cfg3 in miniature: cross-attention UNet over 3x16x16 latents, eps-parameterised ancestral sampling through
+    LatentDiffusion.sample (CUDA-graph path and eager path), then decode_first_stage — against the same composition of
+    the oracle's pieces (each pinned against the reference separately)."""
+    P = _pkg()
+    from diffusion_models_dsdiff_b200 import samplers as S
+    hp, sd = synth_sd("xattn_d40")
+    net = P.UNetModel(**hp, act_dtype=torch.float16)
+    net.load_state_dict(sd, strict=True)
+    ahp, asd = synth_sd("ae_small")
+    ae = P.AutoencoderKL(ahp["ddconfig"], None, ahp["embed_dim"], act_dtype=torch.float16)
+    ae.load_state_dict(asd, strict=True)
+    T = 6
+    ld = S.LatentDiffusion(ae, "__is_first_stage__", unet_config=net, timesteps=T, beta_schedule="linear",
+                           linear_start=1e-4, linear_end=2e-2, conditioning_key="crossattn", parameterization="eps",
+                           scale_factor=0.5, channels=3, image_size=16).cuda().eval()
+    assert ld.clip_denoised is False
+    g = golden("xattn_d40")
+    ctx = g["context"]
+    gen = torch.Generator().manual_seed(3)
+    x_T = torch.randn(2, 3, 16, 16, generator=gen)
+    noises = [torch.randn(2, 3, 16, 16, generator=gen) for _ in range(T)]
+    out = ld.sample({"c_crossattn": [ctx.cuda()]}, batch_size=2, shape=(2, 3, 16, 16), x_T=x_T.cuda(), noises=noises)
+    sch = O.LdmSchedule(timesteps=T)
+    ref = O.ldm_ddpm_loop(lambda xc, ts: O.unet_forward(sd, hp, xc, ts, context=ctx), sch, x_T, None, noises,
+                          parameterization="eps", clip_denoised=False)
+    assert maxabs(out.cpu(), ref) < 2e-2 * max(1.0, float(ref.abs().max()))
+    # graph path: same torch seed => same noise draws as the eager loop
+    outs = []
+    for use_graph in (False, True):
+        ld.use_graph = use_graph
+        torch.manual_seed(11)
+        outs.append(ld.sample({"c_crossattn": [ctx.cuda()]}, batch_size=2, shape=(2, 3, 16, 16), x_T=x_T.cuda()).cpu())
+    assert maxabs(outs[0], outs[1]) < 1e-5
+    img = ld.decode_first_stage(out)
+    ref_img = O.ae_decode(asd, ref / 0.5)
+    assert img.shape == (2, 1, 32, 32)
+    assert maxabs(img.cpu(), ref_img) < 3e-2 * max(1.0, float(ref_img.abs().max()))
+    with pytest.raises(NotImplementedError):      # LatentDiffusion.p_mean_variance has no v branch (ddpm.py:941-946)
+        ld.parameterization = "v"
+        ld.sample({"c_crossattn": [ctx.cuda()]}, batch_size=2, shape=(2, 3, 16, 16))

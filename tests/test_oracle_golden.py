@@ -145,3 +145,15 @@ def test_autoencoder_oracle_matches_reference():
     assert maxabs(O.ae_posterior_sample(g["moments"], None), g["mode"]) == 0.0
     dec = O.ae_decode(sd, g["z"])
     assert maxabs(dec, g["dec"]) < 2e-5
+
+
+# -------------------------------------------------------------------------------------------------
+# SpatialTransformer / cross-attention UNet
+# -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["xattn_small", "xattn_d40"])
+def test_cross_attention_unet_oracle_matches_reference(case):
+    hp, sd = synth_sd(case)
+    g = golden(case)
+    y = O.unet_forward(sd, hp, g["x"], g["t"], context=g["context"])
+    assert g["y"].abs().max() > 0.05
+    assert maxabs(y, g["y"]) < TOL * max(1.0, float(g["y"].abs().max()))
