@@ -22,13 +22,25 @@ class KernelTimer:
     stream around each kernel of libb200diff; nothing is recorded unless a timer is installed."""
 
     def __init__(self):
-        self.records = []      # (name, algorithmic flops, algorithmic bytes, start event, end event)
+        self.records = []      # (name, algorithmic flops, algorithmic bytes, start event, end event, detail)
 
     def summary(self) -> dict:
         torch.cuda.synchronize()
         out = {}
-        for name, fl, by, a, b in self.records:
+        for name, fl, by, a, b, _ in self.records:
             d = out.setdefault(name, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["ms"] += a.elapsed_time(b)
+            d["flops"] += fl
+            d["bytes"] += by
+        return out
+
+    def by_detail(self) -> dict:
+        """The same totals keyed by (kernel, shape string) — tools/step_breakdown.py."""
+        torch.cuda.synchronize()
+        out = {}
+        for name, fl, by, a, b, det in self.records:
+            d = out.setdefault((name, det or ""), {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
             d["launches"] += 1
             d["ms"] += a.elapsed_time(b)
             d["flops"] += fl
@@ -44,14 +56,14 @@ def set_timer(t: Optional[KernelTimer]) -> None:
     _timer = t
 
 
-def _timed(name: str, flops: float, nbytes: float, launch):
+def _timed(name: str, flops: float, nbytes: float, launch, detail: Optional[str] = None):
     if _timer is None:
         return launch()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     r = launch()
     b.record()
-    _timer.records.append((name, flops, nbytes, a, b))
+    _timer.records.append((name, flops, nbytes, a, b, detail))
     return r
 
 
@@ -191,7 +203,9 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
     nbytes = 2.0 * (sum(sg[0].numel() for sg in segs) + out.numel() + cout * kk
                     + (residual.numel() if residual is not None else 0))
     _timed("conv_igemm", flops, nbytes,
-           lambda: L.check(L.lib().b200_conv2d_igemm(C.byref(d), _stream()), "conv2d_igemm"))
+           lambda: L.check(L.lib().b200_conv2d_igemm(C.byref(d), _stream()), "conv2d_igemm"),
+           None if _timer is None else
+           f"{n}x{hout}x{wout} s{stride} " + "+".join(f"k{sg[3]}c{sg[0].shape[3]}" for sg in segs) + f" ->{cout}")
     return out
 
 
@@ -282,6 +296,7 @@ def group_norm(x0: Tensor, gamma: Tensor, beta: Tensor, x1: Optional[Tensor] = N
     film_s = 0 if film is None or film.shape[0] == 1 else film.stride(0)   # [1, 2C]: shared by the batch
     if cs0 is not None and (x1 is None or cs1 is not None):
         _timed("groupnorm_silu", 0.0, 2.0 * 2.0 * out.numel(),
+               detail=f"{n}x{hw} c{c0}+{c1}", launch=
                lambda: L.check(lib.b200_groupnorm_apply_cs(_p(x0), c0, _p(cs0), _p(x1), c1, _p(cs1), n, hw, groups, eps,
                                                            _p(_f32(gamma)), _p(_f32(beta)), film_p, film_s, int(silu),
                                                            _p(out), code, _stream()), "groupnorm_apply_cs"))
@@ -311,7 +326,7 @@ def attention_qkv(qkv: Tensor, heads: int, new_order: bool) -> Tensor:
     ch = c3 // (3 * heads)
     out = torch.empty((b, l, heads * ch), device=qkv.device, dtype=qkv.dtype)
     _timed("attention", 4.0 * b * heads * l * l * ch, 2.0 * (qkv.numel() + out.numel()),
-           lambda: L.check(L.lib().b200_attention_qkv(_p(qkv), _p(out), b, l, heads, ch, int(new_order),
+           detail=f"B{b} L{l} h{heads} d{ch}", launch=lambda: L.check(L.lib().b200_attention_qkv(_p(qkv), _p(out), b, l, heads, ch, int(new_order),
                                                       float(ch) ** -0.5, act_code(qkv.dtype), _stream()),
                            "attention_qkv"))
     return out
