@@ -72,6 +72,9 @@ SIGNATURES = {
     "b200_attention": [C.POINTER(AttnDesc), _P],
     "b200_layernorm": [_P, _P, _P, _P, _P, _I, _I, _L, _I, _F, _P, _I, _P],
     "b200_geglu": [_P, _P, _L, _I, _I, _P],
+    "b200_patchify": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "b200_unpatchify": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "b200_add_f32": [_P, _P, _P, _L, _P],
     "b200_softmax_rows": [_P, _P, _L, _I, _F, _I, _P],
     "b200_conv1x1_f32_nchw": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "b200_gaussian_sample": [_P, _P, _P, _I, _I, _I, _P],

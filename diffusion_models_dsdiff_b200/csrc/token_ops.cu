@@ -83,6 +83,50 @@ geglu_kernel(const T *__restrict__ x, T *__restrict__ out, long long rows, int i
   }
 }
 
+// DiT patch embedding input (timm PatchEmbed = Conv2d(C, d, kernel p, stride p); UNet_DS_Diff/DiT_models.py:192,243):
+// NCHW fp32 image -> tokens [N, (H/p)*(W/p), Kpad] act with k = (c*p + ph)*p + pw, the column order of
+// proj.weight.view(d, C*p*p), so the convolution becomes one tensor-core GEMM over the token matrix.
+template <typename T>
+__global__ void __launch_bounds__(256)
+patchify_kernel(const float *__restrict__ x, T *__restrict__ out, int C, int H, int W, int p, int Kpad, long long total) {
+  const int gw = W / p, gh = H / p, K = C * p * p;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kpad);
+    long long r = i / Kpad;
+    const int tw = (int)(r % gw); r /= gw;
+    const int th = (int)(r % gh);
+    const long long n = r / gh;
+    float v = 0.f;
+    if (k < K) {
+      const int pw = k % p, ph = (k / p) % p, c = k / (p * p);
+      v = x[((n * C + c) * H + th * p + ph) * W + tw * p + pw];
+    }
+    out[i] = Act<T>::from_f(v);
+  }
+}
+
+// DiT.unpatchify (DiT_models.py:220-232): tokens [N, gh*gw, ld] fp32 with feature index (ph*p + pw)*c_out + c
+// -> NCHW fp32 image [N, c_out, gh*p, gw*p].
+__global__ void __launch_bounds__(256)
+unpatchify_kernel(const float *__restrict__ tok, float *__restrict__ out, int Cout, int gh, int gw, int p, int ld,
+                  long long total) {
+  const int H = gh * p, W = gw * p;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i % W);
+    long long r = i / W;
+    const int h = (int)(r % H); r /= H;
+    const int c = (int)(r % Cout);
+    const long long n = r / Cout;
+    const int th = h / p, ph = h - th * p, tw = w / p, pw = w - tw * p;
+    out[i] = tok[((n * gh + th) * gw + tw) * (long long)ld + (ph * p + pw) * Cout + c];
+  }
+}
+
+__global__ void __launch_bounds__(256) add_f32_kernel(const float *a, const float *b, float *out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = a[i] + b[i];
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -117,6 +161,39 @@ extern "C" int b200_geglu(const void *x, void *out, int64_t rows, int inner, int
     geglu_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)out, rows, inner);
   else
     B200_CHECK(false, "geglu: bad act_dtype");
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_patchify(const float *x, void *out, int N, int C, int H, int W, int p, int Kpad, int act_dtype,
+                             void *stream) {
+  B200_CHECK(x && out && N > 0 && C > 0 && p > 0 && H % p == 0 && W % p == 0, "patchify: H, W must be multiples of p");
+  B200_CHECK(Kpad >= C * p * p && Kpad % 8 == 0, "patchify: Kpad must be a multiple of 8 >= C*p*p");
+  const long long total = (long long)N * (H / p) * (W / p) * Kpad;
+  const int blocks = (int)std::min<long long>(cdiv64(total, 256), (long long)num_sms() * 16);
+  if (act_dtype == B200_F16)
+    patchify_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__half *)out, C, H, W, p, Kpad, total);
+  else if (act_dtype == B200_BF16)
+    patchify_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)out, C, H, W, p, Kpad, total);
+  else
+    B200_CHECK(false, "patchify: bad act_dtype");
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_unpatchify(const float *tok, float *out, int N, int Cout, int gh, int gw, int p, int ld, void *stream) {
+  B200_CHECK(tok && out && N > 0 && Cout > 0 && gh > 0 && gw > 0 && p > 0 && ld >= p * p * Cout, "unpatchify: bad geometry");
+  const long long total = (long long)N * Cout * gh * p * gw * p;
+  const int blocks = (int)std::min<long long>(cdiv64(total, 256), (long long)num_sms() * 16);
+  unpatchify_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(tok, out, Cout, gh, gw, p, ld, total);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_add_f32(const float *a, const float *b, float *out, int64_t n, void *stream) {
+  B200_CHECK(a && b && out && n > 0, "add_f32: bad arguments");
+  const int blocks = (int)std::min<long long>(cdiv64(n, 256), (long long)num_sms() * 16);
+  add_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, b, out, n);
   B200_LAUNCH_CHECK();
   return 0;
 }

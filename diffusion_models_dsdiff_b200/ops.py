@@ -384,6 +384,36 @@ def geglu(x: Tensor) -> Tensor:
     return out
 
 
+def patchify(x: Tensor, p: int, dtype: torch.dtype) -> Tensor:
+    """NCHW fp32 [N, C, H, W] -> patch tokens [N, (H/p)*(W/p), Kpad] (column order of PatchEmbed.proj.weight.view(d, -1))."""
+    _dev(x)
+    n, c, h, w = x.shape
+    kpad = (c * p * p + 7) // 8 * 8
+    out = torch.empty((n, (h // p) * (w // p), kpad), device=x.device, dtype=dtype)
+    _timed("patchify", 0.0, 4.0 * x.numel() + 2.0 * out.numel(),
+           lambda: L.check(L.lib().b200_patchify(_p(_f32(x.contiguous())), _p(out), n, c, h, w, p, kpad, act_code(dtype),
+                                                 _stream()), "patchify"))
+    return out
+
+
+def unpatchify(tok: Tensor, cout: int, gh: int, gw: int, p: int) -> Tensor:
+    """fp32 tokens [N, gh*gw, ld] -> NCHW fp32 [N, cout, gh*p, gw*p] (DiT.unpatchify)."""
+    _dev(tok)
+    n, _, ld = tok.shape
+    out = torch.empty((n, cout, gh * p, gw * p), device=tok.device, dtype=torch.float32)
+    L.check(L.lib().b200_unpatchify(_p(_f32(tok)), _p(out), n, cout, gh, gw, p, ld, _stream()), "unpatchify")
+    return out
+
+
+def add_f32(a: Tensor, b: Tensor) -> Tensor:
+    _dev(a)
+    if a.shape != b.shape:
+        raise L.B200Error("add_f32: shape mismatch")
+    out = torch.empty_like(a)
+    L.check(L.lib().b200_add_f32(_p(_f32(a)), _p(_f32(b)), _p(out), a.numel(), _stream()), "add_f32")
+    return out
+
+
 def softmax_rows(s: Tensor, scale: float, dtype: torch.dtype) -> Tensor:
     """softmax(scale * s, dim=-1): fp32 logits [..., cols] -> 16-bit probabilities."""
     _dev(s)

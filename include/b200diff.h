@@ -182,6 +182,14 @@ int b200_layernorm(const void *x, const float *gamma, const float *beta, const f
                    void *stream);
 /* out[r, c] = x[r, c] * gelu(x[r, inner + c])  (GEGLU.forward, ldm/modules/attention.py:49-56; exact erf GELU)      */
 int b200_geglu(const void *x, void *out, int64_t rows, int inner, int act_dtype, void *stream);
+/* DiT patch embedding input (timm PatchEmbed conv, kernel = stride = p; UNet_DS_Diff/DiT_models.py:192,243): NCHW fp32
+ * -> tokens [N, (H/p)*(W/p), Kpad] act, column k = (c*p + ph)*p + pw = the column order of proj.weight.view(d, C*p*p);
+ * columns >= C*p*p are zero.  The convolution itself is then b200_conv2d_igemm over the token matrix.              */
+int b200_patchify(const float *x, void *out, int N, int C, int H, int W, int p, int Kpad, int act_dtype, void *stream);
+/* DiT.unpatchify (DiT_models.py:220-232): tokens [N, gh*gw, ld] fp32, feature (ph*p + pw)*Cout + c -> NCHW fp32.    */
+int b200_unpatchify(const float *tok, float *out, int N, int Cout, int gh, int gw, int p, int ld, void *stream);
+/* out = a + b over n fp32 values (c = t_emb + y_emb, DiT_models.py:246-248).                                        */
+int b200_add_f32(const float *a, const float *b, float *out, int64_t n, void *stream);
 
 /* ---- small dense layers on [B,K] fp32 vectors (timestep path) --------------------------------
  * replaces timestep_embedding (util.py:161-181), time_embed MLP (openaimodel.py:606-610) and

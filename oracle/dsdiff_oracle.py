@@ -433,6 +433,77 @@ def ae_decode(sd: SD, z: Tensor, opq=None) -> Tensor:
 
 
 # ----------------------------------------------------------------------------
+# DiT (UNet_DS_Diff/DiT_models.py).  PatchEmbed / Attention / Mlp come from timm
+# (timm.models.vision_transformer, version NOT pinned by the reference, not under
+# /root/reference): restated here from their published definitions —
+#   PatchEmbed(img, p, C, d, bias) = Conv2d(C, d, kernel p, stride p) -> flatten(2).transpose(1, 2), no norm
+#   Attention(d, heads, qkv_bias=True) = qkv Linear(d, 3d) -> [B, N, 3, heads, d/heads] -> softmax(q k^T (d/heads)^-1/2) v
+#                                        -> proj Linear(d, d)       (no qk-norm, no dropout at inference)
+#   Mlp(d, hidden, act) = fc1 -> act -> fc2
+# The DiT glue itself (modulate, DiTBlock, FinalLayer, TimestepEmbedder, pos-embed, unpatchify) is pinned against the
+# reference file run on top of that restatement (oracle/make_golden_ext.py gen_dit); timm itself stays "parity unpinned".
+# ----------------------------------------------------------------------------
+def sincos_1d(embed_dim: int, pos: np.ndarray) -> np.ndarray:
+    """get_1d_sincos_pos_embed_from_grid.  DiT_models.py:307-326 (float64, sin | cos)."""
+    omega = np.arange(embed_dim // 2, dtype=np.float64)
+    omega /= embed_dim / 2.0
+    omega = 1.0 / 10000 ** omega
+    out = np.einsum("m,d->md", pos.reshape(-1), omega)
+    return np.concatenate([np.sin(out), np.cos(out)], axis=1)
+
+
+def dit_pos_embed(embed_dim: int, grid_size: int) -> Tensor:
+    """get_2d_sincos_pos_embed (DiT_models.py:276-304): meshgrid with w first; first half of the channels encodes
+    grid[0] (= the w coordinate), second half grid[1].  Returns fp32 [1, grid^2, D] as stored in DiT.pos_embed (:196)."""
+    gh = np.arange(grid_size, dtype=np.float32)
+    gw = np.arange(grid_size, dtype=np.float32)
+    grid = np.stack(np.meshgrid(gw, gh), axis=0).reshape([2, 1, grid_size, grid_size])
+    emb = np.concatenate([sincos_1d(embed_dim // 2, grid[0]), sincos_1d(embed_dim // 2, grid[1])], axis=1)
+    return torch.from_numpy(emb).float().unsqueeze(0)
+
+
+def dit_forward(sd: SD, hp: dict, x: Tensor, t: Tensor, y: Optional[Tensor] = None, cond: Optional[Tensor] = None,
+                opq=None) -> Tensor:
+    """DiT.forward.  DiT_models.py:234-254 (+ DiTBlock :118-122, FinalLayer :138-142, TimestepEmbedder :41-64,
+    unpatchify :220-232).  hp: patch_size, hidden_size, depth, num_heads, in_channels, learn_sigma."""
+    p, d, heads = hp["patch_size"], hp["hidden_size"], hp["num_heads"]
+    if cond is not None:
+        x = torch.cat([x, cond], dim=1)                                                    # :241-242
+    h = conv2d(sd, "x_embedder.proj", x.float(), stride=p, padding=0, opq=opq)             # timm PatchEmbed
+    b, _, gh, gw = h.shape
+    h = h.flatten(2).transpose(1, 2) + sd["pos_embed"]                                     # :243
+    fdim = sd["t_embedder.mlp.0.weight"].shape[1]
+    c = linear(sd, "t_embedder.mlp.2", silu(linear(sd, "t_embedder.mlp.0", timestep_embedding(t, fdim), opq)), opq)
+    if y is not None:
+        c = c + sd["y_embedder.embedding_table.weight"][y]                                 # eval: no label dropout
+    sc = silu(c)
+
+    def modulate(v, shift, scale):                                                          # :19-20
+        return v * (1 + scale.unsqueeze(1)) + shift.unsqueeze(1)
+
+    def ln(v):
+        return F.layer_norm(v, (d,), eps=1e-6)
+
+    dh = d // heads
+    for i in range(hp["depth"]):
+        q = f"blocks.{i}"
+        m = linear(sd, q + ".adaLN_modulation.1", sc, opq).chunk(6, dim=1)
+        a = linear(sd, q + ".attn.qkv", modulate(ln(h), m[0], m[1]), opq)
+        qkv = a.reshape(b, -1, 3, heads, dh).permute(2, 0, 3, 1, 4)
+        att = torch.einsum("bhid,bhjd->bhij", _q(opq, qkv[0]), _q(opq, qkv[1])) * (dh ** -0.5)
+        att = torch.einsum("bhij,bhjd->bhid", _q(opq, att.softmax(dim=-1)), _q(opq, qkv[2]))
+        att = att.transpose(1, 2).reshape(b, -1, d)
+        h = h + m[2].unsqueeze(1) * linear(sd, q + ".attn.proj", att, opq)
+        u = F.gelu(linear(sd, q + ".mlp.fc1", modulate(ln(h), m[3], m[4]), opq), approximate="tanh")
+        h = h + m[5].unsqueeze(1) * linear(sd, q + ".mlp.fc2", u, opq)
+    shift, scale = linear(sd, "final_layer.adaLN_modulation.1", sc, opq).chunk(2, dim=1)
+    h = linear(sd, "final_layer.linear", modulate(ln(h), shift, scale), opq)
+    co = h.shape[-1] // (p * p)
+    h = h.reshape(b, gh, gw, p, p, co)
+    return torch.einsum("nhwpqc->nchpwq", h).reshape(b, co, gh * p, gw * p)
+
+
+# ----------------------------------------------------------------------------
 # schedules
 # ----------------------------------------------------------------------------
 def ldm_beta_schedule(schedule: str, n: int, linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3):

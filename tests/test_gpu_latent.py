@@ -192,3 +192,52 @@ def test_latent_diffusion_ancestral_loop_and_decode():
     with pytest.raises(NotImplementedError):      # LatentDiffusion.p_mean_variance has no v branch (ddpm.py:941-946)
         ld.parameterization = "v"
         ld.sample({"c_crossattn": [ctx.cuda()]}, batch_size=2, shape=(2, 3, 16, 16))
+
+
+# -------------------------------------------------------------------------------------------------
+# DiT
+# -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("case", ["dit_small", "dit_p2"])
+def test_dit_forward_matches_reference_golden(case, dtype):
+    import diffusion_models_dsdiff_b200 as P
+    hp, sd = synth_sd(case)
+    g = golden(case)
+    net = P.DiT(**hp, act_dtype=dtype)
+    assert maxabs(net.pos_embed, g["pos_embed"]) < 1e-6        # own sin-cos table == the reference's
+    missing = net.load_state_dict(sd, strict=False)
+    assert missing.missing_keys == ["pos_embed"] and not missing.unexpected_keys
+    net = net.cuda().eval()
+    labels = g["labels"].cuda() if "labels" in g else None
+    cond = g["cond"].cuda() if "cond" in g else None
+    y = net(g["x"].cuda(), g["t"].cuda(), y=labels, cond=cond).cpu()
+    assert y.shape == g["y_out"].shape and y.dtype == torch.float32
+    # tolerance: same operand-rounding floor as the UNet tests (tests/test_gpu_model.py REL_TOL)
+    tol = {torch.float16: 2e-3, torch.bfloat16: 1.6e-2}[dtype]
+    rel = O.rel_err(y, g["y_out"])
+    assert rel < tol, f"{case} {dtype}: rel err {rel:.3e}"
+    sd["pos_embed"] = g["pos_embed"]
+    yq = O.dit_forward(sd, hp, g["x"], g["t"], y=g.get("labels"), cond=g.get("cond"), opq=lambda v: v.to(dtype).float())
+    assert O.rel_err(y, yq) < tol
+
+
+def test_dit_head_padding_and_step_table():
+    """Head width 72 (DiT-XL's) runs zero-padded to 80 inside the packed weights; the step-table entry (engine extension)
+    equals the plain call."""
+    import diffusion_models_dsdiff_b200 as P
+    hp = dict(input_size=16, patch_size=2, in_channels=4, hidden_size=144, depth=2, num_heads=2, learn_sigma=True)
+    torch.manual_seed(3)
+    net = P.DiT(**hp)
+    sd = O.synth_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items() if k != "pos_embed"})
+    net.load_state_dict(sd, strict=False)
+    sd["pos_embed"] = net.pos_embed.detach().clone()
+    net = net.cuda().eval()
+    x = torch.randn(2, 4, 16, 16)
+    t = torch.tensor([11.0, 11.0])
+    y = net(x.cuda(), t.cuda()).cpu()
+    ref = O.dit_forward(sd, hp, x, t)
+    assert O.rel_err(y, ref) < 2e-3
+    table = torch.tensor([500.0, 11.0, 3.0]).cuda()
+    step = torch.tensor([1], dtype=torch.int32).cuda()
+    y2 = net(x.cuda(), table, step_ptr=step).cpu()
+    assert torch.equal(y, y2)

@@ -157,3 +157,21 @@ def test_cross_attention_unet_oracle_matches_reference(case):
     y = O.unet_forward(sd, hp, g["x"], g["t"], context=g["context"])
     assert g["y"].abs().max() > 0.05
     assert maxabs(y, g["y"]) < TOL * max(1.0, float(g["y"].abs().max()))
+
+
+# -------------------------------------------------------------------------------------------------
+# DiT: the reference's DiT_models.py glue run on a restatement of timm's PatchEmbed / Attention /
+# Mlp (timm itself is absent and unpinned -> that part stays "parity unpinned", see oracle/dsdiff_oracle.py)
+# -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["dit_small", "dit_p2"])
+def test_dit_oracle_matches_reference(case):
+    hp, sd = synth_sd(case)
+    g = golden(case)
+    grid = hp["input_size"] // hp["patch_size"]
+    pos = O.dit_pos_embed(hp["hidden_size"], grid)
+    assert maxabs(pos, g["pos_embed"]) < 1e-6          # fixed sin-cos table, DiT_models.py:196-197, 276-326
+    sd["pos_embed"] = g["pos_embed"]
+    y = O.dit_forward(sd, hp, g["x"], g["t"], y=g.get("labels"), cond=g.get("cond"))
+    assert y.shape == g["y_out"].shape
+    assert g["y_out"].abs().max() > 0.05
+    assert maxabs(y, g["y_out"]) < TOL * max(1.0, float(g["y_out"].abs().max()))
