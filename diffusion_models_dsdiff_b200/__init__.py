@@ -13,6 +13,8 @@ from .autoencoder import AutoencoderKL, DiagonalGaussianDistribution  # noqa: F4
 from .samplers import (DDPM, DDIMSampler, DiffusionWrapper, GaussianDiffusion, LatentDiffusion, SpacedDiffusion,  # noqa: F401
                        create_gaussian_diffusion, instantiate_from_config, space_timesteps)
 
-__all__ = ["B200Error", "LIB_PATH", "launch_count", "UNetModel", "DSUnetModel", "DiT", "DiT_models", "AutoencoderKL", "DiagonalGaussianDistribution", "DDPM", "LatentDiffusion", "DDIMSampler",
+from .dpm_solver import DPMSolverSampler, NoiseScheduleVP  # noqa: F401,E402
+
+__all__ = ["DPMSolverSampler", "NoiseScheduleVP", "B200Error", "LIB_PATH", "launch_count", "UNetModel", "DSUnetModel", "DiT", "DiT_models", "AutoencoderKL", "DiagonalGaussianDistribution", "DDPM", "LatentDiffusion", "DDIMSampler",
            "DiffusionWrapper", "GaussianDiffusion", "SpacedDiffusion", "create_gaussian_diffusion",
            "instantiate_from_config", "space_timesteps"]

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200diff.so")
 
 F16, BF16 = 0, 1
-SAMPLER_LDM_DDIM, SAMPLER_LDM_DDPM, SAMPLER_GD_DDIM, SAMPLER_GD_DDPM = 0, 1, 2, 3
+SAMPLER_LDM_DDIM, SAMPLER_LDM_DDPM, SAMPLER_GD_DDIM, SAMPLER_GD_DDPM, SAMPLER_DPMPP_2M = 0, 1, 2, 3, 4
 SAMPLER_NCOEF = 16
 PARAM_EPS, PARAM_X0, PARAM_V = 0, 1, 2
 
@@ -39,7 +39,8 @@ class SamplerDesc(C.Structure):
     _fields_ = [("mode", C.c_int), ("param", C.c_int), ("clip_denoised", C.c_int), ("learned_range", C.c_int),
                 ("N", C.c_int), ("C", C.c_int), ("HW", C.c_int), ("x", C.c_void_p), ("model_out", C.c_void_p),
                 ("noise", C.c_void_p), ("coef", C.c_void_p), ("step_ptr", C.c_void_p), ("step_host", C.c_int),
-                ("x_prev", C.c_void_p), ("pred_x0", C.c_void_p)]
+                ("x_prev", C.c_void_p), ("pred_x0", C.c_void_p), ("hist", C.c_void_p), ("thresh", C.c_void_p),
+                ("phase", C.c_int)]
 
 
 class AttnDesc(C.Structure):
@@ -86,6 +87,7 @@ SIGNATURES = {
     "b200_add4_scale_stats": [_P, _P, _P, _P, _F, _P, _I, _I, _I, _P, _I, _P],
     "b200_se_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "b200_sampler_update": [C.POINTER(SamplerDesc), _P],
+    "b200_abs_quantile": [_P, _I, _L, _F, _F, _P, _P],
     "b200_advance_step": [_P, _I, _P],
 }
 _RESTYPE = {"b200_last_error": C.c_char_p, "b200_launch_count": C.c_uint64}

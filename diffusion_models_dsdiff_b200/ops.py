@@ -550,6 +550,38 @@ def sampler_update(mode: int, param: int, x: Tensor, model_out: Tensor, noise: O
     return x_prev, pred_x0
 
 
+def dpm_solver_update(param: int, x: Tensor, model_out: Optional[Tensor], coef: Tensor, hist: Optional[Tensor],
+                      step: int = 0, step_ptr: Optional[Tensor] = None, phase: int = 0, pred_x0: Optional[Tensor] = None,
+                      thresh: Optional[Tensor] = None, x_next: Optional[Tensor] = None) -> Optional[Tensor]:
+    """One DPM-Solver++ (2M) step (b200_sampler_update, mode DPMPP_2M): phase 0 fused; phase 1 writes the raw x0 into
+    ``pred_x0``; phase 2 thresholds ``pred_x0`` with the per-sample ``thresh`` and updates.  ``hist`` is the previous x0."""
+    _dev(x)
+    n, c = x.shape[0], x.shape[1]
+    d = L.SamplerDesc()
+    d.mode, d.param, d.clip_denoised, d.learned_range = L.SAMPLER_DPMPP_2M, param, 0, 0
+    d.N, d.C, d.HW = n, c, x.numel() // (n * c)
+    if phase != 1 and x_next is None:
+        x_next = torch.empty_like(x)
+    d.x, d.model_out, d.noise, d.coef = _p(_f32(x)), _p(_f32(model_out)), None, _p(_f32(coef))
+    d.step_ptr, d.step_host = _p(step_ptr), step
+    d.x_prev, d.pred_x0, d.hist, d.thresh, d.phase = _p(x_next), _p(pred_x0), _p(hist), _p(_f32(thresh)), phase
+    nb = 4.0 * x.numel() * (4 if phase == 0 else 3 if phase == 1 else 5)
+    _timed("sampler_update", 0.0, nb, lambda: L.check(L.lib().b200_sampler_update(C.byref(d), _stream()),
+                                                       "sampler_update(dpm-solver++)"))
+    return x_next
+
+
+def abs_quantile(x: Tensor, q: float, floor_val: float, out: Optional[Tensor] = None) -> Tensor:
+    """out[n] = max(quantile(|x[n]|, q), floor_val) per sample (dynamic thresholding scale)."""
+    _dev(x)
+    n = x.shape[0]
+    if out is None:
+        out = torch.empty((n,), device=x.device, dtype=torch.float32)
+    L.check(L.lib().b200_abs_quantile(_p(_f32(x)), n, x.numel() // n, float(q), float(floor_val), _p(out), _stream()),
+            "abs_quantile")
+    return out
+
+
 def advance_step(step_ptr: Tensor, delta: int = 1) -> None:
     _dev(step_ptr)
     L.check(L.lib().b200_advance_step(_p(step_ptr), delta, _stream()), "advance_step")

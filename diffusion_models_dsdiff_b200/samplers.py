@@ -30,7 +30,7 @@ from __future__ import annotations
 
 import importlib
 import math
-from typing import Callable, Dict, List, Optional, Sequence
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -155,8 +155,11 @@ class StepEngine:
 
     def __init__(self, model_fn: Callable, mode: int, param: int, coef: Tensor, t_table: Tensor,
                  clip_denoised: bool, learned_range: bool = False, cache: Optional[dict] = None, cache_key=None,
-                 keepalive=None, prepare: Optional[Callable] = None, context: Optional[Tensor] = None):
+                 keepalive=None, prepare: Optional[Callable] = None, context: Optional[Tensor] = None,
+                 thresholding: Optional[Tuple[float, float]] = None):
         self.model_fn, self.mode, self.param = model_fn, mode, param
+        self.thresholding = thresholding    # DPM-Solver++ dynamic thresholding (ratio, max_val) or None
+        self._dpm: Optional[dict] = None    # DPM-Solver++ static buffers: previous x0, raw x0, per-sample thresholds
         self.coef, self.t_table = coef, t_table
         self.clip, self.learned_range = clip_denoised, learned_range
         # captured graphs are reused across calls (the reference builds a new DDIMSampler per batch);
@@ -175,6 +178,22 @@ class StepEngine:
             out = self.model_fn(xc, self.t_table, step_ptr)
         if isinstance(out, tuple):
             out = out[0]
+        if self.mode == L.SAMPLER_DPMPP_2M:      # deterministic ODE solver: no noise is drawn (dpm_solver_pytorch.py)
+            b = self._dpm
+            if out.shape[1] == 2 * x.shape[1]:   # learn-sigma networks: mean half only (gaussian_diffusion.py:484-487)
+                out = out[:, :x.shape[1]]
+            out = out.contiguous()
+            if self.thresholding is None:
+                ops.dpm_solver_update(self.param, x, out, self.coef, b["hist"], step_ptr=step_ptr, pred_x0=pred_x0, x_next=x)
+            else:
+                ops.dpm_solver_update(self.param, x, out, self.coef, None, step_ptr=step_ptr, phase=1, pred_x0=b["x0"])
+                ops.abs_quantile(b["x0"], self.thresholding[0], self.thresholding[1], out=b["thr"])
+                ops.dpm_solver_update(self.param, x, None, self.coef, b["hist"], step_ptr=step_ptr, phase=2,
+                                      pred_x0=b["x0"], thresh=b["thr"], x_next=x)
+                if pred_x0 is not None:
+                    pred_x0.copy_(b["x0"])
+            ops.advance_step(step_ptr, 1)
+            return out
         z = noise if noise is not None else torch.randn_like(x)
         ops.sampler_update(self.mode, self.param, x, out.contiguous(), z, self.coef, step_ptr=step_ptr,
                            clip_denoised=self.clip, learned_range=self.learned_range, x_prev=x,
@@ -190,7 +209,10 @@ class StepEngine:
         step_ptr = torch.zeros(1, dtype=torch.int32, device=dev)
         if self.prepare is not None:       # timestep MLP + emb projections for ALL steps, once per loop
             self.prepare(self.t_table)
-        if noises is not None or not use_graph or steps < 3:
+        if self.mode == L.SAMPLER_DPMPP_2M:
+            self._dpm = {"hist": torch.zeros_like(x), "x0": torch.empty_like(x),
+                         "thr": torch.ones(x.shape[0], dtype=torch.float32, device=dev)}
+        if noises is not None or record is not None or not use_graph or steps < 3:
             for i in range(steps):
                 out = self._one(x, cond, step_ptr, None if noises is None else noises[i].to(dev).float().contiguous(),
                                 pred_x0)
@@ -203,7 +225,7 @@ class StepEngine:
         # ---- graph path ----
         key = None
         if self.cache is not None:
-            key = (self.cache_key, self.mode, self.param, self.clip, self.learned_range, tuple(x.shape),
+            key = (self.cache_key, self.mode, self.param, self.clip, self.learned_range, self.thresholding, tuple(x.shape),
                    tuple(tuple(c.shape) for c in (cond or [])), steps, want_x0,
                    None if self.context is None else tuple(self.context.shape))
         entry = self.cache.get(key) if key is not None else None
@@ -218,6 +240,7 @@ class StepEngine:
             if self.context is not None:
                 entry["context"].copy_(self.context)
             entry["step_ptr"].zero_()
+            self._dpm = entry.get("dpm")
             self.stats = {"graph_launches_per_step": entry["launches"], "graph_reused": True}
         xs, x0s = entry["x"], entry["pred_x0"]
         for i in range(steps):
@@ -253,7 +276,8 @@ class StepEngine:
         launches = L.launch_count() - n0
         # capture does not execute: x / step_ptr / RNG are untouched
         entry = {"graph": graph, "x": x, "cond": cond, "pred_x0": pred_x0, "step_ptr": step_ptr, "coef": coef,
-                 "t_table": t_table, "launches": launches, "keepalive": self.keepalive, "context": self.context}
+                 "t_table": t_table, "launches": launches, "keepalive": self.keepalive, "context": self.context,
+                 "dpm": self._dpm}
         self.stats = {"graph_launches_per_step": launches, "graph_reused": False}
         if key is not None:
             if len(self.cache) >= 4:            # bounded: each entry pins a private activation pool
@@ -837,6 +861,15 @@ class GaussianDiffusion:
                          model_kwargs=None, device=None, progress=False, eta=0.0, **kw):
         return self._loop(L.SAMPLER_GD_DDIM, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs,
                           device, progress, eta, **kw)
+
+
+def _dpm_solver_sample_loop(self, model, shape, clip_denoised=None, model_kwargs=None, noise=None, record=None):
+    """training_project/utils/gaussian_diffusion.py:468-523 (DPM-Solver++ 2M, logSNR steps, dynamic thresholding)."""
+    from .dpm_solver import gaussian_dpm_solver_sample_loop
+    return gaussian_dpm_solver_sample_loop(self, model, shape, clip_denoised, model_kwargs, noise=noise, record=record)
+
+
+GaussianDiffusion.dpm_solver_sample_loop = torch.no_grad()(_dpm_solver_sample_loop)
 
 
 class SpacedDiffusion(GaussianDiffusion):

@@ -233,6 +233,16 @@ int b200_se_attention(const void *x, const float *w1, const float *w2, void *out
  *      B200_SAMPLER_GD_DDIM   — GaussianDiffusion.ddim_sample
  *                               (training_project/utils/gaussian_diffusion.py:620-667, 247-351)
  *      B200_SAMPLER_GD_DDPM   — GaussianDiffusion.p_sample (:423-466)
+ *      B200_SAMPLER_DPMPP_2M  — DPM-Solver++ multistep, order <= 2, data prediction: DPM_Solver.data_prediction_fn /
+ *                               dpm_solver_first_update / multistep_dpm_solver_second_update
+ *                               (ldm/models/diffusion/dpm_solver_new/dpm_solver_pytorch.py:435-444, 549-575, 798-835) as
+ *                               driven by DPMSolverSampler.sample (dpm_solver_new/sampler.py:95-101) and by
+ *                               GaussianDiffusion.dpm_solver_sample_loop (training_project/utils/gaussian_diffusion.py:
+ *                               468-523).  No noise.  `hist` holds the previous step's x0 (read when the row's order is
+ *                               2, always overwritten with this step's x0).  phase 0 = whole step in one launch;
+ *                               phase 1 = write the raw x0 to pred_x0 only; phase 2 = dynamic thresholding
+ *                               x0 = clamp(pred_x0, -s, s) / s with s = thresh[n] (dpm_solver_pytorch.py:418-427, s from
+ *                               b200_abs_quantile), then the update.
  * param: 0 eps, 1 x0, 2 v.  coef row layout (B200_SAMPLER_NCOEF floats) is documented in
  * diffusion_models_dsdiff_b200/samplers.py next to the host code that fills it with the
  * reference's own float64->float32 table expressions.                                          */
@@ -240,6 +250,7 @@ int b200_se_attention(const void *x, const float *w1, const float *w2, void *out
 #define B200_SAMPLER_LDM_DDPM 1
 #define B200_SAMPLER_GD_DDIM 2
 #define B200_SAMPLER_GD_DDPM 3
+#define B200_SAMPLER_DPMPP_2M 4
 #define B200_SAMPLER_NCOEF 16
 typedef struct {
   int mode, param;
@@ -254,8 +265,15 @@ typedef struct {
   int step_host;
   float *x_prev;           /* out                                                         */
   float *pred_x0;          /* out, may be NULL                                            */
+  float *hist;             /* DPMPP_2M: previous x0 [N,C,HW], in/out                       */
+  const float *thresh;     /* DPMPP_2M phase 2: per-sample threshold s [N]                 */
+  int phase;               /* DPMPP_2M: 0 fused step, 1 x0 only, 2 threshold + update      */
 } b200_sampler_desc;
 int b200_sampler_update(const b200_sampler_desc *d, void *stream);
+/* out[n] = max(quantile(|x[n, :]|, q), floor_val) with torch.quantile's linear interpolation between the two
+ * neighbouring order statistics (rank = q*(M-1) in fp32) — the scale of DPM-Solver++'s dynamic thresholding
+ * (dpm_solver_pytorch.py:418-427).  Exact radix select, one CTA per sample.                                         */
+int b200_abs_quantile(const float *x, int N, int64_t M, float q, float floor_val, float *out, void *stream);
 /* *step_ptr += delta (one-thread kernel; keeps the step counter on the device for graph replay). */
 int b200_advance_step(int *step_ptr, int delta, void *stream);
 

@@ -636,6 +636,140 @@ def ldm_ddpm_step(sch: LdmSchedule, x: Tensor, model_out: Tensor, t: int, noise:
     return mean + nonzero * (0.5 * logvar).exp() * noise, x0
 
 
+# ----------------------------------------------------------------------------
+# DPM-Solver++ (2M): ldm/models/diffusion/dpm_solver_new/dpm_solver_pytorch.py driven by
+# DPMSolverSampler.sample (dpm_solver_new/sampler.py:35-103): NoiseScheduleVP('discrete', betas),
+# model_type noise | v, algorithm "dpmsolver++", multistep order 2, skip_type "time_uniform",
+# lower_order_final=True, no x0 corrector.  All scalars are fp32 torch tensors as in the reference.
+# ----------------------------------------------------------------------------
+def piecewise_linear(x: Tensor, xp: Tensor, yp: Tensor) -> Tensor:
+    """interpolate_fn (dpm_solver_pytorch.py:1255-1294) for C = 1: the segment is the pair of keypoints around x,
+    the outermost segment beyond the ends.  x [N], xp / yp [K] increasing xp -> [N]."""
+    k = xp.numel()
+    j = torch.searchsorted(xp.contiguous(), x.contiguous()) - 1
+    j = j.clamp(0, k - 2)
+    x0, x1, y0, y1 = xp[j], xp[j + 1], yp[j], yp[j + 1]
+    return y0 + (x - x0) * (y1 - y0) / (x1 - x0)
+
+
+class DpmNoiseScheduleVP:
+    """NoiseScheduleVP(schedule='discrete', betas=...).  dpm_solver_pytorch.py:8-170."""
+
+    def __init__(self, betas: Tensor):
+        log_alphas = 0.5 * torch.log(1 - betas.float()).cumsum(dim=0)                    # :101-102
+        # numerical_clip_alpha (:116-127): drop the tail whose half-logSNR is below -5.1
+        log_sigmas = 0.5 * torch.log(1.0 - torch.exp(2.0 * log_alphas))
+        lambs = log_alphas - log_sigmas
+        idx = int(torch.searchsorted(torch.flip(lambs, [0]), torch.tensor(-5.1)))
+        if idx > 0:
+            log_alphas = log_alphas[:-idx]
+        self.T = 1.0
+        self.log_alpha_array = log_alphas.to(torch.float32)
+        self.total_N = int(log_alphas.numel())
+        self.t_array = torch.linspace(0.0, 1.0, self.total_N + 1)[1:].to(torch.float32)
+
+    def marginal_log_mean_coeff(self, t: Tensor) -> Tensor:
+        return piecewise_linear(t.reshape(-1), self.t_array, self.log_alpha_array)
+
+    def marginal_alpha(self, t):
+        return torch.exp(self.marginal_log_mean_coeff(t))
+
+    def marginal_std(self, t):
+        return torch.sqrt(1.0 - torch.exp(2.0 * self.marginal_log_mean_coeff(t)))
+
+    def marginal_lambda(self, t):
+        lm = self.marginal_log_mean_coeff(t)
+        return lm - 0.5 * torch.log(1.0 - torch.exp(2.0 * lm))
+
+    def inverse_lambda(self, lamb: Tensor) -> Tensor:
+        """:158-170 (discrete): t of a given half-logSNR."""
+        log_alpha = -0.5 * torch.logaddexp(torch.zeros((1,)), -2.0 * lamb.reshape(-1))
+        return piecewise_linear(log_alpha, torch.flip(self.log_alpha_array, [0]), torch.flip(self.t_array, [0]))
+
+    def model_input_time(self, t: Tensor) -> Tensor:
+        """get_model_input_time (:273-282): continuous t in [1/N, 1] -> the network's timestep."""
+        return (t - 1.0 / self.total_N) * 1000.0
+
+
+class DpmSolverPP2M:
+    """DPM_Solver(algorithm_type='dpmsolver++').sample(method='multistep', order=2) (:1049-1215) with the per-step
+    scalars exposed as a table so the CUDA path can be checked coefficient by coefficient.
+
+    ``skip_type``: 'time_uniform' (ldm DPMSolverSampler) or 'logSNR' (gaussian_diffusion.py:512-516).
+    ``thresholding``: dynamic thresholding of x0 (:418-427; used by the guided-diffusion caller only)."""
+
+    def __init__(self, betas: Tensor, steps: int, skip_type: str = "time_uniform", lower_order_final: bool = True,
+                 thresholding: bool = False, max_val: float = 1.0, ratio: float = 0.995):
+        ns = self.ns = DpmNoiseScheduleVP(betas)
+        self.steps, self.thresholding, self.max_val, self.ratio = steps, thresholding, max_val, ratio
+        t_0, t_T = 1.0 / ns.total_N, ns.T
+        if skip_type == "time_uniform":                                                   # get_time_steps :455-482
+            ts = torch.linspace(t_T, t_0, steps + 1)
+        elif skip_type == "logSNR":
+            l_T, l_0 = ns.marginal_lambda(torch.tensor(t_T)), ns.marginal_lambda(torch.tensor(t_0))
+            ts = ns.inverse_lambda(torch.linspace(l_T.item(), l_0.item(), steps + 1))
+        else:
+            raise ValueError(skip_type)
+        self.timesteps = ts
+        self.orders = []
+        for step in range(1, steps + 1):                                                  # :1184-1203
+            if step == 1:
+                self.orders.append(1)
+            elif lower_order_final and steps < 10:
+                self.orders.append(min(2, steps + 1 - step))
+            else:
+                self.orders.append(2)
+        # per update k (from timesteps[k] to timesteps[k+1]): the scalars of :549-575 (order 1) / :798-835 (order 2)
+        rows = []
+        for k in range(steps):
+            s_t, t_t = ts[k].reshape(1), ts[k + 1].reshape(1)
+            lam_s, lam_t = ns.marginal_lambda(s_t), ns.marginal_lambda(t_t)
+            h = lam_t - lam_s
+            sigma_s, sigma_t = ns.marginal_std(s_t), ns.marginal_std(t_t)
+            alpha_t = torch.exp(ns.marginal_log_mean_coeff(t_t))
+            phi_1 = torch.expm1(-h)
+            row = {"alpha_s": ns.marginal_alpha(s_t), "sigma_s": sigma_s, "A": sigma_t / sigma_s, "B": alpha_t * phi_1,
+                   "inv_r0": torch.zeros(1), "halfB": 0.5 * (alpha_t * phi_1), "order": self.orders[k],
+                   "t_input": ns.model_input_time(s_t)}
+            if self.orders[k] == 2:
+                lam_p = ns.marginal_lambda(ts[k - 1].reshape(1))
+                r0 = (lam_s - lam_p) / h
+                row["inv_r0"] = 1.0 / r0
+            rows.append(row)
+        self.rows = rows
+
+    def data_prediction(self, x: Tensor, out: Tensor, k: int, model_type: str) -> Tensor:
+        """noise_pred_fn (:284-300) + data_prediction_fn (:435-444) at timesteps[k]."""
+        a, sg = self.rows[k]["alpha_s"], self.rows[k]["sigma_s"]
+        noise = out if model_type == "noise" else a * out + sg * x
+        x0 = (x - sg * noise) / a
+        if self.thresholding:                                                             # :418-427
+            q = torch.quantile(torch.abs(x0).reshape((x0.shape[0], -1)), self.ratio, dim=1)
+            q = torch.maximum(q, self.max_val * torch.ones_like(q))[(...,) + (None,) * (x0.dim() - 1)]
+            x0 = torch.clamp(x0, -q, q) / q
+        return x0
+
+    def update(self, x: Tensor, m0: Tensor, m1: Optional[Tensor], k: int) -> Tensor:
+        r = self.rows[k]
+        if r["order"] == 1:
+            return r["A"] * x - r["B"] * m0
+        d1 = r["inv_r0"] * (m0 - m1)
+        return r["A"] * x - r["B"] * m0 - r["halfB"] * d1
+
+    def sample(self, model_fn, x: Tensor, model_type: str = "v", record: Optional[list] = None) -> Tensor:
+        """model_fn(x, t_input[B]) -> network output; ``model_type`` 'noise' | 'v' (sampler.py:14-17)."""
+        m_prev = None
+        for k in range(self.steps):
+            t_in = self.rows[k]["t_input"].expand(x.shape[0])
+            out = model_fn(x, t_in)
+            m0 = self.data_prediction(x, out, k, model_type)
+            x = self.update(x, m0, m_prev, k)
+            m_prev = m0
+            if record is not None:
+                record.append({"model_out": out, "x0": m0, "x": x})
+        return x
+
+
 def gd_named_betas(name: str, n: int) -> np.ndarray:
     """get_named_beta_schedule.  training_project/utils/gaussian_diffusion.py:33-57."""
     if name == "linear":

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/b200diff.h but not exported"
     assert set(L.SIGNATURES) == set(syms), "ctypes table and header disagree"
-    assert L.lib().b200_abi_version() == 2
+    assert L.lib().b200_abi_version() == 3
     assert L.lib().b200_launch_count() == 0 or True
 
 
@@ -251,3 +251,41 @@ def test_unsupported_paths_fail_loudly():
         P.UNetModel(**{**hp, "num_classes": 10})
     with pytest.raises(AssertionError):             # the reference's own ctor check (openaimodel.py:630-637)
         P.UNetModel(**{**hp, "use_spatial_transformer": True})
+
+
+# -------------------------------------------------------------------------------------------------
+# DPM-Solver++ host tables (product code) vs the oracle restatement and the reference-generated goldens
+# -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("steps,skip,lof", [(6, "time_uniform", True), (12, "time_uniform", True), (20, "logSNR", False)])
+def test_dpm_solver_tables_match_oracle(steps, skip, lof):
+    import torch
+    import dsdiff_oracle as O
+    from diffusion_models_dsdiff_b200 import dpm_solver as D
+    sch = O.LdmSchedule(timesteps=2000, beta_schedule="linear", linear_start=1e-4, linear_end=2e-2)
+    betas = torch.from_numpy(sch.betas)
+    ns = D.NoiseScheduleVP("discrete", betas=betas)
+    ref = O.DpmSolverPP2M(betas, steps, skip_type=skip, lower_order_final=lof)
+    assert ns.total_N == ref.ns.total_N < 2000          # the -5.1 logSNR clip drops the tail of the T=2000 schedule
+    coef, t_in, orders = D.multistep_tables(ns, steps, skip, 2, lof)
+    assert orders == ref.orders
+    for k, r in enumerate(ref.rows):
+        got = coef[k]
+        want = [r["alpha_s"], r["sigma_s"], r["A"], r["B"], r["inv_r0"], r["halfB"]]
+        for j, w in enumerate(want):
+            assert abs(float(got[j]) - float(w)) <= 1e-6 * max(1.0, abs(float(w))), (k, j)
+        assert float(got[6]) == r["order"]
+        assert abs(float(t_in[k]) - float(r["t_input"])) < 1e-3
+
+
+def test_dpm_solver_model_timesteps_match_reference_golden():
+    import torch
+    import dsdiff_oracle as O
+    from _util import golden
+    from diffusion_models_dsdiff_b200 import dpm_solver as D
+    sch = O.LdmSchedule(timesteps=2000, beta_schedule="linear", linear_start=1e-4, linear_end=2e-2)
+    for S in (6, 12):
+        g = golden(f"dpmpp_v_S{S}")
+        ns = D.NoiseScheduleVP("discrete", betas=torch.from_numpy(sch.betas))
+        assert ns.total_N == g["total_N"]
+        _, t_in, _ = D.multistep_tables(ns, S)
+        assert float((t_in - g["t_input"]).abs().max()) < 1e-3

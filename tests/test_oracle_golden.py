@@ -175,3 +175,37 @@ def test_dit_oracle_matches_reference(case):
     assert y.shape == g["y_out"].shape
     assert g["y_out"].abs().max() > 0.05
     assert maxabs(y, g["y_out"]) < TOL * max(1.0, float(g["y_out"].abs().max()))
+
+
+# -------------------------------------------------------------------------------------------------
+# DPM-Solver++ 2M: oracle restatement vs the reference's DPMSolverSampler / DPM_Solver outputs
+# -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case,param", [("dpmpp_v_S6", "v"), ("dpmpp_v_S12", "v"), ("dpmpp_eps_S6", "eps"),
+                                        ("dpmpp_eps_S12", "eps")])
+def test_dpm_solver_pp_oracle_matches_reference(case, param):
+    hp, sd = synth_sd("unet_small")
+    g = golden(case)
+    sch = O.LdmSchedule(timesteps=2000, beta_schedule="linear", linear_start=1e-4, linear_end=2e-2)
+    solver = O.DpmSolverPP2M(torch.from_numpy(sch.betas), g["S"])
+    assert solver.ns.total_N == g["total_N"]                 # numerical_clip_alpha drops the same tail
+    t_in = torch.stack([r["t_input"][0] for r in solver.rows])
+    assert maxabs(t_in, g["t_input"]) < 1e-3                  # on a 0..1000 scale
+    rec = []
+    fn = lambda x, t: O.unet_forward(sd, hp, torch.cat([x, g["cond"]], 1), t)
+    out = solver.sample(fn, g["x_T"], "noise" if param == "eps" else "v", record=rec)
+    for i in range(g["S"]):      # eps-parameterised random networks grow to |x| ~ 400: tolerance relative to the scale
+        assert maxabs(rec[i]["x"], g["x_inter"][i]) < 2e-5 * max(1.0, float(g["x_inter"][i].abs().max())), i
+    assert maxabs(out, g["final"]) < 2e-5 * max(1.0, float(g["final"].abs().max()))
+
+
+def test_dpm_solver_pp_thresholding_logsnr_oracle_matches_reference():
+    hp, sd = synth_sd("ds_small")
+    g = golden("dpmpp_gd_thresh")
+    solver = O.DpmSolverPP2M(g["betas"], g["S"], skip_type="logSNR", lower_order_final=False, thresholding=True)
+    assert solver.ns.total_N == g["total_N"]
+    rec = []
+    fn = lambda x, t: O.dsunet_forward(sd, hp, torch.cat([x, g["cond"]], 1), t)[0]
+    out = solver.sample(fn, g["x_T"], "v", record=rec)
+    for i in range(g["S"]):
+        assert maxabs(rec[i]["x"], g["x_inter"][i]) < 2e-4, i
+    assert maxabs(out, g["final"]) < 2e-4
