@@ -271,3 +271,46 @@ def test_dpm_solver_thresholding_logsnr_matches_reference():
     for i in range(g["S"]):
         assert maxabs(rec[i]["x_prev"].cpu(), g["x_inter"][i]) < 1e-2 * max(1.0, float(g["x_inter"][i].abs().max())), i
     assert maxabs(out.cpu(), g["final"]) < 1e-2
+
+
+# -------------------------------------------------------------------------------------------------
+# north_star metric gates at full slice size: PSNR within 0.05 dB, MS-SSIM within 1e-3, SUV within 1e-3 (relative)
+# -------------------------------------------------------------------------------------------------
+def test_metric_parity_on_256x256_slices():
+    import metrics as M
+    import diffusion_models_dsdiff_b200 as P
+    from diffusion_models_dsdiff_b200 import samplers as S
+    hp = dict(image_size=32, in_channels=4, model_channels=32, out_channels=1, num_res_blocks=1,
+              attention_resolutions=[8], channel_mult=[1, 2, 4, 4], num_head_channels=16, use_new_attention_order=True,
+              legacy=False)
+    net = P.UNetModel(**hp)
+    sd = O.synth_state_dict({k: tuple(v.shape) for k, v in net.state_dict().items()})
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    model = S.DDPM(net, timesteps=2000, beta_schedule="linear", linear_start=1e-4, linear_end=2e-2,
+                   conditioning_key="concat", parameterization="v", clip_denoised=True).cuda()
+    B, n_steps = 2, 5
+    gen = torch.Generator().manual_seed(2024)
+    cond = (torch.randn(B, 3, 256, 256, generator=gen) * 0.5).clamp_(-1, 1)
+    x_T = torch.randn(B, 1, 256, 256, generator=torch.Generator().manual_seed(2025))
+    noises = [torch.zeros(B, 1, 256, 256) for _ in range(n_steps)]
+    out, _ = S.DDIMSampler(model).sample(n_steps, B, (1, 256, 256), cond.cuda(), eta=0.0, x_T=x_T.cuda(), verbose=False,
+                                         noises=noises)
+    # the same loop with the oracle (CPU restatement of the reference)
+    sch = O.LdmSchedule(timesteps=2000, beta_schedule="linear", linear_start=1e-4, linear_end=2e-2)
+    tab = O.LdmDdimTables(sch, n_steps, 0.0)
+    x = x_T.clone()
+    with torch.no_grad():
+        for i in range(n_steps):
+            index = n_steps - 1 - i
+            ts = torch.full((B,), int(tab.timesteps[index]), dtype=torch.long)
+            x, _ = O.ldm_ddim_step(sch, tab, x, O.unet_forward(sd, hp, torch.cat([x, cond], 1), ts), index, noises[i], "v", True)
+    got, ref = out.cpu()[:, 0].numpy(), x[:, 0].numpy()
+    assert maxabs(out.cpu(), x) < 1e-2
+    # synthetic ground truth: the reference output plus a smooth perturbation (so PSNR / MS-SSIM are in a realistic range)
+    yy, xx = np.meshgrid(np.linspace(0, 4 * np.pi, 256), np.linspace(0, 4 * np.pi, 256), indexing="ij")
+    gt = np.clip(ref + 0.15 * np.sin(yy)[None] * np.cos(xx)[None], -1, 1)
+    assert abs(M.psnr(gt, got) - M.psnr(gt, ref)) < 0.05
+    assert abs(M.ms_ssim(gt, got) - M.ms_ssim(gt, ref)) < 1e-3
+    suv = lambda a: M.suv_mean(M.pet_to_suv(M.inverse_normalize(a, 0.0, 32000.0), 70.0, 3.7e8, 6586.2, 3600.0))
+    assert abs(suv(got) - suv(ref)) < 1e-3 * suv(ref)

@@ -289,3 +289,25 @@ def test_dpm_solver_model_timesteps_match_reference_golden():
         assert ns.total_N == g["total_N"]
         _, t_in, _ = D.multistep_tables(ns, S)
         assert float((t_in - g["t_input"]).abs().max()) < 1e-3
+
+
+# -------------------------------------------------------------------------------------------------
+# evaluation metrics restated for the parity gates (oracle/metrics.py): closed-form checks
+# -------------------------------------------------------------------------------------------------
+def test_metrics_closed_forms():
+    import numpy as np
+    import metrics as M
+    rs = np.random.RandomState(0)
+    gt = rs.rand(3, 192, 192)
+    assert abs(M.psnr(gt, gt + 0.01) - 10 * np.log10((gt.max() - gt.min()) ** 2 / 1e-4)) < 1e-9
+    assert abs(M.ms_ssim(gt.copy(), gt.copy()) - 1.0) < 1e-12                 # identical volumes
+    noisy = gt + 0.2 * rs.randn(*gt.shape)
+    v = M.ms_ssim(gt.copy(), noisy)
+    assert 0.0 < v < 0.999
+    assert abs(M.ms_ssim(gt.copy(), noisy * 3.0 + 7.0) - v) < 1e-9            # scale12bit removes affine intensity maps
+    s = M.scale12bit(gt)
+    assert abs(s.mean() - 2048.0) < 1e-6 and abs(s.std() - 400.0) < 1e-6
+    x = np.array([-2.0, -1.0, 0.0, 1.0], dtype=np.float32)
+    assert np.allclose(M.inverse_normalize(x, 10.0, 30.0), [10.0, 10.0, 20.0, 30.0])
+    suv = M.pet_to_suv(np.array([1000.0]), weight_kg=70.0, total_dose_bq=3.7e8, half_life_s=6586.2, decay_time_s=6586.2)
+    assert abs(float(suv[0]) - 1000.0 * 1000.0 * 70.0 / (3.7e8 / 2)) < 1e-3
