@@ -311,3 +311,17 @@ def test_metrics_closed_forms():
     assert np.allclose(M.inverse_normalize(x, 10.0, 30.0), [10.0, 10.0, 20.0, 30.0])
     suv = M.pet_to_suv(np.array([1000.0]), weight_kg=70.0, total_dose_bq=3.7e8, half_life_s=6586.2, decay_time_s=6586.2)
     assert abs(float(suv[0]) - 1000.0 * 1000.0 * 70.0 / (3.7e8 / 2)) < 1e-3
+
+
+@pytest.mark.parametrize("case", ["dit_small", "dit_p2"])
+def test_dit_state_dict_matches_reference(case):
+    """Key names / shapes of the reference's DiT (with timm's sub-module names) so its checkpoints load strictly."""
+    import diffusion_models_dsdiff_b200 as P
+    from _util import manifest
+    m = manifest()[case]
+    net = P.DiT(**m["hp"])
+    got = {k: list(v.shape) for k, v in net.state_dict().items() if k != "pos_embed"}
+    assert got == {k: list(v) for k, v in m["shapes"].items()}
+    assert "pos_embed" in net.state_dict()
+    with pytest.raises(P.B200Error):
+        net(torch.zeros(1, m["hp"]["in_channels"], m["hp"]["input_size"], m["hp"]["input_size"]), torch.zeros(1))

@@ -1,0 +1,80 @@
+"""Slice sharding: no data-path collective, one gather of finished slices.  world_size > 1 runs on the
+gloo backend (CPU) here; on the GPU box the same code runs over NCCL (bench.py --gpus N)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from diffusion_models_dsdiff_b200 import parallel as PAR
+
+
+def test_shard_range_partitions_a_brats_volume():
+    sizes = [PAR.shard_range(155, r, 8) for r in range(8)]           # 155 = 8*19 + 3
+    assert [e - b for b, e in sizes] == [20, 20, 20, 19, 19, 19, 19, 19]
+    assert sizes[0][0] == 0 and sizes[-1][1] == 155
+    assert all(sizes[i][1] == sizes[i + 1][0] for i in range(7))      # contiguous, disjoint, covering
+
+
+@pytest.mark.parametrize("n,world", [(0, 4), (3, 8), (64, 8), (1, 1), (7, 2)])
+def test_shard_range_edge_cases(n, world):
+    got = [PAR.shard_range(n, r, world) for r in range(world)]
+    assert sum(e - b for b, e in got) == n
+    assert max(e - b for b, e in got) - min(e - b for b, e in got) <= 1
+    with pytest.raises(ValueError):
+        PAR.shard_range(n, world, world)
+
+
+def test_slice_noise_is_independent_of_the_batch_split():
+    full = PAR.slice_noise(list(range(10)), (1, 8, 8), 2025, "cpu")
+    a = PAR.slice_noise([0, 1, 2], (1, 8, 8), 2025, "cpu")
+    b = PAR.slice_noise([7], (1, 8, 8), 2025, "cpu")
+    assert torch.equal(full[:3], a) and torch.equal(full[7:8], b)
+    assert not torch.equal(full[0], full[1])
+    assert not torch.equal(PAR.slice_noise([0], (1, 8, 8), 2025, "cpu", stream_id=1), full[:1])
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _finished_slice(sid: int) -> torch.Tensor:
+    """CPU stand-in for one sampled slice: depends on the slice id only (the CUDA sampler cannot run here)."""
+    return PAR.slice_noise([sid], (1, 16, 16), 99, "cpu")[0] * 0.5 + sid
+
+
+def _worker(rank, world, port, n_total, out_path):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b, e = PAR.shard_range(n_total, rank, world)
+        local = torch.stack([_finished_slice(i) for i in range(b, e)]) if e > b else torch.empty((0, 1, 16, 16))
+        full = PAR.gather_slices(local, n_total)
+        if rank == 0:
+            torch.save(full, out_path)
+        else:
+            assert full is None
+        with pytest.raises(ValueError):                      # wrong local count is an error, not a silent truncation
+            PAR.gather_slices(torch.zeros((e - b + 1, 1, 16, 16)), n_total)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_total", [(2, 8), (2, 7), (3, 155)])
+def test_gather_slices_gloo_matches_single_process(world, n_total, tmp_path):
+    out = str(tmp_path / "full.pt")
+    mp.spawn(_worker, args=(world, _free_port(), n_total, out), nprocs=world, join=True)
+    full = torch.load(out)
+    ref = torch.stack([_finished_slice(i) for i in range(n_total)])
+    assert full.shape == ref.shape and torch.equal(full, ref)   # result independent of the world size
+
+
+def test_gather_slices_single_process_identity():
+    x = torch.randn(5, 1, 4, 4)
+    assert PAR.gather_slices(x, 5) is x
+    with pytest.raises(ValueError):
+        PAR.gather_slices(x, 6)
