@@ -456,27 +456,58 @@ int pick_bn(int Cout) {
 }
 }  // namespace
 
+// pixel box: TW x TH x TN == 128.  The box is chosen from (Hout, Wout) ONLY — never from N — so that the result
+// for one image is bit-identical whatever batch it is part of (slices are independent units):
+// minimise the padded area of one image, prefer 16-wide boxes on ties (square-ish halo => better L2 locality).
+static void pick_box(int Hout, int Wout, int *TW, int *TH, int *TN) {
+  long best = -1;
+  for (int tw = 32; tw >= 1; tw >>= 1) {
+    int th = std::min(pow2_ceil(Hout), kBM / tw);
+    int tn = kBM / (tw * th);
+    long area = (long)cdiv(Wout, tw) * tw * cdiv(Hout, th) * th;
+    if (best < 0 || area < best || (area == best && tw == 16)) {
+      best = area; *TW = tw; *TH = th; *TN = tn;
+    }
+  }
+}
+
+// (CTAs per tile, N tile) for one launch.  Big layers: CTA pairs with the largest N tile that divides Cout (operand
+// bytes per FLOP are lowest).  Layers with fewer tiles than SMs (8x8 .. 32x32 maps) are latency / weight-streaming
+// bound: shrink the N tile (and drop to single-CTA tiles) until every SM has a tile, using the model
+//   time ~ waves x K-chunks x max(BN/2, 32) cycles   (BN/2 = tensor-pipe cycles of a 128 x BN x 16 MMA, 32 = the cycles
+//   shared memory needs to feed its 4 KB A operand).
+// The choice never changes the K order of any output element, so results stay bit-identical.
+static void choose_tiling(const b200_conv_desc *d, int *ctas, int *bn) {
+  int TW = 1, TH = 1, TN = 1;
+  pick_box(d->Hout, d->Wout, &TW, &TH, &TN);
+  const long ptiles = (long)cdiv(d->Wout, TW) * cdiv(d->Hout, TH) * cdiv(d->N, TN);
+  const int sms = num_sms();
+  *ctas = 2;
+  *bn = pick_bn(d->Cout);
+  if (getenv("B200DIFF_CONV_NO_SMALL_TILES")) return;
+  if (cdiv((int)ptiles, 2) * (long)cdiv(d->Cout, *bn) >= sms / 2) return;      // every CTA pair already has a tile
+  double best = 1e30;
+  for (int c = 2; c >= 1; --c) {
+    for (int b = 256; b >= 32; b -= 16) {
+      if (d->Cout % b) continue;
+      const long tiles = cdiv((int)ptiles, c) * (long)(d->Cout / b);
+      const long waves = (tiles + sms / c - 1) / (sms / c);
+      const double cost = (double)waves * std::max(b / 2, 32) * (c == 1 ? 1.02 : 1.0);   // ties: pairs, then larger N
+      if (cost < best - 1e-9) { best = cost; *ctas = c; *bn = b; }
+    }
+  }
+}
+
 template <typename T, int kCtas>
-static int launch_conv(const b200_conv_desc *d, cudaStream_t stream) {
+static int launch_conv(const b200_conv_desc *d, int bn, cudaStream_t stream) {
   ConvKParams p{};
   ConvMaps maps{};
   p.N = d->N; p.Hout = d->Hout; p.Wout = d->Wout; p.Cout = d->Cout;
   p.stride = d->stride;
   p.nseg = d->nseg;
-  p.BN = pick_bn(d->Cout);
+  p.BN = bn;
   p.n_ntiles = cdiv(d->Cout, p.BN);
-  // pixel box: TW x TH x TN == 128.  The box is chosen from (Hout, Wout) ONLY — never from N — so that the result
-  // for one image is bit-identical whatever batch it is part of (slices are independent units):
-  // minimise the padded area of one image, prefer 16-wide boxes on ties (square-ish halo => better L2 locality).
-  long best = -1;
-  for (int tw = 32; tw >= 1; tw >>= 1) {
-    int th = std::min(pow2_ceil(d->Hout), kBM / tw);
-    int tn = kBM / (tw * th);
-    long area = (long)cdiv(d->Wout, tw) * tw * cdiv(d->Hout, th) * th;
-    if (best < 0 || area < best || (area == best && tw == 16)) {
-      best = area; p.TW = tw; p.TH = th; p.TN = tn;
-    }
-  }
+  pick_box(d->Hout, d->Wout, &p.TW, &p.TH, &p.TN);
   p.tiles_w = cdiv(d->Wout, p.TW);
   p.tiles_h = cdiv(d->Hout, p.TH);
   p.tiles_n = cdiv(d->N, p.TN);
@@ -567,11 +598,14 @@ extern "C" int b200_conv2d_igemm(const b200_conv_desc *d, void *stream) {
   B200_CHECK(d->out_nchw_f32 == nullptr || (d->cout_real >= 1 && d->cout_real <= d->Cout && !d->gn_sums),
              "conv: bad NCHW fp32 head output request");
   // CTA pairs need an N tile that splits into two halves of whole 8-row core groups (BN % 16 == 0 always holds)
-  static const bool one_cta = getenv("B200DIFF_CONV_1CTA") != nullptr;
+  static const bool force_one_cta = getenv("B200DIFF_CONV_1CTA") != nullptr;
+  int ctas, bn;
+  choose_tiling(d, &ctas, &bn);
+  const bool one_cta = force_one_cta || ctas == 1;
   if (d->act_dtype == B200_F16)
-    return one_cta ? launch_conv<__half, 1>(d, (cudaStream_t)stream) : launch_conv<__half, 2>(d, (cudaStream_t)stream);
+    return one_cta ? launch_conv<__half, 1>(d, bn, (cudaStream_t)stream) : launch_conv<__half, 2>(d, bn, (cudaStream_t)stream);
   if (d->act_dtype == B200_BF16)
-    return one_cta ? launch_conv<__nv_bfloat16, 1>(d, (cudaStream_t)stream)
-                   : launch_conv<__nv_bfloat16, 2>(d, (cudaStream_t)stream);
+    return one_cta ? launch_conv<__nv_bfloat16, 1>(d, bn, (cudaStream_t)stream)
+                   : launch_conv<__nv_bfloat16, 2>(d, bn, (cudaStream_t)stream);
   B200_CHECK(false, "conv: bad act_dtype %d", d->act_dtype);
 }

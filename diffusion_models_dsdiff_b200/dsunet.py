@@ -15,6 +15,7 @@ one fused 4-input kernel whose output then enters the concat-aware GroupNorm / s
 from __future__ import annotations
 
 import copy
+import os
 from typing import Optional
 
 import torch
@@ -66,6 +67,14 @@ class DSUnetModel(_EngineModule):
         self.anatomy_proj, self.lesion_proj = mk(), mk()
         self.all_proj = nn.Sequential(nn.SiLU(), nn.Conv2d(half * 6, conv_ch, 1, 1, 0))
         self._init_engine()
+        self.encoder_streams = os.environ.get("B200DIFF_ENCODER_STREAMS", "1") != "0"
+        self._streams = {}
+
+    def _side_streams(self, device):
+        key = (device.type, device.index)
+        if key not in self._streams:
+            self._streams[key] = [torch.cuda.Stream(device=device) for _ in range(3)]
+        return self._streams[key]
 
     # FeatureDisentangle.forward (:165-168): conv_2(conv_1(x) + x)
     def _fd(self, cx: Ctx, m: FeatureDisentangle, x: Act) -> Tensor:
@@ -101,20 +110,45 @@ class DSUnetModel(_EngineModule):
             inputs = [x[:, 0:1], x[:, 1:2], zero, zero]
         else:                     # :660-663
             inputs = [x[:, 0:1], x[:, 1:2], x[:, 2:3], x[:, 3:4]]
-        skips, last = [], []
-        for blocks, xin in zip((self.input_blocks, self.input_blocks_a, self.input_blocks_al, self.input_blocks_l),
-                               inputs):
+        def encoder(blocks, xin):
             h = run_in_conv(cx, blocks[0][0], xin.contiguous(), self.act_dtype)
             hs = [h]
             for blk in list(blocks)[1:]:
                 h = run_sequential(cx, blk, h, None)
                 hs.append(h)
-            skips.append(hs)
-            last.append(h)
+            return hs
+
+        enc_blocks = (self.input_blocks, self.input_blocks_a, self.input_blocks_al, self.input_blocks_l)
+        # The four encoders are independent (separate weights, same emb): the three conditioning encoders run on side
+        # streams, forked after the timestep path and joined before their first consumer, so their latency-bound
+        # 8x8 .. 32x32 layers overlap with the noise stream's instead of leaving most SMs idle.  Inside a captured
+        # CUDA graph this becomes four parallel branches.  (Per-launch event timing keeps everything on one stream.)
+        fork = self.encoder_streams and ops._timer is None
+        if fork:
+            main = torch.cuda.current_stream(x.device)
+            side = self._side_streams(x.device)
+            ev0 = torch.cuda.Event()
+            ev0.record(main)
+            skips = [None] * 4
+            joins = []
+            for i in (1, 2, 3):
+                with torch.cuda.stream(side[i - 1]):
+                    side[i - 1].wait_event(ev0)
+                    skips[i] = encoder(enc_blocks[i], inputs[i])
+                    ev = torch.cuda.Event()
+                    ev.record(side[i - 1])
+                    joins.append(ev)
+            skips[0] = encoder(enc_blocks[0], inputs[0])
+        else:
+            skips = [encoder(b, xin) for b, xin in zip(enc_blocks, inputs)]
+        last = [hs[-1] for hs in skips]
         h_n = run_sequential(cx, self.middle_block, last[0], None)     # :688
         h_a, h_al, h_l = last[1], last[2], last[3]
         fd = lambda m, v: self._fd(cx, m, v)
         h_n_style, h_n_content = fd(self.conv_style, h_n), fd(self.conv_content, h_n)
+        if fork:
+            for ev in joins:
+                main.wait_event(ev)
         style = [fd(self.conv_style, v) for v in (h_a, h_al, h_l)]
         content = [fd(self.conv_content, v) for v in (h_a, h_al, h_l)]
         anatomy = [fd(self.conv_anatomy, v) for v in (h_a, h_al)]
