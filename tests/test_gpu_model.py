@@ -314,3 +314,39 @@ def test_metric_parity_on_256x256_slices():
     assert abs(M.ms_ssim(gt, got) - M.ms_ssim(gt, ref)) < 1e-3
     suv = lambda a: M.suv_mean(M.pet_to_suv(M.inverse_normalize(a, 0.0, 32000.0), 70.0, 3.7e8, 6586.2, 3600.0))
     assert abs(suv(got) - suv(ref)) < 1e-3 * suv(ref)
+
+
+# -------------------------------------------------------------------------------------------------
+# BASELINE.json's configurations at FULL size: one network evaluation of one 256x256 slice vs the oracle
+# (size-independent checks — determinism, batch independence — are in the tests above and hold for any size)
+# -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("workload", ["cfg1", "cfg2"])
+def test_full_size_network_forward_vs_oracle(workload):
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import diffusion_models_dsdiff_b200 as P
+    wl = bench.WORKLOADS[workload]
+    torch.manual_seed(0)
+    with torch.device("cuda"):
+        net = getattr(P, wl["cls"])(**wl["hp"]).eval()
+    sd = {k: v.detach().float().cpu() for k, v in net.state_dict().items()}
+    # zero_module() layers are zero at init (SURVEY §8 gotcha 1): refill them so the output is not trivially the bias
+    g = torch.Generator().manual_seed(1)
+    for k, v in sd.items():
+        if v.numel() and not v.any():
+            sd[k] = torch.randn(v.shape, generator=g) * 0.02
+    net.load_state_dict(sd, strict=True)
+    cond, x_T = bench.synth_inputs(1, wl["cond_ch"], 256, 0)
+    xc = torch.cat([x_T, cond], 1)
+    ts = torch.tensor([1961])
+    fwd = O.dsunet_forward if wl["cls"] == "DSUnetModel" else O.unet_forward
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = fwd(sd, wl["hp"], xc, ts)
+    ref = ref[0] if isinstance(ref, tuple) else ref
+    got = net(xc.cuda(), ts.cuda())
+    got = (got[0] if isinstance(got, tuple) else got).cpu()
+    assert ref.abs().max() > 1e-3
+    rel = O.rel_err(got, ref)
+    assert rel < REL_TOL[torch.float16], f"{workload} full-size rel err {rel:.3e}"
