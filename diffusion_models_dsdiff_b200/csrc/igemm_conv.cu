@@ -15,7 +15,8 @@ namespace b200 {
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kMaxStages = 8;
-constexpr int kConvThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kConvThreads = 320;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
+constexpr int kStatSmem = 8 * 256 * 4;   // per-epilogue-warp GroupNorm column accumulators
 constexpr int kAccCols = 256;      // TMEM columns per accumulator stage
 constexpr int kTmemCols = 512;     // two accumulator stages
 constexpr int kABytes = kBM * kBK * 2;
@@ -193,7 +194,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tmem_full_bar[a]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[a]), 4 * kCtas);  // one arrive per epilogue warp (of both CTAs)
+      mbar_init(smem_u32(&tmem_empty_bar[a]), 8 * kCtas);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
@@ -314,16 +315,43 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       }
     }
   } else {
-    // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
-    const int lane_base = 32 * (warp & 3);
+    // ===================== epilogue: 8 warps, two per TMEM lane quadrant, interleaved 16-column chunks ==========
+    const int ew = warp - 2;                     // 0..7
+    const int g = ew >> 2;                       // this warp takes the chunks with (chunk & 1) == g
+    const int lane_base = 32 * (warp & 3);       // a warp may only touch TMEM lanes 32 * (warp id % 4) ..+31
     const int m = lane_base + lane;
     const int tw = m % p.TW;
     const int th = (m / p.TW) % p.TH;
     const int tn = m / (p.TW * p.TH);
     T *out = reinterpret_cast<T *>(p.out);
     const T *res = reinterpret_cast<const T *>(p.residual);
+    // GroupNorm statistics: per-warp fp32 column accumulators in shared memory, flushed to the fp64 global sums only
+    // when the warp moves to another image / N tile (a persistent CTA stays ~7 tiles inside one image).
+    float *st_sum = reinterpret_cast<float *>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * stage_bytes) + ew * 256;
+    float *st_sq = st_sum + 128;
+    int acc_n = -1, acc_ntile = 0;
+    if (p.gn_sums) {
+      for (int i = lane; i < 256; i += 32) st_sum[i] = 0.f;
+      __syncwarp();
+    }
+    auto flush_stats = [&]() {
+      __syncwarp();
+      for (int slot = lane; slot < 128; slot += 32) {
+        const int chunk = (slot >> 4) * 2 + g;
+        const int ch = acc_ntile * p.BN + chunk * 16 + (slot & 15);
+        if (acc_n >= 0 && acc_n < p.N && chunk * 16 < p.BN && ch < p.Cout) {
+          double *dst = p.gn_sums + ((size_t)acc_n * p.Cout + ch) * 2;
+          atomicAdd(dst, (double)st_sum[slot]);
+          atomicAdd(dst + 1, (double)st_sq[slot]);
+        }
+        st_sum[slot] = 0.f;
+        st_sq[slot] = 0.f;
+      }
+      __syncwarp();
+    };
     int it = 0;
     const uint32_t empty_bar_leader0 = (kCtas == 2) ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
+    const int nch = p.debug_skip_epilogue ? 0 : (p.BN >> 4);
     for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -337,13 +365,26 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       const int n_warp = n0 + lane_base / (p.TW * p.TH);
       const bool valid = (w < p.Wout) && (h < p.Hout) && (n < p.N);
       const size_t pix = ((size_t)n * p.Hout + h) * p.Wout + w;
+      if (p.gn_sums && (n_warp != acc_n || n_tile != acc_ntile)) {
+        if (acc_n >= 0) flush_stats();
+        acc_n = n_warp;
+        acc_ntile = n_tile;
+      }
       mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + acc * kAccCols;
-      for (int c = 0; c < (p.debug_skip_epilogue ? 0 : p.BN); c += 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr + c, r);
-        tmem_ld_wait();
+
+      // residual for one 16-column chunk, issued one chunk ahead so its latency hides behind the previous chunk's math
+      auto load_res = [&](int c, uint4 (&q)[2]) {
+        const int co = n_tile * p.BN + c;
+        q[0] = make_uint4(0, 0, 0, 0);
+        q[1] = q[0];
+        if (res && valid) {
+          if (co < p.Cout) q[0] = *reinterpret_cast<const uint4 *>(res + pix * p.Cout + co);
+          if (co + 8 < p.Cout) q[1] = *reinterpret_cast<const uint4 *>(res + pix * p.Cout + co + 8);
+        }
+      };
+      auto process = [&](const uint32_t (&r)[16], const uint4 (&rq)[2], int c) {
         const int co = n_tile * p.BN + c;
         float v[16];
 #pragma unroll
@@ -382,9 +423,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
               vh[4] *= g1.x; vh[5] *= g1.y; vh[6] *= g1.z; vh[7] *= g1.w;
             }
             if (res) {
-              const uint4 ru = *reinterpret_cast<const uint4 *>(res + pix * p.Cout + cb);
               float rf[8];
-              unpack8<T>(ru, rf);
+              unpack8<T>(rq[half], rf);
 #pragma unroll
               for (int i = 0; i < 8; ++i) vh[i] += p.res_scale * rf[i];
             }
@@ -413,13 +453,39 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
           for (int i = 0; i < 16; ++i) q[i] = v[i] * v[i];
           const float s_tot = warp_colsum16(v, lane);
           const float q_tot = warp_colsum16(q, lane);
-          const int ch = co + (lane >> 1);
-          if ((lane & 1) == 0 && ch < p.Cout && n_warp < p.N) {
-            double *dst = p.gn_sums + ((size_t)n_warp * p.Cout + ch) * 2;
-            atomicAdd(dst, (double)s_tot);
-            atomicAdd(dst + 1, (double)q_tot);
+          if ((lane & 1) == 0) {
+            const int slot = (c >> 5) * 16 + (lane >> 1);      // chunk (c / 16) is this warp's (c / 32)-th chunk
+            st_sum[slot] += s_tot;
+            st_sq[slot] += q_tot;
           }
         }
+      };
+
+      uint32_t ra[16], rb[16];
+      uint4 qa[2], qb[2];
+      int ci = g;
+      if (ci < nch) {
+        tmem_ld16(taddr + ci * 16, ra);
+        load_res(ci * 16, qa);
+      }
+      while (ci < nch) {
+        tmem_ld_wait_dep(ra);
+        int cn = ci + 2;
+        if (cn < nch) {
+          tmem_ld16(taddr + cn * 16, rb);
+          load_res(cn * 16, qb);
+        }
+        process(ra, qa, ci * 16);
+        ci = cn;
+        if (ci >= nch) break;
+        tmem_ld_wait_dep(rb);
+        cn = ci + 2;
+        if (cn < nch) {
+          tmem_ld16(taddr + cn * 16, ra);
+          load_res(cn * 16, qa);
+        }
+        process(rb, qb, ci * 16);
+        ci = cn;
       }
       tc_fence_before();
       __syncwarp();
@@ -428,6 +494,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
         else mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
       }
     }
+    if (p.gn_sums && acc_n >= 0) flush_stats();
   }
 
   tc_fence_before();
@@ -531,7 +598,7 @@ static int launch_conv(const b200_conv_desc *d, int bn, cudaStream_t stream) {
   p.a_bytes = any_halo ? kABytes + 2 * p.TW * 128 : kABytes;
   const size_t b_bytes = (size_t)(p.BN / kCtas) * 128;
   p.stage_bytes = p.a_bytes + (any_halo ? 3 : 1) * (int)b_bytes;
-  p.stages = (int)std::min<size_t>(kMaxStages, (220 * 1024) / p.stage_bytes);
+  p.stages = (int)std::min<size_t>(kMaxStages, (220 * 1024 - kStatSmem) / p.stage_bytes);
   B200_CHECK(p.stages >= 2, "conv: tile too large for shared memory");
 
   for (int s = 0; s < d->nseg; ++s) {
@@ -558,7 +625,7 @@ static int launch_conv(const b200_conv_desc *d, int bn, cudaStream_t stream) {
       if (int rc = cached_tmap(&maps.b[s], g.weight, 3, dims, str, box, es)) return rc;
     }
   }
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + kStatSmem;
   static bool attr_set = false;     // per (T, kCtas) instantiation
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<T, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -1,22 +1,34 @@
-"""One conv shape, a few launches (ncu --set full target)."""
+"""One conv shape, a few launches (ncu --set full target).
+
+    python tools/conv_one.py N H W Cin Cout [k] [flags: s=fused GN statistics, r=residual, b=timestep row bias]
+"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from diffusion_models_dsdiff_b200 import ops
 n, h, w, ci, co = [int(v) for v in sys.argv[1:6]]
 k = int(sys.argv[6]) if len(sys.argv) > 6 else 3
+flags = sys.argv[7] if len(sys.argv) > 7 else ""
 dev = torch.device("cuda:0")
 x = torch.randn(n, h, w, ci, device=dev).half()
 wt = ops.pack_conv_weight(torch.randn(co, ci, k, k, device=dev) * 0.02, torch.float16)
 b = torch.zeros(co, device=dev)
 out = torch.empty(n, h, w, co, device=dev, dtype=torch.float16)
+kw = {}
+if "s" in flags:
+    kw["stats"] = torch.zeros(n, co, 2, device=dev, dtype=torch.float64)
+if "r" in flags:
+    kw["residual"] = torch.randn(n, h, w, co, device=dev).half()
+if "b" in flags:
+    kw["rowbias"] = torch.randn(n, co, device=dev)
+run = lambda: ops.conv2d([(x, wt, 0, k, k // 2)], bias=b, out=out, **kw)
 for _ in range(6):
-    ops.conv2d([(x, wt, 0, k, k // 2)], bias=b, out=out)
+    run()
 torch.cuda.synchronize()
 a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
 for _ in range(10):
-    ops.conv2d([(x, wt, 0, k, k // 2)], bias=b, out=out)
+    run()
 e.record(); torch.cuda.synchronize()
 ms = a.elapsed_time(e) / 10
-print(f"conv {n}x{h}x{w} {ci}->{co} k{k}: {ms:.4f} ms  {2.0*n*h*w*co*ci*k*k/ms/1e9:.1f} TFLOP/s")
+print(f"conv {n}x{h}x{w} {ci}->{co} k{k} [{flags}]: {ms:.4f} ms  {2.0*n*h*w*co*ci*k*k/ms/1e9:.1f} TFLOP/s")
