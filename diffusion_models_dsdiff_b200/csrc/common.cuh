@@ -240,6 +240,18 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 256-bit global accesses (sm_100: LDG.256 / STG.256): one full 32-byte sector per thread
+__device__ __forceinline__ void ld_global_256(const void *p, uint4 &a, uint4 &b) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void st_global_256(void *p, const uint4 &a, const uint4 &b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 // wait for the outstanding tcgen05.ld and tie the destination registers to the wait, so no use of them can be
 // scheduled above it when loads are issued ahead of their consumer
 __device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[16]) {

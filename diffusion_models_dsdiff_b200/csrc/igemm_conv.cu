@@ -16,7 +16,7 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kMaxStages = 8;
 constexpr int kConvThreads = 320;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
-constexpr int kStatSmem = 8 * 256 * 4;   // per-epilogue-warp GroupNorm column accumulators
+constexpr int kStatSmem = 8 * 256 * 4 + 8 * 128 * 4;   // per-epilogue-warp GroupNorm column accumulators + staged biases
 constexpr int kAccCols = 256;      // TMEM columns per accumulator stage
 constexpr int kTmemCols = 512;     // two accumulator stages
 constexpr int kABytes = kBM * kBK * 2;
@@ -53,6 +53,7 @@ struct ConvKParams {
   float *out_f32;            // NCHW fp32 output of the first cout_real channels (network head) instead of `out`
   int cout_real;
   int debug_skip_epilogue;   // B200DIFF_SKIP_EPI: timing experiments only (results are garbage)
+  int vec32;                 // Cout % 16 == 0 and 32-byte aligned out / residual: 256-bit epilogue loads / stores
 };
 
 // Column sums of a 32 (lanes) x 16 (registers) tile by recursive halving: 16 shuffles instead of 16 x 5.
@@ -329,6 +330,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
     // when the warp moves to another image / N tile (a persistent CTA stays ~7 tiles inside one image).
     float *st_sum = reinterpret_cast<float *>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * stage_bytes) + ew * 256;
     float *st_sq = st_sum + 128;
+    // bias + timestep row bias of this warp's columns, staged per tile BEFORE waiting for the accumulator so the global
+    // load latency hides behind the tile's MMAs (a warp's 32 rows lie in one image when TW*TH >= 32)
+    float *bs = reinterpret_cast<float *>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * stage_bytes) + 8 * 256 + ew * 128;
+    const bool staged_bias = (p.TW * p.TH >= 32) && (p.bias || p.rowbias);
     int acc_n = -1, acc_ntile = 0;
     if (p.gn_sums) {
       for (int i = lane; i < 256; i += 32) st_sum[i] = 0.f;
@@ -370,6 +375,26 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
         acc_n = n_warp;
         acc_ntile = n_tile;
       }
+      if (staged_bias) {
+        __syncwarp();
+        for (int slot = lane; slot < 128; slot += 32) {
+          const int chunk = (slot >> 4) * 2 + g;
+          const int co = n_tile * p.BN + chunk * 16 + (slot & 15);
+          float b = 0.f;
+          if (chunk * 16 < p.BN && co < p.Cout) {
+            if (p.bias) b = __ldg(p.bias + co);
+            if (p.rowbias && n_warp < p.N) b += __ldg(p.rowbias + (size_t)n_warp * p.rowbias_stride + co);
+          }
+          bs[slot] = b;
+        }
+        __syncwarp();
+      }
+      if (res && valid) {
+        // pull this pixel's residual row segment HBM -> L2 while the tile's MMAs are still running
+        const char *rrow = reinterpret_cast<const char *>(res + pix * p.Cout + n_tile * p.BN);
+        const int rbytes = min(p.BN, p.Cout - n_tile * p.BN) * 2;
+        for (int o = g * 128; o < rbytes; o += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + o));
+      }
       mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + acc * kAccCols;
@@ -380,13 +405,18 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
         q[0] = make_uint4(0, 0, 0, 0);
         q[1] = q[0];
         if (res && valid) {
-          if (co < p.Cout) q[0] = *reinterpret_cast<const uint4 *>(res + pix * p.Cout + co);
-          if (co + 8 < p.Cout) q[1] = *reinterpret_cast<const uint4 *>(res + pix * p.Cout + co + 8);
+          if (p.vec32 && co < p.Cout) {
+            ld_global_256(res + pix * p.Cout + co, q[0], q[1]);
+          } else {
+            if (co < p.Cout) q[0] = *reinterpret_cast<const uint4 *>(res + pix * p.Cout + co);
+            if (co + 8 < p.Cout) q[1] = *reinterpret_cast<const uint4 *>(res + pix * p.Cout + co + 8);
+          }
         }
       };
       auto process = [&](const uint32_t (&r)[16], const uint4 (&rq)[2], int c) {
         const int co = n_tile * p.BN + c;
         float v[16];
+        uint4 packed[2];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int cb = co + half * 8;
@@ -395,6 +425,13 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
           for (int i = 0; i < 8; ++i) vh[i] = __uint_as_float(r[half * 8 + i]);
           const bool live = valid && cb < p.Cout;
           if (live) {
+            if (staged_bias) {
+              const float *bp = bs + (c >> 5) * 16 + half * 8;
+              const float4 b0 = *reinterpret_cast<const float4 *>(bp);
+              const float4 b1 = *reinterpret_cast<const float4 *>(bp + 4);
+              vh[0] += b0.x; vh[1] += b0.y; vh[2] += b0.z; vh[3] += b0.w;
+              vh[4] += b1.x; vh[5] += b1.y; vh[6] += b1.z; vh[7] += b1.w;
+            } else {
             if (p.bias) {
               const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + cb));
               const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + cb + 4));
@@ -407,6 +444,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
               const float4 b1 = __ldg(reinterpret_cast<const float4 *>(rb + 4));
               vh[0] += b0.x; vh[1] += b0.y; vh[2] += b0.z; vh[3] += b0.w;
               vh[4] += b1.x; vh[5] += b1.y; vh[6] += b1.z; vh[7] += b1.w;
+            }
             }
             if (p.epi_act == 1) {
 #pragma unroll
@@ -437,6 +475,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
               for (int i = 0; i < 8; ++i)
                 if (cb + i < p.cout_real)
                   p.out_f32[(((size_t)n * p.cout_real + cb + i) * p.Hout + h) * p.Wout + w] = vh[i];
+            } else if (p.vec32) {
+              packed[half] = pack8<T>(vh);
             } else {
               *reinterpret_cast<uint4 *>(out + pix * p.Cout + cb) = pack8<T>(vh);
             }
@@ -445,6 +485,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
             for (int i = 0; i < 8; ++i) vh[i] = 0.f;
           }
         }
+        // one 32-byte store per thread = a whole sector (Cout % 16 == 0: a chunk is entirely inside or outside Cout)
+        if (p.vec32 && valid && co < p.Cout && !p.out_f32_nhwc && !p.out_f32)
+          st_global_256(out + pix * p.Cout + co, packed[0], packed[1]);
         if (p.gn_sums) {
           // per-channel (sum, sum of squares) over this warp's 32 pixels for a following GroupNorm; the 32 rows of a
           // warp lie in ONE image (the host enables the fused statistics only when TW*TH >= 32)
@@ -586,6 +629,7 @@ static int launch_conv(const b200_conv_desc *d, int bn, cudaStream_t stream) {
   p.gn_sums = (p.TW * p.TH >= 32) ? d->gn_sums : nullptr;
   p.idesc = umma_idesc(Act<T>::kFmt, kBM * kCtas, p.BN);
   p.debug_skip_epilogue = getenv("B200DIFF_SKIP_EPI") != nullptr;
+  p.vec32 = d->Cout % 16 == 0 && (((uintptr_t)d->out | (uintptr_t)d->residual) & 31) == 0 && !getenv("B200DIFF_NO_VEC32");
   p.out_f32 = d->out_nchw_f32; p.cout_real = d->cout_real; p.out_f32_nhwc = d->out_nhwc_f32;
   p.rowscale = d->rowscale; p.rowscale_stride = d->rowscale_stride; p.epi_act = d->epi_act;
   // halo staging: 3x3 stride-1 pad-1 segments whose 128-pixel box lies in one image and is >= 8 pixels wide
