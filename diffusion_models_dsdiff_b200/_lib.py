@@ -63,7 +63,7 @@ SIGNATURES = {
     "b200_nhwc_to_nchw_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_pack_conv_weight": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_conv2d_igemm": [C.POINTER(ConvDesc), _P],
-    "b200_conv3x3_in": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "b200_conv3x3_in": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P],
     "b200_conv3x3_out": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_groupnorm_stats": [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P],
     "b200_groupnorm_apply": [_P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _I, _I, _P, _I, _P],

@@ -240,6 +240,35 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Per-(image, channel) statistics epilogue of the HBM-bound producers: the `rows` threads of a block that own the same
+// 8-channel column are reduced through shared memory, then ONE fp64 atomic pair per channel per block goes to the global
+// sums (thread layout: threadIdx.x = row * ncol + col, 256 threads).  Must be called by every thread of the block.
+__device__ __forceinline__ void block_flush_col_sums(const float (&s)[8], const float (&q)[8], bool active, int row, int col,
+                                                     int ncol, int rows, double *dst /* sums + (n*C + col*8)*2 */) {
+  __shared__ float red[256 * 16];
+  if (active) {
+    float *r = red + (row * ncol + col) * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { r[i] = s[i]; r[8 + i] = q[i]; }
+  }
+  __syncthreads();
+  if (active && row == 0) {
+    float ts[8], tq[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ts[i] = s[i]; tq[i] = q[i]; }
+    for (int rr = 1; rr < rows; ++rr) {
+      const float *r = red + (rr * ncol + col) * 16;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { ts[i] += r[i]; tq[i] += r[8 + i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(dst + 2 * i, (double)ts[i]);
+      atomicAdd(dst + 2 * i + 1, (double)tq[i]);
+    }
+  }
+}
+
 // 256-bit global accesses (sm_100: LDG.256 / STG.256): one full 32-byte sector per thread
 __device__ __forceinline__ void ld_global_256(const void *p, uint4 &a, uint4 &b) {
   asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"

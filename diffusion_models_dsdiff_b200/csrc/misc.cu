@@ -51,56 +51,83 @@ __global__ void pack_weight_kernel(const float *__restrict__ w, T *__restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// first conv: NCHW fp32 (Cin <= 8) -> NHWC act.  One thread per output pixel, weights in smem as
-// [Cin*9][Cout] so each 8-cout chunk is two broadcast LDS.128.
+// first conv: NCHW fp32 (Cin <= 8) -> NHWC act.  Thread (row, col) of a 256-thread block owns the 8-channel column
+// `col` of pixel `row` (+ k*rows): lanes of a warp write CONSECUTIVE 16-byte chunks of one pixel's channel row (fully
+// coalesced 512-byte stores; the 9*Cin input taps are warp-broadcast loads), weights sit in shared memory as
+// [Cin*9][Cout].  The per-(image, channel) sums for the following GroupNorm are accumulated on the fly.
 // ------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(128)
+template <typename T, bool kRegW>
+__global__ void __launch_bounds__(256)
 conv3x3_in_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
-                  T *__restrict__ out, int N, int Cin, int H, int W, int Cout) {
-  extern __shared__ float sw[];  // [Cin*9][Cout] then bias[Cout]
+                  T *__restrict__ out, int Cin, int H, int W, int Cout, int pix_per_block, double *__restrict__ sums) {
+  extern __shared__ float sw[];  // kRegW ? unused : [Cin*9][Cout]
   const int K = Cin * 9;
-  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
-    const int co = i % Cout, k = i / Cout;   // k = ci*9 + tap
-    sw[i] = w[(size_t)co * K + k];
-  }
-  float *sb = sw + K * Cout;
-  for (int i = threadIdx.x; i < Cout; i += blockDim.x) sb[i] = bias ? bias[i] : 0.f;
-  __syncthreads();
-  const long long total = (long long)N * H * W;
-  const long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (pix >= total) return;
-  const int wq = (int)(pix % W);
-  const int hq = (int)((pix / W) % H);
-  const int n = (int)(pix / ((long long)W * H));
-  float in[72];
-#pragma unroll
-  for (int ci = 0; ci < 8; ++ci) {
-    if (ci < Cin) {
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const int hh = hq + r - 1, ww = wq + s - 1;
-          in[ci * 9 + r * 3 + s] = (hh >= 0 && hh < H && ww >= 0 && ww < W)
-                                       ? __ldg(x + (((size_t)n * Cin + ci) * H + hh) * W + ww)
-                                       : 0.f;
-        }
+  if (!kRegW) {
+    for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+      const int co = i % Cout, k = i / Cout;   // k = ci*9 + tap
+      sw[i] = w[(size_t)co * K + k];
     }
+    __syncthreads();
   }
-  T *o = out + (size_t)pix * Cout;
-  for (int c0 = 0; c0 < Cout; c0 += 8) {
+  const int n = blockIdx.y;
+  const int HW = H * W;
+  const int ncol = Cout >> 3;
+  const int rows = 256 / ncol;
+  const int col = threadIdx.x % ncol;
+  const int row = threadIdx.x / ncol;
+  const bool active = row < rows;
+  const int c0 = col * 8;
+  // each thread walks a RUN of consecutive pixels, so the 3x3 input window slides (3 new loads per pixel)
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_stop = min(HW, p_begin + pix_per_block);
+  const int run = (p_stop - p_begin + rows - 1) / rows;
+  const int p0 = p_begin + row * run;
+  const int p1 = active ? min(p_stop, p0 + run) : 0;
+  float bv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bv[i] = bias ? bias[c0 + i] : 0.f;
+  float wr[kRegW ? 72 : 1];     // Cin == 1: this thread's 9 taps x 8 output channels stay in registers
+  if (kRegW) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) wr[t * 8 + i] = w[(size_t)(c0 + i) * 9 + t];
+  }
+  float s[8] = {0}, q[8] = {0};
+  const float *xn = x + (size_t)n * Cin * HW;
+  T *on = out + (size_t)n * HW * Cout + c0;
+  float win[9];
+  bool fresh = true;
+  for (int p = p0; p < p1; ++p) {
+    const int hq = p / W, wq = p - hq * W;
     float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = sb[c0 + i];
+    for (int i = 0; i < 8; ++i) acc[i] = bv[i];
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float *xc = xn + (size_t)ci * HW;
+      auto tap = [&](int r, int t) {
+        const int hh = hq + r - 1, ww = wq + t - 1;
+        return (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xc + hh * W + ww) : 0.f;
+      };
+      if (kRegW && !fresh && wq != 0) {
 #pragma unroll
-    for (int ci = 0; ci < 8; ++ci) {
-      if (ci < Cin) {
+        for (int r = 0; r < 3; ++r) { win[r * 3] = win[r * 3 + 1]; win[r * 3 + 1] = win[r * 3 + 2]; win[r * 3 + 2] = tap(r, 2); }
+      } else {
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const float v = in[ci * 9 + t];
-          const float4 w0 = *reinterpret_cast<const float4 *>(sw + (ci * 9 + t) * Cout + c0);
-          const float4 w1 = *reinterpret_cast<const float4 *>(sw + (ci * 9 + t) * Cout + c0 + 4);
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int t = 0; t < 3; ++t) win[r * 3 + t] = tap(r, t);
+      }
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float v = win[t];
+        if (kRegW) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] = fmaf(v, wr[t * 8 + i], acc[i]);
+        } else {
+          const float *wp = sw + (ci * 9 + t) * Cout + c0;
+          const float4 w0 = *reinterpret_cast<const float4 *>(wp);
+          const float4 w1 = *reinterpret_cast<const float4 *>(wp + 4);
           acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
           acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
           acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
@@ -108,8 +135,16 @@ conv3x3_in_kernel(const float *__restrict__ x, const float *__restrict__ w, cons
         }
       }
     }
-    *reinterpret_cast<uint4 *>(o + c0) = pack8<T>(acc);
+    fresh = false;
+    const uint4 u = pack8<T>(acc);
+    st_stream(on + (size_t)p * Cout, u);
+    if (sums) {
+      unpack8<T>(u, acc);              // statistics of the stored (rounded) values
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += acc[i]; q[i] += acc[i] * acc[i]; }
+    }
   }
+  if (sums) block_flush_col_sums(s, q, active, row, col, ncol, rows, sums + ((size_t)n * Cout + c0) * 2);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -418,18 +453,25 @@ extern "C" int b200_pack_conv_weight(const float *w, void *dst, int Cout, int Ci
 }
 
 extern "C" int b200_conv3x3_in(const float *x, const float *w, const float *bias, void *out, int N, int Cin,
-                               int H, int W, int Cout, int act_dtype, void *stream) {
+                               int H, int W, int Cout, double *sums, int act_dtype, void *stream) {
   B200_CHECK(x && w && out, "conv3x3_in: null pointer");
   B200_CHECK(Cin >= 1 && Cin <= 8, "conv3x3_in: Cin must be 1..8 (got %d)", Cin);
-  B200_CHECK(Cout % 8 == 0 && Cout > 0, "conv3x3_in: Cout must be a multiple of 8");
+  B200_CHECK(Cout % 8 == 0 && Cout > 0 && Cout <= 2048, "conv3x3_in: Cout must be a multiple of 8, <= 2048");
   const size_t smem = ((size_t)Cin * 9 * Cout + Cout) * sizeof(float);
   B200_CHECK(smem <= 200 * 1024, "conv3x3_in: weights do not fit shared memory");
-  const long long total = (long long)N * H * W;
+  const int HW = H * W;
+  const int rows = std::max(1, 256 / (Cout >> 3));
+  int bps = std::max(1, std::min((num_sms() * 4) / std::max(N, 1), HW / (rows * 4)));
+  const int ppb = cdiv(HW, bps);
+  const dim3 grid(cdiv(HW, ppb), N, 1);
   DISPATCH_ACT(act_dtype, {
-    if (smem > 48 * 1024)
-      B200_CUDA(cudaFuncSetAttribute(conv3x3_in_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv3x3_in_kernel<T><<<(unsigned)cdiv64(total, 128), 128, smem, (cudaStream_t)stream>>>(
-        x, w, bias, (T *)out, N, Cin, H, W, Cout);
+    if (Cin == 1) {
+      conv3x3_in_kernel<T, true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, (T *)out, Cin, H, W, Cout, ppb, sums);
+    } else {
+      if (smem > 48 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(conv3x3_in_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conv3x3_in_kernel<T, false><<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, bias, (T *)out, Cin, H, W, Cout, ppb, sums);
+    }
   })
   B200_LAUNCH_CHECK();
   return 0;

@@ -93,9 +93,9 @@ channel_stats_kernel(const T *__restrict__ x, int C, int HW, int pix_per_block, 
   const int rows = kNormThreads / ncol;
   const int col = threadIdx.x % ncol;
   const int row = threadIdx.x / ncol;
-  if (row >= rows) return;
+  const bool active = row < rows;
   const int p_begin = blockIdx.x * pix_per_block;
-  const int p_end = min(HW, p_begin + pix_per_block);
+  const int p_end = active ? min(HW, p_begin + pix_per_block) : 0;
   float s[8] = {0}, q[8] = {0};
   const T *base = x + (size_t)n * HW * C + col * 8;
   int p = p_begin + row;
@@ -117,12 +117,7 @@ channel_stats_kernel(const T *__restrict__ x, int C, int HW, int pix_per_block, 
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
   }
-  double *dst = sums + ((size_t)n * C + col * 8) * 2;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    atomicAdd(dst + 2 * i, (double)s[i]);
-    atomicAdd(dst + 2 * i + 1, (double)q[i]);
-  }
+  block_flush_col_sums(s, q, active, row, col, ncol, rows, sums + ((size_t)n * C + col * 8) * 2);
 }
 
 // dst = scale * (a + b + c + d) with the per-(image, channel) statistics of dst accumulated on the fly (DS-Diff skip mean,
@@ -136,9 +131,9 @@ add4_stats_kernel(const T *__restrict__ a, const T *__restrict__ b, const T *__r
   const int rows = kNormThreads / ncol;
   const int col = threadIdx.x % ncol;
   const int row = threadIdx.x / ncol;
-  if (row >= rows) return;
+  const bool active = row < rows;
   const int p_begin = blockIdx.x * pix_per_block;
-  const int p_end = min(HW, p_begin + pix_per_block);
+  const int p_end = active ? min(HW, p_begin + pix_per_block) : 0;
   float s[8] = {0}, q[8] = {0};
   const size_t base = (size_t)n * HW * C + col * 8;
   const int nin = 1 + (b != nullptr) + (c != nullptr) + (d != nullptr);
@@ -185,12 +180,7 @@ add4_stats_kernel(const T *__restrict__ a, const T *__restrict__ b, const T *__r
       }
     finish(f, off);
   }
-  double *o = sums + ((size_t)n * C + col * 8) * 2;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    atomicAdd(o + 2 * i, (double)s[i]);
-    atomicAdd(o + 2 * i + 1, (double)q[i]);
-  }
+  block_flush_col_sums(s, q, active, row, col, ncol, rows, sums + ((size_t)n * C + col * 8) * 2);
 }
 
 // y = silu?( (x - mean_g) * rstd_g * gamma_c + beta_c ) [ * (1 + scale_nc) + shift_nc ]
@@ -206,23 +196,37 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
   const int C = C0 + C1;
   const int cpg = C / groups;
   const double cnt = (double)HW * (double)cpg;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    double sum, sq;
-    if (stats) {
-      sum = stats[((size_t)n * groups + g) * 2 + 0];
-      sq = stats[((size_t)n * groups + g) * 2 + 1];
-    } else {   // per-channel sums written by the producers' epilogues (conv / add4 / channel_stats)
-      sum = 0.0; sq = 0.0;
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        const double *src = c < C0 ? cs0 + ((size_t)n * C0 + c) * 2 : cs1 + ((size_t)n * C1 + (c - C0)) * 2;
-        sum += src[0]; sq += src[1];
+  // group statistics: tpg threads per group sum the producers' per-channel fp64 sums, then a shuffle tree (the serial
+  // 30..60-channel loop of one thread per group was the launch floor of the small-map GroupNorms)
+  int tpg = 1;
+  while (tpg * 2 * groups <= kNormThreads && tpg < 32) tpg *= 2;
+  {
+    const int g = threadIdx.x / tpg, sub = threadIdx.x % tpg;
+    double sum = 0.0, sq = 0.0;
+    if (g < groups) {
+      if (stats) {
+        if (sub == 0) {
+          sum = stats[((size_t)n * groups + g) * 2 + 0];
+          sq = stats[((size_t)n * groups + g) * 2 + 1];
+        }
+      } else {   // per-channel sums written by the producers' epilogues (conv / add4 / channel_stats)
+        for (int c = g * cpg + sub; c < (g + 1) * cpg; c += tpg) {
+          const double *src = c < C0 ? cs0 + ((size_t)n * C0 + c) * 2 : cs1 + ((size_t)n * C1 + (c - C0)) * 2;
+          sum += src[0]; sq += src[1];
+        }
       }
     }
-    const double m = sum / cnt;
-    double var = sq / cnt - m * m;
-    if (var < 0.0) var = 0.0;
-    s_mean[g] = (float)m;
-    s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    for (int o = tpg >> 1; o > 0; o >>= 1) {      // tpg divides 32: the tree stays inside one warp
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (g < groups && sub == 0) {
+      const double m = sum / cnt;
+      double var = sq / cnt - m * m;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = (float)m;
+      s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
   }
   __syncthreads();
   const int ncol = C >> 3;

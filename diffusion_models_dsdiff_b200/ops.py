@@ -209,14 +209,15 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
     return out
 
 
-def conv3x3_in(x_nchw: Tensor, w_oihw: Tensor, bias: Optional[Tensor], dtype=torch.float16) -> Tensor:
+def conv3x3_in(x_nchw: Tensor, w_oihw: Tensor, bias: Optional[Tensor], dtype=torch.float16,
+               stats: Optional[Tensor] = None) -> Tensor:
     _dev(x_nchw)
     n, ci, h, w = x_nchw.shape
     co = w_oihw.shape[0]
     out = torch.empty((n, h, w, co), device=x_nchw.device, dtype=dtype)
     _timed("conv3x3_in", 2.0 * n * h * w * co * ci * 9, 4.0 * x_nchw.numel() + 2.0 * out.numel(),
            lambda: L.check(L.lib().b200_conv3x3_in(_p(_f32(x_nchw)), _p(_f32(w_oihw)), _p(_f32(bias)), _p(out), n, ci,
-                                                   h, w, co, act_code(dtype), _stream()), "conv3x3_in"))
+                                                   h, w, co, _p(stats), act_code(dtype), _stream()), "conv3x3_in"))
     return out
 
 

@@ -107,9 +107,10 @@ int b200_conv2d_igemm(const b200_conv_desc *d, void *stream);
 
 /* first conv of the network: tiny Cin (<= 8) read straight from NCHW fp32, writes NHWC act.
  * replaces input_blocks[0] conv (openaimodel.py:717) after DiffusionWrapper's concat
- * (ldm/models/diffusion/ddpm.py:1331-1333).  w is OIHW fp32.                                  */
+ * (ldm/models/diffusion/ddpm.py:1331-1333).  w is OIHW fp32.  sums (may be NULL): zeroed fp64 [N, Cout, 2], receives
+ * the per-(image, channel) sum / sum of squares of the stored output for the following GroupNorm.     */
 int b200_conv3x3_in(const float *x_nchw, const float *w_oihw, const float *bias, void *out_nhwc,
-                    int N, int Cin, int H, int W, int Cout, int act_dtype, void *stream);
+                    int N, int Cin, int H, int W, int Cout, double *sums, int act_dtype, void *stream);
 /* last conv: Cout <= 4, NHWC act -> NCHW fp32.  replaces self.out[2] (openaimodel.py:898-902). */
 int b200_conv3x3_out(const void *x_nhwc, const float *w_oihw, const float *bias, float *out_nchw,
                      int N, int Cin, int H, int W, int Cout, int act_dtype, void *stream);

@@ -209,3 +209,26 @@ def test_dpm_solver_pp_thresholding_logsnr_oracle_matches_reference():
     for i in range(g["S"]):
         assert maxabs(rec[i]["x"], g["x_inter"][i]) < 2e-4, i
     assert maxabs(out, g["final"]) < 2e-4
+
+
+# -------------------------------------------------------------------------------------------------
+# Where north_star's "per-step eps within 1e-3 relative" sits: the reference itself runs its convolutions / matmuls in
+# TF32 on the GPU (inference/inference_2d_main.py:17 + cuDNN default), i.e. with 10-bit-mantissa operands.  Evaluated with
+# the oracle (everything else exact fp32), that operand rounding ALONE moves the output by ~1e-3 relative — the same as
+# the fp16 operands of the B200 path.  The GPU parity tests therefore assert 2e-3 against the pure-fp32 reference.
+# -------------------------------------------------------------------------------------------------
+def _tf32(v):
+    i = v.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("case", ["unet_small", "ds_small"])
+def test_ten_bit_mantissa_operand_floor(case):
+    hp, sd = synth_sd(case)
+    g = golden(case)
+    run = (lambda q: O.unet_forward(sd, hp, g["x"], g["t"], opq=q)) if case == "unet_small" else \
+        (lambda q: O.dsunet_forward(sd, hp, g["x"], g["t"], opq=q)[0])
+    tf32 = O.rel_err(run(_tf32), g["y"])
+    fp16 = O.rel_err(run(lambda v: v.half().float()), g["y"])
+    assert 0.7e-3 < tf32 < 2e-3 and 0.7e-3 < fp16 < 2e-3      # measured: 0.98e-3 / 0.93e-3 (UNet), 1.24e-3 / 1.27e-3 (DS-Diff)
+    assert abs(tf32 - fp16) < 0.3 * tf32                      # same mantissa width -> same floor

@@ -1,8 +1,5 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-python bench.py --no-cpu-baseline > gpurun_out/bench10.json 2>/dev/null
-python - <<PY
-import json
-d=json.load(open("gpurun_out/bench10.json"))
-print(d["value"], d["e2e"]["value"], d["clocks"], d["roofline"]["achieved"], d["kernel_pass_ms_per_denoise_step"])
-for a in d["roofline_aux"][:6]: print(a["kernel"], round(a["achieved"]), round(a["ms_per_denoise_step"],2))
-PY
+for f in "" s; do python tools/conv_one.py 8 256 256 8 320 3 "$f"; done
+B200DIFF_SKIP_EPI=1 python tools/conv_one.py 8 256 256 8 320 3 ""
+B200DIFF_NO_VEC32=1 python tools/conv_one.py 8 256 256 8 320 3 ""
+python tools/conv_one.py 8 256 256 8 256 3 ""
+python tools/conv_one.py 8 256 256 8 64 3 ""
