@@ -62,3 +62,49 @@ def gather_slices(local: Tensor, n_total: int, group: Optional[dist.ProcessGroup
         rb, re = shard_range(n_total, r, world)
         parts.append(bufs[r][: re - rb])
     return torch.cat(parts, dim=0)
+
+
+def pad_to_multiple(x: Tensor, multiple: int = 32) -> Tuple[Tensor, Tuple[int, int, int, int]]:
+    """Zero-pad the last two dims symmetrically up to a multiple of ``multiple`` (what MONAI's ``DivisiblePadd(k=32)``
+    does in the reference's train / val transforms, training_transform.py:261,404; the TEST transform leaves BraTS
+    slices at 240x240, which a 6-level UNet cannot take — SURVEY §8 gotcha 8).  Returns (padded, (top, bottom, left,
+    right)) for ``crop_pad``."""
+    h, w = x.shape[-2], x.shape[-1]
+    ph, pw = (-h) % multiple, (-w) % multiple
+    pads = (ph // 2, ph - ph // 2, pw // 2, pw - pw // 2)
+    if ph == 0 and pw == 0:
+        return x, pads
+    return torch.nn.functional.pad(x, (pads[2], pads[3], pads[0], pads[1])), pads
+
+
+def crop_pad(x: Tensor, pads: Tuple[int, int, int, int]) -> Tensor:
+    t, b, l, r = pads
+    return x[..., t:x.shape[-2] - b, l:x.shape[-1] - r]
+
+
+def sample_volume(sample_fn, cond: Tensor, out_channels: int = 1, batch_size: int = 8, base_seed: int = 2024,
+                  multiple: int = 32, device=None, group: Optional[dist.ProcessGroup] = None) -> Optional[Tensor]:
+    """Sample every 2D slice of one volume, sharded over the ranks of ``group`` (a 155-slice BraTS
+    volume over 8 GPUs), and return the assembled ``[n_slices, out_channels, H, W]`` stack on rank 0 (None elsewhere) —
+    the tensor ``on_predict_end`` turns into a NIfTI volume (trainers/trainer_ds_diff.py:854-875).
+
+    ``cond``      [n_slices, C, H, W] conditioning slices of the volume (any device);
+    ``sample_fn`` (cond_batch [b, C, H', W'], x_T [b, out_channels, H', W']) -> samples [b, out_channels, H', W'], e.g.
+                  ``lambda c, x: DDIMSampler(model).sample(50, len(c), x.shape[1:], c, x_T=x, verbose=False)[0]``.
+    Slices are padded to a multiple of ``multiple`` and cropped back; x_T of slice i comes from its own generator
+    (``slice_noise``), so the result does not depend on the world size or on ``batch_size``.  No collective runs inside
+    the sampling loop; the only communication is the final gather."""
+    n_total = cond.shape[0]
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    device = device if device is not None else cond.device
+    b, e = shard_range(n_total, rank, world)
+    outs = []
+    for s in range(b, e, batch_size):
+        ids = list(range(s, min(e, s + batch_size)))
+        c, pads = pad_to_multiple(cond[ids[0]:ids[-1] + 1].to(device).float(), multiple)
+        x_T = slice_noise(ids, (out_channels, c.shape[-2], c.shape[-1]), base_seed, device)
+        outs.append(crop_pad(sample_fn(c.contiguous(), x_T), pads))
+    shape = (0, out_channels, cond.shape[-2], cond.shape[-1])
+    local = torch.cat(outs, 0) if outs else torch.empty(shape, dtype=torch.float32, device=device)
+    return gather_slices(local.contiguous(), n_total, group)

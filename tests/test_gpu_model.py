@@ -352,3 +352,20 @@ def test_full_size_network_forward_vs_oracle(workload):
     assert ref.abs().max() > 1e-3
     rel = O.rel_err(got, ref)
     assert rel < REL_TOL[torch.float16], f"{workload} full-size rel err {rel:.3e}"
+
+
+def test_sample_volume_batch_split_independent_on_gpu():
+    """cfg4-style driver: a volume of ragged-size slices is padded, sampled in batches and cropped; per-slice x_T and
+    batch-independent kernels make the assembled volume bit-identical for any batch split (hence any world size)."""
+    from diffusion_models_dsdiff_b200 import parallel as PAR
+    S, m = _ldm("v")
+    gen = torch.Generator().manual_seed(9)
+    cond = (torch.randn(5, 3, 24, 24, generator=gen) * 0.5).clamp_(-1, 1)      # 24 -> padded to 32 like 240 -> 256
+
+    def sampler(c, x_T):
+        return S.DDIMSampler(m).sample(3, c.shape[0], tuple(x_T.shape[1:]), c, eta=0.0, x_T=x_T, verbose=False)[0]
+
+    a = PAR.sample_volume(sampler, cond, batch_size=5, base_seed=11, device=torch.device("cuda"))
+    b = PAR.sample_volume(sampler, cond, batch_size=2, base_seed=11, device=torch.device("cuda"))
+    assert a.shape == (5, 1, 24, 24) and torch.isfinite(a).all()
+    assert torch.equal(a, b)

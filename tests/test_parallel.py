@@ -78,3 +78,39 @@ def test_gather_slices_single_process_identity():
     assert PAR.gather_slices(x, 5) is x
     with pytest.raises(ValueError):
         PAR.gather_slices(x, 6)
+
+
+def test_pad_to_multiple_roundtrip():
+    x = torch.randn(3, 2, 240, 240)
+    p, pads = PAR.pad_to_multiple(x, 32)
+    assert p.shape[-2:] == (256, 256) and pads == (8, 8, 8, 8)
+    assert torch.equal(PAR.crop_pad(p, pads), x) and float(p[..., :8, :].abs().max()) == 0.0
+    y = torch.randn(1, 1, 64, 96)
+    assert PAR.pad_to_multiple(y, 32)[0] is y
+
+
+def _fake_sampler(c, x_T):
+    """Deterministic per-slice stand-in for a sampler (no cross-slice op, like the real network)."""
+    return x_T * 0.25 + c[:, :1] * 2.0
+
+
+def _volume_worker(rank, world, port, out_path):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cond = torch.arange(13 * 3 * 24 * 24, dtype=torch.float32).reshape(13, 3, 24, 24) / 1e4
+        full = PAR.sample_volume(_fake_sampler, cond, batch_size=3, base_seed=7, multiple=32)
+        if rank == 0:
+            torch.save(full, out_path)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sample_volume_is_independent_of_world_size_and_batch(world, tmp_path):
+    out = str(tmp_path / "vol.pt")
+    mp.spawn(_volume_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    cond = torch.arange(13 * 3 * 24 * 24, dtype=torch.float32).reshape(13, 3, 24, 24) / 1e4
+    single = PAR.sample_volume(_fake_sampler, cond, batch_size=13, base_seed=7, multiple=32)
+    assert single.shape == (13, 1, 24, 24)
+    assert torch.equal(torch.load(out), single)
