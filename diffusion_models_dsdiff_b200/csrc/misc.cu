@@ -468,7 +468,7 @@ extern "C" int b200_conv3x3_in(const float *x, const float *w, const float *bias
     if (Cin == 1) {
       conv3x3_in_kernel<T, true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, (T *)out, Cin, H, W, Cout, ppb, sums);
     } else {
-      if (smem > 48 * 1024)
+      if (smem + 16 * 1024 > 48 * 1024)     // + the static reduction buffer of block_flush_col_sums
         B200_CUDA(cudaFuncSetAttribute(conv3x3_in_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       conv3x3_in_kernel<T, false><<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, bias, (T *)out, Cin, H, W, Cout, ppb, sums);
     }

@@ -232,10 +232,10 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
   const int ncol = C >> 3;
   const int p_begin = blockIdx.x * pix_per_block;
   const int p_end = min(HW, p_begin + pix_per_block);
-  const int rows = kNormThreads / ncol;   // ncol <= 256 (checked on the host)
-  const int col = threadIdx.x % ncol;
-  const int row = threadIdx.x / ncol;
-  if (row < rows) {
+  const int cpp = min(ncol, kNormThreads);   // 8-channel columns per pass (more than 2048 channels: several passes)
+  const int rows = kNormThreads / cpp;
+  const int row = threadIdx.x / cpp;
+  for (int col = threadIdx.x % cpp; col < ncol && row < rows; col += cpp) {
     const int c = col * 8;
     float a[8], b[8];
 #pragma unroll
@@ -314,7 +314,7 @@ static int gn_apply(const void *x0, int C0, const void *x1, int C1, int N, int H
                     const float *beta, const float *film, int film_stride, int silu, void *out, cudaStream_t st) {
   dim3 grid;
   int ppb;
-  norm_grid(N, HW, (C0 + C1) >> 3, &grid, &ppb);
+  norm_grid(N, HW, std::min((C0 + C1) >> 3, kNormThreads), &grid, &ppb);
   gn_apply_kernel<T><<<grid, kNormThreads, 0, st>>>((const T *)x0, C0, (const T *)x1, C1, HW, groups,
                                                    eps, ppb, stats, cs0, cs1, gamma, beta, film, film_stride,
                                                    silu, (T *)out);
@@ -326,7 +326,7 @@ static int check_gn(int C0, int C1, int N, int HW, int groups) {
   B200_CHECK(C0 > 0 && C0 % 8 == 0 && C1 % 8 == 0 && C1 >= 0, "groupnorm: channels must be multiples of 8");
   B200_CHECK(groups > 0 && groups <= kMaxGroups && (C0 + C1) % groups == 0, "groupnorm: bad group count");
   B200_CHECK(N > 0 && HW > 0, "groupnorm: empty tensor");
-  B200_CHECK(C0 + C1 <= 8 * kNormThreads, "groupnorm: at most %d channels", 8 * kNormThreads);
+  B200_CHECK(C0 + C1 <= 64 * kNormThreads, "groupnorm: at most %d channels", 64 * kNormThreads);
   return 0;
 }
 

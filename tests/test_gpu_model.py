@@ -322,7 +322,7 @@ def test_metric_parity_on_256x256_slices():
 # BASELINE.json's configurations at FULL size: one network evaluation of one 256x256 slice vs the oracle
 # (size-independent checks — determinism, batch independence — are in the tests above and hold for any size)
 # -------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("workload", ["cfg1", "cfg2"])
+@pytest.mark.parametrize("workload", ["cfg1", "cfg2", "cfg2p"])
 def test_full_size_network_forward_vs_oracle(workload):
     import os, sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

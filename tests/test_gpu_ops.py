@@ -168,6 +168,20 @@ def test_groupnorm_concat_and_film(dt):
     close(nchw(y), ref, dt, "gn film")
 
 
+def test_groupnorm_wide_concat_2560_channels():
+    """SD-v1's decoder normalises cat([h, skip]) with 1280 + 1280 channels (> 2048: several column passes), statistics from
+    the producers' per-channel sums."""
+    ops = _ops()
+    dt = torch.float16
+    n, c0, c1, h, w = 2, 1280, 1280, 8, 8
+    x0, x1 = q(rnd(1, n, c0, h, w), dt), q(rnd(2, n, c1, h, w) * 2 + 1, dt)
+    g, b = 1 + 0.1 * rnd(3, c0 + c1), 0.1 * rnd(4, c0 + c1)
+    ref = F.silu(F.group_norm(torch.cat([x0, x1], 1), 32, g, b, 1e-5))
+    a0, a1 = nhwc(x0, dt), nhwc(x1, dt)
+    y = ops.group_norm(a0, g.cuda(), b.cuda(), a1, silu=True, cs0=ops.channel_stats(a0), cs1=ops.channel_stats(a1))
+    close(nchw(y), ref, dt, "gn 2560-channel concat")
+
+
 @pytest.mark.parametrize("dt", DTYPES)
 @pytest.mark.parametrize("case", [(1, 32, 32, 64, 96, 1), (2, 40, 24, 32, 320, 1), (3, 8, 8, 64, 64, 1), (2, 32, 32, 64, 64, 2)])
 def test_conv_fused_channel_stats_and_single_pass_groupnorm(case, dt):

@@ -1,2 +1,2 @@
-ncu --set full --clock-control none --import-source on -k regex:conv_igemm -s 8 -c 1 -o gpurun_out/conv_epi python tools/conv_one.py 8 256 256 8 320 3 s > gpurun_out/ncu10.log 2>&1
-tail -1 gpurun_out/ncu10.log
+python -m pytest tests/test_gpu_ops.py -m gpu -x -q 2>&1 | tail -2
+python tools/step_breakdown.py cfg3 8 > gpurun_out/breakdown_cfg3.txt 2>&1; head -24 gpurun_out/breakdown_cfg3.txt
