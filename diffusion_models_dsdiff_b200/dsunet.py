@@ -145,18 +145,46 @@ class DSUnetModel(_EngineModule):
         h_n = run_sequential(cx, self.middle_block, last[0], None)     # :688
         h_a, h_al, h_l = last[1], last[2], last[3]
         fd = lambda m, v: self._fd(cx, m, v)
-        h_n_style, h_n_content = fd(self.conv_style, h_n), fd(self.conv_content, h_n)
         if fork:
+            # the four feature families (3 + 3 + 2 + 2 FeatureDisentangle heads on 8x8 maps, then mean -> SE -> conv) are
+            # independent chains of latency-bound kernels: one family per stream, joined before the 5-way concat
             for ev in joins:
                 main.wait_event(ev)
-        style = [fd(self.conv_style, v) for v in (h_a, h_al, h_l)]
-        content = [fd(self.conv_content, v) for v in (h_a, h_al, h_l)]
-        anatomy = [fd(self.conv_anatomy, v) for v in (h_a, h_al)]
-        lesion = [fd(self.conv_lesion, v) for v in (h_al, h_l)]
-        h_style = self._proj(cx, self.style_proj, style)
-        h_share = self._proj(cx, self.share_content_proj, content)
-        h_anat = self._proj(cx, self.anatomy_proj, anatomy)
-        h_les = self._proj(cx, self.lesion_proj, lesion)
+            ev1 = torch.cuda.Event()
+            ev1.record(main)
+            fam = {}
+
+            def family(name, head, proj, srcs):
+                feats = [fd(head, v) for v in srcs]
+                fam[name] = (feats, self._proj(cx, proj, feats))
+
+            work = [("content", self.conv_content, self.share_content_proj, (h_a, h_al, h_l)),
+                    ("anatomy", self.conv_anatomy, self.anatomy_proj, (h_a, h_al)),
+                    ("lesion", self.conv_lesion, self.lesion_proj, (h_al, h_l))]
+            joins2 = []
+            for st, args in zip(side, work):
+                with torch.cuda.stream(st):
+                    st.wait_event(ev1)
+                    family(*args)
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    joins2.append(ev)
+            family("style", self.conv_style, self.style_proj, (h_a, h_al, h_l))
+            h_n_style, h_n_content = fd(self.conv_style, h_n), fd(self.conv_content, h_n)
+            for ev in joins2:
+                main.wait_event(ev)
+            (style, h_style), (content, h_share) = fam["style"], fam["content"]
+            (anatomy, h_anat), (lesion, h_les) = fam["anatomy"], fam["lesion"]
+        else:
+            h_n_style, h_n_content = fd(self.conv_style, h_n), fd(self.conv_content, h_n)
+            style = [fd(self.conv_style, v) for v in (h_a, h_al, h_l)]
+            content = [fd(self.conv_content, v) for v in (h_a, h_al, h_l)]
+            anatomy = [fd(self.conv_anatomy, v) for v in (h_a, h_al)]
+            lesion = [fd(self.conv_lesion, v) for v in (h_al, h_l)]
+            h_style = self._proj(cx, self.style_proj, style)
+            h_share = self._proj(cx, self.share_content_proj, content)
+            h_anat = self._proj(cx, self.anatomy_proj, anatomy)
+            h_les = self._proj(cx, self.lesion_proj, lesion)
         cat = torch.cat([h_n.t, h_share, h_style, h_anat, h_les], dim=-1)          # :734 (8x8 maps: tiny)
         ap = self.all_proj[1]
         h = run_conv(cx, [(ops.add4_scale(cat, silu=True), pw.conv[id(ap)], 0, 1, 0)], bias=_f(ap.bias))   # :738

@@ -1,2 +1,3 @@
-python -m pytest tests/test_gpu_ops.py -m gpu -x -q 2>&1 | tail -2
-python tools/step_breakdown.py cfg3 8 > gpurun_out/breakdown_cfg3.txt 2>&1; head -24 gpurun_out/breakdown_cfg3.txt
+python -m pytest tests/test_gpu_model.py -m gpu -x -q 2>&1 | tail -2
+python bench.py --no-cpu-baseline --no-kernel-pass 2>/dev/null | cut -c1-120
+B200DIFF_ENCODER_STREAMS=0 python bench.py --no-cpu-baseline --no-kernel-pass 2>/dev/null | cut -c1-120
