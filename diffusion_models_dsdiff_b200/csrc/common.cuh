@@ -113,6 +113,37 @@ __device__ __forceinline__ uint4 pack8_fast<__nv_bfloat16>(const float (&f)[8]) 
   return u;
 }
 
+// two fp32 -> one packed 16-bit pair with saturation to the largest finite value (single F2FP.SATFINITE)
+template <typename T>
+__device__ __forceinline__ uint32_t pack2_sat(float lo, float hi);
+template <>
+__device__ __forceinline__ uint32_t pack2_sat<__half>(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <>
+__device__ __forceinline__ uint32_t pack2_sat<__nv_bfloat16>(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ uint4 pack8_sat(const float *f) {
+  return make_uint4(pack2_sat<T>(f[0], f[1]), pack2_sat<T>(f[2], f[3]), pack2_sat<T>(f[4], f[5]), pack2_sat<T>(f[6], f[7]));
+}
+// one packed 16-bit pair -> two fp32
+template <typename T>
+__device__ __forceinline__ float2 unpack2(uint32_t w);
+template <>
+__device__ __forceinline__ float2 unpack2<__half>(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2 *>(&w));
+}
+template <>
+__device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+
 // streaming 128-bit access (read-once / write-once tensors)
 __device__ __forceinline__ uint4 ld_stream(const void *p) {
   uint4 r;

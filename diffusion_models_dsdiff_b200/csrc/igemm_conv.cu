@@ -16,7 +16,7 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kMaxStages = 8;
 constexpr int kConvThreads = 320;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue
-constexpr int kStatSmem = 8 * 256 * 4 + 8 * 128 * 4;   // per-epilogue-warp GroupNorm column accumulators + staged biases
+constexpr int kStatSmem = 8 * 256 * 4 + 8 * 128 * 4 + 8 * 1024;   // per-epilogue-warp GroupNorm column accumulators + staged biases + transpose tiles
 constexpr int kAccCols = 256;      // TMEM columns per accumulator stage
 constexpr int kTmemCols = 512;     // two accumulator stages
 constexpr int kABytes = kBM * kBK * 2;
@@ -165,7 +165,10 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
 // kCtas == 1: one CTA per 128 x BN tile.  kCtas == 2: a CTA pair (2-CTA cluster on one TPC) per 256 x BN tile — each CTA
 // stages ITS 128 pixels and HALF of the weight tile, the leader's tcgen05.mma.cta_group::2 consumes both halves, so the
 // weight bytes that cross L2 -> SM per FLOP are halved.
-template <typename T, int kCtas>
+// kFast: the hot epilogue — 16-bit NHWC output with 256-bit stores, full tiles (no bounds masks), bias staged in shared
+// memory, optional residual and GroupNorm statistics; everything else (fp32 heads, GELU, adaLN gate, ragged tiles) takes
+// the generic path.
+template <typename T, int kCtas, bool kFast>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -334,6 +337,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
     // load latency hides behind the tile's MMAs (a warp's 32 rows lie in one image when TW*TH >= 32)
     float *bs = reinterpret_cast<float *>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * stage_bytes) + 8 * 256 + ew * 128;
     const bool staged_bias = (p.TW * p.TH >= 32) && (p.bias || p.rowbias);
+    // fast path: 32 rows x 32 B transpose tile of the stored 16-bit chunk (the two 16-byte halves of row r swapped when
+    // (r >> 2) & 1, which makes both the row writes and the column reads bank-conflict free)
+    uint8_t *tb = smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * stage_bytes + (8 * 256 + 8 * 128) * 4 + ew * 1024;
     int acc_n = -1, acc_ntile = 0;
     if (p.gn_sums) {
       for (int i = lane; i < 256; i += 32) st_sum[i] = 0.f;
@@ -368,7 +374,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       const int n0 = (pt / p.tiles_h) * p.TN;
       const int n = n0 + tn;
       const int n_warp = n0 + lane_base / (p.TW * p.TH);
-      const bool valid = (w < p.Wout) && (h < p.Hout) && (n < p.N);
+      const bool valid = kFast || ((w < p.Wout) && (h < p.Hout) && (n < p.N));
       const size_t pix = ((size_t)n * p.Hout + h) * p.Wout + w;
       if (p.gn_sums && (n_warp != acc_n || n_tile != acc_ntile)) {
         if (acc_n >= 0) flush_stats();
@@ -417,6 +423,59 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
         const int co = n_tile * p.BN + c;
         float v[16];
         uint4 packed[2];
+        if constexpr (kFast) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+          if (staged_bias) {
+            const float4 *bp = reinterpret_cast<const float4 *>(bs + (c >> 5) * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b4 = bp[j];
+              v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+            }
+          }
+          if (res) {
+            const uint32_t *rw = reinterpret_cast<const uint32_t *>(rq);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 f = unpack2<T>(rw[j]);
+              v[2 * j] = fmaf(p.res_scale, f.x, v[2 * j]);
+              v[2 * j + 1] = fmaf(p.res_scale, f.y, v[2 * j + 1]);
+            }
+          }
+          packed[0] = pack8_sat<T>(v);
+          packed[1] = pack8_sat<T>(v + 8);
+          st_global_256(out + pix * p.Cout + co, packed[0], packed[1]);
+          if (p.gn_sums) {
+            // column sums of the STORED values through the transpose tile: lane = (column pair, row mod 4)
+            __syncwarp();
+            const int sw = (lane >> 2) & 1;
+            *reinterpret_cast<uint4 *>(tb + lane * 32 + (sw ? 16 : 0)) = packed[0];
+            *reinterpret_cast<uint4 *>(tb + lane * 32 + (sw ? 0 : 16)) = packed[1];
+            __syncwarp();
+            const int cp = lane >> 2, r0 = lane & 3;
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) {
+              const int half = (cp >> 2) ^ (rr & 1);
+              const uint32_t wv = *reinterpret_cast<const uint32_t *>(tb + (r0 + 4 * rr) * 32 + half * 16 + (cp & 3) * 4);
+              const float2 f = unpack2<T>(wv);
+              s0 += f.x; s1 += f.y;
+              q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+            }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+              s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+              q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+            }
+            if (r0 == 0) {
+              const int slot = (c >> 5) * 16 + 2 * cp;
+              st_sum[slot] += s0; st_sum[slot + 1] += s1;
+              st_sq[slot] += q0; st_sq[slot + 1] += q1;
+            }
+          }
+          return;
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int cb = co + half * 8;
@@ -608,7 +667,7 @@ static void choose_tiling(const b200_conv_desc *d, int *ctas, int *bn) {
   }
 }
 
-template <typename T, int kCtas>
+template <typename T, int kCtas, bool kFast>
 static int launch_conv(const b200_conv_desc *d, int bn, cudaStream_t stream) {
   ConvKParams p{};
   ConvMaps maps{};
@@ -642,7 +701,7 @@ static int launch_conv(const b200_conv_desc *d, int bn, cudaStream_t stream) {
   p.a_bytes = any_halo ? kABytes + 2 * p.TW * 128 : kABytes;
   const size_t b_bytes = (size_t)(p.BN / kCtas) * 128;
   p.stage_bytes = p.a_bytes + (any_halo ? 3 : 1) * (int)b_bytes;
-  p.stages = (int)std::min<size_t>(kMaxStages, (220 * 1024 - kStatSmem) / p.stage_bytes);
+  p.stages = (int)std::min<size_t>(kMaxStages, (226 * 1024 - 1536 - kStatSmem) / p.stage_bytes);
   B200_CHECK(p.stages >= 2, "conv: tile too large for shared memory");
 
   for (int s = 0; s < d->nseg; ++s) {
@@ -672,7 +731,7 @@ static int launch_conv(const b200_conv_desc *d, int bn, cudaStream_t stream) {
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + kStatSmem;
   static bool attr_set = false;     // per (T, kCtas) instantiation
   if (!attr_set) {
-    B200_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<T, kCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<T, kCtas, kFast>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    226 * 1024));
     attr_set = true;
   }
@@ -689,7 +748,7 @@ static int launch_conv(const b200_conv_desc *d, int bn, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B200_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<T, kCtas>, maps, p));
+  B200_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<T, kCtas, kFast>, maps, p));
   B200_LAUNCH_CHECK();
   if (d->gn_sums && !p.gn_sums)
     return b200_channel_stats(d->out, d->N, d->Hout * d->Wout, d->Cout, d->gn_sums, d->act_dtype, stream);
@@ -713,10 +772,25 @@ extern "C" int b200_conv2d_igemm(const b200_conv_desc *d, void *stream) {
   int ctas, bn;
   choose_tiling(d, &ctas, &bn);
   const bool one_cta = force_one_cta || ctas == 1;
-  if (d->act_dtype == B200_F16)
-    return one_cta ? launch_conv<__half, 1>(d, bn, (cudaStream_t)stream) : launch_conv<__half, 2>(d, bn, (cudaStream_t)stream);
-  if (d->act_dtype == B200_BF16)
-    return one_cta ? launch_conv<__nv_bfloat16, 1>(d, bn, (cudaStream_t)stream)
-                   : launch_conv<__nv_bfloat16, 2>(d, bn, (cudaStream_t)stream);
+  const int kc = one_cta ? 1 : 2;
+  // fast epilogue: 16-bit NHWC output, 32-byte aligned rows, every tile full, warp rows inside one image
+  int TW = 1, TH = 1, TN = 1;
+  pick_box(d->Hout, d->Wout, &TW, &TH, &TN);
+  const long ptiles = (long)cdiv(d->Wout, TW) * cdiv(d->Hout, TH) * cdiv(d->N, TN);
+  static const bool no_fast = getenv("B200DIFF_CONV_NO_FAST_EPI") != nullptr;
+  const bool fast = !no_fast && d->out && !d->out_nchw_f32 && !d->out_nhwc_f32 && !d->epi_act && !d->rowscale &&
+                    d->Cout % 16 == 0 && d->Cout % bn == 0 && (((uintptr_t)d->out | (uintptr_t)d->residual) & 31) == 0 &&
+                    d->Wout % TW == 0 && d->Hout % TH == 0 && d->N % TN == 0 && ptiles % kc == 0 && TW * TH >= 32 &&
+                    !getenv("B200DIFF_SKIP_EPI") && !getenv("B200DIFF_NO_VEC32");
+#define B200_CONV_DISPATCH(TT)                                                                           \
+  do {                                                                                                   \
+    if (kc == 1) return fast ? launch_conv<TT, 1, true>(d, bn, (cudaStream_t)stream)                     \
+                             : launch_conv<TT, 1, false>(d, bn, (cudaStream_t)stream);                   \
+    return fast ? launch_conv<TT, 2, true>(d, bn, (cudaStream_t)stream)                                  \
+                : launch_conv<TT, 2, false>(d, bn, (cudaStream_t)stream);                                \
+  } while (0)
+  if (d->act_dtype == B200_F16) B200_CONV_DISPATCH(__half);
+  if (d->act_dtype == B200_BF16) B200_CONV_DISPATCH(__nv_bfloat16);
+#undef B200_CONV_DISPATCH
   B200_CHECK(false, "conv: bad act_dtype %d", d->act_dtype);
 }
