@@ -56,6 +56,19 @@ __global__ void pack_weight_kernel(const float *__restrict__ w, T *__restrict__ 
 // coalesced 512-byte stores; the 9*Cin input taps are warp-broadcast loads), weights sit in shared memory as
 // [Cin*9][Cout].  The per-(image, channel) sums for the following GroupNorm are accumulated on the fly.
 // ------------------------------------------------------------------------------------------
+// packed fp32x2 FMA (sm_100 FFMA2): d = a * b + d on two lanes of a 64-bit register pair
+__device__ __forceinline__ void ffma2(unsigned long long &d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+
 template <typename T, bool kRegW>
 __global__ void __launch_bounds__(256)
 conv3x3_in_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
@@ -83,26 +96,25 @@ conv3x3_in_kernel(const float *__restrict__ x, const float *__restrict__ w, cons
   const int run = (p_stop - p_begin + rows - 1) / rows;
   const int p0 = p_begin + row * run;
   const int p1 = active ? min(p_stop, p0 + run) : 0;
-  float bv[8];
+  unsigned long long bv[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) bv[i] = bias ? bias[c0 + i] : 0.f;
-  float wr[kRegW ? 72 : 1];     // Cin == 1: this thread's 9 taps x 8 output channels stay in registers
+  for (int i = 0; i < 4; ++i) bv[i] = pack_f32x2(bias ? bias[c0 + 2 * i] : 0.f, bias ? bias[c0 + 2 * i + 1] : 0.f);
+  unsigned long long wr[kRegW ? 36 : 1];     // Cin == 1: this thread's 9 taps x 8 output channels stay in registers
   if (kRegW) {
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) wr[t * 8 + i] = w[(size_t)(c0 + i) * 9 + t];
+      for (int i = 0; i < 4; ++i)
+        wr[t * 4 + i] = pack_f32x2(w[(size_t)(c0 + 2 * i) * 9 + t], w[(size_t)(c0 + 2 * i + 1) * 9 + t]);
   }
-  float s[8] = {0}, q[8] = {0};
+  unsigned long long s2[4] = {0, 0, 0, 0}, q2[4] = {0, 0, 0, 0};
   const float *xn = x + (size_t)n * Cin * HW;
   T *on = out + (size_t)n * HW * Cout + c0;
   float win[9];
   bool fresh = true;
+  int hq = p0 / W, wq = p0 - hq * W;
   for (int p = p0; p < p1; ++p) {
-    const int hq = p / W, wq = p - hq * W;
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = bv[i];
+    unsigned long long acc[4] = {bv[0], bv[1], bv[2], bv[3]};
     for (int ci = 0; ci < Cin; ++ci) {
       const float *xc = xn + (size_t)ci * HW;
       auto tap = [&](int r, int t) {
@@ -120,31 +132,42 @@ conv3x3_in_kernel(const float *__restrict__ x, const float *__restrict__ w, cons
       }
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        const float v = win[t];
+        const unsigned long long vv = pack_f32x2(win[t], win[t]);
         if (kRegW) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] = fmaf(v, wr[t * 8 + i], acc[i]);
+          for (int i = 0; i < 4; ++i) ffma2(acc[i], vv, wr[t * 4 + i]);
         } else {
-          const float *wp = sw + (ci * 9 + t) * Cout + c0;
-          const float4 w0 = *reinterpret_cast<const float4 *>(wp);
-          const float4 w1 = *reinterpret_cast<const float4 *>(wp + 4);
-          acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
-          acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-          acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
-          acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+          const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(sw + (ci * 9 + t) * Cout + c0);
+          const ulonglong2 w0 = wp[0], w1 = wp[1];
+          ffma2(acc[0], vv, w0.x); ffma2(acc[1], vv, w0.y);
+          ffma2(acc[2], vv, w1.x); ffma2(acc[3], vv, w1.y);
         }
       }
     }
     fresh = false;
-    const uint4 u = pack8<T>(acc);
-    st_stream(on + (size_t)p * Cout, u);
-    if (sums) {
-      unpack8<T>(u, acc);              // statistics of the stored (rounded) values
+    float f[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i] += acc[i]; q[i] += acc[i] * acc[i]; }
+    for (int i = 0; i < 4; ++i) unpack_f32x2(acc[i], f[2 * i], f[2 * i + 1]);
+    const uint4 u = pack8_sat<T>(f);
+    st_stream(on + (size_t)p * Cout, u);
+    if (sums) {                         // statistics of the stored (rounded) values
+      const uint32_t *uw = reinterpret_cast<const uint32_t *>(&u);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 g = unpack2<T>(uw[i]);
+        const unsigned long long gg = pack_f32x2(g.x, g.y);
+        ffma2(s2[i], gg, pack_f32x2(1.f, 1.f));
+        ffma2(q2[i], gg, gg);
+      }
     }
+    if (++wq == W) { wq = 0; ++hq; }
   }
-  if (sums) block_flush_col_sums(s, q, active, row, col, ncol, rows, sums + ((size_t)n * Cout + c0) * 2);
+  if (sums) {
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { unpack_f32x2(s2[i], s[2 * i], s[2 * i + 1]); unpack_f32x2(q2[i], q[2 * i], q[2 * i + 1]); }
+    block_flush_col_sums(s, q, active, row, col, ncol, rows, sums + ((size_t)n * Cout + c0) * 2);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
