@@ -1,0 +1,20 @@
+"""One GroupNorm+SiLU shape, a few launches (ncu --set full target): python tools/gn_one.py N H W C"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from diffusion_models_dsdiff_b200 import ops
+n, h, w, c = [int(v) for v in sys.argv[1:5]]
+dev = torch.device("cuda:0")
+x = torch.randn(n, h, w, c, device=dev).half()
+g, b = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+cs = ops.channel_stats(x)
+for _ in range(4):
+    ops.group_norm(x, g, b, cs0=cs)
+torch.cuda.synchronize()
+a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(10):
+    ops.group_norm(x, g, b, cs0=cs)
+e.record(); torch.cuda.synchronize()
+ms = a.elapsed_time(e) / 10
+print(f"gn+silu {n}x{h}x{w}x{c}: {ms:.4f} ms  {4.0*x.numel()/ms/1e6:.1f} GB/s (algorithmic: read + write 2 B each)")
