@@ -9,10 +9,12 @@
 //     K=128 keys), fp32 accumulators in TMEM (S double-buffered, O resident for the whole key loop);
 //   * operands are staged by TMA as un-swizzled 8x16-byte core matrices: one box of (8 channels x 128 tokens) per
 //     16-byte channel block, so Q and K land K-major and V lands MN-major with NO transpose pass;
-//   * EXACT softmax in two sweeps over the keys: sweep 1 finds the true row maximum (like the reference's
-//     th.softmax), sweep 2 recomputes S, writes P = exp2((S - max) * scale*log2e) as 16-bit to shared memory and
-//     accumulates O and the row sums; no running-max rescale of O is ever needed.  The second Q K^T costs 50 % more
-//     tensor work on a kernel that is bound by the exponentials (MUFU), not by the MMAs.
+//   * ONE sweep over the keys with an online softmax: per key tile the row maximum of the tile (two warps per row
+//     exchange their 64-column halves through shared memory + a 64-thread named barrier) updates a running reference M
+//     LAZILY — only when it grows by more than 2^8 — so P = exp2((S - M) * scale*log2e) stays <= 256 (exact in 16-bit)
+//     and the O accumulator in TMEM is rescaled (tcgen05.ld -> mul -> tcgen05.st by the softmax warps, after the
+//     previous P V has completed) only on those rare steps.  S is read from TMEM once per tile: the kernel is bound by
+//     the TMEM read port (64 B/clk) and the exponentials (MUFU), both of which the old exact two-sweep version paid twice.
 //   * warp roles: warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 = softmax: thread == (query row,
 //     64-column half of the key tile), two warps per scheduler so MUFU / TMEM-load latency overlaps.
 //
@@ -73,7 +75,7 @@ struct FaParams {
 };
 
 template <typename T, int D>
-__global__ void __launch_bounds__(kFaThreads, 1)
+__global__ void __launch_bounds__(kFaThreads, (D <= 48) ? 2 : 1)
 flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
   constexpr int kDB = D / 8;                         // 16-byte channel blocks per row
   constexpr uint32_t kTileBytes = kDB * kBlkBytes;   // Q / K / V tile: D x 128 x 2 B
@@ -81,8 +83,9 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
   __shared__ __align__(8) uint64_t q_full, o_full;
   __shared__ __align__(8) uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
   __shared__ __align__(8) uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2];
+  __shared__ __align__(8) uint64_t pv_done;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_xchg[2][kFaBM];     // per-row max / sum exchange between the two column halves
+  __shared__ float s_xchg[2][2][kFaBM];  // [tile parity][column half][row]: per-row max / sum exchange between the halves
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,6 +103,7 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     prefetch_tmap(&maps.q); prefetch_tmap(&maps.k); prefetch_tmap(&maps.v);
     mbar_init(smem_u32(&q_full), 1);
     mbar_init(smem_u32(&o_full), 1);
+    mbar_init(smem_u32(&pv_done), 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&k_full[i]), 1);  mbar_init(smem_u32(&k_empty[i]), 1);
       mbar_init(smem_u32(&v_full[i]), 1);  mbar_init(smem_u32(&v_empty[i]), 1);
@@ -108,12 +112,14 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 512);
+  // S (128 columns, single buffer: the softmax warps copy it to registers and hand it back at once) + O (D columns)
+  constexpr uint32_t kTmemCols = (D <= 128) ? 256 : 512;
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const uint32_t tmem_o = tmem_base + 2 * kFaSCols;
+  const uint32_t tmem_o = tmem_base + kFaSCols;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -124,25 +130,21 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         tma_load_3d(sQ + c * kBlkBytes, &maps.q, qb, p.q_off + h * p.q_hstride + c * 8, q0, b);
       int ks = 0, vs = 0;
       uint32_t kph = 0, vph = 0;
-      for (int pass = 0; pass < 2; ++pass) {
-        for (int j = 0; j < nk; ++j) {
-          mbar_wait(smem_u32(&k_empty[ks]), kph ^ 1);
-          const uint32_t kb = smem_u32(&k_full[ks]);
-          mbar_arrive_expect_tx(kb, kTileBytes);
-          for (int c = 0; c < kDB; ++c)
-            tma_load_3d(sK + ks * kTileBytes + c * kBlkBytes, &maps.k, kb, p.k_off + h * p.k_hstride + c * 8,
-                        j * kFaBN, b);
-          if (++ks == p.stages) { ks = 0; kph ^= 1; }
-          if (pass == 1) {
-            mbar_wait(smem_u32(&v_empty[vs]), vph ^ 1);
-            const uint32_t vb = smem_u32(&v_full[vs]);
-            mbar_arrive_expect_tx(vb, kTileBytes);
-            for (int c = 0; c < kDB; ++c)
-              tma_load_3d(sV + vs * kTileBytes + c * kBlkBytes, &maps.v, vb, p.v_off + h * p.v_hstride + c * 8,
-                          j * kFaBN, b);
-            if (++vs == p.stages) { vs = 0; vph ^= 1; }
-          }
-        }
+      for (int j = 0; j < nk; ++j) {
+        mbar_wait(smem_u32(&k_empty[ks]), kph ^ 1);
+        const uint32_t kb = smem_u32(&k_full[ks]);
+        mbar_arrive_expect_tx(kb, kTileBytes);
+        for (int c = 0; c < kDB; ++c)
+          tma_load_3d(sK + ks * kTileBytes + c * kBlkBytes, &maps.k, kb, p.k_off + h * p.k_hstride + c * 8,
+                      j * kFaBN, b);
+        if (++ks == p.stages) { ks = 0; kph ^= 1; }
+        mbar_wait(smem_u32(&v_empty[vs]), vph ^ 1);
+        const uint32_t vb = smem_u32(&v_full[vs]);
+        mbar_arrive_expect_tx(vb, kTileBytes);
+        for (int c = 0; c < kDB; ++c)
+          tma_load_3d(sV + vs * kTileBytes + c * kBlkBytes, &maps.v, vb, p.v_off + h * p.v_hstride + c * 8,
+                      j * kFaBN, b);
+        if (++vs == p.stages) { vs = 0; vph ^= 1; }
       }
     }
     __syncwarp();
@@ -154,9 +156,9 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
       uint32_t kph = 0, vph = 0;
       int g = 0;                       // global S-tile counter (both sweeps)
       auto issue_qk = [&](int gi) {
-        const int sb = gi & 1;
+        const int sb = 0;
         mbar_wait(smem_u32(&k_full[ks]), kph);
-        mbar_wait(smem_u32(&s_empty[sb]), ((gi >> 1) & 1) ^ 1);
+        mbar_wait(smem_u32(&s_empty[sb]), (gi & 1) ^ 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
@@ -169,9 +171,7 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         umma_commit(smem_u32(&s_full[sb]));
         if (++ks == p.stages) { ks = 0; kph ^= 1; }
       };
-      // sweep 1: scores only
-      for (int j = 0; j < nk; ++j) issue_qk(g++);
-      // sweep 2: scores (one tile ahead) + P V
+      // scores run one tile ahead of P V
       issue_qk(g++);
       for (int j = 0; j < nk; ++j) {
         if (j + 1 < nk) issue_qk(g++);
@@ -190,6 +190,7 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         }
         umma_commit(smem_u32(&v_empty[vs]));
         umma_commit(smem_u32(&p_empty[pb]));
+        umma_commit(smem_u32(&pv_done));       // O holds tiles 0..j: the softmax warps may rescale it
         if (++vs == p.stages) { vs = 0; vph ^= 1; }
       }
       umma_commit(smem_u32(&o_full));
@@ -202,79 +203,110 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     const int half = (warp - 2) >> 2;                 // key columns [64*half, 64*half + 64) of every tile
     const int cbase = half * 64;
     const uint32_t t_lane = (uint32_t)lane_base << 16;
-    float m = -INFINITY;
-    int g = 0;
-    // sweep 1: exact row maximum of the raw scores
-    for (int j = 0; j < nk; ++j, ++g) {
-      const int sb = g & 1;
-      mbar_wait(smem_u32(&s_full[sb]), (g >> 1) & 1);
+    const int pair_bar = 2 + (warp & 3);              // named barrier of the two warps that share this row quadrant
+    constexpr int kHalfD = D / 2;                     // O columns this half rescales / writes out (multiple of 8)
+    float M = -INFINITY;                              // running softmax reference (raw-score units), lazily updated
+    float l = 0.f;
+    for (int j = 0; j < nk; ++j) {
+      const int sb = 0, pb = j & 1;
+      mbar_wait(smem_u32(&s_full[sb]), j & 1);
       tc_fence_after();
       const int nvalid = min(kFaBN, p.Lk - j * kFaBN);
-#pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + t_lane + sb * kFaSCols + cbase + c0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (cbase + c0 + i < nvalid) m = fmaxf(m, __uint_as_float(r[i]));
-      }
+      uint32_t r0[32], r1[32];
+      tmem_ld32(tmem_base + t_lane + sb * kFaSCols + cbase, r0);
+      tmem_ld32(tmem_base + t_lane + sb * kFaSCols + cbase + 32, r1);
+      tmem_ld_wait();
+      // S tile is in registers: hand the TMEM buffer back so the next Q K^T can start
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_empty[sb]));
-    }
-    // combine the two halves' maxima (named barrier 1 = the 256 softmax threads)
-    s_xchg[half][row] = m;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    m = fmaxf(s_xchg[0][row], s_xchg[1][row]);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const float mneg = -m * p.scale_log2e;
-    float l = 0.f;
-    // sweep 2: P = exp2((S - m) * scale*log2e) -> shared memory (16-bit, K-major core matrices), row sums
-    for (int j = 0; j < nk; ++j, ++g) {
-      const int sb = g & 1, pb = j & 1;
-      mbar_wait(smem_u32(&s_full[sb]), (g >> 1) & 1);
+      const bool full = nvalid == kFaBN;                // every tile but (possibly) the last: no column masks
+      float mt = -INFINITY;
+      if (full) {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};       // 4 independent chains
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          m4[i & 3] = fmaxf(m4[i & 3], fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+        }
+        mt = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (cbase + i < nvalid) mt = fmaxf(mt, __uint_as_float(r0[i]));
+          if (cbase + 32 + i < nvalid) mt = fmaxf(mt, __uint_as_float(r1[i]));
+        }
+      }
+      s_xchg[j & 1][half][row] = mt;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      mt = fmaxf(mt, s_xchg[j & 1][half ^ 1][row]);
+      // lazy reference update: both halves of a row take the same decision from the same numbers
+      float alpha = 1.f;
+      bool grow = false;
+      if (j == 0) {
+        M = mt;
+      } else if ((mt - M) * p.scale_log2e > 8.f) {
+        alpha = ex2_approx((M - mt) * p.scale_log2e);
+        M = mt;
+        l *= alpha;
+        grow = true;
+      }
+      if (__any_sync(0xffffffffu, grow)) {
+        // rescale this row's half of the O accumulator; P V of tile j-1 must have landed first
+        mbar_wait(smem_u32(&pv_done), (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < kHalfD; c0 += 8) {
+          uint32_t o8[8];
+          tmem_ld8(tmem_o + t_lane + half * kHalfD + c0, o8);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o8[i] = __float_as_uint(__uint_as_float(o8[i]) * alpha);
+          tmem_st8(tmem_o + t_lane + half * kHalfD + c0, o8);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+      }
+      const float mneg = -M * p.scale_log2e;
       mbar_wait(smem_u32(&p_empty[pb]), ((j >> 1) & 1) ^ 1);
-      tc_fence_after();
-      const int nvalid = min(kFaBN, p.Lk - j * kFaBN);
       uint8_t *prow = smem_raw + (sP - smem_u32(smem_raw)) + pb * kFaPBytes + row * 16;
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + t_lane + sb * kFaSCols + cbase + c0, r);
-        tmem_ld_wait();
+        const uint32_t (&r)[32] = c0 ? r1 : r0;
 #pragma unroll
         for (int v8 = 0; v8 < 4; ++v8) {
           float f[8];
+          if (full) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int c = cbase + c0 + v8 * 8 + i;
-            const float e = ex2_approx(fmaf(__uint_as_float(r[v8 * 8 + i]), p.scale_log2e, mneg));
-            f[i] = c < nvalid ? e : 0.f;
-            l += f[i];
+            for (int i = 0; i < 8; ++i) f[i] = ex2_approx(fmaf(__uint_as_float(r[v8 * 8 + i]), p.scale_log2e, mneg));
+            l += ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int c = cbase + c0 + v8 * 8 + i;
+              const float e = ex2_approx(fmaf(__uint_as_float(r[v8 * 8 + i]), p.scale_log2e, mneg));
+              f[i] = c < nvalid ? e : 0.f;
+              l += f[i];
+            }
           }
-          const uint4 u = pack8_unit<T>(f);
+          const uint4 u = pack8_sat<T>(f);
           *reinterpret_cast<uint4 *>(prow + (((cbase + c0) >> 3) + v8) * kBlkBytes) = u;
         }
       }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(smem_u32(&p_full[pb]));
-        mbar_arrive(smem_u32(&s_empty[sb]));
-      }
+      if (lane == 0) mbar_arrive(smem_u32(&p_full[pb]));
     }
-    s_xchg[half][row] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");      // every pair is past its last per-tile exchange
+    s_xchg[0][half][row] = l;
     asm volatile("bar.sync 1, 256;" ::: "memory");
-    l = s_xchg[0][row] + s_xchg[1][row];
+    l = s_xchg[0][0][row] + s_xchg[0][1][row];
     // epilogue: O / l -> out[b, q0+row, h*D ...]; the halves split the D output channels
     mbar_wait(smem_u32(&o_full), 0);
     tc_fence_after();
     const float inv = 1.f / l;
     const int qi = q0 + row;
     T *o = reinterpret_cast<T *>(p.out) + ((size_t)b * p.Lq + qi) * p.ldo + h * D;
-    constexpr int kHalfD = D / 2;      // multiple of 8
 #pragma unroll
     for (int c0 = 0; c0 < kHalfD; c0 += 8) {
       uint32_t r[8];
@@ -293,7 +325,7 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -330,12 +362,16 @@ static int launch_flash(const AttnArgs &a, cudaStream_t st) {
   p.idesc_s = umma_idesc(Act<T>::kFmt, kFaBM, kFaBN, 0);
   p.idesc_o = umma_idesc(Act<T>::kFmt, kFaBM, D, 1);
   const size_t tile = (size_t)D * 256;
-  p.stages = (tile * 5 + 2 * kFaPBytes + 256 <= 200 * 1024) ? 2 : 1;
+  // D <= 48: two CTAs per SM (256 TMEM columns each), so one CTA's TMEM-read phase overlaps the other's exponentials;
+  // its shared memory must stay under ~110 KB
+  const size_t budget = (D <= 48) ? 108 * 1024 : 200 * 1024;
+  p.stages = (tile * 5 + 2 * kFaPBytes + 256 <= budget) ? 2 : 1;
   const size_t smem = tile * (1 + 2 * p.stages) + 2 * kFaPBytes + 256;
   B200_CHECK(smem <= 220 * 1024, "attention: head dim %d does not fit shared memory", D);
   static bool attr_set = false;
   if (!attr_set) {
     B200_CUDA(cudaFuncSetAttribute(flash_attn_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(flash_attn_kernel<T, D>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_set = true;
   }
   const dim3 grid(cdiv(a.Lq, kFaBM), a.heads, a.B);
