@@ -288,7 +288,7 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
 
 static void norm_grid(int N, int HW, int ncol, dim3 *grid, int *pix_per_block) {
   const int rows = std::max(1, kNormThreads / std::max(ncol, 1));
-  int target_blocks = std::max(1, (num_sms() * 8) / std::max(N, 1));
+  int target_blocks = std::max(1, (num_sms() * 4) / std::max(N, 1));   // one resident wave (4 CTAs of 256 threads per SM)
   // at least 4 sweeps of `rows` pixels per block so the unrolled loop body is used
   int max_blocks = std::max(1, HW / (rows * 4));
   int bps = std::min(target_blocks, max_blocks);
