@@ -76,6 +76,7 @@ SIGNATURES = {
     "b200_patchify": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "b200_unpatchify": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_add_f32": [_P, _P, _P, _L, _P],
+    "b200_cfg_combine": [_P, _P, _F, _P, _L, _P],
     "b200_softmax_rows": [_P, _P, _L, _I, _F, _I, _P],
     "b200_conv1x1_f32_nchw": [_P, _P, _P, _P, _I, _I, _I, _I, _P],
     "b200_gaussian_sample": [_P, _P, _P, _I, _I, _I, _P],

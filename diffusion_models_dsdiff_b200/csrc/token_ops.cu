@@ -122,6 +122,12 @@ unpatchify_kernel(const float *__restrict__ tok, float *__restrict__ out, int Co
   }
 }
 
+// classifier-free guidance combine (ldm/models/diffusion/ddim.py:218-219): out = u + s * (c - u), reference op order, no FMA
+__global__ void __launch_bounds__(256) cfg_combine_kernel(const float *u, const float *c, float s, float *out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __fadd_rn(u[i], __fmul_rn(s, __fsub_rn(c[i], u[i])));
+}
+
 __global__ void __launch_bounds__(256) add_f32_kernel(const float *a, const float *b, float *out, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = a[i] + b[i];
@@ -194,6 +200,14 @@ extern "C" int b200_add_f32(const float *a, const float *b, float *out, int64_t 
   B200_CHECK(a && b && out && n > 0, "add_f32: bad arguments");
   const int blocks = (int)std::min<long long>(cdiv64(n, 256), (long long)num_sms() * 16);
   add_f32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, b, out, n);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_cfg_combine(const float *uncond, const float *cond, float scale, float *out, int64_t n, void *stream) {
+  B200_CHECK(uncond && cond && out && n > 0, "cfg_combine: bad arguments");
+  const int blocks = (int)std::min<long long>(cdiv64(n, 256), (long long)num_sms() * 16);
+  cfg_combine_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(uncond, cond, scale, out, n);
   B200_LAUNCH_CHECK();
   return 0;
 }

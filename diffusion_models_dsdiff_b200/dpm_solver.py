@@ -136,13 +136,13 @@ def multistep_tables(ns: NoiseScheduleVP, steps: int, skip_type: str = "time_uni
 
 def run_multistep(net, ns: NoiseScheduleVP, x_T: Tensor, cond: Optional[List[Tensor]], steps: int, model_type: str,
                   skip_type: str, lower_order_final: bool, thresholding, cache: dict, context=None, use_graph=True,
-                  record=None):
+                  record=None, cfg: Optional[dict] = None):
     coef, t_input, _ = multistep_tables(ns, steps, skip_type, 2, lower_order_final)
     dev = x_T.device
     if model_type not in ("noise", "v"):
         raise NotImplementedError(f"B200 path: DPM-Solver++ model_type {model_type!r}")
     eng = StepEngine(_engine_model_fn(net), L.SAMPLER_DPMPP_2M, _PARAM["eps" if model_type == "noise" else "v"],
-                     coef.to(dev), t_input.to(dev), False, context=context, thresholding=thresholding,
+                     coef.to(dev), t_input.to(dev), False, context=context, thresholding=thresholding, **(cfg or {}),
                      **_graph_cache_args(cache, net))
     out = eng.run(x_T, cond, steps, use_graph=use_graph, want_x0=record is not None, record=record)
     return out, eng
@@ -176,8 +176,10 @@ class DPMSolverSampler(object):
         C, H, W = shape
         size = (batch_size, C, H, W)
         print(f'Data shape for DPM-Solver sampling is {size}, sampling steps {S}')
-        if unconditional_conditioning is not None and unconditional_guidance_scale != 1.:
-            raise NotImplementedError("classifier-free guidance is not built in the B200 path")
+        cfg = None
+        if unconditional_conditioning is not None and unconditional_guidance_scale != 1.:     # model_wrapper :323-331
+            cfg = dict(cfg_scale=unconditional_guidance_scale, uncond=self.model._cond_list(unconditional_conditioning),
+                       uncond_context=self.model._context(unconditional_conditioning))
         device = self.model.betas.device
         img = torch.randn(size, device=device) if x_T is None else x_T.to(device)
         ns = NoiseScheduleVP('discrete', betas=self.betas)
@@ -185,7 +187,7 @@ class DPMSolverSampler(object):
         x, eng = run_multistep(m.model.diffusion_model, ns, img, m._cond_list(conditioning), S,
                                MODEL_TYPES[m.parameterization], "time_uniform", True, None,
                                m.__dict__.setdefault("_graphs", {}), context=m._context(conditioning),
-                               use_graph=self.use_graph, record=kwargs.get("record"))
+                               use_graph=self.use_graph, record=kwargs.get("record"), cfg=cfg)
         self.last_engine = m.last_engine = eng
         return x.to(device), None
 

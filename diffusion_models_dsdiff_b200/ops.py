@@ -415,6 +415,17 @@ def add_f32(a: Tensor, b: Tensor) -> Tensor:
     return out
 
 
+def cfg_combine(uncond: Tensor, cond: Tensor, scale: float) -> Tensor:
+    """uncond + scale * (cond - uncond) (classifier-free guidance), fp32."""
+    _dev(uncond)
+    if uncond.shape != cond.shape:
+        raise L.B200Error("cfg_combine: shape mismatch")
+    out = torch.empty_like(uncond)
+    L.check(L.lib().b200_cfg_combine(_p(_f32(uncond)), _p(_f32(cond)), float(scale), _p(out), uncond.numel(), _stream()),
+            "cfg_combine")
+    return out
+
+
 def softmax_rows(s: Tensor, scale: float, dtype: torch.dtype) -> Tensor:
     """softmax(scale * s, dim=-1): fp32 logits [..., cols] -> 16-bit probabilities."""
     _dev(s)

@@ -156,8 +156,15 @@ class StepEngine:
     def __init__(self, model_fn: Callable, mode: int, param: int, coef: Tensor, t_table: Tensor,
                  clip_denoised: bool, learned_range: bool = False, cache: Optional[dict] = None, cache_key=None,
                  keepalive=None, prepare: Optional[Callable] = None, context: Optional[Tensor] = None,
-                 thresholding: Optional[Tuple[float, float]] = None):
+                 thresholding: Optional[Tuple[float, float]] = None, cfg_scale: float = 1.0,
+                 uncond: Optional[Sequence[Tensor]] = None, uncond_context: Optional[Tensor] = None):
         self.model_fn, self.mode, self.param = model_fn, mode, param
+        # classifier-free guidance (ddim.py:194-219): the network runs on [x; x] with [unconditional; conditional]
+        # conditioning and the two halves are combined before the update
+        self.cfg_scale = float(cfg_scale)
+        self.uncond = None if uncond is None else [u.float().contiguous() for u in uncond]
+        self.uncond_context = uncond_context
+        self.cfg = self.cfg_scale != 1.0 and (uncond is not None or uncond_context is not None)
         self.thresholding = thresholding    # DPM-Solver++ dynamic thresholding (ratio, max_val) or None
         self._dpm: Optional[dict] = None    # DPM-Solver++ static buffers: previous x0, raw x0, per-sample thresholds
         self.coef, self.t_table = coef, t_table
@@ -171,13 +178,28 @@ class StepEngine:
 
     def _one(self, x: Tensor, cond: Optional[Sequence[Tensor]], step_ptr: Tensor, noise: Optional[Tensor],
              pred_x0: Optional[Tensor]):
-        xc = x if not cond else torch.cat([x] + list(cond), dim=1)
-        if self.context is not None:
-            out = self.model_fn(xc, self.t_table, step_ptr, context=self.context)
+        if self.cfg:
+            n = x.shape[0]
+            x2 = torch.cat([x, x], dim=0)
+            if cond:
+                unc = self.uncond if self.uncond is not None else cond
+                x2 = torch.cat([x2] + [torch.cat([u, c], dim=0) for u, c in zip(unc, cond)], dim=1)
+            kw = {}
+            if self.context is not None:
+                uctx = self.uncond_context if self.uncond_context is not None else self.context
+                kw["context"] = torch.cat([uctx, self.context], dim=0)
+            out = self.model_fn(x2, self.t_table, step_ptr, **kw)
+            if isinstance(out, tuple):
+                out = out[0]
+            out = ops.cfg_combine(out[:n].contiguous(), out[n:].contiguous(), self.cfg_scale)
         else:
-            out = self.model_fn(xc, self.t_table, step_ptr)
-        if isinstance(out, tuple):
-            out = out[0]
+            xc = x if not cond else torch.cat([x] + list(cond), dim=1)
+            if self.context is not None:
+                out = self.model_fn(xc, self.t_table, step_ptr, context=self.context)
+            else:
+                out = self.model_fn(xc, self.t_table, step_ptr)
+            if isinstance(out, tuple):
+                out = out[0]
         if self.mode == L.SAMPLER_DPMPP_2M:      # deterministic ODE solver: no noise is drawn (dpm_solver_pytorch.py)
             b = self._dpm
             if out.shape[1] == 2 * x.shape[1]:   # learn-sigma networks: mean half only (gaussian_diffusion.py:484-487)
@@ -225,7 +247,8 @@ class StepEngine:
         # ---- graph path ----
         key = None
         if self.cache is not None:
-            key = (self.cache_key, self.mode, self.param, self.clip, self.learned_range, self.thresholding, tuple(x.shape),
+            key = (self.cache_key, self.mode, self.param, self.clip, self.learned_range, self.thresholding, self.cfg,
+                   self.cfg_scale, tuple(x.shape),
                    tuple(tuple(c.shape) for c in (cond or [])), steps, want_x0,
                    None if self.context is None else tuple(self.context.shape))
         entry = self.cache.get(key) if key is not None else None
@@ -239,6 +262,11 @@ class StepEngine:
                 dst.copy_(src)
             if self.context is not None:
                 entry["context"].copy_(self.context)
+            if self.uncond is not None:
+                for dst, src in zip(entry["uncond"], self.uncond):
+                    dst.copy_(src)
+            if self.uncond_context is not None:
+                entry["uncond_context"].copy_(self.uncond_context)
             entry["step_ptr"].zero_()
             self._dpm = entry.get("dpm")
             self.stats = {"graph_launches_per_step": entry["launches"], "graph_reused": True}
@@ -259,6 +287,10 @@ class StepEngine:
         cond = [c.clone().contiguous() for c in (cond or [])]
         if self.context is not None:
             self.context = self.context.clone().contiguous()      # static buffer read by the captured kernels
+        if self.uncond is not None:
+            self.uncond = [u.clone().contiguous() for u in self.uncond]
+        if self.uncond_context is not None:
+            self.uncond_context = self.uncond_context.clone().contiguous()
         gen_state = torch.cuda.get_rng_state(dev)
         scratch = x.clone()
         s = torch.cuda.Stream(device=dev)
@@ -277,7 +309,7 @@ class StepEngine:
         # capture does not execute: x / step_ptr / RNG are untouched
         entry = {"graph": graph, "x": x, "cond": cond, "pred_x0": pred_x0, "step_ptr": step_ptr, "coef": coef,
                  "t_table": t_table, "launches": launches, "keepalive": self.keepalive, "context": self.context,
-                 "dpm": self._dpm}
+                 "dpm": self._dpm, "uncond": self.uncond, "uncond_context": self.uncond_context}
         self.stats = {"graph_launches_per_step": launches, "graph_reused": False}
         if key is not None:
             if len(self.cache) >= 4:            # bounded: each entry pins a private activation pool
@@ -668,10 +700,10 @@ class DDIMSampler(object):
                 raise NotImplementedError(f"DDIMSampler.sample({name}=...) is not built in the B200 path")
         if quantize_x0 or noise_dropout > 0.:
             raise NotImplementedError("quantize_x0 / noise_dropout are not built in the B200 path")
-        if unconditional_conditioning is not None and unconditional_guidance_scale != 1.:
-            raise NotImplementedError("classifier-free guidance is not built in the B200 path")
         return self.ddim_sampling(conditioning, size, callback=callback, img_callback=img_callback,
                                   clip_denoised=clip_denoised,
+                                  unconditional_guidance_scale=unconditional_guidance_scale,
+                                  unconditional_conditioning=unconditional_conditioning,
                                   ddim_use_original_steps=kwargs.get("ddim_use_original_steps", False),
                                   temperature=temperature, x_T=x_T, log_every_t=log_every_t,
                                   noises=kwargs.get("noises"), record=kwargs.get("record"))
@@ -679,7 +711,7 @@ class DDIMSampler(object):
     @torch.no_grad()
     def ddim_sampling(self, cond, shape, x_T=None, ddim_use_original_steps=False, callback=None, timesteps=None,
                       clip_denoised=True, img_callback=None, log_every_t=100, temperature=1., noises=None,
-                      record=None, **unused):
+                      record=None, unconditional_guidance_scale=1., unconditional_conditioning=None, **unused):
         device = self.model.betas.device
         img = torch.randn(shape, device=device) if x_T is None else x_T.to(device)
         if timesteps is not None:
@@ -688,8 +720,12 @@ class DDIMSampler(object):
         total_steps = len(tsteps)
         print(f"Running DDIM Sampling with {total_steps} timesteps")
         t_table = torch.tensor(tsteps, dtype=torch.float32, device=device)
+        cfg = {}
+        if unconditional_conditioning is not None and unconditional_guidance_scale != 1.:
+            cfg = dict(cfg_scale=unconditional_guidance_scale, uncond=self.model._cond_list(unconditional_conditioning),
+                       uncond_context=self.model._context(unconditional_conditioning))
         eng = StepEngine(self.model._model_fn(), L.SAMPLER_LDM_DDIM, _PARAM[self.model.parameterization],
-                         coef.to(device), t_table, clip_denoised, context=self.model._context(cond),
+                         coef.to(device), t_table, clip_denoised, context=self.model._context(cond), **cfg,
                          **self.model._graph_cache_args())
         self.last_engine = self.model.last_engine = eng
         intermediates = {"x_inter": [img], "pred_x0": [img]}

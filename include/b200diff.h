@@ -191,6 +191,9 @@ int b200_patchify(const float *x, void *out, int N, int C, int H, int W, int p, 
 int b200_unpatchify(const float *tok, float *out, int N, int Cout, int gh, int gw, int p, int ld, void *stream);
 /* out = a + b over n fp32 values (c = t_emb + y_emb, DiT_models.py:246-248).                                        */
 int b200_add_f32(const float *a, const float *b, float *out, int64_t n, void *stream);
+/* classifier-free guidance: out = uncond + scale * (cond - uncond) over n fp32 values, the reference's operation order
+ * (DDIMSampler.p_sample_ddim, ldm/models/diffusion/ddim.py:218-219; model_wrapper, dpm_solver_pytorch.py:323-331).   */
+int b200_cfg_combine(const float *uncond, const float *cond, float scale, float *out, int64_t n, void *stream);
 
 /* ---- small dense layers on [B,K] fp32 vectors (timestep path) --------------------------------
  * replaces timestep_embedding (util.py:161-181), time_embed MLP (openaimodel.py:606-610) and

@@ -369,3 +369,22 @@ def test_sample_volume_batch_split_independent_on_gpu():
     b = PAR.sample_volume(sampler, cond, batch_size=2, base_seed=11, device=torch.device("cuda"))
     assert a.shape == (5, 1, 24, 24) and torch.isfinite(a).all()
     assert torch.equal(a, b)
+
+
+def test_ddim_classifier_free_guidance_matches_reference():
+    """DDIMSampler.sample(unconditional_guidance_scale=3, unconditional_conditioning=uc) (ddim.py:194-219)."""
+    S, m = _ldm("v")
+    g = golden("v1_ddim_cfg3")
+    rec = []
+    out, _ = S.DDIMSampler(m).sample(g["S"], 2, (1, 32, 32), g["cond"].cuda(), eta=0.0, x_T=g["x_T"].cuda(), verbose=False,
+                                     noises=list(g["noises"]), record=rec, unconditional_guidance_scale=g["scale"],
+                                     unconditional_conditioning=g["uncond"].cuda())
+    u, c = g["model_out2"][0].chunk(2)
+    # guidance amplifies the network's rounding noise: out = s*c - (s-1)*u carries up to (2s - 1) = 5x the error of one
+    # evaluation; the 1e-2 final-slice gate of the unguided loops scales accordingly (measured 1.5e-2 at s = 3)
+    amp = 2 * g["scale"] - 1
+    assert O.rel_err(rec[0]["model_out"].cpu(), u + g["scale"] * (c - u)) < amp * REL_TOL[torch.float16]
+    assert maxabs(out.cpu(), g["final"]) < 1e-2 * amp
+    out_g, _ = S.DDIMSampler(m).sample(g["S"], 2, (1, 32, 32), g["cond"].cuda(), eta=0.0, x_T=g["x_T"].cuda(), verbose=False,
+                                       unconditional_guidance_scale=g["scale"], unconditional_conditioning=g["uncond"].cuda())
+    assert maxabs(out_g, out) < 1e-6        # CUDA-graph path == eager path (eta = 0: the drawn noise is multiplied by 0)

@@ -232,3 +232,23 @@ def test_ten_bit_mantissa_operand_floor(case):
     fp16 = O.rel_err(run(lambda v: v.half().float()), g["y"])
     assert 0.7e-3 < tf32 < 2e-3 and 0.7e-3 < fp16 < 2e-3      # measured: 0.98e-3 / 0.93e-3 (UNet), 1.24e-3 / 1.27e-3 (DS-Diff)
     assert abs(tf32 - fp16) < 0.3 * tf32                      # same mantissa width -> same floor
+
+
+def test_ddim_classifier_free_guidance_oracle_matches_reference():
+    """ddim.py:194-219: the network runs on [x; x] with [uncond; cond], out = u + s (c - u)."""
+    hp, sd = synth_sd("unet_small")
+    g = golden("v1_ddim_cfg3")
+    sch = O.LdmSchedule(timesteps=2000, beta_schedule="linear", linear_start=1e-4, linear_end=2e-2)
+    S = g["S"]
+    tab = O.LdmDdimTables(sch, S, 0.0)
+    x = g["x_T"]
+    for i in range(S):
+        index = S - 1 - i
+        ts = torch.full((4,), int(tab.timesteps[index]), dtype=torch.long)
+        xin = torch.cat([torch.cat([x, x]), torch.cat([g["uncond"], g["cond"]])], 1)
+        out2 = O.unet_forward(sd, hp, xin, ts)
+        assert maxabs(out2, g["model_out2"][i]) < 2e-5 * max(1.0, float(g["model_out2"][i].abs().max()))
+        u, c = out2.chunk(2)
+        x, _ = O.ldm_ddim_step(sch, tab, x, u + g["scale"] * (c - u), index, g["noises"][i], "v", True)
+        assert maxabs(x, g["x_inter"][i]) < 1e-4, i
+    assert maxabs(x, g["final"]) < 1e-4
