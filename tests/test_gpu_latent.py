@@ -241,3 +241,33 @@ def test_dit_head_padding_and_step_table():
     step = torch.tensor([1], dtype=torch.int32).cuda()
     y2 = net(x.cuda(), table, step_ptr=step).cpu()
     assert torch.equal(y, y2)
+
+
+def test_dit_in_guided_diffusion_ddim_loop_matches_oracle():
+    """trainers/trainer_use_gaussian_diff_adv.py:74-80 — a DiT behind DiffusionWrapper('concat') driven by the
+    guided-diffusion DDIM loop (learned sigma, respaced, rescaled float timesteps): CUDA path (eager and graph) vs the
+    oracle loop on identical weights / x_T / noise."""
+    import diffusion_models_dsdiff_b200 as P
+    from diffusion_models_dsdiff_b200 import samplers as S
+    hp, sd = synth_sd("dit_small")
+    g = golden("dit_small")
+    sd["pos_embed"] = g["pos_embed"]
+    net = P.DiT(**hp)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    wrap = S.DiffusionWrapper(net, "concat")
+    d = S.create_gaussian_diffusion(steps=1000, learn_sigma=True, timestep_respacing="4", rescale_timesteps=True,
+                                    parameterization="v")
+    gen = torch.Generator().manual_seed(77)
+    x_T = torch.randn(2, 1, 32, 32, generator=gen)
+    cond = (torch.randn(2, 3, 32, 32, generator=gen) * 0.5).clamp_(-1, 1)
+    noises = [torch.randn(2, 1, 32, 32, generator=gen) for _ in range(4)]
+    out = d.ddim_sample_loop(wrap, (2, 1, 32, 32), noise=x_T.cuda(), clip_denoised=True,
+                             model_kwargs={"c_concat": [cond.cuda()]}, noises=noises, eta=0.0)
+    sch = O.GdSchedule(steps=1000, timestep_respacing="4", rescale_timesteps=True)
+    ref = O.gd_loop(lambda xc, ts: O.dit_forward(sd, hp, xc, ts), sch, x_T, cond, noises, mode="ddim", eta=0.0,
+                    parameterization="v", learn_sigma=True)
+    assert maxabs(out.cpu(), ref) < 1e-2
+    out_graph = d.ddim_sample_loop(wrap, (2, 1, 32, 32), noise=x_T.cuda(), clip_denoised=True,
+                                   model_kwargs={"c_concat": [cond.cuda()]}, eta=0.0)
+    assert maxabs(out_graph, out) < 1e-6
