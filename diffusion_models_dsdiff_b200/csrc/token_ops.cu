@@ -10,7 +10,9 @@ namespace b200 {
 
 constexpr int kLnMaxVec = 8;   // per-lane 16-byte vectors: C <= 8 * 8 * 32 = 2048
 
-template <typename T>
+// kV = 16-byte vectors per lane (C <= 256 * kV): small rows keep few registers live, so more warps are resident and
+// more bytes are in flight
+template <typename T, int kV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const T *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
                  const float *__restrict__ shift, const float *__restrict__ scale, int mod_stride, int rows_per_batch,
@@ -20,10 +22,10 @@ layernorm_kernel(const T *__restrict__ x, const float *__restrict__ gamma, const
   if (row >= rows) return;
   const int nvec = C >> 3;
   const T *xr = x + row * C;
-  float v[kLnMaxVec][8];
+  float v[kV][8];
   float sum = 0.f;
 #pragma unroll
-  for (int j = 0; j < kLnMaxVec; ++j) {
+  for (int j = 0; j < kV; ++j) {
     const int vi = lane + j * 32;
     if (vi < nvec) {
       unpack8<T>(ld_stream(xr + vi * 8), v[j]);
@@ -35,7 +37,7 @@ layernorm_kernel(const T *__restrict__ x, const float *__restrict__ gamma, const
   const float mean = sum / (float)C;
   float sq = 0.f;
 #pragma unroll
-  for (int j = 0; j < kLnMaxVec; ++j) {
+  for (int j = 0; j < kV; ++j) {
     const int vi = lane + j * 32;
     if (vi < nvec) {
 #pragma unroll
@@ -47,7 +49,7 @@ layernorm_kernel(const T *__restrict__ x, const float *__restrict__ gamma, const
   const long long b = row / rows_per_batch;
   T *orow = out + row * C;
 #pragma unroll
-  for (int j = 0; j < kLnMaxVec; ++j) {
+  for (int j = 0; j < kV; ++j) {
     const int vi = lane + j * 32;
     if (vi < nvec) {
       const int c = vi * 8;
@@ -144,15 +146,21 @@ extern "C" int b200_layernorm(const void *x, const float *gamma, const float *be
   B200_CHECK((shift == nullptr) == (scale == nullptr), "layernorm: shift and scale come together");
   B200_CHECK(rows_per_batch > 0, "layernorm: rows_per_batch must be positive");
   const unsigned blocks = (unsigned)cdiv64(rows, 8);
-  if (act_dtype == B200_F16)
-    layernorm_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half *)x, gamma, beta, shift, scale, mod_stride,
-                                                                     rows_per_batch, rows, C, eps, (__half *)out);
-  else if (act_dtype == B200_BF16)
-    layernorm_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16 *)x, gamma, beta, shift, scale,
-                                                                            mod_stride, rows_per_batch, rows, C, eps,
-                                                                            (__nv_bfloat16 *)out);
-  else
-    B200_CHECK(false, "layernorm: bad act_dtype");
+#define B200_LN_LAUNCH(TT, KV)                                                                                    \
+  layernorm_kernel<TT, KV><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TT *)x, gamma, beta, shift, scale, mod_stride, \
+                                                                     rows_per_batch, rows, C, eps, (TT *)out)
+#define B200_LN_DISPATCH(TT)                     \
+  do {                                           \
+    if (C <= 256) B200_LN_LAUNCH(TT, 1);         \
+    else if (C <= 512) B200_LN_LAUNCH(TT, 2);    \
+    else if (C <= 1024) B200_LN_LAUNCH(TT, 4);   \
+    else B200_LN_LAUNCH(TT, 8);                  \
+  } while (0)
+  if (act_dtype == B200_F16) B200_LN_DISPATCH(__half);
+  else if (act_dtype == B200_BF16) B200_LN_DISPATCH(__nv_bfloat16);
+  else B200_CHECK(false, "layernorm: bad act_dtype");
+#undef B200_LN_DISPATCH
+#undef B200_LN_LAUNCH
   B200_LAUNCH_CHECK();
   return 0;
 }
