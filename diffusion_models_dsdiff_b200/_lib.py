@@ -32,7 +32,8 @@ class ConvDesc(C.Structure):
                 ("Cout", C.c_int), ("stride", C.c_int), ("nseg", C.c_int), ("seg", ConvSeg * 3),
                 ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rowbias_stride", C.c_int),
                 ("residual", C.c_void_p), ("res_scale", C.c_float), ("out", C.c_void_p),
-                ("gn_sums", C.c_void_p), ("act_dtype", C.c_int), ("out_nchw_f32", C.c_void_p), ("cout_real", C.c_int), ("rowscale", C.c_void_p), ("rowscale_stride", C.c_int), ("epi_act", C.c_int), ("out_nhwc_f32", C.c_void_p)]
+                ("gn_sums", C.c_void_p), ("act_dtype", C.c_int), ("out_nchw_f32", C.c_void_p), ("cout_real", C.c_int), ("rowscale", C.c_void_p), ("rowscale_stride", C.c_int), ("epi_act", C.c_int), ("out_nhwc_f32", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
 class SamplerDesc(C.Structure):
@@ -63,6 +64,7 @@ SIGNATURES = {
     "b200_nhwc_to_nchw_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_pack_conv_weight": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_conv2d_igemm": [C.POINTER(ConvDesc), _P],
+    "b200_conv_ksplit": [C.POINTER(ConvDesc)],
     "b200_conv3x3_in": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P],
     "b200_conv3x3_out": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_groupnorm_stats": [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P],

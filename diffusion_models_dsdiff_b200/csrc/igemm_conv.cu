@@ -53,6 +53,9 @@ struct ConvKParams {
   float *out_f32;            // NCHW fp32 output of the first cout_real channels (network head) instead of `out`
   int cout_real;
   int debug_skip_epilogue;   // B200DIFF_SKIP_EPI: timing experiments only (results are garbage)
+  int ksplit;                // > 1: split-K, every (tile, split) item writes an fp32 partial tile to the workspace
+  int groups_total;          // pipeline groups of one tile's K loop (split s takes [s*G/S, (s+1)*G/S))
+  long long split_stride;    // floats between consecutive partial planes of the workspace
   int vec32;                 // Cout % 16 == 0 and 32-byte aligned out / residual: 256-bit epilogue loads / stores
 };
 
@@ -244,7 +247,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       __syncwarp();
       if (++st == p.stages) { st = 0; ph ^= 1; }
     };
-    for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
+    for (int item = tile0; item < p.num_tiles * p.ksplit; item += tile_step) {
+      const int tile = item / p.ksplit, split = item - tile * p.ksplit;
+      const int g_begin = (int)((long long)split * p.groups_total / p.ksplit);
+      const int g_end = (int)((long long)(split + 1) * p.groups_total / p.ksplit);
+      int gi = 0;
       const int n_tile = tile % p.n_ntiles;
       int pt = (tile / p.n_ntiles) * kCtas + (int)rank;      // this CTA's pixel tile of the pair
       const int w0 = (pt % p.tiles_w) * p.TW;
@@ -255,13 +262,14 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
         const int ks = p.seg_ks[s], pad = p.seg_pad[s], cin = p.seg_cin[s];
         if (p.seg_halo[s]) {
           for (int c0 = 0; c0 < cin; c0 += kBK)
-            for (int sx = 0; sx < 3; ++sx)
-              load_group(s, c0, n_tile, sx, 3, 3, halo_bytes, w0 + sx - 1, h0 - 1, n0);
+            for (int sx = 0; sx < 3; ++sx, ++gi)
+              if (gi >= g_begin && gi < g_end) load_group(s, c0, n_tile, sx, 3, 3, halo_bytes, w0 + sx - 1, h0 - 1, n0);
         } else {
           for (int tap = 0; tap < ks * ks; ++tap) {
             const int r = tap / ks, sx = tap - r * ks;
-            for (int c0 = 0; c0 < cin; c0 += kBK)
-              load_group(s, c0, n_tile, tap, 0, 1, (uint32_t)kABytes, w0 * p.stride + sx - pad, h0 * p.stride + r - pad, n0);
+            for (int c0 = 0; c0 < cin; c0 += kBK, ++gi)
+              if (gi >= g_begin && gi < g_end)
+                load_group(s, c0, n_tile, tap, 0, 1, (uint32_t)kABytes, w0 * p.stride + sx - pad, h0 * p.stride + r - pad, n0);
           }
         }
       }
@@ -272,7 +280,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       int st = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
+      for (int item = tile0; item < p.num_tiles * p.ksplit; item += tile_step, ++it) {
+        const int split = item % p.ksplit;
+        const int g_begin = (int)((long long)split * p.groups_total / p.ksplit);
+        const int g_end = (int)((long long)(split + 1) * p.groups_total / p.ksplit);
+        int gi = 0;
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
@@ -306,10 +318,12 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
           if (p.seg_halo[s]) {
             // tap row r = the 128 box rows starting r*TW pixels (r*TW*128 B, a multiple of the 1024-B swizzle atom)
             for (int c0 = 0; c0 < cin; c0 += kBK)
-              for (int sx = 0; sx < 3; ++sx) mma_group(3, (uint32_t)p.TW * 128u, (min(kBK, cin - c0) + 15) >> 4);
+              for (int sx = 0; sx < 3; ++sx, ++gi)
+                if (gi >= g_begin && gi < g_end) mma_group(3, (uint32_t)p.TW * 128u, (min(kBK, cin - c0) + 15) >> 4);
           } else {
             for (int tap = 0; tap < taps; ++tap)
-              for (int c0 = 0; c0 < cin; c0 += kBK) mma_group(1, 0u, (min(kBK, cin - c0) + 15) >> 4);
+              for (int c0 = 0; c0 < cin; c0 += kBK, ++gi)
+                if (gi >= g_begin && gi < g_end) mma_group(1, 0u, (min(kBK, cin - c0) + 15) >> 4);
           }
         }
         if (elect_one()) {
@@ -363,7 +377,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
     int it = 0;
     const uint32_t empty_bar_leader0 = (kCtas == 2) ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
     const int nch = p.debug_skip_epilogue ? 0 : (p.BN >> 4);
-    for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++it) {
+    for (int item = tile0; item < p.num_tiles * p.ksplit; item += tile_step, ++it) {
+      const int tile = item / p.ksplit;
+      float *f32_out = p.out_f32_nhwc + (long long)(item - tile * p.ksplit) * p.split_stride;   // this split's partial plane
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int n_tile = tile % p.n_ntiles;
@@ -526,7 +542,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
               for (int i = 0; i < 8; ++i) vh[i] += p.res_scale * rf[i];
             }
             if (p.out_f32_nhwc) {
-              float4 *o4 = reinterpret_cast<float4 *>(p.out_f32_nhwc + pix * p.Cout + cb);
+              float4 *o4 = reinterpret_cast<float4 *>(f32_out + pix * p.Cout + cb);
               o4[0] = make_float4(vh[0], vh[1], vh[2], vh[3]);
               o4[1] = make_float4(vh[4], vh[5], vh[6], vh[7]);
             } else if (p.out_f32) {
@@ -667,8 +683,97 @@ static void choose_tiling(const b200_conv_desc *d, int *ctas, int *bn) {
   }
 }
 
+// ---- split-K -------------------------------------------------------------------------------------------------------
+// 8x8 / 16x16 maps have 2-32 output tiles for 148 SMs while their K loop (9 taps x 960..1920 channels) streams 17-33 MB
+// of weights: the layer is bound by how many SMs pull operands, not by the tensor pipe.  Each (tile, split) work item runs
+// 1/S of the K groups and writes an fp32 partial tile (plain stores: deterministic); the finalize kernel adds the S
+// partials IN ORDER, applies bias / timestep bias / residual, stores 16-bit and accumulates the GroupNorm sums.
+// S depends on the layer geometry only (never on N), so an image's result does not depend on its batch.
+static int conv_groups_total(const b200_conv_desc *d) {
+  int TW = 1, TH = 1, TN = 1;
+  pick_box(d->Hout, d->Wout, &TW, &TH, &TN);
+  const bool halo_ok = d->stride == 1 && TN == 1 && TW >= 8 && !getenv("B200DIFF_NO_HALO");
+  int g = 0;
+  for (int s = 0; s < d->nseg; ++s) {
+    const int chunks = cdiv(d->seg[s].cin, kBK);
+    g += (halo_ok && d->seg[s].ksize == 3 && d->seg[s].pad == 1) ? chunks * 3 : chunks * d->seg[s].ksize * d->seg[s].ksize;
+  }
+  return g;
+}
+
+static int conv_ksplit(const b200_conv_desc *d) {
+  static const bool off = getenv("B200DIFF_CONV_NO_SPLITK") != nullptr;
+  if (off || d->out == nullptr || d->out_nchw_f32 || d->out_nhwc_f32 || d->epi_act || d->rowscale) return 1;
+  // measured inside a CUDA graph (tools/graph_probe.py): 8x8 3x3 960->960 48.6 -> 33.4 us with S = 9, but 1x1 layers
+  // (G = 15) and 16x16 maps (S = 2) lose to the extra finalize launch, so only long-K layers on <= 8x8 maps split
+  if ((long)d->Hout * d->Wout > 64 || d->Cout % 8) return 1;
+  const int G = conv_groups_total(d);
+  if (G < 36) return 1;
+  // work items a NOMINAL batch of 8 images would give without splitting (geometry only)
+  const long tiles8 = (long)cdiv(8 * d->Hout * d->Wout, 2 * kBM) * cdiv(d->Cout, pick_bn(d->Cout));
+  const int pairs = num_sms() / 2;
+  int S = (int)((pairs + tiles8 / 2) / tiles8);
+  S = std::min(S, std::min(16, G / 4));
+  return S < 4 ? 1 : S;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+splitk_finalize_kernel(const float *__restrict__ ws, int S, long long split_stride, const float *__restrict__ bias,
+                       const float *__restrict__ rowbias, int rowbias_stride, const T *__restrict__ residual,
+                       float res_scale, T *__restrict__ out, int HW, int C, int pix_per_block, double *__restrict__ sums) {
+  const int n = blockIdx.y;
+  const int ncol = C >> 3;
+  const int cpp = min(ncol, 256);
+  const int rows = 256 / cpp;
+  const int row = threadIdx.x / cpp;
+  const int p_begin = blockIdx.x * pix_per_block;
+  const int p_end = min(HW, p_begin + pix_per_block);
+  for (int cb = 0; cb < ncol; cb += cpp) {      // uniform trip count: the flush below has a barrier
+    const int col = cb + threadIdx.x % cpp;
+    const bool active = row < rows && col < ncol;
+    const int c0 = col * 8;
+    float bv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      bv[i] = (bias && active) ? bias[c0 + i] : 0.f;
+      if (rowbias && active) bv[i] += rowbias[(size_t)n * rowbias_stride + c0 + i];
+    }
+    float s[8] = {0}, q[8] = {0};
+    for (int p = p_begin + row; active && p < p_end; p += rows) {
+      const size_t off = ((size_t)n * HW + p) * C + c0;
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      for (int k = 0; k < S; ++k) {                 // fixed order: deterministic
+        const float4 a = *reinterpret_cast<const float4 *>(ws + (size_t)k * split_stride + off);
+        const float4 b = *reinterpret_cast<const float4 *>(ws + (size_t)k * split_stride + off + 4);
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+        v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += bv[i];
+      if (residual) {
+        float rf[8];
+        unpack8<T>(*reinterpret_cast<const uint4 *>(residual + off), rf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaf(res_scale, rf[i], v[i]);
+      }
+      const uint4 u = pack8_sat<T>(v);
+      *reinterpret_cast<uint4 *>(out + off) = u;
+      if (sums) {
+        unpack8<T>(u, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += v[i]; q[i] += v[i] * v[i]; }
+      }
+    }
+    if (sums) block_flush_col_sums(s, q, active, row, col % cpp, cpp, rows, sums + ((size_t)n * C + c0) * 2);
+    __syncthreads();
+  }
+}
+
 template <typename T, int kCtas, bool kFast>
-static int launch_conv(const b200_conv_desc *d, int bn, cudaStream_t stream) {
+static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t stream) {
   ConvKParams p{};
   ConvMaps maps{};
   p.N = d->N; p.Hout = d->Hout; p.Wout = d->Wout; p.Cout = d->Cout;
@@ -691,6 +796,13 @@ static int launch_conv(const b200_conv_desc *d, int bn, cudaStream_t stream) {
   p.vec32 = d->Cout % 16 == 0 && (((uintptr_t)d->out | (uintptr_t)d->residual) & 31) == 0 && !getenv("B200DIFF_NO_VEC32");
   p.out_f32 = d->out_nchw_f32; p.cout_real = d->cout_real; p.out_f32_nhwc = d->out_nhwc_f32;
   p.rowscale = d->rowscale; p.rowscale_stride = d->rowscale_stride; p.epi_act = d->epi_act;
+  p.ksplit = ksplit;
+  p.groups_total = conv_groups_total(d);
+  p.split_stride = (long long)d->N * d->Hout * d->Wout * d->Cout;
+  if (ksplit > 1) {       // partial planes only: the epilogue proper runs in splitk_finalize_kernel
+    p.out_f32_nhwc = reinterpret_cast<float *>(d->workspace);
+    p.out = nullptr; p.bias = nullptr; p.rowbias = nullptr; p.residual = nullptr; p.gn_sums = nullptr;
+  }
   // halo staging: 3x3 stride-1 pad-1 segments whose 128-pixel box lies in one image and is >= 8 pixels wide
   const bool halo_ok = d->stride == 1 && p.TN == 1 && p.TW >= 8 && !getenv("B200DIFF_NO_HALO");
   bool any_halo = false;
@@ -735,7 +847,7 @@ static int launch_conv(const b200_conv_desc *d, int bn, cudaStream_t stream) {
                                    226 * 1024));
     attr_set = true;
   }
-  const int grid = kCtas * std::min(p.num_tiles, num_sms() / kCtas);
+  const int grid = kCtas * std::min(p.num_tiles * p.ksplit, num_sms() / kCtas);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid, 1, 1);
   cfg.blockDim = dim3(kConvThreads, 1, 1);
@@ -750,6 +862,17 @@ static int launch_conv(const b200_conv_desc *d, int bn, cudaStream_t stream) {
   cfg.numAttrs = 1;
   B200_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<T, kCtas, kFast>, maps, p));
   B200_LAUNCH_CHECK();
+  if (ksplit > 1) {
+    const int HW = d->Hout * d->Wout;
+    const int cpp = std::min(d->Cout >> 3, 256), rows = 256 / cpp;
+    const int bps = std::max(1, std::min((num_sms() * 4) / std::max(d->N, 1), HW / rows));
+    const int ppb = cdiv(HW, bps);
+    splitk_finalize_kernel<T><<<dim3(cdiv(HW, ppb), d->N), 256, 0, stream>>>(
+        p.out_f32_nhwc, ksplit, p.split_stride, d->bias, d->rowbias, d->rowbias_stride, (const T *)d->residual, d->res_scale,
+        (T *)d->out, HW, d->Cout, ppb, d->gn_sums);
+    B200_LAUNCH_CHECK();
+    return 0;
+  }
   if (d->gn_sums && !p.gn_sums)
     return b200_channel_stats(d->out, d->N, d->Hout * d->Wout, d->Cout, d->gn_sums, d->act_dtype, stream);
   return 0;
@@ -771,6 +894,14 @@ extern "C" int b200_conv2d_igemm(const b200_conv_desc *d, void *stream) {
   static const bool force_one_cta = getenv("B200DIFF_CONV_1CTA") != nullptr;
   int ctas, bn;
   choose_tiling(d, &ctas, &bn);
+  int ksplit = conv_ksplit(d);
+  if (ksplit > 1) {
+    const size_t need = (size_t)ksplit * d->N * d->Hout * d->Wout * d->Cout * sizeof(float);
+    B200_CHECK(d->workspace != nullptr && d->workspace_bytes >= need && ((uintptr_t)d->workspace & 15) == 0,
+               "conv: this layer runs split-K (b200_conv_ksplit() = %d) and needs a %zu-byte workspace", ksplit, need);
+    ctas = 2;                       // biggest tiles: least operand traffic; the split supplies the parallelism
+    bn = pick_bn(d->Cout);
+  }
   const bool one_cta = force_one_cta || ctas == 1;
   const int kc = one_cta ? 1 : 2;
   // fast epilogue: 16-bit NHWC output, 32-byte aligned rows, every tile full, warp rows inside one image
@@ -781,16 +912,22 @@ extern "C" int b200_conv2d_igemm(const b200_conv_desc *d, void *stream) {
   const bool fast = !no_fast && d->out && !d->out_nchw_f32 && !d->out_nhwc_f32 && !d->epi_act && !d->rowscale &&
                     d->Cout % 16 == 0 && d->Cout % bn == 0 && (((uintptr_t)d->out | (uintptr_t)d->residual) & 31) == 0 &&
                     d->Wout % TW == 0 && d->Hout % TH == 0 && d->N % TN == 0 && ptiles % kc == 0 && TW * TH >= 32 &&
-                    !getenv("B200DIFF_SKIP_EPI") && !getenv("B200DIFF_NO_VEC32");
+                    !getenv("B200DIFF_SKIP_EPI") && !getenv("B200DIFF_NO_VEC32") && ksplit == 1;
 #define B200_CONV_DISPATCH(TT)                                                                           \
   do {                                                                                                   \
-    if (kc == 1) return fast ? launch_conv<TT, 1, true>(d, bn, (cudaStream_t)stream)                     \
-                             : launch_conv<TT, 1, false>(d, bn, (cudaStream_t)stream);                   \
-    return fast ? launch_conv<TT, 2, true>(d, bn, (cudaStream_t)stream)                                  \
-                : launch_conv<TT, 2, false>(d, bn, (cudaStream_t)stream);                                \
+    if (kc == 1) return fast ? launch_conv<TT, 1, true>(d, bn, ksplit, (cudaStream_t)stream)             \
+                             : launch_conv<TT, 1, false>(d, bn, ksplit, (cudaStream_t)stream);           \
+    return fast ? launch_conv<TT, 2, true>(d, bn, ksplit, (cudaStream_t)stream)                          \
+                : launch_conv<TT, 2, false>(d, bn, ksplit, (cudaStream_t)stream);                        \
   } while (0)
   if (d->act_dtype == B200_F16) B200_CONV_DISPATCH(__half);
   if (d->act_dtype == B200_BF16) B200_CONV_DISPATCH(__nv_bfloat16);
 #undef B200_CONV_DISPATCH
   B200_CHECK(false, "conv: bad act_dtype %d", d->act_dtype);
+}
+
+extern "C" int b200_conv_ksplit(const b200_conv_desc *d) {
+  using namespace b200;
+  if (d == nullptr || d->nseg < 1 || d->nseg > 3 || d->Hout <= 0 || d->Wout <= 0 || d->Cout <= 0) return 1;
+  return conv_ksplit(d);
 }

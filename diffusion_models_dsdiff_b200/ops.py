@@ -198,6 +198,11 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
         raise L.B200Error("conv2d: stats must be a zeroed float64 [N, Cout, 2] tensor")
     d.gn_sums = _p(stats)
     d.act_dtype = act_code(src0.dtype)
+    ks = L.lib().b200_conv_ksplit(C.byref(d))
+    if ks > 1:          # small maps run split-K: fp32 partial planes in a per-stream scratch buffer (never shared by
+        need = ks * out.numel() * 4          # two launches that may overlap)
+        ws = _workspace(src0.device, need)
+        d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
     kk = sum(sg[0].shape[3] * sg[3] * sg[3] for sg in segs)
     flops = 2.0 * n * hout * wout * cout * kk
     nbytes = 2.0 * (sum(sg[0].numel() for sg in segs) + out.numel() + cout * kk
@@ -207,6 +212,22 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
            None if _timer is None else
            f"{n}x{hout}x{wout} s{stride} " + "+".join(f"k{sg[3]}c{sg[0].shape[3]}" for sg in segs) + f" ->{cout}")
     return out
+
+
+_workspaces = {}
+
+
+def _workspace(device, nbytes: int) -> Tensor:
+    """Split-K scratch, one buffer per (device, stream): captured CUDA graphs keep raw pointers, so a buffer that was
+    ever handed out is never freed or shrunk — a larger request retires it into the keep-alive list."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    cur = _workspaces.get(key)
+    if cur is None or cur[0].numel() < nbytes:
+        size = max(nbytes, 32 << 20)
+        buf = torch.empty(size, dtype=torch.uint8, device=device)
+        _workspaces[key] = (buf, (cur[1] + [cur[0]]) if cur else [])
+        cur = _workspaces[key]
+    return cur[0]
 
 
 def conv3x3_in(x_nchw: Tensor, w_oihw: Tensor, bias: Optional[Tensor], dtype=torch.float16,

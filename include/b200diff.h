@@ -102,8 +102,15 @@ typedef struct {
   float *out_nhwc_f32;     /* optional: write the result as NHWC fp32 [N,Hout,Wout,Cout] INSTEAD of `out` (attention
                               logits q k^T of the KL-autoencoder AttnBlock, ldm/modules/diffusionmodules/model.py:186-189,
                               which must stay fp32 until the softmax); NULL otherwise                       */
+  void *workspace;          /* split-K scratch (fp32 partial tiles), >= b200_conv_ksplit(d) * N*Hout*Wout*Cout*4 bytes,
+                              16-byte aligned; only read / written by this call; may be NULL when the factor is 1      */
+  size_t workspace_bytes;
 } b200_conv_desc;
 int b200_conv2d_igemm(const b200_conv_desc *d, void *stream);
+/* split-K factor b200_conv2d_igemm will use for this descriptor (1 = none).  It depends on the layer geometry only
+ * (Hout, Wout, channels, kernel sizes; never on N), so one image's result is the same in any batch; the caller sizes
+ * `workspace` from it (the library never allocates).                                                                 */
+int b200_conv_ksplit(const b200_conv_desc *d);
 
 /* first conv of the network: tiny Cin (<= 8) read straight from NCHW fp32, writes NHWC act.
  * replaces input_blocks[0] conv (openaimodel.py:717) after DiffusionWrapper's concat
