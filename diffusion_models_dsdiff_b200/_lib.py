@@ -70,7 +70,7 @@ SIGNATURES = {
     "b200_groupnorm_stats": [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P],
     "b200_groupnorm_apply": [_P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _I, _I, _P, _I, _P],
     "b200_channel_stats": [_P, _I, _I, _I, _P, _I, _P],
-    "b200_groupnorm_apply_cs": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _I, _I, _P, _I, _P],
+    "b200_groupnorm_apply_cs": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _I, _I, _P, _P, _I, _I, _P],
     "b200_attention_qkv": [_P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
     "b200_attention": [C.POINTER(AttnDesc), _P],
     "b200_layernorm": [_P, _P, _P, _P, _P, _I, _I, _L, _I, _F, _P, _I, _P],

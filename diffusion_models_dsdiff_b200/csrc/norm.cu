@@ -190,7 +190,11 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
                 int groups, float eps, int pix_per_block, const double *__restrict__ stats,
                 const double *__restrict__ cs0, const double *__restrict__ cs1,
                 const float *__restrict__ gamma, const float *__restrict__ beta,
-                const float *__restrict__ film, int film_stride, int silu, T *__restrict__ out) {
+                const float *__restrict__ film, int film_stride, int silu, T *__restrict__ out,
+                const float *__restrict__ preshift, int preshift_stride) {
+  // preshift (optional, first source only): the tensor normalised is x0 + preshift[n, c] — a per-(image, channel)
+  // constant added on the fly (the timestep-embedding add of a ResBlock whose conv1 output is cached across steps); the
+  // producer's sums of x0 are corrected analytically: sum' = sum + HW s, sq' = sq + 2 s sum + HW s^2
   __shared__ float s_mean[kMaxGroups], s_rstd[kMaxGroups];
   const int n = blockIdx.y;
   const int C = C0 + C1;
@@ -212,7 +216,13 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
       } else {   // per-channel sums written by the producers' epilogues (conv / add4 / channel_stats)
         for (int c = g * cpg + sub; c < (g + 1) * cpg; c += tpg) {
           const double *src = c < C0 ? cs0 + ((size_t)n * C0 + c) * 2 : cs1 + ((size_t)n * C1 + (c - C0)) * 2;
-          sum += src[0]; sq += src[1];
+          double cs = src[0], cq = src[1];
+          if (preshift && c < C0) {
+            const double sh = (double)preshift[(size_t)n * preshift_stride + c];
+            cq += 2.0 * sh * cs + (double)HW * sh * sh;
+            cs += (double)HW * sh;
+          }
+          sum += cs; sq += cq;
         }
       }
     }
@@ -244,6 +254,7 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
       const float ga = gamma[c + i] * s_rstd[g];
       float aa = ga;
       float bb = beta[c + i] - s_mean[g] * ga;
+      if (preshift && c + i < C0) bb = fmaf(ga, preshift[(size_t)n * preshift_stride + c + i], bb);
       if (film) {
         const float sc = 1.f + film[(size_t)n * film_stride + c + i];
         const float sh = film[(size_t)n * film_stride + C + c + i];
@@ -311,13 +322,14 @@ static int gn_stats(const void *x0, int C0, const void *x1, int C1, int N, int H
 template <typename T>
 static int gn_apply(const void *x0, int C0, const void *x1, int C1, int N, int HW, int groups,
                     float eps, const double *stats, const double *cs0, const double *cs1, const float *gamma,
-                    const float *beta, const float *film, int film_stride, int silu, void *out, cudaStream_t st) {
+                    const float *beta, const float *film, int film_stride, int silu, void *out, cudaStream_t st,
+                    const float *preshift = nullptr, int preshift_stride = 0) {
   dim3 grid;
   int ppb;
   norm_grid(N, HW, std::min((C0 + C1) >> 3, kNormThreads), &grid, &ppb);
   gn_apply_kernel<T><<<grid, kNormThreads, 0, st>>>((const T *)x0, C0, (const T *)x1, C1, HW, groups,
                                                    eps, ppb, stats, cs0, cs1, gamma, beta, film, film_stride,
-                                                   silu, (T *)out);
+                                                   silu, (T *)out, preshift, preshift_stride);
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -359,15 +371,15 @@ extern "C" int b200_groupnorm_apply(const void *x0, int C0, const void *x1, int 
 extern "C" int b200_groupnorm_apply_cs(const void *x0, int C0, const double *cs0, const void *x1, int C1,
                                        const double *cs1, int N, int HW, int groups, float eps, const float *gamma,
                                        const float *beta, const float *film, int film_stride, int silu, void *out,
-                                       int act_dtype, void *stream) {
+                                       const float *preshift, int preshift_stride, int act_dtype, void *stream) {
   using namespace b200;
   if (x1 == nullptr) C1 = 0;
   if (int rc = check_gn(C0, C1, N, HW, groups)) return rc;
   B200_CHECK(cs0 != nullptr && (C1 == 0 || cs1 != nullptr), "groupnorm_apply_cs: missing channel sums");
   if (act_dtype == B200_F16)
-    return gn_apply<__half>(x0, C0, x1, C1, N, HW, groups, eps, nullptr, cs0, cs1, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream);
+    return gn_apply<__half>(x0, C0, x1, C1, N, HW, groups, eps, nullptr, cs0, cs1, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream, preshift, preshift_stride);
   if (act_dtype == B200_BF16)
-    return gn_apply<__nv_bfloat16>(x0, C0, x1, C1, N, HW, groups, eps, nullptr, cs0, cs1, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream);
+    return gn_apply<__nv_bfloat16>(x0, C0, x1, C1, N, HW, groups, eps, nullptr, cs0, cs1, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream, preshift, preshift_stride);
   B200_CHECK(false, "groupnorm: bad act_dtype");
 }
 

@@ -22,8 +22,8 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .unet import (Act, Ctx, _EngineModule, _f, _gn, build_unet_trunk, run_conv, run_gn, run_in_conv, run_out_head,
-                   run_sequential)
+from .unet import (Act, Ctx, ResBlock, _EngineModule, _f, _gn, build_unet_trunk, run_conv, run_gn, run_in_conv,
+                   run_out_head, run_resblock_conv1_raw, run_sequential)
 
 Tensor = torch.Tensor
 
@@ -69,6 +69,57 @@ class DSUnetModel(_EngineModule):
         self._init_engine()
         self.encoder_streams = os.environ.get("B200DIFF_ENCODER_STREAMS", "1") != "0"
         self._streams = {}
+        # loop-invariant prefix of the conditioning encoders (see prepare_conditioning)
+        self.hoist_conditioning = os.environ.get("B200DIFF_HOIST_COND", "1") != "0"
+        self._cond_caches = {}
+        self._cond_key = None
+
+    def invalidate(self):
+        super().invalidate()
+        self._cond_key = None
+
+    @torch.no_grad()
+    def prepare_conditioning(self, cond) -> bool:
+        """Called by the sampling loops once per run with the conditioning tensors they will concatenate to x_t at EVERY
+        step (DiffusionWrapper 'concat', ddpm.py:1331-1333).  The three conditioning encoders see the same input at every
+        step, and a ResBlock only meets the timestep after its first convolution (openaimodel.py:271-282), so
+        ``input_blocks_X[0]`` (first conv), and GN -> SiLU -> conv1 of ``input_blocks_X[1]`` are loop invariants: they
+        are evaluated here once per run — not 50 (or 2000) times — into persistent buffers that the per-step graph reads.
+        Each step then adds the bias + timestep term inside the next GroupNorm (statistics corrected analytically).
+        Exactly the reference's arithmetic up to the rounding point of the cached 16-bit tensor.  Returns True if the
+        cache is armed (``forward(..., cond_cached=True)`` will use it)."""
+        self._cond_key = None
+        if not self.hoist_conditioning or cond is None:
+            return False
+        cond = list(cond) if isinstance(cond, (list, tuple)) else [cond]
+        c = torch.cat([t.float() for t in cond], dim=1) if len(cond) > 1 else cond[0].float()
+        if c.dim() != 4 or c.shape[1] not in (1, 3) or not c.is_cuda:
+            return False
+        if not isinstance(self.input_blocks[1][0], ResBlock):
+            return False
+        pw = self.packed()
+        n = c.shape[0]
+        streams = [c[:, 0:1]] + ([c[:, 1:2], c[:, 2:3]] if c.shape[1] == 3 else [torch.zeros_like(c[:, 0:1])] * 2)
+        key = (n, c.shape[2], c.shape[3], self.act_dtype, c.device.index)
+        arena = ops.StatsArena()
+        arena.begin(c.device)
+        cx = Ctx(pw, None, arena)
+        fresh = []
+        for blocks, xin in zip((self.input_blocks_a, self.input_blocks_al, self.input_blocks_l), streams):
+            h0 = run_in_conv(cx, blocks[0][0], xin.contiguous(), self.act_dtype)
+            if h0.cs is None:
+                h0.cs = ops.channel_stats(h0.t, cx.stats_for(n, h0.t.shape[-1]))
+            c1 = run_resblock_conv1_raw(cx, blocks[1][0], h0)
+            fresh.append((h0, c1))
+        slot = self._cond_caches.get(key)
+        if slot is None:        # persistent buffers (captured graphs keep pointing at them); statistics outside the arena
+            slot = [(Act(h0.t.clone(), h0.cs.clone()), Act(c1.t.clone(), c1.cs.clone())) for h0, c1 in fresh]
+            self._cond_caches[key] = slot
+        else:
+            for (ph0, pc1), (h0, c1) in zip(slot, fresh):
+                ph0.t.copy_(h0.t); ph0.cs.copy_(h0.cs); pc1.t.copy_(c1.t); pc1.cs.copy_(c1.cs)
+        self._cond_key = key
+        return True
 
     def _side_streams(self, device):
         key = (device.type, device.index)
@@ -94,7 +145,7 @@ class DSUnetModel(_EngineModule):
 
     @torch.no_grad()
     def forward(self, x, timesteps=None, context=None, y=None, step_ptr: Optional[Tensor] = None,
-                return_features: bool = True, **kwargs):
+                return_features: bool = True, cond_cached: bool = False, **kwargs):
         assert (y is not None) == (self.num_classes is not None), \
             "must specify y if and only if the model is class-conditional"
         if context is not None:
@@ -110,10 +161,22 @@ class DSUnetModel(_EngineModule):
             inputs = [x[:, 0:1], x[:, 1:2], zero, zero]
         else:                     # :660-663
             inputs = [x[:, 0:1], x[:, 1:2], x[:, 2:3], x[:, 3:4]]
-        def encoder(blocks, xin):
-            h = run_in_conv(cx, blocks[0][0], xin.contiguous(), self.act_dtype)
-            hs = [h]
-            for blk in list(blocks)[1:]:
+        cached = None
+        if cond_cached and self._cond_key is not None and self._cond_key[:3] == (n, x.shape[2], x.shape[3]):
+            cached = self._cond_caches[self._cond_key]      # armed by prepare_conditioning() for THIS run's cond
+
+        def encoder(blocks, xin, pre=None):
+            if pre is not None:           # (first conv, conv1 of the first ResBlock) from the per-run cache
+                h, c1 = pre
+                hs = [h]
+                h = run_sequential(cx, blocks[1], h, None, conv1_raw=c1)
+                hs.append(h)
+                rest = list(blocks)[2:]
+            else:
+                h = run_in_conv(cx, blocks[0][0], xin.contiguous(), self.act_dtype)
+                hs = [h]
+                rest = list(blocks)[1:]
+            for blk in rest:
                 h = run_sequential(cx, blk, h, None)
                 hs.append(h)
             return hs
@@ -134,13 +197,14 @@ class DSUnetModel(_EngineModule):
             for i in (1, 2, 3):
                 with torch.cuda.stream(side[i - 1]):
                     side[i - 1].wait_event(ev0)
-                    skips[i] = encoder(enc_blocks[i], inputs[i])
+                    skips[i] = encoder(enc_blocks[i], inputs[i], None if cached is None else cached[i - 1])
                     ev = torch.cuda.Event()
                     ev.record(side[i - 1])
                     joins.append(ev)
             skips[0] = encoder(enc_blocks[0], inputs[0])
         else:
-            skips = [encoder(b, xin) for b, xin in zip(enc_blocks, inputs)]
+            skips = [encoder(b, xin, None if (cached is None or i == 0) else cached[i - 1])
+                     for i, (b, xin) in enumerate(zip(enc_blocks, inputs))]
         last = [hs[-1] for hs in skips]
         h_n = run_sequential(cx, self.middle_block, last[0], None)     # :688
         h_a, h_al, h_l = last[1], last[2], last[3]

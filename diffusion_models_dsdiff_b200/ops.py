@@ -301,7 +301,8 @@ def channel_stats(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
 
 def group_norm(x0: Tensor, gamma: Tensor, beta: Tensor, x1: Optional[Tensor] = None, groups: int = 32,
                eps: float = 1e-5, silu: bool = True, film: Optional[Tensor] = None,
-               stats: Optional[Tensor] = None, cs0: Optional[Tensor] = None, cs1: Optional[Tensor] = None) -> Tensor:
+               stats: Optional[Tensor] = None, cs0: Optional[Tensor] = None, cs1: Optional[Tensor] = None,
+               preshift: Optional[Tensor] = None) -> Tensor:
     """GroupNorm(+FiLM)(+SiLU) of the channel concatenation [x0 | x1]; NHWC in, NHWC out.
 
     With ``cs0`` (and ``cs1`` when ``x1`` is given) — the producers' per-channel sums — this is ONE read + ONE write
@@ -316,12 +317,18 @@ def group_norm(x0: Tensor, gamma: Tensor, beta: Tensor, x1: Optional[Tensor] = N
     out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=x0.dtype)
     film_p = None if film is None else film.data_ptr()
     film_s = 0 if film is None or film.shape[0] == 1 else film.stride(0)   # [1, 2C]: shared by the batch
+    ps_p, ps_s = None, 0
+    if preshift is not None:      # x0 + preshift[n, c] is what gets normalised (cached-conv1 ResBlocks); fp32 [N or 1, C0]
+        if cs0 is None or _f32(preshift).stride(-1) != 1 or preshift.shape[-1] != c0 or preshift.shape[0] not in (1, n):
+            raise L.B200Error("group_norm: preshift must be fp32 [N or 1, C0] and needs the producer's channel sums")
+        ps_p = preshift.data_ptr()
+        ps_s = preshift.stride(0) if preshift.shape[0] == n and n > 1 else 0
     if cs0 is not None and (x1 is None or cs1 is not None):
         _timed("groupnorm_silu", 0.0, 2.0 * 2.0 * out.numel(),
                detail=f"{n}x{hw} c{c0}+{c1}", launch=
                lambda: L.check(lib.b200_groupnorm_apply_cs(_p(x0), c0, _p(cs0), _p(x1), c1, _p(cs1), n, hw, groups, eps,
                                                            _p(_f32(gamma)), _p(_f32(beta)), film_p, film_s, int(silu),
-                                                           _p(out), code, _stream()), "groupnorm_apply_cs"))
+                                                           _p(out), ps_p, ps_s, code, _stream()), "groupnorm_apply_cs"))
         return out
     if stats is None:
         stats = torch.zeros((n, groups, 2), device=x0.device, dtype=torch.float64)

@@ -155,7 +155,8 @@ class StepEngine:
 
     def __init__(self, model_fn: Callable, mode: int, param: int, coef: Tensor, t_table: Tensor,
                  clip_denoised: bool, learned_range: bool = False, cache: Optional[dict] = None, cache_key=None,
-                 keepalive=None, prepare: Optional[Callable] = None, context: Optional[Tensor] = None,
+                 keepalive=None, prepare: Optional[Callable] = None, prepare_cond: Optional[Callable] = None,
+                 context: Optional[Tensor] = None,
                  thresholding: Optional[Tuple[float, float]] = None, cfg_scale: float = 1.0,
                  uncond: Optional[Sequence[Tensor]] = None, uncond_context: Optional[Tensor] = None):
         self.model_fn, self.mode, self.param = model_fn, mode, param
@@ -173,6 +174,8 @@ class StepEngine:
         # cache_key must change whenever the network's packed weights do, keepalive pins them
         self.cache, self.cache_key, self.keepalive = cache, cache_key, keepalive
         self.prepare = prepare
+        self.prepare_cond = prepare_cond  # loop-invariant conditioning prefix of the network, once per run
+        self.model_kwargs: dict = {}
         self.context = context          # cross-attention conditioning [B, Lk, D], constant over the steps
         self.stats: dict = {}
 
@@ -188,16 +191,16 @@ class StepEngine:
             if self.context is not None:
                 uctx = self.uncond_context if self.uncond_context is not None else self.context
                 kw["context"] = torch.cat([uctx, self.context], dim=0)
-            out = self.model_fn(x2, self.t_table, step_ptr, **kw)
+            out = self.model_fn(x2, self.t_table, step_ptr, **kw, **self.model_kwargs)
             if isinstance(out, tuple):
                 out = out[0]
             out = ops.cfg_combine(out[:n].contiguous(), out[n:].contiguous(), self.cfg_scale)
         else:
             xc = x if not cond else torch.cat([x] + list(cond), dim=1)
             if self.context is not None:
-                out = self.model_fn(xc, self.t_table, step_ptr, context=self.context)
+                out = self.model_fn(xc, self.t_table, step_ptr, context=self.context, **self.model_kwargs)
             else:
-                out = self.model_fn(xc, self.t_table, step_ptr)
+                out = self.model_fn(xc, self.t_table, step_ptr, **self.model_kwargs)
             if isinstance(out, tuple):
                 out = out[0]
         if self.mode == L.SAMPLER_DPMPP_2M:      # deterministic ODE solver: no noise is drawn (dpm_solver_pytorch.py)
@@ -231,6 +234,14 @@ class StepEngine:
         step_ptr = torch.zeros(1, dtype=torch.int32, device=dev)
         if self.prepare is not None:       # timestep MLP + emb projections for ALL steps, once per loop
             self.prepare(self.t_table)
+        self.model_kwargs = {}
+        if self.prepare_cond is not None and cond:
+            cc = list(cond)
+            if self.cfg:                   # the network runs on [uncond; cond] (see _one)
+                unc = self.uncond if self.uncond is not None else cc
+                cc = [torch.cat([u.to(dev), c.to(dev)], dim=0) for u, c in zip(unc, cc)]
+            if self.prepare_cond(cc):
+                self.model_kwargs = {"cond_cached": True}
         if self.mode == L.SAMPLER_DPMPP_2M:
             self._dpm = {"hist": torch.zeros_like(x), "x0": torch.empty_like(x),
                          "thr": torch.ones(x.shape[0], dtype=torch.float32, device=dev)}
@@ -248,6 +259,7 @@ class StepEngine:
         key = None
         if self.cache is not None:
             key = (self.cache_key, self.mode, self.param, self.clip, self.learned_range, self.thresholding, self.cfg,
+                   bool(self.model_kwargs),
                    self.cfg_scale, tuple(x.shape),
                    tuple(tuple(c.shape) for c in (cond or [])), steps, want_x0,
                    None if self.context is None else tuple(self.context.shape))
@@ -328,7 +340,7 @@ def _engine_model_fn(net):
 def _graph_cache_args(cache: dict, net) -> dict:
     pw = net.packed() if hasattr(net, "packed") else None
     return {"cache": cache, "cache_key": (id(net), id(pw)), "keepalive": pw,
-            "prepare": getattr(net, "prepare_steps", None)}
+            "prepare": getattr(net, "prepare_steps", None), "prepare_cond": getattr(net, "prepare_conditioning", None)}
 
 
 # ---------------------------------------------------------------------------------------------

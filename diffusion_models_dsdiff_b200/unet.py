@@ -128,7 +128,12 @@ class PackedWeights:
             if isinstance(m, ResBlock):
                 lin = m.emb_layers[1]
                 emb_w.append(lin.weight.detach().float())
-                emb_b.append(lin.bias.detach().float())
+                eb = lin.bias.detach().float()
+                if not m.use_scale_shift_norm:
+                    # h = conv1(.) + b1 + Linear(SiLU(emb)) (openaimodel.py:271-282): b1 rides in the projection's bias,
+                    # so the per-(n, c) row the conv epilogue (or the cached-conv1 GroupNorm) adds is the whole term
+                    eb = eb + m.in_layers[2].bias.detach().float()
+                emb_b.append(eb)
                 self.emb_slices[id(m)] = (off, lin.weight.shape[0])
                 off += lin.weight.shape[0]
                 b2 = m.out_layers[3].bias.detach().float()
@@ -183,21 +188,38 @@ def run_conv(cx: Ctx, segs, want_stats: bool = True, **kw) -> Act:
     return Act(ops.conv2d(segs, stats=st, **kw), st)
 
 
-def run_resblock(cx: Ctx, m: ResBlock, x0: Act, x1: Optional[Act]) -> Act:
-    """ResBlock._forward (openaimodel.py:264-284) on NHWC activations; input = cat([x0, x1], C)."""
+def run_resblock_conv1_raw(cx: Ctx, m: ResBlock, x0: Act) -> Act:
+    """conv1(SiLU(GN(x0))) WITHOUT bias / timestep term: the part of a ResBlock that does not depend on the timestep.
+    When x0 is loop-invariant across sampling steps (the DS-Diff conditioning streams) it is computed once per run."""
+    a = run_gn(cx, m.in_layers[0], x0, None)
+    return run_conv(cx, [(a, cx.pw.conv[id(m.in_layers[2])], 0, 3, 1)])
+
+
+def run_resblock(cx: Ctx, m: ResBlock, x0: Act, x1: Optional[Act], conv1_raw: Optional[Act] = None) -> Act:
+    """ResBlock._forward (openaimodel.py:264-284) on NHWC activations; input = cat([x0, x1], C).
+    ``conv1_raw``: cached output of ``run_resblock_conv1_raw`` for this x0 — GN1 and conv1 are skipped and the bias +
+    timestep term is added on the fly inside the second GroupNorm (its statistics are corrected analytically)."""
     if m.up or m.down:
         raise NotImplementedError("resblock_updown=True is not supported by the B200 engine yet")
     pw = cx.pw
     gin, gout = m.in_layers[0], m.out_layers[0]
-    a = run_gn(cx, gin, x0, x1)
     off, width = pw.emb_slices[id(m)]
     emb_out = cx.emb_all[:, off:off + width]
     conv1, conv2 = m.in_layers[2], m.out_layers[3]
-    if m.use_scale_shift_norm:
+    if conv1_raw is not None:
+        if m.use_scale_shift_norm:      # h = conv1 + b1 is timestep-free; only the FiLM modulation varies
+            a2 = ops.group_norm(conv1_raw.t, _f(gout.weight), _f(gout.bias), groups=gout.num_groups, eps=gout.eps,
+                                film=emb_out, cs0=conv1_raw.cs, preshift=_f(conv1.bias).view(1, -1))
+        else:
+            a2 = ops.group_norm(conv1_raw.t, _f(gout.weight), _f(gout.bias), groups=gout.num_groups, eps=gout.eps,
+                                cs0=conv1_raw.cs, preshift=emb_out)
+    elif m.use_scale_shift_norm:
+        a = run_gn(cx, gin, x0, x1)
         h = run_conv(cx, [(a, pw.conv[id(conv1)], 0, 3, 1)], bias=_f(conv1.bias))
         a2 = run_gn(cx, gout, h, film=emb_out)
     else:
-        h = run_conv(cx, [(a, pw.conv[id(conv1)], 0, 3, 1)], bias=_f(conv1.bias), rowbias=emb_out)
+        a = run_gn(cx, gin, x0, x1)
+        h = run_conv(cx, [(a, pw.conv[id(conv1)], 0, 3, 1)], rowbias=emb_out)      # b1 is folded into emb_out
         a2 = run_gn(cx, gout, h)
     segs = [(a2, pw.conv[id(conv2)], 0, 3, 1)]
     residual = None
@@ -242,12 +264,13 @@ def run_spatial_transformer(cx: Ctx, m: "tfm.SpatialTransformer", x: Act) -> Act
     return run_conv(cx, [(t.view(n, h, w, -1), wout, 0, 1, 0)], bias=_f(m.proj_out.bias), residual=x.t)
 
 
-def run_sequential(cx: Ctx, seq: nn.Sequential, x0: Act, x1: Optional[Act]) -> Act:
-    """TimestepEmbedSequential.forward (openaimodel.py:80-90)."""
+def run_sequential(cx: Ctx, seq: nn.Sequential, x0: Act, x1: Optional[Act], conv1_raw: Optional[Act] = None) -> Act:
+    """TimestepEmbedSequential.forward (openaimodel.py:80-90).  ``conv1_raw``: cached first-ResBlock prefix (see
+    run_resblock); only valid when the sequential starts with a ResBlock."""
     pw = cx.pw
-    for layer in seq:
+    for li, layer in enumerate(seq):
         if isinstance(layer, ResBlock):
-            x0, x1 = run_resblock(cx, layer, x0, x1), None
+            x0, x1 = run_resblock(cx, layer, x0, x1, conv1_raw if li == 0 else None), None
             continue
         if x1 is not None:
             x0, x1 = Act(torch.cat([x0.t, x1.t], dim=-1)), None

@@ -136,12 +136,15 @@ int b200_groupnorm_apply(const void *x0, int C0, const void *x1, int C1, int N, 
 
 /* Producer-side statistics: sums[N][C][2] fp64 = per-(image, channel) sum and sum of squares, accumulated (zero first).
  * b200_conv2d_igemm fills the same layout from its epilogue (gn_sums); b200_groupnorm_apply_cs reduces the channel
- * sums of the two concatenated sources to group statistics itself, so a GroupNorm is ONE read + ONE write pass. */
+ * sums of the two concatenated sources to group statistics itself, so a GroupNorm is ONE read + ONE write pass.
+ * preshift (may be NULL): fp32 [N or 1][C0] row pitch preshift_stride (0 = one row for the batch): the tensor normalised
+ * is x0 + preshift[n, c]; the sums of x0 are corrected analytically.  Used for `h + emb_out` of ResBlock._forward
+ * (openaimodel.py:282) when conv1's output is loop-invariant across sampling steps and cached.                       */
 int b200_channel_stats(const void *x, int N, int HW, int C, double *sums, int act_dtype, void *stream);
 int b200_groupnorm_apply_cs(const void *x0, int C0, const double *cs0, const void *x1, int C1,
                             const double *cs1, int N, int HW, int groups, float eps, const float *gamma,
                             const float *beta, const float *film, int film_stride, int silu, void *out,
-                            int act_dtype, void *stream);
+                            const float *preshift, int preshift_stride, int act_dtype, void *stream);
 
 /* ---- attention -------------------------------------------------------------------------------
  * replaces QKVAttention / QKVAttentionLegacy (openaimodel.py:537-555 / 505-521): fused

@@ -388,3 +388,38 @@ def test_ddim_classifier_free_guidance_matches_reference():
     out_g, _ = S.DDIMSampler(m).sample(g["S"], 2, (1, 32, 32), g["cond"].cuda(), eta=0.0, x_T=g["x_T"].cuda(), verbose=False,
                                        unconditional_guidance_scale=g["scale"], unconditional_conditioning=g["uncond"].cuda())
     assert maxabs(out_g, out) < 1e-6        # CUDA-graph path == eager path (eta = 0: the drawn noise is multiplied by 0)
+
+
+@pytest.mark.parametrize("case", ["ds_small", "ds_film2"])
+def test_dsdiff_loop_invariant_conditioning_prefix(case):
+    """DSUnetModel.prepare_conditioning: the conditioning encoders' first conv + GN/conv1 of their first ResBlock are
+    evaluated once per sampling run; each step adds bias + timestep term inside the next GroupNorm.  Same result as
+    recomputing them every step up to the rounding point of one cached 16-bit tensor.  That single early rounding change
+    decorrelates the network's (chaotic) roundoff, so the two results differ from EACH OTHER by about as much as each differs
+    from the fp32 reference (measured on ds_small: 1.47e-3 and 1.46e-3 vs the golden, 1.34e-3 between them): the bound is
+    the per-step tolerance, and accuracy against the reference is unchanged."""
+    import diffusion_models_dsdiff_b200 as P
+    hp, sd, net = _net(case, torch.float16, P.DSUnetModel)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 4, 32, 32, generator=gen).cuda()
+    t_table = torch.tensor([900.0, 37.5], device="cuda")
+    step = torch.tensor([1], dtype=torch.int32, device="cuda")
+    full, _ = net(x, t_table, step_ptr=step, return_features=False)
+    assert net.prepare_conditioning([x[:, 1:]])
+    hoisted, _ = net(x, t_table, step_ptr=step, return_features=False, cond_cached=True)
+    n0 = P.launch_count(); net(x, t_table, step_ptr=step, return_features=False); n_full = P.launch_count() - n0
+    n0 = P.launch_count(); net(x, t_table, step_ptr=step, return_features=False, cond_cached=True); n_h = P.launch_count() - n0
+    assert n_h <= n_full - 6                                   # 3 streams x (first conv, GN, conv1) fewer launches
+    assert O.rel_err(hoisted, full) < REL_TOL[torch.float16]
+    if case == "ds_small":                                     # accuracy vs the reference's fp32 output is unchanged
+        g = golden("ds_small")
+        net.prepare_conditioning([g["x"][:, 1:].cuda()])
+        y_h, _ = net(g["x"].cuda(), g["t"].cuda(), return_features=False, cond_cached=True)
+        y_f, _ = net(g["x"].cuda(), g["t"].cuda(), return_features=False)
+        e_h, e_f = O.rel_err(y_h.cpu(), g["y"]), O.rel_err(y_f.cpu(), g["y"])
+        assert e_h < REL_TOL[torch.float16] and e_h < 1.15 * e_f
+    other = x.clone(); other[:, 1:] = x[:, 1:].flip(0) * 0.7   # a different conditioning re-arms the same buffers
+    assert net.prepare_conditioning([other[:, 1:]])
+    ref2, _ = net(other, t_table, step_ptr=step, return_features=False)
+    got2, _ = net(other, t_table, step_ptr=step, return_features=False, cond_cached=True)
+    assert O.rel_err(got2, ref2) < REL_TOL[torch.float16]

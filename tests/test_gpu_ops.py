@@ -316,3 +316,25 @@ def test_elementwise(dt):
     close(nchw(y), x * gate[:, :, None, None], dt, "se_attention")
     back = ops.nhwc_to_nchw(ops.nchw_to_nhwc(x.cuda(), 40, dt), 32).cpu()
     assert torch.equal(back, x)
+
+
+@pytest.mark.parametrize("batch_rows", [True, False])
+def test_groupnorm_preshift_matches_shifted_input(batch_rows):
+    """GroupNorm of (x0 + per-(n, c) constant) with the statistics corrected analytically from x0's channel sums."""
+    ops = _ops()
+    dt = torch.float16
+    n, c, h, w = 2, 96, 16, 16
+    x = q(rnd(1, n, c, h, w) * 1.3, dt)
+    s = rnd(2, n if batch_rows else 1, c) * 0.8
+    g, b = 1 + 0.1 * rnd(3, c), 0.1 * rnd(4, c)
+    ref = F.silu(F.group_norm(x + s[:, :, None, None], 32, g, b, 1e-5))
+    a = nhwc(x, dt)
+    wide = torch.zeros(s.shape[0], 3 * c + 8)          # preshift as a column slice of a wider matrix (like emb_all)
+    wide[:, 8:8 + c] = s
+    wide = wide.cuda()
+    y = ops.group_norm(a, g.cuda(), b.cuda(), cs0=ops.channel_stats(a), preshift=wide[:, 8:8 + c])
+    close(nchw(y), ref, dt, "gn preshift")
+    film = rnd(5, n, 2 * c, scale=0.5).cuda()
+    ref2 = F.silu(F.group_norm(x + s[:, :, None, None], 32, g, b, 1e-5) * (1 + film.cpu()[:, :c, None, None]) + film.cpu()[:, c:, None, None])
+    y2 = ops.group_norm(a, g.cuda(), b.cuda(), cs0=ops.channel_stats(a), preshift=wide[:, 8:8 + c], film=film)
+    close(nchw(y2), ref2, dt, "gn preshift + film")
