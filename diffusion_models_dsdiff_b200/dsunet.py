@@ -124,7 +124,7 @@ class DSUnetModel(_EngineModule):
     def _side_streams(self, device):
         key = (device.type, device.index)
         if key not in self._streams:
-            self._streams[key] = [torch.cuda.Stream(device=device) for _ in range(3)]
+            self._streams[key] = [torch.cuda.Stream(device=device) for _ in range(4)]
         return self._streams[key]
 
     # FeatureDisentangle.forward (:165-168): conv_2(conv_1(x) + x)
@@ -206,6 +206,26 @@ class DSUnetModel(_EngineModule):
             skips = [encoder(b, xin, None if (cached is None or i == 0) else cached[i - 1])
                      for i, (b, xin) in enumerate(zip(enc_blocks, inputs))]
         last = [hs[-1] for hs in skips]
+
+        def skip_mean(level_acts):
+            s0 = level_acts[0].t
+            st = cx.stats_for(s0.shape[0], s0.shape[-1])
+            return Act(ops.add4_scale_stats(s0, level_acts[1].t, level_acts[2].t, level_acts[3].t, 0.25, st), st)  # :745
+
+        skip_means = None
+        if fork and os.environ.get("B200DIFF_SKIP_MEAN_STREAM", "1") != "0":
+            # the decoder's skip inputs (mean of the four encoders' skips) only need the encoders: all of them are computed
+            # on a fourth stream right away, so these HBM-bound passes overlap the latency-bound 8x8 middle block and feature
+            # heads instead of sitting between the decoder's convolutions
+            ev_enc = torch.cuda.Event()
+            ev_enc.record(main)                      # the noise encoder (and everything before it) on the main stream
+            with torch.cuda.stream(side[3]):
+                side[3].wait_event(ev_enc)
+                for ev in joins:
+                    side[3].wait_event(ev)
+                skip_means = [skip_mean([skips[e][lvl] for e in range(4)]) for lvl in range(len(skips[0]))]
+                ev_means = torch.cuda.Event()
+                ev_means.record(side[3])
         h_n = run_sequential(cx, self.middle_block, last[0], None)     # :688
         h_a, h_al, h_l = last[1], last[2], last[3]
         fd = lambda m, v: self._fd(cx, m, v)
@@ -252,10 +272,13 @@ class DSUnetModel(_EngineModule):
         cat = torch.cat([h_n.t, h_share, h_style, h_anat, h_les], dim=-1)          # :734 (8x8 maps: tiny)
         ap = self.all_proj[1]
         h = run_conv(cx, [(ops.add4_scale(cat, silu=True), pw.conv[id(ap)], 0, 1, 0)], bias=_f(ap.bias))   # :738
+        if skip_means is not None:
+            main.wait_event(ev_means)
         for blk in self.output_blocks:
-            s0 = skips[0].pop().t
-            st = cx.stats_for(s0.shape[0], s0.shape[-1])
-            skip = Act(ops.add4_scale_stats(s0, skips[1].pop().t, skips[2].pop().t, skips[3].pop().t, 0.25, st), st)  # :745
+            if skip_means is not None:
+                skip = skip_means.pop()
+            else:
+                skip = skip_mean([skips[e].pop() for e in range(4)])
             h = run_sequential(cx, blk, h, skip)
         out = run_out_head(cx, self.out, h).to(x.dtype)
         if not return_features:
