@@ -865,7 +865,7 @@ static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t
   if (ksplit > 1) {
     const int HW = d->Hout * d->Wout;
     const int cpp = std::min(d->Cout >> 3, 256), rows = 256 / cpp;
-    const int bps = std::max(1, std::min((num_sms() * 4) / std::max(d->N, 1), HW / rows));
+    const int bps = std::max(1, std::min(num_sms(), HW / rows));       // independent of N (bit-identical statistics)
     const int ppb = cdiv(HW, bps);
     splitk_finalize_kernel<T><<<dim3(cdiv(HW, ppb), d->N), 256, 0, stream>>>(
         p.out_f32_nhwc, ksplit, p.split_stride, d->bias, d->rowbias, d->rowbias_stride, (const T *)d->residual, d->res_scale,

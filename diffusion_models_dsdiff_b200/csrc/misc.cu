@@ -484,7 +484,8 @@ extern "C" int b200_conv3x3_in(const float *x, const float *w, const float *bias
   B200_CHECK(smem <= 200 * 1024, "conv3x3_in: weights do not fit shared memory");
   const int HW = H * W;
   const int rows = std::max(1, 256 / (Cout >> 3));
-  int bps = std::max(1, std::min((num_sms() * 4) / std::max(N, 1), HW / (rows * 4)));
+  // pixel partition independent of N: the fused statistics of an image are bit-identical in any batch
+  int bps = std::max(1, std::min(num_sms(), HW / (rows * 4)));
   const int ppb = cdiv(HW, bps);
   const dim3 grid(cdiv(HW, ppb), N, 1);
   DISPATCH_ACT(act_dtype, {

@@ -297,6 +297,15 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
   }
 }
 
+// Kernels that PRODUCE statistics (fp32 per-thread partial sums) split an image's pixels the same way whatever the batch
+// size, so an image's sums — and everything downstream — are bit-identical in any batch.
+static void stats_grid(int N, int HW, int ncol, dim3 *grid, int *pix_per_block) {
+  const int rows = std::max(1, kNormThreads / std::max(ncol, 1));
+  const int bps = std::max(1, std::min(num_sms(), HW / (rows * 4)));
+  *pix_per_block = cdiv(HW, bps);
+  *grid = dim3(cdiv(HW, *pix_per_block), N, 1);
+}
+
 static void norm_grid(int N, int HW, int ncol, dim3 *grid, int *pix_per_block) {
   const int rows = std::max(1, kNormThreads / std::max(ncol, 1));
   int target_blocks = std::max(1, (num_sms() * 4) / std::max(N, 1));   // one resident wave (4 CTAs of 256 threads per SM)
@@ -312,7 +321,7 @@ static int gn_stats(const void *x0, int C0, const void *x1, int C1, int N, int H
                     double *stats, cudaStream_t st) {
   dim3 grid;
   int ppb;
-  norm_grid(N, HW, std::max(C0, C1) >> 3, &grid, &ppb);
+  stats_grid(N, HW, std::max(C0, C1) >> 3, &grid, &ppb);
   gn_stats_kernel<T><<<grid, kNormThreads, 0, st>>>((const T *)x0, C0, (const T *)x1, C1, HW, groups,
                                                    ppb, stats);
   B200_LAUNCH_CHECK();
@@ -390,7 +399,7 @@ extern "C" int b200_add4_scale_stats(const void *a, const void *b, const void *c
              "add4_scale_stats: bad arguments");
   dim3 grid;
   int ppb;
-  norm_grid(N, HW, C >> 3, &grid, &ppb);
+  stats_grid(N, HW, C >> 3, &grid, &ppb);
   if (act_dtype == B200_F16)
     add4_stats_kernel<__half><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(
         (const __half *)a, (const __half *)b, (const __half *)c, (const __half *)d, scale, (__half *)dst, C, HW, ppb, sums);
@@ -409,7 +418,7 @@ extern "C" int b200_channel_stats(const void *x, int N, int HW, int C, double *s
   B200_CHECK(x && sums && N > 0 && HW > 0 && C > 0 && C % 8 == 0 && C <= 8 * kNormThreads, "channel_stats: bad arguments");
   dim3 grid;
   int ppb;
-  norm_grid(N, HW, C >> 3, &grid, &ppb);
+  stats_grid(N, HW, C >> 3, &grid, &ppb);
   if (act_dtype == B200_F16)
     channel_stats_kernel<__half><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>((const __half *)x, C, HW, ppb, sums);
   else if (act_dtype == B200_BF16)

@@ -423,3 +423,30 @@ def test_dsdiff_loop_invariant_conditioning_prefix(case):
     ref2, _ = net(other, t_table, step_ptr=step, return_features=False)
     got2, _ = net(other, t_table, step_ptr=step, return_features=False, cond_cached=True)
     assert O.rel_err(got2, ref2) < REL_TOL[torch.float16]
+
+
+@pytest.mark.parametrize("workload", ["cfg1", "cfg2"])
+def test_full_size_determinism_and_batch_independence(workload):
+    """Size-independent properties at BASELINE's full slice size: the same input gives the same bits twice, and a slice's
+    result does not depend on the batch it is sampled in (tile shapes / split-K / statistics partitions never depend on
+    N; forked streams, fp64 statistic atomics) — the property that makes sharded sampling independent of the world size."""
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import diffusion_models_dsdiff_b200 as P
+    wl = bench.WORKLOADS[workload]
+    torch.manual_seed(0)
+    with torch.device("cuda"):
+        net = getattr(P, wl["cls"])(**wl["hp"]).eval()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    with torch.no_grad():
+        for p_ in net.parameters():
+            if p_.numel() and not bool(p_.any()):
+                p_.copy_(torch.randn(p_.shape, generator=g, device="cuda") * 0.02)
+    net.invalidate()
+    x = torch.randn(3, 4, 256, 256, device="cuda")
+    t = torch.full((3,), 801, device="cuda")
+    f = lambda xx, tt: (lambda o: o[0] if isinstance(o, tuple) else o)(net(xx, tt))
+    y1, y2, y0 = f(x, t), f(x, t), f(x[:1], t[:1])
+    assert torch.equal(y1, y2)
+    assert torch.equal(y0, y1[:1])
