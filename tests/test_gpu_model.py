@@ -352,6 +352,11 @@ def test_full_size_network_forward_vs_oracle(workload):
     assert ref.abs().max() > 1e-3
     rel = O.rel_err(got, ref)
     assert rel < REL_TOL[torch.float16], f"{workload} full-size rel err {rel:.3e}"
+    if hasattr(net, "prepare_conditioning"):        # the step as the samplers run it: conditioning prefix hoisted
+        assert net.prepare_conditioning([cond.cuda()])
+        got_h = net(xc.cuda(), ts.cuda(), cond_cached=True)[0].cpu()
+        rel_h = O.rel_err(got_h, ref)
+        assert rel_h < REL_TOL[torch.float16], f"{workload} full-size (hoisted) rel err {rel_h:.3e}"
 
 
 def test_sample_volume_batch_split_independent_on_gpu():
