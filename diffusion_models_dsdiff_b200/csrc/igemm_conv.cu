@@ -56,6 +56,7 @@ struct ConvKParams {
   int ksplit;                // > 1: split-K, every (tile, split) item writes an fp32 partial tile to the workspace
   int groups_total;          // pipeline groups of one tile's K loop (split s takes [s*G/S, (s+1)*G/S))
   long long split_stride;    // floats between consecutive partial planes of the workspace
+  int pdl;                   // launched with programmatic stream serialization (B200DIFF_PDL=1)
   int vec32;                 // Cout % 16 == 0 and 32-byte aligned out / residual: 256-bit epilogue loads / stores
 };
 
@@ -213,6 +214,13 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
   if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  // programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the
+  // tail of the previous kernel in the stream; nothing below may start before that kernel's results are visible.  The
+  // next kernel is released at once — it blocks at its own griddepcontrol.wait until this grid has completed.
+  if (p.pdl) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
 
   // A pipeline stage is a GROUP of work, identical for the producer and the MMA issuer, per tile and segment:
   //   halo segment : for c0 (64-channel chunk) / for sx (column shift): ONE activation box of (TH+2) rows + the THREE
@@ -853,13 +861,17 @@ static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t
   cfg.blockDim = dim3(kConvThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  static const bool pdl = getenv("B200DIFF_PDL") != nullptr && getenv("B200DIFF_PDL")[0] == '1';
+  p.pdl = pdl;
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCtas;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   B200_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<T, kCtas, kFast>, maps, p));
   B200_LAUNCH_CHECK();
   if (ksplit > 1) {

@@ -191,7 +191,11 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
                 const double *__restrict__ cs0, const double *__restrict__ cs1,
                 const float *__restrict__ gamma, const float *__restrict__ beta,
                 const float *__restrict__ film, int film_stride, int silu, T *__restrict__ out,
-                const float *__restrict__ preshift, int preshift_stride) {
+                const float *__restrict__ preshift, int preshift_stride, int pdl) {
+  if (pdl) {      // programmatic dependent launch (see igemm_conv.cu): wait for the producer, release the consumer
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
   // preshift (optional, first source only): the tensor normalised is x0 + preshift[n, c] — a per-(image, channel)
   // constant added on the fly (the timestep-embedding add of a ResBlock whose conv1 output is cached across steps); the
   // producer's sums of x0 are corrected analytically: sum' = sum + HW s, sq' = sq + 2 s sum + HW s^2
@@ -336,9 +340,18 @@ static int gn_apply(const void *x0, int C0, const void *x1, int C1, int N, int H
   dim3 grid;
   int ppb;
   norm_grid(N, HW, std::min((C0 + C1) >> 3, kNormThreads), &grid, &ppb);
-  gn_apply_kernel<T><<<grid, kNormThreads, 0, st>>>((const T *)x0, C0, (const T *)x1, C1, HW, groups,
-                                                   eps, ppb, stats, cs0, cs1, gamma, beta, film, film_stride,
-                                                   silu, (T *)out, preshift, preshift_stride);
+  static const bool pdl = getenv("B200DIFF_PDL") != nullptr && getenv("B200DIFF_PDL")[0] == '1';
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kNormThreads, 1, 1);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, gn_apply_kernel<T>, (const T *)x0, C0, (const T *)x1, C1, HW, groups, eps, ppb, stats, cs0,
+                               cs1, gamma, beta, film, film_stride, silu, (T *)out, preshift, preshift_stride, (int)pdl));
   B200_LAUNCH_CHECK();
   return 0;
 }
