@@ -351,7 +351,10 @@ def test_full_size_network_forward_vs_oracle(workload):
     got = (got[0] if isinstance(got, tuple) else got).cpu()
     assert ref.abs().max() > 1e-3
     rel = O.rel_err(got, ref)
-    assert rel < REL_TOL[torch.float16], f"{workload} full-size rel err {rel:.3e}"
+    # cfg1 (BASELINE configs[0]) meets north_star's 1e-3 outright at full size (measured 6.5e-4 .. 6.9e-4 over a whole
+    # DDIM-50 run, profiles/r1_full_loop_parity_cfg1.json); the DS-Diff backbones sit at their 10-bit-operand floor (1.2e-3)
+    tol = 1e-3 if workload == "cfg1" else REL_TOL[torch.float16]
+    assert rel < tol, f"{workload} full-size rel err {rel:.3e}"
     if hasattr(net, "prepare_conditioning"):        # the step as the samplers run it: conditioning prefix hoisted
         assert net.prepare_conditioning([cond.cuda()])
         got_h = net(xc.cuda(), ts.cuda(), cond_cached=True)[0].cpu()
