@@ -86,6 +86,7 @@ SIGNATURES = {
     "b200_linear_f32": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "b200_gather_row_f32": [_P, _P, _P, _I, _P],
     "b200_upsample_nearest2x": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "b200_avgpool2x": [_P, _P, _I, _I, _I, _I, _I, _P],
     "b200_add4_scale": [_P, _P, _P, _P, _F, _P, _L, _I, _I, _P],
     "b200_add4_scale_stats": [_P, _P, _P, _P, _F, _P, _I, _I, _I, _P, _I, _P],
     "b200_se_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],

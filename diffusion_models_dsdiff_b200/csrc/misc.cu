@@ -297,6 +297,34 @@ __global__ void upsample2x_kernel(const uint4 *__restrict__ src, uint4 *__restri
   }
 }
 
+// 2x2 average pooling, NHWC act -> NHWC act (Downsample(use_conv=False) / ResBlock(down=True): nn.AvgPool2d(2, 2),
+// openaimodel.py:158-160, 216-218); fp32 average, rounded once.
+template <typename T>
+__global__ void avgpool2x_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, int N, int Ho, int Wo, int C8) {
+  const long long total = (long long)N * Ho * Wo * C8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8);
+    long long r = i / C8;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const long long n = r / Ho;
+    const long long base = ((n * (2 * Ho) + 2 * ho) * (2 * Wo) + 2 * wo) * C8 + c;
+    float acc[8] = {0}, f[8];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        unpack8<T>(__ldg(src + base + ((long long)dy * (2 * Wo) + dx) * C8), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += f[k];
+      }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] *= 0.25f;
+    dst[i] = pack8_fast<T>(acc);
+  }
+}
+
 template <typename T>
 __global__ void add4_scale_kernel(const uint4 *__restrict__ a, const uint4 *__restrict__ b,
                                   const uint4 *__restrict__ c, const uint4 *__restrict__ d, float scale,
@@ -586,6 +614,15 @@ extern "C" int b200_upsample_nearest2x(const void *src, void *dst, int N, int H,
   const long long total = (long long)N * 4 * H * W * (C / 8);
   DISPATCH_ACT(act_dtype, upsample2x_kernel<T><<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
                               (const uint4 *)src, (uint4 *)dst, N, H, W, C / 8);)
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int b200_avgpool2x(const void *src, void *dst, int N, int H, int W, int C, int act_dtype, void *stream) {
+  B200_CHECK(src && dst && N > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0,
+             "avgpool2x: H, W must be even and C a multiple of 8");
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  DISPATCH_ACT(act_dtype, avgpool2x_kernel<T><<<ew_blocks(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                              (const uint4 *)src, (uint4 *)dst, N, H / 2, W / 2, C / 8);)
   B200_LAUNCH_CHECK();
   return 0;
 }

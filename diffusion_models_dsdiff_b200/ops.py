@@ -523,6 +523,16 @@ def upsample_nearest2x(x: Tensor) -> Tensor:
     return out
 
 
+def avg_pool2x(x: Tensor) -> Tensor:
+    """nn.AvgPool2d(2, 2) on an NHWC activation."""
+    _dev(x)
+    n, h, w, c = x.shape
+    out = torch.empty((n, h // 2, w // 2, c), device=x.device, dtype=x.dtype)
+    _timed("avgpool2x", 0.0, 2.0 * (x.numel() + out.numel()),
+           lambda: L.check(L.lib().b200_avgpool2x(_p(x), _p(out), n, h, w, c, act_code(x.dtype), _stream()), "avgpool2x"))
+    return out
+
+
 def add4_scale(a: Tensor, b: Optional[Tensor] = None, c: Optional[Tensor] = None, d: Optional[Tensor] = None,
                scale: float = 1.0, silu: bool = False) -> Tensor:
     _dev(a)

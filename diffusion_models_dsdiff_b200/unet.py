@@ -199,11 +199,28 @@ def run_resblock(cx: Ctx, m: ResBlock, x0: Act, x1: Optional[Act], conv1_raw: Op
     """ResBlock._forward (openaimodel.py:264-284) on NHWC activations; input = cat([x0, x1], C).
     ``conv1_raw``: cached output of ``run_resblock_conv1_raw`` for this x0 — GN1 and conv1 are skipped and the bias +
     timestep term is added on the fly inside the second GroupNorm (its statistics are corrected analytically)."""
-    if m.up or m.down:
-        raise NotImplementedError("resblock_updown=True is not supported by the B200 engine yet")
     pw = cx.pw
     gin, gout = m.in_layers[0], m.out_layers[0]
     off, width = pw.emb_slices[id(m)]
+    if m.up or m.down:      # openaimodel.py:265-270: resample BOTH the normalised branch and the skip input
+        resample = ops.upsample_nearest2x if m.up else ops.avg_pool2x
+        a = resample(run_gn(cx, gin, x0, x1))
+        xr = resample(x0.t if x1 is None else torch.cat([x0.t, x1.t], dim=-1))
+        emb_out = cx.emb_all[:, off:off + width]
+        conv1, conv2 = m.in_layers[2], m.out_layers[3]
+        if m.use_scale_shift_norm:
+            h = run_conv(cx, [(a, pw.conv[id(conv1)], 0, 3, 1)], bias=_f(conv1.bias))
+            a2 = run_gn(cx, gout, h, film=emb_out)
+        else:
+            h = run_conv(cx, [(a, pw.conv[id(conv1)], 0, 3, 1)], rowbias=emb_out)
+            a2 = run_gn(cx, gout, h)
+        segs = [(a2, pw.conv[id(conv2)], 0, 3, 1)]
+        sk = m.skip_connection
+        if isinstance(sk, nn.Conv2d):
+            ks = sk.kernel_size[0]
+            segs.append((xr, pw.conv[id(sk)], 0, ks, ks // 2))
+            return run_conv(cx, segs, bias=pw.bias2[id(m)])
+        return run_conv(cx, segs, bias=pw.bias2[id(m)], residual=xr)
     emb_out = cx.emb_all[:, off:off + width]
     conv1, conv2 = m.in_layers[2], m.out_layers[3]
     if conv1_raw is not None:
@@ -280,8 +297,9 @@ def run_sequential(cx: Ctx, seq: nn.Sequential, x0: Act, x1: Optional[Act], conv
             x0 = run_spatial_transformer(cx, layer, x0)
         elif isinstance(layer, Downsample):
             if not layer.use_conv:
-                raise NotImplementedError("Downsample(use_conv=False) is not supported by the B200 engine yet")
-            x0 = run_conv(cx, [(x0.t, pw.conv[id(layer.op)], 0, 3, 1)], stride=2, bias=_f(layer.op.bias))
+                x0 = Act(ops.avg_pool2x(x0.t))
+            else:
+                x0 = run_conv(cx, [(x0.t, pw.conv[id(layer.op)], 0, 3, 1)], stride=2, bias=_f(layer.op.bias))
         elif isinstance(layer, Upsample):
             x0 = Act(ops.upsample_nearest2x(x0.t))
             if layer.use_conv:
@@ -341,11 +359,13 @@ class TimeEmbedding:
         self.dim = model_channels
 
     def __call__(self, pw: PackedWeights, time_embed: nn.Sequential, t_table: Tensor, batch: int,
-                 step_ptr: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+                 step_ptr: Optional[Tensor] = None, label: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
         t_emb = ops.timestep_embedding(t_table, self.freqs, batch, self.dim, step_ptr)
         l0, l2 = time_embed[0], time_embed[2]
         hid = ops.linear_f32(t_emb, _f(l0.weight), _f(l0.bias), out_silu=True)
         emb = ops.linear_f32(hid, _f(l2.weight), _f(l2.bias))
+        if label is not None:          # emb = emb + label_emb(y), openaimodel.py:941-943
+            emb = ops.add_f32(emb, label)
         emb_all = ops.linear_f32(emb, pw.emb_w, pw.emb_b, in_silu=True)
         return emb, emb_all
 
@@ -402,16 +422,31 @@ class _EngineModule(nn.Module):
         with torch.no_grad():
             self._temb.prepare_steps(pw, self.time_embed, t_table.to(torch.float32).contiguous())
 
-    def _emb_all(self, pw, timesteps: Tensor, n: int, step_ptr: Optional[Tensor]) -> Tensor:
+    def _label_embedding(self, y: Optional[Tensor], n: int) -> Optional[Tensor]:
+        """label_emb(y) as fp32 [N, 4*C0] (openaimodel.py:696-712, 941-943); None for unconditional models."""
+        if getattr(self, "num_classes", None) is None:
+            return None
+        assert y.shape[0] == n
+        le = self.label_emb
+        if isinstance(le, nn.Embedding):
+            return _f(le.weight)[y.long()].contiguous()                # row gather: no arithmetic
+        if isinstance(le, nn.Linear):                                     # "continuous": Linear(1, ted)
+            return ops.linear_f32(y.float().reshape(n, -1).contiguous(), _f(le.weight), _f(le.bias))
+        l0, l2 = le[0][0], le[0][2]                                        # "sequential": Linear, SiLU, Linear
+        hid = ops.linear_f32(y.float().reshape(n, -1).contiguous(), _f(l0.weight), _f(l0.bias), out_silu=True)
+        return ops.linear_f32(hid, _f(l2.weight), _f(l2.bias))
+
+    def _emb_all(self, pw, timesteps: Tensor, n: int, step_ptr: Optional[Tensor], y: Optional[Tensor] = None) -> Tensor:
         """Batched emb_layers projections [N or 1, total] for this call."""
+        label = self._label_embedding(y, n)
         if step_ptr is not None:
-            row = self._temb.step_row(int(timesteps.numel()), step_ptr)
+            row = None if label is not None else self._temb.step_row(int(timesteps.numel()), step_ptr)
             if row is not None:
                 return row
             t_table = timesteps.to(torch.float32).contiguous()
         else:
             t_table = self._t_table(timesteps, n)
-        return self._temb(pw, self.time_embed, t_table, n, step_ptr)[1]
+        return self._temb(pw, self.time_embed, t_table, n, step_ptr, label=label)[1]
 
     @staticmethod
     def _t_table(timesteps: Tensor, batch: int) -> Tensor:
@@ -443,8 +478,8 @@ def build_unet_trunk(self, image_size, in_channels, model_channels, out_channels
             "Fool!! You forgot to use the spatial transformer for your cross-attention conditioning..."
         if not isinstance(context_dim, (int, list, tuple)):
             context_dim = list(context_dim)
-    if num_classes is not None or n_embed is not None:
-        raise NotImplementedError("B200 engine: class conditioning / codebook head are not built yet")
+    if n_embed is not None:
+        raise NotImplementedError("B200 engine: the codebook-id head (n_embed) is not built")
     if num_heads_upsample == -1:
         num_heads_upsample = num_heads
     if num_heads == -1:
@@ -462,11 +497,21 @@ def build_unet_trunk(self, image_size, in_channels, model_channels, out_channels
         self.num_res_blocks = list(num_res_blocks)
     self.attention_resolutions = attention_resolutions
     self.channel_mult = channel_mult
-    self.num_classes = None
+    self.num_classes = num_classes
     self.dtype = torch.float32
     self.act_dtype = act_dtype or default_act_dtype()
     ted = model_channels * 4
     self.time_embed = nn.Sequential(nn.Linear(model_channels, ted), nn.SiLU(), nn.Linear(ted, ted))
+    if num_classes is not None:      # openaimodel.py:696-712
+        if isinstance(num_classes, int):
+            self.label_emb = nn.Embedding(num_classes, ted)
+        elif num_classes == "continuous":
+            self.label_emb = nn.Linear(1, ted)
+        elif num_classes == "sequential":
+            assert adm_in_channels is not None
+            self.label_emb = nn.Sequential(nn.Sequential(nn.Linear(adm_in_channels, ted), nn.SiLU(), nn.Linear(ted, ted)))
+        else:
+            raise ValueError()
 
     def attn(ch, heads, disabled_sa=False):
         # head-count resolution of openaimodel.py:739-747 / 795-802
@@ -536,7 +581,7 @@ class UNetModel(_EngineModule):
             "must specify y if and only if the model is class-conditional"
         pw = self.packed()
         n = x.shape[0]
-        emb_all = self._emb_all(pw, timesteps, n, step_ptr)
+        emb_all = self._emb_all(pw, timesteps, n, step_ptr, y)
         self._arena.begin(x.device)
         cx = Ctx(pw, emb_all, self._arena, tfm.context_tokens(context, self.act_dtype))
         hs = []

@@ -224,6 +224,9 @@ int b200_gather_row_f32(const float *table, const int *step_ptr, float *out, int
  * nearest x2 upsample (Upsample.forward F.interpolate, openaimodel.py:113-117), NHWC.          */
 int b200_upsample_nearest2x(const void *src, void *dst, int N, int H, int W, int C, int act_dtype,
                             void *stream);
+/* nn.AvgPool2d(2, 2) on NHWC act: Downsample(use_conv=False) and the h_upd / x_upd of ResBlock(down=True)
+ * (openaimodel.py:158-160, 216-218, 265-270).  H, W even.                                                     */
+int b200_avgpool2x(const void *src_nhwc, void *dst_nhwc, int N, int H, int W, int C, int act_dtype, void *stream);
 /* dst = scale * (a + b + c + d)   (b,c,d may be NULL) — DS-Diff skip mean
  * (hs+hs_a+hs_al+hs_l)/4, UNet_DS_Diff/model.py:745; mean of FeatureDisentangle outputs :722.   */
 int b200_add4_scale(const void *a, const void *b, const void *c, const void *d, float scale,

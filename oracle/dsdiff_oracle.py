@@ -227,13 +227,17 @@ def spatial_transformer(sd: SD, p: str, x: Tensor, context: Optional[Tensor], he
     return x + x_in
 
 
-def timestep_embed_sequential(sd: SD, p: str, x: Tensor, emb: Tensor, hp: dict, opq=None, context=None) -> Tensor:
+def timestep_embed_sequential(sd: SD, p: str, x: Tensor, emb: Tensor, hp: dict, opq=None, context=None,
+                              updown: Optional[dict] = None) -> Tensor:
     """TimestepEmbedSequential.forward dispatch, decided from the keys present.
-    openaimodel.py:80-90."""
+    openaimodel.py:80-90.  ``updown``: {sub-index: "up" | "down"} for resblock_updown ResBlocks (they have the same
+    parameters as plain ones, so the layout comes from the hyper-parameters: see _updown_layout)."""
     for j in _sub_indices(sd, p + "."):
         q = f"{p}.{j}"
         if q + ".in_layers.0.weight" in sd:
-            x = resblock(sd, q, x, emb, hp.get("use_scale_shift_norm", False), opq=opq)
+            kind = (updown or {}).get(j)
+            x = resblock(sd, q, x, emb, hp.get("use_scale_shift_norm", False), up=kind == "up", down=kind == "down",
+                         opq=opq)
         elif q + ".transformer_blocks.0.attn1.to_q.weight" in sd:
             x = spatial_transformer(sd, q, x, context, _heads_for(hp, x.shape[1]), opq=opq)
         elif q + ".qkv.weight" in sd:
@@ -262,19 +266,61 @@ def out_head(sd: SD, h: Tensor, opq=None) -> Tensor:
     return conv2d(sd, "out.2", h, opq=opq)
 
 
-def unet_forward(sd: SD, hp: dict, x: Tensor, t: Tensor, opq=None, context: Optional[Tensor] = None) -> Tensor:
-    """UNetModel.forward (no class label; ``context`` feeds the SpatialTransformer cross-attention).
+def _updown_layout(hp: dict):
+    """Which ResBlocks resample when resblock_updown=True (openaimodel.py:757-775, 855-871): the block after each
+    level's ResBlocks on the way down, the LAST layer of the last block of each level on the way up."""
+    down, up = set(), {}
+    if not hp.get("resblock_updown", False):
+        return down, up
+    mult = list(hp["channel_mult"])
+    nrb = hp["num_res_blocks"]
+    nrb = [nrb] * len(mult) if isinstance(nrb, int) else list(nrb)
+    idx = 0
+    for level in range(len(mult)):
+        idx += nrb[level]
+        if level != len(mult) - 1:
+            idx += 1
+            down.add(idx)
+    ob = 0
+    for level in reversed(range(len(mult))):
+        for i in range(nrb[level] + 1):
+            if level and i == nrb[level]:
+                up[ob] = True
+            ob += 1
+    return down, up
+
+
+def label_embedding(sd: SD, hp: dict, y: Tensor, opq=None) -> Tensor:
+    """self.label_emb(y).  openaimodel.py:696-712."""
+    nc = hp["num_classes"]
+    if isinstance(nc, int):
+        return sd["label_emb.weight"][y.long()]
+    if nc == "continuous":
+        return linear(sd, "label_emb", y.float().reshape(y.shape[0], -1), opq)
+    return linear(sd, "label_emb.0.2", silu(linear(sd, "label_emb.0.0", y.float().reshape(y.shape[0], -1), opq)), opq)
+
+
+def unet_forward(sd: SD, hp: dict, x: Tensor, t: Tensor, opq=None, context: Optional[Tensor] = None,
+                 y: Optional[Tensor] = None) -> Tensor:
+    """UNetModel.forward (``context`` feeds the SpatialTransformer cross-attention, ``y`` the class embedding).
     openaimodel.py:926-958."""
     emb = time_embed(sd, hp, t, opq)
+    if hp.get("num_classes") is not None:
+        emb = emb + label_embedding(sd, hp, y, opq)                        # :941-943
+    down, up = _updown_layout(hp)
     hs = []
     h = x.float()
     for i in _sub_indices(sd, "input_blocks."):
-        h = timestep_embed_sequential(sd, f"input_blocks.{i}", h, emb, hp, opq, context)
+        h = timestep_embed_sequential(sd, f"input_blocks.{i}", h, emb, hp, opq, context,
+                                      updown={0: "down"} if i in down else None)
         hs.append(h)
     h = timestep_embed_sequential(sd, "middle_block", h, emb, hp, opq, context)
     for i in _sub_indices(sd, "output_blocks."):
         h = torch.cat([h, hs.pop()], dim=1)
-        h = timestep_embed_sequential(sd, f"output_blocks.{i}", h, emb, hp, opq, context)
+        ud = None
+        if i in up:
+            ud = {max(_sub_indices(sd, f"output_blocks.{i}.")): "up"}
+        h = timestep_embed_sequential(sd, f"output_blocks.{i}", h, emb, hp, opq, context, updown=ud)
     return out_head(sd, h, opq)
 
 

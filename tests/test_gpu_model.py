@@ -458,3 +458,16 @@ def test_full_size_determinism_and_batch_independence(workload):
     y1, y2, y0 = f(x, t), f(x, t), f(x[:1], t[:1])
     assert torch.equal(y1, y2)
     assert torch.equal(y0, y1[:1])
+
+
+@pytest.mark.parametrize("case", ["unet_updown", "unet_seq_label"])
+def test_resblock_updown_and_label_embedding_match_reference(case):
+    """resblock_updown=True (AvgPool / nearest resampling inside the ResBlock) and class-conditional label_emb(y)
+    (openaimodel.py:213-218, 265-270, 696-712, 941-943) against the reference's output."""
+    hp, sd, net = _net(case, torch.float16)
+    g = golden(case)
+    y = net(g["x"].cuda(), g["t"].cuda(), y=g["labels"].cuda()).cpu()
+    rel = O.rel_err(y, g["y"])
+    assert rel < REL_TOL[torch.float16], f"{case}: rel err {rel:.3e}"
+    with pytest.raises(AssertionError):
+        net(g["x"].cuda(), g["t"].cuda())          # class-conditional model without y

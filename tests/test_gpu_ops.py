@@ -338,3 +338,11 @@ def test_groupnorm_preshift_matches_shifted_input(batch_rows):
     ref2 = F.silu(F.group_norm(x + s[:, :, None, None], 32, g, b, 1e-5) * (1 + film.cpu()[:, :c, None, None]) + film.cpu()[:, c:, None, None])
     y2 = ops.group_norm(a, g.cuda(), b.cuda(), cs0=ops.channel_stats(a), preshift=wide[:, 8:8 + c], film=film)
     close(nchw(y2), ref2, dt, "gn preshift + film")
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_avg_pool2x(dt):
+    ops = _ops()
+    x = q(rnd(1, 2, 24, 12, 20), dt)
+    y = ops.avg_pool2x(nhwc(x, dt))
+    close(nchw(y), F.avg_pool2d(x, 2, 2), dt, "avgpool 2x2")

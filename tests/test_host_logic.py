@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/b200diff.h but not exported"
     assert set(L.SIGNATURES) == set(syms), "ctypes table and header disagree"
-    assert L.lib().b200_abi_version() == 6
+    assert L.lib().b200_abi_version() == 7
     assert L.lib().b200_launch_count() == 0 or True
 
 
@@ -54,7 +54,7 @@ def test_error_path_reports_text_without_gpu():
 # -------------------------------------------------------------------------------------------------
 # drop-in modules: constructor keywords + state_dict keys/shapes of the reference
 # -------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("case", ["unet_small", "unet_legacy_film"])
+@pytest.mark.parametrize("case", ["unet_small", "unet_legacy_film", "unet_updown", "unet_seq_label", "xattn_small"])
 def test_unet_state_dict_matches_reference(case):
     hp, sd = synth_sd(case)
     net = P.UNetModel(**hp)

@@ -252,3 +252,12 @@ def test_ddim_classifier_free_guidance_oracle_matches_reference():
         x, _ = O.ldm_ddim_step(sch, tab, x, u + g["scale"] * (c - u), index, g["noises"][i], "v", True)
         assert maxabs(x, g["x_inter"][i]) < 1e-4, i
     assert maxabs(x, g["final"]) < 1e-4
+
+
+@pytest.mark.parametrize("case", ["unet_updown", "unet_seq_label"])
+def test_resblock_updown_and_label_embedding_oracle_matches_reference(case):
+    hp, sd = synth_sd(case)
+    g = golden(case)
+    y = O.unet_forward(sd, hp, g["x"], g["t"], y=g["labels"])
+    assert g["y"].abs().max() > 0.05
+    assert maxabs(y, g["y"]) < TOL * max(1.0, float(g["y"].abs().max()))
