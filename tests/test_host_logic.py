@@ -248,7 +248,7 @@ def test_unsupported_paths_fail_loudly():
         smp.sample(5, 1, (1, 8, 8), None, mask=torch.ones(1), verbose=False)
     hp, _ = synth_sd("unet_small")
     with pytest.raises(NotImplementedError):
-        P.UNetModel(**{**hp, "num_classes": 10})
+        P.UNetModel(**{**hp, "n_embed": 32})           # codebook-id head: not built
     with pytest.raises(AssertionError):             # the reference's own ctor check (openaimodel.py:630-637)
         P.UNetModel(**{**hp, "use_spatial_transformer": True})
 
