@@ -254,13 +254,17 @@ class DSUnetModel(_EngineModule):
                     ev.record(st)
                     joins2.append(ev)
             family("style", self.conv_style, self.style_proj, (h_a, h_al, h_l))
-            h_n_style, h_n_content = fd(self.conv_style, h_n), fd(self.conv_content, h_n)
+            # style / content heads of the NOISE stream only feed the returned feature dict (model.py:695-700, 751-756):
+            # every sampler discards it, so they are skipped when the caller does not ask for features
+            h_n_style, h_n_content = (fd(self.conv_style, h_n), fd(self.conv_content, h_n)) if return_features else (None, None)
             for ev in joins2:
                 main.wait_event(ev)
             (style, h_style), (content, h_share) = fam["style"], fam["content"]
             (anatomy, h_anat), (lesion, h_les) = fam["anatomy"], fam["lesion"]
         else:
-            h_n_style, h_n_content = fd(self.conv_style, h_n), fd(self.conv_content, h_n)
+            # style / content heads of the NOISE stream only feed the returned feature dict (model.py:695-700, 751-756):
+            # every sampler discards it, so they are skipped when the caller does not ask for features
+            h_n_style, h_n_content = (fd(self.conv_style, h_n), fd(self.conv_content, h_n)) if return_features else (None, None)
             style = [fd(self.conv_style, v) for v in (h_a, h_al, h_l)]
             content = [fd(self.conv_content, v) for v in (h_a, h_al, h_l)]
             anatomy = [fd(self.conv_anatomy, v) for v in (h_a, h_al)]
