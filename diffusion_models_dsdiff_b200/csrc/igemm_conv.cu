@@ -458,6 +458,18 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
               v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
             }
           }
+          if (p.epi_act == 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = gelu_tanh_f(v[i]);
+          }
+          if (p.rowscale) {          // adaLN-Zero gate of this image (a warp's rows lie in one image: TW*TH >= 32)
+            const float4 *gp = reinterpret_cast<const float4 *>(p.rowscale + (size_t)n * p.rowscale_stride + co);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 g4 = __ldg(gp + j);
+              v[4 * j] *= g4.x; v[4 * j + 1] *= g4.y; v[4 * j + 2] *= g4.z; v[4 * j + 3] *= g4.w;
+            }
+          }
           if (res) {
             const uint32_t *rw = reinterpret_cast<const uint32_t *>(rq);
 #pragma unroll
@@ -531,10 +543,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
             }
             if (p.epi_act == 1) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float x = vh[i];
-                vh[i] = 0.5f * x * (1.f + tanhf(0.7978845608028654f * (x + 0.044715f * x * x * x)));
-              }
+              for (int i = 0; i < 8; ++i) vh[i] = gelu_tanh_f(vh[i]);
             }
             if (p.rowscale) {
               const float *rs = p.rowscale + (size_t)n * p.rowscale_stride + cb;
@@ -653,6 +662,8 @@ int pick_bn(int Cout) {
 // for one image is bit-identical whatever batch it is part of (slices are independent units):
 // minimise the padded area of one image, prefer 16-wide boxes on ties (square-ish halo => better L2 locality).
 static void pick_box(int Hout, int Wout, int *TW, int *TH, int *TN) {
+  // minimise the padded area of ONE image.  Tallest box per width first (fewest images per tile: halo reuse needs TN == 1),
+  // ties prefer 16-wide boxes (square-ish halo => better L2 locality) ...
   long best = -1;
   for (int tw = 32; tw >= 1; tw >>= 1) {
     int th = std::min(pow2_ceil(Hout), kBM / tw);
@@ -660,6 +671,16 @@ static void pick_box(int Hout, int Wout, int *TW, int *TH, int *TN) {
     long area = (long)cdiv(Wout, tw) * tw * cdiv(Hout, th) * th;
     if (best < 0 || area < best || (area == best && tw == 16)) {
       best = area; *TW = tw; *TH = th; *TN = tn;
+    }
+  }
+  // ... then shorter boxes spanning several images, only where they STRICTLY cut the padding: token "images" such as
+  // 18 x 32 (DiT, 576 tokens) tile exactly with 32 x 2 x 2 boxes where 32 x 4 x 1 wastes 10 %
+  for (int tw = 32; tw >= 8; tw >>= 1) {
+    for (int th = std::min(pow2_ceil(Hout), kBM / tw) >> 1; th >= 1 && tw * th >= 32; th >>= 1) {
+      const long area = (long)cdiv(Wout, tw) * tw * cdiv(Hout, th) * th;
+      if (area < best) {
+        best = area; *TW = tw; *TH = th; *TN = kBM / (tw * th);
+      }
     }
   }
 }
@@ -921,7 +942,7 @@ extern "C" int b200_conv2d_igemm(const b200_conv_desc *d, void *stream) {
   pick_box(d->Hout, d->Wout, &TW, &TH, &TN);
   const long ptiles = (long)cdiv(d->Wout, TW) * cdiv(d->Hout, TH) * cdiv(d->N, TN);
   static const bool no_fast = getenv("B200DIFF_CONV_NO_FAST_EPI") != nullptr;
-  const bool fast = !no_fast && d->out && !d->out_nchw_f32 && !d->out_nhwc_f32 && !d->epi_act && !d->rowscale &&
+  const bool fast = !no_fast && d->out && !d->out_nchw_f32 && !d->out_nhwc_f32 && d->epi_act <= 1 &&
                     d->Cout % 16 == 0 && d->Cout % bn == 0 && (((uintptr_t)d->out | (uintptr_t)d->residual) & 31) == 0 &&
                     d->Wout % TW == 0 && d->Hout % TH == 0 && d->N % TN == 0 && ptiles % kc == 0 && TW * TH >= 32 &&
                     !getenv("B200DIFF_SKIP_EPI") && !getenv("B200DIFF_NO_VEC32") && ksplit == 1;
