@@ -69,13 +69,14 @@ struct FaParams {
   int q_hstride, k_hstride, v_hstride;  // channels between consecutive heads
   int ldo;                            // output row pitch (elements); head h writes channels [h*D, h*D+D)
   int stages;                         // K / V ring depth (1 or 2)
+  int pbufs;                          // P buffers in shared memory (2, or 1 to fit two CTAs per SM at D = 64)
   float scale_log2e;
   void *out;
   uint32_t idesc_s, idesc_o;
 };
 
 template <typename T, int D>
-__global__ void __launch_bounds__(kFaThreads, (D <= 48) ? 2 : 1)
+__global__ void __launch_bounds__(kFaThreads, (D <= 64) ? 2 : 1)
 flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
   constexpr int kDB = D / 8;                         // 16-byte channel blocks per row
   constexpr uint32_t kTileBytes = kDB * kBlkBytes;   // Q / K / V tile: D x 128 x 2 B
@@ -175,9 +176,9 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
       issue_qk(g++);
       for (int j = 0; j < nk; ++j) {
         if (j + 1 < nk) issue_qk(g++);
-        const int pb = j & 1;
+        const int pb = (p.pbufs == 2) ? (j & 1) : 0;
         mbar_wait(smem_u32(&v_full[vs]), vph);
-        mbar_wait(smem_u32(&p_full[pb]), (j >> 1) & 1);
+        mbar_wait(smem_u32(&p_full[pb]), (p.pbufs == 2) ? ((j >> 1) & 1) : (j & 1));
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < kFaBN / 16; ++kk) {
@@ -208,7 +209,7 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     float M = -INFINITY;                              // running softmax reference (raw-score units), lazily updated
     float l = 0.f;
     for (int j = 0; j < nk; ++j) {
-      const int sb = 0, pb = j & 1;
+      const int sb = 0, pb = (p.pbufs == 2) ? (j & 1) : 0;
       mbar_wait(smem_u32(&s_full[sb]), j & 1);
       tc_fence_after();
       const int nvalid = min(kFaBN, p.Lk - j * kFaBN);
@@ -267,7 +268,7 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         tc_fence_before();
       }
       const float mneg = -M * p.scale_log2e;
-      mbar_wait(smem_u32(&p_empty[pb]), ((j >> 1) & 1) ^ 1);
+      mbar_wait(smem_u32(&p_empty[pb]), ((p.pbufs == 2) ? ((j >> 1) & 1) : (j & 1)) ^ 1);
       uint8_t *prow = smem_raw + (sP - smem_u32(smem_raw)) + pb * kFaPBytes + row * 16;
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -362,11 +363,12 @@ static int launch_flash(const AttnArgs &a, cudaStream_t st) {
   p.idesc_s = umma_idesc(Act<T>::kFmt, kFaBM, kFaBN, 0);
   p.idesc_o = umma_idesc(Act<T>::kFmt, kFaBM, D, 1);
   const size_t tile = (size_t)D * 256;
-  // D <= 48: two CTAs per SM (256 TMEM columns each), so one CTA's TMEM-read phase overlaps the other's exponentials;
+  // D <= 64: two CTAs per SM (256 TMEM columns each), so one CTA's TMEM-read phase overlaps the other's exponentials;
   // its shared memory must stay under ~110 KB
-  const size_t budget = (D <= 48) ? 108 * 1024 : 200 * 1024;
-  p.stages = (tile * 5 + 2 * kFaPBytes + 256 <= budget) ? 2 : 1;
-  const size_t smem = tile * (1 + 2 * p.stages) + 2 * kFaPBytes + 256;
+  const size_t budget = (D <= 64) ? 108 * 1024 : 200 * 1024;
+  p.pbufs = (tile * 3 + 2 * kFaPBytes + 256 <= budget) ? 2 : 1;      // D = 64: one P buffer so that two CTAs fit
+  p.stages = (tile * 5 + p.pbufs * kFaPBytes + 256 <= budget) ? 2 : 1;
+  const size_t smem = tile * (1 + 2 * p.stages) + p.pbufs * kFaPBytes + 256;
   B200_CHECK(smem <= 220 * 1024, "attention: head dim %d does not fit shared memory", D);
   static bool attr_set = false;
   if (!attr_set) {
