@@ -84,6 +84,7 @@ SIGNATURES = {
     "b200_gaussian_sample": [_P, _P, _P, _I, _I, _I, _P],
     "b200_timestep_embedding": [_P, _P, _P, _P, _I, _I, _P],
     "b200_linear_f32": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "b200_silu_f32": [_P, _P, _L, _P],
     "b200_gather_row_f32": [_P, _P, _P, _I, _P],
     "b200_upsample_nearest2x": [_P, _P, _I, _I, _I, _I, _I, _P],
     "b200_avgpool2x": [_P, _P, _I, _I, _I, _I, _I, _P],

@@ -608,6 +608,19 @@ extern "C" int b200_linear_f32(const float *in, const float *W, const float *bia
   return 0;
 }
 
+__global__ void __launch_bounds__(256) silu_f32_kernel(const float *in, float *out, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = in[i];
+    out[i] = v / (1.f + expf(-v));
+  }
+}
+extern "C" int b200_silu_f32(const float *in, float *out, int64_t n, void *stream) {
+  B200_CHECK(in && out && n > 0, "silu_f32: bad arguments");
+  silu_f32_kernel<<<ew_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, n);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int b200_upsample_nearest2x(const void *src, void *dst, int N, int H, int W, int C, int act_dtype,
                                        void *stream) {
   B200_CHECK(src && dst && C % 8 == 0, "upsample: C must be a multiple of 8");

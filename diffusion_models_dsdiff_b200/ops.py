@@ -499,6 +499,10 @@ def linear_f32(x: Tensor, w: Tensor, bias: Optional[Tensor], in_silu: bool = Fal
     _dev(x)
     b, k = x.shape
     o = w.shape[0]
+    if in_silu and b > 8:      # the GEMV kernel activates its input per output row: for big batches do it once up front
+        act = torch.empty_like(x, memory_format=torch.contiguous_format)
+        L.check(L.lib().b200_silu_f32(_p(_f32(x.contiguous())), _p(act), x.numel(), _stream()), "silu_f32")
+        x, in_silu = act, False
     out = torch.empty((b, o), device=x.device, dtype=torch.float32)
     L.check(L.lib().b200_linear_f32(_p(_f32(x)), _p(_f32(w)), _p(_f32(bias)), _p(out), b, k, o, int(in_silu),
                                     int(out_silu), _stream()), "linear_f32")

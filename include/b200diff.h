@@ -215,6 +215,9 @@ int b200_timestep_embedding(const float *t_table, const int *step_ptr, const flo
 /* out[b][o] = bias[o] + sum_k act(in[b][k]) * W[o][k];  in_silu / out_silu select the SiLU.     */
 int b200_linear_f32(const float *in, const float *W, const float *bias, float *out, int B, int K,
                     int O, int in_silu, int out_silu, void *stream);
+/* out = SiLU(in) over n fp32 values: the activation in front of emb_layers / adaLN_modulation Linears
+ * (openaimodel.py:221-228, DiT_models.py:114-117) applied ONCE when the batch is large, instead of per output row. */
+int b200_silu_f32(const float *in, float *out, int64_t n, void *stream);
 
 /* out[0:width] = table[*step_ptr][0:width]: selects the current step's row of a table precomputed for ALL sampling
  * steps (the timestep MLP + every ResBlock's emb projection depend on t only), inside a replayed CUDA graph.      */

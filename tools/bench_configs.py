@@ -42,6 +42,20 @@ def timed(fn, reps=2, warm=2):
     return a.elapsed_time(b) / reps
 
 
+def timed_graph(fn, reps=5):
+    """Device-limited time of one call: captured as a CUDA graph (like the step engine does) and replayed."""
+    fn(); torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fn()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        fn()
+    return timed(g.replay, reps=reps)
+
+
 def emit(**kw):
     print(json.dumps(kw), flush=True)
 
@@ -86,14 +100,14 @@ def run_cfg3():
     x = torch.randn(B, 3, 64, 64, device=dev)
     ctx = torch.randn(B, 77, 768, device=dev)
     t = torch.full((B,), 500, device=dev)
-    ms = timed(lambda: net(x, t, context=ctx), reps=5)
+    ms = timed_graph(lambda: net(x, t, context=ctx))
     emit(config="cfg3 SD-v1 cross-attention UNetModel (v1-inference.yaml, in/out 3 ch) 64x64 latent, one network evaluation",
          batch=B, ms_per_eval=ms, evals_per_s=B / ms * 1e3, model_tflops=803.3 * B / ms / 1e3)
     ae = P.AutoencoderKL(ddconfig=dict(double_z=True, z_channels=3, resolution=256, in_channels=1, out_ch=1, ch=128,
                                        ch_mult=[1, 2, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0),
                          embed_dim=3).to(dev).eval()
     z = torch.randn(B, 3, 64, 64, device=dev)
-    ms = timed(lambda: ae.decode(z), reps=3)
+    ms = timed_graph(lambda: ae.decode(z))
     emit(config="cfg3 AutoencoderKL (autoencoder_kl_64x64x3.yaml) decode 64x64x3 -> 256x256", batch=B, ms_per_batch=ms,
          slices_per_s=B / ms * 1e3)
 
@@ -111,7 +125,7 @@ def run_dit():
     B = 64
     x = torch.randn(B, 4, 192, 192, device=dev)
     t = torch.full((B,), 500.0, device=dev)
-    ms = timed(lambda: net(x, t), reps=5)
+    ms = timed_graph(lambda: net(x, t))
     emit(config="DiT-B/8 input 192 in_channels 4 (trainer_use_gaussian_diff_adv.py), one forward", batch=B, ms_per_eval=ms,
          evals_per_s=B / ms * 1e3)
 
