@@ -70,7 +70,7 @@ def run_cfg1():
         ms = timed(lambda: S.DDIMSampler(model).sample(50, B, (1, 256, 256), cond, eta=0.0, x_T=x_T, verbose=False))
         sys.stdout = old
         emit(config="cfg1 UNetModel 160-ch (v2-1-cddpm.yaml) DDIM-50 256x256", batch=B, ms_per_batch=ms,
-             slices_per_s=B / ms * 1e3, model_tflops=1679.7 * B * 50 / ms / 1e3)
+             slices_per_s=B / ms * 1e3, model_tflops=1679.7 * B * 50 / ms)
 
 
 def run_cfg2p(volume=False):
@@ -102,7 +102,7 @@ def run_cfg3():
     t = torch.full((B,), 500, device=dev)
     ms = timed_graph(lambda: net(x, t, context=ctx))
     emit(config="cfg3 SD-v1 cross-attention UNetModel (v1-inference.yaml, in/out 3 ch) 64x64 latent, one network evaluation",
-         batch=B, ms_per_eval=ms, evals_per_s=B / ms * 1e3, model_tflops=803.3 * B / ms / 1e3)
+         batch=B, ms_per_eval=ms, evals_per_s=B / ms * 1e3, model_tflops=803.3 * B / ms)
     ae = P.AutoencoderKL(ddconfig=dict(double_z=True, z_channels=3, resolution=256, in_channels=1, out_ch=1, ch=128,
                                        ch_mult=[1, 2, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0),
                          embed_dim=3).to(dev).eval()
