@@ -346,3 +346,16 @@ def test_avg_pool2x(dt):
     x = q(rnd(1, 2, 24, 12, 20), dt)
     y = ops.avg_pool2x(nhwc(x, dt))
     close(nchw(y), F.avg_pool2d(x, 2, 2), dt, "avgpool 2x2")
+
+
+def test_empty_and_cpu_inputs_fail_loudly():
+    """No silent fallbacks: an empty batch or a CPU tensor is an error, reported through b200_last_error()."""
+    import diffusion_models_dsdiff_b200 as P
+    ops = _ops()
+    wt = ops.pack_conv_weight(torch.randn(16, 16, 3, 3, device="cuda") * 0.1, torch.float16)
+    with pytest.raises(P.B200Error):
+        ops.conv2d([(torch.empty(0, 8, 8, 16, device="cuda", dtype=torch.float16), wt, 0, 3, 1)])
+    with pytest.raises(P.B200Error):
+        ops.conv2d([(torch.zeros(1, 8, 8, 16, dtype=torch.float16), wt, 0, 3, 1)])
+    with pytest.raises(P.B200Error):
+        ops.group_norm(torch.zeros(1, 8, 8, 32, dtype=torch.float16), torch.ones(32), torch.zeros(32))
