@@ -510,8 +510,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
               st_sq[slot] += q0; st_sq[slot + 1] += q1;
             }
           }
-          return;
-        }
+        } else {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int cb = co + half * 8;
@@ -593,6 +592,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
             st_sum[slot] += s_tot;
             st_sq[slot] += q_tot;
           }
+        }
         }
       };
 
