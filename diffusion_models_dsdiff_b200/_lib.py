@@ -93,6 +93,7 @@ SIGNATURES = {
     "b200_se_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "b200_sampler_update": [C.POINTER(SamplerDesc), _P],
     "b200_abs_quantile": [_P, _I, _L, _F, _F, _P, _P],
+    "b200_lincomb2": [_P, _P, _P, _P, _P, _I, _L, _I, _P],
     "b200_advance_step": [_P, _I, _P],
 }
 _RESTYPE = {"b200_last_error": C.c_char_p, "b200_launch_count": C.c_uint64}

@@ -222,6 +222,20 @@ __global__ void __launch_bounds__(256) sampler_kernel(const SamplerK k) {
   }
 }
 
+// out = c1[n] * x (+|-) c2[n] * y with per-sample coefficients: q_sample, predict_start_from_noise, predict_start_from_z_and_v,
+// predict_eps_from_z_and_v, get_v, posterior mean (ldm/models/diffusion/ddpm.py:284-311; gaussian_diffusion.py:
+// 184-199, 223-245) — the reference's operation order (two multiplies, then one add / subtract; no FMA contraction)
+__global__ void __launch_bounds__(256) lincomb2_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                                                       const float *__restrict__ c1, const float *__restrict__ c2,
+                                                       float *__restrict__ out, long long per_sample, long long total,
+                                                       int subtract) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / per_sample;
+    const float a = mul(c1[n], x[i]), b = mul(c2[n], y[i]);
+    out[i] = subtract ? sub(a, b) : add(a, b);
+  }
+}
+
 __global__ void advance_step_kernel(int *step, int delta) { *step += delta; }
 
 }  // namespace b200
@@ -277,6 +291,17 @@ extern "C" int b200_abs_quantile(const float *x, int N, int64_t M, float q, floa
   using namespace b200;
   B200_CHECK(x && out && N > 0 && M > 0 && q >= 0.f && q <= 1.f, "abs_quantile: bad arguments");
   abs_quantile_kernel<<<N, 1024, 0, (cudaStream_t)stream>>>(x, (long long)M, q, floor_val, out);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_lincomb2(const float *x, const float *y, const float *c1, const float *c2, float *out, int N,
+                             int64_t per_sample, int subtract, void *stream) {
+  using namespace b200;
+  B200_CHECK(x && y && c1 && c2 && out && N > 0 && per_sample > 0, "lincomb2: bad arguments");
+  const long long total = (long long)N * per_sample;
+  const int blocks = (int)std::min<long long>(cdiv64(total, 256), (long long)num_sms() * 8);
+  lincomb2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, y, c1, c2, out, per_sample, total, subtract);
   B200_LAUNCH_CHECK();
   return 0;
 }

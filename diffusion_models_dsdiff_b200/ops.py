@@ -636,6 +636,19 @@ def abs_quantile(x: Tensor, q: float, floor_val: float, out: Optional[Tensor] = 
     return out
 
 
+def lincomb2(x: Tensor, y: Tensor, c1: Tensor, c2: Tensor, subtract: bool = False) -> Tensor:
+    """c1[n] * x[n] (+|-) c2[n] * y[n] with per-sample fp32 coefficients [N] (schedule-table gathers)."""
+    _dev(x)
+    if x.shape != y.shape or c1.numel() != x.shape[0] or c2.numel() != x.shape[0]:
+        raise L.B200Error("lincomb2: shape mismatch")
+    xf, yf = _f32(x.contiguous()), _f32(y.contiguous())
+    out = torch.empty_like(xf)
+    n = x.shape[0]
+    L.check(L.lib().b200_lincomb2(_p(xf), _p(yf), _p(_f32(c1.contiguous())), _p(_f32(c2.contiguous())), _p(out), n,
+                                  x.numel() // n, int(subtract), _stream()), "lincomb2")
+    return out
+
+
 def advance_step(step_ptr: Tensor, delta: int = 1) -> None:
     _dev(step_ptr)
     L.check(L.lib().b200_advance_step(_p(step_ptr), delta, _stream()), "advance_step")

@@ -446,28 +446,35 @@ class DDPM(nn.Module):
         reg("posterior_mean_coef2", (1. - alphas_cumprod_prev) * np.sqrt(alphas) / (1. - alphas_cumprod))
 
     # ---- the reference's elementwise helpers (API parity; the sampling loops use the fused kernel) ----
+    # ---- forward-process / parameterisation helpers (ddpm.py:284-311, 349-356): one fused kernel each; the per-sample
+    # coefficients are row gathers of the schedule buffers (no arithmetic on the host side) ----
+    def _comb(self, c1_name, x, c2_name, y, t, subtract):
+        t = t.reshape(-1).long()
+        c1 = getattr(self, c1_name).to(x.device)[t]
+        c2 = getattr(self, c2_name).to(x.device)[t]
+        return ops.lincomb2(x.float(), y.float(), c1, c2, subtract)
+
     def predict_start_from_noise(self, x_t, t, noise):
-        return (extract_into_tensor(self.sqrt_recip_alphas_cumprod, t, x_t.shape) * x_t
-                - extract_into_tensor(self.sqrt_recipm1_alphas_cumprod, t, x_t.shape) * noise)
+        return self._comb("sqrt_recip_alphas_cumprod", x_t, "sqrt_recipm1_alphas_cumprod", noise, t, True)
 
     def predict_start_from_z_and_v(self, x_t, t, v):
-        return (extract_into_tensor(self.sqrt_alphas_cumprod, t, x_t.shape) * x_t
-                - extract_into_tensor(self.sqrt_one_minus_alphas_cumprod, t, x_t.shape) * v)
+        return self._comb("sqrt_alphas_cumprod", x_t, "sqrt_one_minus_alphas_cumprod", v, t, True)
 
     def predict_eps_from_z_and_v(self, x_t, t, v):
-        return (extract_into_tensor(self.sqrt_alphas_cumprod, t, x_t.shape) * v
-                + extract_into_tensor(self.sqrt_one_minus_alphas_cumprod, t, x_t.shape) * x_t)
+        return self._comb("sqrt_alphas_cumprod", v, "sqrt_one_minus_alphas_cumprod", x_t, t, False)
+
+    def get_v(self, x, noise, t):
+        """ddpm.py:358-362: v = sqrt(ac) * noise - sqrt(1 - ac) * x."""
+        return self._comb("sqrt_alphas_cumprod", noise, "sqrt_one_minus_alphas_cumprod", x, t, True)
 
     def q_posterior(self, x_start, x_t, t):
-        mean = (extract_into_tensor(self.posterior_mean_coef1, t, x_t.shape) * x_start
-                + extract_into_tensor(self.posterior_mean_coef2, t, x_t.shape) * x_t)
+        mean = self._comb("posterior_mean_coef1", x_start, "posterior_mean_coef2", x_t, t, False)
         return (mean, extract_into_tensor(self.posterior_variance, t, x_t.shape),
                 extract_into_tensor(self.posterior_log_variance_clipped, t, x_t.shape))
 
     def q_sample(self, x_start, t, noise=None):
         noise = torch.randn_like(x_start) if noise is None else noise
-        return (extract_into_tensor(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start
-                + extract_into_tensor(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise)
+        return self._comb("sqrt_alphas_cumprod", x_start, "sqrt_one_minus_alphas_cumprod", noise, t, False)
 
     # ---- model call (trainers/trainer_ds_diff.py:740-755) ----
     def apply_model(self, x_noisy, t, cond, return_ids=False, **kw):

@@ -294,6 +294,12 @@ int b200_sampler_update(const b200_sampler_desc *d, void *stream);
  * neighbouring order statistics (rank = q*(M-1) in fp32) — the scale of DPM-Solver++'s dynamic thresholding
  * (dpm_solver_pytorch.py:418-427).  Exact radix select, one CTA per sample.                                         */
 int b200_abs_quantile(const float *x, int N, int64_t M, float q, float floor_val, float *out, void *stream);
+/* out[n, :] = c1[n] * x[n, :] (+ or -) c2[n] * y[n, :] over N samples of per_sample fp32 values, coefficients gathered
+ * per sample from the schedule tables by the caller: DDPM.q_sample / predict_start_from_noise /
+ * predict_start_from_z_and_v / predict_eps_from_z_and_v / get_v / q_posterior mean
+ * (ldm/models/diffusion/ddpm.py:284-311, 349-356; training_project/utils/gaussian_diffusion.py:184-245).           */
+int b200_lincomb2(const float *x, const float *y, const float *c1, const float *c2, float *out, int N, int64_t per_sample,
+                  int subtract, void *stream);
 /* *step_ptr += delta (one-thread kernel; keeps the step counter on the device for graph replay). */
 int b200_advance_step(int *step_ptr, int delta, void *stream);
 

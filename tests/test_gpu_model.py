@@ -471,3 +471,28 @@ def test_resblock_updown_and_label_embedding_match_reference(case):
     assert rel < REL_TOL[torch.float16], f"{case}: rel err {rel:.3e}"
     with pytest.raises(AssertionError):
         net(g["x"].cuda(), g["t"].cuda())          # class-conditional model without y
+
+
+@pytest.mark.parametrize("param", ["v", "eps"])
+def test_forward_process_helpers_bitlevel(param):
+    """DDPM.q_sample / get_v / predict_* / q_posterior (ddpm.py:284-311, 349-362) as one fused kernel each vs the reference's
+    torch expressions evaluated on the CPU with the same fp32 schedule buffers."""
+    S, m = _ldm(param)
+    gen = torch.Generator().manual_seed(4)
+    x0 = torch.randn(3, 1, 32, 32, generator=gen)
+    nz = torch.randn(3, 1, 32, 32, generator=gen)
+    t = torch.tensor([0, 977, 1999])
+    ex = lambda name: getattr(m, name).cpu()[t].reshape(3, 1, 1, 1)
+    sa, s1 = ex("sqrt_alphas_cumprod"), ex("sqrt_one_minus_alphas_cumprod")
+    ref = {"q_sample": sa * x0 + s1 * nz, "get_v": sa * nz - s1 * x0,
+           "start_from_v": sa * x0 - s1 * nz, "eps_from_v": sa * nz + s1 * x0,
+           "start_from_noise": ex("sqrt_recip_alphas_cumprod") * x0 - ex("sqrt_recipm1_alphas_cumprod") * nz,
+           "post_mean": ex("posterior_mean_coef1") * x0 + ex("posterior_mean_coef2") * nz}
+    c = lambda v: v.cuda()
+    got = {"q_sample": m.q_sample(c(x0), c(t), c(nz)), "get_v": m.get_v(c(x0), c(nz), c(t)),
+           "start_from_v": m.predict_start_from_z_and_v(c(x0), c(t), c(nz)),
+           "eps_from_v": m.predict_eps_from_z_and_v(c(x0), c(t), c(nz)),
+           "start_from_noise": m.predict_start_from_noise(c(x0), c(t), c(nz)),
+           "post_mean": m.q_posterior(c(x0), c(nz), c(t))[0]}
+    for k in ref:
+        assert torch.equal(got[k].cpu(), ref[k]), k            # same fp32 ops in the same order: bit-identical
