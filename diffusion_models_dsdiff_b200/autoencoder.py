@@ -166,13 +166,23 @@ class DiagonalGaussianDistribution(object):
 
     def __init__(self, parameters, deterministic=False):
         self.parameters = parameters
-        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
-        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.mean = torch.chunk(parameters, 2, dim=1)[0]
         self.deterministic = deterministic
-        self.std = torch.exp(0.5 * self.logvar)
-        self.var = torch.exp(self.logvar)
-        if deterministic:
-            self.var = self.std = torch.zeros_like(self.mean)
+
+    # logvar / std / var / kl are the TRAINING-side attributes of the reference class (KL regulariser of the autoencoder
+    # loss, out of scope here): kept for interface compatibility, evaluated lazily on access; encode -> sample / mode,
+    # i.e. everything the sampling path touches, runs in b200_gaussian_sample and never reads them.
+    @property
+    def logvar(self):
+        return torch.clamp(torch.chunk(self.parameters, 2, dim=1)[1], -30.0, 20.0)
+
+    @property
+    def std(self):
+        return torch.zeros_like(self.mean) if self.deterministic else torch.exp(0.5 * self.logvar)
+
+    @property
+    def var(self):
+        return torch.zeros_like(self.mean) if self.deterministic else torch.exp(self.logvar)
 
     def sample(self, noise: Optional[Tensor] = None):
         if self.deterministic:
