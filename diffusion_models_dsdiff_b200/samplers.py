@@ -595,7 +595,7 @@ class LatentDiffusion(DDPM):
     def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):
         if predict_cids:
             raise NotImplementedError("decode_first_stage(predict_cids=True) is not built in the B200 path")
-        return self.first_stage_model.decode(1. / self.scale_factor * z)
+        return self.first_stage_model.decode(self._scaled(z, 1. / float(self.scale_factor)))
 
     @torch.no_grad()
     def encode_first_stage(self, x):
@@ -603,7 +603,16 @@ class LatentDiffusion(DDPM):
 
     def get_first_stage_encoding(self, encoder_posterior):
         z = encoder_posterior.sample() if hasattr(encoder_posterior, "sample") else encoder_posterior
-        return self.scale_factor * z
+        return self._scaled(z, float(self.scale_factor))
+
+    @staticmethod
+    def _scaled(z, s: float):
+        """s * z (ddpm.py:808, 830): one fp32 multiply per element in the fused kernel; the identity when s == 1."""
+        if s == 1.0:
+            return z
+        n = z.shape[0]
+        c = torch.full((n,), s, dtype=torch.float32, device=z.device)
+        return ops.lincomb2(z, z, c, torch.zeros_like(c))
 
     @torch.no_grad()
     def p_sample_loop(self, cond, shape, return_intermediates=False, x_T=None, verbose=True, callback=None,
