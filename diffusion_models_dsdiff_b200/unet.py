@@ -330,22 +330,22 @@ def run_in_conv(cx: Ctx, conv: nn.Conv2d, x: Tensor, dtype: torch.dtype) -> Act:
 
 
 def run_out_head(cx: Ctx, out: nn.Sequential, h: Act) -> Tensor:
-    """self.out = GN, SiLU, conv3x3 (openaimodel.py:898-902): NHWC 16-bit -> NCHW fp32."""
+    """self.out = GN, SiLU, conv3x3 (openaimodel.py:898-902) or id_predictor = GN, conv1x1 (:903-907):
+    NHWC 16-bit -> NCHW fp32."""
     pw = cx.pw
-    gn, conv = out[0], out[2]
-    a = run_gn(cx, gn, h)
-    # tensor-core path with the output channels zero-padded to one 16-wide N tile; the epilogue writes fp32 NCHW
+    gn, conv = out[0], out[-1]
+    a = run_gn(cx, gn, h, silu=len(out) == 3)
+    # tensor-core path with the output channels zero-padded to whole 16-wide N tiles; the epilogue writes fp32 NCHW
     key = ("out", id(conv))
     if key not in pw.conv:
-        w = torch.zeros((16,) + tuple(conv.weight.shape[1:]), device=a.device)
+        cpad = (conv.out_channels + 15) // 16 * 16
+        w = torch.zeros((cpad,) + tuple(conv.weight.shape[1:]), device=a.device)
         w[:conv.out_channels] = conv.weight.detach().float()
-        b = torch.zeros(16, device=a.device)
+        b = torch.zeros(cpad, device=a.device)
         b[:conv.out_channels] = conv.bias.detach().float()
         pw.conv[key] = (ops.pack_conv_weight(w, a.dtype), b)
-    if conv.out_channels > 16:
-        raise B200Error("B200 engine: output heads wider than 16 channels are not supported")
     wp, bp = pw.conv[key]
-    return ops.conv2d([(a, wp, 0, 3, 1)], bias=bp, head_channels=conv.out_channels)
+    return ops.conv2d([(a, wp, 0, conv.kernel_size[0], conv.padding[0])], bias=bp, head_channels=conv.out_channels)
 
 
 class TimeEmbedding:
@@ -478,8 +478,6 @@ def build_unet_trunk(self, image_size, in_channels, model_channels, out_channels
             "Fool!! You forgot to use the spatial transformer for your cross-attention conditioning..."
         if not isinstance(context_dim, (int, list, tuple)):
             context_dim = list(context_dim)
-    if n_embed is not None:
-        raise NotImplementedError("B200 engine: the codebook-id head (n_embed) is not built")
     if num_heads_upsample == -1:
         num_heads_upsample = num_heads
     if num_heads == -1:
@@ -561,6 +559,9 @@ def build_unet_trunk(self, image_size, in_channels, model_channels, out_channels
                 ds //= 2
             self.output_blocks.append(TimestepEmbedSequential(*layers))
     self.out = nn.Sequential(_gn(ch), nn.SiLU(), nn.Conv2d(model_channels, out_channels, 3, padding=1))
+    self.predict_codebook_ids = n_embed is not None
+    if self.predict_codebook_ids:     # openaimodel.py:903-907
+        self.id_predictor = nn.Sequential(_gn(ch), nn.Conv2d(model_channels, n_embed, 1))
 
 
 class UNetModel(_EngineModule):
@@ -593,4 +594,6 @@ class UNetModel(_EngineModule):
         h = run_sequential(cx, self.middle_block, h, None)
         for blk in self.output_blocks:
             h = run_sequential(cx, blk, h, hs.pop())
+        if self.predict_codebook_ids:     # openaimodel.py:955-956
+            return run_out_head(cx, self.id_predictor, h)
         return run_out_head(cx, self.out, h).to(x.dtype)

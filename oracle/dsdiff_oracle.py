@@ -321,6 +321,9 @@ def unet_forward(sd: SD, hp: dict, x: Tensor, t: Tensor, opq=None, context: Opti
         if i in up:
             ud = {max(_sub_indices(sd, f"output_blocks.{i}.")): "up"}
         h = timestep_embed_sequential(sd, f"output_blocks.{i}", h, emb, hp, opq, context, updown=ud)
+    if hp.get("n_embed") is not None:                                      # :903-907, 955-956
+        h = group_norm(h, sd["id_predictor.0.weight"], sd["id_predictor.0.bias"])
+        return conv2d(sd, "id_predictor.1", h, padding=0, opq=opq)
     return out_head(sd, h, opq)
 
 

@@ -473,6 +473,17 @@ def test_resblock_updown_and_label_embedding_match_reference(case):
         net(g["x"].cuda(), g["t"].cuda())          # class-conditional model without y
 
 
+def test_codebook_id_head_matches_reference():
+    """n_embed: the id_predictor head (GroupNorm32 + 1x1 conv to 40 logits, openaimodel.py:903-907, 955-956) — an N tile
+    padded 40 -> 48 with the fp32 NCHW epilogue writing only the real channels."""
+    hp, sd, net = _net("unet_codebook", torch.float16)
+    g = golden("unet_codebook")
+    y = net(g["x"].cuda(), g["t"].cuda()).cpu()
+    assert y.shape == g["y"].shape and y.dtype == torch.float32
+    rel = O.rel_err(y, g["y"])
+    assert rel < REL_TOL[torch.float16], f"rel err {rel:.3e}"
+
+
 @pytest.mark.parametrize("param", ["v", "eps"])
 def test_forward_process_helpers_bitlevel(param):
     """DDPM.q_sample / get_v / predict_* / q_posterior (ddpm.py:284-311, 349-362) as one fused kernel each vs the reference's

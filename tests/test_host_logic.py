@@ -54,7 +54,8 @@ def test_error_path_reports_text_without_gpu():
 # -------------------------------------------------------------------------------------------------
 # drop-in modules: constructor keywords + state_dict keys/shapes of the reference
 # -------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("case", ["unet_small", "unet_legacy_film", "unet_updown", "unet_seq_label", "xattn_small"])
+@pytest.mark.parametrize("case", ["unet_small", "unet_legacy_film", "unet_updown", "unet_seq_label", "xattn_small",
+                                  "unet_codebook"])
 def test_unet_state_dict_matches_reference(case):
     hp, sd = synth_sd(case)
     net = P.UNetModel(**hp)
@@ -248,7 +249,7 @@ def test_unsupported_paths_fail_loudly():
         smp.sample(5, 1, (1, 8, 8), None, mask=torch.ones(1), verbose=False)
     hp, _ = synth_sd("unet_small")
     with pytest.raises(NotImplementedError):
-        P.UNetModel(**{**hp, "n_embed": 32})           # codebook-id head: not built
+        P.UNetModel(**{**hp, "dims": 3})               # 3D UNet: out of scope
     with pytest.raises(AssertionError):             # the reference's own ctor check (openaimodel.py:630-637)
         P.UNetModel(**{**hp, "use_spatial_transformer": True})
 

@@ -254,6 +254,15 @@ def test_ddim_classifier_free_guidance_oracle_matches_reference():
     assert maxabs(x, g["final"]) < 1e-4
 
 
+def test_codebook_id_head_oracle_matches_reference():
+    """predict_codebook_ids: id_predictor = GroupNorm32 + 1x1 conv (openaimodel.py:903-907, 955-956)."""
+    hp, sd = synth_sd("unet_codebook")
+    g = golden("unet_codebook")
+    y = O.unet_forward(sd, hp, g["x"], g["t"])
+    assert y.shape == (2, 40, 16, 16) and g["y"].abs().max() > 0.05
+    assert maxabs(y, g["y"]) < TOL * max(1.0, float(g["y"].abs().max()))
+
+
 @pytest.mark.parametrize("case", ["unet_updown", "unet_seq_label"])
 def test_resblock_updown_and_label_embedding_oracle_matches_reference(case):
     hp, sd = synth_sd(case)
