@@ -347,8 +347,8 @@ def _graph_cache_args(cache: dict, net) -> dict:
 # ldm: DiffusionWrapper + DDPM
 # ---------------------------------------------------------------------------------------------
 class DiffusionWrapper(nn.Module):
-    """ldm/models/diffusion/ddpm.py:1319-1365 ('concat' and unconditional keys; the cross-attention
-    keys raise until the SpatialTransformer path is built)."""
+    """ldm/models/diffusion/ddpm.py:1319-1365: every conditioning key of the reference (None, concat, crossattn, hybrid,
+    adm, hybrid-adm, crossattn-adm)."""
 
     def __init__(self, diff_model_config, conditioning_key):
         super().__init__()
@@ -371,7 +371,17 @@ class DiffusionWrapper(nn.Module):
         if self.conditioning_key == "hybrid":
             xc = torch.cat([x] + list(c_concat), dim=1)
             return self.diffusion_model(xc, t, context=torch.cat(list(c_crossattn), 1), **kw)
-        raise NotImplementedError(f"conditioning_key={self.conditioning_key!r} is not built in the B200 path yet")
+        if self.conditioning_key == "hybrid-adm":          # ddpm.py:1350-1354
+            assert c_adm is not None
+            xc = torch.cat([x] + list(c_concat), dim=1)
+            return self.diffusion_model(xc, t, context=torch.cat(list(c_crossattn), 1), y=c_adm, **kw)
+        if self.conditioning_key == "crossattn-adm":       # ddpm.py:1355-1358
+            assert c_adm is not None
+            cc = torch.cat(list(c_crossattn), 1) if c_crossattn[0] is not None else None
+            return self.diffusion_model(x, t, context=cc, y=c_adm, **kw)
+        if self.conditioning_key == "adm":                 # ddpm.py:1359-1361
+            return self.diffusion_model(x, t, y=c_crossattn[0], **kw)
+        raise NotImplementedError()
 
 
 class DDPM(nn.Module):

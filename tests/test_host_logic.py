@@ -326,3 +326,34 @@ def test_dit_state_dict_matches_reference(case):
     assert "pos_embed" in net.state_dict()
     with pytest.raises(P.B200Error):
         net(torch.zeros(1, m["hp"]["in_channels"], m["hp"]["input_size"], m["hp"]["input_size"]), torch.zeros(1))
+
+
+def test_diffusion_wrapper_dispatches_every_conditioning_key():
+    """DiffusionWrapper.forward (ddpm.py:1328-1365): which tensors reach the denoiser as x / context / y for each key."""
+    class Probe(torch.nn.Module):
+        def forward(self, x, t, context=None, y=None):
+            self.seen = (x, context, y)
+            return x[:, :1]
+
+    x, t = torch.zeros(2, 1, 4, 4), torch.zeros(2)
+    cc, ca = [torch.ones(2, 3, 4, 4)], [torch.ones(2, 5, 8), 2 * torch.ones(2, 2, 8)]
+    adm = torch.full((2, 6), 3.0)
+    for key, kw, xch, ctx_len, y in (
+            (None, {}, 1, None, None),
+            ("concat", {"c_concat": cc}, 4, None, None),
+            ("crossattn", {"c_crossattn": ca}, 1, 7, None),
+            ("hybrid", {"c_concat": cc, "c_crossattn": ca}, 4, 7, None),
+            ("hybrid-adm", {"c_concat": cc, "c_crossattn": ca, "c_adm": adm}, 4, 7, adm),
+            ("crossattn-adm", {"c_crossattn": ca, "c_adm": adm}, 1, 7, adm),
+            ("crossattn-adm", {"c_crossattn": [None], "c_adm": adm}, 1, None, adm),
+            ("adm", {"c_crossattn": [adm]}, 1, None, adm)):
+        probe = Probe()
+        out = S.DiffusionWrapper(probe, key)(x, t, **kw)
+        sx, sc, sy = probe.seen
+        assert out.shape == (2, 1, 4, 4) and sx.shape[1] == xch, key
+        assert (sc is None) if ctx_len is None else (sc.shape == (2, ctx_len, 8)), key
+        assert (sy is None) if y is None else torch.equal(sy, y), key
+    with pytest.raises(AssertionError):
+        S.DiffusionWrapper(Probe(), "hybrid-adm")(x, t, c_concat=cc, c_crossattn=ca)
+    with pytest.raises(AssertionError):
+        S.DiffusionWrapper(Probe(), "bogus")
