@@ -752,9 +752,14 @@ class DDIMSampler(object):
                       record=None, unconditional_guidance_scale=1., unconditional_conditioning=None, **unused):
         device = self.model.betas.device
         img = torch.randn(shape, device=device) if x_T is None else x_T.to(device)
-        if timesteps is not None:
-            raise NotImplementedError("ddim_sampling(timesteps=...) is not built in the B200 path")
         coef, tsteps = self._coef(ddim_use_original_steps, temperature)
+        if timesteps is not None:       # run only the LAST (lowest-noise) steps of the schedule, ddim.py:143-147
+            if ddim_use_original_steps:
+                keep = len(range(0, int(timesteps)))
+            else:
+                n = self.ddim_timesteps.shape[0]
+                keep = len(range(n)[:int(min(timesteps / n, 1) * n) - 1])
+            coef, tsteps = coef[len(tsteps) - keep:].contiguous(), tsteps[len(tsteps) - keep:]
         total_steps = len(tsteps)
         print(f"Running DDIM Sampling with {total_steps} timesteps")
         t_table = torch.tensor(tsteps, dtype=torch.float32, device=device)
@@ -767,6 +772,8 @@ class DDIMSampler(object):
                          **self.model._graph_cache_args())
         self.last_engine = self.model.last_engine = eng
         intermediates = {"x_inter": [img], "pred_x0": [img]}
+        if total_steps == 0:
+            return img, intermediates
 
         def on_step(i, x, x0):
             index = total_steps - i - 1

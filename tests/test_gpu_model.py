@@ -157,6 +157,32 @@ def test_graph_replay_equals_eager_loop():
     assert maxabs(outs[0], outs[1]) < 1e-5
 
 
+@pytest.mark.parametrize("orig", [False, True])
+def test_ddim_sampling_timestep_subset_runs_the_last_steps(orig):
+    """ddim_sampling(timesteps=k) (ddim.py:143-147): only the lowest-noise steps of the schedule run, with the table rows
+    index = k'-1 .. 0; checked against single p_sample_ddim steps at those indices with the same noise."""
+    S, m = _ldm("v", T=40 if orig else 2000)
+    g = golden("v1_ddim_v_eta0.7")
+    x_T, cond = g["x_T"].cuda(), g["cond"].cuda()
+    smp = S.DDIMSampler(m)
+    smp.make_schedule(8, ddim_eta=0.7, verbose=False)
+    k = 5
+    keep = k if orig else int(min(k / 8, 1) * 8) - 1             # the reference drops one more step in this branch
+    nz = [torch.randn_like(x_T) for _ in range(keep)]
+    out, inter = smp.ddim_sampling(cond, tuple(x_T.shape), x_T=x_T, timesteps=k, ddim_use_original_steps=orig,
+                                   noises=nz, log_every_t=1)
+    assert len(inter["x_inter"]) == keep + 1
+    steps = list(range(40)) if orig else list(smp.ddim_timesteps)
+    x = x_T
+    for i in range(keep):
+        index = keep - 1 - i
+        ts = torch.full((x.shape[0],), int(steps[index]), device="cuda", dtype=torch.long)
+        x, _ = smp.p_sample_ddim(x, cond, ts, index=index, use_original_steps=orig, noise=nz[i])
+    assert maxabs(out.cpu(), x.cpu()) < 1e-5
+    same, _ = smp.ddim_sampling(cond, tuple(x_T.shape), x_T=x_T, timesteps=0 if orig else 1, ddim_use_original_steps=orig)
+    assert torch.equal(same, x_T)                                 # empty subset: x_T comes back untouched
+
+
 # -------------------------------------------------------------------------------------------------
 # DS-Diff backbone + guided-diffusion samplers (the shipped default inference path, cfg2')
 # -------------------------------------------------------------------------------------------------
