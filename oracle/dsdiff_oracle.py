@@ -82,7 +82,7 @@ def _q(opq, x):
 def timestep_embedding(t: Tensor, dim: int, max_period: float = 10000.0) -> Tensor:
     """cos||sin sinusoidal embedding; accepts float t.  util.py:161-181."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half).to(t.device)  # :171-174
     args = t[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:
