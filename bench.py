@@ -406,7 +406,11 @@ def run_b200(args):
             ach = (v["flops"] / v["ms"] / 1e9) if tensor else (v["bytes"] / v["ms"] / 1e6)
             peak = pk["tensor"] if tensor else pk["hbm"]
             entry = {"kernel": name, "bound": "tensor" if tensor else "hbm", "achieved": ach, "peak": peak,
-                     "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak, "traffic": traffic_note(name),
+                     "unit": "TFLOP/s" if tensor else "GB/s", "frac": ach / peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch from the committed ncu --set full capture
+                     # (bytes; null when no capture exists); which launch and its algorithmic bytes: traffic_detail
+                     "traffic": (traffic_note(name) or {}).get("dram_bytes_per_launch"),
+                     "traffic_detail": traffic_note(name),
                      "launches_per_denoise_step": v["launches"], "ms_per_denoise_step": v["ms"],
                      "share_of_step": (v["ms"] / total_ms) if not name.startswith("sampler_update") else None,
                      "peak_source": pk["source"] + (" (sustained)" if tensor else " (copy)")}
@@ -417,7 +421,7 @@ def run_b200(args):
                                            "share_of_bytes": lg["bytes"] / v["bytes"]}
             aux.append(entry)
         dom = next(e for e in aux if e["kernel"] == "conv_igemm")
-        res["roofline"] = {k: dom[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
+        res["roofline"] = {k: dom[k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "traffic_detail")}
         res["roofline"].update({"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM)", "peak_source": dom["peak_source"],
                                 "share_of_step": dom["share_of_step"],
                                 "how": "sum of algorithmic conv FLOPs of one denoising step / sum of per-launch "
