@@ -931,6 +931,92 @@ class GaussianDiffusion:
         return eng.run(img, cond, T, noises=noises, use_graph=self.use_graph, want_x0=record is not None,
                        record=record)
 
+    # ---- forward process + single reverse steps (the pieces the loops above fuse) ----
+    def _gather(self, arr, t: Tensor) -> Tensor:
+        """_extract_into_tensor (:1097-1109) without the broadcast: float64 table -> float32 -> [t]."""
+        return _f32(arr).to(t.device)[t.reshape(-1).long()]
+
+    @torch.no_grad()
+    def q_sample(self, x_start, t, noise=None):
+        """sqrt(abar_t) x_0 + sqrt(1 - abar_t) noise (:199-215), per-sample t."""
+        noise = torch.randn_like(x_start) if noise is None else noise
+        assert noise.shape == x_start.shape
+        return ops.lincomb2(x_start, noise, self._gather(self.sqrt_alphas_cumprod, t),
+                            self._gather(self.sqrt_one_minus_alphas_cumprod, t))
+
+    @torch.no_grad()
+    def get_v(self, x, noise, t):
+        """sqrt(abar_t) noise - sqrt(1 - abar_t) x (:376-380)."""
+        return ops.lincomb2(noise, x, self._gather(self.sqrt_alphas_cumprod, t),
+                            self._gather(self.sqrt_one_minus_alphas_cumprod, t), subtract=True)
+
+    @torch.no_grad()
+    def predict_start_from_z_and_v(self, x_t, t, v):
+        """sqrt(abar_t) x_t - sqrt(1 - abar_t) v (:239-245)."""
+        return ops.lincomb2(x_t, v, self._gather(self.sqrt_alphas_cumprod, t),
+                            self._gather(self.sqrt_one_minus_alphas_cumprod, t), subtract=True)
+
+    def _single_step(self, mode, model, x, t, clip_denoised, denoised_fn, cond_fn, model_kwargs, eta, noise=None):
+        if denoised_fn is not None or cond_fn is not None:
+            raise NotImplementedError("denoised_fn / cond_fn are not built in the B200 path")
+        tt = t.reshape(-1)
+        ti = int(tt[0])
+        if not bool((tt == ti).all()):
+            raise NotImplementedError("B200 path: one timestep per p_sample / ddim_sample call")
+        net = model.diffusion_model if isinstance(model, DiffusionWrapper) else model
+        xc = x.float()
+        if model_kwargs and model_kwargs.get("c_concat") is not None:
+            xc = torch.cat([xc] + [c.to(x.device).float() for c in model_kwargs["c_concat"]], dim=1)
+        tm = torch.full((x.shape[0],), self._model_timestep(ti), dtype=torch.float32, device=x.device)
+        extra = {"return_features": False} if getattr(net, "_returns_features", False) else {}
+        out = net(xc.contiguous(), tm, **extra)
+        out = out[0] if isinstance(out, tuple) else out
+        cache = self.__dict__.setdefault("_coef_cache", {})
+        key = (float(eta), str(x.device))
+        if key not in cache:
+            cache[key] = self._coef(eta).to(x.device)
+        z = torch.randn_like(x) if noise is None else noise.to(x.device)     # drawn even at t == 0, like :455 / :653
+        x_prev, x0 = ops.sampler_update(mode, self._param(), x.float().contiguous(), out.contiguous(),
+                                        z.float().contiguous(), cache[key], step=self.num_timesteps - 1 - ti,
+                                        clip_denoised=clip_denoised, learned_range=self.model_var_type == "learned_range")
+        return {"sample": x_prev, "pred_xstart": x0}
+
+    @torch.no_grad()
+    def p_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None, noise=None):
+        """One ancestral step (:423-466): {'sample', 'pred_xstart'}."""
+        return self._single_step(L.SAMPLER_GD_DDPM, model, x, t, clip_denoised, denoised_fn, cond_fn, model_kwargs, 0.0,
+                                 noise)
+
+    @torch.no_grad()
+    def ddim_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None, eta=0.0,
+                    noise=None):
+        """One DDIM step (:620-667): {'sample', 'pred_xstart'}."""
+        return self._single_step(L.SAMPLER_GD_DDIM, model, x, t, clip_denoised, denoised_fn, cond_fn, model_kwargs, eta,
+                                 noise)
+
+    def _progressive(self, step_fn, model, shape, noise, device, **kw):
+        if device is None:
+            device = next(model.parameters()).device
+        assert isinstance(shape, (tuple, list))
+        img = noise.to(device) if noise is not None else torch.randn(*shape, device=device)
+        for i in range(self.num_timesteps - 1, -1, -1):
+            t = torch.tensor([i] * shape[0], device=device)
+            out = step_fn(model, img, t, **kw)
+            yield out
+            img = out["sample"]
+
+    def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                                  model_kwargs=None, device=None, progress=False):
+        """Generator over the per-step dicts (:570-618); eager single steps (the graph-replayed loop is p_sample_loop)."""
+        return self._progressive(self.p_sample, model, shape, noise, device, clip_denoised=clip_denoised,
+                                 denoised_fn=denoised_fn, cond_fn=cond_fn, model_kwargs=model_kwargs)
+
+    def ddim_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                                     model_kwargs=None, device=None, progress=False, eta=0.0):
+        """:742-789."""
+        return self._progressive(self.ddim_sample, model, shape, noise, device, clip_denoised=clip_denoised,
+                                 denoised_fn=denoised_fn, cond_fn=cond_fn, model_kwargs=model_kwargs, eta=eta)
+
     @torch.no_grad()
     def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                       model_kwargs=None, device=None, progress=False, **kw):
