@@ -30,6 +30,7 @@ from __future__ import annotations
 
 import importlib
 import math
+import warnings
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -668,6 +669,14 @@ class DDIMSampler(object):
         setattr(self, name, attr)
 
     def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
+        # The tables are evaluated with numpy ufuncs on torch tensors, like the reference: numpy's fp32 sqrt / log and its
+        # float64-ndarray x fp32-tensor promotion decide the last bit (torch.sqrt differs by 1 ulp on some entries —
+        # measured), and tests/test_host_logic.py pins them bit-exactly.  NumPy 2 flags Tensor.__array_wrap__'s signature.
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", DeprecationWarning)
+            self._make_schedule(ddim_num_steps, ddim_discretize, ddim_eta, verbose)
+
+    def _make_schedule(self, ddim_num_steps, ddim_discretize, ddim_eta, verbose):
         self.ddim_timesteps = make_ddim_timesteps(ddim_discretize, ddim_num_steps, self.ddpm_num_timesteps, verbose)
         ac = self.model.alphas_cumprod
         assert ac.shape[0] == self.ddpm_num_timesteps, "alphas have to be defined for each timestep"
