@@ -52,6 +52,26 @@ def main():
         save(f"train_ds_film2_{tag}", x0=x0, cond=torch.stack(cond), noise=noise, t=t, x_t=x_t,
              **{k: v for k, v in terms.items() if k != "contrast_map"})
 
+    # gradients of the trainer's total loss (trainers/trainer_use_gaussian_diff.py:464-478):
+    #   mean(contrast_lambda * (disen_c_s + disen_s_a_l) + mse + vb)
+    lam = 0.1
+    diff = create_gaussian_diffusion(steps=1000, learn_sigma=True, noise_schedule="linear", rescale_timesteps=True,
+                                     timestep_respacing="", parameterization="v")
+    net.zero_grad()
+    terms = diff.training_losses(model, x0, t, noise=noise, disentangle="eu", disen_lambda=lam,
+                                 model_kwargs={"F_Data1": cond[0], "F_Data2": cond[1], "S_Data1": cond[2]})
+    total = (lam * (terms["disen_c_s_loss"] + terms["disen_s_a_l_loss"]) + terms["loss"]).mean()
+    total.backward()
+    names = [k for k, p in net.named_parameters()]
+    norms = np.array([float(p.grad.double().norm()) if p.grad is not None else -1.0 for _, p in net.named_parameters()])
+    picks = ["out.2.weight", "time_embed.0.bias", "input_blocks.0.0.weight", "input_blocks_a.0.0.weight",
+             "middle_block.0.in_layers.2.bias"]
+    params = dict(net.named_parameters())
+    save("train_ds_film2_grads", total=total.detach(), lam=np.float64(lam), grad_norms=norms,
+         **{"g:" + k: params[k].grad for k in picks})
+    with open(os.path.join(MG.GOLD, "train_ds_film2_grads.names.txt"), "w") as f:
+        f.write("\n".join(names) + "\n")
+
 
 if __name__ == "__main__":
     main()

@@ -67,3 +67,40 @@ def test_disentangle_loss_labels_and_value():
     diff = sum(np.sqrt(2) * abs(a - b) / 2 for a in (0.0, 0.1) for b in (10.0, 10.1)) * 2
     assert abs(float(loss) - same / diff) < 1e-6
     assert perfect.tolist()[0] == [1, 1, -1, -1] and logits.shape == (4, 4)
+
+
+def test_training_gradients_oracle_matches_reference():
+    """Backward of the trainer's total loss (trainer_use_gaussian_diff.py:464-478) through the oracle network (torch autograd
+    over the restated forward) vs the reference's own .backward(): per-parameter gradient norms for all 384 parameter
+    tensors plus five full gradient tensors.  This is the target the CUDA dgrad / wgrad / GroupNorm-backward kernels will be
+    held to."""
+    import os
+    from _util import GOLD
+    g = golden("train_ds_film2_grads")
+    gi = golden("train_ds_film2_mse")
+    names = open(os.path.join(GOLD, "train_ds_film2_grads.names.txt")).read().split()
+    hp, sd = synth_sd("ds_film2")
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    sch = O.GdSchedule(steps=1000, noise_schedule="linear", timestep_respacing="", rescale_timesteps=True)
+    terms = TO.training_losses(sch, lambda xc, tm: O.dsunet_forward(sd, hp, xc, tm), gi["x0"], gi["t"], gi["noise"],
+                               list(gi["cond"]), parameterization="v", learn_sigma=True, disentangle="eu")
+    total = (g["lam"] * (terms["disen_c_s_loss"] + terms["disen_s_a_l_loss"]) + terms["loss"]).mean()
+    assert _close(total.detach(), g["total"])
+    total.backward()
+    assert len(names) == g["grad_norms"].numel() == 384
+    worst = 0.0
+    # a bias in front of a one-channel-per-group GroupNorm has an exactly zero gradient; both sides hold ~1e-9 of
+    # roundoff there, so the relative check carries an absolute floor tied to the largest gradient in the network
+    floor = 1e-4 * float(g["grad_norms"].max())
+    for name, ref in zip(names, g["grad_norms"].tolist()):
+        got = sd[name].grad
+        if ref < 0:                      # parameter unused by the forward in the reference
+            assert got is None or float(got.abs().max()) == 0.0, name
+            continue
+        assert got is not None, name
+        worst = max(worst, abs(float(got.double().norm()) - ref) / max(ref, floor))
+    assert worst < 2e-4, worst
+    for k in g:
+        if k.startswith("g:"):
+            ref = g[k]
+            assert maxabs(sd[k[2:]].grad, ref) <= 2e-4 * max(floor, float(ref.abs().max())), k
