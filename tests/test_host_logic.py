@@ -357,3 +357,18 @@ def test_diffusion_wrapper_dispatches_every_conditioning_key():
         S.DiffusionWrapper(Probe(), "hybrid-adm")(x, t, c_concat=cc, c_crossattn=ca)
     with pytest.raises(AssertionError):
         S.DiffusionWrapper(Probe(), "bogus")
+
+
+def test_every_runtime_switch_is_documented():
+    """Each B200DIFF_* environment variable read by the library or the package is described in DESIGN.md."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "diffusion_models_dsdiff_b200")
+    found = set()
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".py", ".h")):
+                found |= set(re.findall(r"B200DIFF_[A-Z0-9_]+", open(os.path.join(d, f), errors="ignore").read()))
+    found.discard("B200DIFF_DEBUG_TOGGLES")          # compile-time macro, described next to B200DIFF_SKIP_EPI
+    design = open(os.path.join(root, "DESIGN.md")).read()
+    missing = sorted(v for v in found if v not in design)
+    assert not missing, missing
