@@ -114,3 +114,34 @@ def test_sample_volume_is_independent_of_world_size_and_batch(world, tmp_path):
     single = PAR.sample_volume(_fake_sampler, cond, batch_size=13, base_seed=7, multiple=32)
     assert single.shape == (13, 1, 24, 24)
     assert torch.equal(torch.load(out), single)
+
+
+def _predict_worker(rank, world, port, tdir, odir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from diffusion_models_dsdiff_b200 import volume_io as V
+        cond = torch.arange(7 * 3 * 24 * 24, dtype=torch.float32).reshape(7, 3, 24, 24) / 1e4
+        full = PAR.sample_volume(_fake_sampler, cond, batch_size=2, base_seed=11, multiple=32)
+        assert (full is None) == (rank != 0)
+        if rank == 0:            # rank 0 alone owns the 2D -> 3D assembly and the file (on_predict_end)
+            asm = V.PredictionAssembler(["P7"])
+            asm.add_paths([f"/data/test/P7/P7_{i}.h5" for i in range(7)], full)
+            asm.finalize(tdir, odir)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_volume_to_nifti_end_to_end(tmp_path):
+    """cfg4 glue on two gloo ranks: shard the slices, sample, gather, assemble, write <id>_pred.nii.gz from the template."""
+    import numpy as np
+    from test_volume_io import _write_template
+    from diffusion_models_dsdiff_b200 import volume_io as V
+    tdir, odir = str(tmp_path / "templates"), str(tmp_path / "out")
+    _write_template(os.path.join(tdir, "P7", "T1CE.nii.gz"), np.zeros((7, 24, 24), np.float32))
+    mp.spawn(_predict_worker, args=(2, _free_port(), tdir, odir), nprocs=2, join=True)
+    cond = torch.arange(7 * 3 * 24 * 24, dtype=torch.float32).reshape(7, 3, 24, 24) / 1e4
+    single = PAR.sample_volume(_fake_sampler, cond, batch_size=7, base_seed=11, multiple=32)
+    vol, hdr = V.read_nifti(os.path.join(odir, "P7_pred.nii.gz"))
+    assert hdr.shape == (7, 24, 24)
+    assert np.array_equal(vol, single[:, 0].numpy())
