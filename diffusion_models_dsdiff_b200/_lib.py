@@ -12,6 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200diff.so")
 
+ABI_VERSION = 10        # must equal B200_ABI_VERSION of the header the library was built from
 F16, BF16 = 0, 1
 SAMPLER_LDM_DDIM, SAMPLER_LDM_DDPM, SAMPLER_GD_DDIM, SAMPLER_GD_DDPM, SAMPLER_DPMPP_2M = 0, 1, 2, 3, 4
 SAMPLER_NCOEF = 16
@@ -33,7 +34,8 @@ class ConvDesc(C.Structure):
                 ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rowbias_stride", C.c_int),
                 ("residual", C.c_void_p), ("res_scale", C.c_float), ("out", C.c_void_p),
                 ("gn_sums", C.c_void_p), ("act_dtype", C.c_int), ("out_nchw_f32", C.c_void_p), ("cout_real", C.c_int), ("rowscale", C.c_void_p), ("rowscale_stride", C.c_int), ("epi_act", C.c_int), ("out_nhwc_f32", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("range_events", C.c_void_p),
+                ("wsets", C.c_int), ("rowbias_gstride", C.c_int), ("rowscale_gstride", C.c_int)]
 
 
 class SamplerDesc(C.Structure):
@@ -70,7 +72,7 @@ SIGNATURES = {
     "b200_groupnorm_stats": [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P],
     "b200_groupnorm_apply": [_P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _I, _I, _P, _I, _P],
     "b200_channel_stats": [_P, _I, _I, _I, _P, _I, _P],
-    "b200_groupnorm_apply_cs": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _I, _I, _P, _P, _I, _I, _P],
+    "b200_groupnorm_apply_cs": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P],
     "b200_attention_qkv": [_P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
     "b200_attention": [C.POINTER(AttnDesc), _P],
     "b200_layernorm": [_P, _P, _P, _P, _P, _I, _I, _L, _I, _F, _P, _I, _P],
@@ -115,6 +117,10 @@ def lib() -> C.CDLL:
             fn = getattr(l, name)
             fn.argtypes = args
             fn.restype = _RESTYPE.get(name, C.c_int)
+        got = int(l.b200_abi_version())
+        if got != ABI_VERSION:      # struct layouts below would not match: refuse instead of corrupting memory
+            raise B200Error(f"{LIB_PATH} was built for ABI {got}, this package binds ABI {ABI_VERSION}: rebuild it "
+                            "(__graft_entry__.build() or `make -C diffusion_models_dsdiff_b200/csrc`)")
         _lib = l
     return _lib
 

@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import ops
 from ._lib import B200Error
-from .unet import Act, Ctx, PackedWeights, _f, default_act_dtype, run_conv, run_gn
+from .unet import Act, Ctx, PackedWeights, _f, default_act_dtype, param_fingerprint, run_conv, run_gn
 
 Tensor = torch.Tensor
 
@@ -369,24 +369,35 @@ class AutoencoderKL(nn.Module):
     def _ctx(self, device) -> Ctx:
         if device.type != "cuda":
             raise B200Error("the B200 engine has no CPU path: move the module and its input to a CUDA device")
+        fp = param_fingerprint(self)
+        if self._pw is not None and fp != getattr(self, "_pw_fp", None):      # in-place weight update since the last pack
+            self.invalidate()
         if self._pw is None or self._pw.dtype != self.act_dtype:
             with torch.no_grad():
                 self._pw = PackedWeights(self, self.act_dtype)
+            self._pw_fp = fp
         self._arena.begin(device)
         return Ctx(self._pw, None, self._arena)
+
+    def _range_check(self, device) -> None:
+        if not torch.cuda.is_current_stream_capturing():      # fp16 range guard (ops.check_range)
+            ops.check_range(device, "AutoencoderKL")
 
     @torch.no_grad()
     def encode(self, x):
         cx = self._ctx(x.device)
         h = run_encoder(cx, self.encoder, x, self.act_dtype)
         moments = ops.conv1x1_f32(h, _f(self.quant_conv.weight), _f(self.quant_conv.bias))
+        self._range_check(x.device)
         return DiagonalGaussianDistribution(moments)
 
     @torch.no_grad()
     def decode(self, z):
         cx = self._ctx(z.device)
         z = ops.conv1x1_f32(z.float(), _f(self.post_quant_conv.weight), _f(self.post_quant_conv.bias))
-        return run_decoder(cx, self.decoder, z, self.act_dtype)
+        out = run_decoder(cx, self.decoder, z, self.act_dtype)
+        self._range_check(z.device)
+        return out
 
     @torch.no_grad()
     def forward(self, input, sample_posterior=True):

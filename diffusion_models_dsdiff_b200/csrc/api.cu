@@ -105,7 +105,7 @@ int cached_tmap(CUtensorMap *out, const void *base, int rank, const uint64_t *di
 
 }  // namespace b200
 
-extern "C" int b200_abi_version(void) { return 9; }
+extern "C" int b200_abi_version(void) { return B200_ABI_VERSION; }
 extern "C" const char *b200_last_error(void) { return b200::g_err; }
 extern "C" uint64_t b200_launch_count(void) { return b200::g_launches.load(); }
 

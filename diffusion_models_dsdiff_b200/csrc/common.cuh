@@ -93,6 +93,31 @@ __device__ __forceinline__ float silu_f(float v) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
   return v * r;
 }
+// SiLU of 8 values with 1.25 MUFU ops per element instead of 2: one ex2 each, and ONE reciprocal per four values —
+// 1/a = (1/(abcd)) * bcd.  The GroupNorm+SiLU pass is HBM-bound on paper but sat at ~70 % MUFU-pipe utilisation (2 MUFU
+// per element), which capped it at 0.72-0.82 of the copy bandwidth.  The exponent is clamped to 2^30 so the four-way
+// product stays finite: sigmoid(v) for v < -20.8 becomes 9.3e-10 instead of <= 9.3e-10 (absolute error of SiLU < 2e-8).
+// ~4 ulp (5e-7 relative) — three orders below the 16-bit rounding of the stored result.
+__device__ __forceinline__ void silu8(float (&v)[8]) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(v[i] * -1.4426950408889634f, 30.f)));
+    a[i] = 1.f + e;
+  }
+#pragma unroll
+  for (int h = 0; h < 8; h += 4) {
+    const float pab = a[h] * a[h + 1], pcd = a[h + 2] * a[h + 3];
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(pab * pcd));
+    const float rab = r * pcd, rcd = r * pab;
+    v[h] *= rab * a[h + 1];
+    v[h + 1] *= rab * a[h];
+    v[h + 2] *= rcd * a[h + 3];
+    v[h + 3] *= rcd * a[h + 2];
+  }
+}
 // GELU(tanh) (DiTBlock's Mlp, UNet_DS_Diff/DiT_models.py:111): 0.5 x (1 + tanh(u)) = x * sigmoid(2u),
 // u = sqrt(2/pi) (x + 0.044715 x^3); two MUFU ops (~1e-7 relative) instead of tanhf
 __device__ __forceinline__ float gelu_tanh_f(float x) {

@@ -58,7 +58,14 @@ struct ConvKParams {
   long long split_stride;    // floats between consecutive partial planes of the workspace
   int pdl;                   // launched with programmatic stream serialization (B200DIFF_PDL=1)
   int vec32;                 // Cout % 16 == 0 and 32-byte aligned out / residual: 256-bit epilogue loads / stores
+  unsigned int *range_events; // fp16 only: += 1 per (thread, tile) that had to saturate a result (see b200diff.h)
+  int wsets, n_per_set;      // grouped along N: image n uses weight set n / n_per_set (wsets == 1: n_per_set = N)
+  int rowbias_gstride, rowscale_gstride;
 };
+
+template <typename T> struct IsHalf { static constexpr bool value = false; };
+template <> struct IsHalf<__half> { static constexpr bool value = true; };
+constexpr float kHalfOverflow = 65520.f;    // smallest magnitude that rounds past the largest finite fp16 (65504)
 
 // Column sums of a 32 (lanes) x 16 (registers) tile by recursive halving: 16 shuffles instead of 16 x 5.
 // Returns on every lane the total of column (lane >> 1).
@@ -266,18 +273,22 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       pt /= p.tiles_w;
       const int h0 = (pt % p.tiles_h) * p.TH;
       const int n0 = (pt / p.tiles_h) * p.TN;                // >= N for the odd tile out: all-zero boxes
+      const int wset = min(n0 / p.n_per_set, p.wsets - 1);   // the tile's weight set (a tile never straddles two sets)
       for (int s = 0; s < p.nseg; ++s) {
         const int ks = p.seg_ks[s], pad = p.seg_pad[s], cin = p.seg_cin[s];
+        const int tbase = wset * ks * ks;                    // weight sets are stacked along the tap axis of the TMA map
         if (p.seg_halo[s]) {
           for (int c0 = 0; c0 < cin; c0 += kBK)
             for (int sx = 0; sx < 3; ++sx, ++gi)
-              if (gi >= g_begin && gi < g_end) load_group(s, c0, n_tile, sx, 3, 3, halo_bytes, w0 + sx - 1, h0 - 1, n0);
+              if (gi >= g_begin && gi < g_end)
+                load_group(s, c0, n_tile, tbase + sx, 3, 3, halo_bytes, w0 + sx - 1, h0 - 1, n0);
         } else {
           for (int tap = 0; tap < ks * ks; ++tap) {
             const int r = tap / ks, sx = tap - r * ks;
             for (int c0 = 0; c0 < cin; c0 += kBK, ++gi)
               if (gi >= g_begin && gi < g_end)
-                load_group(s, c0, n_tile, tap, 0, 1, (uint32_t)kABytes, w0 * p.stride + sx - pad, h0 * p.stride + r - pad, n0);
+                load_group(s, c0, n_tile, tbase + tap, 0, 1, (uint32_t)kABytes, w0 * p.stride + sx - pad,
+                           h0 * p.stride + r - pad, n0);
           }
         }
       }
@@ -405,6 +416,14 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
         acc_n = n_warp;
         acc_ntile = n_tile;
       }
+      // weight set of this warp's rows / of this thread's row (grouped along N; 0 for ordinary launches)
+      const int ws_warp = min(n_warp / p.n_per_set, p.wsets - 1);
+      const int ws_thr = min(n / p.n_per_set, p.wsets - 1);
+      const float *bias_t = p.bias ? p.bias + (size_t)ws_thr * p.Cout : nullptr;
+      const float *rowbias_t = p.rowbias ? p.rowbias + (size_t)ws_thr * p.rowbias_gstride +
+                                               (size_t)(n - ws_thr * p.n_per_set) * p.rowbias_stride : nullptr;
+      const float *rowscale_t = p.rowscale ? p.rowscale + (size_t)ws_thr * p.rowscale_gstride +
+                                                 (size_t)(n - ws_thr * p.n_per_set) * p.rowscale_stride : nullptr;
       if (staged_bias) {
         __syncwarp();
         for (int slot = lane; slot < 128; slot += 32) {
@@ -412,13 +431,17 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
           const int co = n_tile * p.BN + chunk * 16 + (slot & 15);
           float b = 0.f;
           if (chunk * 16 < p.BN && co < p.Cout) {
-            if (p.bias) b = __ldg(p.bias + co);
-            if (p.rowbias && n_warp < p.N) b += __ldg(p.rowbias + (size_t)n_warp * p.rowbias_stride + co);
+            if (p.bias) b = __ldg(p.bias + (size_t)ws_warp * p.Cout + co);
+            if (p.rowbias && n_warp < p.N)
+              b += __ldg(p.rowbias + (size_t)ws_warp * p.rowbias_gstride +
+                         (size_t)(n_warp - ws_warp * p.n_per_set) * p.rowbias_stride + co);
           }
           bs[slot] = b;
         }
         __syncwarp();
       }
+      float amax = 0.f;          // largest |result| this thread stores in this tile (fp16 range guard)
+      const bool guard = IsHalf<T>::value && p.range_events != nullptr;
       if (res && valid) {
         // pull this pixel's residual row segment HBM -> L2 while the tile's MMAs are still running
         const char *rrow = reinterpret_cast<const char *>(res + pix * p.Cout + n_tile * p.BN);
@@ -463,7 +486,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
             for (int i = 0; i < 16; ++i) v[i] = gelu_tanh_f(v[i]);
           }
           if (p.rowscale) {          // adaLN-Zero gate of this image (a warp's rows lie in one image: TW*TH >= 32)
-            const float4 *gp = reinterpret_cast<const float4 *>(p.rowscale + (size_t)n * p.rowscale_stride + co);
+            const float4 *gp = reinterpret_cast<const float4 *>(rowscale_t + co);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 g4 = __ldg(gp + j);
@@ -478,6 +501,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
               v[2 * j] = fmaf(p.res_scale, f.x, v[2 * j]);
               v[2 * j + 1] = fmaf(p.res_scale, f.y, v[2 * j + 1]);
             }
+          }
+          if (guard) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(v[i]));
           }
           packed[0] = pack8_sat<T>(v);
           packed[1] = pack8_sat<T>(v + 8);
@@ -527,13 +554,13 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
               vh[4] += b1.x; vh[5] += b1.y; vh[6] += b1.z; vh[7] += b1.w;
             } else {
             if (p.bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4 *>(p.bias + cb));
-              const float4 b1 = __ldg(reinterpret_cast<const float4 *>(p.bias + cb + 4));
+              const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias_t + cb));
+              const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias_t + cb + 4));
               vh[0] += b0.x; vh[1] += b0.y; vh[2] += b0.z; vh[3] += b0.w;
               vh[4] += b1.x; vh[5] += b1.y; vh[6] += b1.z; vh[7] += b1.w;
             }
             if (p.rowbias) {
-              const float *rb = p.rowbias + (size_t)n * p.rowbias_stride + cb;
+              const float *rb = rowbias_t + cb;
               const float4 b0 = __ldg(reinterpret_cast<const float4 *>(rb));
               const float4 b1 = __ldg(reinterpret_cast<const float4 *>(rb + 4));
               vh[0] += b0.x; vh[1] += b0.y; vh[2] += b0.z; vh[3] += b0.w;
@@ -545,7 +572,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
               for (int i = 0; i < 8; ++i) vh[i] = gelu_tanh_f(vh[i]);
             }
             if (p.rowscale) {
-              const float *rs = p.rowscale + (size_t)n * p.rowscale_stride + cb;
+              const float *rs = rowscale_t + cb;
               const float4 g0 = __ldg(reinterpret_cast<const float4 *>(rs));
               const float4 g1 = __ldg(reinterpret_cast<const float4 *>(rs + 4));
               vh[0] *= g0.x; vh[1] *= g0.y; vh[2] *= g0.z; vh[3] *= g0.w;
@@ -556,6 +583,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
               unpack8<T>(rq[half], rf);
 #pragma unroll
               for (int i = 0; i < 8; ++i) vh[i] += p.res_scale * rf[i];
+            }
+            if (guard && !p.out_f32_nhwc && !p.out_f32) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(vh[i]));
             }
             if (p.out_f32_nhwc) {
               float4 *o4 = reinterpret_cast<float4 *>(f32_out + pix * p.Cout + cb);
@@ -628,6 +659,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
         if (kCtas == 2) mbar_arrive_cluster(empty_bar_leader0 + acc * 8u);   // the leader's barrier (8 B apart)
         else mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
       }
+      if (guard && amax >= kHalfOverflow) atomicAdd(p.range_events, 1u);
     }
     if (p.gn_sums && acc_n >= 0) flush_stats();
   }
@@ -750,7 +782,7 @@ static int conv_ksplit(const b200_conv_desc *d) {
   const int G = conv_groups_total(d);
   if (G < 36) return 1;
   // work items a NOMINAL batch of 8 images would give without splitting (geometry only)
-  const long tiles8 = (long)cdiv(8 * d->Hout * d->Wout, 2 * kBM) * cdiv(d->Cout, pick_bn(d->Cout));
+  const long tiles8 = (long)std::max(1, d->wsets) * cdiv(8 * d->Hout * d->Wout, 2 * kBM) * cdiv(d->Cout, pick_bn(d->Cout));
   const int pairs = num_sms() / 2;
   int S = (int)((pairs + tiles8 / 2) / tiles8);
   S = std::min(S, std::min(16, G / 4));
@@ -761,8 +793,13 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 splitk_finalize_kernel(const float *__restrict__ ws, int S, long long split_stride, const float *__restrict__ bias,
                        const float *__restrict__ rowbias, int rowbias_stride, const T *__restrict__ residual,
-                       float res_scale, T *__restrict__ out, int HW, int C, int pix_per_block, double *__restrict__ sums) {
+                       float res_scale, T *__restrict__ out, int HW, int C, int pix_per_block, double *__restrict__ sums,
+                       int n_per_set, int rowbias_gstride, unsigned int *range_events) {
   const int n = blockIdx.y;
+  const int wset = n / n_per_set;
+  if (bias) bias += (size_t)wset * C;
+  if (rowbias) rowbias += (size_t)wset * rowbias_gstride + (size_t)(n - wset * n_per_set) * rowbias_stride;
+  float amax = 0.f;
   const int ncol = C >> 3;
   const int cpp = min(ncol, 256);
   const int rows = 256 / cpp;
@@ -777,7 +814,7 @@ splitk_finalize_kernel(const float *__restrict__ ws, int S, long long split_stri
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       bv[i] = (bias && active) ? bias[c0 + i] : 0.f;
-      if (rowbias && active) bv[i] += rowbias[(size_t)n * rowbias_stride + c0 + i];
+      if (rowbias && active) bv[i] += rowbias[c0 + i];
     }
     float s[8] = {0}, q[8] = {0};
     for (int p = p_begin + row; active && p < p_end; p += rows) {
@@ -799,6 +836,10 @@ splitk_finalize_kernel(const float *__restrict__ ws, int S, long long split_stri
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = fmaf(res_scale, rf[i], v[i]);
       }
+      if (IsHalf<T>::value && range_events) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[i]));
+      }
       const uint4 u = pack8_sat<T>(v);
       *reinterpret_cast<uint4 *>(out + off) = u;
       if (sums) {
@@ -810,6 +851,7 @@ splitk_finalize_kernel(const float *__restrict__ ws, int S, long long split_stri
     if (sums) block_flush_col_sums(s, q, active, row, col % cpp, cpp, rows, sums + ((size_t)n * C + c0) * 2);
     __syncthreads();
   }
+  if (IsHalf<T>::value && range_events && amax >= kHalfOverflow) atomicAdd(range_events, 1u);
 }
 
 template <typename T, int kCtas, bool kFast>
@@ -836,6 +878,10 @@ static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t
   p.vec32 = d->Cout % 16 == 0 && (((uintptr_t)d->out | (uintptr_t)d->residual) & 31) == 0 && !getenv("B200DIFF_NO_VEC32");
   p.out_f32 = d->out_nchw_f32; p.cout_real = d->cout_real; p.out_f32_nhwc = d->out_nhwc_f32;
   p.rowscale = d->rowscale; p.rowscale_stride = d->rowscale_stride; p.epi_act = d->epi_act;
+  p.range_events = d->range_events;
+  p.wsets = std::max(1, d->wsets);
+  p.n_per_set = d->N / p.wsets;
+  p.rowbias_gstride = d->rowbias_gstride; p.rowscale_gstride = d->rowscale_gstride;
   p.ksplit = ksplit;
   p.groups_total = conv_groups_total(d);
   p.split_stride = (long long)d->N * d->Hout * d->Wout * d->Cout;
@@ -873,7 +919,7 @@ static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t
       if (int rc = cached_tmap(&maps.a[s], g.src, 4, dims, str, box, es)) return rc;
     }
     {  // weights: (Cin, Cout, taps)
-      uint64_t dims[3] = {(uint64_t)g.wcin, (uint64_t)d->Cout, (uint64_t)(g.ksize * g.ksize)};
+      uint64_t dims[3] = {(uint64_t)g.wcin, (uint64_t)d->Cout, (uint64_t)(g.ksize * g.ksize * p.wsets)};
       uint64_t str[2] = {(uint64_t)g.wcin * 2, (uint64_t)d->Cout * g.wcin * 2};
       uint32_t box[3] = {kBK, (uint32_t)(p.BN / kCtas), 1};
       uint32_t es[3] = {1, 1, 1};
@@ -913,7 +959,7 @@ static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t
     const int ppb = cdiv(HW, bps);
     splitk_finalize_kernel<T><<<dim3(cdiv(HW, ppb), d->N), 256, 0, stream>>>(
         p.out_f32_nhwc, ksplit, p.split_stride, d->bias, d->rowbias, d->rowbias_stride, (const T *)d->residual, d->res_scale,
-        (T *)d->out, HW, d->Cout, ppb, d->gn_sums);
+        (T *)d->out, HW, d->Cout, ppb, d->gn_sums, p.n_per_set, d->rowbias_gstride, d->range_events);
     B200_LAUNCH_CHECK();
     return 0;
   }
@@ -934,6 +980,9 @@ extern "C" int b200_conv2d_igemm(const b200_conv_desc *d, void *stream) {
   B200_CHECK(d->out != nullptr || d->out_nchw_f32 != nullptr || d->out_nhwc_f32 != nullptr, "conv: no output pointer");
   B200_CHECK(d->out_nchw_f32 == nullptr || (d->cout_real >= 1 && d->cout_real <= d->Cout && !d->gn_sums),
              "conv: bad NCHW fp32 head output request");
+  const int wsets = std::max(1, d->wsets);
+  B200_CHECK(wsets <= 8 && d->N % wsets == 0, "conv: N (%d) must be a multiple of the number of weight sets (%d <= 8)", d->N,
+             wsets);
   // CTA pairs need an N tile that splits into two halves of whole 8-row core groups (BN % 16 == 0 always holds)
   static const bool force_one_cta = getenv("B200DIFF_CONV_1CTA") != nullptr;
   int ctas, bn;
@@ -946,11 +995,21 @@ extern "C" int b200_conv2d_igemm(const b200_conv_desc *d, void *stream) {
     ctas = 2;                       // biggest tiles: least operand traffic; the split supplies the parallelism
     bn = pick_bn(d->Cout);
   }
-  const bool one_cta = force_one_cta || ctas == 1;
-  const int kc = one_cta ? 1 : 2;
-  // fast epilogue: 16-bit NHWC output, 32-byte aligned rows, every tile full, warp rows inside one image
   int TW = 1, TH = 1, TN = 1;
   pick_box(d->Hout, d->Wout, &TW, &TH, &TN);
+  bool one_cta = force_one_cta || ctas == 1;
+  if (wsets > 1) {
+    // a pixel tile (and a CTA pair's two tiles, which share one weight tile) must lie inside ONE weight set
+    const int n_per_set = d->N / wsets;
+    B200_CHECK(n_per_set % TN == 0, "conv: %d images per weight set do not tile with %d-image boxes", n_per_set, TN);
+    const long tiles_per_set = (long)cdiv(d->Wout, TW) * cdiv(d->Hout, TH) * (n_per_set / TN);
+    if (tiles_per_set % 2) {
+      B200_CHECK(ksplit == 1, "conv: grouped split-K launch needs an even number of pixel tiles per weight set");
+      one_cta = true;
+    }
+  }
+  const int kc = one_cta ? 1 : 2;
+  // fast epilogue: 16-bit NHWC output, 32-byte aligned rows, every tile full, warp rows inside one image
   const long ptiles = (long)cdiv(d->Wout, TW) * cdiv(d->Hout, TH) * cdiv(d->N, TN);
   static const bool no_fast = getenv("B200DIFF_CONV_NO_FAST_EPI") != nullptr;
   const bool fast = !no_fast && d->out && !d->out_nchw_f32 && !d->out_nhwc_f32 && d->epi_act <= 1 &&

@@ -191,7 +191,8 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
                 const double *__restrict__ cs0, const double *__restrict__ cs1,
                 const float *__restrict__ gamma, const float *__restrict__ beta,
                 const float *__restrict__ film, int film_stride, int silu, T *__restrict__ out,
-                const float *__restrict__ preshift, int preshift_stride, int pdl) {
+                const float *__restrict__ preshift, int preshift_stride, int pdl, int n_per_set, int film_gstride,
+                int preshift_gstride) {
   if (pdl) {      // programmatic dependent launch (see igemm_conv.cu): wait for the producer, release the consumer
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -204,6 +205,13 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
   const int C = C0 + C1;
   const int cpg = C / groups;
   const double cnt = (double)HW * (double)cpg;
+  {   // grouped along N (see b200_groupnorm_apply_cs): image n belongs to weight set n / n_per_set
+    const int wset = n / n_per_set, nl = n - wset * n_per_set;
+    gamma += (size_t)wset * C;
+    beta += (size_t)wset * C;
+    if (film) film += (size_t)wset * film_gstride + (size_t)nl * film_stride;
+    if (preshift) preshift += (size_t)wset * preshift_gstride + (size_t)nl * preshift_stride;
+  }
   // group statistics: tpg threads per group sum the producers' per-channel fp64 sums, then a shuffle tree (the serial
   // 30..60-channel loop of one thread per group was the launch floor of the small-map GroupNorms)
   int tpg = 1;
@@ -222,7 +230,7 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
           const double *src = c < C0 ? cs0 + ((size_t)n * C0 + c) * 2 : cs1 + ((size_t)n * C1 + (c - C0)) * 2;
           double cs = src[0], cq = src[1];
           if (preshift && c < C0) {
-            const double sh = (double)preshift[(size_t)n * preshift_stride + c];
+            const double sh = (double)preshift[c];
             cq += 2.0 * sh * cs + (double)HW * sh * sh;
             cs += (double)HW * sh;
           }
@@ -258,10 +266,10 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
       const float ga = gamma[c + i] * s_rstd[g];
       float aa = ga;
       float bb = beta[c + i] - s_mean[g] * ga;
-      if (preshift && c + i < C0) bb = fmaf(ga, preshift[(size_t)n * preshift_stride + c + i], bb);
+      if (preshift && c + i < C0) bb = fmaf(ga, preshift[c + i], bb);
       if (film) {
-        const float sc = 1.f + film[(size_t)n * film_stride + c + i];
-        const float sh = film[(size_t)n * film_stride + C + c + i];
+        const float sc = 1.f + film[c + i];
+        const float sh = film[C + c + i];
         aa *= sc;
         bb = bb * sc + sh;
       }
@@ -281,10 +289,8 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
         float f[8];
         unpack8<T>(u[j], f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float v = fmaf(f[i], a[i], b[i]);
-          f[i] = silu ? silu_f(v) : v;
-        }
+        for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], a[i], b[i]);
+        if (silu) silu8(f);
         st_stream(dst + (size_t)(p + j * rows) * C, pack8_fast<T>(f));
       }
     }
@@ -292,10 +298,8 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
       float f[8];
       unpack8<T>(ld_stream(src + (size_t)p * Cs), f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float v = fmaf(f[i], a[i], b[i]);
-        f[i] = silu ? silu_f(v) : v;
-      }
+      for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], a[i], b[i]);
+      if (silu) silu8(f);
       st_stream(dst + (size_t)p * C, pack8_fast<T>(f));
     }
   }
@@ -336,7 +340,10 @@ template <typename T>
 static int gn_apply(const void *x0, int C0, const void *x1, int C1, int N, int HW, int groups,
                     float eps, const double *stats, const double *cs0, const double *cs1, const float *gamma,
                     const float *beta, const float *film, int film_stride, int silu, void *out, cudaStream_t st,
-                    const float *preshift = nullptr, int preshift_stride = 0) {
+                    const float *preshift = nullptr, int preshift_stride = 0, int wsets = 1, int film_gstride = 0,
+                    int preshift_gstride = 0) {
+  wsets = std::max(1, wsets);
+  B200_CHECK(N % wsets == 0, "groupnorm: N (%d) must be a multiple of the number of weight sets (%d)", N, wsets);
   dim3 grid;
   int ppb;
   norm_grid(N, HW, std::min((C0 + C1) >> 3, kNormThreads), &grid, &ppb);
@@ -351,7 +358,8 @@ static int gn_apply(const void *x0, int C0, const void *x1, int C1, int N, int H
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   B200_CUDA(cudaLaunchKernelEx(&cfg, gn_apply_kernel<T>, (const T *)x0, C0, (const T *)x1, C1, HW, groups, eps, ppb, stats, cs0,
-                               cs1, gamma, beta, film, film_stride, silu, (T *)out, preshift, preshift_stride, (int)pdl));
+                               cs1, gamma, beta, film, film_stride, silu, (T *)out, preshift, preshift_stride, (int)pdl, N / wsets,
+                               film_gstride, preshift_gstride));
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -393,15 +401,16 @@ extern "C" int b200_groupnorm_apply(const void *x0, int C0, const void *x1, int 
 extern "C" int b200_groupnorm_apply_cs(const void *x0, int C0, const double *cs0, const void *x1, int C1,
                                        const double *cs1, int N, int HW, int groups, float eps, const float *gamma,
                                        const float *beta, const float *film, int film_stride, int silu, void *out,
-                                       const float *preshift, int preshift_stride, int act_dtype, void *stream) {
+                                       const float *preshift, int preshift_stride, int wsets, int film_gstride,
+                                       int preshift_gstride, int act_dtype, void *stream) {
   using namespace b200;
   if (x1 == nullptr) C1 = 0;
   if (int rc = check_gn(C0, C1, N, HW, groups)) return rc;
   B200_CHECK(cs0 != nullptr && (C1 == 0 || cs1 != nullptr), "groupnorm_apply_cs: missing channel sums");
   if (act_dtype == B200_F16)
-    return gn_apply<__half>(x0, C0, x1, C1, N, HW, groups, eps, nullptr, cs0, cs1, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream, preshift, preshift_stride);
+    return gn_apply<__half>(x0, C0, x1, C1, N, HW, groups, eps, nullptr, cs0, cs1, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream, preshift, preshift_stride, wsets, film_gstride, preshift_gstride);
   if (act_dtype == B200_BF16)
-    return gn_apply<__nv_bfloat16>(x0, C0, x1, C1, N, HW, groups, eps, nullptr, cs0, cs1, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream, preshift, preshift_stride);
+    return gn_apply<__nv_bfloat16>(x0, C0, x1, C1, N, HW, groups, eps, nullptr, cs0, cs1, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream, preshift, preshift_stride, wsets, film_gstride, preshift_gstride);
   B200_CHECK(false, "groupnorm: bad act_dtype");
 }
 

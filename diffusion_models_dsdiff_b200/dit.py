@@ -29,7 +29,7 @@ import torch.nn as nn
 from . import ops
 from ._lib import B200Error
 from .transformer import _dpad, _pad_heads_in, _pad_heads_out, linear_tokens
-from .unet import default_act_dtype
+from .unet import default_act_dtype, param_fingerprint
 
 Tensor = torch.Tensor
 
@@ -180,6 +180,7 @@ class _Packed:
 
 class DiT(nn.Module):
     """Diffusion model with a Transformer backbone (DiT_models.py:145-272)."""
+    _b200_engine = True       # the samplers' step engine drives this network (samplers._engine_model_fn)
 
     def __init__(self, input_size=32, patch_size=2, in_channels=4, hidden_size=1152, depth=28, num_heads=16,
                  mlp_ratio=4.0, class_dropout_prob=0.1, num_classes=1000, learn_sigma=True,
@@ -241,9 +242,13 @@ class DiT(nn.Module):
         dev = self.pos_embed.device
         if dev.type != "cuda":
             raise B200Error("the B200 engine has no CPU path: move the module to a CUDA device")
+        fp = param_fingerprint(self)
+        if self._pw is not None and fp != getattr(self, "_pw_fp", None):      # in-place weight update since the last pack
+            self.invalidate()
         if self._pw is None or self._pw.dtype != self.act_dtype:
             with torch.no_grad():
                 self._pw = _Packed(self, self.act_dtype)
+            self._pw_fp = fp
         return self._pw
 
     @torch.no_grad()
@@ -298,7 +303,10 @@ class DiT(nn.Module):
         fm = mod[:, len(self.blocks) * 6 * d:]
         a = ops.layer_norm(h, None, None, 1e-6, shift=fm[:, :d], scale=fm[:, d:])
         out = linear_tokens(a, pw.final, bias=pw.final_b, out_f32=True)                  # fp32 [N, T, >= p*p*c]
-        return ops.unpatchify(out, self.out_channels, gh, gw, p).to(x.dtype)
+        res = ops.unpatchify(out, self.out_channels, gh, gw, p).to(x.dtype)
+        if step_ptr is None and not torch.cuda.is_current_stream_capturing():      # fp16 range guard (ops.check_range)
+            ops.check_range(x.device, "DiT.forward")
+        return res
 
     def forward_with_cfg(self, x, t, y, cfg_scale):
         """DiT_models.py:256-272: classifier-free guidance on the first three channels (sic)."""

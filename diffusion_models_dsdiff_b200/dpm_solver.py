@@ -19,7 +19,8 @@ from typing import List, Optional
 import torch
 
 from . import _lib as L
-from .samplers import NCOEF, StepEngine, _engine_model_fn, _graph_cache_args, _PARAM, DiffusionWrapper
+from .samplers import (NCOEF, StepEngine, _engine_model_fn, _graph_cache_args, _PARAM, DiffusionWrapper, gd_conditioning,  # noqa: F401
+                       host_cond_list, host_context, host_denoiser, host_graph_cache)
 
 Tensor = torch.Tensor
 MODEL_TYPES = {"eps": "noise", "v": "v"}        # dpm_solver_new/sampler.py:14-17
@@ -178,17 +179,19 @@ class DPMSolverSampler(object):
         print(f'Data shape for DPM-Solver sampling is {size}, sampling steps {S}')
         cfg = None
         if unconditional_conditioning is not None and unconditional_guidance_scale != 1.:     # model_wrapper :323-331
-            cfg = dict(cfg_scale=unconditional_guidance_scale, uncond=self.model._cond_list(unconditional_conditioning),
-                       uncond_context=self.model._context(unconditional_conditioning))
+            cfg = dict(cfg_scale=unconditional_guidance_scale,
+                       uncond=host_cond_list(self.model, unconditional_conditioning),
+                       uncond_context=host_context(self.model, unconditional_conditioning))
         device = self.model.betas.device
         img = torch.randn(size, device=device) if x_T is None else x_T.to(device)
         ns = NoiseScheduleVP('discrete', betas=self.betas)
         m = self.model
-        x, eng = run_multistep(m.model.diffusion_model, ns, img, m._cond_list(conditioning), S,
+        x, eng = run_multistep(host_denoiser(m), ns, img, host_cond_list(m, conditioning), S,
                                MODEL_TYPES[m.parameterization], "time_uniform", True, None,
-                               m.__dict__.setdefault("_graphs", {}), context=m._context(conditioning),
+                               host_graph_cache(m), context=host_context(m, conditioning),
                                use_graph=self.use_graph, record=kwargs.get("record"), cfg=cfg)
-        self.last_engine = m.last_engine = eng
+        self.last_engine = eng
+        m.__dict__["last_engine"] = eng
         return x.to(device), None
 
 
@@ -201,12 +204,10 @@ def gaussian_dpm_solver_sample_loop(diffusion, model, shape, clip_denoised=None,
     x = torch.randn(*shape, device=device) if noise is None else noise.to(device)
     print(x.shape)
     ns = NoiseScheduleVP(schedule='discrete', betas=torch.from_numpy(diffusion.betas).float())
-    cond = None
-    if model_kwargs and model_kwargs.get("c_concat") is not None:
-        cond = list(model_kwargs["c_concat"])
-    net = model.diffusion_model if isinstance(model, DiffusionWrapper) else model
+    cond, context = gd_conditioning(model, model_kwargs)
+    net = host_denoiser(model)
     out, eng = run_multistep(net, ns, x, cond, diffusion.num_timesteps, "v", "logSNR", False, (0.995, 1.0),
                              diffusion.__dict__.setdefault("_graphs", {}), use_graph=getattr(diffusion, "use_graph", True),
-                             record=record)
+                             record=record, context=context)
     diffusion.last_engine = eng
     return out

@@ -285,6 +285,7 @@ class DSUnetModel(_EngineModule):
                 skip = skip_mean([skips[e].pop() for e in range(4)])
             h = run_sequential(cx, blk, h, skip)
         out = run_out_head(cx, self.out, h).to(x.dtype)
+        self._range_check(x.device, step_ptr)
         if not return_features:
             return out, None
         to = ops.nhwc_to_nchw

@@ -8,6 +8,7 @@ like the reference.  Nothing here has a CPU or eager fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -82,7 +83,11 @@ def _stream() -> int:
 def _dev(t: Tensor) -> None:
     if not t.is_cuda:
         raise L.B200Error("libb200diff has no CPU path: tensor is not on a CUDA device")
-    L.ensure_init(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    cur = torch.cuda.current_device()
+    idx = t.device.index if t.device.index is not None else cur
+    if idx != cur:      # kernels launch on the CURRENT device's stream: one process per GPU (torch.cuda.set_device first)
+        raise L.B200Error(f"tensor lives on cuda:{idx} but the current device is cuda:{cur}")
+    L.ensure_init(idx)
 
 
 def _p(t: Optional[Tensor]) -> Optional[int]:
@@ -147,8 +152,12 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
            rowbias: Optional[Tensor] = None, residual: Optional[Tensor] = None, res_scale: float = 1.0,
            out: Optional[Tensor] = None, stats: Optional[Tensor] = None, head_channels: int = 0,
            out_hw: Optional[Tuple[int, int]] = None, out_f32: bool = False, rowscale: Optional[Tensor] = None,
-           act: int = 0) -> Tensor:
-    """tcgen05 implicit-GEMM conv over up to 3 K-segments (see b200_conv2d_igemm)."""
+           act: int = 0, wsets: int = 1, rowbias_gstride: int = 0) -> Tensor:
+    """tcgen05 implicit-GEMM conv over up to 3 K-segments (see b200_conv2d_igemm).
+
+    ``wsets`` > 1: grouped along N — the batch is ``wsets`` equal groups of images, group g convolves with its own weight
+    set (``weight`` is the stack [wsets * k * k, Cout, Cin]), ``bias`` is [wsets, Cout] and ``rowbias`` advances by
+    ``rowbias_gstride`` floats per group."""
     src0, w0, _, k0, p0 = segs[0]
     _dev(src0)
     n, hin, win, _ = src0.shape
@@ -162,7 +171,8 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
     for i, (src, wt, coff, ks, pad) in enumerate(segs):
         if src.shape[:3] != src0.shape[:3] or src.dtype != src0.dtype or wt.dtype != src0.dtype:
             raise L.B200Error("conv2d: segments must share N,H,W and dtype")
-        if (out_hw is None and (hin + 2 * pad - ks) // stride + 1 != hout) or wt.shape[1] != cout or wt.shape[0] != ks * ks:
+        if ((out_hw is None and (hin + 2 * pad - ks) // stride + 1 != hout) or wt.shape[1] != cout
+                or wt.shape[0] != ks * ks * wsets):
             raise L.B200Error("conv2d: segment geometry mismatch")
         s = d.seg[i]
         s.src, s.weight, s.cin, s.wcin, s.coff, s.ksize, s.pad = _p(src), _p(wt), src.shape[3], wt.shape[2], coff, ks, pad
@@ -176,12 +186,16 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
         out = torch.empty((n, hout, wout, cout), device=src0.device, dtype=src0.dtype)
     d.bias = _p(_f32(bias))
     d.rowbias, d.rowbias_stride = None, 0
+    d.wsets, d.rowbias_gstride, d.rowscale_gstride = wsets, rowbias_gstride, 0
+    npg = n // max(wsets, 1)
+    if wsets > 1 and (n % wsets or rowscale is not None or (bias is not None and bias.numel() != wsets * cout)):
+        raise L.B200Error("conv2d: grouped launch needs N % wsets == 0, a [wsets, Cout] bias and no rowscale")
     if rowbias is not None:       # may be a column slice of the batched emb projection
-        if (_f32(rowbias).stride(-1) != 1 or rowbias.shape[1] != cout or rowbias.shape[0] not in (1, n)
-                or rowbias.data_ptr() % 16):
+        if (_f32(rowbias).stride(-1) != 1 or rowbias.shape[1] != cout or rowbias.shape[0] not in (1, npg)
+                or rowbias.data_ptr() % 16 or (wsets > 1 and rowbias_gstride % 4)):
             raise L.B200Error("conv2d: rowbias must be [N or 1, Cout] fp32 with dense, 16B-aligned rows")
         d.rowbias = rowbias.data_ptr()
-        d.rowbias_stride = rowbias.stride(0) if rowbias.shape[0] == n and n > 1 else 0   # [1, Cout]: shared by the batch
+        d.rowbias_stride = rowbias.stride(0) if rowbias.shape[0] == npg and npg > 1 else 0   # [1, Cout]: shared by the batch
     d.rowscale, d.rowscale_stride, d.epi_act = None, 0, int(act)
     if rowscale is not None:      # adaLN-Zero gate, [N or 1, Cout] fp32 (may be a column slice)
         if (_f32(rowscale).stride(-1) != 1 or rowscale.shape[1] != cout or rowscale.shape[0] not in (1, n)
@@ -198,6 +212,7 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
         raise L.B200Error("conv2d: stats must be a zeroed float64 [N, Cout, 2] tensor")
     d.gn_sums = _p(stats)
     d.act_dtype = act_code(src0.dtype)
+    d.range_events = range_counter(src0.device).data_ptr() if src0.dtype == torch.float16 and _range_check else None
     ks = L.lib().b200_conv_ksplit(C.byref(d))
     if ks > 1:          # small maps run split-K: fp32 partial planes in a per-stream scratch buffer (never shared by
         need = ks * out.numel() * 4          # two launches that may overlap)
@@ -215,6 +230,42 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
 
 
 _workspaces = {}
+
+# ---------------------------------------------------------------------------------------------
+# fp16 range guard
+# ---------------------------------------------------------------------------------------------
+# fp16 activations saturate at +-65504 where the reference's fp32 path keeps going.  Every convolution launch counts the
+# output tiles in which it had to saturate a result into a per-device counter (b200_conv_desc.range_events); the sampling
+# loops (and direct network calls) read it once per run and RAISE instead of returning slices computed from clipped
+# activations.  B200DIFF_RANGE_CHECK=0 disables counting and checking.
+_range_check = os.environ.get("B200DIFF_RANGE_CHECK", "1") != "0"
+_range_counters = {}
+
+
+def range_counter(device) -> Tensor:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    t = _range_counters.get(idx)
+    if t is None:
+        t = _range_counters[idx] = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", idx))
+    return t
+
+
+def check_range(device, what: str = "the network") -> None:
+    """Raise if any fp16 activation was saturated since the last check (one 4-byte device->host read: synchronises)."""
+    if not _range_check:
+        return
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    t = _range_counters.get(idx)
+    if t is None:
+        return
+    n = int(t.item())
+    if n:
+        t.zero_()
+        raise L.B200Error(
+            f"fp16 range overflow in {what}: {n} convolution output tile(s) held values beyond +-65504 and were "
+            "saturated, so the result would differ from the reference's fp32 arithmetic.  Run this checkpoint with bf16 "
+            "activations (act_dtype=torch.bfloat16 or B200DIFF_ACT_DTYPE=bf16).")
+
 
 
 def _workspace(device, nbytes: int) -> Tensor:
@@ -259,28 +310,42 @@ def conv3x3_out(x: Tensor, w_oihw: Tensor, bias: Optional[Tensor]) -> Tensor:
 class StatsArena:
     """Bump allocator for the per-(image, channel) fp64 statistics buffers of one network forward: ONE memset at
     ``begin`` instead of one per GroupNorm.  Buffers that were ever handed out stay alive (captured CUDA graphs keep
-    raw pointers to them)."""
+    raw pointers to them).
+
+    The arena is only ever (re)allocated and zeroed in ``begin`` — on the caller's stream, BEFORE the network forks its
+    side streams (dsunet.py) — sized from the high-water mark of earlier forwards.  A forward that needs more than the
+    arena holds (the first one of a new, larger shape) gets private zero-filled buffers for the overflow, each zeroed on
+    the stream its producer kernel runs on, so no stream can ever see a slot being cleared under it; the next ``begin``
+    grows the arena."""
+
+    MIN = 1 << 18
 
     def __init__(self):
         self.buf: Optional[Tensor] = None
         self.off = 0
+        self.need = 0          # doubles requested in the current forward
+        self.high = 0          # high-water mark over all forwards
+        self.overflows = 0     # take() calls served outside the arena (diagnostics / tests)
         self.retired = []
 
     def begin(self, device) -> None:
-        if self.buf is None or self.buf.device != device:
+        want = max(self.MIN, -(-int(self.high * 1.25) // 4096) * 4096)
+        if self.buf is None or self.buf.device != device or self.buf.numel() < want:
             if self.buf is not None:
                 self.retired.append(self.buf)
-            self.buf = torch.zeros(1 << 18, dtype=torch.float64, device=device)
+            self.buf = torch.zeros(want, dtype=torch.float64, device=device)
         else:
             self.buf.zero_()
         self.off = 0
+        self.need = 0
 
     def take(self, n: int, c: int) -> Tensor:
         k = n * c * 2
+        self.need += k
+        self.high = max(self.high, self.need)
         if self.off + k > self.buf.numel():
-            self.retired.append(self.buf)
-            self.buf = torch.zeros(max(2 * self.buf.numel(), 4 * k), dtype=torch.float64, device=self.buf.device)
-            self.off = 0
+            self.overflows += 1
+            return torch.zeros((n, c, 2), dtype=torch.float64, device=self.buf.device)
         v = self.buf[self.off:self.off + k].view(n, c, 2)
         self.off += k
         return v
@@ -302,7 +367,8 @@ def channel_stats(x: Tensor, out: Optional[Tensor] = None) -> Tensor:
 def group_norm(x0: Tensor, gamma: Tensor, beta: Tensor, x1: Optional[Tensor] = None, groups: int = 32,
                eps: float = 1e-5, silu: bool = True, film: Optional[Tensor] = None,
                stats: Optional[Tensor] = None, cs0: Optional[Tensor] = None, cs1: Optional[Tensor] = None,
-               preshift: Optional[Tensor] = None) -> Tensor:
+               preshift: Optional[Tensor] = None, wsets: int = 1, film_gstride: int = 0,
+               preshift_gstride: int = 0) -> Tensor:
     """GroupNorm(+FiLM)(+SiLU) of the channel concatenation [x0 | x1]; NHWC in, NHWC out.
 
     With ``cs0`` (and ``cs1`` when ``x1`` is given) — the producers' per-channel sums — this is ONE read + ONE write
@@ -315,20 +381,24 @@ def group_norm(x0: Tensor, gamma: Tensor, beta: Tensor, x1: Optional[Tensor] = N
     code = act_code(x0.dtype)
     lib = L.lib()
     out = torch.empty(tuple(x0.shape[:-1]) + (c0 + c1,), device=x0.device, dtype=x0.dtype)
+    if wsets > 1 and (cs0 is None or (x1 is not None and cs1 is None) or n % wsets or gamma.numel() != wsets * (c0 + c1)):
+        raise L.B200Error("group_norm: grouped launch needs producer sums, N % wsets == 0 and [wsets, C] gamma / beta")
     film_p = None if film is None else film.data_ptr()
     film_s = 0 if film is None or film.shape[0] == 1 else film.stride(0)   # [1, 2C]: shared by the batch
     ps_p, ps_s = None, 0
     if preshift is not None:      # x0 + preshift[n, c] is what gets normalised (cached-conv1 ResBlocks); fp32 [N or 1, C0]
-        if cs0 is None or _f32(preshift).stride(-1) != 1 or preshift.shape[-1] != c0 or preshift.shape[0] not in (1, n):
+        npg = n // max(wsets, 1)
+        if cs0 is None or _f32(preshift).stride(-1) != 1 or preshift.shape[-1] != c0 or preshift.shape[0] not in (1, npg):
             raise L.B200Error("group_norm: preshift must be fp32 [N or 1, C0] and needs the producer's channel sums")
         ps_p = preshift.data_ptr()
-        ps_s = preshift.stride(0) if preshift.shape[0] == n and n > 1 else 0
+        ps_s = preshift.stride(0) if preshift.shape[0] == npg and npg > 1 else 0
     if cs0 is not None and (x1 is None or cs1 is not None):
         _timed("groupnorm_silu", 0.0, 2.0 * 2.0 * out.numel(),
                detail=f"{n}x{hw} c{c0}+{c1}", launch=
                lambda: L.check(lib.b200_groupnorm_apply_cs(_p(x0), c0, _p(cs0), _p(x1), c1, _p(cs1), n, hw, groups, eps,
                                                            _p(_f32(gamma)), _p(_f32(beta)), film_p, film_s, int(silu),
-                                                           _p(out), ps_p, ps_s, code, _stream()), "groupnorm_apply_cs"))
+                                                           _p(out), ps_p, ps_s, wsets, film_gstride, preshift_gstride,
+                                                           code, _stream()), "groupnorm_apply_cs"))
         return out
     if stats is None:
         stats = torch.zeros((n, groups, 2), device=x0.device, dtype=torch.float64)

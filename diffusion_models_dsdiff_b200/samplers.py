@@ -255,6 +255,7 @@ class StepEngine:
                                    "pred_x0": None if pred_x0 is None else pred_x0.clone()})
                 if on_step:
                     on_step(i, x, pred_x0)
+            ops.check_range(dev, "the sampling loop")
             return x
         # ---- graph path ----
         key = None
@@ -289,6 +290,7 @@ class StepEngine:
             if on_step:
                 on_step(i, xs, x0s)
         self.stats["replays"] = steps
+        ops.check_range(dev, "the sampling loop")
         return xs.clone() if key is not None else xs
 
     def _capture(self, x, cond, pred_x0, step_ptr, key):
@@ -334,6 +336,11 @@ class StepEngine:
 def _engine_model_fn(net):
     """model_fn(xc, t_table, step_ptr) for a B200 engine network; the DS-Diff feature dict (discarded by
     every sampler, trainer_ds_diff.py:752-755 / gaussian_diffusion.py:278-279) is not materialised."""
+    if not getattr(net, "_b200_engine", False):
+        raise L.B200Error(
+            f"{type(net).__module__}.{type(net).__name__} is not a B200 engine network: point the yaml "
+            "`unet_config.target` at diffusion_models_dsdiff_b200.unet.UNetModel / .dsunet.DSUnetModel / .dit.DiT "
+            "(INTEGRATION.md §1).  The samplers have no eager / PyTorch fallback.")
     extra = {"return_features": False} if getattr(net, "_returns_features", False) else {}
     return lambda xc, t_table, step_ptr, **kw: net(xc, t_table, step_ptr=step_ptr, **extra, **kw)
 
@@ -342,6 +349,71 @@ def _graph_cache_args(cache: dict, net) -> dict:
     pw = net.packed() if hasattr(net, "packed") else None
     return {"cache": cache, "cache_key": (id(net), id(pw)), "keepalive": pw,
             "prepare": getattr(net, "prepare_steps", None), "prepare_cond": getattr(net, "prepare_conditioning", None)}
+
+
+# ---------------------------------------------------------------------------------------------
+# the sampler seam: everything the samplers need from the HOST object is read through these helpers,
+# from PUBLIC attributes only, so the host may be this package's DDPM / DiffusionWrapper or the REFERENCE's own
+# (``trainers.trainer_ds_diff.DSDiffModel(DDPM)``: ``DDIMSampler(self)`` at trainer_ds_diff.py:672;
+# ``TryTrainerDiffusion.model = DiffusionWrapper(...)``: ``sample_fn(self.model, ...)`` at
+# trainer_use_gaussian_diff.py:86,615) holding a B200 network instantiated from the swapped yaml ``target``.
+# ---------------------------------------------------------------------------------------------
+def host_denoiser(model_or_wrapper):
+    """DDPM-like host (``.model`` is a DiffusionWrapper), a DiffusionWrapper (``.diffusion_model``) or a bare network
+    -> the network (ddpm.py:1320-1326)."""
+    m = model_or_wrapper
+    inner = getattr(m, "model", None)
+    if inner is not None and hasattr(inner, "diffusion_model"):
+        m = inner
+    return getattr(m, "diffusion_model", m)
+
+
+def host_conditioning_key(model_or_wrapper):
+    m = model_or_wrapper
+    inner = getattr(m, "model", None)
+    if inner is not None and hasattr(inner, "diffusion_model"):
+        m = inner
+    return getattr(m, "conditioning_key", None)
+
+
+def host_cond_list(model, cond):
+    """The tensors DiffusionWrapper concatenates to x on the channel axis (ddpm.py:1331-1333), from whatever the caller
+    passes as conditioning: a tensor, a list (apply_model wraps it under the wrapper's key, trainer_ds_diff.py:740-748)
+    or the hybrid dict."""
+    key = host_conditioning_key(model)
+    if cond is None or key is None or key in ("crossattn", "adm", "crossattn-adm"):
+        return None
+    if isinstance(cond, dict):
+        cond = cond.get("c_concat")
+        if cond is None:
+            return None
+    return list(cond) if isinstance(cond, (list, tuple)) else [cond]
+
+
+def host_context(model, cond) -> Optional[Tensor]:
+    """The cross-attention context of the 'crossattn' / 'hybrid' keys: cat(c_crossattn, 1) (ddpm.py:1334-1347)."""
+    key = host_conditioning_key(model)
+    if cond is None or key not in ("crossattn", "hybrid"):
+        return None
+    if isinstance(cond, dict):
+        cond = cond.get("c_crossattn")
+        if cond is None:
+            return None
+    elif key == "hybrid":
+        return None
+    cond = list(cond) if isinstance(cond, (list, tuple)) else [cond]
+    return torch.cat(cond, 1).float().contiguous()
+
+
+def host_graph_cache(host) -> dict:
+    """Captured step graphs live on the host object (the reference builds a fresh DDIMSampler per batch,
+    trainer_ds_diff.py:672); ``__dict__`` so a reference nn.Module host does not try to register it."""
+    return host.__dict__.setdefault("_b200_graphs", {})
+
+
+def host_engine_args(host, net=None) -> dict:
+    net = host_denoiser(host) if net is None else net
+    return _graph_cache_args(host_graph_cache(host), net)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -513,40 +585,25 @@ class DDPM(nn.Module):
         return _coef_table({0: ca, 1: cb, 2: g("posterior_mean_coef1"), 3: g("posterior_mean_coef2"), 4: std}, len(t))
 
     def _cond_list(self, cond):
-        """The tensors DiffusionWrapper concatenates to x on the channel axis (ddpm.py:1331-1333)."""
-        key = self.model.conditioning_key
-        if cond is None or key is None or key == "crossattn":
-            return None
-        if isinstance(cond, dict):
-            cond = cond.get("c_concat")
-            if cond is None:
-                return None
-        return list(cond) if isinstance(cond, (list, tuple)) else [cond]
+        return host_cond_list(self, cond)
 
     def _context(self, cond) -> Optional[Tensor]:
-        """The cross-attention context of the 'crossattn' / 'hybrid' keys: cat(c_crossattn, 1) (ddpm.py:1334-1347)."""
-        key = self.model.conditioning_key
-        if cond is None or key not in ("crossattn", "hybrid"):
-            return None
-        if isinstance(cond, dict):
-            cond = cond.get("c_crossattn")
-            if cond is None:
-                return None
-        elif key == "hybrid":
-            return None
-        cond = list(cond) if isinstance(cond, (list, tuple)) else [cond]
-        return torch.cat(cond, 1).float().contiguous()
+        return host_context(self, cond)
 
     def _model_fn(self):
-        return _engine_model_fn(self.model.diffusion_model)
+        return _engine_model_fn(host_denoiser(self))
 
     def _graph_cache_args(self):
-        return _graph_cache_args(self.__dict__.setdefault("_graphs", {}), self.model.diffusion_model)
+        return host_engine_args(self)
 
     @torch.no_grad()
     def p_sample(self, x, t, cond=None, clip_denoised=True, repeat_noise=False, noise=None, **kw):
         """One ancestral step at per-batch timesteps ``t`` (all equal, as every reference loop passes)."""
-        tt = int(t.reshape(-1)[0].item())
+        tv = t.reshape(-1)
+        tt = int(tv[0].item())
+        if not bool((tv == tt).all()):
+            raise NotImplementedError("B200 path: one timestep per p_sample call (every reference loop passes "
+                                      "torch.full((b,), i))")
         coef = self._ddpm_coef([tt]).to(x.device)
         out = self.apply_model(x, t, cond)
         z = noise if noise is not None else noise_like(x.shape, x.device, repeat_noise)
@@ -773,13 +830,15 @@ class DDIMSampler(object):
         print(f"Running DDIM Sampling with {total_steps} timesteps")
         t_table = torch.tensor(tsteps, dtype=torch.float32, device=device)
         cfg = {}
+        m = self.model
         if unconditional_conditioning is not None and unconditional_guidance_scale != 1.:
-            cfg = dict(cfg_scale=unconditional_guidance_scale, uncond=self.model._cond_list(unconditional_conditioning),
-                       uncond_context=self.model._context(unconditional_conditioning))
-        eng = StepEngine(self.model._model_fn(), L.SAMPLER_LDM_DDIM, _PARAM[self.model.parameterization],
-                         coef.to(device), t_table, clip_denoised, context=self.model._context(cond), **cfg,
-                         **self.model._graph_cache_args())
-        self.last_engine = self.model.last_engine = eng
+            cfg = dict(cfg_scale=unconditional_guidance_scale, uncond=host_cond_list(m, unconditional_conditioning),
+                       uncond_context=host_context(m, unconditional_conditioning))
+        eng = StepEngine(_engine_model_fn(host_denoiser(m)), L.SAMPLER_LDM_DDIM, _PARAM[m.parameterization],
+                         coef.to(device), t_table, clip_denoised, context=host_context(m, cond), **cfg,
+                         **host_engine_args(m))
+        self.last_engine = eng
+        m.__dict__["last_engine"] = eng
         intermediates = {"x_inter": [img], "pred_x0": [img]}
         if total_steps == 0:
             return img, intermediates
@@ -794,7 +853,7 @@ class DDIMSampler(object):
                 intermediates["x_inter"].append(x.clone())
                 intermediates["pred_x0"].append(x0.clone())
 
-        out = eng.run(img, self.model._cond_list(cond), total_steps, noises=noises, use_graph=self.use_graph,
+        out = eng.run(img, host_cond_list(m, cond), total_steps, noises=noises, use_graph=self.use_graph,
                       on_step=on_step, want_x0=True, record=record)
         return out, intermediates
 
@@ -803,10 +862,34 @@ class DDIMSampler(object):
                       temperature=1., noise_dropout=0., score_corrector=None, corrector_kwargs=None,
                       unconditional_guidance_scale=1., unconditional_conditioning=None, clip_denoised=True,
                       dynamic_threshold=None, noise=None):
-        """Single step (ddim.py:188-261): network call + fused update at table row ``index``."""
+        """Single step (ddim.py:188-261): network call(s) + fused update at table row ``index``."""
+        for name, val in (("score_corrector", score_corrector), ("dynamic_threshold", dynamic_threshold)):
+            if val is not None:
+                raise NotImplementedError(f"DDIMSampler.p_sample_ddim({name}=...) is not built in the B200 path")
+        if quantize_denoised or noise_dropout > 0.:
+            raise NotImplementedError("quantize_denoised / noise_dropout are not built in the B200 path")
         coef, _ = self._coef(use_original_steps, temperature)
         total = coef.shape[0]
-        out = self.model.apply_model(x, t, c)
+        if unconditional_conditioning is None or unconditional_guidance_scale == 1.:
+            out = self.model.apply_model(x, t, c)
+        else:                           # classifier-free guidance, ddim.py:197-219: [uncond; cond] in one batch
+            x_in, t_in = torch.cat([x] * 2), torch.cat([t] * 2)
+            if isinstance(c, dict):
+                assert isinstance(unconditional_conditioning, dict)
+                c_in = {}
+                for k in c:
+                    if isinstance(c[k], list):
+                        c_in[k] = [torch.cat([unconditional_conditioning[k][i], c[k][i]]) for i in range(len(c[k]))]
+                    else:
+                        c_in[k] = torch.cat([unconditional_conditioning[k], c[k]])
+            elif isinstance(c, list):
+                assert isinstance(unconditional_conditioning, list)
+                c_in = [torch.cat([unconditional_conditioning[i], c[i]]) for i in range(len(c))]
+            else:
+                c_in = torch.cat([unconditional_conditioning, c])
+            both = self.model.apply_model(x_in, t_in, c_in)
+            n = x.shape[0]
+            out = ops.cfg_combine(both[:n].contiguous(), both[n:].contiguous(), float(unconditional_guidance_scale))
         z = noise if noise is not None else noise_like(x.shape, x.device, repeat_noise)
         return ops.sampler_update(L.SAMPLER_LDM_DDIM, _PARAM[self.model.parameterization], x.float().contiguous(),
                                   out.contiguous(), z.contiguous(), coef.to(x.device), step=total - 1 - index,
@@ -852,6 +935,24 @@ def space_timesteps(num_timesteps, section_counts):
             cur_idx += frac_stride
         start_idx += size
     return set(all_steps)
+
+
+def gd_conditioning(model, model_kwargs):
+    """What ``model(x, t, **model_kwargs)`` (gaussian_diffusion.py:276) makes of the caller's ``model_kwargs`` when
+    ``model`` is a DiffusionWrapper (ours or the reference's; trainer_use_gaussian_diff.py:603-620 passes
+    ``dict(c_concat=[images(, edge)])``): (tensors concatenated to x, cross-attention context)."""
+    if not model_kwargs:
+        return None, None
+    unknown = set(model_kwargs) - {"c_concat", "c_crossattn"}
+    if unknown:
+        raise NotImplementedError(f"B200 path: model_kwargs {sorted(unknown)} are not built")
+    key = host_conditioning_key(model) if hasattr(model, "diffusion_model") else "hybrid"
+    cond = context = None
+    if model_kwargs.get("c_concat") is not None and key in ("concat", "hybrid"):
+        cond = list(model_kwargs["c_concat"])
+    if model_kwargs.get("c_crossattn") is not None and key in ("crossattn", "hybrid"):
+        context = torch.cat(list(model_kwargs["c_crossattn"]), 1).float().contiguous()
+    return cond, context
 
 
 class GaussianDiffusion:
@@ -929,12 +1030,10 @@ class GaussianDiffusion:
         T = self.num_timesteps
         t_table = torch.tensor([self._model_timestep(t) for t in range(T - 1, -1, -1)], dtype=torch.float32,
                                device=device)
-        cond = None
-        if model_kwargs and model_kwargs.get("c_concat") is not None:
-            cond = list(model_kwargs["c_concat"])
-        net = model.diffusion_model if isinstance(model, DiffusionWrapper) else model
+        cond, context = gd_conditioning(model, model_kwargs)
+        net = host_denoiser(model)
         eng = StepEngine(_engine_model_fn(net), mode, self._param(), self._coef(eta).to(device), t_table, clip_denoised,
-                         learned_range=self.model_var_type == "learned_range",
+                         learned_range=self.model_var_type == "learned_range", context=context,
                          **_graph_cache_args(self.__dict__.setdefault("_graphs", {}), net))
         self.last_engine = eng
         return eng.run(img, cond, T, noises=noises, use_graph=self.use_graph, want_x0=record is not None,
@@ -972,12 +1071,16 @@ class GaussianDiffusion:
         ti = int(tt[0])
         if not bool((tt == ti).all()):
             raise NotImplementedError("B200 path: one timestep per p_sample / ddim_sample call")
-        net = model.diffusion_model if isinstance(model, DiffusionWrapper) else model
+        net = host_denoiser(model)
+        _engine_model_fn(net)           # loud rejection of a non-engine denoiser
+        cond, context = gd_conditioning(model, model_kwargs)
         xc = x.float()
-        if model_kwargs and model_kwargs.get("c_concat") is not None:
-            xc = torch.cat([xc] + [c.to(x.device).float() for c in model_kwargs["c_concat"]], dim=1)
+        if cond:
+            xc = torch.cat([xc] + [c.to(x.device).float() for c in cond], dim=1)
         tm = torch.full((x.shape[0],), self._model_timestep(ti), dtype=torch.float32, device=x.device)
         extra = {"return_features": False} if getattr(net, "_returns_features", False) else {}
+        if context is not None:
+            extra["context"] = context.to(x.device)
         out = net(xc.contiguous(), tm, **extra)
         out = out[0] if isinstance(out, tuple) else out
         cache = self.__dict__.setdefault("_coef_cache", {})
@@ -1084,3 +1187,14 @@ def create_gaussian_diffusion(*, steps=1000, learn_sigma=False, sigma_small=Fals
                            model_mean_type="x0" if predict_xstart else "eps", model_var_type=var,
                            loss_type="rescaled_kl" if use_kl else ("rescaled_mse" if rescale_learned_sigmas else "mse"),
                            rescale_timesteps=rescale_timesteps, parameterization=parameterization)
+
+
+def sr_create_model_and_diffusion(args):
+    """script_util.py:57-86: the trainers call this with their config object and keep only the diffusion
+    (trainer_use_gaussian_diff.py:70-76, 591-596); the network comes from ``unet_config`` through DiffusionWrapper."""
+    diffusion = create_gaussian_diffusion(
+        steps=args.diffusion_steps, learn_sigma=args.learn_sigma, noise_schedule=args.noise_schedule,
+        use_kl=args.use_kl, predict_xstart=args.predict_xstart, rescale_timesteps=args.rescale_timesteps,
+        rescale_learned_sigmas=args.rescale_learned_sigmas, timestep_respacing=args.timestep_respacing,
+        parameterization=args.parameterization)
+    return None, diffusion

@@ -144,6 +144,13 @@ class PackedWeights:
         self.emb_b = torch.cat(emb_b, 0).contiguous() if emb_b else None
 
 
+def param_fingerprint(module: nn.Module) -> int:
+    """Changes whenever any parameter of ``module`` is replaced OR updated in place (optimizer steps, the reference's
+    LitEma.copy_to / restore inside ema_scope, ``p.data.copy_``): the kernel-layout weight copies are rebuilt — and the
+    captured step graphs, keyed on them, re-captured — instead of silently running on stale weights."""
+    return hash(tuple((p.data_ptr(), p._version) for p in module.parameters()))
+
+
 def _f(p: Tensor) -> Tensor:
     t = p.detach()
     return t if t.dtype == torch.float32 and t.is_contiguous() else t.float().contiguous()
@@ -391,9 +398,11 @@ class _EngineModule(nn.Module):
     """Shared plumbing: packed-weight cache invalidation + timestep handling."""
 
     act_dtype: torch.dtype
+    _b200_engine = True       # the samplers' step engine drives this network (samplers._engine_model_fn)
 
     def _init_engine(self):
         self._pw: Optional[PackedWeights] = None
+        self._pw_fp: Optional[int] = None
         self._temb: Optional[TimeEmbedding] = None
         self._arena = ops.StatsArena()
         self.register_load_state_dict_post_hook(lambda mod, keys: mod.invalidate())
@@ -410,11 +419,21 @@ class _EngineModule(nn.Module):
         dev = next(self.parameters()).device
         if dev.type != "cuda":
             raise B200Error("the B200 engine has no CPU path: move the module to a CUDA device")
+        fp = param_fingerprint(self)
+        if self._pw is not None and fp != self._pw_fp:       # in-place weight update since the last pack
+            self.invalidate()
         if self._pw is None or self._pw.dtype != self.act_dtype:
             with torch.no_grad():
                 self._pw = PackedWeights(self, self.act_dtype)
                 self._temb = TimeEmbedding(self.model_channels, dev)
+            self._pw_fp = fp
         return self._pw
+
+    def _range_check(self, device, step_ptr) -> None:
+        """Direct calls (no step engine around them, which checks once per sampling run) verify the fp16 range guard
+        themselves; never inside a CUDA-graph capture (the check reads a device counter)."""
+        if step_ptr is None and not torch.cuda.is_current_stream_capturing():
+            ops.check_range(device, type(self).__name__ + ".forward")
 
     def prepare_steps(self, t_table: Tensor) -> None:
         """Called by the sampling loops before (re)playing their step graph; see TimeEmbedding.prepare_steps."""
@@ -594,6 +613,6 @@ class UNetModel(_EngineModule):
         h = run_sequential(cx, self.middle_block, h, None)
         for blk in self.output_blocks:
             h = run_sequential(cx, blk, h, hs.pop())
-        if self.predict_codebook_ids:     # openaimodel.py:955-956
-            return run_out_head(cx, self.id_predictor, h)
-        return run_out_head(cx, self.out, h).to(x.dtype)
+        out = run_out_head(cx, self.id_predictor if self.predict_codebook_ids else self.out, h)   # openaimodel.py:955-958
+        self._range_check(x.device, step_ptr)
+        return out if self.predict_codebook_ids else out.to(x.dtype)

@@ -25,6 +25,7 @@
 extern "C" {
 #endif
 
+#define B200_ABI_VERSION 10
 #define B200_F16 0
 #define B200_BF16 1
 
@@ -105,6 +106,17 @@ typedef struct {
   void *workspace;          /* split-K scratch (fp32 partial tiles), >= b200_conv_ksplit(d) * N*Hout*Wout*Cout*4 bytes,
                               16-byte aligned; only read / written by this call; may be NULL when the factor is 1      */
   size_t workspace_bytes;
+  unsigned int *range_events; /* optional device counter (caller-owned, zeroed by the caller): incremented once per output
+                              tile in which an fp16 result had to be SATURATED to +-65504 (|value| >= 65520, or inf).  The
+                              reference computes in fp32 and cannot overflow here; a caller that sees a non-zero count must
+                              treat the results as invalid (the Python layer raises and suggests bf16 activations).  NULL =
+                              no counting.  Never written for B200_BF16 (fp32 exponent range).                          */
+  int wsets;                /* 0 or 1: one weight set.  G > 1: "grouped along N" — the N images are G equal groups and group
+                              g = n / (N / G) uses its own weights, bias and timestep rows: seg[i].weight is the stack
+                              [G][k*k][Cout][wcin], bias [G][Cout], rowbias / rowscale advance by *_gstride floats per group
+                              (their per-image stride then counts images WITHIN the group).  One launch for the G same-shape
+                              encoders of DSUnetModel (UNet_DS_Diff/model.py:674-686) instead of G latency-bound ones.      */
+  int rowbias_gstride, rowscale_gstride;
 } b200_conv_desc;
 int b200_conv2d_igemm(const b200_conv_desc *d, void *stream);
 /* split-K factor b200_conv2d_igemm will use for this descriptor (1 = none).  It depends on the layer geometry only
@@ -139,12 +151,16 @@ int b200_groupnorm_apply(const void *x0, int C0, const void *x1, int C1, int N, 
  * sums of the two concatenated sources to group statistics itself, so a GroupNorm is ONE read + ONE write pass.
  * preshift (may be NULL): fp32 [N or 1][C0] row pitch preshift_stride (0 = one row for the batch): the tensor normalised
  * is x0 + preshift[n, c]; the sums of x0 are corrected analytically.  Used for `h + emb_out` of ResBlock._forward
- * (openaimodel.py:282) when conv1's output is loop-invariant across sampling steps and cached.                       */
-int b200_channel_stats(const void *x, int N, int HW, int C, double *sums, int act_dtype, void *stream);
+ * (openaimodel.py:282) when conv1's output is loop-invariant across sampling steps and cached.
+ * wsets > 1: "grouped along N" like b200_conv_desc.wsets — the N images are wsets equal groups, group g uses
+ * gamma / beta rows g of [wsets][C0+C1] and film / preshift advance by *_gstride floats per group (their per-image stride
+ * then counts images within the group): one launch normalises the same layer of DSUnetModel's four encoders.          */
 int b200_groupnorm_apply_cs(const void *x0, int C0, const double *cs0, const void *x1, int C1,
                             const double *cs1, int N, int HW, int groups, float eps, const float *gamma,
                             const float *beta, const float *film, int film_stride, int silu, void *out,
-                            const float *preshift, int preshift_stride, int act_dtype, void *stream);
+                            const float *preshift, int preshift_stride, int wsets, int film_gstride,
+                            int preshift_gstride, int act_dtype, void *stream);
+int b200_channel_stats(const void *x, int N, int HW, int C, double *sums, int act_dtype, void *stream);
 
 /* ---- attention -------------------------------------------------------------------------------
  * replaces QKVAttention / QKVAttentionLegacy (openaimodel.py:537-555 / 505-521): fused

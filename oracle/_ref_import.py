@@ -1,9 +1,12 @@
 """Import shim for the UNMODIFIED reference tree (test infrastructure only).
 
-Used ONLY by ``oracle/make_golden.py`` (run in the authoring container, where
+Used by ``oracle/make_golden*.py`` (run in the authoring container, where
 ``/root/reference`` exists) to pin the oracle restatement against the real
-reference code.  Nothing in the product package, ``bench.py`` or the ``-m gpu``
-tests imports this file: ``/root/reference`` does not exist on the GPU box.
+reference code, and — through the byte-compiled copy ``oracle/_ref/`` that
+``oracle/build_ref.py`` produces and ``gpurun`` ships — by ``bench.py``'s
+reference arm / ``gpu_eager_reference`` leg and the reference-deviation tests on
+the GPU box, where ``/root/reference`` does not exist.  Nothing in the product
+package imports this file.
 
 The reference imports a number of third-party packages that are absent from
 this image (pytorch_lightning, lightning, omegaconf, monai, SimpleITK,
@@ -12,6 +15,7 @@ so they are replaced with inert ``sys.modules`` stubs.
 """
 from __future__ import annotations
 
+import importlib.abc
 import importlib.machinery
 import os
 import sys
@@ -19,7 +23,22 @@ import types
 
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("DSDIFF_REFERENCE_ROOT", "/root/reference")
+COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _default_root() -> str:
+    env = os.environ.get("DSDIFF_REFERENCE_ROOT")
+    if env:
+        return env
+    return "/root/reference" if os.path.isdir("/root/reference") else COMPILED_ROOT
+
+
+REFERENCE_ROOT = _default_root()
+
+
+def available() -> bool:
+    """True when the reference (sources here, or the byte-compiled oracle/_ref on the GPU box) can be imported."""
+    return os.path.isdir(os.path.join(_default_root(), "ldm"))
 
 
 class _Anything:
@@ -66,6 +85,32 @@ def _stub(name: str) -> types.ModuleType:
     return m
 
 
+# third-party packages the reference imports that are absent from the image; none does arithmetic on the hot path
+ABSENT_TOP = {"pytorch_lightning", "lightning", "omegaconf", "monai", "SimpleITK", "diffusers", "h5py", "deepspeed",
+              "matplotlib", "skimage", "lpips", "torchmetrics", "kornia", "open_clip", "timm", "openpyxl", "nibabel",
+              "seaborn", "thop", "fvcore", "clip", "taming", "pytorch_msssim", "medpy", "natsort", "wandb", "tensorboard",
+              "torchsummary", "albumentations", "imageio", "ants", "torchio", "einops_exts", "mpi4py", "blobfile"}
+
+
+class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    """Last-resort finder: any (sub)module of an ABSENT_TOP package that no real finder provides becomes an inert stub."""
+
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname.split(".")[0] in ABSENT_TOP:
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        m = _StubModule(spec.name)
+        m.__path__ = []
+        return m
+
+    def exec_module(self, module):
+        parent, _, child = module.__name__.rpartition(".")
+        if parent and parent in sys.modules:
+            setattr(sys.modules[parent], child, module)
+
+
 class _LightningModule(nn.Module):
     """pl.LightningModule := nn.Module + the few attributes the reference touches."""
 
@@ -88,12 +133,16 @@ class _LightningModule(nn.Module):
         pass
 
 
-def install(reference_root: str = REFERENCE_ROOT) -> str:
-    """Put the reference on sys.path behind inert stubs; returns the root."""
-    if not os.path.isdir(reference_root):
+def install(reference_root: str = None) -> str:
+    """Put the reference on sys.path behind inert stubs; returns the root (/root/reference in the authoring container,
+    else the byte-compiled oracle/_ref)."""
+    reference_root = reference_root or _default_root()
+    if not os.path.isdir(os.path.join(reference_root, "ldm")):
         raise FileNotFoundError(
-            f"reference tree not found at {reference_root}; golden generation only runs "
-            "in the authoring container")
+            f"reference tree not found at {reference_root}: run oracle/build_ref.py in the authoring container "
+            "(it byte-compiles /root/reference into oracle/_ref, which gpurun ships to the GPU box)")
+    if not any(isinstance(f, _StubFinder) for f in sys.meta_path):
+        sys.meta_path.append(_StubFinder())
     for name in [
         "pytorch_lightning", "pytorch_lightning.utilities", "pytorch_lightning.callbacks",
         "pytorch_lightning.loggers", "pytorch_lightning.utilities.distributed",
