@@ -54,7 +54,8 @@ def gather_slices(local: Tensor, n_total: int, group: Optional[dist.ProcessGroup
     pad = torch.zeros((nmax, *local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: e - b] = local
     bufs: Optional[List[Tensor]] = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
-    dist.gather(pad, bufs, dst=0, group=group)
+    dst = dist.get_global_rank(group, 0) if group is not None else 0      # dst is a GLOBAL rank
+    dist.gather(pad, bufs, dst=dst, group=group)
     if rank != 0:
         return None
     parts = []
@@ -92,8 +93,10 @@ def sample_volume(sample_fn, cond: Tensor, out_channels: int = 1, batch_size: in
     ``sample_fn`` (cond_batch [b, C, H', W'], x_T [b, out_channels, H', W']) -> samples [b, out_channels, H', W'], e.g.
                   ``lambda c, x: DDIMSampler(model).sample(50, len(c), x.shape[1:], c, x_T=x, verbose=False)[0]``.
     Slices are padded to a multiple of ``multiple`` and cropped back; x_T of slice i comes from its own generator
-    (``slice_noise``), so the result does not depend on the world size or on ``batch_size``.  No collective runs inside
-    the sampling loop; the only communication is the final gather."""
+    (``slice_noise``), so for DETERMINISTIC samplers (DDIM eta = 0, DPM-Solver++) the result does not depend on the world
+    size or on ``batch_size``.  Samplers that draw per-step noise (ancestral, DDIM eta > 0) take it from the rank's global
+    CUDA generator inside the step engine, batch-shaped: reproducible for a fixed (world size, batch_size, seed) only.
+    No collective runs inside the sampling loop; the only communication is the final gather."""
     n_total = cond.shape[0]
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
