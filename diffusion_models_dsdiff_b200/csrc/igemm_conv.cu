@@ -31,6 +31,7 @@ struct ConvKParams {
   int BN, n_ntiles;
   int TW, TH, TN;
   int tiles_w, tiles_h, tiles_n;
+  int tiles_n_set;           // image tiles per weight set: cdiv(n_per_set, TN) (a tile never straddles two sets)
   int num_tiles;
   int stride;
   int stages;               // pipeline stages; one stage = [activation box | up to 3 weight tiles]
@@ -272,8 +273,12 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       const int w0 = (pt % p.tiles_w) * p.TW;
       pt /= p.tiles_w;
       const int h0 = (pt % p.tiles_h) * p.TH;
-      const int n0 = (pt / p.tiles_h) * p.TN;                // >= N for the odd tile out: all-zero boxes
-      const int wset = min(n0 / p.n_per_set, p.wsets - 1);   // the tile's weight set (a tile never straddles two sets)
+      const int tni = pt / p.tiles_h;
+      const int wset_raw = tni / p.tiles_n_set;              // == wsets for the odd tile out
+      // image tiles restart at every weight set's first image: a box may run past the set's last image (those rows are
+      // computed with the wrong weights and never stored); n0 >= N for the odd tile out: all-zero boxes
+      const int n0 = wset_raw * p.n_per_set + (tni - wset_raw * p.tiles_n_set) * p.TN;
+      const int wset = min(wset_raw, p.wsets - 1);           // the tile's weight set
       for (int s = 0; s < p.nseg; ++s) {
         const int ks = p.seg_ks[s], pad = p.seg_pad[s], cin = p.seg_cin[s];
         const int tbase = wset * ks * ks;                    // weight sets are stacked along the tap axis of the TMA map
@@ -406,10 +411,13 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       const int w = (pt % p.tiles_w) * p.TW + tw;
       pt /= p.tiles_w;
       const int h = (pt % p.tiles_h) * p.TH + th;
-      const int n0 = (pt / p.tiles_h) * p.TN;
+      const int tni = pt / p.tiles_h;
+      const int wset_raw = tni / p.tiles_n_set;
+      const int n0 = wset_raw * p.n_per_set + (tni - wset_raw * p.tiles_n_set) * p.TN;
+      const int n_end = min(wset_raw + 1, p.wsets) * p.n_per_set;      // rows of the tile past its weight set are dropped
       const int n = n0 + tn;
       const int n_warp = n0 + lane_base / (p.TW * p.TH);
-      const bool valid = kFast || ((w < p.Wout) && (h < p.Hout) && (n < p.N));
+      const bool valid = kFast || ((w < p.Wout) && (h < p.Hout) && (n < n_end));
       const size_t pix = ((size_t)n * p.Hout + h) * p.Wout + w;
       if (p.gn_sums && (n_warp != acc_n || n_tile != acc_ntile)) {
         if (acc_n >= 0) flush_stats();
@@ -597,10 +605,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
               for (int i = 0; i < 8; ++i)
                 if (cb + i < p.cout_real)
                   p.out_f32[(((size_t)n * p.cout_real + cb + i) * p.Hout + h) * p.Wout + w] = vh[i];
-            } else if (p.vec32) {
-              packed[half] = pack8<T>(vh);
             } else {
-              *reinterpret_cast<uint4 *>(out + pix * p.Cout + cb) = pack8<T>(vh);
+              const uint4 pk = pack8<T>(vh);
+              if (p.gn_sums) unpack8<T>(pk, vh);      // statistics of the STORED values, exactly like the fast epilogue
+              if (p.vec32) packed[half] = pk;
+              else *reinterpret_cast<uint4 *>(out + pix * p.Cout + cb) = pk;
             }
           } else if (p.gn_sums) {
 #pragma unroll
@@ -737,7 +746,8 @@ static bool debug_skip_epilogue() {
 static void choose_tiling(const b200_conv_desc *d, int *ctas, int *bn) {
   int TW = 1, TH = 1, TN = 1;
   pick_box(d->Hout, d->Wout, &TW, &TH, &TN);
-  const long ptiles = (long)cdiv(d->Wout, TW) * cdiv(d->Hout, TH) * cdiv(d->N, TN);
+  const int nsets = std::max(1, d->wsets);
+  const long ptiles = (long)cdiv(d->Wout, TW) * cdiv(d->Hout, TH) * cdiv(d->N / nsets, TN) * nsets;
   const int sms = num_sms();
   *ctas = 2;
   *bn = pick_bn(d->Cout);
@@ -866,7 +876,8 @@ static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t
   pick_box(d->Hout, d->Wout, &p.TW, &p.TH, &p.TN);
   p.tiles_w = cdiv(d->Wout, p.TW);
   p.tiles_h = cdiv(d->Hout, p.TH);
-  p.tiles_n = cdiv(d->N, p.TN);
+  p.tiles_n_set = cdiv(d->N / std::max(1, d->wsets), p.TN);
+  p.tiles_n = p.tiles_n_set * std::max(1, d->wsets);
   p.num_tiles = cdiv(p.tiles_w * p.tiles_h * p.tiles_n, kCtas) * p.n_ntiles;   // (pairs of) pixel tiles x N tiles
   p.bias = d->bias; p.rowbias = d->rowbias; p.rowbias_stride = d->rowbias_stride;
   p.residual = d->residual; p.res_scale = d->res_scale; p.out = d->out;
@@ -1000,21 +1011,16 @@ extern "C" int b200_conv2d_igemm(const b200_conv_desc *d, void *stream) {
   bool one_cta = force_one_cta || ctas == 1;
   if (wsets > 1) {
     // a pixel tile (and a CTA pair's two tiles, which share one weight tile) must lie inside ONE weight set
-    const int n_per_set = d->N / wsets;
-    B200_CHECK(n_per_set % TN == 0, "conv: %d images per weight set do not tile with %d-image boxes", n_per_set, TN);
-    const long tiles_per_set = (long)cdiv(d->Wout, TW) * cdiv(d->Hout, TH) * (n_per_set / TN);
-    if (tiles_per_set % 2) {
-      B200_CHECK(ksplit == 1, "conv: grouped split-K launch needs an even number of pixel tiles per weight set");
-      one_cta = true;
-    }
+    const long tiles_per_set = (long)cdiv(d->Wout, TW) * cdiv(d->Hout, TH) * cdiv(d->N / wsets, TN);
+    if (tiles_per_set % 2) one_cta = true;
   }
   const int kc = one_cta ? 1 : 2;
   // fast epilogue: 16-bit NHWC output, 32-byte aligned rows, every tile full, warp rows inside one image
-  const long ptiles = (long)cdiv(d->Wout, TW) * cdiv(d->Hout, TH) * cdiv(d->N, TN);
+  const long ptiles = (long)cdiv(d->Wout, TW) * cdiv(d->Hout, TH) * cdiv(d->N / wsets, TN) * wsets;
   static const bool no_fast = getenv("B200DIFF_CONV_NO_FAST_EPI") != nullptr;
   const bool fast = !no_fast && d->out && !d->out_nchw_f32 && !d->out_nhwc_f32 && d->epi_act <= 1 &&
                     d->Cout % 16 == 0 && d->Cout % bn == 0 && (((uintptr_t)d->out | (uintptr_t)d->residual) & 31) == 0 &&
-                    d->Wout % TW == 0 && d->Hout % TH == 0 && d->N % TN == 0 && ptiles % kc == 0 && TW * TH >= 32 &&
+                    d->Wout % TW == 0 && d->Hout % TH == 0 && (d->N / wsets) % TN == 0 && ptiles % kc == 0 && TW * TH >= 32 &&
                     !debug_skip_epilogue() && !getenv("B200DIFF_NO_VEC32") && ksplit == 1;
 #define B200_CONV_DISPATCH(TT)                                                                           \
   do {                                                                                                   \

@@ -22,8 +22,8 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .unet import (Act, Ctx, ResBlock, _EngineModule, _f, _gn, build_unet_trunk, run_conv, run_gn, run_in_conv,
-                   run_out_head, run_resblock_conv1_raw, run_sequential)
+from .unet import (Act, AttentionBlock, Ctx, Downsample, ResBlock, _EngineModule, _cs, _f, _gn, build_unet_trunk, run_conv,
+                   run_gn, run_in_conv, run_out_head, run_resblock_conv1_raw, run_sequential)
 
 Tensor = torch.Tensor
 
@@ -44,6 +44,96 @@ class FeatureDisentangle(nn.Module):
         super().__init__()
         self.conv_1 = nn.Sequential(_gn(in_channels), nn.SiLU(), nn.Conv2d(in_channels, in_channels, 3, 1, 1))
         self.conv_2 = nn.Sequential(_gn(in_channels), nn.SiLU(), nn.Conv2d(in_channels, half_conv_ch, 1, 1, 0))
+
+
+# ---------------------------------------------------------------------------------------------
+# grouped execution: same-shape modules with different weights as ONE launch (b200_conv_desc.wsets)
+# ---------------------------------------------------------------------------------------------
+def _gstack(pw, mods, kind: str) -> Tensor:
+    """Parameters of the same-shape modules ``mods`` stacked along a leading weight-set axis, cached in the packed-weight
+    object (rebuilt with it).  Packed conv weights are stacked along the tap axis and the per-module entries are re-pointed
+    at slices of the stack, so nothing is held twice."""
+    key = (kind, id(mods[0]))
+    t = pw.grouped.get(key)
+    if t is None:
+        if kind == "w":
+            t = torch.cat([pw.conv[id(m)] for m in mods], dim=0).contiguous()
+            taps = t.shape[0] // len(mods)
+            for i, m in enumerate(mods):
+                pw.conv[id(m)] = t[i * taps:(i + 1) * taps]
+        elif kind == "bias2":
+            t = torch.stack([pw.bias2[id(m)] for m in mods]).contiguous()
+        elif kind == "bias":
+            t = torch.stack([_f(m.bias) for m in mods]).contiguous()
+        else:       # GroupNorm gamma
+            t = torch.stack([_f(m.weight) for m in mods]).contiguous()
+        pw.grouped[key] = t
+    return t
+
+
+def run_gn_g(cx: Ctx, gns, x: Act, silu: bool = True, film: Optional[Tensor] = None, film_gstride: int = 0) -> Tensor:
+    g = gns[0]
+    return ops.group_norm(x.t, _gstack(cx.pw, gns, "gamma"), _gstack(cx.pw, gns, "bias"), groups=g.num_groups, eps=g.eps,
+                          silu=silu, film=film, cs0=x.cs, wsets=len(gns), film_gstride=film_gstride)
+
+
+def run_resblock_g(cx: Ctx, ms, x: Act) -> Act:
+    """run_resblock for ``len(ms)`` same-shape ResBlocks with separate weights: the batch of ``x`` is that many equal
+    groups of images, group g goes through ms[g] (plain and FiLM variants; no up / down resampling)."""
+    pw, m, G = cx.pw, ms[0], len(ms)
+    off, width = pw.emb_slices[id(m)]
+    gstride = pw.emb_slices[id(ms[1])][0] - off          # uniform pitch: see DSUnetModel._pack_modules
+    emb_out = cx.emb_all[:, off:off + width]
+    conv1s, conv2s = [b.in_layers[2] for b in ms], [b.out_layers[3] for b in ms]
+    a = run_gn_g(cx, [b.in_layers[0] for b in ms], x)
+    w1 = _gstack(pw, conv1s, "w")
+    if m.use_scale_shift_norm:
+        h = run_conv(cx, [(a, w1, 0, 3, 1)], bias=_gstack(pw, conv1s, "bias"), wsets=G)
+        a2 = run_gn_g(cx, [b.out_layers[0] for b in ms], h, film=emb_out, film_gstride=gstride)
+    else:
+        h = run_conv(cx, [(a, w1, 0, 3, 1)], rowbias=emb_out, wsets=G, rowbias_gstride=gstride)   # b1 folded into emb_out
+        a2 = run_gn_g(cx, [b.out_layers[0] for b in ms], h)
+    segs = [(a2, _gstack(pw, conv2s, "w"), 0, 3, 1)]
+    residual = None
+    if isinstance(m.skip_connection, nn.Conv2d):
+        ks = m.skip_connection.kernel_size[0]
+        segs.append((x.t, _gstack(pw, [b.skip_connection for b in ms], "w"), 0, ks, ks // 2))
+    else:
+        residual = x.t
+    return run_conv(cx, segs, bias=_gstack(pw, ms, "bias2"), residual=residual, wsets=G)
+
+
+def run_attention_g(cx: Ctx, ms, x: Act) -> Act:
+    pw, m, G = cx.pw, ms[0], len(ms)
+    n, h, w, c = x.t.shape
+    a = run_gn_g(cx, [b.norm for b in ms], x, silu=False)
+    qkvs, projs = [b.qkv for b in ms], [b.proj_out for b in ms]
+    qkv = ops.conv2d([(a, _gstack(pw, qkvs, "w"), 0, 1, 0)], bias=_gstack(pw, qkvs, "bias"), wsets=G)
+    att = ops.attention_qkv(qkv.view(n, h * w, 3 * c), m.num_heads, m.use_new_attention_order)
+    return run_conv(cx, [(att.view(n, h, w, c), _gstack(pw, projs, "w"), 0, 1, 0)], bias=_gstack(pw, projs, "bias"),
+                    residual=x.t, wsets=G)
+
+
+def _groupable(layers) -> bool:
+    l0 = layers[0]
+    if isinstance(l0, ResBlock):
+        return not (l0.up or l0.down)
+    return isinstance(l0, AttentionBlock) or (isinstance(l0, Downsample) and l0.use_conv)
+
+
+def run_sequential_g(cx: Ctx, seqs, x: Act) -> Act:
+    """The same TimestepEmbedSequential position of several encoders (separate weights) as grouped launches."""
+    for layers in zip(*seqs):
+        l0 = layers[0]
+        if isinstance(l0, ResBlock):
+            x = run_resblock_g(cx, layers, x)
+        elif isinstance(l0, AttentionBlock):
+            x = run_attention_g(cx, layers, x)
+        else:
+            ops_ = [d.op for d in layers]
+            x = run_conv(cx, [(x.t, _gstack(cx.pw, ops_, "w"), 0, 3, 1)], stride=2, bias=_gstack(cx.pw, ops_, "bias"),
+                         wsets=len(layers))
+    return x
 
 
 class DSUnetModel(_EngineModule):
@@ -73,6 +163,44 @@ class DSUnetModel(_EngineModule):
         self.hoist_conditioning = os.environ.get("B200DIFF_HOIST_COND", "1") != "0"
         self._cond_caches = {}
         self._cond_key = None
+        # the four encoders (same shapes, separate weights: model.py:674-686) run as ONE grouped launch per layer wherever a
+        # single encoder's map cannot fill the GPU: every input block whose OUTPUT map has at most this many pixels
+        # (geometry only, so a slice's result does not depend on the batch it is sampled in); 0 disables grouping
+        self.group_max_pixels = int(os.environ.get("B200DIFF_GROUP_MAXPIX", "1024"))
+
+    def _pack_modules(self):
+        """Module walk order for PackedWeights: the four encoders first, so that block j of encoder e has its timestep
+        projection rows at ``e * pitch + off_j`` inside emb_all (grouped launches address them with one group stride)."""
+        seen = set()
+        for root in (self.input_blocks, self.input_blocks_a, self.input_blocks_al, self.input_blocks_l):
+            for m in root.modules():
+                seen.add(id(m))
+                yield m
+        for m in self.modules():
+            if id(m) not in seen:
+                yield m
+
+    def _group_start(self, h: int, w: int) -> int:
+        """Index of the first input block that runs grouped for an h x w input (len(input_blocks) = none)."""
+        nb = len(self.input_blocks)
+        if self.group_max_pixels <= 0:
+            return nb
+        start, px = nb, h * w
+        sizes = []
+        for blk in self.input_blocks:
+            if any(isinstance(l, Downsample) or (isinstance(l, ResBlock) and l.down) for l in blk):
+                px //= 4
+            sizes.append(px)
+        for i in range(nb - 1, 0, -1):          # the longest groupable suffix of small-map blocks
+            if sizes[i] <= self.group_max_pixels and all(_groupable(layers) for layers in zip(self.input_blocks[i])):
+                start = i
+            else:
+                break
+        start = max(start, 2)       # blocks 0 / 1 hold the first conv and the loop-invariant conditioning prefix
+        # the block before the grouped suffix must end in a ResBlock (its last conv writes straight into the stacked buffer)
+        if start < nb and not isinstance(self.input_blocks[start - 1][-1], ResBlock):
+            start = nb
+        return min(start, nb)
 
     def invalidate(self):
         super().invalidate()
@@ -143,6 +271,32 @@ class DSUnetModel(_EngineModule):
         gated = ops.se_attention(mean, _f(se[0].weight), _f(se[2].weight))
         return ops.conv2d([(gated, cx.pw.conv[id(conv)], 0, 3, 1)], bias=_f(conv.bias))
 
+    def _fd_grouped(self, cx: Ctx, x3: Act, n: int):
+        """All four FeatureDisentangle heads (:695-719) over the stacked conditioning streams ``x3`` = [h_a; h_al; h_l]
+        ([3N, h, w, C]) as FOUR grouped launches (weight set = head; order style, content, anatomy, lesion), then the four
+        family means -> SE_Attention -> 3x3 projections (:722-725) with one grouped convolution.  Returns
+        (features [4 * 3N, h, w, C/2], projections [4N, h, w, C/2]).  The anatomy head also sees h_l and the lesion head h_a —
+        two unused 8x8 maps per slice, the price of equal-sized groups."""
+        pw = cx.pw
+        heads = (self.conv_style, self.conv_content, self.conv_anatomy, self.conv_lesion)
+        projs = (self.style_proj, self.share_content_proj, self.anatomy_proj, self.lesion_proj)
+        xin = Act(x3.t.repeat(4, 1, 1, 1), x3.cs.repeat(4, 1, 1))
+        c1s, c2s = [m.conv_1[2] for m in heads], [m.conv_2[2] for m in heads]
+        a = run_gn_g(cx, [m.conv_1[0] for m in heads], xin)
+        mid = run_conv(cx, [(a, _gstack(pw, c1s, "w"), 0, 3, 1)], bias=_gstack(pw, c1s, "bias"), residual=xin.t, wsets=4)
+        a2 = run_gn_g(cx, [m.conv_2[0] for m in heads], mid)
+        f = ops.conv2d([(a2, _gstack(pw, c2s, "w"), 0, 1, 0)], bias=_gstack(pw, c2s, "bias"), wsets=4)
+        sl = lambda head, j: f[(3 * head + j) * n:(3 * head + j + 1) * n]
+        fams = ([sl(0, 0), sl(0, 1), sl(0, 2)], [sl(1, 0), sl(1, 1), sl(1, 2)], [sl(2, 0), sl(2, 1)], [sl(3, 1), sl(3, 2)])
+        gated = torch.empty((4 * n,) + tuple(f.shape[1:]), device=f.device, dtype=f.dtype)
+        for i, (feats, seq) in enumerate(zip(fams, projs)):
+            mean = ops.add4_scale(*feats, *([None] * (4 - len(feats))), scale=1.0 / len(feats))
+            se = seq[0].se
+            ops.se_attention(mean, _f(se[0].weight), _f(se[2].weight), out=gated[i * n:(i + 1) * n])
+        pcs = [seq[1] for seq in projs]
+        proj = ops.conv2d([(gated, _gstack(pw, pcs, "w"), 0, 3, 1)], bias=_gstack(pw, pcs, "bias"), wsets=4)
+        return f, proj
+
     @torch.no_grad()
     def forward(self, x, timesteps=None, context=None, y=None, step_ptr: Optional[Tensor] = None,
                 return_features: bool = True, cond_cached: bool = False, **kwargs):
@@ -165,23 +319,40 @@ class DSUnetModel(_EngineModule):
         if cond_cached and self._cond_key is not None and self._cond_key[:3] == (n, x.shape[2], x.shape[3]):
             cached = self._cond_caches[self._cond_key]      # armed by prepare_conditioning() for THIS run's cond
 
-        def encoder(blocks, xin, pre=None):
+        enc_blocks = (self.input_blocks, self.input_blocks_a, self.input_blocks_al, self.input_blocks_l)
+        gstart = self._group_start(x.shape[2], x.shape[3])
+        stacked = None
+        if gstart < len(self.input_blocks):
+            # output of block gstart-1 of the four encoders, stacked along N: [4N, h, w, C] + its statistics, allocated
+            # here (before any fork) and written in place by each encoder's last ungrouped convolution
+            px = x.shape[2] * x.shape[3]
+            for blk in list(self.input_blocks)[:gstart]:
+                if any(isinstance(l, Downsample) or (isinstance(l, ResBlock) and l.down) for l in blk):
+                    px //= 4
+            shrink = int(round((x.shape[2] * x.shape[3] / px) ** 0.5))
+            cch = self.input_blocks[gstart - 1][-1].out_channels
+            stacked = Act(torch.empty((4 * n, x.shape[2] // shrink, x.shape[3] // shrink, cch), device=x.device,
+                                      dtype=self.act_dtype), cx.stats_for(4 * n, cch))
+
+        def encoder(e, xin, pre=None):
+            blocks = enc_blocks[e]
+            dst_of = lambda i: (Act(stacked.t[e * n:(e + 1) * n], stacked.cs[e * n:(e + 1) * n])
+                                if stacked is not None and i == gstart - 1 else None)
             if pre is not None:           # (first conv, conv1 of the first ResBlock) from the per-run cache
                 h, c1 = pre
                 hs = [h]
-                h = run_sequential(cx, blocks[1], h, None, conv1_raw=c1)
+                h = run_sequential(cx, blocks[1], h, None, conv1_raw=c1, dst=dst_of(1))
                 hs.append(h)
-                rest = list(blocks)[2:]
+                first = 2
             else:
                 h = run_in_conv(cx, blocks[0][0], xin.contiguous(), self.act_dtype)
                 hs = [h]
-                rest = list(blocks)[1:]
-            for blk in rest:
-                h = run_sequential(cx, blk, h, None)
+                first = 1
+            for i in range(first, gstart):
+                h = run_sequential(cx, blocks[i], h, None, dst=dst_of(i))
                 hs.append(h)
             return hs
 
-        enc_blocks = (self.input_blocks, self.input_blocks_a, self.input_blocks_al, self.input_blocks_l)
         # The four encoders are independent (separate weights, same emb): the three conditioning encoders run on side
         # streams, forked after the timestep path and joined before their first consumer, so their latency-bound
         # 8x8 .. 32x32 layers overlap with the noise stream's instead of leaving most SMs idle.  Inside a captured
@@ -197,14 +368,25 @@ class DSUnetModel(_EngineModule):
             for i in (1, 2, 3):
                 with torch.cuda.stream(side[i - 1]):
                     side[i - 1].wait_event(ev0)
-                    skips[i] = encoder(enc_blocks[i], inputs[i], None if cached is None else cached[i - 1])
+                    skips[i] = encoder(i, inputs[i], None if cached is None else cached[i - 1])
                     ev = torch.cuda.Event()
                     ev.record(side[i - 1])
                     joins.append(ev)
-            skips[0] = encoder(enc_blocks[0], inputs[0])
+            skips[0] = encoder(0, inputs[0])
         else:
-            skips = [encoder(b, xin, None if (cached is None or i == 0) else cached[i - 1])
-                     for i, (b, xin) in enumerate(zip(enc_blocks, inputs))]
+            skips = [encoder(i, xin, None if (cached is None or i == 0) else cached[i - 1])
+                     for i, xin in enumerate(inputs)]
+        hg = None
+        if stacked is not None:
+            # grouped suffix of the four encoders: ONE launch per layer over the [4N, ...] stack (weight set = encoder)
+            if fork:
+                for ev in joins:
+                    main.wait_event(ev)
+            hg = stacked
+            for i in range(gstart, len(self.input_blocks)):
+                hg = run_sequential_g(cx, [blocks[i] for blocks in enc_blocks], hg)
+                for e in range(4):
+                    skips[e].append(Act(hg.t[e * n:(e + 1) * n], None if hg.cs is None else hg.cs[e * n:(e + 1) * n]))
         last = [hs[-1] for hs in skips]
 
         def skip_mean(level_acts):
@@ -226,53 +408,84 @@ class DSUnetModel(_EngineModule):
                 skip_means = [skip_mean([skips[e][lvl] for e in range(4)]) for lvl in range(len(skips[0]))]
                 ev_means = torch.cuda.Event()
                 ev_means.record(side[3])
-        h_n = run_sequential(cx, self.middle_block, last[0], None)     # :688
-        h_a, h_al, h_l = last[1], last[2], last[3]
-        fd = lambda m, v: self._fd(cx, m, v)
-        if fork:
-            # the four feature families (3 + 3 + 2 + 2 FeatureDisentangle heads on 8x8 maps, then mean -> SE -> conv) are
-            # independent chains of latency-bound kernels: one family per stream, joined before the 5-way concat
-            for ev in joins:
-                main.wait_event(ev)
-            ev1 = torch.cuda.Event()
-            ev1.record(main)
-            fam = {}
-
-            def family(name, head, proj, srcs):
-                feats = [fd(head, v) for v in srcs]
-                fam[name] = (feats, self._proj(cx, proj, feats))
-
-            work = [("content", self.conv_content, self.share_content_proj, (h_a, h_al, h_l)),
-                    ("anatomy", self.conv_anatomy, self.anatomy_proj, (h_a, h_al)),
-                    ("lesion", self.conv_lesion, self.lesion_proj, (h_al, h_l))]
-            joins2 = []
-            for st, args in zip(side, work):
-                with torch.cuda.stream(st):
-                    st.wait_event(ev1)
-                    family(*args)
-                    ev = torch.cuda.Event()
-                    ev.record(st)
-                    joins2.append(ev)
-            family("style", self.conv_style, self.style_proj, (h_a, h_al, h_l))
-            # style / content heads of the NOISE stream only feed the returned feature dict (model.py:695-700, 751-756):
-            # every sampler discards it, so they are skipped when the caller does not ask for features
+        group_fd = self.group_max_pixels > 0
+        if group_fd:
+            # the ten FeatureDisentangle applications (four heads over the conditioning streams' 8x8 maps) and the four
+            # mean -> SE -> conv projections as grouped launches on a side stream, overlapping the noise stream's middle block
+            if hg is not None:
+                x3 = Act(hg.t[n:], hg.cs[n:])
+            else:
+                if fork:
+                    for ev in joins:
+                        main.wait_event(ev)
+                x3 = Act(torch.cat([last[i].t for i in (1, 2, 3)]), torch.cat([_cs(cx, last[i]) for i in (1, 2, 3)]))
+            if fork:
+                ev1 = torch.cuda.Event()
+                ev1.record(main)
+                with torch.cuda.stream(side[0]):
+                    side[0].wait_event(ev1)
+                    f, proj = self._fd_grouped(cx, x3, n)
+                    ev_fd = torch.cuda.Event()
+                    ev_fd.record(side[0])
+            else:
+                f, proj = self._fd_grouped(cx, x3, n)
+            h_n = run_sequential(cx, self.middle_block, last[0], None)     # :688
+            fd = lambda m, v: self._fd(cx, m, v)
             h_n_style, h_n_content = (fd(self.conv_style, h_n), fd(self.conv_content, h_n)) if return_features else (None, None)
-            for ev in joins2:
-                main.wait_event(ev)
-            (style, h_style), (content, h_share) = fam["style"], fam["content"]
-            (anatomy, h_anat), (lesion, h_les) = fam["anatomy"], fam["lesion"]
+            if fork:
+                main.wait_event(ev_fd)
+            sl = lambda head, j: f[(3 * head + j) * n:(3 * head + j + 1) * n]
+            style, content = [sl(0, j) for j in range(3)], [sl(1, j) for j in range(3)]
+            anatomy, lesion = [sl(2, 0), sl(2, 1)], [sl(3, 1), sl(3, 2)]
+            h_style, h_share, h_anat, h_les = (proj[i * n:(i + 1) * n] for i in range(4))
         else:
-            # style / content heads of the NOISE stream only feed the returned feature dict (model.py:695-700, 751-756):
-            # every sampler discards it, so they are skipped when the caller does not ask for features
-            h_n_style, h_n_content = (fd(self.conv_style, h_n), fd(self.conv_content, h_n)) if return_features else (None, None)
-            style = [fd(self.conv_style, v) for v in (h_a, h_al, h_l)]
-            content = [fd(self.conv_content, v) for v in (h_a, h_al, h_l)]
-            anatomy = [fd(self.conv_anatomy, v) for v in (h_a, h_al)]
-            lesion = [fd(self.conv_lesion, v) for v in (h_al, h_l)]
-            h_style = self._proj(cx, self.style_proj, style)
-            h_share = self._proj(cx, self.share_content_proj, content)
-            h_anat = self._proj(cx, self.anatomy_proj, anatomy)
-            h_les = self._proj(cx, self.lesion_proj, lesion)
+            h_n = run_sequential(cx, self.middle_block, last[0], None)     # :688
+            h_a, h_al, h_l = last[1], last[2], last[3]
+            fd = lambda m, v: self._fd(cx, m, v)
+            if fork:
+                # the four feature families (3 + 3 + 2 + 2 FeatureDisentangle heads on 8x8 maps, then mean -> SE -> conv) are
+                # independent chains of latency-bound kernels: one family per stream, joined before the 5-way concat
+                for ev in joins:
+                    main.wait_event(ev)
+                ev1 = torch.cuda.Event()
+                ev1.record(main)
+                fam = {}
+
+                def family(name, head, proj, srcs):
+                    feats = [fd(head, v) for v in srcs]
+                    fam[name] = (feats, self._proj(cx, proj, feats))
+
+                work = [("content", self.conv_content, self.share_content_proj, (h_a, h_al, h_l)),
+                        ("anatomy", self.conv_anatomy, self.anatomy_proj, (h_a, h_al)),
+                        ("lesion", self.conv_lesion, self.lesion_proj, (h_al, h_l))]
+                joins2 = []
+                for st, args in zip(side, work):
+                    with torch.cuda.stream(st):
+                        st.wait_event(ev1)
+                        family(*args)
+                        ev = torch.cuda.Event()
+                        ev.record(st)
+                        joins2.append(ev)
+                family("style", self.conv_style, self.style_proj, (h_a, h_al, h_l))
+                # style / content heads of the NOISE stream only feed the returned feature dict (model.py:695-700, 751-756):
+                # every sampler discards it, so they are skipped when the caller does not ask for features
+                h_n_style, h_n_content = (fd(self.conv_style, h_n), fd(self.conv_content, h_n)) if return_features else (None, None)
+                for ev in joins2:
+                    main.wait_event(ev)
+                (style, h_style), (content, h_share) = fam["style"], fam["content"]
+                (anatomy, h_anat), (lesion, h_les) = fam["anatomy"], fam["lesion"]
+            else:
+                # style / content heads of the NOISE stream only feed the returned feature dict (model.py:695-700, 751-756):
+                # every sampler discards it, so they are skipped when the caller does not ask for features
+                h_n_style, h_n_content = (fd(self.conv_style, h_n), fd(self.conv_content, h_n)) if return_features else (None, None)
+                style = [fd(self.conv_style, v) for v in (h_a, h_al, h_l)]
+                content = [fd(self.conv_content, v) for v in (h_a, h_al, h_l)]
+                anatomy = [fd(self.conv_anatomy, v) for v in (h_a, h_al)]
+                lesion = [fd(self.conv_lesion, v) for v in (h_al, h_l)]
+                h_style = self._proj(cx, self.style_proj, style)
+                h_share = self._proj(cx, self.share_content_proj, content)
+                h_anat = self._proj(cx, self.anatomy_proj, anatomy)
+                h_les = self._proj(cx, self.lesion_proj, lesion)
         cat = torch.cat([h_n.t, h_share, h_style, h_anat, h_les], dim=-1)          # :734 (8x8 maps: tiny)
         ap = self.all_proj[1]
         h = run_conv(cx, [(ops.add4_scale(cat, silu=True), pw.conv[id(ap)], 0, 1, 0)], bias=_f(ap.bias))   # :738

@@ -184,6 +184,8 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
         d.out_nhwc_f32 = _p(out)
     elif out is None:
         out = torch.empty((n, hout, wout, cout), device=src0.device, dtype=src0.dtype)
+    elif tuple(out.shape) != (n, hout, wout, cout) or out.dtype != src0.dtype:
+        raise L.B200Error("conv2d: out shape/dtype mismatch")
     d.bias = _p(_f32(bias))
     d.rowbias, d.rowbias_stride = None, 0
     d.wsets, d.rowbias_gstride, d.rowscale_gstride = wsets, rowbias_gstride, 0
@@ -608,9 +610,12 @@ def avg_pool2x(x: Tensor) -> Tensor:
 
 
 def add4_scale(a: Tensor, b: Optional[Tensor] = None, c: Optional[Tensor] = None, d: Optional[Tensor] = None,
-               scale: float = 1.0, silu: bool = False) -> Tensor:
+               scale: float = 1.0, silu: bool = False, out: Optional[Tensor] = None) -> Tensor:
     _dev(a)
-    out = torch.empty_like(a)
+    if out is None:
+        out = torch.empty_like(a)
+    elif out.shape != a.shape or out.dtype != a.dtype:
+        raise L.B200Error("add4_scale: out shape/dtype mismatch")
     nin = 1 + (b is not None) + (c is not None) + (d is not None)
     _timed("add4_scale", 0.0, 2.0 * a.numel() * (nin + 1),
            lambda: L.check(L.lib().b200_add4_scale(_p(a), _p(b), _p(c), _p(d), scale, _p(out), a.numel(), int(silu),
@@ -632,12 +637,15 @@ def add4_scale_stats(a: Tensor, b: Optional[Tensor], c: Optional[Tensor], d: Opt
     return out
 
 
-def se_attention(x: Tensor, w1: Tensor, w2: Tensor) -> Tensor:
+def se_attention(x: Tensor, w1: Tensor, w2: Tensor, out: Optional[Tensor] = None) -> Tensor:
     _dev(x)
     n, h, w, c = x.shape
     cr = w1.shape[0]
     scratch = torch.empty((2, n, c), device=x.device, dtype=torch.float32)
-    out = torch.empty_like(x)
+    if out is None:
+        out = torch.empty_like(x)
+    elif out.shape != x.shape or out.dtype != x.dtype:
+        raise L.B200Error("se_attention: out shape/dtype mismatch")
     L.check(L.lib().b200_se_attention(_p(x), _p(_f32(w1)), _p(_f32(w2)), _p(out), _p(scratch), n, h * w, c, cr,
                                       act_code(x.dtype), _stream()), "se_attention")
     return out

@@ -559,6 +559,14 @@ class DDPM(nn.Module):
         noise = torch.randn_like(x_start) if noise is None else noise
         return self._comb("sqrt_alphas_cumprod", x_start, "sqrt_one_minus_alphas_cumprod", noise, t, False)
 
+    # ---- batch -> network input (ddpm.py:423-429; trainers/trainer_ds_diff.py:532-546 with cond_k) ----
+    def get_input(self, batch, k, cond_k=None, **kwargs):
+        x = batch[k]
+        if len(x.shape) == 3:
+            x = x[..., None]
+        x = x.to(memory_format=torch.contiguous_format).float()
+        return x if cond_k is None else (x, batch[cond_k])
+
     # ---- model call (trainers/trainer_ds_diff.py:740-755) ----
     def apply_model(self, x_noisy, t, cond, return_ids=False, **kw):
         if not isinstance(cond, dict):
@@ -672,6 +680,66 @@ class LatentDiffusion(DDPM):
     def get_first_stage_encoding(self, encoder_posterior):
         z = encoder_posterior.sample() if hasattr(encoder_posterior, "sample") else encoder_posterior
         return self._scaled(z, float(self.scale_factor))
+
+    def _posterior_sample(self, posterior, noise=None):
+        """encode -> sample of either first-stage flavour: the in-tree KL returns the distribution itself
+        (ldm/models/autoencoder.py:138-142), the diffusers one wraps it in ``.latent_dist``
+        (trainers/trainer_latent_diffusion.py:185-186, ddpm.py:779-780)."""
+        posterior = getattr(posterior, "latent_dist", posterior)
+        if noise is not None:
+            return posterior.sample(noise)
+        return posterior.sample()
+
+    @torch.no_grad()
+    def get_input(self, batch, k, return_first_stage_outputs=False, force_c_encode=False, cond_key=None,
+                  return_original_cond=False, bs=None, return_x=False, noise=None):
+        """LatentDiffusion.get_input (ddpm.py:771-824): target image -> first-stage posterior sample -> scaled latent z, plus
+        the conditioning ``c`` (the un-encoded ``batch[cond_key]``: the trainers' cond stage is the identity / the concat
+        glue below).  ``noise``: optional N(0,1) tensor for the posterior sample (reproducible fixtures)."""
+        x = DDPM.get_input(self, batch, k)
+        if bs is not None:
+            x = x[:bs]
+        x = x.to(self.betas.device)
+        z = self.get_first_stage_encoding(self._posterior_sample(self.encode_first_stage(x), noise)).detach()
+        c = xc = None
+        if self.model.conditioning_key is not None and not getattr(self, "force_null_conditioning", False):
+            cond_key = cond_key or getattr(self, "cond_stage_key", "image")
+            xc = x if cond_key == k else batch[cond_key]
+            if torch.is_tensor(xc):
+                xc = xc.to(self.betas.device)
+            c = xc
+            if bs is not None and torch.is_tensor(c):
+                c = c[:bs]
+        out = [z, c]
+        if return_first_stage_outputs:
+            out.extend([x, self.decode_first_stage(z)])
+        if return_x:
+            out.append(x)
+        if return_original_cond:
+            out.append(xc)
+        return out
+
+    @torch.no_grad()
+    def get_concat_conditioning(self, img, n_keys: int = 1, bs=None, noises=None):
+        """The latent-conditioning glue of LatentDiffusionModel.get_input (trainers/trainer_latent_diffusion.py:153-191,
+        conditioning_key 'concat'): the conditioning image holds ``n_keys`` contrasts stacked along C; EVERY contrast is
+        pushed through the first-stage encoder separately, its posterior sampled and scaled, and the latents are
+        concatenated along C -> ``{"c_concat": [c_cat]}``.  Here the ``n_keys`` encodes run as ONE batched encoder pass
+        ([n_keys * B, C/n_keys, H, W]) on the same kernels as ``encode``; ``noises``: optional per-contrast N(0,1)
+        tensors."""
+        if bs is not None:
+            img = img[:bs]
+        img = img.to(self.betas.device).float()
+        if img.shape[1] > 3 and n_keys > 1:            # :157-158
+            parts = list(torch.chunk(img, n_keys, 1))
+        else:
+            parts = [img]
+        b = img.shape[0]
+        stacked = torch.cat(parts, 0).contiguous() if len(parts) > 1 else parts[0].contiguous()
+        noise = None if noises is None else torch.cat([nz.to(img.device) for nz in noises], 0)
+        z = self.get_first_stage_encoding(self._posterior_sample(self.encode_first_stage(stacked), noise))
+        c_cat = torch.cat([z[i * b:(i + 1) * b] for i in range(len(parts))], dim=1) if len(parts) > 1 else z
+        return {"c_concat": [c_cat]}
 
     @staticmethod
     def _scaled(z, s: float):

@@ -119,8 +119,11 @@ class PackedWeights:
         self.conv = {}        # id(module) -> packed [taps, Cout, CinPad]
         self.bias2 = {}       # id(ResBlock) -> conv2 bias + skip bias
         self.emb_slices = {}  # id(ResBlock) -> (offset, width)
+        self.grouped = {}     # (kind, id(first module)) -> parameters of same-shape modules stacked for grouped launches
         emb_w, emb_b, off = [], [], 0
-        for m in root.modules():
+        # a root may fix the walk order (DSUnetModel: its four encoders first, so their timestep-projection rows sit at a
+        # uniform pitch inside emb_all and one grouped launch can address all four)
+        for m in (root._pack_modules() if hasattr(root, "_pack_modules") else root.modules()):
             if isinstance(m, (nn.Conv2d, nn.Conv1d)):
                 w = m.weight.detach()
                 if w.shape[1] % 8 == 0 and w.shape[0] % 8 == 0:
@@ -189,8 +192,13 @@ def run_gn(cx: Ctx, gn: nn.GroupNorm, x0: Act, x1: Optional[Act] = None, silu: b
                           eps=gn.eps, silu=silu, film=film, cs0=_cs(cx, x0), cs1=None if x1 is None else _cs(cx, x1))
 
 
-def run_conv(cx: Ctx, segs, want_stats: bool = True, **kw) -> Act:
+def run_conv(cx: Ctx, segs, want_stats: bool = True, dst: Optional[Act] = None, **kw) -> Act:
+    """``dst``: write the result (and its statistics) into this pre-allocated activation — a slice of a buffer that
+    stacks several producers along N for a later grouped launch."""
     src0, w0 = segs[0][0], segs[0][1]
+    if dst is not None:
+        ops.conv2d(segs, stats=dst.cs, out=dst.t, **kw)
+        return dst
     st = cx.stats_for(src0.shape[0], w0.shape[1]) if want_stats else None
     return Act(ops.conv2d(segs, stats=st, **kw), st)
 
@@ -202,7 +210,8 @@ def run_resblock_conv1_raw(cx: Ctx, m: ResBlock, x0: Act) -> Act:
     return run_conv(cx, [(a, cx.pw.conv[id(m.in_layers[2])], 0, 3, 1)])
 
 
-def run_resblock(cx: Ctx, m: ResBlock, x0: Act, x1: Optional[Act], conv1_raw: Optional[Act] = None) -> Act:
+def run_resblock(cx: Ctx, m: ResBlock, x0: Act, x1: Optional[Act], conv1_raw: Optional[Act] = None,
+                 dst: Optional[Act] = None) -> Act:
     """ResBlock._forward (openaimodel.py:264-284) on NHWC activations; input = cat([x0, x1], C).
     ``conv1_raw``: cached output of ``run_resblock_conv1_raw`` for this x0 — GN1 and conv1 are skipped and the bias +
     timestep term is added on the fly inside the second GroupNorm (its statistics are corrected analytically)."""
@@ -226,8 +235,8 @@ def run_resblock(cx: Ctx, m: ResBlock, x0: Act, x1: Optional[Act], conv1_raw: Op
         if isinstance(sk, nn.Conv2d):
             ks = sk.kernel_size[0]
             segs.append((xr, pw.conv[id(sk)], 0, ks, ks // 2))
-            return run_conv(cx, segs, bias=pw.bias2[id(m)])
-        return run_conv(cx, segs, bias=pw.bias2[id(m)], residual=xr)
+            return run_conv(cx, segs, bias=pw.bias2[id(m)], dst=dst)
+        return run_conv(cx, segs, bias=pw.bias2[id(m)], residual=xr, dst=dst)
     emb_out = cx.emb_all[:, off:off + width]
     conv1, conv2 = m.in_layers[2], m.out_layers[3]
     if conv1_raw is not None:
@@ -256,7 +265,7 @@ def run_resblock(cx: Ctx, m: ResBlock, x0: Act, x1: Optional[Act], conv1_raw: Op
             segs.append((x1.t, wsk, x0.t.shape[-1], ks, ks // 2))
     else:
         residual = x0.t if x1 is None else torch.cat([x0.t, x1.t], dim=-1)
-    return run_conv(cx, segs, bias=pw.bias2[id(m)], residual=residual)
+    return run_conv(cx, segs, bias=pw.bias2[id(m)], residual=residual, dst=dst)
 
 
 def run_attention(cx: Ctx, m: AttentionBlock, x: Act) -> Act:
@@ -288,13 +297,16 @@ def run_spatial_transformer(cx: Ctx, m: "tfm.SpatialTransformer", x: Act) -> Act
     return run_conv(cx, [(t.view(n, h, w, -1), wout, 0, 1, 0)], bias=_f(m.proj_out.bias), residual=x.t)
 
 
-def run_sequential(cx: Ctx, seq: nn.Sequential, x0: Act, x1: Optional[Act], conv1_raw: Optional[Act] = None) -> Act:
+def run_sequential(cx: Ctx, seq: nn.Sequential, x0: Act, x1: Optional[Act], conv1_raw: Optional[Act] = None,
+                   dst: Optional[Act] = None) -> Act:
     """TimestepEmbedSequential.forward (openaimodel.py:80-90).  ``conv1_raw``: cached first-ResBlock prefix (see
-    run_resblock); only valid when the sequential starts with a ResBlock."""
+    run_resblock); only valid when the sequential starts with a ResBlock.  ``dst``: pre-allocated output (honoured when the
+    sequential ENDS with a ResBlock; the caller checks)."""
     pw = cx.pw
+    last = len(seq) - 1
     for li, layer in enumerate(seq):
         if isinstance(layer, ResBlock):
-            x0, x1 = run_resblock(cx, layer, x0, x1, conv1_raw if li == 0 else None), None
+            x0, x1 = run_resblock(cx, layer, x0, x1, conv1_raw if li == 0 else None, dst if li == last else None), None
             continue
         if x1 is not None:
             x0, x1 = Act(torch.cat([x0.t, x1.t], dim=-1)), None

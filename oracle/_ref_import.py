@@ -38,7 +38,8 @@ REFERENCE_ROOT = _default_root()
 
 def available() -> bool:
     """True when the reference (sources here, or the byte-compiled oracle/_ref on the GPU box) can be imported."""
-    return os.path.isdir(os.path.join(_default_root(), "ldm"))
+    root = _default_root()
+    return any(os.path.isfile(os.path.join(root, "UNet_DS_Diff", "model" + ext)) for ext in (".py", ".refc"))
 
 
 class _Anything:
@@ -137,7 +138,7 @@ def install(reference_root: str = None) -> str:
     """Put the reference on sys.path behind inert stubs; returns the root (/root/reference in the authoring container,
     else the byte-compiled oracle/_ref)."""
     reference_root = reference_root or _default_root()
-    if not os.path.isdir(os.path.join(reference_root, "ldm")):
+    if not any(os.path.isfile(os.path.join(reference_root, "UNet_DS_Diff", "model" + ext)) for ext in (".py", ".refc")):
         raise FileNotFoundError(
             f"reference tree not found at {reference_root}: run oracle/build_ref.py in the authoring container "
             "(it byte-compiles /root/reference into oracle/_ref, which gpurun ships to the GPU box)")
@@ -166,9 +167,42 @@ def install(reference_root: str = None) -> str:
     sys.modules["lightning.pytorch.utilities"].rank_zero_only = lambda f: f
     sys.modules["omegaconf"].ListConfig = list
     sys.modules["omegaconf.listconfig"].ListConfig = list
+    if os.path.isfile(os.path.join(reference_root, "BUILD_INFO.txt")):     # compiled tree: .refc modules
+        _register_compiled_root(reference_root)
     if reference_root not in sys.path:
         sys.path.insert(0, reference_root)
     return reference_root
+
+
+_COMPILED_EXT = ".refc"      # oracle/build_ref.py
+
+
+def _compiled_path_hook(path: str):
+    """sys.path_hooks entry: directories under a compiled reference tree are searched for ``.refc`` modules (the .pyc
+    format under an extension that snapshot tools do not treat as cache files)."""
+    if not os.path.isdir(path) or _compiled_root_of(path) is None:
+        raise ImportError("not a compiled reference directory")
+    return importlib.machinery.FileFinder(path, (importlib.machinery.SourcelessFileLoader, [_COMPILED_EXT]))
+
+
+def _compiled_root_of(path: str):
+    path = os.path.abspath(path)
+    for root in _compiled_roots:
+        if path == root or path.startswith(root + os.sep):
+            return root
+    return None
+
+
+_compiled_roots = []
+
+
+def _register_compiled_root(root: str) -> None:
+    root = os.path.abspath(root)
+    if root not in _compiled_roots:
+        _compiled_roots.append(root)
+    if _compiled_path_hook not in sys.path_hooks:
+        sys.path_hooks.insert(0, _compiled_path_hook)
+    sys.path_importer_cache.clear()
 
 
 class AttrDict(dict):

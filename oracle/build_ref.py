@@ -1,7 +1,7 @@
 """Build recipe for ``oracle/_ref/`` — the UNMODIFIED reference, compiled (test / baseline infrastructure).
 
 The reference is pure Python, so "building" it means byte-compiling its modules FROM THE SOURCES WHERE THEY LIE under
-``/root/reference`` into sourceless ``.pyc`` files that mirror its package layout:
+``/root/reference`` into sourceless compiled modules (``.refc``: the ``.pyc`` format under an extension snapshot tools do not drop) that mirror its package layout:
 
     python oracle/build_ref.py            # also run by __graft_entry__.build() when /root/reference is present
 
@@ -24,6 +24,9 @@ SRC = os.environ.get("DSDIFF_REFERENCE_ROOT", "/root/reference")
 
 # packages the sampling hot path and its callers import
 PACKAGES = ["ldm", "UNet_DS_Diff", "training_project", "trainers", "Disc_diff/guided_diffusion", "loss_function"]
+# compiled-module extension: NOT ".pyc" — snapshot tools (gpurun among them) drop *.pyc as cache files, so the compiled
+# reference would silently stay behind; oracle/_ref_import.py registers a sourceless loader for this extension
+EXT = ".refc"
 # namespace parents that hold no needed code of their own
 PARENTS = ["Disc_diff"]
 
@@ -41,7 +44,7 @@ def build(src: str = SRC, out: str = OUT) -> int:
             for f in files:
                 if not f.endswith(".py"):
                     continue
-                dst = os.path.join(out, rel, f + "c")
+                dst = os.path.join(out, rel, f[:-3] + EXT)
                 os.makedirs(os.path.dirname(dst), exist_ok=True)
                 try:
                     # dfile: the path tracebacks show (the reference's own), checked-hash pyc without source validation

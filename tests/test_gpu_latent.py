@@ -271,3 +271,49 @@ def test_dit_in_guided_diffusion_ddim_loop_matches_oracle():
     out_graph = d.ddim_sample_loop(wrap, (2, 1, 32, 32), noise=x_T.cuda(), clip_denoised=True,
                                    model_kwargs={"c_concat": [cond.cuda()]}, eta=0.0)
     assert maxabs(out_graph, out) < 1e-6
+
+
+# -------------------------------------------------------------------------------------------------
+# LatentDiffusion.get_input + the trainer's latent concat-conditioning glue
+# -------------------------------------------------------------------------------------------------
+def test_latent_get_input_and_concat_conditioning_glue():
+    """ddpm.py:771-824 + trainers/trainer_latent_diffusion.py:153-191: the target and EVERY conditioning contrast are
+    pushed through the first-stage encoder, the posterior sampled, scaled by scale_factor and (conditioning) concatenated
+    along C — checked against the oracle's encoder (pinned to the reference's AutoencoderKL) with the same noise."""
+    P = _pkg()
+    from diffusion_models_dsdiff_b200 import samplers as S
+    hp, sd = synth_sd("xattn_d40")
+    net = P.UNetModel(**hp, act_dtype=torch.float16)
+    ahp, asd = synth_sd("ae_small")
+    ae = P.AutoencoderKL(ahp["ddconfig"], None, ahp["embed_dim"], act_dtype=torch.float16)
+    ae.load_state_dict(asd, strict=True)
+    ld = S.LatentDiffusion(ae, "__is_first_stage__", unet_config=net, timesteps=10, conditioning_key="concat",
+                           parameterization="eps", scale_factor=0.18215, channels=3, image_size=16).cuda().eval()
+    gen = torch.Generator().manual_seed(21)
+    target = torch.randn(3, 1, 32, 32, generator=gen).clamp(-1, 1)
+    contrasts = [torch.randn(3, 1, 32, 32, generator=gen).clamp(-1, 1) for _ in range(3)]
+    image = torch.cat(contrasts, 1)
+    nz = [torch.randn(3, 3, 16, 16, generator=gen) for _ in range(4)]
+    batch = {"pet": target, "image": image}
+
+    def ref_latent(x, noise):
+        return 0.18215 * O.ae_posterior_sample(O.ae_encode_moments(asd, x), noise)
+
+    z, c = ld.get_input(batch, "pet", cond_key="image", noise=nz[0].cuda())
+    assert z.shape == (3, 3, 16, 16) and torch.equal(c.cpu(), image)
+    zr = ref_latent(target, nz[0])
+    assert O.rel_err(z.cpu(), zr) < REL_TOL[torch.float16]
+    z2, c2, x, xrec = ld.get_input(batch, "pet", cond_key="image", bs=2, return_first_stage_outputs=True, noise=nz[0][:2].cuda())
+    assert z2.shape[0] == 2 and c2.shape[0] == 2 and x.shape == (2, 1, 32, 32) and xrec.shape == (2, 1, 32, 32)
+    assert torch.equal(z2, z[:2])
+    # a 3-contrast conditioning image is 3 channels: the reference only splits when C > 3 (:157-158) — then ONE encode ...
+    one = ld.get_concat_conditioning(image[:, :1], n_keys=1, noises=[nz[1]])["c_concat"][0]
+    assert O.rel_err(one.cpu(), ref_latent(contrasts[0], nz[1])) < REL_TOL[torch.float16]
+    # ... while 4+ channels are chunked into len(keys) images, each encoded on its own and concatenated along C
+    four = torch.cat(contrasts + [target], 1)
+    ae3 = P.AutoencoderKL(ahp["ddconfig"], None, ahp["embed_dim"], act_dtype=torch.float16)
+    ae3.load_state_dict(asd, strict=True)
+    got = ld.get_concat_conditioning(four, n_keys=4, noises=nz)["c_concat"][0]
+    assert got.shape == (3, 12, 16, 16)
+    want = torch.cat([ref_latent(v, n_) for v, n_ in zip(contrasts + [target], nz)], 1)
+    assert O.rel_err(got.cpu(), want) < REL_TOL[torch.float16]

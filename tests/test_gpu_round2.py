@@ -83,10 +83,12 @@ def test_grouped_conv_matches_separate_launches(case, dt):
                         rowbias=emb[:, 8 + g * co:8 + (g + 1) * co], residual=nhwc(res[g], dt), stats=st1)
         if ci * k * k < 8000:      # long-K 8x8 layers run split-K with a set-count-dependent split: equal to rounding only
             assert torch.equal(y1, y[g * npg:(g + 1) * npg]), f"grouped != separate launch, set {g}"
-            assert torch.allclose(st1, st[g * npg:(g + 1) * npg], rtol=1e-12, atol=1e-9)
+            # statistics of the same stored values; the two launches may take different epilogue flavours (fast / generic),
+            # whose fp32 column sums add in a different order
+            assert torch.allclose(st1, st[g * npg:(g + 1) * npg], rtol=1e-5, atol=1e-4)
         else:
             close(nchw(y1), nchw(y[g * npg:(g + 1) * npg]), dt, "grouped vs separate (split-K)")
-            assert torch.allclose(st1, st[g * npg:(g + 1) * npg], rtol=2e-2, atol=1e-2)
+            assert torch.allclose(st1, st[g * npg:(g + 1) * npg], rtol=2e-2, atol=1e-2 if dt == torch.float16 else 1e-1)
 
 
 @pytest.mark.parametrize("dt", DTYPES)
@@ -248,3 +250,49 @@ def test_inplace_weight_update_repacks_and_recaptures():
     with torch.no_grad():
         net.out[2].weight.mul_(0.5)
     assert not torch.equal(a, run())
+
+
+# -------------------------------------------------------------------------------------------------
+# DS-Diff: the four encoders' small-map suffix and the FeatureDisentangle section as grouped launches
+# -------------------------------------------------------------------------------------------------
+def _ds_net(dtype=torch.float16):
+    import diffusion_models_dsdiff_b200 as P
+    from _util import synth_sd
+    hp, sd = synth_sd("ds_small")
+    net = P.DSUnetModel(**hp, act_dtype=dtype)
+    net.load_state_dict(sd, strict=True)
+    return net.cuda().eval()
+
+
+@pytest.mark.parametrize("streams", [True, False])
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_grouped_encoders_match_separate_launches(n, streams):
+    """Grouping only changes which launch computes a layer (and the split-K partition of the 8x8 long-K layers): the
+    result agrees with the one-launch-per-encoder path far inside the precision bound, for odd images-per-set too."""
+    import dsdiff_oracle as O
+    from _util import golden
+    net = _ds_net()
+    net.encoder_streams = streams
+    g = golden("ds_small")
+    x = torch.cat([g["x"][:1] * (1.0 + 0.1 * i) for i in range(n)]).cuda()
+    t = g["t"][:1].repeat(n).cuda()
+    assert net._group_start(x.shape[2], x.shape[3]) < len(net.input_blocks), "fixture does not exercise grouping"
+    y_g, f_g = net(x, t)
+    net.group_max_pixels = 0
+    y_s, f_s = net(x, t)
+    assert O.rel_err(y_g.cpu(), y_s.cpu()) < 3e-4
+    for k in f_g:
+        for a, b in zip(f_g[k], f_s[k]):
+            assert O.rel_err(a.cpu(), b.cpu()) < 3e-4, k
+
+
+def test_grouped_encoders_are_batch_independent():
+    """A slice's result must not depend on the batch it is sampled in (per-slice reproducibility across world sizes)."""
+    from _util import golden
+    net = _ds_net()
+    g = golden("ds_small")
+    x = torch.cat([g["x"][:1] * (1.0 + 0.1 * i) for i in range(3)]).cuda()
+    t = g["t"][:1].repeat(3).cuda()
+    y3, _ = net(x, t)
+    y1, _ = net(x[1:2].contiguous(), t[1:2])
+    assert torch.equal(y3[1:2], y1)
