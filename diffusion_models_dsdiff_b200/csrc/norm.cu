@@ -185,7 +185,7 @@ add4_stats_kernel(const T *__restrict__ a, const T *__restrict__ b, const T *__r
 
 // y = silu?( (x - mean_g) * rstd_g * gamma_c + beta_c ) [ * (1 + scale_nc) + shift_nc ]
 template <typename T>
-__global__ void __launch_bounds__(kNormThreads)
+__global__ void __launch_bounds__(kNormThreads, 4)
 gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int C1, int HW,
                 int groups, float eps, int pix_per_block, const double *__restrict__ stats,
                 const double *__restrict__ cs0, const double *__restrict__ cs1,

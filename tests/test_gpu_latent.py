@@ -311,8 +311,6 @@ def test_latent_get_input_and_concat_conditioning_glue():
     assert O.rel_err(one.cpu(), ref_latent(contrasts[0], nz[1])) < REL_TOL[torch.float16]
     # ... while 4+ channels are chunked into len(keys) images, each encoded on its own and concatenated along C
     four = torch.cat(contrasts + [target], 1)
-    ae3 = P.AutoencoderKL(ahp["ddconfig"], None, ahp["embed_dim"], act_dtype=torch.float16)
-    ae3.load_state_dict(asd, strict=True)
     got = ld.get_concat_conditioning(four, n_keys=4, noises=nz)["c_concat"][0]
     assert got.shape == (3, 12, 16, 16)
     want = torch.cat([ref_latent(v, n_) for v, n_ in zip(contrasts + [target], nz)], 1)
