@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200diff.so")
 
-ABI_VERSION = 10        # must equal B200_ABI_VERSION of the header the library was built from
+ABI_VERSION = 11        # must equal B200_ABI_VERSION of the header the library was built from
 F16, BF16 = 0, 1
 SAMPLER_LDM_DDIM, SAMPLER_LDM_DDPM, SAMPLER_GD_DDIM, SAMPLER_GD_DDPM, SAMPLER_DPMPP_2M = 0, 1, 2, 3, 4
 SAMPLER_NCOEF = 16
@@ -35,7 +35,8 @@ class ConvDesc(C.Structure):
                 ("residual", C.c_void_p), ("res_scale", C.c_float), ("out", C.c_void_p),
                 ("gn_sums", C.c_void_p), ("act_dtype", C.c_int), ("out_nchw_f32", C.c_void_p), ("cout_real", C.c_int), ("rowscale", C.c_void_p), ("rowscale_stride", C.c_int), ("epi_act", C.c_int), ("out_nhwc_f32", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("range_events", C.c_void_p),
-                ("wsets", C.c_int), ("rowbias_gstride", C.c_int), ("rowscale_gstride", C.c_int)]
+                ("wsets", C.c_int), ("rowbias_gstride", C.c_int), ("rowscale_gstride", C.c_int),
+                ("force_ksplit", C.c_int)]
 
 
 class SamplerDesc(C.Structure):
@@ -52,7 +53,7 @@ class AttnDesc(C.Structure):
                 ("ldq", C.c_int), ("ldk", C.c_int), ("ldv", C.c_int), ("ldo", C.c_int),
                 ("q_off", C.c_int), ("k_off", C.c_int), ("v_off", C.c_int),
                 ("q_hstride", C.c_int), ("k_hstride", C.c_int), ("v_hstride", C.c_int),
-                ("scale", C.c_float), ("act_dtype", C.c_int), ("force_simt", C.c_int)]
+                ("scale", C.c_float), ("act_dtype", C.c_int), ("force_simt", C.c_int), ("lse", C.c_void_p)]
 
 
 _P, _I, _F, _L = C.c_void_p, C.c_int, C.c_float, C.c_int64
@@ -97,6 +98,21 @@ SIGNATURES = {
     "b200_abs_quantile": [_P, _I, _L, _F, _F, _P, _P],
     "b200_lincomb2": [_P, _P, _P, _P, _P, _I, _L, _I, _P],
     "b200_advance_step": [_P, _I, _P],
+    # training step (csrc/train.cu)
+    "b200_transpose16": [_P, _P, _L, _I, _P],
+    "b200_colsum16": [_P, _P, _L, _I, _I, _P],
+    "b200_gelu_fwd": [_P, _P, _L, _I, _P],
+    "b200_gelu_bwd": [_P, _P, _P, _L, _I, _P],
+    "b200_gated_residual": [_P, _P, _P, _I, _P, _L, _I, _I, _I, _P],
+    "b200_gate_bwd": [_P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P],
+    "b200_ln_mod_bwd": [_P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P],
+    "b200_attention_bwd": [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P],
+    "b200_unpatchify_bwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "b200_q_sample": [_P, _P, _P, _P, _I, _I, _P],
+    "b200_diffusion_loss": [_P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _P],
+    "b200_linear_f32_wgrad": [_P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P],
+    "b200_linear_f32_dgrad": [_P, _I, _P, _P, _P, _I, _I, _I, _P],
+    "b200_adamw": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
 }
 _RESTYPE = {"b200_last_error": C.c_char_p, "b200_launch_count": C.c_uint64}
 

@@ -72,6 +72,7 @@ struct FaParams {
   int pbufs;                          // P buffers in shared memory (2, or 1 to fit two CTAs per SM at D = 64)
   float scale_log2e;
   void *out;
+  float *lse;                         // optional [B, heads, Lq]: log-sum-exp of the scaled scores (training)
   uint32_t idesc_s, idesc_o;
 };
 
@@ -307,6 +308,8 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     tc_fence_after();
     const float inv = 1.f / l;
     const int qi = q0 + row;
+    if (p.lse && half == 0 && qi < p.Lq)      // P = exp2((S - M) scale log2e) -> lse = M scale + ln(l)   (natural-log units)
+      p.lse[((size_t)b * p.heads + h) * p.Lq + qi] = M * p.scale_log2e * 0.6931471805599453f + logf(l);
     T *o = reinterpret_cast<T *>(p.out) + ((size_t)b * p.Lq + qi) * p.ldo + h * D;
 #pragma unroll
     for (int c0 = 0; c0 < kHalfD; c0 += 8) {
@@ -333,6 +336,7 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
 struct AttnArgs {
   const void *q, *k, *v;
   void *out;
+  float *lse;
   int B, Lq, Lk, heads, d;
   int ldq, ldk, ldv, ldo;
   int q_off, k_off, v_off, q_hstride, k_hstride, v_hstride;
@@ -359,6 +363,7 @@ static int launch_flash(const AttnArgs &a, cudaStream_t st) {
   p.q_hstride = a.q_hstride; p.k_hstride = a.k_hstride; p.v_hstride = a.v_hstride;
   p.ldo = a.ldo;
   p.out = a.out;
+  p.lse = a.lse;
   p.scale_log2e = a.scale * 1.4426950408889634f;
   p.idesc_s = umma_idesc(Act<T>::kFmt, kFaBM, kFaBN, 0);
   p.idesc_o = umma_idesc(Act<T>::kFmt, kFaBM, D, 1);
@@ -518,6 +523,8 @@ extern "C" int b200_attention(const b200_attn_desc *d, void *stream) {
              "attention: unaligned pointer");
   AttnArgs a;
   a.q = d->q; a.k = d->k; a.v = d->v; a.out = d->out;
+  a.lse = d->lse;
+  B200_CHECK(d->lse == nullptr || (d->d % 16 == 0 && !d->force_simt), "attention: lse needs the tcgen05 kernel (d %% 16 == 0)");
   a.B = d->B; a.Lq = d->Lq; a.Lk = d->Lk; a.heads = d->heads; a.d = d->d;
   a.ldq = d->ldq; a.ldk = d->ldk; a.ldv = d->ldv; a.ldo = d->ldo;
   a.q_off = d->q_off; a.k_off = d->k_off; a.v_off = d->v_off;
@@ -547,5 +554,6 @@ extern "C" int b200_attention_qkv(const void *qkv, void *out, int B, int L, int 
   d.scale = scale;
   d.act_dtype = act_dtype;
   d.force_simt = 0;
+  d.lse = nullptr;
   return b200_attention(&d, stream);
 }

@@ -784,6 +784,7 @@ static int conv_groups_total(const b200_conv_desc *d) {
 }
 
 static int conv_ksplit(const b200_conv_desc *d) {
+  if (d->force_ksplit > 1) return std::max(1, std::min(d->force_ksplit, std::min(64, conv_groups_total(d))));
   static const bool off = getenv("B200DIFF_CONV_NO_SPLITK") != nullptr;
   if (off || d->out == nullptr || d->out_nchw_f32 || d->out_nhwc_f32 || d->epi_act || d->rowscale) return 1;
   // measured inside a CUDA graph (tools/graph_probe.py): 8x8 3x3 960->960 48.6 -> 33.4 us with S = 9, but 1x1 layers
@@ -862,6 +863,19 @@ splitk_finalize_kernel(const float *__restrict__ ws, int S, long long split_stri
     __syncthreads();
   }
   if (IsHalf<T>::value && range_events && amax >= kHalfOverflow) atomicAdd(range_events, 1u);
+}
+
+// forced split-K with an fp32 result (weight gradients): out[i] = sum_k ws[k][i], fixed order
+__global__ void __launch_bounds__(256)
+splitk_reduce_f32_kernel(const float *__restrict__ ws, int S, long long split_stride, float *__restrict__ out, long long n4) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = *reinterpret_cast<const float4 *>(ws + i * 4);
+    for (int k = 1; k < S; ++k) {
+      const float4 b = *reinterpret_cast<const float4 *>(ws + (size_t)k * split_stride + i * 4);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    *reinterpret_cast<float4 *>(out + i * 4) = a;
+  }
 }
 
 template <typename T, int kCtas, bool kFast>
@@ -963,6 +977,13 @@ static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t
   cfg.numAttrs = pdl ? 2 : 1;
   B200_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<T, kCtas, kFast>, maps, p));
   B200_LAUNCH_CHECK();
+  if (ksplit > 1 && d->out_nhwc_f32) {
+    const long long n4 = p.split_stride / 4;
+    const int blocks = (int)std::min<long long>((n4 + 255) / 256, (long long)num_sms() * 8);
+    splitk_reduce_f32_kernel<<<blocks, 256, 0, stream>>>(p.out_f32_nhwc, ksplit, p.split_stride, d->out_nhwc_f32, n4);
+    B200_LAUNCH_CHECK();
+    return 0;
+  }
   if (ksplit > 1) {
     const int HW = d->Hout * d->Wout;
     const int cpp = std::min(d->Cout >> 3, 256), rows = 256 / cpp;
@@ -999,6 +1020,9 @@ extern "C" int b200_conv2d_igemm(const b200_conv_desc *d, void *stream) {
   int ctas, bn;
   choose_tiling(d, &ctas, &bn);
   int ksplit = conv_ksplit(d);
+  B200_CHECK(d->force_ksplit <= 1 || (d->out_nhwc_f32 && !d->bias && !d->rowbias && !d->residual && !d->rowscale &&
+                                      !d->epi_act && !d->gn_sums && std::max(1, d->wsets) == 1),
+             "conv: force_ksplit is for plain fp32-output GEMMs (no epilogue terms)");
   if (ksplit > 1) {
     const size_t need = (size_t)ksplit * d->N * d->Hout * d->Wout * d->Cout * sizeof(float);
     B200_CHECK(d->workspace != nullptr && d->workspace_bytes >= need && ((uintptr_t)d->workspace & 15) == 0,

@@ -1,0 +1,937 @@
+// Training-step kernels for the DiT diffusion model (BASELINE config 5): everything of one
+// forward + backward + AdamW step that is NOT a GEMM.  The GEMMs — forward linears, dgrad (transposed packed weights) and
+// wgrad (token-major operands transposed to K-major, fp32 split-K result) — run on conv_igemm_kernel (igemm_conv.cu).
+//
+// Reference arithmetic restated here (all citations relative to the reference root):
+//   * training objective  training_project/utils/gaussian_diffusion.py:824-983 (MSE / RESCALED_MSE branch): Charbonnier
+//     "mse" term (:20-30, :972) + learned-range variational bound on the variance channels (:791-822, :247-351;
+//     training_project/utils/diffusion_utils.py:10-84), q_sample :199-215, get_v :376-380;
+//   * DiTBlock / FinalLayer backward   UNet_DS_Diff/DiT_models.py:101-142 (adaLN-Zero: x + gate * f(modulate(LN(x))));
+//   * timm Attention / Mlp backward    (softmax(q k^T / sqrt(d)) v, GELU(tanh));
+//   * AdamW                            torch.optim.AdamW as configured by the trainers
+//                                      (trainers/trainer_use_gaussian_diff.py: configure_optimizers).
+// HBM-bound kernels: 16-byte vector accesses, warp-shuffle row reductions, fp32 atomics for the per-sample column sums.
+#include <mma.h>
+
+#include "common.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------------------------
+// 16-bit transpose [R, C] -> [C, R]  (wgrad operands: token-major activations / gradients become K-major rows)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+transpose16_kernel(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int R, int C) {
+  __shared__ uint16_t tile[64][64 + 2];
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;      // 64 x 4
+  for (int i = ty; i < 64; i += 4) {
+    const int r = r0 + i, c = c0 + tx;
+    tile[i][tx] = (r < R && c < C) ? src[(size_t)r * C + c] : (uint16_t)0;
+  }
+  __syncthreads();
+  for (int i = ty; i < 64; i += 4) {
+    const int c = c0 + i, r = r0 + tx;
+    if (c < C && r < R) dst[(size_t)c * R + r] = tile[tx][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// bias gradient: out[c] += sum_r x[r, c]   (fp32 atomics; zero `out` first)
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum16_kernel(const T *__restrict__ x, float *__restrict__ out, int64_t R, int C, int rows_per_block) {
+  const int ncol = C >> 3;
+  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t r_end = min(R, r_begin + rows_per_block);
+  for (int col = threadIdx.x; col < ncol; col += blockDim.x) {
+    float s[8] = {0};
+    for (int64_t r = r_begin; r < r_end; ++r) {
+      float f[8];
+      unpack8<T>(ld_stream(x + r * C + col * 8), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += f[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(out + col * 8 + i, s[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// GELU(tanh) backward: dpre = du * gelu'(pre);  gelu(x) = x * s, s = sigmoid(2u), u = k (x + c x^3)
+//   gelu'(x) = s + x * s (1 - s) * 2k (1 + 3 c x^2)
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+  const float k = 0.7978845608028654f, c = 0.044715f;
+  const float u2 = 2.f * k * (x + c * x * x * x);
+  const float s = 1.f / (1.f + __expf(-u2));
+  return s + x * s * (1.f - s) * 2.f * k * (1.f + 3.f * c * x * x);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gelu_bwd_kernel(const T *__restrict__ pre, const T *__restrict__ du, T *__restrict__ dpre, int64_t nvec) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float p[8], g[8];
+    unpack8<T>(ld_stream(pre + i * 8), p);
+    unpack8<T>(ld_stream(du + i * 8), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= gelu_tanh_grad(p[j]);
+    st_stream(dpre + i * 8, pack8<T>(g));
+  }
+}
+
+// GELU(tanh) forward on a stored pre-activation (training keeps both: the fused-epilogue GELU of the sampling path stores
+// only the activated value)
+template <typename T>
+__global__ void __launch_bounds__(256)
+gelu_fwd_kernel(const T *__restrict__ pre, T *__restrict__ out, int64_t nvec) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float p[8];
+    unpack8<T>(ld_stream(pre + i * 8), p);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p[j] = gelu_tanh_f(p[j]);
+    st_stream(out + i * 8, pack8<T>(p));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// gated residual (adaLN-Zero):  h_out = h_in + gate[n] * f           (DiT_models.py:120-121)
+// and its backward:            df = gate[n] * dh ; dgate[n, c] += sum_t dh * f
+// One warp walks `rows_per_warp` consecutive token rows of ONE sample; lane l owns the 8-channel vectors l, l+32, ...
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kMaxVec = 6;      // up to 6 * 32 * 8 = 1536 channels (NV = vectors per lane is a template parameter)
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gated_residual_kernel(const T *__restrict__ h_in, const T *__restrict__ f, const float *__restrict__ gate, int gate_stride,
+                      T *__restrict__ h_out, int64_t rows, int L, int C) {
+  const int nvec = C >> 3;
+  const int64_t total = rows * nvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / nvec;
+    const int v = (int)(i - r * nvec);
+    const int n = (int)(r / L);
+    float a[8], b[8];
+    unpack8<T>(ld_stream(h_in + r * C + v * 8), a);
+    unpack8<T>(ld_stream(f + r * C + v * 8), b);
+    const float4 g0 = *reinterpret_cast<const float4 *>(gate + (size_t)n * gate_stride + v * 8);
+    const float4 g1 = *reinterpret_cast<const float4 *>(gate + (size_t)n * gate_stride + v * 8 + 4);
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = fmaf(g[j], b[j], a[j]);
+    st_stream(h_out + r * C + v * 8, pack8<T>(a));
+  }
+}
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(256)
+gate_bwd_kernel(const T *__restrict__ dh, const T *__restrict__ f, const float *__restrict__ gate, int gate_stride,
+                T *__restrict__ df, float *__restrict__ dgate, int dgate_stride, int N, int L, int C, int rows_per_warp) {
+  constexpr int kMaxVec = NV;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int warps_per_sample = (L + rows_per_warp - 1) / rows_per_warp;
+  const int n = warp / warps_per_sample;
+  if (n >= N) return;
+  const int t0 = (warp - n * warps_per_sample) * rows_per_warp;
+  const int t1 = min(L, t0 + rows_per_warp);
+  const int nvec = C >> 3;
+  float acc[kMaxVec][8];
+  float g[kMaxVec][8];
+#pragma unroll
+  for (int k = 0; k < kMaxVec; ++k) {
+    const int v = lane + 32 * k;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[k][j] = 0.f; g[k][j] = (v < nvec) ? gate[(size_t)n * gate_stride + v * 8 + j] : 0.f; }
+  }
+  for (int t = t0; t < t1; ++t) {
+    const size_t row = ((size_t)n * L + t) * C;
+#pragma unroll
+    for (int k = 0; k < kMaxVec; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nvec) {
+        float d[8], ff[8];
+        unpack8<T>(ld_stream(dh + row + v * 8), d);
+        unpack8<T>(ld_stream(f + row + v * 8), ff);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[k][j] = fmaf(d[j], ff[j], acc[k][j]); d[j] *= g[k][j]; }
+        st_stream(df + row + v * 8, pack8<T>(d));
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kMaxVec; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nvec && t1 > t0)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(dgate + (size_t)n * dgate_stride + v * 8 + j, acc[k][j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm (no affine, eps) + adaLN modulate backward:   a = LN(x) * (1 + scale[n]) + shift[n]
+//   nhat = (x - mean) * rstd ; g = da * (1 + scale)
+//   dx   = rstd * (g - mean_c(g) - nhat * mean_c(g * nhat))  (+ dres: the gradient arriving on the residual branch)
+//   dshift[n, c] += sum_t da ; dscale[n, c] += sum_t da * nhat
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T, int NV>
+__global__ void __launch_bounds__(256)
+ln_mod_bwd_kernel(const T *__restrict__ x, const T *__restrict__ da, const float *__restrict__ scale, int mod_stride,
+                  const T *__restrict__ dres, T *__restrict__ dx, float *__restrict__ dshift, float *__restrict__ dscale,
+                  int dmod_stride, int N, int L, int C, float eps, int rows_per_warp) {
+  constexpr int kMaxVec = NV;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int warps_per_sample = (L + rows_per_warp - 1) / rows_per_warp;
+  const int n = warp / warps_per_sample;
+  if (n >= N) return;
+  const int t0 = (warp - n * warps_per_sample) * rows_per_warp;
+  const int t1 = min(L, t0 + rows_per_warp);
+  const int nvec = C >> 3;
+  const float invC = 1.f / (float)C;
+  float sc1[kMaxVec][8], a_sh[kMaxVec][8], a_sc[kMaxVec][8];
+#pragma unroll
+  for (int k = 0; k < kMaxVec; ++k) {
+    const int v = lane + 32 * k;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc1[k][j] = (v < nvec) ? 1.f + scale[(size_t)n * mod_stride + v * 8 + j] : 0.f;
+      a_sh[k][j] = 0.f; a_sc[k][j] = 0.f;
+    }
+  }
+  for (int t = t0; t < t1; ++t) {
+    const size_t row = ((size_t)n * L + t) * C;
+    float xv[kMaxVec][8], gv[kMaxVec][8];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxVec; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nvec) {
+        unpack8<T>(ld_stream(x + row + v * 8), xv[k]);
+        unpack8<T>(ld_stream(da + row + v * 8), gv[k]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += xv[k][j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { xv[k][j] = 0.f; gv[k][j] = 0.f; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxVec; ++k)
+      if (lane + 32 * k < nvec)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = xv[k][j] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * invC + eps);
+    float sg = 0.f, sgn = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxVec; ++k)
+      if (lane + 32 * k < nvec)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float nh = (xv[k][j] - mean) * rstd;
+          const float d = gv[k][j];
+          a_sh[k][j] += d;
+          a_sc[k][j] = fmaf(d, nh, a_sc[k][j]);
+          const float g = d * sc1[k][j];
+          xv[k][j] = nh;            // keep nhat
+          gv[k][j] = g;             // keep g
+          sg += g;
+          sgn = fmaf(g, nh, sgn);
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      sgn += __shfl_xor_sync(0xffffffffu, sgn, o);
+    }
+    const float mg = sg * invC, mgn = sgn * invC;
+#pragma unroll
+    for (int k = 0; k < kMaxVec; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nvec) {
+        float o8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o8[j] = rstd * (gv[k][j] - mg - xv[k][j] * mgn);
+        if (dres) {
+          float r8[8];
+          unpack8<T>(ld_stream(dres + row + v * 8), r8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o8[j] += r8[j];
+        }
+        st_stream(dx + row + v * 8, pack8<T>(o8));
+      }
+    }
+  }
+  if (t1 > t0) {
+#pragma unroll
+    for (int k = 0; k < kMaxVec; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nvec)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          atomicAdd(dshift + (size_t)n * dmod_stride + v * 8 + j, a_sh[k][j]);
+          atomicAdd(dscale + (size_t)n * dmod_stride + v * 8 + j, a_sc[k][j]);
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// attention backward (timm Attention as DiT uses it): S = scale q k^T, P = softmax(S), O = P v
+//   D_i = sum_c dO[i, c] O[i, c] ;  dP = dO v^T ;  dS = P (dP - D) ;  dq = scale dS k ; dk = scale dS^T q ; dv = P^T dO
+// One CTA = (64-key tile, head, batch); it walks the 64-query tiles, keeps dK / dV of its keys in registers and adds its
+// dQ contributions to an fp32 buffer with atomics.  Tensor cores through mma.sync (wmma) fragments: first correct
+// version of the backward — the tcgen05 port of this loop (S, dP, dV, dK, dQ accumulators in TMEM like the forward kernel)
+// is the next step named in DESIGN.md.
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+attn_bwd_prep_kernel(const T *__restrict__ o, const T *__restrict__ dout, float *__restrict__ dsum, int64_t rows, int heads,
+                     int D) {
+  // one thread per (row, head)
+  const int64_t total = rows * heads;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / heads;
+    const int h = (int)(i - r * heads);
+    const T *po = o + r * (int64_t)heads * D + h * D;
+    const T *pd = dout + r * (int64_t)heads * D + h * D;
+    float s = 0.f;
+    for (int c = 0; c < D; c += 8) {
+      float a[8], b[8];
+      unpack8<T>(*reinterpret_cast<const uint4 *>(po + c), a);
+      unpack8<T>(*reinterpret_cast<const uint4 *>(pd + c), b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s = fmaf(a[j], b[j], s);
+    }
+    dsum[i] = s;      // [B, L, heads]
+  }
+}
+
+template <typename T> struct WmmaT;
+template <> struct WmmaT<__half> { using type = __half; };
+template <> struct WmmaT<__nv_bfloat16> { using type = __nv_bfloat16; };
+
+template <typename T, int D>
+__global__ void __launch_bounds__(128)
+attn_bwd_kernel(const T *__restrict__ qkv, int ld, int q_off, int k_off, int v_off, const T *__restrict__ dout,
+                const float *__restrict__ lse, const float *__restrict__ dsum, float *__restrict__ dq_f32,
+                T *__restrict__ dqkv, int L, int heads, float scale) {
+  using namespace nvcuda;
+  using WT = typename WmmaT<T>::type;
+  constexpr int BT = 64;                       // keys per CTA, queries per inner tile
+  constexpr int LDT = D + 8;                   // padded 16-bit tile pitch
+  constexpr int LDS = BT + 8;                  // padded pitch of the 64 x 64 tiles
+  extern __shared__ __align__(128) uint8_t smem[];
+  T *sK = reinterpret_cast<T *>(smem);                    // [64][LDT]
+  T *sV = sK + BT * LDT;
+  T *sQ = sV + BT * LDT;
+  T *sdO = sQ + BT * LDT;
+  T *sP = sdO + BT * LDT;                                 // [64 q][LDS]
+  T *sdS = sP + BT * LDS;
+  float *sS = reinterpret_cast<float *>(sdS + BT * LDS);  // [64][LDS] fp32 scratch (S, then dQ)
+  float *sdP = sS + BT * LDS;                             // [64][LDS] fp32 (dP), later the dK / dV staging
+  float *sL = sdP + BT * LDS;                             // lse[64], dsum[64]
+  float *sD = sL + BT;
+
+  const int j0 = blockIdx.x * BT, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const T *base = qkv + (size_t)b * L * ld;
+  const T *dob = dout + (size_t)b * L * heads * D + h * D;
+  const int ldo = heads * D;
+
+  // K_j, V_j tiles (rows past L zero-filled)
+  for (int i = tid; i < BT * (D / 8); i += 128) {
+    const int r = i / (D / 8), c = (i - r * (D / 8)) * 8;
+    uint4 k4 = make_uint4(0, 0, 0, 0), v4 = k4;
+    if (j0 + r < L) {
+      k4 = *reinterpret_cast<const uint4 *>(base + (size_t)(j0 + r) * ld + k_off + h * D + c);
+      v4 = *reinterpret_cast<const uint4 *>(base + (size_t)(j0 + r) * ld + v_off + h * D + c);
+    }
+    *reinterpret_cast<uint4 *>(sK + r * LDT + c) = k4;
+    *reinterpret_cast<uint4 *>(sV + r * LDT + c) = v4;
+  }
+  // this warp's 16 keys x D accumulators
+  wmma::fragment<wmma::accumulator, 16, 16, 16, float> dK[D / 16], dV[D / 16];
+#pragma unroll
+  for (int c = 0; c < D / 16; ++c) { wmma::fill_fragment(dK[c], 0.f); wmma::fill_fragment(dV[c], 0.f); }
+
+  for (int i0 = 0; i0 < L; i0 += BT) {
+    __syncthreads();
+    for (int i = tid; i < BT * (D / 8); i += 128) {
+      const int r = i / (D / 8), c = (i - r * (D / 8)) * 8;
+      uint4 q4 = make_uint4(0, 0, 0, 0), d4 = q4;
+      if (i0 + r < L) {
+        q4 = *reinterpret_cast<const uint4 *>(base + (size_t)(i0 + r) * ld + q_off + h * D + c);
+        d4 = *reinterpret_cast<const uint4 *>(dob + (size_t)(i0 + r) * ldo + c);
+      }
+      *reinterpret_cast<uint4 *>(sQ + r * LDT + c) = q4;
+      *reinterpret_cast<uint4 *>(sdO + r * LDT + c) = d4;
+    }
+    if (tid < BT) {
+      const int qi = i0 + tid;
+      sL[tid] = qi < L ? lse[((size_t)b * heads + h) * L + qi] : 0.f;
+      sD[tid] = qi < L ? dsum[((size_t)b * L + qi) * heads + h] : 0.f;
+    }
+    __syncthreads();
+    // S = Q K^T and dP = dO V^T: this warp's 16 query rows x 64 keys
+    {
+      wmma::fragment<wmma::accumulator, 16, 16, 16, float> s[4], dp[4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) { wmma::fill_fragment(s[n], 0.f); wmma::fill_fragment(dp[n], 0.f); }
+#pragma unroll
+      for (int kk = 0; kk < D; kk += 16) {
+        wmma::fragment<wmma::matrix_a, 16, 16, 16, WT, wmma::row_major> aq, ad;
+        wmma::load_matrix_sync(aq, reinterpret_cast<const WT *>(sQ + warp * 16 * LDT + kk), LDT);
+        wmma::load_matrix_sync(ad, reinterpret_cast<const WT *>(sdO + warp * 16 * LDT + kk), LDT);
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          wmma::fragment<wmma::matrix_b, 16, 16, 16, WT, wmma::col_major> bk, bv;     // (k = channel, n = key) = K[key][ch]
+          wmma::load_matrix_sync(bk, reinterpret_cast<const WT *>(sK + n * 16 * LDT + kk), LDT);
+          wmma::load_matrix_sync(bv, reinterpret_cast<const WT *>(sV + n * 16 * LDT + kk), LDT);
+          wmma::mma_sync(s[n], aq, bk, s[n]);
+          wmma::mma_sync(dp[n], ad, bv, dp[n]);
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        wmma::store_matrix_sync(sS + warp * 16 * LDS + n * 16, s[n], LDS, wmma::mem_row_major);
+        wmma::store_matrix_sync(sdP + warp * 16 * LDS + n * 16, dp[n], LDS, wmma::mem_row_major);
+      }
+    }
+    __syncthreads();
+    // P = exp(scale S - lse), dS = P (dP - D) scale  (16-bit copies for the next three products)
+    for (int i = tid; i < BT * BT; i += 128) {
+      const int r = i >> 6, c = i & 63;
+      float pv = 0.f, ds = 0.f;
+      if (i0 + r < L && j0 + c < L) {
+        pv = __expf(fmaf(sS[r * LDS + c], scale, -sL[r]));
+        ds = pv * (sdP[r * LDS + c] - sD[r]) * scale;
+      }
+      sP[r * LDS + c] = Act<T>::from_f(pv);
+      sdS[r * LDS + c] = Act<T>::from_f(ds);
+    }
+    __syncthreads();
+    // dV += P^T dO ; dK += dS^T Q : this warp's 16 keys (rows of the transposed tiles) x D, K = 64 queries
+#pragma unroll
+    for (int kk = 0; kk < BT; kk += 16) {
+      wmma::fragment<wmma::matrix_a, 16, 16, 16, WT, wmma::col_major> ap, as;       // (m = key, k = query) = P[query][key]
+      wmma::load_matrix_sync(ap, reinterpret_cast<const WT *>(sP + kk * LDS + warp * 16), LDS);
+      wmma::load_matrix_sync(as, reinterpret_cast<const WT *>(sdS + kk * LDS + warp * 16), LDS);
+#pragma unroll
+      for (int c = 0; c < D / 16; ++c) {
+        wmma::fragment<wmma::matrix_b, 16, 16, 16, WT, wmma::row_major> bd, bq;     // (k = query, n = channel)
+        wmma::load_matrix_sync(bd, reinterpret_cast<const WT *>(sdO + kk * LDT + c * 16), LDT);
+        wmma::load_matrix_sync(bq, reinterpret_cast<const WT *>(sQ + kk * LDT + c * 16), LDT);
+        wmma::mma_sync(dV[c], ap, bd, dV[c]);
+        wmma::mma_sync(dK[c], as, bq, dK[c]);
+      }
+    }
+    // dQ_i += dS K_j : this warp's 16 queries x D, K = 64 keys -> fp32 staging -> global atomics
+    {
+      wmma::fragment<wmma::accumulator, 16, 16, 16, float> dq[D / 16];
+#pragma unroll
+      for (int c = 0; c < D / 16; ++c) wmma::fill_fragment(dq[c], 0.f);
+#pragma unroll
+      for (int kk = 0; kk < BT; kk += 16) {
+        wmma::fragment<wmma::matrix_a, 16, 16, 16, WT, wmma::row_major> as;
+        wmma::load_matrix_sync(as, reinterpret_cast<const WT *>(sdS + warp * 16 * LDS + kk), LDS);
+#pragma unroll
+        for (int c = 0; c < D / 16; ++c) {
+          wmma::fragment<wmma::matrix_b, 16, 16, 16, WT, wmma::row_major> bk;       // (k = key, n = channel)
+          wmma::load_matrix_sync(bk, reinterpret_cast<const WT *>(sK + kk * LDT + c * 16), LDT);
+          wmma::mma_sync(dq[c], as, bk, dq[c]);
+        }
+      }
+      __syncwarp();
+      // sS rows [16 warp .. +16) are this warp's own: reuse them as the staging area (D <= 64 columns)
+#pragma unroll
+      for (int c = 0; c < D / 16; ++c)
+        wmma::store_matrix_sync(sS + warp * 16 * LDS + c * 16, dq[c], LDS, wmma::mem_row_major);
+      __syncwarp();
+      for (int i = lane; i < 16 * D; i += 32) {
+        const int r = i / D, c = i - r * D;
+        const int qi = i0 + warp * 16 + r;
+        if (qi < L) atomicAdd(dq_f32 + ((size_t)b * L + qi) * ldo + h * D + c, sS[(warp * 16 + r) * LDS + c]);
+      }
+    }
+  }
+  __syncthreads();
+  // dK, dV of this CTA's keys -> dqkv (16-bit), through the fp32 scratch
+#pragma unroll
+  for (int c = 0; c < D / 16; ++c) {
+    wmma::store_matrix_sync(sS + warp * 16 * LDS + c * 16, dK[c], LDS, wmma::mem_row_major);
+    wmma::store_matrix_sync(sdP + warp * 16 * LDS + c * 16, dV[c], LDS, wmma::mem_row_major);
+  }
+  __syncthreads();
+  T *ob = dqkv + (size_t)b * L * ld;
+  for (int i = tid; i < BT * (D / 8); i += 128) {
+    const int r = i / (D / 8), c = (i - r * (D / 8)) * 8;
+    if (j0 + r < L) {
+      float a[8], v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] = sS[r * LDS + c + j]; v[j] = sdP[r * LDS + c + j]; }
+      *reinterpret_cast<uint4 *>(ob + (size_t)(j0 + r) * ld + k_off + h * D + c) = pack8<T>(a);
+      *reinterpret_cast<uint4 *>(ob + (size_t)(j0 + r) * ld + v_off + h * D + c) = pack8<T>(v);
+    }
+  }
+}
+
+// fp32 [rows, C] -> 16-bit with a destination pitch / offset (dq into the q section of dqkv)
+template <typename T>
+__global__ void __launch_bounds__(256)
+f32_to_act_strided_kernel(const float *__restrict__ src, T *__restrict__ dst, int64_t rows, int C, int ld_dst, int off) {
+  const int nvec = C >> 3;
+  const int64_t total = rows * nvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / nvec;
+    const int v = (int)(i - r * nvec);
+    const float4 a = *reinterpret_cast<const float4 *>(src + r * C + v * 8);
+    const float4 b = *reinterpret_cast<const float4 *>(src + r * C + v * 8 + 4);
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    *reinterpret_cast<uint4 *>(dst + r * ld_dst + off + v * 8) = pack8<T>(f);
+  }
+}
+
+// backward of DiT.unpatchify (DiT_models.py:220-232): image gradient [N, Cout, gh*p, gw*p] fp32 -> token gradient
+// [N, gh*gw, ld] 16-bit with feature index (ph*p + pw)*Cout + c, columns >= p*p*Cout zero (the padded N tile of the head)
+template <typename T>
+__global__ void __launch_bounds__(256)
+unpatchify_bwd_kernel(const float *__restrict__ dimg, T *__restrict__ dtok, int Cout, int gh, int gw, int p, int ld,
+                      long long total) {
+  const int H = gh * p, W = gw * p, K = p * p * Cout;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % ld);
+    long long r = i / ld;
+    const int tw = (int)(r % gw); r /= gw;
+    const int th = (int)(r % gh);
+    const long long n = r / gh;
+    float v = 0.f;
+    if (k < K) {
+      const int c = k % Cout, pq = k / Cout, pw = pq % p, ph = pq / p;
+      v = dimg[((n * Cout + c) * H + th * p + ph) * W + tw * p + pw];
+    }
+    dtok[i] = Act<T>::from_f(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// training objective + its gradient w.r.t. the network output (gaussian_diffusion.py:824-983, MSE / RESCALED_MSE)
+//   model_out [N, C or 2C, H, W] fp32 ; x_start, x_t, noise [N, C, H, W] fp32 ; coef [N][8] fp32 per-sample table rows:
+//   0 sqrt_ac  1 sqrt_1m_ac  2 post_mean_coef1  3 post_mean_coef2  4 post_logvar_clipped  5 log(beta)  6 t == 0  7 vb weight
+//   (also 8 sqrt_recip_ac, 9 sqrt_recipm1_ac for the eps parameterisation: pitch 12)
+//   terms [N][2] += (sum of the Charbonnier elements, sum of the vb elements in nats) ; d_out = d(mean_n(mse_n + vb_n)) / d out
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float approx_cdf(float x, float *dcdf) {
+  const float k = 0.7978845608028654f, c = 0.044715f;
+  const float u = k * (x + c * x * x * x);
+  const float th = tanhf(u);
+  *dcdf = 0.5f * (1.f - th * th) * k * (1.f + 3.f * c * x * x);
+  return 0.5f * (1.f + th);
+}
+
+__global__ void __launch_bounds__(256)
+diffusion_loss_kernel(const float *__restrict__ out, const float *__restrict__ x_start, const float *__restrict__ x_t,
+                      const float *__restrict__ noise, const float *__restrict__ coef, int param, int learn_sigma,
+                      float *__restrict__ terms, float *__restrict__ d_out, int N, int C, int HW, float charb_eps) {
+  const int n = blockIdx.y;
+  const float *cf = coef + n * 12;
+  const float sa = cf[0], s1 = cf[1], c1 = cf[2], c2 = cf[3], min_log = cf[4], max_log = cf[5];
+  const bool t0 = cf[6] != 0.f;
+  const float vbw = cf[7];
+  const int per = C * HW;
+  const float inv = 1.f / ((float)per * (float)N);            // mean_flat then the batch mean
+  const float inv_ln2 = 1.4426950408889634f;
+  const int oc = learn_sigma ? 2 * C : C;
+  float mse_acc = 0.f, vb_acc = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per; i += gridDim.x * blockDim.x) {
+    const int c = i / HW, p = i - c * HW;
+    const size_t xi = (size_t)n * per + i;
+    const size_t oi = ((size_t)n * oc + c) * HW + p;
+    const float x0 = x_start[xi], xt = x_t[xi], nz = noise[xi];
+    const float m = out[oi];
+    const float target = param == 0 ? nz : (param == 1 ? x0 : sa * nz - s1 * x0);      // eps / x0 / v (:376-380)
+    const float diff = target - m;
+    const float ch = sqrtf(diff * diff + charb_eps);                                    // :20-30
+    mse_acc += ch;
+    d_out[oi] = -diff / ch * inv;
+    if (learn_sigma) {
+      const size_t si = oi + (size_t)C * HW;
+      const float s = out[si];
+      const float frac = 0.5f * (s + 1.f);
+      const float lv2 = frac * max_log + (1.f - frac) * min_log;                        // :297-305
+      float px0;
+      if (param == 2) px0 = sa * xt - s1 * m;                                           // :323-324 (v)
+      else if (param == 1) px0 = m;
+      else px0 = cf[8] * xt - cf[9] * m;
+      const float mean2 = c1 * px0 + c2 * xt;          // model mean (frozen: no gradient, :866)
+      const float mean1 = c1 * x0 + c2 * xt;           // true posterior mean
+      float term, dlv;
+      if (!t0) {                                        // normal_kl (diffusion_utils.py:10-37)
+        const float e1 = __expf(min_log - lv2), e2 = __expf(-lv2);
+        const float dm = mean1 - mean2;
+        term = 0.5f * (-1.f + lv2 - min_log + e1 + dm * dm * e2);
+        dlv = 0.5f * (1.f - e1 - dm * dm * e2);
+      } else {                                          // decoder NLL (diffusion_utils.py:48-84), log_scales = 0.5 lv2
+        const float ls = 0.5f * lv2;
+        const float istd = __expf(-ls);
+        const float cen = x0 - mean2;
+        const float zp = istd * (cen + 1.f / 255.f), zm = istd * (cen - 1.f / 255.f);
+        float dp, dmn;
+        const float cp = approx_cdf(zp, &dp), cm = approx_cdf(zm, &dmn);
+        // d z / d ls = -z
+        float ll, dll;
+        if (x0 < -0.999f) {
+          const float v = fmaxf(cp, 1e-12f);
+          ll = logf(v);
+          dll = cp > 1e-12f ? (dp * -zp) / v : 0.f;
+        } else if (x0 > 0.999f) {
+          const float v = fmaxf(1.f - cm, 1e-12f);
+          ll = logf(v);
+          dll = (1.f - cm) > 1e-12f ? (-dmn * -zm) / v : 0.f;
+        } else {
+          const float v = fmaxf(cp - cm, 1e-12f);
+          ll = logf(v);
+          dll = (cp - cm) > 1e-12f ? (dp * -zp - dmn * -zm) / v : 0.f;
+        }
+        term = -ll;
+        dlv = -dll * 0.5f;
+      }
+      vb_acc += term;
+      // vb_n = mean_flat(term) / ln 2 * vbw ; d lv2 / d s = (max_log - min_log) / 2
+      d_out[si] = dlv * 0.5f * (max_log - min_log) * inv_ln2 * vbw * inv;
+    }
+  }
+  // block reduction -> per-sample atomics
+  __shared__ float sm[2][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mse_acc += __shfl_xor_sync(0xffffffffu, mse_acc, o);
+    vb_acc += __shfl_xor_sync(0xffffffffu, vb_acc, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = mse_acc; sm[1][threadIdx.x >> 5] = vb_acc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < 8; ++w) { a += sm[0][w]; b += sm[1][w]; }
+    atomicAdd(terms + 2 * n, a / (float)per);
+    atomicAdd(terms + 2 * n + 1, b / (float)per * inv_ln2 * vbw);
+  }
+}
+
+// q_sample (:199-215): x_t = sqrt_ac[t] x0 + sqrt_1m_ac[t] noise, per-sample coefficients from the same table rows
+__global__ void __launch_bounds__(256)
+q_sample_kernel(const float *__restrict__ x0, const float *__restrict__ noise, const float *__restrict__ coef,
+                float *__restrict__ xt, int per, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i / per);
+    xt[i] = coef[n * 12] * x0[i] + coef[n * 12 + 1] * noise[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// small fp32 linears of the conditioning path (TimestepEmbedder MLP, all adaLN modulation projections): backward
+//   y[N, O] = xin[N, I] W[O, I]^T + b,  xin = silu(x) when in_silu
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float silu_grad(float x) {
+  const float s = 1.f / (1.f + __expf(-x));
+  return s * (1.f + x * (1.f - s));
+}
+
+// dW[o, i] (+)= sum_n dy[n, o] xin[n, i] ; db[o] (+)= sum_n dy[n, o]        (N <= 64 rows staged in shared memory)
+__global__ void __launch_bounds__(256)
+linear_f32_wgrad_kernel(const float *__restrict__ dy, int dy_stride, const float *__restrict__ x, int x_stride, int in_silu,
+                        float *__restrict__ dW, float *__restrict__ db, int N, int O, int I, int accumulate) {
+  __shared__ float sdy[64];
+  const int o = blockIdx.y;
+  if (threadIdx.x < N) sdy[threadIdx.x] = dy[(size_t)threadIdx.x * dy_stride + o];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < I) {
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n) {
+      float xv = x[(size_t)n * x_stride + i];
+      if (in_silu) xv = xv / (1.f + __expf(-xv));
+      acc = fmaf(sdy[n], xv, acc);
+    }
+    const size_t w = (size_t)o * I + i;
+    dW[w] = accumulate ? dW[w] + acc : acc;
+  }
+  if (db && blockIdx.x == 0 && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int n = 0; n < N; ++n) s += sdy[n];
+    db[o] = accumulate ? db[o] + s : s;
+  }
+}
+
+// dx[n, i] += sum_o dy[n, o] W[o, i]   (then * silu'(x) applied by the caller-side finish kernel)
+__global__ void __launch_bounds__(256)
+linear_f32_dgrad_kernel(const float *__restrict__ dy, int dy_stride, const float *__restrict__ W, float *__restrict__ dx,
+                        int N, int O, int I, int o_chunk) {
+  extern __shared__ float sdyc[];      // [o_chunk][N]
+  const int o0 = blockIdx.y * o_chunk;
+  const int oc = min(o_chunk, O - o0);
+  for (int k = threadIdx.x; k < oc * N; k += blockDim.x) {
+    const int oo = k / N, n = k - oo * N;
+    sdyc[k] = dy[(size_t)n * dy_stride + o0 + oo];
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= I) return;
+  float acc[64];
+#pragma unroll
+  for (int n = 0; n < 64; ++n) acc[n] = 0.f;
+  for (int oo = 0; oo < oc; ++oo) {
+    const float w = W[(size_t)(o0 + oo) * I + i];
+#pragma unroll
+    for (int n = 0; n < 64; ++n)
+      if (n < N) acc[n] = fmaf(sdyc[oo * N + n], w, acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < 64; ++n)
+    if (n < N) atomicAdd(dx + (size_t)n * I + i, acc[n]);
+}
+
+// dx[i] *= silu'(x[i])
+__global__ void __launch_bounds__(256) silu_bwd_f32_kernel(const float *__restrict__ x, float *__restrict__ dx, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dx[i] *= silu_grad(x[i]);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// fused AdamW over a flat fp32 parameter arena (decoupled weight decay, bias-corrected; torch.optim.AdamW semantics)
+//   p *= 1 - lr wd ; m = b1 m + (1 - b1) g ; v = b2 v + (1 - b2) g^2 ; p -= lr / bc1 * m / (sqrt(v) / sqrt(bc2) + eps)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, int64_t n,
+             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+  }
+}
+
+static int ew_blocks(int64_t n) { return (int)std::min<int64_t>(cdiv64(n, 256), (int64_t)num_sms() * 16); }
+
+}  // namespace b200
+
+using namespace b200;
+
+#define B200_ACT_DISPATCH(FN, ...)                                           \
+  do {                                                                       \
+    if (act_dtype == B200_F16) { FN(__half, __VA_ARGS__); }                  \
+    else if (act_dtype == B200_BF16) { FN(__nv_bfloat16, __VA_ARGS__); }     \
+    else B200_CHECK(false, "bad act_dtype %d", act_dtype);                   \
+  } while (0)
+
+extern "C" int b200_transpose16(const void *src, void *dst, int64_t R, int C, void *stream) {
+  B200_CHECK(src && dst && R > 0 && C > 0 && R < (1ll << 31), "transpose16: bad arguments");
+  dim3 grid(cdiv(C, 64), (unsigned)cdiv64(R, 64));
+  transpose16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t *)src, (uint16_t *)dst, (int)R, C);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_colsum16(const void *x, float *out, int64_t R, int C, int act_dtype, void *stream) {
+  B200_CHECK(x && out && R > 0 && C > 0 && C % 8 == 0, "colsum16: bad arguments");
+  const int rpb = (int)std::max<int64_t>(16, cdiv64(R, (int64_t)num_sms() * 8));
+  const int blocks = (int)cdiv64(R, rpb);
+#define L_(TT, ...) colsum16_kernel<TT><<<blocks, 128, 0, (cudaStream_t)stream>>>((const TT *)x, out, R, C, rpb)
+  B200_ACT_DISPATCH(L_, 0);
+#undef L_
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_gelu_bwd(const void *pre, const void *du, void *dpre, int64_t n, int act_dtype, void *stream) {
+  B200_CHECK(pre && du && dpre && n > 0 && n % 8 == 0, "gelu_bwd: bad arguments");
+#define L_(TT, ...) gelu_bwd_kernel<TT><<<ew_blocks(n / 8), 256, 0, (cudaStream_t)stream>>>((const TT *)pre, (const TT *)du, (TT *)dpre, n / 8)
+  B200_ACT_DISPATCH(L_, 0);
+#undef L_
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_gelu_fwd(const void *pre, void *out, int64_t n, int act_dtype, void *stream) {
+  B200_CHECK(pre && out && n > 0 && n % 8 == 0, "gelu_fwd: bad arguments");
+#define L_(TT, ...) gelu_fwd_kernel<TT><<<ew_blocks(n / 8), 256, 0, (cudaStream_t)stream>>>((const TT *)pre, (TT *)out, n / 8)
+  B200_ACT_DISPATCH(L_, 0);
+#undef L_
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_gated_residual(const void *h_in, const void *f, const float *gate, int gate_stride, void *h_out,
+                                   int64_t rows, int L, int C, int act_dtype, void *stream) {
+  B200_CHECK(h_in && f && gate && h_out && rows > 0 && L > 0 && C % 8 == 0, "gated_residual: bad arguments");
+#define L_(TT, ...) gated_residual_kernel<TT><<<ew_blocks(rows * (C / 8)), 256, 0, (cudaStream_t)stream>>>( \
+      (const TT *)h_in, (const TT *)f, gate, gate_stride, (TT *)h_out, rows, L, C)
+  B200_ACT_DISPATCH(L_, 0);
+#undef L_
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+static int rows_per_warp_for(int N, int L) {
+  // enough warps to fill the GPU, but long enough runs that the per-(sample, channel) atomics stay cheap
+  int rpw = 32;
+  while (rpw > 4 && (int64_t)N * cdiv(L, rpw) < (int64_t)num_sms() * 16) rpw >>= 1;
+  return rpw;
+}
+
+extern "C" int b200_gate_bwd(const void *dh, const void *f, const float *gate, int gate_stride, void *df, float *dgate,
+                             int dgate_stride, int N, int L, int C, int act_dtype, void *stream) {
+  B200_CHECK(dh && f && gate && df && dgate && N > 0 && L > 0 && C % 8 == 0 && C <= kMaxVec * 256,
+             "gate_bwd: bad arguments (C <= %d)", kMaxVec * 256);
+  const int rpw = rows_per_warp_for(N, L);
+  const int64_t warps = (int64_t)N * cdiv(L, rpw);
+  const int blocks = (int)cdiv64(warps, 8);
+  const int nv = cdiv(C / 8, 32);
+#define L2_(TT, NV) gate_bwd_kernel<TT, NV><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TT *)dh, (const TT *)f, gate, \
+      gate_stride, (TT *)df, dgate, dgate_stride, N, L, C, rpw)
+#define L_(TT, ...)                                                                         \
+  switch (nv) {                                                                             \
+    case 1: L2_(TT, 1); break; case 2: L2_(TT, 2); break; case 3: L2_(TT, 3); break;        \
+    case 4: L2_(TT, 4); break; case 5: L2_(TT, 5); break; default: L2_(TT, 6); break;       \
+  }
+  B200_ACT_DISPATCH(L_, 0);
+#undef L_
+#undef L2_
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_ln_mod_bwd(const void *x, const void *da, const float *scale, int mod_stride, const void *dres, void *dx,
+                               float *dshift, float *dscale, int dmod_stride, int N, int L, int C, float eps, int act_dtype,
+                               void *stream) {
+  B200_CHECK(x && da && scale && dx && dshift && dscale && N > 0 && L > 0 && C % 8 == 0 && C <= kMaxVec * 256,
+             "ln_mod_bwd: bad arguments (C <= %d)", kMaxVec * 256);
+  const int rpw = rows_per_warp_for(N, L);
+  const int64_t warps = (int64_t)N * cdiv(L, rpw);
+  const int blocks = (int)cdiv64(warps, 8);
+  const int nv = cdiv(C / 8, 32);
+#define L2_(TT, NV) ln_mod_bwd_kernel<TT, NV><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TT *)x, (const TT *)da, scale, \
+      mod_stride, (const TT *)dres, (TT *)dx, dshift, dscale, dmod_stride, N, L, C, eps, rpw)
+#define L_(TT, ...)                                                                         \
+  switch (nv) {                                                                             \
+    case 1: L2_(TT, 1); break; case 2: L2_(TT, 2); break; case 3: L2_(TT, 3); break;        \
+    case 4: L2_(TT, 4); break; case 5: L2_(TT, 5); break; default: L2_(TT, 6); break;       \
+  }
+  B200_ACT_DISPATCH(L_, 0);
+#undef L_
+#undef L2_
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_attention_bwd(const void *qkv, int ld, int q_off, int k_off, int v_off, const void *out, const void *dout,
+                                  const float *lse, float *dsum_ws, float *dq_ws, void *dqkv, int B, int L, int heads, int d,
+                                  float scale, int act_dtype, void *stream) {
+  B200_CHECK(qkv && out && dout && lse && dsum_ws && dq_ws && dqkv && B > 0 && L > 0 && heads > 0, "attention_bwd: bad arguments");
+  B200_CHECK(d == 32 || d == 64, "attention_bwd: head dim %d not built (32, 64)", d);
+  B200_CHECK(ld % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0, "attention_bwd: offsets must be multiples of 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = (int64_t)B * L;
+  B200_CUDA(cudaMemsetAsync(dq_ws, 0, (size_t)rows * heads * d * sizeof(float), st));
+  const dim3 grid(cdiv(L, 64), heads, B);
+#define LAUNCH_(TT, DD)                                                                                                    \
+  do {                                                                                                                     \
+    attn_bwd_prep_kernel<TT><<<ew_blocks(rows * heads), 256, 0, st>>>((const TT *)out, (const TT *)dout, dsum_ws, rows, heads, DD); \
+    B200_LAUNCH_CHECK();                                                                                                   \
+    const size_t smem = (size_t)(4 * 64 * (DD + 8) + 2 * 64 * 72) * 2 + (size_t)(2 * 64 * 72 + 128) * 4;                   \
+    static bool attr = false;                                                                                              \
+    if (!attr) {                                                                                                           \
+      B200_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<TT, DD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+      attr = true;                                                                                                         \
+    }                                                                                                                      \
+    attn_bwd_kernel<TT, DD><<<grid, 128, smem, st>>>((const TT *)qkv, ld, q_off, k_off, v_off, (const TT *)dout, lse,      \
+                                                     dsum_ws, dq_ws, (TT *)dqkv, L, heads, scale);                         \
+    B200_LAUNCH_CHECK();                                                                                                   \
+    f32_to_act_strided_kernel<TT><<<ew_blocks(rows * (heads * DD / 8)), 256, 0, st>>>(dq_ws, (TT *)dqkv, rows, heads * DD, \
+                                                                                        ld, q_off);                        \
+    B200_LAUNCH_CHECK();                                                                                                   \
+  } while (0)
+  if (act_dtype == B200_F16) { if (d == 32) LAUNCH_(__half, 32); else LAUNCH_(__half, 64); }
+  else if (act_dtype == B200_BF16) { if (d == 32) LAUNCH_(__nv_bfloat16, 32); else LAUNCH_(__nv_bfloat16, 64); }
+  else B200_CHECK(false, "attention_bwd: bad act_dtype");
+#undef LAUNCH_
+  return 0;
+}
+
+extern "C" int b200_unpatchify_bwd(const float *dimg, void *dtok, int N, int Cout, int gh, int gw, int p, int ld, int act_dtype,
+                                   void *stream) {
+  B200_CHECK(dimg && dtok && N > 0 && Cout > 0 && gh > 0 && gw > 0 && p > 0 && ld >= p * p * Cout, "unpatchify_bwd: bad geometry");
+  const long long total = (long long)N * gh * gw * ld;
+#define L_(TT, ...) unpatchify_bwd_kernel<TT><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(dimg, (TT *)dtok, Cout, gh, gw, p, ld, total)
+  B200_ACT_DISPATCH(L_, 0);
+#undef L_
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_q_sample(const float *x0, const float *noise, const float *coef, float *xt, int N, int per, void *stream) {
+  B200_CHECK(x0 && noise && coef && xt && N > 0 && per > 0, "q_sample: bad arguments");
+  const int64_t total = (int64_t)N * per;
+  q_sample_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x0, noise, coef, xt, per, total);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_diffusion_loss(const float *model_out, const float *x_start, const float *x_t, const float *noise,
+                                   const float *coef, int param, int learn_sigma, float *terms, float *d_out, int N, int C,
+                                   int HW, void *stream) {
+  B200_CHECK(model_out && x_start && x_t && noise && coef && terms && d_out && N > 0 && C > 0 && HW > 0 && param >= 0 && param <= 2,
+             "diffusion_loss: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CUDA(cudaMemsetAsync(terms, 0, (size_t)N * 2 * sizeof(float), st));
+  const dim3 grid(std::max(1, std::min(cdiv(C * HW, 256), num_sms() * 4 / std::max(1, N))), N);
+  diffusion_loss_kernel<<<grid, 256, 0, st>>>(model_out, x_start, x_t, noise, coef, param, learn_sigma, terms, d_out, N, C, HW,
+                                              1e-6f);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_linear_f32_wgrad(const float *dy, int dy_stride, const float *x, int x_stride, int in_silu, float *dW,
+                                     float *db, int N, int O, int I, int accumulate, void *stream) {
+  B200_CHECK(dy && x && dW && N > 0 && N <= 64 && O > 0 && I > 0, "linear_f32_wgrad: bad arguments (N <= 64)");
+  const dim3 grid(cdiv(I, 256), O);
+  linear_f32_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, dy_stride, x, x_stride, in_silu, dW, db, N, O, I, accumulate);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_linear_f32_dgrad(const float *dy, int dy_stride, const float *W, const float *x_pre, float *dx, int N, int O,
+                                     int I, void *stream) {
+  B200_CHECK(dy && W && dx && N > 0 && N <= 64 && O > 0 && I > 0, "linear_f32_dgrad: bad arguments (N <= 64)");
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CUDA(cudaMemsetAsync(dx, 0, (size_t)N * I * sizeof(float), st));
+  const int o_chunk = 128;
+  const dim3 grid(cdiv(I, 128), cdiv(O, o_chunk));
+  linear_f32_dgrad_kernel<<<grid, 128, (size_t)o_chunk * N * sizeof(float), st>>>(dy, dy_stride, W, dx, N, O, I, o_chunk);
+  B200_LAUNCH_CHECK();
+  if (x_pre) {      // the linear's input was silu(x_pre): chain through the activation
+    silu_bwd_f32_kernel<<<ew_blocks((int64_t)N * I), 256, 0, st>>>(x_pre, dx, (int64_t)N * I);
+    B200_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int b200_adamw(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, int step, float grad_scale, void *stream) {
+  B200_CHECK(p && g && m && v && n > 0 && step >= 1, "adamw: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = 1.f - powf(beta2, (float)step);
+  adamw_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1,
+                                                               sqrtf(bc2), grad_scale);
+  B200_LAUNCH_CHECK();
+  return 0;
+}

@@ -152,7 +152,7 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
            rowbias: Optional[Tensor] = None, residual: Optional[Tensor] = None, res_scale: float = 1.0,
            out: Optional[Tensor] = None, stats: Optional[Tensor] = None, head_channels: int = 0,
            out_hw: Optional[Tuple[int, int]] = None, out_f32: bool = False, rowscale: Optional[Tensor] = None,
-           act: int = 0, wsets: int = 1, rowbias_gstride: int = 0) -> Tensor:
+           act: int = 0, wsets: int = 1, rowbias_gstride: int = 0, force_ksplit: int = 0) -> Tensor:
     """tcgen05 implicit-GEMM conv over up to 3 K-segments (see b200_conv2d_igemm).
 
     ``wsets`` > 1: grouped along N — the batch is ``wsets`` equal groups of images, group g convolves with its own weight
@@ -189,6 +189,7 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
     d.bias = _p(_f32(bias))
     d.rowbias, d.rowbias_stride = None, 0
     d.wsets, d.rowbias_gstride, d.rowscale_gstride = wsets, rowbias_gstride, 0
+    d.force_ksplit = int(force_ksplit)
     npg = n // max(wsets, 1)
     if wsets > 1 and (n % wsets or rowscale is not None or (bias is not None and bias.numel() != wsets * cout)):
         raise L.B200Error("conv2d: grouped launch needs N % wsets == 0, a [wsets, Cout] bias and no rowscale")
@@ -435,7 +436,7 @@ def attention_qkv(qkv: Tensor, heads: int, new_order: bool) -> Tensor:
 
 def attention(q: Tensor, k: Tensor, v: Tensor, heads: int, d: int, scale: float, q_off: int = 0, k_off: int = 0,
               v_off: int = 0, q_hstride: Optional[int] = None, k_hstride: Optional[int] = None,
-              v_hstride: Optional[int] = None, force_simt: bool = False) -> Tensor:
+              v_hstride: Optional[int] = None, force_simt: bool = False, lse: Optional[Tensor] = None) -> Tensor:
     """General fused attention over token tensors q [B,Lq,ldq], k/v [B,Lk,ld*] (heads are channel slices)."""
     _dev(q)
     b, lq, ldq = q.shape
@@ -450,6 +451,9 @@ def attention(q: Tensor, k: Tensor, v: Tensor, heads: int, d: int, scale: float,
     a.k_hstride = d if k_hstride is None else k_hstride
     a.v_hstride = d if v_hstride is None else v_hstride
     a.scale, a.act_dtype, a.force_simt = scale, act_code(q.dtype), int(force_simt)
+    if lse is not None and (lse.dtype != torch.float32 or lse.numel() != b * heads * lq):
+        raise L.B200Error("attention: lse must be fp32 [B, heads, Lq]")
+    a.lse = _p(lse)
     _timed("attention", 4.0 * b * heads * lq * lk * d, 2.0 * (b * heads * d * (2 * lq + 2 * lk)),
            lambda: L.check(L.lib().b200_attention(C.byref(a), _stream()), "attention"))
     return out

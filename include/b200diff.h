@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 10
+#define B200_ABI_VERSION 11
 #define B200_F16 0
 #define B200_BF16 1
 
@@ -117,6 +117,10 @@ typedef struct {
                               (their per-image stride then counts images WITHIN the group).  One launch for the G same-shape
                               encoders of DSUnetModel (UNet_DS_Diff/model.py:674-686) instead of G latency-bound ones.      */
   int rowbias_gstride, rowscale_gstride;
+  int force_ksplit;         /* 0: split-K factor chosen by b200_conv_ksplit (geometry only).  S > 1: run exactly S K-splits; with
+                              out_nhwc_f32 set the S fp32 partial planes (workspace) are summed in fixed order into out_nhwc_f32
+                              with no epilogue terms (bias / residual must be NULL) — the weight-gradient GEMM of the training
+                              step, dW[Cout, Cin] = dY^T X with K = all tokens of the batch (trainers' loss.backward()).        */
 } b200_conv_desc;
 int b200_conv2d_igemm(const b200_conv_desc *d, void *stream);
 /* split-K factor b200_conv2d_igemm will use for this descriptor (1 = none).  It depends on the layer geometry only
@@ -185,6 +189,8 @@ typedef struct {
   float scale;
   int act_dtype;
   int force_simt;
+  float *lse;        /* optional [B, heads, Lq] fp32: log-sum-exp of the scaled scores of every query row, saved for
+                        b200_attention_bwd (training); tcgen05 kernel only (d % 16 == 0); NULL for inference            */
 } b200_attn_desc;
 int b200_attention(const b200_attn_desc *d, void *stream);
 
@@ -318,6 +324,59 @@ int b200_lincomb2(const float *x, const float *y, const float *c1, const float *
                   int subtract, void *stream);
 /* *step_ptr += delta (one-thread kernel; keeps the step counter on the device for graph replay). */
 int b200_advance_step(int *step_ptr, int delta, void *stream);
+
+/* ---- training step (BASELINE config 5: DiT diffusion training) ---------------------------------------
+ * Everything of forward + backward + optimizer that is not a GEMM; the GEMMs run on b200_conv2d_igemm (forward and dgrad
+ * with a transposed packed weight; wgrad with both operands transposed to K-major by b200_transpose16 and force_ksplit).
+ * The reference gets all of this from torch autograd (loss.backward(), trainers/trainer_use_gaussian_diff.py:464-478) over
+ * UNet_DS_Diff/DiT_models.py:101-142 and training_project/utils/gaussian_diffusion.py:824-983.                          */
+/* dst[C, R] = src[R, C]^T, 16-bit elements */
+int b200_transpose16(const void *src, void *dst, int64_t R, int C, void *stream);
+/* out[c] += sum_r x[r, c]  (bias gradients; fp32, zero `out` first) */
+int b200_colsum16(const void *x, float *out, int64_t R, int C, int act_dtype, void *stream);
+/* GELU(tanh) on a stored pre-activation, and its backward dpre = du * gelu'(pre)  (timm Mlp, DiT_models.py:111-112) */
+int b200_gelu_fwd(const void *pre, void *out, int64_t n, int act_dtype, void *stream);
+int b200_gelu_bwd(const void *pre, const void *du, void *dpre, int64_t n, int act_dtype, void *stream);
+/* adaLN-Zero gated residual h_out = h_in + gate[n] * f (DiT_models.py:120-121; gate fp32 [N, C] rows of pitch gate_stride,
+ * L token rows per sample) and its backward df = gate[n] * dh, dgate[n, c] += sum_t dh * f  (dgate zeroed by the caller) */
+int b200_gated_residual(const void *h_in, const void *f, const float *gate, int gate_stride, void *h_out, int64_t rows, int L,
+                        int C, int act_dtype, void *stream);
+int b200_gate_bwd(const void *dh, const void *f, const float *gate, int gate_stride, void *df, float *dgate, int dgate_stride,
+                  int N, int L, int C, int act_dtype, void *stream);
+/* backward of a = LayerNorm(x; no affine, eps) * (1 + scale[n]) + shift[n]  (modulate(norm(x), shift, scale), :19-20, :119):
+ * dx = LN-backward(da * (1 + scale)) (+ dres), dshift[n, c] += sum_t da, dscale[n, c] += sum_t da * nhat  (caller zeroes) */
+int b200_ln_mod_bwd(const void *x, const void *da, const float *scale, int mod_stride, const void *dres, void *dx,
+                    float *dshift, float *dscale, int dmod_stride, int N, int L, int C, float eps, int act_dtype, void *stream);
+/* attention backward for self-attention over a packed qkv tensor [B, L, ld] (head h of q at q_off + h*d, ...):
+ * out / dout [B, L, heads*d]; lse [B, heads, L] from b200_attention; writes dq | dk | dv into dqkv (same layout as qkv).
+ * Workspaces: dsum_ws >= B*L*heads floats, dq_ws >= B*L*heads*d floats.  d in {32, 64}.                                  */
+int b200_attention_bwd(const void *qkv, int ld, int q_off, int k_off, int v_off, const void *out, const void *dout,
+                       const float *lse, float *dsum_ws, float *dq_ws, void *dqkv, int B, int L, int heads, int d, float scale,
+                       int act_dtype, void *stream);
+/* backward of DiT.unpatchify (DiT_models.py:220-232): dimg [N, Cout, gh*p, gw*p] fp32 -> dtok [N, gh*gw, ld] act, feature
+ * (ph*p + pw)*Cout + c, columns >= p*p*Cout zero                                                                          */
+int b200_unpatchify_bwd(const float *dimg, void *dtok, int N, int Cout, int gh, int gw, int p, int ld, int act_dtype,
+                        void *stream);
+/* q_sample (gaussian_diffusion.py:199-215) with per-sample coefficient rows coef[N][12] (see b200_diffusion_loss) */
+int b200_q_sample(const float *x0, const float *noise, const float *coef, float *xt, int N, int per, void *stream);
+/* GaussianDiffusion.training_losses, MSE / RESCALED_MSE branch (:851-977), and its gradient w.r.t. the network output:
+ *   terms[N][2] = (mean_flat(Charbonnier(target, mean channels)), vb term in bits/dim x weight);
+ *   d_out = d( mean_n(terms[n][0] + terms[n][1]) ) / d model_out, same shape as model_out ([N, C or 2C, HW] fp32).
+ * param: 0 eps, 1 x0, 2 v.  coef[N][12] fp32 rows gathered at each sample's t on the host from the float64 tables:
+ *   sqrt_ac, sqrt_1m_ac, post_mean_coef1, post_mean_coef2, post_logvar_clipped, log(beta), t == 0, vb weight
+ *   (num_timesteps / 1000 for RESCALED_MSE, else 1), sqrt_recip_ac, sqrt_recipm1_ac, 0, 0.                              */
+int b200_diffusion_loss(const float *model_out, const float *x_start, const float *x_t, const float *noise, const float *coef,
+                        int param, int learn_sigma, float *terms, float *d_out, int N, int C, int HW, void *stream);
+/* backward of the small fp32 linears of the conditioning path, y = xin W^T + b with xin = silu(x) when in_silu (N <= 64):
+ *   wgrad: dW[O, I] (+)= dy^T xin, db[O] (+)= sum_n dy;   dgrad: dx[N, I] = dy W (then * silu'(x_pre) when x_pre != NULL) */
+int b200_linear_f32_wgrad(const float *dy, int dy_stride, const float *x, int x_stride, int in_silu, float *dW, float *db,
+                          int N, int O, int I, int accumulate, void *stream);
+int b200_linear_f32_dgrad(const float *dy, int dy_stride, const float *W, const float *x_pre, float *dx, int N, int O, int I,
+                          void *stream);
+/* fused AdamW over a flat fp32 arena (torch.optim.AdamW semantics; step counts from 1; g is multiplied by grad_scale first:
+ * 1 / world_size after a summing all-reduce)                                                                            */
+int b200_adamw(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2, float eps,
+               float weight_decay, int step, float grad_scale, void *stream);
 
 #ifdef __cplusplus
 }

@@ -104,3 +104,34 @@ def test_training_gradients_oracle_matches_reference():
         if k.startswith("g:"):
             ref = g[k]
             assert maxabs(sd[k[2:]].grad, ref) <= 2e-4 * max(floor, float(ref.abs().max())), k
+
+
+@pytest.mark.parametrize("name", ["train_dit_v", "train_dit_eps_rescaled"])
+def test_dit_training_step_oracle_matches_reference(name):
+    """cfg5 groundwork: loss terms and gradients of ONE DiT training step — the oracle's restated forward (dit_forward) and
+    objective under torch autograd vs the reference's own DiT + training_losses + .backward()
+    (oracle/make_golden_train_dit.py)."""
+    import os
+    from _util import GOLD, manifest
+    g = golden(name)
+    man = manifest()[name]
+    hp, sd = synth_sd(name)
+    sd["pos_embed"] = g["pos_embed"]
+    names = open(os.path.join(GOLD, name + ".names.txt")).read().split()
+    sd = {k: (v.clone().requires_grad_(True) if k != "pos_embed" else v) for k, v in sd.items()}
+    sch = O.GdSchedule(steps=1000, noise_schedule="linear", timestep_respacing="", rescale_timesteps=True)
+    terms = TO.training_losses(sch, lambda xc, tm: O.dit_forward(sd, hp, xc, tm), g["x0"], g["t"], g["noise"], list(g["cond"]),
+                               parameterization=man["parameterization"], learn_sigma=True, rescaled_mse=man["rescaled"])
+    for k in ("mse", "vb", "loss"):
+        assert _close(terms[k].detach(), g[k]), (k, terms[k], g[k])
+    terms["loss"].mean().backward()
+    floor = 1e-4 * float(g["grad_norms"].max())
+    for nm, ref in zip(names, g["grad_norms"].tolist()):
+        got = sd[nm].grad
+        if ref < 0:
+            assert got is None or float(got.abs().max()) == 0.0, nm
+            continue
+        assert abs(float(got.double().norm()) - ref) / max(ref, floor) < 2e-4, nm
+    for k in g:
+        if k.startswith("g:"):
+            assert maxabs(sd[k[2:]].grad.reshape(g[k].shape), g[k]) <= 2e-4 * max(floor, float(g[k].abs().max())), k
