@@ -99,7 +99,7 @@ SIGNATURES = {
     "b200_lincomb2": [_P, _P, _P, _P, _P, _I, _L, _I, _P],
     "b200_advance_step": [_P, _I, _P],
     # training step (csrc/train.cu)
-    "b200_transpose16": [_P, _P, _L, _I, _P],
+    "b200_transpose16": [_P, _P, _P, _L, _I, _I, _P],
     "b200_colsum16": [_P, _P, _L, _I, _I, _P],
     "b200_gelu_fwd": [_P, _P, _L, _I, _P],
     "b200_gelu_bwd": [_P, _P, _P, _L, _I, _P],

@@ -1,0 +1,336 @@
+// Attention BACKWARD on tcgen05 / TMEM (training step of DiT): the gradient of
+//   O = softmax(scale Q K^T) V      (timm Attention inside DiTBlock, UNet_DS_Diff/DiT_models.py:108)
+// which the reference obtains from torch autograd (loss.backward(), trainers/trainer_use_gaussian_diff_adv.py:345-382).
+//
+//   S = Q K^T,  P = exp(scale S - lse),  dP = dO V^T,  dS = scale P (dP - D),  D_i = sum_c dO[i, c] O[i, c]
+//   dV = P^T dO,   dK = dS^T Q,   dQ = dS K
+//
+// Two instantiations of ONE kernel, so that no accumulator is shared between CTAs (no atomics, deterministic):
+//   kDQ = false : CTA = 128 KEYS of one (batch, head); streams the 128-query tiles; dK / dV accumulate in TMEM;
+//   kDQ = true  : CTA = 128 QUERIES; streams the 128-key tiles; dQ accumulates in TMEM.
+// Both recompute S and dP per tile pair (7 GEMMs per pair instead of the minimal 5).  Same machinery as the forward kernel
+// (attention.cu): operands staged by TMA as UN-SWIZZLED 8 x 16-byte core matrices, one box of (8 channels x 128 tokens)
+// per 16-byte channel block — that one shared-memory image serves as a K-major operand when the contraction runs over
+// channels (S, dP) and as an MN-major operand when it runs over tokens (dV, dK, dQ), so nothing is ever transposed;
+// warp 0 = TMA producer, warp 1 = single-thread MMA issuer + TMEM owner, warps 2-9 = the element-wise stage
+// (thread = (query row, 64-column half)): tcgen05.ld S and dP -> registers, hand the TMEM buffers back at once so the
+// next tile's S / dP overlap the exponentials, write P and dS as 16-bit operand tiles to shared memory.
+// TMEM columns: S 128 | dP 128 | accumulator 0 (D) | accumulator 1 (D).
+#include "common.cuh"
+
+namespace b200 {
+
+constexpr int kBwThreads = 320;
+constexpr int kBwT = 128;                                // tokens per tile (both queries and keys)
+constexpr uint32_t kBwBlk = 128 * 16;                    // one (8 channels x 128 tokens) TMA box = 2048 B
+constexpr uint32_t kBwPBytes = kBwT * kBwT * 2;          // a 128 x 128 16-bit operand tile (P or dS)
+
+struct BwMaps {
+  CUtensorMap qkv, dout;
+};
+
+struct BwParams {
+  int L, heads;
+  int q_off, k_off, v_off;      // first channel of head 0 inside a qkv row
+  int ld;                       // qkv / dqkv row pitch (elements)
+  float scale, scale_log2e;
+  const float *lse;             // [B, heads, L] natural-log units (b200_attention)
+  const float *dsum;            // [B, L, heads]
+  void *dqkv;
+  uint32_t idesc_s, idesc_acc;
+};
+
+__device__ __forceinline__ float bw_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <typename T, int D, bool kDQ>
+__global__ void __launch_bounds__(kBwThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ BwMaps maps, const BwParams p) {
+  constexpr int kDB = D / 8;
+  constexpr uint32_t kTile = kDB * kBwBlk;               // a [128 tokens x D] operand tile
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t res_full, acc_full, s_full, s_empty, p_full, p_empty;
+  __shared__ __align__(8) uint64_t str_full[2], str_empty[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = blockIdx.x * kBwT;                      // first resident token (keys when !kDQ, queries when kDQ)
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_it = (p.L + kBwT - 1) / kBwT;
+
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t sRes0 = base, sRes1 = base + kTile;     // resident pair: (K, V) or (Q, dO)
+  const uint32_t sStr = sRes1 + kTile;                   // streamed pair x 2 stages: (Q, dO) or (K, V)
+  const uint32_t sdS = sStr + 4 * kTile;
+  const uint32_t sP = sdS + kBwPBytes;                   // only when !kDQ
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&maps.qkv); prefetch_tmap(&maps.dout);
+    mbar_init(smem_u32(&res_full), 1);
+    mbar_init(smem_u32(&acc_full), 1);
+    mbar_init(smem_u32(&s_full), 1);
+    mbar_init(smem_u32(&s_empty), 8);
+    mbar_init(smem_u32(&p_full), 8);
+    mbar_init(smem_u32(&p_empty), 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&str_full[i]), 1); mbar_init(smem_u32(&str_empty[i]), 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 128;
+  const uint32_t tmem_a0 = tmem_base + 256, tmem_a1 = tmem_base + 256 + D;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int qc = p.q_off + h * D, kc = p.k_off + h * D, vc = p.v_off + h * D, oc = h * D;
+      {
+        const uint32_t bar = smem_u32(&res_full);
+        mbar_arrive_expect_tx(bar, 2 * kTile);
+        for (int c = 0; c < kDB; ++c) {
+          if (kDQ) {
+            tma_load_3d(sRes0 + c * kBwBlk, &maps.qkv, bar, qc + c * 8, t0, b);
+            tma_load_3d(sRes1 + c * kBwBlk, &maps.dout, bar, oc + c * 8, t0, b);
+          } else {
+            tma_load_3d(sRes0 + c * kBwBlk, &maps.qkv, bar, kc + c * 8, t0, b);
+            tma_load_3d(sRes1 + c * kBwBlk, &maps.qkv, bar, vc + c * 8, t0, b);
+          }
+        }
+      }
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        mbar_wait(smem_u32(&str_empty[st]), ((it >> 1) & 1) ^ 1);
+        const uint32_t bar = smem_u32(&str_full[st]);
+        mbar_arrive_expect_tx(bar, 2 * kTile);
+        const uint32_t d0 = sStr + st * 2 * kTile, d1 = d0 + kTile;
+        for (int c = 0; c < kDB; ++c) {
+          if (kDQ) {
+            tma_load_3d(d0 + c * kBwBlk, &maps.qkv, bar, kc + c * 8, it * kBwT, b);
+            tma_load_3d(d1 + c * kBwBlk, &maps.qkv, bar, vc + c * 8, it * kBwT, b);
+          } else {
+            tma_load_3d(d0 + c * kBwBlk, &maps.qkv, bar, qc + c * 8, it * kBwT, b);
+            tma_load_3d(d1 + c * kBwBlk, &maps.dout, bar, oc + c * 8, it * kBwT, b);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      mbar_wait(smem_u32(&res_full), 0);
+      // S = Q K^T and dP = dO V^T of tile `g`: contraction over the D channels, every operand K-major
+      auto issue_first = [&](int g) {
+        const int st = g & 1;
+        mbar_wait(smem_u32(&str_full[st]), (g >> 1) & 1);
+        mbar_wait(smem_u32(&s_empty), (g & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t x0 = sStr + st * 2 * kTile, x1 = x0 + kTile;
+        const uint32_t aQ = kDQ ? sRes0 : x0, bK = kDQ ? x0 : sRes0;
+        const uint32_t aO = kDQ ? sRes1 : x1, bV = kDQ ? x1 : sRes1;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_f16(tmem_s, umma_desc_nosw(aQ + kk * 2 * kBwBlk, kBwBlk, 128), umma_desc_nosw(bK + kk * 2 * kBwBlk, kBwBlk, 128),
+                   p.idesc_s, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_f16(tmem_dp, umma_desc_nosw(aO + kk * 2 * kBwBlk, kBwBlk, 128), umma_desc_nosw(bV + kk * 2 * kBwBlk, kBwBlk, 128),
+                   p.idesc_s, kk > 0);
+        umma_commit(smem_u32(&s_full));
+      };
+      issue_first(0);
+      for (int it = 0; it < n_it; ++it) {
+        if (it + 1 < n_it) issue_first(it + 1);          // runs while the element-wise warps work on tile `it`
+        const int st = it & 1;
+        mbar_wait(smem_u32(&p_full), it & 1);
+        tc_fence_after();
+        const uint32_t x0 = sStr + st * 2 * kTile, x1 = x0 + kTile;
+        const uint32_t acc = (it > 0) ? 1u : 0u;
+        if (!kDQ) {
+          // dV += P^T dO, dK += dS^T Q: contraction over the 128 QUERIES.  A = P / dS tile [key block][query][8 keys] read
+          // MN-major (8 keys contiguous, queries 16 B apart: core matrices 128 B apart along K, 2048 B along M);
+          // B = dO / Q tile [channel block][query][8 ch] read MN-major.  16 queries per instruction = +256 B.
+#pragma unroll
+          for (int kk = 0; kk < kBwT / 16; ++kk)
+            umma_f16(tmem_a0, umma_desc_nosw(sP + kk * 256, 128, kBwBlk), umma_desc_nosw(x1 + kk * 256, 128, kBwBlk),
+                     p.idesc_acc, acc | (uint32_t)(kk > 0));
+#pragma unroll
+          for (int kk = 0; kk < kBwT / 16; ++kk)
+            umma_f16(tmem_a1, umma_desc_nosw(sdS + kk * 256, 128, kBwBlk), umma_desc_nosw(x0 + kk * 256, 128, kBwBlk),
+                     p.idesc_acc, acc | (uint32_t)(kk > 0));
+        } else {
+          // dQ += dS K: contraction over the 128 KEYS.  A = dS tile read K-major (16 keys = 2 key blocks = +4096 B);
+          // B = K tile [channel block][key][8 ch] read MN-major (+256 B per 16 keys).
+#pragma unroll
+          for (int kk = 0; kk < kBwT / 16; ++kk)
+            umma_f16(tmem_a0, umma_desc_nosw(sdS + kk * 2 * kBwBlk, kBwBlk, 128), umma_desc_nosw(x0 + kk * 256, 128, kBwBlk),
+                     p.idesc_acc, acc | (uint32_t)(kk > 0));
+        }
+        umma_commit(smem_u32(&str_empty[st]));
+        umma_commit(smem_u32(&p_empty));
+      }
+      umma_commit(smem_u32(&acc_full));
+    }
+    __syncwarp();
+  } else {
+    // ===================== element-wise warps: thread == (query row, 64-column half of the key tile) =====================
+    const int lane_base = 32 * (warp & 3);
+    const int row = lane_base + lane;
+    const int half = (warp - 2) >> 2;
+    const int cbase = half * 64;
+    const uint32_t t_lane = (uint32_t)lane_base << 16;
+    const float log2e = 1.4426950408889634f;
+    float lse2 = 0.f, dsm = 0.f;
+    if (kDQ) {
+      const int qi = t0 + row;
+      if (qi < p.L) {
+        lse2 = p.lse[((size_t)b * p.heads + h) * p.L + qi] * log2e;
+        dsm = p.dsum[((size_t)b * p.L + qi) * p.heads + h];
+      }
+    }
+    uint8_t *srow_ds = smem_raw + (sdS - smem_u32(smem_raw)) + row * 16;
+    uint8_t *srow_p = smem_raw + (sP - smem_u32(smem_raw)) + row * 16;
+    for (int it = 0; it < n_it; ++it) {
+      if (!kDQ) {
+        const int qi = it * kBwT + row;
+        lse2 = 0.f; dsm = 0.f;
+        if (qi < p.L) {
+          lse2 = p.lse[((size_t)b * p.heads + h) * p.L + qi] * log2e;
+          dsm = p.dsum[((size_t)b * p.L + qi) * p.heads + h];
+        }
+      }
+      mbar_wait(smem_u32(&s_full), it & 1);
+      tc_fence_after();
+      uint32_t s0[32], s1[32], d0[32], d1[32];
+      tmem_ld32(tmem_s + t_lane + cbase, s0);
+      tmem_ld32(tmem_s + t_lane + cbase + 32, s1);
+      tmem_ld32(tmem_dp + t_lane + cbase, d0);
+      tmem_ld32(tmem_dp + t_lane + cbase + 32, d1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_empty));    // S / dP are in registers: the next tile's MMAs may overwrite them
+      // the previous tile's dV / dK / dQ MMAs must have finished reading the operand tiles before they are rewritten
+      mbar_wait(smem_u32(&p_empty), (it & 1) ^ 1);
+      // keys past the end of the sequence (zero-filled by TMA) contribute nothing, but exp2(-lse) of their zero scores may
+      // overflow the 16-bit range: mask them
+      const int nvalid = min(kBwT, p.L - (kDQ ? it * kBwT : t0));
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        const uint32_t (&sr)[32] = c0 ? s1 : s0;
+        const uint32_t (&dr)[32] = c0 ? d1 : d0;
+#pragma unroll
+        for (int v8 = 0; v8 < 4; ++v8) {
+          float pv[8], ds[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            pv[i] = bw_ex2(fmaf(__uint_as_float(sr[v8 * 8 + i]), p.scale_log2e, -lse2));
+            if (nvalid < kBwT && cbase + c0 + v8 * 8 + i >= nvalid) pv[i] = 0.f;
+            ds[i] = pv[i] * (__uint_as_float(dr[v8 * 8 + i]) - dsm) * p.scale;
+          }
+          const uint32_t off = (((cbase + c0) >> 3) + v8) * kBwBlk;
+          *reinterpret_cast<uint4 *>(srow_ds + off) = pack8<T>(ds);
+          if (!kDQ) *reinterpret_cast<uint4 *>(srow_p + off) = pack8<T>(pv);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&p_full));
+    }
+    // epilogue: accumulators -> dqkv (16-bit); the halves split the D channels
+    mbar_wait(smem_u32(&acc_full), 0);
+    tc_fence_after();
+    constexpr int kHalfD = D / 2;
+    const int ti = t0 + row;
+    T *orow = reinterpret_cast<T *>(p.dqkv) + ((size_t)b * p.L + ti) * p.ld + h * D + half * kHalfD;
+#pragma unroll
+    for (int c0 = 0; c0 < kHalfD; c0 += 8) {
+      uint32_t r0[8], r1[8];
+      tmem_ld8(tmem_a0 + t_lane + half * kHalfD + c0, r0);
+      if (!kDQ) tmem_ld8(tmem_a1 + t_lane + half * kHalfD + c0, r1);
+      tmem_ld_wait();
+      if (ti < p.L) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r0[i]);
+        *reinterpret_cast<uint4 *>(orow + (kDQ ? p.q_off : p.v_off) + c0) = pack8<T>(f);
+        if (!kDQ) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r1[i]);
+          *reinterpret_cast<uint4 *>(orow + p.k_off + c0) = pack8<T>(f);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <typename T, int D>
+static int launch_bwd_tc(const void *qkv, int ld, int q_off, int k_off, int v_off, const void *dout, const float *lse,
+                         const float *dsum, void *dqkv, int B, int L, int heads, float scale, cudaStream_t st) {
+  BwMaps maps{};
+  BwParams p{};
+  {
+    uint64_t dims[3] = {(uint64_t)ld, (uint64_t)L, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)L * ld * 2};
+    uint32_t box[3] = {8, 128, 1}, es[3] = {1, 1, 1};
+    if (int rc = cached_tmap(&maps.qkv, qkv, 3, dims, str, box, es, /*swizzle128=*/false)) return rc;
+  }
+  {
+    const int ldo = heads * D;
+    uint64_t dims[3] = {(uint64_t)ldo, (uint64_t)L, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)ldo * 2, (uint64_t)L * ldo * 2};
+    uint32_t box[3] = {8, 128, 1}, es[3] = {1, 1, 1};
+    if (int rc = cached_tmap(&maps.dout, dout, 3, dims, str, box, es, /*swizzle128=*/false)) return rc;
+  }
+  p.L = L; p.heads = heads; p.q_off = q_off; p.k_off = k_off; p.v_off = v_off; p.ld = ld;
+  p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
+  p.lse = lse; p.dsum = dsum; p.dqkv = dqkv;
+  p.idesc_s = umma_idesc(Act<T>::kFmt, 128, 128, 0);
+  const size_t tile = (size_t)D * 256;
+  const dim3 grid(cdiv(L, kBwT), heads, B);
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<T, D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<T, D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  // dK, dV: both second-stage operands MN-major (a_major bit 15, b_major bit 16)
+  p.idesc_acc = umma_idesc(Act<T>::kFmt, 128, D, 1) | (1u << 15);
+  attn_bwd_tc_kernel<T, D, false><<<grid, kBwThreads, tile * 6 + 2 * kBwPBytes + 256, st>>>(maps, p);
+  B200_LAUNCH_CHECK();
+  // dQ: A = dS K-major, B = K MN-major
+  p.idesc_acc = umma_idesc(Act<T>::kFmt, 128, D, 1);
+  attn_bwd_tc_kernel<T, D, true><<<grid, kBwThreads, tile * 6 + kBwPBytes + 256, st>>>(maps, p);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+int attention_bwd_tc(const void *qkv, int ld, int q_off, int k_off, int v_off, const void *dout, const float *lse,
+                     const float *dsum, void *dqkv, int B, int L, int heads, int d, float scale, int act_dtype,
+                     cudaStream_t st) {
+#define BW_(TT)                                                                                                         \
+  do {                                                                                                                  \
+    if (d == 32) return launch_bwd_tc<TT, 32>(qkv, ld, q_off, k_off, v_off, dout, lse, dsum, dqkv, B, L, heads, scale, st); \
+    if (d == 64) return launch_bwd_tc<TT, 64>(qkv, ld, q_off, k_off, v_off, dout, lse, dsum, dqkv, B, L, heads, scale, st); \
+  } while (0)
+  if (act_dtype == B200_F16) BW_(__half);
+  if (act_dtype == B200_BF16) BW_(__nv_bfloat16);
+#undef BW_
+  B200_CHECK(false, "attention_bwd: unsupported head dim %d / act_dtype %d", d, act_dtype);
+}
+
+}  // namespace b200

@@ -20,19 +20,67 @@ namespace b200 {
 // ------------------------------------------------------------------------------------------------------------------
 // 16-bit transpose [R, C] -> [C, R]  (wgrad operands: token-major activations / gradients become K-major rows)
 // ------------------------------------------------------------------------------------------------------------------
+// 64 x 64 tiles through shared memory; 16-byte global loads (8 columns of a row) and 16-byte global stores (8 rows of a
+// column), eight lanes writing 128 contiguous bytes of one output row.  Optional fused column sums of the SOURCE (the bias
+// gradient db[c] = sum_t dY[t, c] of the same tensor the weight-gradient GEMM needs transposed): one fp32 atomic per
+// (column, tile).
+template <typename T>
 __global__ void __launch_bounds__(256)
-transpose16_kernel(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst, int R, int C) {
-  __shared__ uint16_t tile[64][64 + 2];
+transpose16_kernel(const T *__restrict__ src, T *__restrict__ dst, float *__restrict__ colsum, int R, int C) {
+  constexpr int P = 66;                                     // tile pitch in elements (132 B)
+  __shared__ __align__(16) uint16_t tile[64 * P];
   const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;      // 64 x 4
-  for (int i = ty; i < 64; i += 4) {
-    const int r = r0 + i, c = c0 + tx;
-    tile[i][tx] = (r < R && c < C) ? src[(size_t)r * C + c] : (uint16_t)0;
+  const uint16_t *s16 = reinterpret_cast<const uint16_t *>(src);
+  uint16_t *d16 = reinterpret_cast<uint16_t *>(dst);
+  const bool vec_ok = (C % 8 == 0) && (R % 8 == 0);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {                             // 64 rows x 8 vectors
+    const int idx = threadIdx.x + 256 * k;
+    const int r = idx >> 3, v = idx & 7;
+    const int gr = r0 + r, gc = c0 + v * 8;
+    uint16_t e[8];
+    if (vec_ok && gr < R && gc + 8 <= C) {
+      *reinterpret_cast<uint4 *>(e) = ld_stream(s16 + (size_t)gr * C + gc);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) e[j] = (gr < R && gc + j < C) ? s16[(size_t)gr * C + gc + j] : (uint16_t)0;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j += 2)
+      *reinterpret_cast<uint32_t *>(&tile[r * P + v * 8 + j]) = (uint32_t)e[j] | ((uint32_t)e[j + 1] << 16);
   }
   __syncthreads();
-  for (int i = ty; i < 64; i += 4) {
-    const int c = c0 + i, r = r0 + tx;
-    if (c < C && r < R) dst[(size_t)c * R + r] = tile[tx][i];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {                             // 64 columns x 8 row groups
+    const int idx = threadIdx.x + 256 * k;
+    const int c = idx >> 3, rg = idx & 7;
+    uint16_t e[8];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      e[j] = tile[(rg * 8 + j) * P + c];
+      if (colsum) {
+        T t;
+        *reinterpret_cast<uint16_t *>(&t) = e[j];
+        sum += Act<T>::to_f(t);
+      }
+    }
+    const int gc = c0 + c, gr = r0 + rg * 8;
+    if (gc < C) {
+      if (vec_ok && gr + 8 <= R) {
+        st_stream(d16 + (size_t)gc * R + gr, *reinterpret_cast<uint4 *>(e));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (gr + j < R) d16[(size_t)gc * R + gr + j] = e[j];
+      }
+    }
+    if (colsum) {                                           // the 8 lanes of a column are adjacent
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+      if (rg == 0 && gc < C) atomicAdd(colsum + gc, sum);
+    }
   }
 }
 
@@ -129,18 +177,21 @@ template <typename T, int NV>
 __global__ void __launch_bounds__(256)
 gate_bwd_kernel(const T *__restrict__ dh, const T *__restrict__ f, const float *__restrict__ gate, int gate_stride,
                 T *__restrict__ df, float *__restrict__ dgate, int dgate_stride, int N, int L, int C, int rows_per_warp) {
-  constexpr int kMaxVec = NV;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int warps_per_sample = (L + rows_per_warp - 1) / rows_per_warp;
-  const int n = warp / warps_per_sample;
-  if (n >= N) return;
-  const int t0 = (warp - n * warps_per_sample) * rows_per_warp;
+  // block = 8 warps walking consecutive row chunks of ONE sample; their per-channel partial sums meet in shared memory, so a
+  // block issues one global atomic per channel
+  extern __shared__ float s_acc[];                       // [C]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int blocks_per_sample = (L + 8 * rows_per_warp - 1) / (8 * rows_per_warp);
+  const int n = blockIdx.x / blocks_per_sample;
+  const int t0 = ((blockIdx.x - n * blocks_per_sample) * 8 + warp) * rows_per_warp;
   const int t1 = min(L, t0 + rows_per_warp);
   const int nvec = C >> 3;
-  float acc[kMaxVec][8];
-  float g[kMaxVec][8];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  float acc[NV][8];
+  float g[NV][8];
 #pragma unroll
-  for (int k = 0; k < kMaxVec; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int v = lane + 32 * k;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[k][j] = 0.f; g[k][j] = (v < nvec) ? gate[(size_t)n * gate_stride + v * 8 + j] : 0.f; }
@@ -148,7 +199,7 @@ gate_bwd_kernel(const T *__restrict__ dh, const T *__restrict__ f, const float *
   for (int t = t0; t < t1; ++t) {
     const size_t row = ((size_t)n * L + t) * C;
 #pragma unroll
-    for (int k = 0; k < kMaxVec; ++k) {
+    for (int k = 0; k < NV; ++k) {
       const int v = lane + 32 * k;
       if (v < nvec) {
         float d[8], ff[8];
@@ -161,12 +212,14 @@ gate_bwd_kernel(const T *__restrict__ dh, const T *__restrict__ f, const float *
     }
   }
 #pragma unroll
-  for (int k = 0; k < kMaxVec; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int v = lane + 32 * k;
     if (v < nvec && t1 > t0)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(dgate + (size_t)n * dgate_stride + v * 8 + j, acc[k][j]);
+      for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[v * 8 + j], acc[k][j]);
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dgate + (size_t)n * dgate_stride + i, s_acc[i]);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -176,35 +229,36 @@ gate_bwd_kernel(const T *__restrict__ dh, const T *__restrict__ f, const float *
 //   dshift[n, c] += sum_t da ; dscale[n, c] += sum_t da * nhat
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T, int NV>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (NV <= 3) ? 2 : 1)
 ln_mod_bwd_kernel(const T *__restrict__ x, const T *__restrict__ da, const float *__restrict__ scale, int mod_stride,
                   const T *__restrict__ dres, T *__restrict__ dx, float *__restrict__ dshift, float *__restrict__ dscale,
                   int dmod_stride, int N, int L, int C, float eps, int rows_per_warp) {
-  constexpr int kMaxVec = NV;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int warps_per_sample = (L + rows_per_warp - 1) / rows_per_warp;
-  const int n = warp / warps_per_sample;
-  if (n >= N) return;
-  const int t0 = (warp - n * warps_per_sample) * rows_per_warp;
+  // block = 8 warps walking consecutive row chunks of ONE sample (see gate_bwd_kernel); 1 + scale[n] sits in shared memory
+  extern __shared__ float s_buf[];                       // [3][C]: dshift partials, dscale partials, 1 + scale
+  float *s_sh = s_buf, *s_sc = s_buf + C, *s_s1 = s_buf + 2 * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int blocks_per_sample = (L + 8 * rows_per_warp - 1) / (8 * rows_per_warp);
+  const int n = blockIdx.x / blocks_per_sample;
+  const int t0 = ((blockIdx.x - n * blocks_per_sample) * 8 + warp) * rows_per_warp;
   const int t1 = min(L, t0 + rows_per_warp);
   const int nvec = C >> 3;
   const float invC = 1.f / (float)C;
-  float sc1[kMaxVec][8], a_sh[kMaxVec][8], a_sc[kMaxVec][8];
-#pragma unroll
-  for (int k = 0; k < kMaxVec; ++k) {
-    const int v = lane + 32 * k;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sc1[k][j] = (v < nvec) ? 1.f + scale[(size_t)n * mod_stride + v * 8 + j] : 0.f;
-      a_sh[k][j] = 0.f; a_sc[k][j] = 0.f;
-    }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    s_sh[i] = 0.f; s_sc[i] = 0.f;
+    s_s1[i] = 1.f + scale[(size_t)n * mod_stride + i];
   }
+  __syncthreads();
+  float a_sh[NV][8], a_sc[NV][8];
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a_sh[k][j] = 0.f; a_sc[k][j] = 0.f; }
   for (int t = t0; t < t1; ++t) {
     const size_t row = ((size_t)n * L + t) * C;
-    float xv[kMaxVec][8], gv[kMaxVec][8];
+    float xv[NV][8], gv[NV][8];
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxVec; ++k) {
+    for (int k = 0; k < NV; ++k) {
       const int v = lane + 32 * k;
       if (v < nvec) {
         unpack8<T>(ld_stream(x + row + v * 8), xv[k]);
@@ -221,7 +275,7 @@ ln_mod_bwd_kernel(const T *__restrict__ x, const T *__restrict__ da, const float
     const float mean = s * invC;
     float q = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxVec; ++k)
+    for (int k = 0; k < NV; ++k)
       if (lane + 32 * k < nvec)
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float d = xv[k][j] - mean; q = fmaf(d, d, q); }
@@ -230,20 +284,26 @@ ln_mod_bwd_kernel(const T *__restrict__ x, const T *__restrict__ da, const float
     const float rstd = rsqrtf(q * invC + eps);
     float sg = 0.f, sgn = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxVec; ++k)
-      if (lane + 32 * k < nvec)
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nvec) {
+        const float4 m0 = *reinterpret_cast<const float4 *>(s_s1 + v * 8);
+        const float4 m1 = *reinterpret_cast<const float4 *>(s_s1 + v * 8 + 4);
+        const float sc1[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float nh = (xv[k][j] - mean) * rstd;
           const float d = gv[k][j];
           a_sh[k][j] += d;
           a_sc[k][j] = fmaf(d, nh, a_sc[k][j]);
-          const float g = d * sc1[k][j];
+          const float g = d * sc1[j];
           xv[k][j] = nh;            // keep nhat
           gv[k][j] = g;             // keep g
           sg += g;
           sgn = fmaf(g, nh, sgn);
         }
+      }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       sg += __shfl_xor_sync(0xffffffffu, sg, o);
@@ -251,7 +311,7 @@ ln_mod_bwd_kernel(const T *__restrict__ x, const T *__restrict__ da, const float
     }
     const float mg = sg * invC, mgn = sgn * invC;
 #pragma unroll
-    for (int k = 0; k < kMaxVec; ++k) {
+    for (int k = 0; k < NV; ++k) {
       const int v = lane + 32 * k;
       if (v < nvec) {
         float o8[8];
@@ -269,15 +329,20 @@ ln_mod_bwd_kernel(const T *__restrict__ x, const T *__restrict__ da, const float
   }
   if (t1 > t0) {
 #pragma unroll
-    for (int k = 0; k < kMaxVec; ++k) {
+    for (int k = 0; k < NV; ++k) {
       const int v = lane + 32 * k;
       if (v < nvec)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          atomicAdd(dshift + (size_t)n * dmod_stride + v * 8 + j, a_sh[k][j]);
-          atomicAdd(dscale + (size_t)n * dmod_stride + v * 8 + j, a_sc[k][j]);
+          atomicAdd(&s_sh[v * 8 + j], a_sh[k][j]);
+          atomicAdd(&s_sc[v * 8 + j], a_sc[k][j]);
         }
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(dshift + (size_t)n * dmod_stride + i, s_sh[i]);
+    atomicAdd(dscale + (size_t)n * dmod_stride + i, s_sc[i]);
   }
 }
 
@@ -720,6 +785,10 @@ adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restri
   }
 }
 
+// tcgen05 / TMEM implementation (attention_bwd.cu)
+int attention_bwd_tc(const void *qkv, int ld, int q_off, int k_off, int v_off, const void *dout, const float *lse,
+                     const float *dsum, void *dqkv, int B, int L, int heads, int d, float scale, int act_dtype, cudaStream_t st);
+
 static int ew_blocks(int64_t n) { return (int)std::min<int64_t>(cdiv64(n, 256), (int64_t)num_sms() * 16); }
 
 }  // namespace b200
@@ -733,10 +802,12 @@ using namespace b200;
     else B200_CHECK(false, "bad act_dtype %d", act_dtype);                   \
   } while (0)
 
-extern "C" int b200_transpose16(const void *src, void *dst, int64_t R, int C, void *stream) {
+extern "C" int b200_transpose16(const void *src, void *dst, float *colsum, int64_t R, int C, int act_dtype, void *stream) {
   B200_CHECK(src && dst && R > 0 && C > 0 && R < (1ll << 31), "transpose16: bad arguments");
   dim3 grid(cdiv(C, 64), (unsigned)cdiv64(R, 64));
-  transpose16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t *)src, (uint16_t *)dst, (int)R, C);
+#define L_(TT, ...) transpose16_kernel<TT><<<grid, 256, 0, (cudaStream_t)stream>>>((const TT *)src, (TT *)dst, colsum, (int)R, C)
+  B200_ACT_DISPATCH(L_, 0);
+#undef L_
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -784,7 +855,7 @@ extern "C" int b200_gated_residual(const void *h_in, const void *f, const float 
 static int rows_per_warp_for(int N, int L) {
   // enough warps to fill the GPU, but long enough runs that the per-(sample, channel) atomics stay cheap
   int rpw = 32;
-  while (rpw > 4 && (int64_t)N * cdiv(L, rpw) < (int64_t)num_sms() * 16) rpw >>= 1;
+  while (rpw > 4 && (int64_t)N * cdiv(L, 8 * rpw) < (int64_t)num_sms() * 4) rpw >>= 1;
   return rpw;
 }
 
@@ -793,10 +864,9 @@ extern "C" int b200_gate_bwd(const void *dh, const void *f, const float *gate, i
   B200_CHECK(dh && f && gate && df && dgate && N > 0 && L > 0 && C % 8 == 0 && C <= kMaxVec * 256,
              "gate_bwd: bad arguments (C <= %d)", kMaxVec * 256);
   const int rpw = rows_per_warp_for(N, L);
-  const int64_t warps = (int64_t)N * cdiv(L, rpw);
-  const int blocks = (int)cdiv64(warps, 8);
+  const int blocks = N * cdiv(L, 8 * rpw);
   const int nv = cdiv(C / 8, 32);
-#define L2_(TT, NV) gate_bwd_kernel<TT, NV><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TT *)dh, (const TT *)f, gate, \
+#define L2_(TT, NV) gate_bwd_kernel<TT, NV><<<blocks, 256, (size_t)C * sizeof(float), (cudaStream_t)stream>>>((const TT *)dh, (const TT *)f, gate, \
       gate_stride, (TT *)df, dgate, dgate_stride, N, L, C, rpw)
 #define L_(TT, ...)                                                                         \
   switch (nv) {                                                                             \
@@ -816,10 +886,9 @@ extern "C" int b200_ln_mod_bwd(const void *x, const void *da, const float *scale
   B200_CHECK(x && da && scale && dx && dshift && dscale && N > 0 && L > 0 && C % 8 == 0 && C <= kMaxVec * 256,
              "ln_mod_bwd: bad arguments (C <= %d)", kMaxVec * 256);
   const int rpw = rows_per_warp_for(N, L);
-  const int64_t warps = (int64_t)N * cdiv(L, rpw);
-  const int blocks = (int)cdiv64(warps, 8);
+  const int blocks = N * cdiv(L, 8 * rpw);
   const int nv = cdiv(C / 8, 32);
-#define L2_(TT, NV) ln_mod_bwd_kernel<TT, NV><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TT *)x, (const TT *)da, scale, \
+#define L2_(TT, NV) ln_mod_bwd_kernel<TT, NV><<<blocks, 256, (size_t)3 * C * sizeof(float), (cudaStream_t)stream>>>((const TT *)x, (const TT *)da, scale, \
       mod_stride, (const TT *)dres, (TT *)dx, dshift, dscale, dmod_stride, N, L, C, eps, rpw)
 #define L_(TT, ...)                                                                         \
   switch (nv) {                                                                             \
@@ -841,6 +910,18 @@ extern "C" int b200_attention_bwd(const void *qkv, int ld, int q_off, int k_off,
   B200_CHECK(ld % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0, "attention_bwd: offsets must be multiples of 8");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t rows = (int64_t)B * L;
+  // default: the tcgen05 kernels (attention_bwd.cu); B200DIFF_ATTN_BWD_WMMA=1 selects the first mma.sync version below
+  // (kept for A/B tests: atomics on an fp32 dQ buffer, 64 x 64 tiles)
+  static const bool use_wmma = getenv("B200DIFF_ATTN_BWD_WMMA") != nullptr && getenv("B200DIFF_ATTN_BWD_WMMA")[0] == '1';
+  if (!use_wmma) {
+    if (act_dtype == B200_F16) attn_bwd_prep_kernel<__half><<<ew_blocks(rows * heads), 256, 0, st>>>(
+        (const __half *)out, (const __half *)dout, dsum_ws, rows, heads, d);
+    else if (act_dtype == B200_BF16) attn_bwd_prep_kernel<__nv_bfloat16><<<ew_blocks(rows * heads), 256, 0, st>>>(
+        (const __nv_bfloat16 *)out, (const __nv_bfloat16 *)dout, dsum_ws, rows, heads, d);
+    else B200_CHECK(false, "attention_bwd: bad act_dtype");
+    B200_LAUNCH_CHECK();
+    return attention_bwd_tc(qkv, ld, q_off, k_off, v_off, dout, lse, dsum_ws, dqkv, B, L, heads, d, scale, act_dtype, st);
+  }
   B200_CUDA(cudaMemsetAsync(dq_ws, 0, (size_t)rows * heads * d * sizeof(float), st));
   const dim3 grid(cdiv(L, 64), heads, B);
 #define LAUNCH_(TT, DD)                                                                                                    \

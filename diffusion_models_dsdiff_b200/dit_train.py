@@ -254,8 +254,7 @@ class DiTTrainer:
         """dy [N, L, O], x [N, L, I] -> accumulates dW, db into the gradient arena, returns dx [N, L, I]."""
         n, l, o = dy.shape
         dy2, x2 = dy.view(n * l, o), x.view(n * l, -1)
-        lin.gw.copy_(T.linear_wgrad(dy2, x2))
-        T.colsum(dy2, lin.gb)
+        T.linear_wgrad(dy2, x2, lin.gb, out=lin.gw)
         return linear_tokens(dy, lin.wt) if need_dx else None
 
     def _backward(self, d_out: Tensor, sv: dict) -> list:
@@ -270,10 +269,9 @@ class DiTTrainer:
         cp, cols = sv["cp"], sv["cols"]
         dtok = T.unpatchify_bwd(d_out, p, cp, dt)                                   # [N, T, cp]
         t_all = dtok.shape[0] * dtok.shape[1]
-        gwf = T.linear_wgrad(dtok.view(t_all, cp), sv["af"].view(t_all, d))         # [cp, d]
-        self._grad_view("final_layer.linear.weight", (cols, d)).copy_(gwf[:cols])
         gbf = torch.zeros(cp, device=dtok.device)
-        T.colsum(dtok.view(t_all, cp), gbf)
+        gwf = T.linear_wgrad(dtok.view(t_all, cp), sv["af"].view(t_all, d), gbf)    # [cp, d]
+        self._grad_view("final_layer.linear.weight", (cols, d)).copy_(gwf[:cols])
         self._grad_view("final_layer.linear.bias", (cols,)).copy_(gbf[:cols])
         daf = linear_tokens(dtok, ops.pack_conv_weight(sv["wfp"].t().contiguous(), dt))     # [N, T, d]
         fo = depth * 6 * d
@@ -301,10 +299,10 @@ class DiTTrainer:
             self._reduce(self.block_ranges[i], handles)        # bucket complete: overlap its all-reduce with the rest
         # patch embedding: h = tok W^T + b + pos
         t_all = dh_.shape[0] * dh_.shape[1]
-        gpe = T.linear_wgrad(dh_.view(t_all, d), sv["tok"].view(t_all, -1))        # [d, kpad]
+        gpe = T.linear_wgrad(dh_.view(t_all, d), sv["tok"].view(t_all, -1),
+                             self._grad_view("x_embedder.proj.bias", (d,)))        # [d, kpad]
         k = sv["k"]
         self._grad_view("x_embedder.proj.weight", (d, k)).copy_(gpe[:, :k])
-        T.colsum(dh_.view(t_all, d), self._grad_view("x_embedder.proj.bias", (d,)))
         # conditioning path: final adaLN projection, then mod -> c -> TimestepEmbedder MLP
         pre = "final_layer.adaLN_modulation.1"
         T.linear_f32_wgrad(dmod[:, fo:fo + 2 * d], sv["c"], self._grad_view(pre + ".weight", (2 * d, d)),

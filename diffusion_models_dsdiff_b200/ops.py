@@ -179,8 +179,11 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
     if head_channels:      # network head: fp32 NCHW output of the first head_channels (zero-padded N tile)
         out = torch.empty((n, head_channels, hout, wout), device=src0.device, dtype=torch.float32)
         d.out_nchw_f32, d.cout_real = _p(out), head_channels
-    elif out_f32:          # fp32 NHWC result (attention logits)
-        out = torch.empty((n, hout, wout, cout), device=src0.device, dtype=torch.float32)
+    elif out_f32:          # fp32 NHWC result (attention logits; weight gradients)
+        if out is None:
+            out = torch.empty((n, hout, wout, cout), device=src0.device, dtype=torch.float32)
+        elif out.dtype != torch.float32 or out.numel() != n * hout * wout * cout:
+            raise L.B200Error("conv2d: fp32 out shape/dtype mismatch")
         d.out_nhwc_f32 = _p(out)
     elif out is None:
         out = torch.empty((n, hout, wout, cout), device=src0.device, dtype=src0.dtype)

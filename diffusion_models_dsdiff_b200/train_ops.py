@@ -17,13 +17,16 @@ from .ops import _dev, _f32, _p, _stream, _timed, act_code
 Tensor = torch.Tensor
 
 
-def transpose16(x: Tensor) -> Tensor:
-    """[R, C] 16-bit -> [C, R]."""
+def transpose16(x: Tensor, colsum_out: Optional[Tensor] = None) -> Tensor:
+    """[R, C] 16-bit -> [C, R]; ``colsum_out`` (fp32 [C], overwritten): the column sums of ``x`` from the same pass."""
     _dev(x)
     r, c = x.shape
     out = torch.empty((c, r), device=x.device, dtype=x.dtype)
+    if colsum_out is not None:
+        colsum_out.zero_()
     _timed("transpose16", 0.0, 4.0 * x.numel(),
-           lambda: L.check(L.lib().b200_transpose16(_p(x), _p(out), r, c, _stream()), "transpose16"))
+           lambda: L.check(L.lib().b200_transpose16(_p(x), _p(out), _p(_f32(colsum_out)), r, c, act_code(x.dtype), _stream()),
+                           "transpose16"))
     return out
 
 
@@ -206,10 +209,11 @@ def wgrad_split(o: int, i: int, t: int) -> int:
     return max(1, min(s, t // 512))
 
 
-def linear_wgrad(dy: Tensor, x: Tensor) -> Tensor:
-    """dW [O, I] fp32 = dy^T x for token-major dy [T, O], x [T, I] (16-bit).  T, O, I multiples of 8."""
+def linear_wgrad(dy: Tensor, x: Tensor, db: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
+    """dW [O, I] fp32 = dy^T x for token-major dy [T, O], x [T, I] (16-bit).  T, O, I multiples of 8.
+    ``db`` (fp32 [O], overwritten): the bias gradient sum_t dy[t], fused into dy's transpose pass."""
     t, o = dy.shape
     i = x.shape[1]
-    dyt, xt = transpose16(dy), transpose16(x)                   # K-major rows: [O, T], [I, T]
-    out = ops.conv2d([(_img(dyt), xt.view(1, i, t), 0, 1, 0)], out_f32=True, force_ksplit=wgrad_split(o, i, t))
-    return out.view(o, i)
+    dyt, xt = transpose16(dy, db), transpose16(x)               # K-major rows: [O, T], [I, T]
+    res = ops.conv2d([(_img(dyt), xt.view(1, i, t), 0, 1, 0)], out_f32=True, force_ksplit=wgrad_split(o, i, t), out=out)
+    return res.view(o, i)

@@ -330,8 +330,9 @@ int b200_advance_step(int *step_ptr, int delta, void *stream);
  * with a transposed packed weight; wgrad with both operands transposed to K-major by b200_transpose16 and force_ksplit).
  * The reference gets all of this from torch autograd (loss.backward(), trainers/trainer_use_gaussian_diff.py:464-478) over
  * UNet_DS_Diff/DiT_models.py:101-142 and training_project/utils/gaussian_diffusion.py:824-983.                          */
-/* dst[C, R] = src[R, C]^T, 16-bit elements */
-int b200_transpose16(const void *src, void *dst, int64_t R, int C, void *stream);
+/* dst[C, R] = src[R, C]^T, 16-bit elements; colsum (may be NULL): fp32 [C], += sum_r src[r, c] (zero it first) — the bias
+ * gradient of the tensor the weight-gradient GEMM needs transposed anyway */
+int b200_transpose16(const void *src, void *dst, float *colsum, int64_t R, int C, int act_dtype, void *stream);
 /* out[c] += sum_r x[r, c]  (bias gradients; fp32, zero `out` first) */
 int b200_colsum16(const void *x, float *out, int64_t R, int C, int act_dtype, void *stream);
 /* GELU(tanh) on a stored pre-activation, and its backward dpre = du * gelu'(pre)  (timm Mlp, DiT_models.py:111-112) */
