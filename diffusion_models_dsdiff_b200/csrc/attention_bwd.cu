@@ -12,15 +12,16 @@
 // (attention.cu): operands staged by TMA as UN-SWIZZLED 8 x 16-byte core matrices, one box of (8 channels x 128 tokens)
 // per 16-byte channel block — that one shared-memory image serves as a K-major operand when the contraction runs over
 // channels (S, dP) and as an MN-major operand when it runs over tokens (dV, dK, dQ), so nothing is ever transposed;
-// warp 0 = TMA producer, warp 1 = single-thread MMA issuer + TMEM owner, warps 2-9 = the element-wise stage
-// (thread = (query row, 64-column half)): tcgen05.ld S and dP -> registers, hand the TMEM buffers back at once so the
-// next tile's S / dP overlap the exponentials, write P and dS as 16-bit operand tiles to shared memory.
+// warp 0 = TMA producer, warp 1 = single-thread MMA issuer + TMEM owner, warps 2-17 = the element-wise stage
+// (thread = (query row, 32-column quarter)): tcgen05.ld S and dP -> registers, hand the TMEM buffers back at once so the
+// next tile's S / dP MMAs overlap the exponentials; P and dS are computed and packed in registers BEFORE waiting for the
+// previous tile's dV / dK / dQ MMAs to release the operand tiles, so those MMAs overlap this tile's arithmetic too.
 // TMEM columns: S 128 | dP 128 | accumulator 0 (D) | accumulator 1 (D).
 #include "common.cuh"
 
 namespace b200 {
 
-constexpr int kBwThreads = 320;
+constexpr int kBwThreads = 576;                          // warp 0 TMA, warp 1 MMA, warps 2-17 element-wise
 constexpr int kBwT = 128;                                // tokens per tile (both queries and keys)
 constexpr uint32_t kBwBlk = 128 * 16;                    // one (8 channels x 128 tokens) TMA box = 2048 B
 constexpr uint32_t kBwPBytes = kBwT * kBwT * 2;          // a 128 x 128 16-bit operand tile (P or dS)
@@ -38,6 +39,7 @@ struct BwParams {
   const float *dsum;            // [B, L, heads]
   void *dqkv;
   uint32_t idesc_s, idesc_acc;
+  int debug;                    // B200DIFF_DEBUG_TOGGLES builds only: timing experiments (results are garbage)
 };
 
 __device__ __forceinline__ float bw_ex2(float x) {
@@ -51,9 +53,15 @@ __global__ void __launch_bounds__(kBwThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ BwMaps maps, const BwParams p) {
   constexpr int kDB = D / 8;
   constexpr uint32_t kTile = kDB * kBwBlk;               // a [128 tokens x D] operand tile
+  // D == 64: a token row is exactly one 128-byte swizzle row, so each Q / K / V / dO tile is ONE TMA box of (64 channels x
+  // 128 tokens) with SWIZZLE_128B — 128 row fetches of 128 B instead of 1024 fetches of 16 B.  The same shared-memory
+  // image is the canonical K-major SW128 tile (rows = tokens = M/N, 128 B = 64 K elements) AND the canonical MN-major SW128
+  // tile (rows = tokens = K, 128 B = 64 MN elements; 8-row atoms 1024 B apart along K).
+  constexpr bool kSw = (D == 64);
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t res_full, acc_full, s_full, s_empty, p_full, p_empty;
-  __shared__ __align__(8) uint64_t str_full[2], str_empty[2];
+  constexpr int NS = kDQ ? 4 : 3;                        // stages of the streamed pair (TMA latency is the loop's critical path)
+  __shared__ __align__(8) uint64_t str_full[NS], str_empty[NS];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -61,10 +69,10 @@ attn_bwd_tc_kernel(const __grid_constant__ BwMaps maps, const BwParams p) {
   const int h = blockIdx.y, b = blockIdx.z;
   const int n_it = (p.L + kBwT - 1) / kBwT;
 
-  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t sRes0 = base, sRes1 = base + kTile;     // resident pair: (K, V) or (Q, dO)
   const uint32_t sStr = sRes1 + kTile;                   // streamed pair x 2 stages: (Q, dO) or (K, V)
-  const uint32_t sdS = sStr + 4 * kTile;
+  const uint32_t sdS = sStr + 2 * NS * kTile;
   const uint32_t sP = sdS + kBwPBytes;                   // only when !kDQ
 
   if (threadIdx.x == 0) {
@@ -72,10 +80,10 @@ attn_bwd_tc_kernel(const __grid_constant__ BwMaps maps, const BwParams p) {
     mbar_init(smem_u32(&res_full), 1);
     mbar_init(smem_u32(&acc_full), 1);
     mbar_init(smem_u32(&s_full), 1);
-    mbar_init(smem_u32(&s_empty), 8);
-    mbar_init(smem_u32(&p_full), 8);
+    mbar_init(smem_u32(&s_empty), 16);
+    mbar_init(smem_u32(&p_full), 16);
     mbar_init(smem_u32(&p_empty), 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&str_full[i]), 1); mbar_init(smem_u32(&str_empty[i]), 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&str_full[i]), 1); mbar_init(smem_u32(&str_empty[i]), 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 512);
@@ -93,7 +101,7 @@ attn_bwd_tc_kernel(const __grid_constant__ BwMaps maps, const BwParams p) {
       {
         const uint32_t bar = smem_u32(&res_full);
         mbar_arrive_expect_tx(bar, 2 * kTile);
-        for (int c = 0; c < kDB; ++c) {
+        for (int c = 0; c < (kSw ? 1 : kDB); ++c) {
           if (kDQ) {
             tma_load_3d(sRes0 + c * kBwBlk, &maps.qkv, bar, qc + c * 8, t0, b);
             tma_load_3d(sRes1 + c * kBwBlk, &maps.dout, bar, oc + c * 8, t0, b);
@@ -104,12 +112,12 @@ attn_bwd_tc_kernel(const __grid_constant__ BwMaps maps, const BwParams p) {
         }
       }
       for (int it = 0; it < n_it; ++it) {
-        const int st = it & 1;
-        mbar_wait(smem_u32(&str_empty[st]), ((it >> 1) & 1) ^ 1);
+        const int st = it % NS;
+        mbar_wait(smem_u32(&str_empty[st]), ((it / NS) & 1) ^ 1);
         const uint32_t bar = smem_u32(&str_full[st]);
         mbar_arrive_expect_tx(bar, 2 * kTile);
         const uint32_t d0 = sStr + st * 2 * kTile, d1 = d0 + kTile;
-        for (int c = 0; c < kDB; ++c) {
+        for (int c = 0; c < (kSw ? 1 : kDB); ++c) {
           if (kDQ) {
             tma_load_3d(d0 + c * kBwBlk, &maps.qkv, bar, kc + c * 8, it * kBwT, b);
             tma_load_3d(d1 + c * kBwBlk, &maps.qkv, bar, vc + c * 8, it * kBwT, b);
@@ -127,50 +135,60 @@ attn_bwd_tc_kernel(const __grid_constant__ BwMaps maps, const BwParams p) {
       mbar_wait(smem_u32(&res_full), 0);
       // S = Q K^T and dP = dO V^T of tile `g`: contraction over the D channels, every operand K-major
       auto issue_first = [&](int g) {
-        const int st = g & 1;
-        mbar_wait(smem_u32(&str_full[st]), (g >> 1) & 1);
+        const int st = g % NS;
+        mbar_wait(smem_u32(&str_full[st]), (g / NS) & 1);
         mbar_wait(smem_u32(&s_empty), (g & 1) ^ 1);
         tc_fence_after();
         const uint32_t x0 = sStr + st * 2 * kTile, x1 = x0 + kTile;
         const uint32_t aQ = kDQ ? sRes0 : x0, bK = kDQ ? x0 : sRes0;
         const uint32_t aO = kDQ ? sRes1 : x1, bV = kDQ ? x1 : sRes1;
+        // 16 channels per instruction: two un-swizzled core-matrix columns (+2 boxes), or +32 B inside the swizzled row
+        auto kdesc = [&](uint32_t tile, int kk) -> uint64_t {
+          return kSw ? umma_desc_sw128(tile) + (uint64_t)(kk * 2) : umma_desc_nosw(tile + kk * 2 * kBwBlk, kBwBlk, 128);
+        };
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)
-          umma_f16(tmem_s, umma_desc_nosw(aQ + kk * 2 * kBwBlk, kBwBlk, 128), umma_desc_nosw(bK + kk * 2 * kBwBlk, kBwBlk, 128),
-                   p.idesc_s, kk > 0);
+        for (int kk = 0; kk < D / 16; ++kk) umma_f16(tmem_s, kdesc(aQ, kk), kdesc(bK, kk), p.idesc_s, kk > 0);
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)
-          umma_f16(tmem_dp, umma_desc_nosw(aO + kk * 2 * kBwBlk, kBwBlk, 128), umma_desc_nosw(bV + kk * 2 * kBwBlk, kBwBlk, 128),
-                   p.idesc_s, kk > 0);
+        for (int kk = 0; kk < D / 16; ++kk) umma_f16(tmem_dp, kdesc(aO, kk), kdesc(bV, kk), p.idesc_s, kk > 0);
         umma_commit(smem_u32(&s_full));
       };
       issue_first(0);
       for (int it = 0; it < n_it; ++it) {
         if (it + 1 < n_it) issue_first(it + 1);          // runs while the element-wise warps work on tile `it`
-        const int st = it & 1;
+        const int st = it % NS;
         mbar_wait(smem_u32(&p_full), it & 1);
         tc_fence_after();
         const uint32_t x0 = sStr + st * 2 * kTile, x1 = x0 + kTile;
         const uint32_t acc = (it > 0) ? 1u : 0u;
+        // B operand read MN-major over 16 tokens: un-swizzled core matrices 128 B apart along K (tokens), 2048 B along N
+        // (+256 B per 16 tokens); swizzled: 8-token atoms 1024 B apart (+2048 B per 16 tokens)
+        auto mndesc = [&](uint32_t tile, int kk) -> uint64_t {
+          return kSw ? umma_desc_sw128(tile + kk * 2048) : umma_desc_nosw(tile + kk * 256, 128, kBwBlk);
+        };
+#ifdef B200DIFF_DEBUG_TOGGLES
+        if (p.debug & 8) {
+          umma_commit(smem_u32(&str_empty[st]));
+          umma_commit(smem_u32(&p_empty));
+          continue;
+        }
+#endif
         if (!kDQ) {
           // dV += P^T dO, dK += dS^T Q: contraction over the 128 QUERIES.  A = P / dS tile [key block][query][8 keys] read
           // MN-major (8 keys contiguous, queries 16 B apart: core matrices 128 B apart along K, 2048 B along M);
           // B = dO / Q tile [channel block][query][8 ch] read MN-major.  16 queries per instruction = +256 B.
 #pragma unroll
           for (int kk = 0; kk < kBwT / 16; ++kk)
-            umma_f16(tmem_a0, umma_desc_nosw(sP + kk * 256, 128, kBwBlk), umma_desc_nosw(x1 + kk * 256, 128, kBwBlk),
-                     p.idesc_acc, acc | (uint32_t)(kk > 0));
+            umma_f16(tmem_a0, umma_desc_nosw(sP + kk * 256, 128, kBwBlk), mndesc(x1, kk), p.idesc_acc, acc | (uint32_t)(kk > 0));
 #pragma unroll
           for (int kk = 0; kk < kBwT / 16; ++kk)
-            umma_f16(tmem_a1, umma_desc_nosw(sdS + kk * 256, 128, kBwBlk), umma_desc_nosw(x0 + kk * 256, 128, kBwBlk),
-                     p.idesc_acc, acc | (uint32_t)(kk > 0));
+            umma_f16(tmem_a1, umma_desc_nosw(sdS + kk * 256, 128, kBwBlk), mndesc(x0, kk), p.idesc_acc, acc | (uint32_t)(kk > 0));
         } else {
           // dQ += dS K: contraction over the 128 KEYS.  A = dS tile read K-major (16 keys = 2 key blocks = +4096 B);
           // B = K tile [channel block][key][8 ch] read MN-major (+256 B per 16 keys).
 #pragma unroll
           for (int kk = 0; kk < kBwT / 16; ++kk)
-            umma_f16(tmem_a0, umma_desc_nosw(sdS + kk * 2 * kBwBlk, kBwBlk, 128), umma_desc_nosw(x0 + kk * 256, 128, kBwBlk),
-                     p.idesc_acc, acc | (uint32_t)(kk > 0));
+            umma_f16(tmem_a0, umma_desc_nosw(sdS + kk * 2 * kBwBlk, kBwBlk, 128), mndesc(x0, kk), p.idesc_acc,
+                     acc | (uint32_t)(kk > 0));
         }
         umma_commit(smem_u32(&str_empty[st]));
         umma_commit(smem_u32(&p_empty));
@@ -179,11 +197,11 @@ attn_bwd_tc_kernel(const __grid_constant__ BwMaps maps, const BwParams p) {
     }
     __syncwarp();
   } else {
-    // ===================== element-wise warps: thread == (query row, 64-column half of the key tile) =====================
+    // ===================== element-wise warps: thread == (query row, 32-column quarter of the key tile) ===============
     const int lane_base = 32 * (warp & 3);
     const int row = lane_base + lane;
-    const int half = (warp - 2) >> 2;
-    const int cbase = half * 64;
+    const int quarter = (warp - 2) >> 2;
+    const int cbase = quarter * 32;
     const uint32_t t_lane = (uint32_t)lane_base << 16;
     const float log2e = 1.4426950408889634f;
     float lse2 = 0.f, dsm = 0.f;
@@ -196,65 +214,101 @@ attn_bwd_tc_kernel(const __grid_constant__ BwMaps maps, const BwParams p) {
     }
     uint8_t *srow_ds = smem_raw + (sdS - smem_u32(smem_raw)) + row * 16;
     uint8_t *srow_p = smem_raw + (sP - smem_u32(smem_raw)) + row * 16;
+    // per-row scalars of the NEXT query tile are fetched one iteration ahead (their global-load latency would otherwise sit
+    // between the accumulator wait and the arithmetic of every tile)
+    float lse_n = 0.f, dsm_n = 0.f;
+    auto fetch_row = [&](int qi, float &l2, float &dm) {
+      l2 = 0.f; dm = 0.f;
+      if (qi < p.L) {
+        l2 = __ldg(p.lse + ((size_t)b * p.heads + h) * p.L + qi) * log2e;
+        dm = __ldg(p.dsum + ((size_t)b * p.L + qi) * p.heads + h);
+      }
+    };
+    if (!kDQ) fetch_row(row, lse_n, dsm_n);
     for (int it = 0; it < n_it; ++it) {
       if (!kDQ) {
-        const int qi = it * kBwT + row;
-        lse2 = 0.f; dsm = 0.f;
-        if (qi < p.L) {
-          lse2 = p.lse[((size_t)b * p.heads + h) * p.L + qi] * log2e;
-          dsm = p.dsum[((size_t)b * p.L + qi) * p.heads + h];
-        }
+        lse2 = lse_n; dsm = dsm_n;
+        if (it + 1 < n_it) fetch_row((it + 1) * kBwT + row, lse_n, dsm_n);
       }
+      const float dsm_s = dsm * p.scale;
       mbar_wait(smem_u32(&s_full), it & 1);
       tc_fence_after();
-      uint32_t s0[32], s1[32], d0[32], d1[32];
-      tmem_ld32(tmem_s + t_lane + cbase, s0);
-      tmem_ld32(tmem_s + t_lane + cbase + 32, s1);
-      tmem_ld32(tmem_dp + t_lane + cbase, d0);
-      tmem_ld32(tmem_dp + t_lane + cbase + 32, d1);
-      tmem_ld_wait();
+      uint32_t sr[32], dr[32];
+#ifdef B200DIFF_DEBUG_TOGGLES
+      if (p.debug & 4) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { sr[i] = 0; dr[i] = 0; }
+      } else
+#endif
+      {
+        tmem_ld32(tmem_s + t_lane + cbase, sr);
+        tmem_ld32(tmem_dp + t_lane + cbase, dr);
+        tmem_ld_wait();
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_empty));    // S / dP are in registers: the next tile's MMAs may overwrite them
-      // the previous tile's dV / dK / dQ MMAs must have finished reading the operand tiles before they are rewritten
-      mbar_wait(smem_u32(&p_empty), (it & 1) ^ 1);
       // keys past the end of the sequence (zero-filled by TMA) contribute nothing, but exp2(-lse) of their zero scores may
       // overflow the 16-bit range: mask them
       const int nvalid = min(kBwT, p.L - (kDQ ? it * kBwT : t0));
+      uint4 pk_p[4], pk_s[4];
+      if (nvalid == kBwT) {                              // every tile but (possibly) the last: no column masks
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        const uint32_t (&sr)[32] = c0 ? s1 : s0;
-        const uint32_t (&dr)[32] = c0 ? d1 : d0;
+        for (int v8 = 0; v8 < 4; ++v8) {
+          float pv[8], ds[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+#ifdef B200DIFF_DEBUG_TOGGLES
+            if (p.debug & 1) pv[i] = fmaf(__uint_as_float(sr[v8 * 8 + i]), p.scale_log2e, -lse2);
+            else
+#endif
+            pv[i] = bw_ex2(fmaf(__uint_as_float(sr[v8 * 8 + i]), p.scale_log2e, -lse2));
+            ds[i] = pv[i] * fmaf(__uint_as_float(dr[v8 * 8 + i]), p.scale, -dsm_s);
+          }
+          pk_s[v8] = pack8_fast<T>(ds);
+          if (!kDQ) pk_p[v8] = pack8_fast<T>(pv);
+        }
+      } else {
 #pragma unroll
         for (int v8 = 0; v8 < 4; ++v8) {
           float pv[8], ds[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             pv[i] = bw_ex2(fmaf(__uint_as_float(sr[v8 * 8 + i]), p.scale_log2e, -lse2));
-            if (nvalid < kBwT && cbase + c0 + v8 * 8 + i >= nvalid) pv[i] = 0.f;
-            ds[i] = pv[i] * (__uint_as_float(dr[v8 * 8 + i]) - dsm) * p.scale;
+            if (cbase + v8 * 8 + i >= nvalid) pv[i] = 0.f;
+            ds[i] = pv[i] * fmaf(__uint_as_float(dr[v8 * 8 + i]), p.scale, -dsm_s);
           }
-          const uint32_t off = (((cbase + c0) >> 3) + v8) * kBwBlk;
-          *reinterpret_cast<uint4 *>(srow_ds + off) = pack8<T>(ds);
-          if (!kDQ) *reinterpret_cast<uint4 *>(srow_p + off) = pack8<T>(pv);
+          pk_s[v8] = pack8<T>(ds);
+          if (!kDQ) pk_p[v8] = pack8<T>(pv);
         }
+      }
+      // the previous tile's dV / dK / dQ MMAs must have finished reading the operand tiles before they are rewritten
+      mbar_wait(smem_u32(&p_empty), (it & 1) ^ 1);
+#ifdef B200DIFF_DEBUG_TOGGLES
+      if (!(p.debug & 2) || (pk_s[0].x == 0x12345678u && pk_p[0].x == 0x9abcdef0u))
+#endif
+#pragma unroll
+      for (int v8 = 0; v8 < 4; ++v8) {
+        const uint32_t off = ((cbase >> 3) + v8) * kBwBlk;
+        *reinterpret_cast<uint4 *>(srow_ds + off) = pk_s[v8];
+        if (!kDQ) *reinterpret_cast<uint4 *>(srow_p + off) = pk_p[v8];
       }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&p_full));
     }
-    // epilogue: accumulators -> dqkv (16-bit); the halves split the D channels
+    // epilogue: accumulators -> dqkv (16-bit); the quarters split the D channels
     mbar_wait(smem_u32(&acc_full), 0);
     tc_fence_after();
-    constexpr int kHalfD = D / 2;
+    constexpr int kQD = D / 4;                           // 8 or 16 channels per quarter
     const int ti = t0 + row;
-    T *orow = reinterpret_cast<T *>(p.dqkv) + ((size_t)b * p.L + ti) * p.ld + h * D + half * kHalfD;
+    T *orow = reinterpret_cast<T *>(p.dqkv) + ((size_t)b * p.L + ti) * p.ld + h * D + quarter * kQD;
 #pragma unroll
-    for (int c0 = 0; c0 < kHalfD; c0 += 8) {
+    for (int c0 = 0; c0 < kQD; c0 += 8) {
       uint32_t r0[8], r1[8];
-      tmem_ld8(tmem_a0 + t_lane + half * kHalfD + c0, r0);
-      if (!kDQ) tmem_ld8(tmem_a1 + t_lane + half * kHalfD + c0, r1);
+      tmem_ld8(tmem_a0 + t_lane + quarter * kQD + c0, r0);
+      if (!kDQ) tmem_ld8(tmem_a1 + t_lane + quarter * kQD + c0, r1);
       tmem_ld_wait();
       if (ti < p.L) {
         float f[8];
@@ -286,19 +340,20 @@ static int launch_bwd_tc(const void *qkv, int ld, int q_off, int k_off, int v_of
   {
     uint64_t dims[3] = {(uint64_t)ld, (uint64_t)L, (uint64_t)B};
     uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)L * ld * 2};
-    uint32_t box[3] = {8, 128, 1}, es[3] = {1, 1, 1};
-    if (int rc = cached_tmap(&maps.qkv, qkv, 3, dims, str, box, es, /*swizzle128=*/false)) return rc;
+    uint32_t box[3] = {(uint32_t)(D == 64 ? 64 : 8), 128, 1}, es[3] = {1, 1, 1};
+    if (int rc = cached_tmap(&maps.qkv, qkv, 3, dims, str, box, es, /*swizzle128=*/D == 64)) return rc;
   }
   {
     const int ldo = heads * D;
     uint64_t dims[3] = {(uint64_t)ldo, (uint64_t)L, (uint64_t)B};
     uint64_t str[2] = {(uint64_t)ldo * 2, (uint64_t)L * ldo * 2};
-    uint32_t box[3] = {8, 128, 1}, es[3] = {1, 1, 1};
-    if (int rc = cached_tmap(&maps.dout, dout, 3, dims, str, box, es, /*swizzle128=*/false)) return rc;
+    uint32_t box[3] = {(uint32_t)(D == 64 ? 64 : 8), 128, 1}, es[3] = {1, 1, 1};
+    if (int rc = cached_tmap(&maps.dout, dout, 3, dims, str, box, es, /*swizzle128=*/D == 64)) return rc;
   }
   p.L = L; p.heads = heads; p.q_off = q_off; p.k_off = k_off; p.v_off = v_off; p.ld = ld;
   p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
   p.lse = lse; p.dsum = dsum; p.dqkv = dqkv;
+  p.debug = getenv("B200DIFF_ABW_DEBUG") ? atoi(getenv("B200DIFF_ABW_DEBUG")) : 0;
   p.idesc_s = umma_idesc(Act<T>::kFmt, 128, 128, 0);
   const size_t tile = (size_t)D * 256;
   const dim3 grid(cdiv(L, kBwT), heads, B);
@@ -310,11 +365,11 @@ static int launch_bwd_tc(const void *qkv, int ld, int q_off, int k_off, int v_of
   }
   // dK, dV: both second-stage operands MN-major (a_major bit 15, b_major bit 16)
   p.idesc_acc = umma_idesc(Act<T>::kFmt, 128, D, 1) | (1u << 15);
-  attn_bwd_tc_kernel<T, D, false><<<grid, kBwThreads, tile * 6 + 2 * kBwPBytes + 256, st>>>(maps, p);
+  attn_bwd_tc_kernel<T, D, false><<<grid, kBwThreads, tile * (2 + 2 * 3) + 2 * kBwPBytes + 1024, st>>>(maps, p);
   B200_LAUNCH_CHECK();
   // dQ: A = dS K-major, B = K MN-major
   p.idesc_acc = umma_idesc(Act<T>::kFmt, 128, D, 1);
-  attn_bwd_tc_kernel<T, D, true><<<grid, kBwThreads, tile * 6 + kBwPBytes + 256, st>>>(maps, p);
+  attn_bwd_tc_kernel<T, D, true><<<grid, kBwThreads, tile * (2 + 2 * 4) + kBwPBytes + 1024, st>>>(maps, p);
   B200_LAUNCH_CHECK();
   return 0;
 }
