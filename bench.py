@@ -79,7 +79,7 @@ NAMES = {"cfg2": "DSUnetModel 320-ch (configs/v2-1-cddpm-ds-disc.yaml) 256x256 D
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 3; cfg5: 20)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=["cfg1", "cfg2", "cfg5"])
@@ -883,6 +883,8 @@ def run_reference_cfg5(args):
 
 def main():
     args = parse()
+    if args.steps is None:
+        args.steps = 20 if args.workload == "cfg5" and args.impl != "reference" else 3
     if args.workload == "cfg5":
         (run_reference_cfg5 if args.impl == "reference" else run_cfg5)(args)
         return

@@ -44,6 +44,30 @@ class _Lin:
     __slots__ = ("w", "wt", "b", "gw", "gb", "o", "i")
 
 
+def arena_layout(named_shapes, depth: int):
+    """Flat-arena placement of the trainable parameters (in ``named_parameters`` order, 32-byte aligned slots) and the
+    gradient all-reduce buckets: one per DiTBlock — its parameters are contiguous — plus everything before / after the blocks.
+    ``named_shapes``: [(name, numel)].  Returns (slots {name: slice}, total, block_ranges, head_range, tail_range)."""
+    slots: Dict[str, slice] = {}
+    off = 0
+    for k, numel in named_shapes:
+        slots[k] = slice(off, off + numel)
+        off += -(-numel // 8) * 8
+    total = off
+    block_ranges: List[slice] = []
+    for i in range(depth):
+        ks = [k for k in slots if k.startswith(f"blocks.{i}.")]
+        block_ranges.append(slice(min(slots[k].start for k in ks), max(slots[k].stop for k in ks)))
+    return slots, total, block_ranges, slice(0, block_ranges[0].start), slice(block_ranges[-1].stop, total)
+
+
+def reduce_bucket(flat_g: Tensor, rng: slice, group, handles: list) -> None:
+    """Asynchronous SUM all-reduce of one contiguous gradient bucket (issued as soon as the bucket is complete; the caller
+    waits on the handles before the optimizer step; AdamW divides by the world size)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 and rng.stop > rng.start:
+        handles.append(dist.all_reduce(flat_g[rng], group=group, async_op=True))
+
+
 class DiTTrainer:
     def __init__(self, model: DiT, diffusion, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-2, parameterization: Optional[str] = None, rescaled_mse: bool = False,
@@ -71,29 +95,17 @@ class DiTTrainer:
         # y_embedder is never reached when y is None (the reference's configuration): torch leaves its .grad None and
         # AdamW skips it — so it stays out of the arenas instead of being weight-decayed with a zero gradient
         named = [(k, p) for k, p in model.named_parameters() if p.requires_grad and not k.startswith("y_embedder.")]
-        sizes = [(-(-p.numel() // 8) * 8) for _, p in named]              # 32-byte aligned slots
-        total = int(sum(sizes))
+        self.slots, total, self.block_ranges, self.head_range, self.tail_range = arena_layout(
+            [(k, p.numel()) for k, p in named], len(model.blocks))
         self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros_like(self.flat_p)
         self.flat_m = torch.zeros_like(self.flat_p)
         self.flat_v = torch.zeros_like(self.flat_p)
-        self.slots: Dict[str, slice] = {}
-        off = 0
         with torch.no_grad():
-            for (k, p), sz in zip(named, sizes):
-                view = self.flat_p[off:off + p.numel()].view_as(p)
+            for k, p in named:
+                view = self.flat_p[self.slots[k]].view_as(p)
                 view.copy_(p.detach().float())
                 p.data = view
-                self.slots[k] = slice(off, off + p.numel())
-                off += sz
-        # buckets for the gradient all-reduce: one per DiTBlock (contiguous in the arena), one for everything before the
-        # blocks, one for everything after them
-        self.block_ranges: List[slice] = []
-        for i in range(len(model.blocks)):
-            ks = [k for k in self.slots if k.startswith(f"blocks.{i}.")]
-            self.block_ranges.append(slice(min(self.slots[k].start for k in ks), max(self.slots[k].stop for k in ks)))
-        self.head_range = slice(0, self.block_ranges[0].start)
-        self.tail_range = slice(self.block_ranges[-1].stop, total)
         self.last_terms: Optional[Tensor] = None
 
     # -- helpers -------------------------------------------------------------------------------
@@ -181,8 +193,7 @@ class DiTTrainer:
         return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
 
     def _reduce(self, rng: slice, handles: list) -> None:
-        if self._distributed() and rng.stop > rng.start:
-            handles.append(dist.all_reduce(self.flat_g[rng], group=self.group, async_op=True))
+        reduce_bucket(self.flat_g, rng, self.group, handles)
 
     # -- forward with saved activations --------------------------------------------------------
     def _forward(self, x: Tensor, t_model: Tensor):

@@ -145,3 +145,66 @@ def test_sharded_volume_to_nifti_end_to_end(tmp_path):
     vol, hdr = V.read_nifti(os.path.join(odir, "P7_pred.nii.gz"))
     assert hdr.shape == (7, 24, 24)
     assert np.array_equal(vol, single[:, 0].numpy())
+
+
+# -------------------------------------------------------------------------------------------------
+# cfg5: gradient arena layout + bucketed all-reduce of the DiT trainer (gloo, world size 2)
+# -------------------------------------------------------------------------------------------------
+def _dit_named_shapes():
+    import diffusion_models_dsdiff_b200 as P
+    with torch.device("meta"):
+        net = P.DiT(input_size=16, patch_size=2, in_channels=4, hidden_size=64, depth=3, num_heads=2, learn_sigma=True)
+    return [(k, p.numel()) for k, p in net.named_parameters() if p.requires_grad and not k.startswith("y_embedder.")]
+
+
+def test_trainer_arena_layout_buckets_cover_the_arena_once():
+    from diffusion_models_dsdiff_b200.dit_train import arena_layout
+    named = _dit_named_shapes()
+    slots, total, blocks, head, tail = arena_layout(named, 3)
+    assert total % 8 == 0 and all(s.start % 8 == 0 for s in slots.values())
+    order = [head] + blocks + [tail]
+    assert order[0].start == 0 and order[-1].stop == total
+    for a, b in zip(order, order[1:]):
+        assert a.stop == b.start                                    # contiguous, non-overlapping, in backward-friendly order
+    for k, sl in slots.items():                                      # every parameter lies inside exactly one bucket
+        owner = [r for r in order if r.start <= sl.start and sl.stop <= r.stop]
+        assert len(owner) == 1, k
+        if k.startswith("blocks.1."):
+            assert owner[0] is blocks[1]
+
+
+def _bucket_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from diffusion_models_dsdiff_b200.dit_train import arena_layout, reduce_bucket
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        slots, total, blocks, head, tail = arena_layout(_dit_named_shapes(), 3)
+        g = torch.Generator().manual_seed(rank)
+        flat = torch.randn(total, generator=g)
+        mine = flat.clone()
+        handles = []
+        for r in reversed(blocks):                                   # the order the backward completes them
+            reduce_bucket(flat, r, None, handles)
+        reduce_bucket(flat, head, None, handles)
+        reduce_bucket(flat, tail, None, handles)
+        for h in handles:
+            h.wait()
+        other = torch.randn(total, generator=torch.Generator().manual_seed(1 - rank))
+        q.put((rank, len(handles), float((flat - (mine + other)).abs().max())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_trainer_bucketed_allreduce_sums_every_gradient_once():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    for rank, n_handles, err in res:
+        assert n_handles == 5 and err < 1e-6, (rank, n_handles, err)
