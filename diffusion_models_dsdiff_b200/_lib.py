@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200diff.so")
 
-ABI_VERSION = 11        # must equal B200_ABI_VERSION of the header the library was built from
+ABI_VERSION = 12        # must equal B200_ABI_VERSION of the header the library was built from
 F16, BF16 = 0, 1
 SAMPLER_LDM_DDIM, SAMPLER_LDM_DDPM, SAMPLER_GD_DDIM, SAMPLER_GD_DDPM, SAMPLER_DPMPP_2M = 0, 1, 2, 3, 4
 SAMPLER_NCOEF = 16
@@ -25,7 +25,7 @@ class B200Error(RuntimeError):
 
 class ConvSeg(C.Structure):
     _fields_ = [("src", C.c_void_p), ("weight", C.c_void_p), ("cin", C.c_int), ("wcin", C.c_int),
-                ("coff", C.c_int), ("ksize", C.c_int), ("pad", C.c_int)]
+                ("coff", C.c_int), ("ksize", C.c_int), ("pad", C.c_int), ("pad_w1", C.c_int)]
 
 
 class ConvDesc(C.Structure):
@@ -36,6 +36,7 @@ class ConvDesc(C.Structure):
                 ("gn_sums", C.c_void_p), ("act_dtype", C.c_int), ("out_nchw_f32", C.c_void_p), ("cout_real", C.c_int), ("rowscale", C.c_void_p), ("rowscale_stride", C.c_int), ("epi_act", C.c_int), ("out_nhwc_f32", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("range_events", C.c_void_p),
                 ("wsets", C.c_int), ("rowbias_gstride", C.c_int), ("rowscale_gstride", C.c_int),
+                ("out_sy", C.c_int), ("out_sx", C.c_int), ("out_oy", C.c_int), ("out_ox", C.c_int),
                 ("force_ksplit", C.c_int)]
 
 

@@ -20,7 +20,8 @@ import torch.nn as nn
 
 from . import ops
 from ._lib import B200Error
-from .unet import Act, Ctx, PackedWeights, _f, default_act_dtype, param_fingerprint, run_conv, run_gn
+from .unet import (Act, Ctx, PackedWeights, _FOLD_UPSAMPLE, _f, default_act_dtype, param_fingerprint, run_conv, run_gn,
+                   run_upsample_conv)
 
 Tensor = torch.Tensor
 
@@ -315,9 +316,12 @@ def run_decoder(cx: Ctx, dec: Decoder, z: Tensor, dtype) -> Tensor:
             if len(lvl.attn) > 0:
                 h = _run_attn(cx, lvl.attn[i_block], h)
         if i_level != 0:
-            h = Act(ops.upsample_nearest2x(h.t))
-            if lvl.upsample.with_conv:
-                h = run_conv(cx, [(h.t, pw.conv[id(lvl.upsample.conv)], 0, 3, 1)], bias=_f(lvl.upsample.conv.bias))
+            if lvl.upsample.with_conv and _FOLD_UPSAMPLE and min(h.t.shape[1], h.t.shape[2]) >= 8:
+                h = run_upsample_conv(cx, lvl.upsample.conv, h)      # nearest x2 + conv3x3 as four 2x2 sub-pixel convolutions
+            else:
+                h = Act(ops.upsample_nearest2x(h.t))
+                if lvl.upsample.with_conv:
+                    h = run_conv(cx, [(h.t, pw.conv[id(lvl.upsample.conv)], 0, 3, 1)], bias=_f(lvl.upsample.conv.bias))
     return _out_conv(cx, dec.norm_out, dec.conv_out, h)
 
 

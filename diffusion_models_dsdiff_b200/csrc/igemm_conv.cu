@@ -38,6 +38,8 @@ struct ConvKParams {
   int a_bytes, stage_bytes; // bytes of the activation region / of a whole stage (multiples of 1024)
   int nseg;
   int seg_cin[3], seg_coff[3], seg_ks[3], seg_pad[3];
+  int seg_padw[3];          // W padding (== seg_pad except for the 2x2 sub-pixel convolutions of a folded Upsample)
+  int out_sy, out_sx, out_oy, out_ox;   // output pixel (h, w) is stored at (h*out_sy + out_oy, w*out_sx + out_ox); 1,1,0,0 = dense
   int seg_halo[3];          // 3x3 stride-1 segment staged as 3 column-shifted (TH+2)-row boxes reused by the 3 tap rows
   const float *bias;
   const float *rowbias;
@@ -292,7 +294,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
             const int r = tap / ks, sx = tap - r * ks;
             for (int c0 = 0; c0 < cin; c0 += kBK, ++gi)
               if (gi >= g_begin && gi < g_end)
-                load_group(s, c0, n_tile, tbase + tap, 0, 1, (uint32_t)kABytes, w0 * p.stride + sx - pad,
+                load_group(s, c0, n_tile, tbase + tap, 0, 1, (uint32_t)kABytes, w0 * p.stride + sx - p.seg_padw[s],
                            h0 * p.stride + r - pad, n0);
           }
         }
@@ -418,7 +420,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       const int n = n0 + tn;
       const int n_warp = n0 + lane_base / (p.TW * p.TH);
       const bool valid = kFast || ((w < p.Wout) && (h < p.Hout) && (n < n_end));
-      const size_t pix = ((size_t)n * p.Hout + h) * p.Wout + w;
+      // dense, or one parity class of a 2x nearest-upsampled output (sub-pixel form of Upsample -> conv3x3)
+      const size_t pix = ((size_t)n * (p.Hout * p.out_sy) + (h * p.out_sy + p.out_oy)) * (p.Wout * p.out_sx) + (w * p.out_sx + p.out_ox);
       if (p.gn_sums && (n_warp != acc_n || n_tile != acc_ntile)) {
         if (acc_n >= 0) flush_stats();
         acc_n = n_warp;
@@ -778,7 +781,7 @@ static int conv_groups_total(const b200_conv_desc *d) {
   int g = 0;
   for (int s = 0; s < d->nseg; ++s) {
     const int chunks = cdiv(d->seg[s].cin, kBK);
-    g += (halo_ok && d->seg[s].ksize == 3 && d->seg[s].pad == 1) ? chunks * 3 : chunks * d->seg[s].ksize * d->seg[s].ksize;
+    g += (halo_ok && d->seg[s].ksize == 3 && d->seg[s].pad == 1 && d->seg[s].pad_w1 == 0) ? chunks * 3 : chunks * d->seg[s].ksize * d->seg[s].ksize;
   }
   return g;
 }
@@ -786,7 +789,8 @@ static int conv_groups_total(const b200_conv_desc *d) {
 static int conv_ksplit(const b200_conv_desc *d) {
   if (d->force_ksplit > 1) return std::max(1, std::min(d->force_ksplit, std::min(64, conv_groups_total(d))));
   static const bool off = getenv("B200DIFF_CONV_NO_SPLITK") != nullptr;
-  if (off || d->out == nullptr || d->out_nchw_f32 || d->out_nhwc_f32 || d->epi_act || d->rowscale) return 1;
+  if (off || d->out == nullptr || d->out_nchw_f32 || d->out_nhwc_f32 || d->epi_act || d->rowscale || d->out_sy > 1 || d->out_sx > 1)
+    return 1;
   // measured inside a CUDA graph (tools/graph_probe.py): 8x8 3x3 960->960 48.6 -> 33.4 us with S = 9, but 1x1 layers
   // (G = 15) and 16x16 maps (S = 2) lose to the extra finalize launch, so only long-K layers on <= 8x8 maps split
   if ((long)d->Hout * d->Wout > 64 || d->Cout % 8) return 1;
@@ -906,6 +910,7 @@ static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t
   p.range_events = d->range_events;
   p.wsets = std::max(1, d->wsets);
   p.n_per_set = d->N / p.wsets;
+  p.out_sy = std::max(1, d->out_sy); p.out_sx = std::max(1, d->out_sx); p.out_oy = d->out_oy; p.out_ox = d->out_ox;
   p.rowbias_gstride = d->rowbias_gstride; p.rowscale_gstride = d->rowscale_gstride;
   p.ksplit = ksplit;
   p.groups_total = conv_groups_total(d);
@@ -918,7 +923,7 @@ static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t
   const bool halo_ok = d->stride == 1 && p.TN == 1 && p.TW >= 8 && !getenv("B200DIFF_NO_HALO");
   bool any_halo = false;
   for (int s = 0; s < d->nseg; ++s) {
-    p.seg_halo[s] = halo_ok && d->seg[s].ksize == 3 && d->seg[s].pad == 1;
+    p.seg_halo[s] = halo_ok && d->seg[s].ksize == 3 && d->seg[s].pad == 1 && d->seg[s].pad_w1 == 0;
     any_halo |= p.seg_halo[s] != 0;
   }
   p.a_bytes = any_halo ? kABytes + 2 * p.TW * 128 : kABytes;
@@ -929,11 +934,12 @@ static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t
 
   for (int s = 0; s < d->nseg; ++s) {
     const b200_conv_seg &g = d->seg[s];
-    B200_CHECK(g.ksize == 1 || g.ksize == 3, "conv: ksize must be 1 or 3 (got %d)", g.ksize);
+    B200_CHECK(g.ksize >= 1 && g.ksize <= 3, "conv: ksize must be 1, 2 or 3 (got %d)", g.ksize);
     B200_CHECK(g.cin % 8 == 0 && g.wcin % 8 == 0, "conv: channel counts must be multiples of 8");
     B200_CHECK(g.coff % 8 == 0 && g.coff + g.cin <= g.wcin, "conv: bad weight channel window");
     B200_CHECK(((uintptr_t)g.src & 15) == 0 && ((uintptr_t)g.weight & 15) == 0, "conv: unaligned pointer");
     p.seg_cin[s] = g.cin; p.seg_coff[s] = g.coff; p.seg_ks[s] = g.ksize; p.seg_pad[s] = g.pad;
+    p.seg_padw[s] = g.pad_w1 > 0 ? g.pad_w1 - 1 : g.pad;
     {  // activations: (C, W, H, N)
       uint64_t dims[4] = {(uint64_t)g.cin, (uint64_t)d->Win, (uint64_t)d->Hin, (uint64_t)d->N};
       uint64_t str[3] = {(uint64_t)g.cin * 2, (uint64_t)d->Win * g.cin * 2,
@@ -995,6 +1001,8 @@ static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t
     B200_LAUNCH_CHECK();
     return 0;
   }
+  B200_CHECK(!(d->gn_sums && !p.gn_sums && (d->out_sy > 1 || d->out_sx > 1)),
+             "conv: fused statistics of a strided (sub-pixel) output need maps of at least 32 pixels");
   if (d->gn_sums && !p.gn_sums)
     return b200_channel_stats(d->out, d->N, d->Hout * d->Wout, d->Cout, d->gn_sums, d->act_dtype, stream);
   return 0;
@@ -1012,6 +1020,10 @@ extern "C" int b200_conv2d_igemm(const b200_conv_desc *d, void *stream) {
   B200_CHECK(d->out != nullptr || d->out_nchw_f32 != nullptr || d->out_nhwc_f32 != nullptr, "conv: no output pointer");
   B200_CHECK(d->out_nchw_f32 == nullptr || (d->cout_real >= 1 && d->cout_real <= d->Cout && !d->gn_sums),
              "conv: bad NCHW fp32 head output request");
+  const bool sub = d->out_sy > 1 || d->out_sx > 1;
+  B200_CHECK(!sub || (d->out != nullptr && !d->out_nchw_f32 && !d->out_nhwc_f32 && !d->residual && d->out_oy >= 0 &&
+                      d->out_oy < d->out_sy && d->out_ox >= 0 && d->out_ox < d->out_sx),
+             "conv: a strided (sub-pixel) output needs a 16-bit NHWC `out`, no residual and 0 <= offset < stride");
   const int wsets = std::max(1, d->wsets);
   B200_CHECK(wsets <= 8 && d->N % wsets == 0, "conv: N (%d) must be a multiple of the number of weight sets (%d <= 8)", d->N,
              wsets);

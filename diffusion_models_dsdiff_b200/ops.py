@@ -152,13 +152,20 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
            rowbias: Optional[Tensor] = None, residual: Optional[Tensor] = None, res_scale: float = 1.0,
            out: Optional[Tensor] = None, stats: Optional[Tensor] = None, head_channels: int = 0,
            out_hw: Optional[Tuple[int, int]] = None, out_f32: bool = False, rowscale: Optional[Tensor] = None,
-           act: int = 0, wsets: int = 1, rowbias_gstride: int = 0, force_ksplit: int = 0) -> Tensor:
+           act: int = 0, wsets: int = 1, rowbias_gstride: int = 0, force_ksplit: int = 0,
+           out_sub: Optional[Tuple[int, int, int, int]] = None) -> Tensor:
     """tcgen05 implicit-GEMM conv over up to 3 K-segments (see b200_conv2d_igemm).
 
     ``wsets`` > 1: grouped along N — the batch is ``wsets`` equal groups of images, group g convolves with its own weight
     set (``weight`` is the stack [wsets * k * k, Cout, Cin]), ``bias`` is [wsets, Cout] and ``rowbias`` advances by
-    ``rowbias_gstride`` floats per group."""
+    ``rowbias_gstride`` floats per group.
+
+    ``out_sub`` = (sy, sx, oy, ox): the result is one parity class of a [N, Hout*sy, Wout*sx, Cout] tensor ``out`` (required),
+    stored at (h*sy + oy, w*sx + ox) — the sub-pixel form of Upsample -> conv3x3; a segment's ``pad`` may then be a
+    (pad_top, pad_left) pair (2x2 kernels)."""
     src0, w0, _, k0, p0 = segs[0]
+    if isinstance(p0, tuple):
+        p0 = p0[0]
     _dev(src0)
     n, hin, win, _ = src0.shape
     cout = w0.shape[1]
@@ -169,6 +176,9 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
     d = L.ConvDesc()
     d.N, d.Hin, d.Win, d.Hout, d.Wout, d.Cout, d.stride, d.nseg = n, hin, win, hout, wout, cout, stride, len(segs)
     for i, (src, wt, coff, ks, pad) in enumerate(segs):
+        pad_w1 = 0
+        if isinstance(pad, tuple):
+            pad, pad_w1 = pad[0], pad[1] + 1
         if src.shape[:3] != src0.shape[:3] or src.dtype != src0.dtype or wt.dtype != src0.dtype:
             raise L.B200Error("conv2d: segments must share N,H,W and dtype")
         if ((out_hw is None and (hin + 2 * pad - ks) // stride + 1 != hout) or wt.shape[1] != cout
@@ -176,6 +186,7 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
             raise L.B200Error("conv2d: segment geometry mismatch")
         s = d.seg[i]
         s.src, s.weight, s.cin, s.wcin, s.coff, s.ksize, s.pad = _p(src), _p(wt), src.shape[3], wt.shape[2], coff, ks, pad
+        s.pad_w1 = pad_w1
     if head_channels:      # network head: fp32 NCHW output of the first head_channels (zero-padded N tile)
         out = torch.empty((n, head_channels, hout, wout), device=src0.device, dtype=torch.float32)
         d.out_nchw_f32, d.cout_real = _p(out), head_channels
@@ -187,8 +198,15 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
         d.out_nhwc_f32 = _p(out)
     elif out is None:
         out = torch.empty((n, hout, wout, cout), device=src0.device, dtype=src0.dtype)
+    elif out_sub is not None:
+        if tuple(out.shape) != (n, hout * out_sub[0], wout * out_sub[1], cout) or out.dtype != src0.dtype:
+            raise L.B200Error("conv2d: strided out shape/dtype mismatch")
     elif tuple(out.shape) != (n, hout, wout, cout) or out.dtype != src0.dtype:
         raise L.B200Error("conv2d: out shape/dtype mismatch")
+    if out_sub is not None:
+        if out is None or head_channels or out_f32 or residual is not None:
+            raise L.B200Error("conv2d: out_sub needs a pre-allocated 16-bit NHWC out and no residual")
+        d.out_sy, d.out_sx, d.out_oy, d.out_ox = out_sub
     d.bias = _p(_f32(bias))
     d.rowbias, d.rowbias_stride = None, 0
     d.wsets, d.rowbias_gstride, d.rowscale_gstride = wsets, rowbias_gstride, 0

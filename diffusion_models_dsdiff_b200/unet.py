@@ -320,15 +320,56 @@ def run_sequential(cx: Ctx, seq: nn.Sequential, x0: Act, x1: Optional[Act], conv
             else:
                 x0 = run_conv(cx, [(x0.t, pw.conv[id(layer.op)], 0, 3, 1)], stride=2, bias=_f(layer.op.bias))
         elif isinstance(layer, Upsample):
-            x0 = Act(ops.upsample_nearest2x(x0.t))
-            if layer.use_conv:
-                x0 = run_conv(cx, [(x0.t, pw.conv[id(layer.conv)], 0, 3, 1)], bias=_f(layer.conv.bias))
+            if layer.use_conv and _FOLD_UPSAMPLE and min(x0.t.shape[1], x0.t.shape[2]) >= 8:
+                x0 = run_upsample_conv(cx, layer.conv, x0)
+            else:
+                x0 = Act(ops.upsample_nearest2x(x0.t))
+                if layer.use_conv:
+                    x0 = run_conv(cx, [(x0.t, pw.conv[id(layer.conv)], 0, 3, 1)], bias=_f(layer.conv.bias))
         elif isinstance(layer, nn.Conv2d):
             x0 = run_conv(cx, [(x0.t, pw.conv[id(layer)], 0, layer.kernel_size[0], layer.padding[0])],
                           bias=_f(layer.bias))
         else:
             raise B200Error(f"B200 engine: unsupported layer {type(layer).__name__}")
     return x0
+
+
+_FOLD_UPSAMPLE = os.environ.get("B200DIFF_NO_UPSAMPLE_FOLD", "0") != "1"
+
+
+def run_upsample_conv(cx: Ctx, conv: nn.Conv2d, x: Act) -> Act:
+    """``Upsample`` = nearest x2 then conv3x3 pad 1 (openaimodel.py:113-120; AE: model.py:61-77) WITHOUT the 4x-sized
+    intermediate: output pixel (2i + a, 2j + b) only sees the 2 x 2 input neighbourhood rows {i - 1 + a, i + a}, columns
+    {j - 1 + b, j + b}, so each output parity class (a, b) is a 2x2 convolution of the LOW-resolution map whose weights
+    are sums of the 3x3 taps that read the same input pixel (a = 0: rows [w0 | w1 + w2]; a = 1: rows [w0 + w1 | w2];
+    same for columns).  Four launches write the four interleaved classes of one output tensor (b200_conv_desc.out_sy ...)
+    and accumulate its GroupNorm statistics: 16 instead of 36 multiply-adds per output pixel and channel pair, and neither
+    the upsampled tensor nor its re-read exist.  The tap sums are formed once per weight load in fp32 and rounded to the
+    16-bit operand type once (the unfolded form rounds every tap separately)."""
+    pw = cx.pw
+    key = ("up4", id(conv))
+    if key not in pw.conv:
+        w = conv.weight.detach().float()
+
+        def fold(t: Tensor, a: int, dim: int) -> Tensor:
+            r0, r1, r2 = t.unbind(dim)
+            return torch.stack([r0, r1 + r2] if a == 0 else [r0 + r1, r2], dim)
+
+        pw.conv[key] = [ops.pack_conv_weight(fold(fold(w, a, 2), b, 3).contiguous(), x.t.dtype)
+                        for a in (0, 1) for b in (0, 1)]
+    packs = pw.conv[key]
+    n, h, w_, _ = x.t.shape
+    cout = conv.out_channels
+    out = torch.empty((n, 2 * h, 2 * w_, cout), device=x.t.device, dtype=x.t.dtype)
+    st = cx.stats_for(n, cout)
+    bias = _f(conv.bias)
+    i = 0
+    for a in (0, 1):
+        for b in (0, 1):
+            ops.conv2d([(x.t, packs[i], 0, 2, (1 - a, 1 - b))], bias=bias, out=out, stats=st, out_hw=(h, w_),
+                       out_sub=(2, 2, a, b))
+            i += 1
+    return Act(out, st)
 
 
 def run_in_conv(cx: Ctx, conv: nn.Conv2d, x: Tensor, dtype: torch.dtype) -> Act:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 11
+#define B200_ABI_VERSION 12
 #define B200_F16 0
 #define B200_BF16 1
 
@@ -71,8 +71,9 @@ typedef struct {
   int cin;             /* channels of src                                            */
   int wcin;            /* Cin pitch of the packed weight (>= coff+cin)               */
   int coff;            /* first weight input-channel used by this segment            */
-  int ksize;           /* 1 or 3                                                     */
-  int pad;             /* 0 or 1                                                     */
+  int ksize;           /* 1 or 3 (2: the 2x2 sub-pixel kernels of a folded Upsample) */
+  int pad;             /* 0 or 1: zero padding (top / left)                          */
+  int pad_w1;          /* 0: left padding = pad; k + 1: left padding = k (asymmetric 2x2 sub-pixel kernels) */
 } b200_conv_seg;
 
 typedef struct {
@@ -117,6 +118,14 @@ typedef struct {
                               (their per-image stride then counts images WITHIN the group).  One launch for the G same-shape
                               encoders of DSUnetModel (UNet_DS_Diff/model.py:674-686) instead of G latency-bound ones.      */
   int rowbias_gstride, rowscale_gstride;
+  int out_sy, out_sx, out_oy, out_ox;
+                            /* 0 / 1: dense output.  out_sy, out_sx > 1: output pixel (h, w) of this launch is stored at
+                              (h*out_sy + out_oy, w*out_sx + out_ox) of an NHWC tensor [N, Hout*out_sy, Wout*out_sx, Cout] —
+                              one parity class of `Upsample` (nearest x2, openaimodel.py:113-117) followed by its 3x3 conv
+                              (:118-120), which collapses to four 2x2 convolutions of the LOW-resolution input (one per output
+                              parity, weights = sums of the 3x3 taps that read the same input pixel): the 4x-sized intermediate
+                              is never written and 16 instead of 36 multiply-adds per output pixel and channel pair remain.
+                              gn_sums of the four launches accumulate into the same buffer.                              */
   int force_ksplit;         /* 0: split-K factor chosen by b200_conv_ksplit (geometry only).  S > 1: run exactly S K-splits; with
                               out_nhwc_f32 set the S fp32 partial planes (workspace) are summed in fixed order into out_nhwc_f32
                               with no epilogue terms (bias / residual must be NULL) — the weight-gradient GEMM of the training

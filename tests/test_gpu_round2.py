@@ -304,3 +304,37 @@ def test_grouped_encoders_are_batch_independent():
     y3, _ = net(x, t)
     y1, _ = net(x[1:2].contiguous(), t[1:2])
     assert torch.equal(y3[1:2], y1)
+
+
+# -------------------------------------------------------------------------------------------------
+# Upsample folded into the convolution: four 2x2 sub-pixel convolutions, strided output
+# -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64, 96), (1, 24, 40, 32, 32), (3, 8, 8, 128, 64)])
+def test_folded_upsample_conv_matches_interpolate_then_conv(shape, dt):
+    """nearest x2 -> conv3x3 pad 1 (openaimodel.py:113-120) without the upsampled intermediate; GroupNorm statistics of the
+    interleaved output included."""
+    import torch.nn as nn
+    from diffusion_models_dsdiff_b200 import unet as U
+    ops = _ops()
+    n, h, w, ci, co = shape
+    x = q(rnd(70, n, ci, h, w), dt)
+    conv = nn.Conv2d(ci, co, 3, padding=1)
+    with torch.no_grad():
+        conv.weight.copy_(rnd(71, co, ci, 3, 3, scale=1.0 / math.sqrt(9 * ci)))
+        conv.bias.copy_(rnd(72, co, scale=0.1))
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), conv.weight, conv.bias, padding=1)
+    conv = conv.cuda()
+
+    class PW:
+        conv = {}
+    arena = ops.StatsArena()
+    arena.begin(torch.device("cuda"))
+    cx = U.Ctx(PW(), None, arena)
+    got = U.run_upsample_conv(cx, conv, U.Act(nhwc(x, dt)))
+    assert tuple(got.t.shape) == (n, 2 * h, 2 * w, co)
+    # one rounding of the summed taps instead of one per tap: the same operand-rounding class as the unfolded form
+    close(nchw(got.t), ref, dt, f"folded upsample conv {shape}")
+    yf = got.t.float()
+    exact = torch.stack([yf.double().sum((1, 2)), (yf.double() ** 2).sum((1, 2))], -1)
+    assert torch.allclose(got.cs, exact, rtol=1e-5, atol=1e-3)
