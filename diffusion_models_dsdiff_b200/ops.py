@@ -242,7 +242,9 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
         need = ks * out.numel() * 4          # two launches that may overlap)
         ws = _workspace(src0.device, need)
         d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel()
-    kk = sum(sg[0].shape[3] * sg[3] * sg[3] for sg in segs)
+    # ALGORITHMIC work (the reference's count): a 2x2 sub-pixel launch stands for its share of a 3x3 convolution on the
+    # upsampled map (9 taps per output pixel) although it executes 4
+    kk = sum(sg[0].shape[3] * (9 if (out_sub is not None and sg[3] == 2) else sg[3] * sg[3]) for sg in segs)
     flops = 2.0 * n * hout * wout * cout * kk
     nbytes = 2.0 * (sum(sg[0].numel() for sg in segs) + out.numel() + cout * kk
                     + (residual.numel() if residual is not None else 0))
