@@ -27,7 +27,8 @@ constexpr uint32_t kBwBlk = 128 * 16;                    // one (8 channels x 12
 constexpr uint32_t kBwPBytes = kBwT * kBwT * 2;          // a 128 x 128 16-bit operand tile (P or dS)
 
 struct BwMaps {
-  CUtensorMap qkv, dout;
+  CUtensorMap qkv, dout;        // 128-token boxes
+  CUtensorMap qkv_s, dout_s;    // 64-token boxes (v2: streamed tiles)
 };
 
 struct BwParams {
@@ -332,6 +333,288 @@ attn_bwd_tc_kernel(const __grid_constant__ BwMaps maps, const BwParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// v2 (head dim 64): TWO CTAs per SM.  The S / dP hand-off between the MMA issuer and the element-wise warps is a latency
+// chain (commit -> mbarrier -> tcgen05.ld -> arrive -> next MMA) that one resident CTA cannot hide (tensor pipe 16 % active
+// in v1, and switching off the exponentials, the operand stores and the second-stage MMAs one by one moved the time by < 15 %),
+// so v2 halves every per-CTA resource: tiles of 128 x 64, TMEM 256 columns, ~96 KB of shared memory.
+//   kDQ = true  : CTA = 128 queries (lanes), streams 64-KEY tiles:  S [128 q x 64 k] = Q K^T, dP = dO V^T, dQ += dS K.
+//   kDQ = false : CTA = 128 keys (lanes), streams 64-QUERY tiles and works on the TRANSPOSED scores so that lanes stay keys:
+//                 S^T [128 k x 64 q] = K Q^T, dP^T = V dO^T; P^T and dS^T are then K-major A operands (contraction over the
+//                 queries) of dV += P^T dO and dK += dS^T Q; the per-query lse / D are per COLUMN (staged in shared memory).
+// Every Q / K / V / dO tile is one SWIZZLE_128B TMA box; in both modes the second-stage operands are A = un-swizzled K-major
+// tile written by the element-wise warps, B = the streamed tile read MN-major.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kV2Threads = 320;                          // warp 0 TMA, warp 1 MMA, warps 2-9 element-wise
+constexpr int kV2S = 64;                                 // streamed tokens per tile
+
+template <typename T, bool kDQ>
+__global__ void __launch_bounds__(kV2Threads, 2)
+attn_bwd_v2_kernel(const __grid_constant__ BwMaps maps, const BwParams p) {
+  constexpr int D = 64;
+  constexpr uint32_t kResTile = 128 * D * 2;             // 16 KB: 128 resident tokens
+  constexpr uint32_t kStrTile = kV2S * D * 2;            // 8 KB: 64 streamed tokens
+  constexpr uint32_t kOpTile = 128 * kV2S * 2;           // 16 KB: [128 lanes x 64] 16-bit operand tile (dS, or P^T / dS^T)
+  constexpr int NS = kDQ ? 3 : 2;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t res_full, acc_full, s_full, s_empty, p_full, p_empty;
+  __shared__ __align__(8) uint64_t str_full[NS], str_empty[NS];
+  __shared__ uint32_t tmem_base_smem;
+  // kDQ == false: per-column (query) scalars (lse * log2e, D * scale) of three consecutive tiles.  Tile it + 1's row is
+  // written during iteration it BEFORE the writer's s_empty arrive; s_empty -> MMA issue -> s_full orders it before every
+  // reader of iteration it + 1, and a warp can be at most one iteration ahead of another, so three rows never collide.
+  __shared__ __align__(16) float2 s_col[3][kV2S];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = blockIdx.x * 128;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_it = (p.L + kV2S - 1) / kV2S;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sRes0 = base, sRes1 = base + kResTile;
+  const uint32_t sStr = sRes1 + kResTile;                // NS x (tile0, tile1)
+  const uint32_t sOp0 = sStr + NS * 2 * kStrTile;        // dS (kDQ) / dS^T
+  const uint32_t sOp1 = sOp0 + kOpTile;                  // P^T (only !kDQ)
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&maps.qkv); prefetch_tmap(&maps.dout); prefetch_tmap(&maps.qkv_s); prefetch_tmap(&maps.dout_s);
+    mbar_init(smem_u32(&res_full), 1);
+    mbar_init(smem_u32(&acc_full), 1);
+    mbar_init(smem_u32(&s_full), 1);
+    mbar_init(smem_u32(&s_empty), 8);
+    mbar_init(smem_u32(&p_full), 8);
+    mbar_init(smem_u32(&p_empty), 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(smem_u32(&str_full[i]), 1); mbar_init(smem_u32(&str_empty[i]), 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_smem), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + 64, tmem_a0 = tmem_base + 128, tmem_a1 = tmem_base + 192;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int qc = p.q_off + h * D, kc = p.k_off + h * D, vc = p.v_off + h * D, oc = h * D;
+      const uint32_t rb = smem_u32(&res_full);
+      mbar_arrive_expect_tx(rb, 2 * kResTile);
+      if (kDQ) {
+        tma_load_3d(sRes0, &maps.qkv, rb, qc, t0, b);
+        tma_load_3d(sRes1, &maps.dout, rb, oc, t0, b);
+      } else {
+        tma_load_3d(sRes0, &maps.qkv, rb, kc, t0, b);
+        tma_load_3d(sRes1, &maps.qkv, rb, vc, t0, b);
+      }
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it % NS;
+        mbar_wait(smem_u32(&str_empty[st]), ((it / NS) & 1) ^ 1);
+        const uint32_t bar = smem_u32(&str_full[st]);
+        mbar_arrive_expect_tx(bar, 2 * kStrTile);
+        const uint32_t d0 = sStr + st * 2 * kStrTile, d1 = d0 + kStrTile;
+        if (kDQ) {
+          tma_load_3d(d0, &maps.qkv_s, bar, kc, it * kV2S, b);
+          tma_load_3d(d1, &maps.qkv_s, bar, vc, it * kV2S, b);
+        } else {
+          tma_load_3d(d0, &maps.qkv_s, bar, qc, it * kV2S, b);
+          tma_load_3d(d1, &maps.dout_s, bar, oc, it * kV2S, b);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(smem_u32(&res_full), 0);
+      // first stage: [128 resident lanes x 64 streamed columns], contraction over the 64 channels (+32 B per 16 channels)
+      auto issue_first = [&](int g) {
+        const int st = g % NS;
+        mbar_wait(smem_u32(&str_full[st]), (g / NS) & 1);
+        mbar_wait(smem_u32(&s_empty), (g & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t x0 = sStr + st * 2 * kStrTile, x1 = x0 + kStrTile;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_f16(tmem_s, umma_desc_sw128(sRes0) + (uint64_t)(kk * 2), umma_desc_sw128(x0) + (uint64_t)(kk * 2), p.idesc_s, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_f16(tmem_dp, umma_desc_sw128(sRes1) + (uint64_t)(kk * 2), umma_desc_sw128(x1) + (uint64_t)(kk * 2), p.idesc_s, kk > 0);
+        umma_commit(smem_u32(&s_full));
+      };
+      issue_first(0);
+      for (int it = 0; it < n_it; ++it) {
+        if (it + 1 < n_it) issue_first(it + 1);
+        const int st = it % NS;
+        mbar_wait(smem_u32(&p_full), it & 1);
+        tc_fence_after();
+        const uint32_t x0 = sStr + st * 2 * kStrTile, x1 = x0 + kStrTile;
+        const uint32_t acc = (it > 0) ? 1u : 0u;
+        // second stage: contraction over the 64 streamed tokens.  A = operand tile [token block][lane][8 tokens] K-major
+        // (16 tokens = 2 blocks = +4096 B); B = streamed tile read MN-major (8-token atoms 1024 B apart: +2048 B per 16)
+#pragma unroll
+        for (int kk = 0; kk < kV2S / 16; ++kk) {
+          const uint64_t a0 = umma_desc_nosw(sOp0 + kk * 2 * kBwBlk, kBwBlk, 128);
+          if (kDQ) {
+            umma_f16(tmem_a0, a0, umma_desc_sw128(x0 + kk * 2048), p.idesc_acc, acc | (uint32_t)(kk > 0));        // dQ += dS K
+          } else {
+            umma_f16(tmem_a0, umma_desc_nosw(sOp1 + kk * 2 * kBwBlk, kBwBlk, 128), umma_desc_sw128(x1 + kk * 2048), p.idesc_acc,
+                     acc | (uint32_t)(kk > 0));                                                                    // dV += P^T dO
+            umma_f16(tmem_a1, a0, umma_desc_sw128(x0 + kk * 2048), p.idesc_acc, acc | (uint32_t)(kk > 0));        // dK += dS^T Q
+          }
+        }
+        umma_commit(smem_u32(&str_empty[st]));
+        umma_commit(smem_u32(&p_empty));
+      }
+      umma_commit(smem_u32(&acc_full));
+    }
+    __syncwarp();
+  } else {
+    // element-wise warps: thread == (lane row, 32-column half)
+    const int lane_base = 32 * (warp & 3);
+    const int row = lane_base + lane;
+    const int half = (warp - 2) >> 2;
+    const int cbase = half * 32;
+    const int ew_tid = threadIdx.x - 64;                 // 0 .. 255
+    const uint32_t t_lane = (uint32_t)lane_base << 16;
+    const float log2e = 1.4426950408889634f;
+    auto fetch = [&](int qi, float &l2, float &dm) {
+      l2 = 0.f; dm = 0.f;
+      if (qi < p.L) {
+        l2 = __ldg(p.lse + ((size_t)b * p.heads + h) * p.L + qi) * log2e;
+        dm = __ldg(p.dsum + ((size_t)b * p.L + qi) * p.heads + h) * p.scale;
+      }
+    };
+    float lse2 = 0.f, dsm_s = 0.f;                       // kDQ: this thread's query row
+    float nl = 0.f, nd = 0.f;                            // !kDQ: prefetched column scalars (threads 0..63 of the group)
+    if (kDQ) fetch(t0 + row, lse2, dsm_s);
+    else {
+      if (ew_tid < kV2S) {
+        fetch(ew_tid, nl, nd);
+        s_col[0][ew_tid] = make_float2(nl, nd);
+        if (n_it > 1) fetch(kV2S + ew_tid, nl, nd);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");      // once: row 0 is visible to all element-wise warps
+    }
+    uint8_t *srow0 = smem_raw + (sOp0 - smem_u32(smem_raw)) + row * 16;
+    uint8_t *srow1 = smem_raw + (sOp1 - smem_u32(smem_raw)) + row * 16;
+    for (int it = 0; it < n_it; ++it) {
+      if (!kDQ && ew_tid < kV2S && it + 1 < n_it) {
+        s_col[(it + 1) % 3][ew_tid] = make_float2(nl, nd);
+        if (it + 2 < n_it) fetch((it + 2) * kV2S + ew_tid, nl, nd);
+      }
+      mbar_wait(smem_u32(&s_full), it & 1);
+      tc_fence_after();
+      uint32_t sr[32], dr[32];
+      tmem_ld32(tmem_s + t_lane + cbase, sr);
+      tmem_ld32(tmem_dp + t_lane + cbase, dr);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_empty));
+      // dQ mode: streamed keys past the end of the sequence are masked (exp2(-lse) of their zero scores may overflow)
+      const int nvalid = kDQ ? min(kV2S, p.L - it * kV2S) : kV2S;
+      uint4 pk_p[4], pk_s[4];
+#pragma unroll
+      for (int v8 = 0; v8 < 4; ++v8) {
+        float pv[8], ds[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const int c = cbase + v8 * 8 + i;
+          float4 cc = make_float4(lse2, dsm_s, lse2, dsm_s);
+          if (!kDQ) cc = *reinterpret_cast<const float4 *>(&s_col[it % 3][c]);      // two columns per 16-byte broadcast load
+          pv[i] = bw_ex2(fmaf(__uint_as_float(sr[v8 * 8 + i]), p.scale_log2e, -cc.x));
+          pv[i + 1] = bw_ex2(fmaf(__uint_as_float(sr[v8 * 8 + i + 1]), p.scale_log2e, -cc.z));
+          if (kDQ && c >= nvalid) pv[i] = 0.f;
+          if (kDQ && c + 1 >= nvalid) pv[i + 1] = 0.f;
+          ds[i] = pv[i] * fmaf(__uint_as_float(dr[v8 * 8 + i]), p.scale, -cc.y);
+          ds[i + 1] = pv[i + 1] * fmaf(__uint_as_float(dr[v8 * 8 + i + 1]), p.scale, -cc.w);
+        }
+        pk_s[v8] = pack8<T>(ds);
+        if (!kDQ) pk_p[v8] = pack8<T>(pv);
+      }
+      mbar_wait(smem_u32(&p_empty), (it & 1) ^ 1);
+#pragma unroll
+      for (int v8 = 0; v8 < 4; ++v8) {
+        const uint32_t off = ((cbase >> 3) + v8) * kBwBlk;
+        *reinterpret_cast<uint4 *>(srow0 + off) = pk_s[v8];
+        if (!kDQ) *reinterpret_cast<uint4 *>(srow1 + off) = pk_p[v8];
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&p_full));
+    }
+    // epilogue: the halves split the 64 channels
+    mbar_wait(smem_u32(&acc_full), 0);
+    tc_fence_after();
+    const int ti = t0 + row;
+    T *orow = reinterpret_cast<T *>(p.dqkv) + ((size_t)b * p.L + ti) * p.ld + h * D + half * 32;
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 8) {
+      uint32_t r0[8], r1[8];
+      tmem_ld8(tmem_a0 + t_lane + half * 32 + c0, r0);
+      if (!kDQ) tmem_ld8(tmem_a1 + t_lane + half * 32 + c0, r1);
+      tmem_ld_wait();
+      if (ti < p.L) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r0[i]);
+        *reinterpret_cast<uint4 *>(orow + (kDQ ? p.q_off : p.v_off) + c0) = pack8<T>(f);
+        if (!kDQ) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r1[i]);
+          *reinterpret_cast<uint4 *>(orow + p.k_off + c0) = pack8<T>(f);
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+template <typename T>
+static int launch_bwd_v2(const void *qkv, int ld, int q_off, int k_off, int v_off, const void *dout, const float *lse,
+                         const float *dsum, void *dqkv, int B, int L, int heads, float scale, cudaStream_t st) {
+  constexpr int D = 64;
+  BwMaps maps{};
+  BwParams p{};
+  const int ldo = heads * D;
+  for (int which = 0; which < 4; ++which) {            // 128-token and 64-token boxes over qkv and dout
+    const bool is_out = which & 1;
+    const uint32_t rows = (which & 2) ? 64 : 128;
+    const int pitch = is_out ? ldo : ld;
+    uint64_t dims[3] = {(uint64_t)pitch, (uint64_t)L, (uint64_t)B};
+    uint64_t str[2] = {(uint64_t)pitch * 2, (uint64_t)L * pitch * 2};
+    uint32_t box[3] = {64, rows, 1}, es[3] = {1, 1, 1};
+    CUtensorMap *m = which == 0 ? &maps.qkv : which == 1 ? &maps.dout : which == 2 ? &maps.qkv_s : &maps.dout_s;
+    if (int rc = cached_tmap(m, is_out ? dout : qkv, 3, dims, str, box, es, /*swizzle128=*/true)) return rc;
+  }
+  p.L = L; p.heads = heads; p.q_off = q_off; p.k_off = k_off; p.v_off = v_off; p.ld = ld;
+  p.scale = scale; p.scale_log2e = scale * 1.4426950408889634f;
+  p.lse = lse; p.dsum = dsum; p.dqkv = dqkv; p.debug = 0;
+  p.idesc_s = umma_idesc(Act<T>::kFmt, 128, 64, 0);
+  p.idesc_acc = umma_idesc(Act<T>::kFmt, 128, 64, 1);       // A K-major, B MN-major
+  const dim3 grid(cdiv(L, 128), heads, B);
+  const size_t smem_kv = 2 * 16384 + 2 * 2 * 8192 + 2 * 16384 + 1024;
+  const size_t smem_q = 2 * 16384 + 3 * 2 * 8192 + 16384 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA(cudaFuncSetAttribute(attn_bwd_v2_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv));
+    B200_CUDA(cudaFuncSetAttribute(attn_bwd_v2_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q));
+    B200_CUDA(cudaFuncSetAttribute(attn_bwd_v2_kernel<T, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    B200_CUDA(cudaFuncSetAttribute(attn_bwd_v2_kernel<T, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_set = true;
+  }
+  attn_bwd_v2_kernel<T, false><<<grid, kV2Threads, smem_kv, st>>>(maps, p);
+  B200_LAUNCH_CHECK();
+  attn_bwd_v2_kernel<T, true><<<grid, kV2Threads, smem_q, st>>>(maps, p);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename T, int D>
 static int launch_bwd_tc(const void *qkv, int ld, int q_off, int k_off, int v_off, const void *dout, const float *lse,
                          const float *dsum, void *dqkv, int B, int L, int heads, float scale, cudaStream_t st) {
@@ -377,9 +660,11 @@ static int launch_bwd_tc(const void *qkv, int ld, int q_off, int k_off, int v_of
 int attention_bwd_tc(const void *qkv, int ld, int q_off, int k_off, int v_off, const void *dout, const float *lse,
                      const float *dsum, void *dqkv, int B, int L, int heads, int d, float scale, int act_dtype,
                      cudaStream_t st) {
+  static const bool v1 = getenv("B200DIFF_ATTN_BWD_V1") != nullptr && getenv("B200DIFF_ATTN_BWD_V1")[0] == '1';
 #define BW_(TT)                                                                                                         \
   do {                                                                                                                  \
     if (d == 32) return launch_bwd_tc<TT, 32>(qkv, ld, q_off, k_off, v_off, dout, lse, dsum, dqkv, B, L, heads, scale, st); \
+    if (d == 64 && !v1) return launch_bwd_v2<TT>(qkv, ld, q_off, k_off, v_off, dout, lse, dsum, dqkv, B, L, heads, scale, st); \
     if (d == 64) return launch_bwd_tc<TT, 64>(qkv, ld, q_off, k_off, v_off, dout, lse, dsum, dqkv, B, L, heads, scale, st); \
   } while (0)
   if (act_dtype == B200_F16) BW_(__half);
