@@ -779,6 +779,7 @@ def run_cfg5(args):
         "data": "synthetic", "gpu_launches": launches,
         "config": {"workload": CFG5_NAME, "samples_per_gpu_per_step": B, "global_batch": B * world, "tokens_per_sample": 1024,
                    "parameters": int(tr.flat_p.numel()), "optimizer": "AdamW lr 1e-4 (torch defaults)",
+                   "cuda_graph": bool(tr.use_graph and world == 1),
                    "parallelism": f"data parallel x{world}: replicated weights, per-block gradient buckets all-reduced over NCCL "
                                   "as the backward produces them",
                    "l2": "activations per layer (50-200 MB) exceed the 126 MB L2 across a step; no explicit flush"},
@@ -793,7 +794,7 @@ def run_cfg5(args):
         tm = ops.KernelTimer()
         ops.set_timer(tm)
         torch.cuda._sleep(int(2e8))
-        step_resident()
+        tr.training_step(x0_d, t, cond=[cond_d], use_graph=False)       # eager: per-launch events need individual launches
         ops.set_timer(None)
         summ = tm.summary()
         tot = sum(v["ms"] for v in summ.values())

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200diff.so")
 
-ABI_VERSION = 12        # must equal B200_ABI_VERSION of the header the library was built from
+ABI_VERSION = 13        # must equal B200_ABI_VERSION of the header the library was built from
 F16, BF16 = 0, 1
 SAMPLER_LDM_DDIM, SAMPLER_LDM_DDPM, SAMPLER_GD_DDIM, SAMPLER_GD_DDPM, SAMPLER_DPMPP_2M = 0, 1, 2, 3, 4
 SAMPLER_NCOEF = 16
@@ -113,7 +113,7 @@ SIGNATURES = {
     "b200_diffusion_loss": [_P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _P],
     "b200_linear_f32_wgrad": [_P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P],
     "b200_linear_f32_dgrad": [_P, _I, _P, _P, _P, _I, _I, _I, _P],
-    "b200_adamw": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P],
+    "b200_adamw": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _F, _P, _P],
 }
 _RESTYPE = {"b200_last_error": C.c_char_p, "b200_launch_count": C.c_uint64}
 

@@ -773,7 +773,11 @@ __global__ void __launch_bounds__(256) silu_bwd_f32_kernel(const float *__restri
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 adamw_kernel(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, int64_t n,
-             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float grad_scale,
+             const float *__restrict__ hyper) {
+  if (hyper) {      // step-dependent scalars from device memory: a captured CUDA graph is replayed for every step
+    lr = hyper[0]; bc1 = hyper[1]; bc2_sqrt = hyper[2];
+  }
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * grad_scale;
     float pi = p[i] * (1.f - lr * wd);
@@ -1007,12 +1011,13 @@ extern "C" int b200_linear_f32_dgrad(const float *dy, int dy_stride, const float
 }
 
 extern "C" int b200_adamw(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2, float eps,
-                          float weight_decay, int step, float grad_scale, void *stream) {
-  B200_CHECK(p && g && m && v && n > 0 && step >= 1, "adamw: bad arguments");
+                          float weight_decay, int step, float grad_scale, const float *hyper, void *stream) {
+  B200_CHECK(p && g && m && v && n > 0 && (step >= 1 || hyper), "adamw: bad arguments");
+  step = std::max(step, 1);
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = 1.f - powf(beta2, (float)step);
   adamw_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1,
-                                                               sqrtf(bc2), grad_scale);
+                                                               sqrtf(bc2), grad_scale, hyper);
   B200_LAUNCH_CHECK();
   return 0;
 }

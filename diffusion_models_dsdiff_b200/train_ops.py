@@ -184,11 +184,16 @@ def linear_f32_dgrad(dy: Tensor, w: Tensor, x_pre: Optional[Tensor] = None) -> T
 
 
 def adamw(p: Tensor, g: Tensor, m: Tensor, v: Tensor, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
-          weight_decay: float = 1e-2, step: int = 1, grad_scale: float = 1.0) -> None:
+          weight_decay: float = 1e-2, step: int = 1, grad_scale: float = 1.0, hyper: Optional[Tensor] = None) -> None:
+    """``hyper``: device fp32 [3] = (lr, 1 - beta1^step, sqrt(1 - beta2^step)) read instead of ``lr`` / ``step`` (graph replay)."""
     _dev(p)
     _timed("adamw", 0.0, 4.0 * 7 * p.numel(),
            lambda: L.check(L.lib().b200_adamw(_p(_f32(p)), _p(_f32(g)), _p(_f32(m)), _p(_f32(v)), p.numel(), lr, betas[0],
-                                              betas[1], eps, weight_decay, step, grad_scale, _stream()), "adamw"))
+                                              betas[1], eps, weight_decay, step, grad_scale, _p(hyper), _stream()), "adamw"))
+
+
+def adamw_hyper(lr: float, betas, step: int) -> Tuple[float, float, float]:
+    return lr, 1.0 - betas[0] ** step, (1.0 - betas[1] ** step) ** 0.5
 
 
 # ---------------------------------------------------------------------------------------------

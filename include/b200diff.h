@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 12
+#define B200_ABI_VERSION 13
 #define B200_F16 0
 #define B200_BF16 1
 
@@ -384,9 +384,10 @@ int b200_linear_f32_wgrad(const float *dy, int dy_stride, const float *x, int x_
 int b200_linear_f32_dgrad(const float *dy, int dy_stride, const float *W, const float *x_pre, float *dx, int N, int O, int I,
                           void *stream);
 /* fused AdamW over a flat fp32 arena (torch.optim.AdamW semantics; step counts from 1; g is multiplied by grad_scale first:
- * 1 / world_size after a summing all-reduce)                                                                            */
+ * 1 / world_size after a summing all-reduce).  hyper (may be NULL): device fp32 [3] = (lr, 1 - beta1^step,
+ * sqrt(1 - beta2^step)) read by the kernel INSTEAD of lr / step, so a captured CUDA graph can be replayed for every step.   */
 int b200_adamw(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2, float eps,
-               float weight_decay, int step, float grad_scale, void *stream);
+               float weight_decay, int step, float grad_scale, const float *hyper, void *stream);
 
 #ifdef __cplusplus
 }

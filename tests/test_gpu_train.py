@@ -256,3 +256,27 @@ def test_two_optimizer_steps_reach_the_reference_parameters(name):
     x = torch.cat([g["x0"]] + cond, 1).cuda()
     y = net(x, torch.tensor([3.0, 500.0, 900.0], device="cuda"))
     assert torch.isfinite(y).all()
+
+
+def test_graph_replayed_training_steps_equal_eager_steps():
+    """The captured-and-replayed step (static input buffers, optimizer scalars read from device memory) walks the same
+    parameter trajectory as eager launches: five steps with changing t / noise, the last three replayed."""
+    name = "train_dit_v"
+    runs = []
+    for use_graph in (False, True):
+        g, net, tr = _trainer(name, torch.bfloat16, 1e-3)
+        tr.use_graph = use_graph
+        cond = [c for c in g["cond"]]
+        losses = []
+        for k in range(5):
+            noise = rnd(200 + k, *g["noise"].shape)
+            t = torch.tensor([(17 * k + 3) % 1000, (400 + 91 * k) % 1000, 999 - 55 * k])
+            losses.append(float(tr.training_step(g["x0"], t, cond=cond, noise=noise)["loss"]))
+        assert (len(tr._graphs) == 1) == use_graph
+        assert tr.step_count == 5
+        runs.append((losses, tr.flat_p.detach().clone()))
+    (l0, p0), (l1, p1) = runs
+    assert max(abs(a - b) / abs(a) for a, b in zip(l0, l1)) < 2e-3, (l0, l1)
+    # fp32 atomics (column sums) add in a run-dependent order, and Adam turns near-zero gradients into +-lr steps:
+    # mean, not max
+    assert float((p0 - p1).abs().mean()) < 0.05 * 1e-3
