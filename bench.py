@@ -816,6 +816,8 @@ def run_cfg5(args):
                         "frac": ach / (pk["tensor"] if tensor else pk["hbm"]), "launches_per_step": v["launches"],
                         "ms_per_step": v["ms"], "share_of_step": v["ms"] / max(tot, 1e-9)})
         res["roofline_aux"] = aux
+    if rank == 0 and world == 1 and not args.no_gpu_eager_reference and reference_available():
+        res["gpu_eager_reference"] = cfg5_gpu_eager_reference(B, dev, res["value"])
     # gradient all-reduce alone: the whole fp32 gradient arena, NCCL ring / NVLS
     if world > 1:
         gbytes = tr.flat_g.numel() * 4
@@ -832,6 +834,86 @@ def run_cfg5(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def cfg5_gpu_eager_reference(B, dev, our_value):
+    """The UNMODIFIED reference DiT + GaussianDiffusion.training_losses + autograd + torch.optim.AdamW on this GPU (eager
+    PyTorch; bf16 autocast as BASELINE cfg5 states; TF32 'high' for the fp32 variant).  timm is absent and unpinned: its
+    Attention is restated twice — the classic softmax(q k^T) v and the fused F.scaled_dot_product_attention current timm
+    releases dispatch to — and both are reported."""
+    import torch
+    import torch.nn.functional as F
+    import _ref_import
+    _ref_import.install()
+    import make_golden_ext as MGE
+    MGE._install_timm_restatement()
+    import sys as _sys
+    vt = _sys.modules["timm.models.vision_transformer"]
+    classic = vt.Attention
+
+    class FusedAttention(classic):
+        def forward(self, x):
+            b, n, c = x.shape
+            qkv = self.qkv(x).reshape(b, n, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4)
+            q, k, v = qkv.unbind(0)
+            x = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, n, c)
+            return self.proj(x)
+
+    import training_project.utils.gaussian_diffusion as GD
+    from training_project.utils.script_util import create_gaussian_diffusion
+    import UNet_DS_Diff.DiT_models as RD
+    GD.get_heatmap = lambda m: m
+    out = {"what": "unmodified reference modules (byte-compiled oracle/_ref) + torch autograd + torch.optim.AdamW on this GPU, "
+                   f"{B} samples per step, 3 timed steps after 2 warm-up steps", "batch": B}
+    s = CFG5["input_size"]
+    x0 = torch.clamp(torch.randn(B, 1, s, s, device=dev) * 0.5, -1, 1)
+    cond = [torch.clamp(torch.randn(B, 1, s, s, device=dev) * 0.5, -1, 1) for _ in range(3)]
+    kw = {"F_Data1": cond[0], "F_Data2": cond[1], "S_Data1": cond[2]}
+    diff = create_gaussian_diffusion(steps=1000, learn_sigma=True, noise_schedule="linear", rescale_timesteps=True,
+                                     timestep_respacing="", parameterization="v")
+    for attn_name, attn_cls in (("sdpa_attention", FusedAttention), ("classic_attention", classic)):
+        RD.Attention = attn_cls
+        for mode in ("bf16_autocast", "tf32"):
+            torch.manual_seed(0)
+            net = RD.DiT(**CFG5).to(dev)
+            with torch.no_grad():
+                for p_ in net.parameters():
+                    if p_.requires_grad and not p_.detach().any():
+                        p_.normal_(0, 0.02)
+            opt = torch.optim.AdamW(net.parameters(), lr=1e-4)
+            model = lambda x, t, c_concat=None: net(torch.cat([x] + c_concat, 1), t)
+            torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
+            torch.set_float32_matmul_precision("high" if mode == "tf32" else "highest")
+
+            def step():
+                opt.zero_grad(set_to_none=True)
+                t = torch.randint(0, 1000, (B,), device=dev)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16_autocast"):
+                    terms = diff.training_losses(model, x0, t, model_kwargs=kw)
+                    loss = terms["loss"].mean()
+                loss.backward()
+                opt.step()
+
+            try:
+                for _ in range(2):
+                    step()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(3):
+                    step()
+                b.record()
+                torch.cuda.synchronize()
+                ms = a.elapsed_time(b) / 3
+                out[f"{attn_name}.{mode}"] = {"ms_per_step": ms, "samples_per_s": B / ms * 1e3,
+                                              "speedup_of_this_path": our_value / (B / ms * 1e3)}
+            except Exception as e:      # e.g. out of memory for the materialised fp32 score matrices
+                out[f"{attn_name}.{mode}"] = {"error": f"{type(e).__name__}: {str(e)[:120]}"}
+            del net, opt
+            torch.cuda.empty_cache()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+    return out
 
 
 def run_reference_cfg5(args):
