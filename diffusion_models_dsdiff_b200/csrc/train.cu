@@ -179,15 +179,13 @@ gate_bwd_kernel(const T *__restrict__ dh, const T *__restrict__ f, const float *
                 T *__restrict__ df, float *__restrict__ dgate, int dgate_stride, int N, int L, int C, int rows_per_warp) {
   // block = 8 warps walking consecutive row chunks of ONE sample; their per-channel partial sums meet in shared memory, so a
   // block issues one global atomic per channel
-  extern __shared__ float s_acc[];                       // [C]
+  extern __shared__ float s_acc[];                       // [8 warps][C]: per-warp partial sums, no atomics
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int blocks_per_sample = (L + 8 * rows_per_warp - 1) / (8 * rows_per_warp);
   const int n = blockIdx.x / blocks_per_sample;
   const int t0 = ((blockIdx.x - n * blocks_per_sample) * 8 + warp) * rows_per_warp;
   const int t1 = min(L, t0 + rows_per_warp);
   const int nvec = C >> 3;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
   float acc[NV][8];
   float g[NV][8];
 #pragma unroll
@@ -214,12 +212,18 @@ gate_bwd_kernel(const T *__restrict__ dh, const T *__restrict__ f, const float *
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int v = lane + 32 * k;
-    if (v < nvec && t1 > t0)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[v * 8 + j], acc[k][j]);
+    if (v < nvec) {
+      *reinterpret_cast<float4 *>(&s_acc[warp * C + v * 8]) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+      *reinterpret_cast<float4 *>(&s_acc[warp * C + v * 8 + 4]) = make_float4(acc[k][4], acc[k][5], acc[k][6], acc[k][7]);
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dgate + (size_t)n * dgate_stride + i, s_acc[i]);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_acc[w * C + i];
+    atomicAdd(dgate + (size_t)n * dgate_stride + i, t);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -234,8 +238,8 @@ ln_mod_bwd_kernel(const T *__restrict__ x, const T *__restrict__ da, const float
                   const T *__restrict__ dres, T *__restrict__ dx, float *__restrict__ dshift, float *__restrict__ dscale,
                   int dmod_stride, int N, int L, int C, float eps, int rows_per_warp) {
   // block = 8 warps walking consecutive row chunks of ONE sample (see gate_bwd_kernel); 1 + scale[n] sits in shared memory
-  extern __shared__ float s_buf[];                       // [3][C]: dshift partials, dscale partials, 1 + scale
-  float *s_sh = s_buf, *s_sc = s_buf + C, *s_s1 = s_buf + 2 * C;
+  extern __shared__ float s_buf[];                       // [C] 1 + scale | [8 warps][2][C] per-warp dshift / dscale partials
+  float *s_s1 = s_buf, *s_part = s_buf + C;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int blocks_per_sample = (L + 8 * rows_per_warp - 1) / (8 * rows_per_warp);
   const int n = blockIdx.x / blocks_per_sample;
@@ -243,10 +247,7 @@ ln_mod_bwd_kernel(const T *__restrict__ x, const T *__restrict__ da, const float
   const int t1 = min(L, t0 + rows_per_warp);
   const int nvec = C >> 3;
   const float invC = 1.f / (float)C;
-  for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    s_sh[i] = 0.f; s_sc[i] = 0.f;
-    s_s1[i] = 1.f + scale[(size_t)n * mod_stride + i];
-  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_s1[i] = 1.f + scale[(size_t)n * mod_stride + i];
   __syncthreads();
   float a_sh[NV][8], a_sc[NV][8];
 #pragma unroll
@@ -327,22 +328,24 @@ ln_mod_bwd_kernel(const T *__restrict__ x, const T *__restrict__ da, const float
       }
     }
   }
-  if (t1 > t0) {
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int v = lane + 32 * k;
-      if (v < nvec)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          atomicAdd(&s_sh[v * 8 + j], a_sh[k][j]);
-          atomicAdd(&s_sc[v * 8 + j], a_sc[k][j]);
-        }
+  for (int k = 0; k < NV; ++k) {
+    const int v = lane + 32 * k;
+    if (v < nvec) {
+      float *ps = s_part + (size_t)(warp * 2) * C + v * 8, *pc = ps + C;
+      *reinterpret_cast<float4 *>(ps) = make_float4(a_sh[k][0], a_sh[k][1], a_sh[k][2], a_sh[k][3]);
+      *reinterpret_cast<float4 *>(ps + 4) = make_float4(a_sh[k][4], a_sh[k][5], a_sh[k][6], a_sh[k][7]);
+      *reinterpret_cast<float4 *>(pc) = make_float4(a_sc[k][0], a_sc[k][1], a_sc[k][2], a_sc[k][3]);
+      *reinterpret_cast<float4 *>(pc + 4) = make_float4(a_sc[k][4], a_sc[k][5], a_sc[k][6], a_sc[k][7]);
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    atomicAdd(dshift + (size_t)n * dmod_stride + i, s_sh[i]);
-    atomicAdd(dscale + (size_t)n * dmod_stride + i, s_sc[i]);
+    float ts = 0.f, tc = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { ts += s_part[(size_t)(w * 2) * C + i]; tc += s_part[(size_t)(w * 2 + 1) * C + i]; }
+    atomicAdd(dshift + (size_t)n * dmod_stride + i, ts);
+    atomicAdd(dscale + (size_t)n * dmod_stride + i, tc);
   }
 }
 
@@ -859,7 +862,7 @@ extern "C" int b200_gated_residual(const void *h_in, const void *f, const float 
 static int rows_per_warp_for(int N, int L) {
   // enough warps to fill the GPU, but long enough runs that the per-(sample, channel) atomics stay cheap
   int rpw = 32;
-  while (rpw > 4 && (int64_t)N * cdiv(L, 8 * rpw) < (int64_t)num_sms() * 4) rpw >>= 1;
+  while (rpw > 4 && (int64_t)N * cdiv(L, 8 * rpw) < (int64_t)num_sms() * 3) rpw >>= 1;
   return rpw;
 }
 
@@ -870,8 +873,14 @@ extern "C" int b200_gate_bwd(const void *dh, const void *f, const float *gate, i
   const int rpw = rows_per_warp_for(N, L);
   const int blocks = N * cdiv(L, 8 * rpw);
   const int nv = cdiv(C / 8, 32);
-#define L2_(TT, NV) gate_bwd_kernel<TT, NV><<<blocks, 256, (size_t)C * sizeof(float), (cudaStream_t)stream>>>((const TT *)dh, (const TT *)f, gate, \
-      gate_stride, (TT *)df, dgate, dgate_stride, N, L, C, rpw)
+#define L2_(TT, NV)                                                                                                  \
+  do {                                                                                                               \
+    const size_t smem_ = (size_t)8 * C * sizeof(float);                                                              \
+    if (smem_ > 48 * 1024)                                                                                           \
+      B200_CUDA(cudaFuncSetAttribute(gate_bwd_kernel<TT, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_)); \
+    gate_bwd_kernel<TT, NV><<<blocks, 256, smem_, (cudaStream_t)stream>>>((const TT *)dh, (const TT *)f, gate,       \
+        gate_stride, (TT *)df, dgate, dgate_stride, N, L, C, rpw);                                                    \
+  } while (0)
 #define L_(TT, ...)                                                                         \
   switch (nv) {                                                                             \
     case 1: L2_(TT, 1); break; case 2: L2_(TT, 2); break; case 3: L2_(TT, 3); break;        \
@@ -892,8 +901,14 @@ extern "C" int b200_ln_mod_bwd(const void *x, const void *da, const float *scale
   const int rpw = rows_per_warp_for(N, L);
   const int blocks = N * cdiv(L, 8 * rpw);
   const int nv = cdiv(C / 8, 32);
-#define L2_(TT, NV) ln_mod_bwd_kernel<TT, NV><<<blocks, 256, (size_t)3 * C * sizeof(float), (cudaStream_t)stream>>>((const TT *)x, (const TT *)da, scale, \
-      mod_stride, (const TT *)dres, (TT *)dx, dshift, dscale, dmod_stride, N, L, C, eps, rpw)
+#define L2_(TT, NV)                                                                                                  \
+  do {                                                                                                               \
+    const size_t smem_ = (size_t)17 * C * sizeof(float);                                                             \
+    if (smem_ > 48 * 1024)                                                                                           \
+      B200_CUDA(cudaFuncSetAttribute(ln_mod_bwd_kernel<TT, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_)); \
+    ln_mod_bwd_kernel<TT, NV><<<blocks, 256, smem_, (cudaStream_t)stream>>>((const TT *)x, (const TT *)da, scale,    \
+        mod_stride, (const TT *)dres, (TT *)dx, dshift, dscale, dmod_stride, N, L, C, eps, rpw);                      \
+  } while (0)
 #define L_(TT, ...)                                                                         \
   switch (nv) {                                                                             \
     case 1: L2_(TT, 1); break; case 2: L2_(TT, 2); break; case 3: L2_(TT, 3); break;        \
