@@ -435,6 +435,29 @@ def other_workloads(dev, rank, world):
                           "per GPU, eager launches", "ms_per_batch": ms, "slices_per_s": 16 * world / ms * 1e3})
     del ae
     torch.cuda.empty_cache()
+    # cfg5: DiT-B/2 training step (full line: python bench.py --workload cfg5), 32 samples per GPU, eager launches so the
+    # per-block gradient all-reduce runs at N > 1 exactly as in the dedicated workload
+    from diffusion_models_dsdiff_b200.dit_train import DiTTrainer
+    torch.manual_seed(0)
+    with torch.device(dev):
+        dit = P.DiT(**CFG5, act_dtype=torch.bfloat16)
+    g5 = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for p_ in dit.parameters():
+            if p_.requires_grad and not p_.detach().any():
+                p_.copy_((torch.randn(p_.shape, generator=g5) * 0.02).to(dev))
+    gd = S.create_gaussian_diffusion(steps=1000, learn_sigma=True, noise_schedule="linear", rescale_timesteps=True,
+                                     timestep_respacing="", parameterization="v")
+    tr = DiTTrainer(dit, gd, lr=1e-4, act_dtype=torch.bfloat16)
+    gen = torch.Generator().manual_seed(100 + rank)
+    x0 = torch.clamp(torch.randn(32, 1, 64, 64, generator=gen) * 0.5, -1, 1).to(dev)
+    cd = torch.clamp(torch.randn(32, 3, 64, 64, generator=gen) * 0.5, -1, 1).to(dev)
+    tt = torch.randint(0, 1000, (32,), generator=gen)
+    ms = timed(lambda: tr.training_step(x0, tt, cond=[cd], use_graph=False), reps=5, warm=3)
+    res.append({"config": "cfg5 " + CFG5_NAME + f"; 32 samples per GPU, bf16, data parallel x{world}",
+                "ms_per_step": ms, "samples_per_s": 32 * world / ms * 1e3})
+    del tr, dit
+    torch.cuda.empty_cache()
     return res
 
 
