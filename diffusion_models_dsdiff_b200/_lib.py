@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200diff.so")
 
-ABI_VERSION = 13        # must equal B200_ABI_VERSION of the header the library was built from
+ABI_VERSION = 14        # must equal B200_ABI_VERSION of the header the library was built from
 F16, BF16 = 0, 1
 SAMPLER_LDM_DDIM, SAMPLER_LDM_DDPM, SAMPLER_GD_DDIM, SAMPLER_GD_DDPM, SAMPLER_DPMPP_2M = 0, 1, 2, 3, 4
 SAMPLER_NCOEF = 16
@@ -102,6 +102,8 @@ SIGNATURES = {
     # training step (csrc/train.cu)
     "b200_transpose16": [_P, _P, _P, _L, _I, _I, _P],
     "b200_colsum16": [_P, _P, _L, _I, _I, _P],
+    "b200_wgrad_splits": [_L, _I, _I],
+    "b200_linear_wgrad": [_P, _P, _P, _P, _L, _I, _I, _I, _P],
     "b200_gelu_fwd": [_P, _P, _L, _I, _P],
     "b200_gelu_bwd": [_P, _P, _P, _L, _I, _P],
     "b200_gated_residual": [_P, _P, _P, _I, _P, _L, _I, _I, _I, _P],

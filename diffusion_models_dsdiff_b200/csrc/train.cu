@@ -87,20 +87,48 @@ transpose16_kernel(const T *__restrict__ src, T *__restrict__ dst, float *__rest
 // ------------------------------------------------------------------------------------------------------------------
 // bias gradient: out[c] += sum_r x[r, c]   (fp32 atomics; zero `out` first)
 // ------------------------------------------------------------------------------------------------------------------
+// block = (up to 64 eight-channel columns) x (256 / columns row lanes); every thread streams its column down the block's row
+// range with four 16-byte loads in flight, the row lanes meet in shared memory, one fp32 atomic per (column, block)
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum16_kernel(const T *__restrict__ x, float *__restrict__ out, int64_t R, int C, int rows_per_block) {
+colsum16_kernel(const T *__restrict__ x, float *__restrict__ out, int64_t R, int C, int rows_per_block, int cpb) {
+  __shared__ float red[256 * 8];
   const int ncol = C >> 3;
-  const int64_t r_begin = (int64_t)blockIdx.x * rows_per_block;
+  const int lanes = 256 / cpb;                           // row lanes
+  const int cl = threadIdx.x % cpb, rl = threadIdx.x / cpb;
+  const int col = blockIdx.x * cpb + cl;
+  const int64_t r_begin = (int64_t)blockIdx.y * rows_per_block;
   const int64_t r_end = min(R, r_begin + rows_per_block);
-  for (int col = threadIdx.x; col < ncol; col += blockDim.x) {
-    float s[8] = {0};
-    for (int64_t r = r_begin; r < r_end; ++r) {
+  float s[8] = {0};
+  if (col < ncol && rl < lanes) {
+    const T *base = x + col * 8;
+    int64_t r = r_begin + rl;
+    for (; r + 3 * lanes < r_end; r += 4 * lanes) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = ld_stream(base + (r + (int64_t)k * lanes) * C);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        unpack8<T>(u[k], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[i] += f[i];
+      }
+    }
+    for (; r < r_end; r += lanes) {
       float f[8];
-      unpack8<T>(ld_stream(x + r * C + col * 8), f);
+      unpack8<T>(ld_stream(base + r * C), f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) s[i] += f[i];
     }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = s[i];
+  __syncthreads();
+  if (rl == 0 && col < ncol) {
+    for (int l = 1; l < lanes; ++l)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += red[(l * cpb + cl) * 8 + i];
 #pragma unroll
     for (int i = 0; i < 8; ++i) atomicAdd(out + col * 8 + i, s[i]);
   }
@@ -821,9 +849,15 @@ extern "C" int b200_transpose16(const void *src, void *dst, float *colsum, int64
 
 extern "C" int b200_colsum16(const void *x, float *out, int64_t R, int C, int act_dtype, void *stream) {
   B200_CHECK(x && out && R > 0 && C > 0 && C % 8 == 0, "colsum16: bad arguments");
-  const int rpb = (int)std::max<int64_t>(16, cdiv64(R, (int64_t)num_sms() * 8));
-  const int blocks = (int)cdiv64(R, rpb);
-#define L_(TT, ...) colsum16_kernel<TT><<<blocks, 128, 0, (cudaStream_t)stream>>>((const TT *)x, out, R, C, rpb)
+  const int ncol = C / 8;
+  int cpb = 64;
+  while (cpb > ncol && cpb > 1) cpb >>= 1;               // power of two <= 64 (a partial last column block is masked)
+  const int gx = cdiv(ncol, cpb);
+  const int lanes = 256 / cpb;
+  int gy = std::max(1, std::min((int)cdiv64(R, (int64_t)lanes * 8), num_sms() * 4 / gx));
+  const int rpb = (int)cdiv64(R, gy);
+  gy = (int)cdiv64(R, rpb);
+#define L_(TT, ...) colsum16_kernel<TT><<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>((const TT *)x, out, R, C, rpb, cpb)
   B200_ACT_DISPATCH(L_, 0);
 #undef L_
   B200_LAUNCH_CHECK();

@@ -6,6 +6,7 @@ kernel (``ops.conv2d``): forward ``y = x W^T``, dgrad ``dx = dy W`` (a linear wi
 ``dW = dy^T x`` (both token-major operands transposed to K-major, fp32 result, forced split-K over the token axis)."""
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -15,6 +16,7 @@ from . import ops
 from .ops import _dev, _f32, _p, _stream, _timed, act_code
 
 Tensor = torch.Tensor
+_NO_MN_WGRAD = os.environ.get("B200DIFF_WGRAD_TRANSPOSE", "0") == "1"
 
 
 def transpose16(x: Tensor, colsum_out: Optional[Tensor] = None) -> Tensor:
@@ -216,9 +218,28 @@ def wgrad_split(o: int, i: int, t: int) -> int:
 
 def linear_wgrad(dy: Tensor, x: Tensor, db: Optional[Tensor] = None, out: Optional[Tensor] = None) -> Tensor:
     """dW [O, I] fp32 = dy^T x for token-major dy [T, O], x [T, I] (16-bit).  T, O, I multiples of 8.
-    ``db`` (fp32 [O], overwritten): the bias gradient sum_t dy[t], fused into dy's transpose pass."""
+    ``db`` (fp32 [O], overwritten): the bias gradient sum_t dy[t].
+
+    O and I multiples of 64 (every Linear of a DiT block): the MN-major tcgen05 GEMM reads dy and x as they are
+    (b200_linear_wgrad) and the bias gradient is one column-sum pass.  Otherwise (patch embedding, final layer: 16-wide
+    operands) both operands are transposed to K-major — the bias gradient comes out of dy's transpose pass — and the
+    implicit-GEMM kernel runs with a forced K split."""
     t, o = dy.shape
     i = x.shape[1]
+    if o % 64 == 0 and i % 64 == 0 and not _NO_MN_WGRAD:
+        _dev(dy)
+        if out is None:
+            out = torch.empty((o, i), device=dy.device, dtype=torch.float32)
+        elif out.dtype != torch.float32 or out.numel() != o * i or not out.is_contiguous():
+            raise L.B200Error("linear_wgrad: out must be a contiguous fp32 [O, I] tensor")
+        splits = int(L.lib().b200_wgrad_splits(t, o, i))
+        ws = ops._workspace(dy.device, splits * o * i * 4) if splits > 1 else None
+        _timed("wgrad_tn", 2.0 * t * o * i, 2.0 * (dy.numel() + x.numel()) + 4.0 * o * i,
+               lambda: L.check(L.lib().b200_linear_wgrad(_p(dy), _p(x), _p(out), _p(ws), t, o, i, act_code(dy.dtype), _stream()),
+                               "linear_wgrad"), detail=f"T{t} {o}x{i} S{splits}")
+        if db is not None:
+            colsum(dy, db)
+        return out.view(o, i)
     dyt, xt = transpose16(dy, db), transpose16(x)               # K-major rows: [O, T], [I, T]
     res = ops.conv2d([(_img(dyt), xt.view(1, i, t), 0, 1, 0)], out_f32=True, force_ksplit=wgrad_split(o, i, t), out=out)
     return res.view(o, i)

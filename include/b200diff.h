@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 13
+#define B200_ABI_VERSION 14
 #define B200_F16 0
 #define B200_BF16 1
 
@@ -344,6 +344,13 @@ int b200_advance_step(int *step_ptr, int delta, void *stream);
 int b200_transpose16(const void *src, void *dst, float *colsum, int64_t R, int C, int act_dtype, void *stream);
 /* out[c] += sum_r x[r, c]  (bias gradients; fp32, zero `out` first) */
 int b200_colsum16(const void *x, float *out, int64_t R, int C, int act_dtype, void *stream);
+/* dW[M, N] fp32 = dy^T x for TOKEN-MAJOR 16-bit dy [T, M], x [T, N] (the weight gradient of y = x W^T over all T tokens of
+ * the batch) on tcgen05 with both operands read MN-major straight from those tensors — no transposed copies.  M, N multiples
+ * of 64, T of 8.  b200_wgrad_splits(T, M, N) K splits (geometry only) write fp32 partial planes to `workspace`
+ * (>= splits * M * N floats; may be NULL when the factor is 1) that are summed in fixed order.                           */
+int b200_wgrad_splits(int64_t T, int M, int N);
+int b200_linear_wgrad(const void *dy, const void *x, float *out, float *workspace, int64_t T, int M, int N, int act_dtype,
+                      void *stream);
 /* GELU(tanh) on a stored pre-activation, and its backward dpre = du * gelu'(pre)  (timm Mlp, DiT_models.py:111-112) */
 int b200_gelu_fwd(const void *pre, void *out, int64_t n, int act_dtype, void *stream);
 int b200_gelu_bwd(const void *pre, const void *du, void *dpre, int64_t n, int act_dtype, void *stream);
