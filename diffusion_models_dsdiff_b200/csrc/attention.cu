@@ -81,6 +81,10 @@ __global__ void __launch_bounds__(kFaThreads, (D <= 64) ? 2 : 1)
 flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
   constexpr int kDB = D / 8;                         // 16-byte channel blocks per row
   constexpr uint32_t kTileBytes = kDB * kBlkBytes;   // Q / K / V tile: D x 128 x 2 B
+  // D == 64: a token row is one 128-byte swizzle row, so every Q / K / V tile is ONE SWIZZLE_128B TMA box (128 row fetches of
+  // 128 B instead of 1024 of 16 B) whose shared-memory image is the canonical K-major tile for Q K^T and the canonical
+  // MN-major tile for P V (see attention_bwd.cu)
+  constexpr bool kSw = (D == 64);
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t q_full, o_full;
   __shared__ __align__(8) uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2];
@@ -95,7 +99,7 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
   const int h = blockIdx.y, b = blockIdx.z;
   const int nk = (p.Lk + kFaBN - 1) / kFaBN;
 
-  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B tiles: 1024-byte alignment
   const uint32_t sQ = base;
   const uint32_t sK = sQ + kTileBytes;
   const uint32_t sV = sK + p.stages * kTileBytes;
@@ -128,7 +132,7 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
     if (lane == 0) {
       const uint32_t qb = smem_u32(&q_full);
       mbar_arrive_expect_tx(qb, kTileBytes);
-      for (int c = 0; c < kDB; ++c)
+      for (int c = 0; c < (kSw ? 1 : kDB); ++c)
         tma_load_3d(sQ + c * kBlkBytes, &maps.q, qb, p.q_off + h * p.q_hstride + c * 8, q0, b);
       int ks = 0, vs = 0;
       uint32_t kph = 0, vph = 0;
@@ -136,14 +140,14 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
         mbar_wait(smem_u32(&k_empty[ks]), kph ^ 1);
         const uint32_t kb = smem_u32(&k_full[ks]);
         mbar_arrive_expect_tx(kb, kTileBytes);
-        for (int c = 0; c < kDB; ++c)
+        for (int c = 0; c < (kSw ? 1 : kDB); ++c)
           tma_load_3d(sK + ks * kTileBytes + c * kBlkBytes, &maps.k, kb, p.k_off + h * p.k_hstride + c * 8,
                       j * kFaBN, b);
         if (++ks == p.stages) { ks = 0; kph ^= 1; }
         mbar_wait(smem_u32(&v_empty[vs]), vph ^ 1);
         const uint32_t vb = smem_u32(&v_full[vs]);
         mbar_arrive_expect_tx(vb, kTileBytes);
-        for (int c = 0; c < kDB; ++c)
+        for (int c = 0; c < (kSw ? 1 : kDB); ++c)
           tma_load_3d(sV + vs * kTileBytes + c * kBlkBytes, &maps.v, vb, p.v_off + h * p.v_hstride + c * 8,
                       j * kFaBN, b);
         if (++vs == p.stages) { vs = 0; vph ^= 1; }
@@ -165,8 +169,9 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           // 16 channels = 2 core-matrix columns: advance 2 * LBO
-          const uint64_t da = umma_desc_nosw(sQ + kk * 2 * kBlkBytes, kBlkBytes, 128);
-          const uint64_t db = umma_desc_nosw(sK + ks * kTileBytes + kk * 2 * kBlkBytes, kBlkBytes, 128);
+          const uint64_t da = kSw ? umma_desc_sw128(sQ) + (uint64_t)(kk * 2) : umma_desc_nosw(sQ + kk * 2 * kBlkBytes, kBlkBytes, 128);
+          const uint64_t db = kSw ? umma_desc_sw128(sK + ks * kTileBytes) + (uint64_t)(kk * 2)
+                                  : umma_desc_nosw(sK + ks * kTileBytes + kk * 2 * kBlkBytes, kBlkBytes, 128);
           umma_f16(tmem_base + sb * kFaSCols, da, db, p.idesc_s, kk > 0);
         }
         umma_commit(smem_u32(&k_empty[ks]));
@@ -187,7 +192,8 @@ flash_attn_kernel(const __grid_constant__ FaMaps maps, const FaParams p) {
           const uint64_t da = umma_desc_nosw(sP + pb * kFaPBytes + kk * 2 * kBlkBytes, kBlkBytes, 128);
           // B = V, MN-major [channel block][key][8 ch]: along K (keys) core matrices are 128 B apart,
           // along N (channels) 2048 B apart.
-          const uint64_t db = umma_desc_nosw(sV + vs * kTileBytes + kk * 2 * 128, 128, kBlkBytes);
+          const uint64_t db = kSw ? umma_desc_sw128(sV + vs * kTileBytes + kk * 2048)      // 8-key atoms 1024 B apart
+                                  : umma_desc_nosw(sV + vs * kTileBytes + kk * 2 * 128, 128, kBlkBytes);
           umma_f16(tmem_o, da, db, p.idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(smem_u32(&v_empty[vs]));
@@ -354,9 +360,9 @@ static int launch_flash(const AttnArgs &a, cudaStream_t st) {
   for (int i = 0; i < 3; ++i) {
     uint64_t dims[3] = {(uint64_t)ld[i], (uint64_t)len[i], (uint64_t)a.B};
     uint64_t str[2] = {(uint64_t)ld[i] * 2, (uint64_t)len[i] * ld[i] * 2};
-    uint32_t box[3] = {8, 128, 1};
+    uint32_t box[3] = {(uint32_t)(D == 64 ? 64 : 8), 128, 1};
     uint32_t es[3] = {1, 1, 1};
-    if (int rc = cached_tmap(mp[i], ptr[i], 3, dims, str, box, es, /*swizzle128=*/false)) return rc;
+    if (int rc = cached_tmap(mp[i], ptr[i], 3, dims, str, box, es, /*swizzle128=*/D == 64)) return rc;
   }
   p.Lq = a.Lq; p.Lk = a.Lk; p.heads = a.heads; p.B = a.B;
   p.q_off = a.q_off; p.k_off = a.k_off; p.v_off = a.v_off;
@@ -373,7 +379,7 @@ static int launch_flash(const AttnArgs &a, cudaStream_t st) {
   const size_t budget = (D <= 64) ? 108 * 1024 : 200 * 1024;
   p.pbufs = (tile * 3 + 2 * kFaPBytes + 256 <= budget) ? 2 : 1;      // D = 64: one P buffer so that two CTAs fit
   p.stages = (tile * 5 + p.pbufs * kFaPBytes + 256 <= budget) ? 2 : 1;
-  const size_t smem = tile * (1 + 2 * p.stages) + p.pbufs * kFaPBytes + 256;
+  const size_t smem = tile * (1 + 2 * p.stages) + p.pbufs * kFaPBytes + 1024;
   B200_CHECK(smem <= 220 * 1024, "attention: head dim %d does not fit shared memory", D);
   static bool attr_set = false;
   if (!attr_set) {

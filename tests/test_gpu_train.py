@@ -112,15 +112,22 @@ def test_attention_backward_matches_autograd(dt, shape):
 
 
 @pytest.mark.parametrize("dt", DTYPES)
-@pytest.mark.parametrize("t_o_i", [(192, 384, 128), (4096, 768, 768), (2048, 16, 768), (1024, 128, 16)])
+@pytest.mark.parametrize("t_o_i", [(192, 384, 128), (4096, 768, 768), (2048, 16, 768), (1024, 128, 16),
+                                   (520, 192, 320), (8192, 2304, 768), (40, 64, 64)])
 def test_linear_wgrad_on_tensor_cores(dt, t_o_i):
+    """MN-major wgrad_tn kernel (O, I multiples of 64: ragged 128 x 256 tiles, token counts that are not a multiple of the
+    64-token chunk, K splits) and the transposing fallback (16-wide operands), with the bias gradient."""
     T = _T()
     t, o, i = t_o_i
     dy, x = rnd(12, t, o).to(dt), rnd(13, t, i).to(dt)
-    got = T.linear_wgrad(dy.cuda(), x.cuda())
+    db = torch.full((o,), 7.0, device="cuda")
+    got = T.linear_wgrad(dy.cuda(), x.cuda(), db)
     want = dy.float().t() @ x.float()
     assert got.dtype == torch.float32 and tuple(got.shape) == (o, i)
     assert rel(got, want) < 1e-5          # operands are exact 16-bit values; fp32 accumulation / split-K order only
+    assert rel(db, dy.float().sum(0)) < 1e-5
+    out = torch.zeros(o, i, device="cuda")
+    assert T.linear_wgrad(dy.cuda(), x.cuda(), out=out).data_ptr() == out.data_ptr() and rel(out, want) < 1e-5
 
 
 @pytest.mark.parametrize("param,learn_sigma,rescaled", [("v", True, False), ("eps", True, True), ("x0", False, False)])
