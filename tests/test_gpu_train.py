@@ -287,3 +287,52 @@ def test_graph_replayed_training_steps_equal_eager_steps():
     # fp32 atomics (column sums) add in a run-dependent order, and Adam turns near-zero gradients into +-lr steps:
     # mean, not max
     assert float((p0 - p1).abs().mean()) < 0.05 * 1e-3
+
+
+def test_dit_b2_training_step_at_the_baseline_size_vs_oracle_autograd():
+    """BASELINE cfg5 at its real size — DiT-B/2 (12 x 768, 12 heads of 64), 64 x 64 x (1 + 3) input = 1024 tokens, bf16 —
+    on two samples: loss terms and gradients against torch autograd through the CPU oracle's restated forward + objective
+    (which tests/test_training_oracle.py pins to the reference's own training step on the small fixtures)."""
+    import bench
+    import diffusion_models_dsdiff_b200 as P
+    from diffusion_models_dsdiff_b200 import samplers as S
+    from diffusion_models_dsdiff_b200.dit_train import DiTTrainer
+    hp = dict(bench.CFG5)
+    torch.manual_seed(0)
+    net = P.DiT(**hp, act_dtype=torch.bfloat16)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for p_ in net.parameters():
+            if p_.requires_grad and not p_.detach().any():
+                p_.copy_(torch.randn(p_.shape, generator=g) * 0.02)       # adaLN-Zero / zero heads would zero most gradients
+    sd = {k: v.detach().clone().float() for k, v in net.state_dict().items()}
+    net = net.cuda()
+    gd = S.create_gaussian_diffusion(steps=1000, learn_sigma=True, noise_schedule="linear", rescale_timesteps=True,
+                                     timestep_respacing="", parameterization="v")
+    tr = DiTTrainer(net, gd, lr=1e-4, act_dtype=torch.bfloat16)
+    n, s = 2, hp["input_size"]
+    x0 = torch.clamp(rnd(301, n, 1, s, s) * 0.5, -1, 1)
+    cond = [torch.clamp(rnd(302 + i, n, 1, s, s) * 0.5, -1, 1) for i in range(3)]
+    noise = rnd(310, n, 1, s, s)
+    t = torch.tensor([37, 812])
+    out = tr.training_step(x0, t, cond=cond, noise=noise, update=False)
+    grads = tr.grads()
+    # oracle: same weights, fp32, autograd
+    sdg = {k: (v.clone().requires_grad_(True) if k != "pos_embed" else v) for k, v in sd.items()}
+    sch = O.GdSchedule(steps=1000, noise_schedule="linear", timestep_respacing="", rescale_timesteps=True)
+    ohp = dict(patch_size=hp["patch_size"], hidden_size=hp["hidden_size"], depth=hp["depth"], num_heads=hp["num_heads"],
+               in_channels=hp["in_channels"], learn_sigma=True)
+    terms = TO.training_losses(sch, lambda xc, tm: O.dit_forward(sdg, ohp, xc, tm), x0, t, noise, cond, parameterization="v",
+                               learn_sigma=True)
+    total = terms["loss"].mean()
+    total.backward()
+    assert abs(float(out["loss"]) - float(total)) < 3e-2 * abs(float(total))
+    assert rel(tr.last_terms[:, 0], terms["mse"].detach()) < 3e-2
+    worst = 0.0
+    for k in ("final_layer.linear.weight", "blocks.11.mlp.fc2.weight", "blocks.11.attn.qkv.weight", "blocks.6.attn.proj.weight",
+              "blocks.6.mlp.fc1.bias", "blocks.0.attn.qkv.weight", "blocks.0.adaLN_modulation.1.weight", "x_embedder.proj.weight",
+              "t_embedder.mlp.0.weight", "final_layer.adaLN_modulation.1.bias"):
+        r = rel(grads[k].reshape(sdg[k].grad.shape), sdg[k].grad)
+        worst = max(worst, r)
+        assert r < 1.5e-1, (k, r)        # bf16 activations + activation gradients through 12 blocks
+    print(f"\n[cfg5 full size] loss {float(out['loss']):.5f} vs oracle {float(total):.5f}; worst gradient rel L2 {worst:.3e}")
