@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200diff.so")
 
-ABI_VERSION = 14        # must equal B200_ABI_VERSION of the header the library was built from
+ABI_VERSION = 15        # must equal B200_ABI_VERSION of the header the library was built from
 F16, BF16 = 0, 1
 SAMPLER_LDM_DDIM, SAMPLER_LDM_DDPM, SAMPLER_GD_DDIM, SAMPLER_GD_DDPM, SAMPLER_DPMPP_2M = 0, 1, 2, 3, 4
 SAMPLER_NCOEF = 16
@@ -37,7 +37,7 @@ class ConvDesc(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("range_events", C.c_void_p),
                 ("wsets", C.c_int), ("rowbias_gstride", C.c_int), ("rowscale_gstride", C.c_int),
                 ("out_sy", C.c_int), ("out_sx", C.c_int), ("out_oy", C.c_int), ("out_ox", C.c_int),
-                ("force_ksplit", C.c_int)]
+                ("force_ksplit", C.c_int), ("out_lo", C.c_void_p), ("residual_lo", C.c_void_p)]
 
 
 class SamplerDesc(C.Structure):
@@ -69,12 +69,12 @@ SIGNATURES = {
     "b200_pack_conv_weight": [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_conv2d_igemm": [C.POINTER(ConvDesc), _P],
     "b200_conv_ksplit": [C.POINTER(ConvDesc)],
-    "b200_conv3x3_in": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I, _P],
+    "b200_conv3x3_in": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P],
     "b200_conv3x3_out": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "b200_groupnorm_stats": [_P, _I, _P, _I, _I, _I, _I, _P, _I, _P],
     "b200_groupnorm_apply": [_P, _I, _P, _I, _I, _I, _I, _F, _P, _P, _P, _P, _I, _I, _P, _I, _P],
     "b200_channel_stats": [_P, _I, _I, _I, _P, _I, _P],
-    "b200_groupnorm_apply_cs": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P],
+    "b200_groupnorm_apply_cs": [_P, _I, _P, _P, _I, _P, _I, _I, _I, _F, _P, _P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P],
     "b200_attention_qkv": [_P, _P, _I, _I, _I, _I, _I, _F, _I, _P],
     "b200_attention": [C.POINTER(AttnDesc), _P],
     "b200_layernorm": [_P, _P, _P, _P, _P, _I, _I, _L, _I, _F, _P, _I, _P],
@@ -93,7 +93,7 @@ SIGNATURES = {
     "b200_upsample_nearest2x": [_P, _P, _I, _I, _I, _I, _I, _P],
     "b200_avgpool2x": [_P, _P, _I, _I, _I, _I, _I, _P],
     "b200_add4_scale": [_P, _P, _P, _P, _F, _P, _L, _I, _I, _P],
-    "b200_add4_scale_stats": [_P, _P, _P, _P, _F, _P, _I, _I, _I, _P, _I, _P],
+    "b200_add4_scale_stats": [_P, _P, _P, _P, _F, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P],
     "b200_se_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "b200_sampler_update": [C.POINTER(SamplerDesc), _P],
     "b200_abs_quantile": [_P, _I, _L, _F, _F, _P, _P],

@@ -64,6 +64,8 @@ struct ConvKParams {
   unsigned int *range_events; // fp16 only: += 1 per (thread, tile) that had to saturate a result (see b200diff.h)
   int wsets, n_per_set;      // grouped along N: image n uses weight set n / n_per_set (wsets == 1: n_per_set = N)
   int rowbias_gstride, rowscale_gstride;
+  void *out_lo;              // low 16-bit plane of `out` (b200_conv_desc.out_lo): out + out_lo = the fp32 result
+  const void *residual_lo;   // low plane of `residual`
 };
 
 template <typename T> struct IsHalf { static constexpr bool value = false; };
@@ -369,6 +371,8 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
     const int tn = m / (p.TW * p.TH);
     T *out = reinterpret_cast<T *>(p.out);
     const T *res = reinterpret_cast<const T *>(p.residual);
+    T *out_lo = reinterpret_cast<T *>(p.out_lo);
+    const T *res_lo = reinterpret_cast<const T *>(p.residual_lo);
     // GroupNorm statistics: per-warp fp32 column accumulators in shared memory, flushed to the fp64 global sums only
     // when the warp moves to another image / N tile (a persistent CTA stays ~7 tiles inside one image).
     float *st_sum = reinterpret_cast<float *>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * stage_bytes) + ew * 256;
@@ -458,6 +462,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
         const char *rrow = reinterpret_cast<const char *>(res + pix * p.Cout + n_tile * p.BN);
         const int rbytes = min(p.BN, p.Cout - n_tile * p.BN) * 2;
         for (int o = g * 128; o < rbytes; o += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + o));
+        if (res_lo) {
+          const char *lrow = reinterpret_cast<const char *>(res_lo + pix * p.Cout + n_tile * p.BN);
+          for (int o = g * 128; o < rbytes; o += 256) asm volatile("prefetch.global.L2 [%0];" ::"l"(lrow + o));
+        }
       }
       mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
       tc_fence_after();
@@ -513,6 +521,17 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
               v[2 * j + 1] = fmaf(p.res_scale, f.y, v[2 * j + 1]);
             }
           }
+          if (res_lo) {      // low plane of the residual (prefetched into L2 above; loaded here to keep the register budget)
+            uint4 lq[2];
+            ld_global_256(res_lo + pix * p.Cout + co, lq[0], lq[1]);
+            const uint32_t *lw = reinterpret_cast<const uint32_t *>(lq);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float2 f = unpack2<T>(lw[j]);
+              v[2 * j] = fmaf(p.res_scale, f.x, v[2 * j]);
+              v[2 * j + 1] = fmaf(p.res_scale, f.y, v[2 * j + 1]);
+            }
+          }
           if (guard) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(v[i]));
@@ -520,6 +539,19 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
           packed[0] = pack8_sat<T>(v);
           packed[1] = pack8_sat<T>(v + 8);
           st_global_256(out + pix * p.Cout + co, packed[0], packed[1]);
+          if (out_lo) {      // what the 16-bit store dropped
+            const uint32_t *hw = reinterpret_cast<const uint32_t *>(packed);
+            float d0[8], d1[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack2<T>(hw[j]), f1 = unpack2<T>(hw[j + 4]);
+              d0[2 * j] = v[2 * j] - f.x;
+              d0[2 * j + 1] = v[2 * j + 1] - f.y;
+              d1[2 * j] = v[8 + 2 * j] - f1.x;
+              d1[2 * j + 1] = v[8 + 2 * j + 1] - f1.y;
+            }
+            st_global_256(out_lo + pix * p.Cout + co, pack8_fast<T>(d0), pack8_fast<T>(d1));
+          }
           if (p.gn_sums) {
             // column sums of the STORED values through the transpose tile: lane = (column pair, row mod 4)
             __syncwarp();
@@ -594,6 +626,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
               unpack8<T>(rq[half], rf);
 #pragma unroll
               for (int i = 0; i < 8; ++i) vh[i] += p.res_scale * rf[i];
+              if (res_lo) {
+                unpack8<T>(*reinterpret_cast<const uint4 *>(res_lo + pix * p.Cout + cb), rf);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vh[i] += p.res_scale * rf[i];
+              }
             }
             if (guard && !p.out_f32_nhwc && !p.out_f32) {
 #pragma unroll
@@ -610,6 +647,13 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
                   p.out_f32[(((size_t)n * p.cout_real + cb + i) * p.Hout + h) * p.Wout + w] = vh[i];
             } else {
               const uint4 pk = pack8<T>(vh);
+              if (out_lo) {
+                float hf[8];
+                unpack8<T>(pk, hf);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) hf[i] = vh[i] - hf[i];
+                *reinterpret_cast<uint4 *>(out_lo + pix * p.Cout + cb) = pack8_fast<T>(hf);
+              }
               if (p.gn_sums) unpack8<T>(pk, vh);      // statistics of the STORED values, exactly like the fast epilogue
               if (p.vec32) packed[half] = pk;
               else *reinterpret_cast<uint4 *>(out + pix * p.Cout + cb) = pk;
@@ -912,6 +956,7 @@ static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t
   p.n_per_set = d->N / p.wsets;
   p.out_sy = std::max(1, d->out_sy); p.out_sx = std::max(1, d->out_sx); p.out_oy = d->out_oy; p.out_ox = d->out_ox;
   p.rowbias_gstride = d->rowbias_gstride; p.rowscale_gstride = d->rowscale_gstride;
+  p.out_lo = d->out_lo; p.residual_lo = d->residual_lo;
   p.ksplit = ksplit;
   p.groups_total = conv_groups_total(d);
   p.split_stride = (long long)d->N * d->Hout * d->Wout * d->Cout;
@@ -1035,6 +1080,10 @@ extern "C" int b200_conv2d_igemm(const b200_conv_desc *d, void *stream) {
   B200_CHECK(d->force_ksplit <= 1 || (d->out_nhwc_f32 && !d->bias && !d->rowbias && !d->residual && !d->rowscale &&
                                       !d->epi_act && !d->gn_sums && std::max(1, d->wsets) == 1),
              "conv: force_ksplit is for plain fp32-output GEMMs (no epilogue terms)");
+  B200_CHECK((!d->out_lo && !d->residual_lo) ||
+                 (ksplit == 1 && d->out && !d->out_nchw_f32 && !d->out_nhwc_f32 && (!d->residual_lo || d->residual) &&
+                  (((uintptr_t)d->out_lo | (uintptr_t)d->residual_lo) & 31) == 0),
+             "conv: out_lo / residual_lo need a 16-bit NHWC out, 32-byte aligned planes, a residual for residual_lo and no split-K");
   if (ksplit > 1) {
     const size_t need = (size_t)ksplit * d->N * d->Hout * d->Wout * d->Cout * sizeof(float);
     B200_CHECK(d->workspace != nullptr && d->workspace_bytes >= need && ((uintptr_t)d->workspace & 15) == 0,

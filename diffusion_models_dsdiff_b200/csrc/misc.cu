@@ -72,7 +72,8 @@ __device__ __forceinline__ void unpack_f32x2(unsigned long long v, float &lo, fl
 template <typename T, bool kRegW>
 __global__ void __launch_bounds__(256)
 conv3x3_in_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
-                  T *__restrict__ out, int Cin, int H, int W, int Cout, int pix_per_block, double *__restrict__ sums) {
+                  T *__restrict__ out, int Cin, int H, int W, int Cout, int pix_per_block, double *__restrict__ sums,
+                  T *__restrict__ out_lo) {
   extern __shared__ float sw[];  // kRegW ? unused : [Cin*9][Cout]
   const int K = Cin * 9;
   if (!kRegW) {
@@ -150,6 +151,13 @@ conv3x3_in_kernel(const float *__restrict__ x, const float *__restrict__ w, cons
     for (int i = 0; i < 4; ++i) unpack_f32x2(acc[i], f[2 * i], f[2 * i + 1]);
     const uint4 u = pack8_sat<T>(f);
     st_stream(on + (size_t)p * Cout, u);
+    if (out_lo) {                       // what the 16-bit store dropped (b200_conv_desc.out_lo)
+      float hf[8];
+      unpack8<T>(u, hf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) hf[i] = f[i] - hf[i];
+      st_stream(out_lo + (size_t)n * HW * Cout + c0 + (size_t)p * Cout, pack8_fast<T>(hf));
+    }
     if (sums) {                         // statistics of the stored (rounded) values
       const uint32_t *uw = reinterpret_cast<const uint32_t *>(&u);
 #pragma unroll
@@ -504,7 +512,7 @@ extern "C" int b200_pack_conv_weight(const float *w, void *dst, int Cout, int Ci
 }
 
 extern "C" int b200_conv3x3_in(const float *x, const float *w, const float *bias, void *out, int N, int Cin,
-                               int H, int W, int Cout, double *sums, int act_dtype, void *stream) {
+                               int H, int W, int Cout, double *sums, void *out_lo, int act_dtype, void *stream) {
   B200_CHECK(x && w && out, "conv3x3_in: null pointer");
   B200_CHECK(Cin >= 1 && Cin <= 8, "conv3x3_in: Cin must be 1..8 (got %d)", Cin);
   B200_CHECK(Cout % 8 == 0 && Cout > 0 && Cout <= 2048, "conv3x3_in: Cout must be a multiple of 8, <= 2048");
@@ -518,11 +526,11 @@ extern "C" int b200_conv3x3_in(const float *x, const float *w, const float *bias
   const dim3 grid(cdiv(HW, ppb), N, 1);
   DISPATCH_ACT(act_dtype, {
     if (Cin == 1) {
-      conv3x3_in_kernel<T, true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, (T *)out, Cin, H, W, Cout, ppb, sums);
+      conv3x3_in_kernel<T, true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, (T *)out, Cin, H, W, Cout, ppb, sums, (T *)out_lo);
     } else {
       if (smem + 16 * 1024 > 48 * 1024)     // + the static reduction buffer of block_flush_col_sums
         B200_CUDA(cudaFuncSetAttribute(conv3x3_in_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      conv3x3_in_kernel<T, false><<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, bias, (T *)out, Cin, H, W, Cout, ppb, sums);
+      conv3x3_in_kernel<T, false><<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, bias, (T *)out, Cin, H, W, Cout, ppb, sums, (T *)out_lo);
     }
   })
   B200_LAUNCH_CHECK();

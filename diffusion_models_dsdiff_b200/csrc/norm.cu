@@ -120,12 +120,12 @@ channel_stats_kernel(const T *__restrict__ x, int C, int HW, int pix_per_block, 
   block_flush_col_sums(s, q, active, row, col, ncol, rows, sums + ((size_t)n * C + col * 8) * 2);
 }
 
-// dst = scale * (a + b + c + d) with the per-(image, channel) statistics of dst accumulated on the fly (DS-Diff skip mean,
-// UNet_DS_Diff/model.py:745, whose result feeds the decoder's GroupNorm).  Thread mapping as channel_stats_kernel.
-template <typename T>
-__global__ void __launch_bounds__(kNormThreads)
-add4_stats_kernel(const T *__restrict__ a, const T *__restrict__ b, const T *__restrict__ c, const T *__restrict__ d,
-                  float scale, T *__restrict__ dst, int C, int HW, int pix_per_block, double *__restrict__ sums) {
+template <typename T, bool kLo>
+__device__ __forceinline__ void
+add4_stats_body(const T *__restrict__ a, const T *__restrict__ b, const T *__restrict__ c, const T *__restrict__ d,
+                float scale, T *__restrict__ dst, int C, int HW, int pix_per_block, double *__restrict__ sums,
+                const T *__restrict__ a_lo, const T *__restrict__ b_lo, const T *__restrict__ c_lo,
+                const T *__restrict__ d_lo, T *__restrict__ dst_lo) {
   const int n = blockIdx.y;
   const int ncol = C >> 3;
   const int rows = kNormThreads / ncol;
@@ -138,11 +138,22 @@ add4_stats_kernel(const T *__restrict__ a, const T *__restrict__ b, const T *__r
   const size_t base = (size_t)n * HW * C + col * 8;
   const int nin = 1 + (b != nullptr) + (c != nullptr) + (d != nullptr);
   const T *src[4] = {a, b, c, d};
+  const T *los[4] = {a_lo, b_lo, c_lo, d_lo};
+  (void)los;
   auto finish = [&](float (&f)[8], size_t off) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] *= scale;
     const uint4 u = pack8_fast<T>(f);     // a mean of stored 16-bit values cannot overflow
     st_stream(dst + off, u);
+    if constexpr (kLo) {
+      if (dst_lo) {
+        float hf[8];
+        unpack8<T>(u, hf);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hf[i] = f[i] - hf[i];
+        st_stream(dst_lo + off, pack8_fast<T>(hf));
+      }
+    }
     unpack8<T>(u, f);                     // statistics of the stored (rounded) values, like channel_stats on dst
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] += f[i]; q[i] += f[i] * f[i]; }
@@ -165,6 +176,19 @@ add4_stats_kernel(const T *__restrict__ a, const T *__restrict__ b, const T *__r
 #pragma unroll
         for (int i = 0; i < 8; ++i) f1[i] += g[i];
       }
+    if constexpr (kLo) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < nin && los[j]) {
+          const uint4 l0 = ld_stream(los[j] + off0), l1 = ld_stream(los[j] + off1);
+          unpack8<T>(l0, g);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f0[i] += g[i];
+          unpack8<T>(l1, g);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f1[i] += g[i];
+        }
+    }
     finish(f0, off0);
     finish(f1, off1);
   }
@@ -177,14 +201,40 @@ add4_stats_kernel(const T *__restrict__ a, const T *__restrict__ b, const T *__r
         unpack8<T>(ld_stream(src[j] + off), g);
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] += g[i];
+        if constexpr (kLo) {
+          if (los[j]) {
+            unpack8<T>(ld_stream(los[j] + off), g);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] += g[i];
+          }
+        }
       }
     finish(f, off);
   }
   block_flush_col_sums(s, q, active, row, col, ncol, rows, sums + ((size_t)n * C + col * 8) * 2);
 }
 
-// y = silu?( (x - mean_g) * rstd_g * gamma_c + beta_c ) [ * (1 + scale_nc) + shift_nc ]
+// dst = scale * (a + b + c + d) with the per-(image, channel) statistics of dst accumulated on the fly (DS-Diff skip mean,
+// UNet_DS_Diff/model.py:745, whose result feeds the decoder's GroupNorm).  Thread mapping as channel_stats_kernel.
 template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+add4_stats_kernel(const T *__restrict__ a, const T *__restrict__ b, const T *__restrict__ c, const T *__restrict__ d,
+                  float scale, T *__restrict__ dst, int C, int HW, int pix_per_block, double *__restrict__ sums) {
+  add4_stats_body<T, false>(a, b, c, d, scale, dst, C, HW, pix_per_block, sums, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+// the same with LOW planes (b200_conv_desc.out_lo) of some sources added in and / or a low plane of the result written
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+add4_stats_lo_kernel(const T *__restrict__ a, const T *__restrict__ b, const T *__restrict__ c, const T *__restrict__ d,
+                     float scale, T *__restrict__ dst, int C, int HW, int pix_per_block, double *__restrict__ sums,
+                     const T *__restrict__ a_lo, const T *__restrict__ b_lo, const T *__restrict__ c_lo,
+                     const T *__restrict__ d_lo, T *__restrict__ dst_lo) {
+  add4_stats_body<T, true>(a, b, c, d, scale, dst, C, HW, pix_per_block, sums, a_lo, b_lo, c_lo, d_lo, dst_lo);
+}
+
+// y = silu?( (x - mean_g) * rstd_g * gamma_c + beta_c ) [ * (1 + scale_nc) + shift_nc ]
+template <typename T, bool kLo>
 __global__ void __launch_bounds__(kNormThreads, 4)
 gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int C1, int HW,
                 int groups, float eps, int pix_per_block, const double *__restrict__ stats,
@@ -192,7 +242,8 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
                 const float *__restrict__ gamma, const float *__restrict__ beta,
                 const float *__restrict__ film, int film_stride, int silu, T *__restrict__ out,
                 const float *__restrict__ preshift, int preshift_stride, int pdl, int n_per_set, int film_gstride,
-                int preshift_gstride) {
+                int preshift_gstride, const T *__restrict__ x0_lo, const T *__restrict__ x1_lo) {
+  // kLo: a source may come with a LOW plane (b200_conv_desc.out_lo): the value normalised is x + x_lo
   if (pdl) {      // programmatic dependent launch (see igemm_conv.cu): wait for the producer, release the consumer
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -280,6 +331,40 @@ gn_apply_kernel(const T *__restrict__ x0, int C0, const T *__restrict__ x1, int 
     const int Cs = from0 ? C0 : C1;
     T *dst = out + (size_t)n * HW * C + c;
     int p = p_begin + row;
+    if constexpr (kLo) {
+      const T *lo = from0 ? x0_lo : x1_lo;
+      if (lo != nullptr) {
+        lo += (size_t)n * HW * Cs + (from0 ? c : c - C0);
+        for (; p + rows < p_end; p += 2 * rows) {
+          uint4 u[2], ul[2];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            u[j] = ld_stream(src + (size_t)(p + j * rows) * Cs);
+            ul[j] = ld_stream(lo + (size_t)(p + j * rows) * Cs);
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            float f[8], fl[8];
+            unpack8<T>(u[j], f);
+            unpack8<T>(ul[j], fl);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i] + fl[i], a[i], b[i]);
+            if (silu) silu8(f);
+            st_stream(dst + (size_t)(p + j * rows) * C, pack8_fast<T>(f));
+          }
+        }
+        for (; p < p_end; p += rows) {
+          float f[8], fl[8];
+          unpack8<T>(ld_stream(src + (size_t)p * Cs), f);
+          unpack8<T>(ld_stream(lo + (size_t)p * Cs), fl);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i] + fl[i], a[i], b[i]);
+          if (silu) silu8(f);
+          st_stream(dst + (size_t)p * C, pack8_fast<T>(f));
+        }
+        continue;
+      }
+    }
     for (; p + 3 * rows < p_end; p += 4 * rows) {
       uint4 u[4];
 #pragma unroll
@@ -341,7 +426,7 @@ static int gn_apply(const void *x0, int C0, const void *x1, int C1, int N, int H
                     float eps, const double *stats, const double *cs0, const double *cs1, const float *gamma,
                     const float *beta, const float *film, int film_stride, int silu, void *out, cudaStream_t st,
                     const float *preshift = nullptr, int preshift_stride = 0, int wsets = 1, int film_gstride = 0,
-                    int preshift_gstride = 0) {
+                    int preshift_gstride = 0, const void *x0_lo = nullptr, const void *x1_lo = nullptr) {
   wsets = std::max(1, wsets);
   B200_CHECK(N % wsets == 0, "groupnorm: N (%d) must be a multiple of the number of weight sets (%d)", N, wsets);
   dim3 grid;
@@ -357,9 +442,14 @@ static int gn_apply(const void *x0, int C0, const void *x1, int C1, int N, int H
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  B200_CUDA(cudaLaunchKernelEx(&cfg, gn_apply_kernel<T>, (const T *)x0, C0, (const T *)x1, C1, HW, groups, eps, ppb, stats, cs0,
-                               cs1, gamma, beta, film, film_stride, silu, (T *)out, preshift, preshift_stride, (int)pdl, N / wsets,
-                               film_gstride, preshift_gstride));
+  if (x0_lo || x1_lo)
+    B200_CUDA(cudaLaunchKernelEx(&cfg, gn_apply_kernel<T, true>, (const T *)x0, C0, (const T *)x1, C1, HW, groups, eps, ppb, stats,
+                                 cs0, cs1, gamma, beta, film, film_stride, silu, (T *)out, preshift, preshift_stride, (int)pdl,
+                                 N / wsets, film_gstride, preshift_gstride, (const T *)x0_lo, (const T *)x1_lo));
+  else
+    B200_CUDA(cudaLaunchKernelEx(&cfg, gn_apply_kernel<T, false>, (const T *)x0, C0, (const T *)x1, C1, HW, groups, eps, ppb, stats,
+                                 cs0, cs1, gamma, beta, film, film_stride, silu, (T *)out, preshift, preshift_stride, (int)pdl,
+                                 N / wsets, film_gstride, preshift_gstride, (const T *)nullptr, (const T *)nullptr));
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -402,26 +492,48 @@ extern "C" int b200_groupnorm_apply_cs(const void *x0, int C0, const double *cs0
                                        const double *cs1, int N, int HW, int groups, float eps, const float *gamma,
                                        const float *beta, const float *film, int film_stride, int silu, void *out,
                                        const float *preshift, int preshift_stride, int wsets, int film_gstride,
-                                       int preshift_gstride, int act_dtype, void *stream) {
+                                       int preshift_gstride, const void *x0_lo, const void *x1_lo, int act_dtype,
+                                       void *stream) {
   using namespace b200;
   if (x1 == nullptr) C1 = 0;
   if (int rc = check_gn(C0, C1, N, HW, groups)) return rc;
   B200_CHECK(cs0 != nullptr && (C1 == 0 || cs1 != nullptr), "groupnorm_apply_cs: missing channel sums");
+  if (C1 == 0) x1_lo = nullptr;
+  B200_CHECK(!(preshift && x0_lo), "groupnorm_apply_cs: preshift and a low plane of x0 cannot be combined");
   if (act_dtype == B200_F16)
-    return gn_apply<__half>(x0, C0, x1, C1, N, HW, groups, eps, nullptr, cs0, cs1, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream, preshift, preshift_stride, wsets, film_gstride, preshift_gstride);
+    return gn_apply<__half>(x0, C0, x1, C1, N, HW, groups, eps, nullptr, cs0, cs1, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream, preshift, preshift_stride, wsets, film_gstride, preshift_gstride, x0_lo, x1_lo);
   if (act_dtype == B200_BF16)
-    return gn_apply<__nv_bfloat16>(x0, C0, x1, C1, N, HW, groups, eps, nullptr, cs0, cs1, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream, preshift, preshift_stride, wsets, film_gstride, preshift_gstride);
+    return gn_apply<__nv_bfloat16>(x0, C0, x1, C1, N, HW, groups, eps, nullptr, cs0, cs1, gamma, beta, film, film_stride, silu, out, (cudaStream_t)stream, preshift, preshift_stride, wsets, film_gstride, preshift_gstride, x0_lo, x1_lo);
   B200_CHECK(false, "groupnorm: bad act_dtype");
 }
 
 extern "C" int b200_add4_scale_stats(const void *a, const void *b, const void *c, const void *d, float scale, void *dst,
-                                     int N, int HW, int C, double *sums, int act_dtype, void *stream) {
+                                     int N, int HW, int C, double *sums, const void *a_lo, const void *b_lo,
+                                     const void *c_lo, const void *d_lo, void *dst_lo, int act_dtype, void *stream) {
   using namespace b200;
   B200_CHECK(a && dst && sums && N > 0 && HW > 0 && C > 0 && C % 8 == 0 && C <= 8 * kNormThreads,
              "add4_scale_stats: bad arguments");
   dim3 grid;
   int ppb;
   stats_grid(N, HW, C >> 3, &grid, &ppb);
+  if (!b) b_lo = nullptr;
+  if (!c) c_lo = nullptr;
+  if (!d) d_lo = nullptr;
+  if (a_lo || b_lo || c_lo || d_lo || dst_lo) {
+    if (act_dtype == B200_F16)
+      add4_stats_lo_kernel<__half><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(
+          (const __half *)a, (const __half *)b, (const __half *)c, (const __half *)d, scale, (__half *)dst, C, HW, ppb, sums,
+          (const __half *)a_lo, (const __half *)b_lo, (const __half *)c_lo, (const __half *)d_lo, (__half *)dst_lo);
+    else if (act_dtype == B200_BF16)
+      add4_stats_lo_kernel<__nv_bfloat16><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(
+          (const __nv_bfloat16 *)a, (const __nv_bfloat16 *)b, (const __nv_bfloat16 *)c, (const __nv_bfloat16 *)d, scale,
+          (__nv_bfloat16 *)dst, C, HW, ppb, sums, (const __nv_bfloat16 *)a_lo, (const __nv_bfloat16 *)b_lo,
+          (const __nv_bfloat16 *)c_lo, (const __nv_bfloat16 *)d_lo, (__nv_bfloat16 *)dst_lo);
+    else
+      B200_CHECK(false, "add4_scale_stats: bad act_dtype");
+    B200_LAUNCH_CHECK();
+    return 0;
+  }
   if (act_dtype == B200_F16)
     add4_stats_kernel<__half><<<grid, kNormThreads, 0, (cudaStream_t)stream>>>(
         (const __half *)a, (const __half *)b, (const __half *)c, (const __half *)d, scale, (__half *)dst, C, HW, ppb, sums);

@@ -153,7 +153,8 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
            out: Optional[Tensor] = None, stats: Optional[Tensor] = None, head_channels: int = 0,
            out_hw: Optional[Tuple[int, int]] = None, out_f32: bool = False, rowscale: Optional[Tensor] = None,
            act: int = 0, wsets: int = 1, rowbias_gstride: int = 0, force_ksplit: int = 0,
-           out_sub: Optional[Tuple[int, int, int, int]] = None) -> Tensor:
+           out_sub: Optional[Tuple[int, int, int, int]] = None, out_lo=None,
+           residual_lo: Optional[Tensor] = None):
     """tcgen05 implicit-GEMM conv over up to 3 K-segments (see b200_conv2d_igemm).
 
     ``wsets`` > 1: grouped along N — the batch is ``wsets`` equal groups of images, group g convolves with its own weight
@@ -162,7 +163,11 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
 
     ``out_sub`` = (sy, sx, oy, ox): the result is one parity class of a [N, Hout*sy, Wout*sx, Cout] tensor ``out`` (required),
     stored at (h*sy + oy, w*sx + ox) — the sub-pixel form of Upsample -> conv3x3; a segment's ``pad`` may then be a
-    (pad_top, pad_left) pair (2x2 kernels)."""
+    (pad_top, pad_left) pair (2x2 kernels).
+
+    ``out_lo``: True (allocate) or a pre-allocated tensor of ``out``'s shape / dtype — the LOW plane of the result
+    (b200_conv_desc.out_lo: ``out + out_lo`` carries the fp32 value); the call then returns ``(out, out_lo)``.
+    ``residual_lo``: low plane of ``residual``."""
     src0, w0, _, k0, p0 = segs[0]
     if isinstance(p0, tuple):
         p0 = p0[0]
@@ -230,6 +235,20 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
     if residual is not None and (head_channels or out_f32 or residual.shape != out.shape or residual.dtype != out.dtype):
         raise L.B200Error("conv2d: residual shape/dtype mismatch")
     d.residual = _p(residual)
+    if residual_lo is not None and (residual is None or residual_lo.shape != residual.shape
+                                    or residual_lo.dtype != residual.dtype):
+        raise L.B200Error("conv2d: residual_lo must match residual")
+    d.residual_lo = _p(residual_lo)
+    if out_lo is not None and out_lo is not False:
+        if head_channels or out_f32:
+            raise L.B200Error("conv2d: out_lo needs a 16-bit NHWC output")
+        if out_lo is True:
+            out_lo = torch.empty_like(out)
+        elif out_lo.shape != out.shape or out_lo.dtype != out.dtype:
+            raise L.B200Error("conv2d: out_lo shape/dtype mismatch")
+        d.out_lo = _p(out_lo)
+    else:
+        out_lo = None
     d.res_scale = res_scale
     d.out = None if (head_channels or out_f32) else _p(out)
     if stats is not None and (stats.dtype != torch.float64 or stats.numel() != n * cout * 2):
@@ -238,6 +257,10 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
     d.act_dtype = act_code(src0.dtype)
     d.range_events = range_counter(src0.device).data_ptr() if src0.dtype == torch.float16 and _range_check else None
     ks = L.lib().b200_conv_ksplit(C.byref(d))
+    if ks > 1 and (out_lo is not None or residual_lo is not None):
+        # split-K layers (small maps) finish in a separate kernel that has no low planes: they are best-effort extra
+        # precision, so the result simply keeps 16 bits there
+        d.out_lo, d.residual_lo, out_lo, residual_lo = None, None, None, None
     if ks > 1:          # small maps run split-K: fp32 partial planes in a per-stream scratch buffer (never shared by
         need = ks * out.numel() * 4          # two launches that may overlap)
         ws = _workspace(src0.device, need)
@@ -247,12 +270,15 @@ def conv2d(segs: Sequence[Seg], stride: int = 1, bias: Optional[Tensor] = None,
     kk = sum(sg[0].shape[3] * (9 if (out_sub is not None and sg[3] == 2) else sg[3] * sg[3]) for sg in segs)
     flops = 2.0 * n * hout * wout * cout * kk
     nbytes = 2.0 * (sum(sg[0].numel() for sg in segs) + out.numel() + cout * kk
-                    + (residual.numel() if residual is not None else 0))
+                    + (residual.numel() if residual is not None else 0)
+                    + (out_lo.numel() if out_lo is not None else 0)
+                    + (residual_lo.numel() if residual_lo is not None else 0))
     _timed("conv_igemm", flops, nbytes,
            lambda: L.check(L.lib().b200_conv2d_igemm(C.byref(d), _stream()), "conv2d_igemm"),
            None if _timer is None else
-           f"{n}x{hout}x{wout} s{stride} " + "+".join(f"k{sg[3]}c{sg[0].shape[3]}" for sg in segs) + f" ->{cout}")
-    return out
+           f"{n}x{hout}x{wout} s{stride} " + "+".join(f"k{sg[3]}c{sg[0].shape[3]}" for sg in segs) + f" ->{cout}"
+           + (" +lo" if out_lo is not None else "") + (" +rlo" if residual_lo is not None else ""))
+    return out if out_lo is None else (out, out_lo)
 
 
 _workspaces = {}
@@ -308,15 +334,17 @@ def _workspace(device, nbytes: int) -> Tensor:
 
 
 def conv3x3_in(x_nchw: Tensor, w_oihw: Tensor, bias: Optional[Tensor], dtype=torch.float16,
-               stats: Optional[Tensor] = None) -> Tensor:
+               stats: Optional[Tensor] = None, want_lo: bool = False):
+    """``want_lo``: also write the LOW plane of the output (see conv2d) and return ``(out, out_lo)``."""
     _dev(x_nchw)
     n, ci, h, w = x_nchw.shape
     co = w_oihw.shape[0]
     out = torch.empty((n, h, w, co), device=x_nchw.device, dtype=dtype)
-    _timed("conv3x3_in", 2.0 * n * h * w * co * ci * 9, 4.0 * x_nchw.numel() + 2.0 * out.numel(),
+    lo = torch.empty_like(out) if want_lo else None
+    _timed("conv3x3_in", 2.0 * n * h * w * co * ci * 9, 4.0 * x_nchw.numel() + 2.0 * out.numel() * (2 if want_lo else 1),
            lambda: L.check(L.lib().b200_conv3x3_in(_p(_f32(x_nchw)), _p(_f32(w_oihw)), _p(_f32(bias)), _p(out), n, ci,
-                                                   h, w, co, _p(stats), act_code(dtype), _stream()), "conv3x3_in"))
-    return out
+                                                   h, w, co, _p(stats), _p(lo), act_code(dtype), _stream()), "conv3x3_in"))
+    return (out, lo) if want_lo else out
 
 
 def conv3x3_out(x: Tensor, w_oihw: Tensor, bias: Optional[Tensor]) -> Tensor:
@@ -394,7 +422,7 @@ def group_norm(x0: Tensor, gamma: Tensor, beta: Tensor, x1: Optional[Tensor] = N
                eps: float = 1e-5, silu: bool = True, film: Optional[Tensor] = None,
                stats: Optional[Tensor] = None, cs0: Optional[Tensor] = None, cs1: Optional[Tensor] = None,
                preshift: Optional[Tensor] = None, wsets: int = 1, film_gstride: int = 0,
-               preshift_gstride: int = 0) -> Tensor:
+               preshift_gstride: int = 0, x0_lo: Optional[Tensor] = None, x1_lo: Optional[Tensor] = None) -> Tensor:
     """GroupNorm(+FiLM)(+SiLU) of the channel concatenation [x0 | x1]; NHWC in, NHWC out.
 
     With ``cs0`` (and ``cs1`` when ``x1`` is given) — the producers' per-channel sums — this is ONE read + ONE write
@@ -418,13 +446,19 @@ def group_norm(x0: Tensor, gamma: Tensor, beta: Tensor, x1: Optional[Tensor] = N
             raise L.B200Error("group_norm: preshift must be fp32 [N or 1, C0] and needs the producer's channel sums")
         ps_p = preshift.data_ptr()
         ps_s = preshift.stride(0) if preshift.shape[0] == npg and npg > 1 else 0
+    for lo_t, src_t in ((x0_lo, x0), (x1_lo, x1)):
+        if lo_t is not None and (src_t is None or lo_t.shape != src_t.shape or lo_t.dtype != src_t.dtype):
+            raise L.B200Error("group_norm: a low plane must match its source")
+    if (x0_lo is not None or x1_lo is not None) and not (cs0 is not None and (x1 is None or cs1 is not None)):
+        raise L.B200Error("group_norm: low planes need the producers' channel sums (single-pass form)")
     if cs0 is not None and (x1 is None or cs1 is not None):
-        _timed("groupnorm_silu", 0.0, 2.0 * 2.0 * out.numel(),
-               detail=f"{n}x{hw} c{c0}+{c1}", launch=
+        lo_elems = (x0_lo.numel() if x0_lo is not None else 0) + (x1_lo.numel() if x1_lo is not None else 0)
+        _timed("groupnorm_silu", 0.0, 2.0 * (2.0 * out.numel() + lo_elems),
+               detail=f"{n}x{hw} c{c0}+{c1}" + (" +lo" if lo_elems else ""), launch=
                lambda: L.check(lib.b200_groupnorm_apply_cs(_p(x0), c0, _p(cs0), _p(x1), c1, _p(cs1), n, hw, groups, eps,
                                                            _p(_f32(gamma)), _p(_f32(beta)), film_p, film_s, int(silu),
                                                            _p(out), ps_p, ps_s, wsets, film_gstride, preshift_gstride,
-                                                           code, _stream()), "groupnorm_apply_cs"))
+                                                           _p(x0_lo), _p(x1_lo), code, _stream()), "groupnorm_apply_cs"))
         return out
     if stats is None:
         stats = torch.zeros((n, groups, 2), device=x0.device, dtype=torch.float64)
@@ -651,17 +685,26 @@ def add4_scale(a: Tensor, b: Optional[Tensor] = None, c: Optional[Tensor] = None
 
 
 def add4_scale_stats(a: Tensor, b: Optional[Tensor], c: Optional[Tensor], d: Optional[Tensor], scale: float,
-                     stats: Tensor) -> Tensor:
-    """scale * (a + b + c + d) over NHWC tensors, accumulating the result's per-(image, channel) sums into ``stats``."""
+                     stats: Tensor, los: Sequence[Optional[Tensor]] = (), want_lo: bool = False):
+    """scale * (a + b + c + d) over NHWC tensors, accumulating the result's per-(image, channel) sums into ``stats``.
+    ``los``: low planes of (a, b, c, d) (None where a source has none), added in; ``want_lo``: also write the low plane of
+    the result and return ``(out, out_lo)``."""
     _dev(a)
     n, ch = a.shape[0], a.shape[-1]
     hw = a.numel() // (n * ch)
     out = torch.empty_like(a)
     nin = 1 + (b is not None) + (c is not None) + (d is not None)
-    _timed("add4_scale", 0.0, 2.0 * a.numel() * (nin + 1),
+    los = list(los) + [None] * (4 - len(los))
+    for lo_t in los:
+        if lo_t is not None and (lo_t.shape != a.shape or lo_t.dtype != a.dtype):
+            raise L.B200Error("add4_scale_stats: a low plane must match its source")
+    out_lo = torch.empty_like(a) if want_lo else None
+    planes = nin + 1 + sum(t is not None for t in los) + (1 if want_lo else 0)
+    _timed("add4_scale", 0.0, 2.0 * a.numel() * planes,
            lambda: L.check(L.lib().b200_add4_scale_stats(_p(a), _p(b), _p(c), _p(d), scale, _p(out), n, hw, ch, _p(stats),
+                                                         _p(los[0]), _p(los[1]), _p(los[2]), _p(los[3]), _p(out_lo),
                                                          act_code(a.dtype), _stream()), "add4_scale_stats"))
-    return out
+    return (out, out_lo) if want_lo else out
 
 
 def se_attention(x: Tensor, w1: Tensor, w2: Tensor, out: Optional[Tensor] = None) -> Tensor:

@@ -161,22 +161,60 @@ def _f(p: Tensor) -> Tensor:
 
 class Act:
     """An NHWC activation travelling through the engine together with its per-(image, channel) statistics
-    (``cs``: fp64 [N, C, 2], filled by the producing kernel's epilogue, or computed on first use)."""
-    __slots__ = ("t", "cs")
+    (``cs``: fp64 [N, C, 2], filled by the producing kernel's epilogue, or computed on first use) and, for the tensors a
+    ``LoPolicy`` selects, its LOW plane ``lo`` (same shape / type): ``t + lo`` is the fp32 value the producer computed,
+    ``t`` alone its 16-bit rounding.  Tensor-core operand reads (TMA) use ``t``; GroupNorm / residual / skip-mean readers
+    add ``lo``."""
+    __slots__ = ("t", "cs", "lo")
 
-    def __init__(self, t: Tensor, cs: Optional[Tensor] = None):
-        self.t, self.cs = t, cs
+    def __init__(self, t: Tensor, cs: Optional[Tensor] = None, lo: Optional[Tensor] = None):
+        self.t, self.cs, self.lo = t, cs, lo
+
+
+class LoPolicy:
+    """Which stored activations keep a low plane (hi + lo = fp32), i.e. more than the 16 bits the engine stores by default.
+
+    The reference keeps every activation in fp32 and only rounds tensor-core OPERANDS (TF32).  This engine additionally
+    rounds every STORED activation to 16 bits; on DS-Diff (four encoders + decoder at 256x256) that second rounding is
+    what lifts the per-step deviation from the 10-bit-operand floor to 1.33 x the reference's own TF32 deviation
+    (tools/store_sim.py).  ``kinds`` names the producers whose outputs keep both planes on maps of at
+    least ``min_pixels`` pixels: ``in`` (first convolution), ``enc_rb`` / ``dec_rb`` (ResBlock outputs of the input /
+    output blocks), ``enc_conv1`` / ``dec_conv1`` (conv1 + timestep term), ``mean`` (DS-Diff skip mean), ``up``
+    (Upsample convolution)."""
+    __slots__ = ("min_pixels", "kinds")
+
+    def __init__(self, kinds, min_pixels: int = 256 * 256):
+        self.kinds, self.min_pixels = frozenset(kinds), int(min_pixels)
+
+    @staticmethod
+    def parse(spec: Optional[str], default: Optional["LoPolicy"] = None) -> Optional["LoPolicy"]:
+        """``B200DIFF_LO_PLANES``: ``0`` / ``none`` = off, ``kind,kind,...[@min_pixels]``; unset = ``default``."""
+        if spec is None or spec == "":
+            return default
+        if spec.lower() in ("0", "none", "off"):
+            return None
+        kinds, _, px = spec.partition("@")
+        return LoPolicy([k.strip() for k in kinds.split(",") if k.strip()], int(px) if px else 256 * 256)
 
 
 class Ctx:
-    """Per-forward engine state: packed weights, the batched timestep projections, the statistics arena."""
-    __slots__ = ("pw", "emb_all", "arena", "context")
+    """Per-forward engine state: packed weights, the batched timestep projections, the statistics arena, the low-plane
+    policy and which part of the network is running (``where``: "enc" / "mid" / "dec")."""
+    __slots__ = ("pw", "emb_all", "arena", "context", "lo", "where")
 
-    def __init__(self, pw: PackedWeights, emb_all: Tensor, arena: "ops.StatsArena", context: Optional[Tensor] = None):
+    def __init__(self, pw: PackedWeights, emb_all: Tensor, arena: "ops.StatsArena", context: Optional[Tensor] = None,
+                 lo: Optional[LoPolicy] = None):
         self.pw, self.emb_all, self.arena, self.context = pw, emb_all, arena, context
+        self.lo, self.where = lo, "enc"
 
     def stats_for(self, n: int, c: int) -> Tensor:
         return self.arena.take(n, c)
+
+    def want_lo(self, kind: str, h: int, w: int) -> bool:
+        pol = self.lo
+        if pol is None or h * w < pol.min_pixels:
+            return False
+        return kind in pol.kinds or f"{self.where}_{kind}" in pol.kinds
 
 
 def _cs(cx: Ctx, a: Act) -> Tensor:
@@ -189,18 +227,27 @@ def run_gn(cx: Ctx, gn: nn.GroupNorm, x0: Act, x1: Optional[Act] = None, silu: b
            film: Optional[Tensor] = None) -> Tensor:
     """GroupNorm32 (+SiLU / FiLM) of cat([x0, x1], C) in one read + one write pass."""
     return ops.group_norm(x0.t, _f(gn.weight), _f(gn.bias), None if x1 is None else x1.t, groups=gn.num_groups,
-                          eps=gn.eps, silu=silu, film=film, cs0=_cs(cx, x0), cs1=None if x1 is None else _cs(cx, x1))
+                          eps=gn.eps, silu=silu, film=film, cs0=_cs(cx, x0), cs1=None if x1 is None else _cs(cx, x1),
+                          x0_lo=x0.lo, x1_lo=None if x1 is None else x1.lo)
 
 
-def run_conv(cx: Ctx, segs, want_stats: bool = True, dst: Optional[Act] = None, **kw) -> Act:
+def run_conv(cx: Ctx, segs, want_stats: bool = True, dst: Optional[Act] = None, lo: bool = False, **kw) -> Act:
     """``dst``: write the result (and its statistics) into this pre-allocated activation — a slice of a buffer that
-    stacks several producers along N for a later grouped launch."""
+    stacks several producers along N for a later grouped launch.  ``lo``: keep the result's low plane (Act.lo)."""
     src0, w0 = segs[0][0], segs[0][1]
     if dst is not None:
         ops.conv2d(segs, stats=dst.cs, out=dst.t, **kw)
         return dst
     st = cx.stats_for(src0.shape[0], w0.shape[1]) if want_stats else None
-    return Act(ops.conv2d(segs, stats=st, **kw), st)
+    r = ops.conv2d(segs, stats=st, out_lo=True if lo else None, **kw)
+    return Act(r[0], st, r[1]) if isinstance(r, tuple) else Act(r, st)
+
+
+def _cat_lo(x0: Act, x1: Act) -> Optional[Tensor]:
+    """Low plane of cat([x0, x1], C) (None when neither source has one)."""
+    if x0.lo is None and x1.lo is None:
+        return None
+    return torch.cat([a.lo if a.lo is not None else torch.zeros_like(a.t) for a in (x0, x1)], dim=-1)
 
 
 def run_resblock_conv1_raw(cx: Ctx, m: ResBlock, x0: Act) -> Act:
@@ -248,24 +295,28 @@ def run_resblock(cx: Ctx, m: ResBlock, x0: Act, x1: Optional[Act], conv1_raw: Op
                                 cs0=conv1_raw.cs, preshift=emb_out)
     elif m.use_scale_shift_norm:
         a = run_gn(cx, gin, x0, x1)
-        h = run_conv(cx, [(a, pw.conv[id(conv1)], 0, 3, 1)], bias=_f(conv1.bias))
+        h = run_conv(cx, [(a, pw.conv[id(conv1)], 0, 3, 1)], bias=_f(conv1.bias), lo=cx.want_lo("conv1", *a.shape[1:3]))
         a2 = run_gn(cx, gout, h, film=emb_out)
     else:
         a = run_gn(cx, gin, x0, x1)
-        h = run_conv(cx, [(a, pw.conv[id(conv1)], 0, 3, 1)], rowbias=emb_out)      # b1 is folded into emb_out
+        h = run_conv(cx, [(a, pw.conv[id(conv1)], 0, 3, 1)], rowbias=emb_out,      # b1 is folded into emb_out
+                     lo=cx.want_lo("conv1", *a.shape[1:3]))
         a2 = run_gn(cx, gout, h)
     segs = [(a2, pw.conv[id(conv2)], 0, 3, 1)]
-    residual = None
+    residual = residual_lo = None
     sk = m.skip_connection
-    if isinstance(sk, nn.Conv2d):
+    if isinstance(sk, nn.Conv2d):       # operand reads: the 16-bit plane alone is the operand rounding
         ks = sk.kernel_size[0]
         wsk = pw.conv[id(sk)]
         segs.append((x0.t, wsk, 0, ks, ks // 2))
         if x1 is not None:
             segs.append((x1.t, wsk, x0.t.shape[-1], ks, ks // 2))
+    elif x1 is None:
+        residual, residual_lo = x0.t, x0.lo
     else:
-        residual = x0.t if x1 is None else torch.cat([x0.t, x1.t], dim=-1)
-    return run_conv(cx, segs, bias=pw.bias2[id(m)], residual=residual, dst=dst)
+        residual, residual_lo = torch.cat([x0.t, x1.t], dim=-1), _cat_lo(x0, x1)
+    return run_conv(cx, segs, bias=pw.bias2[id(m)], residual=residual, residual_lo=residual_lo, dst=dst,
+                    lo=dst is None and cx.want_lo("rb", *a2.shape[1:3]))
 
 
 def run_attention(cx: Ctx, m: AttentionBlock, x: Act) -> Act:
@@ -276,7 +327,7 @@ def run_attention(cx: Ctx, m: AttentionBlock, x: Act) -> Act:
     qkv = ops.conv2d([(a, pw.conv[id(m.qkv)], 0, 1, 0)], bias=_f(m.qkv.bias))
     att = ops.attention_qkv(qkv.view(n, h * w, 3 * c), m.num_heads, m.use_new_attention_order)
     return run_conv(cx, [(att.view(n, h, w, c), pw.conv[id(m.proj_out)], 0, 1, 0)], bias=_f(m.proj_out.bias),
-                    residual=x.t)
+                    residual=x.t, residual_lo=x.lo)
 
 
 def run_spatial_transformer(cx: Ctx, m: "tfm.SpatialTransformer", x: Act) -> Act:
@@ -294,7 +345,8 @@ def run_spatial_transformer(cx: Ctx, m: "tfm.SpatialTransformer", x: Act) -> Act
     t = ops.conv2d([(a, win, 0, 1, 0)], bias=_f(m.proj_in.bias)).view(n, h * w, -1)
     for blk in m.transformer_blocks:
         t = tfm.run_basic_block(pw, blk, t, cx.context)
-    return run_conv(cx, [(t.view(n, h, w, -1), wout, 0, 1, 0)], bias=_f(m.proj_out.bias), residual=x.t)
+    return run_conv(cx, [(t.view(n, h, w, -1), wout, 0, 1, 0)], bias=_f(m.proj_out.bias), residual=x.t,
+                    residual_lo=x.lo)
 
 
 def run_sequential(cx: Ctx, seq: nn.Sequential, x0: Act, x1: Optional[Act], conv1_raw: Optional[Act] = None,
@@ -309,7 +361,7 @@ def run_sequential(cx: Ctx, seq: nn.Sequential, x0: Act, x1: Optional[Act], conv
             x0, x1 = run_resblock(cx, layer, x0, x1, conv1_raw if li == 0 else None, dst if li == last else None), None
             continue
         if x1 is not None:
-            x0, x1 = Act(torch.cat([x0.t, x1.t], dim=-1)), None
+            x0, x1 = Act(torch.cat([x0.t, x1.t], dim=-1), None, _cat_lo(x0, x1)), None
         if isinstance(layer, AttentionBlock):
             x0 = run_attention(cx, layer, x0)
         elif isinstance(layer, tfm.SpatialTransformer):
@@ -361,15 +413,16 @@ def run_upsample_conv(cx: Ctx, conv: nn.Conv2d, x: Act) -> Act:
     n, h, w_, _ = x.t.shape
     cout = conv.out_channels
     out = torch.empty((n, 2 * h, 2 * w_, cout), device=x.t.device, dtype=x.t.dtype)
+    out_lo = torch.empty_like(out) if cx.want_lo("up", 2 * h, 2 * w_) else None
     st = cx.stats_for(n, cout)
     bias = _f(conv.bias)
     i = 0
     for a in (0, 1):
         for b in (0, 1):
             ops.conv2d([(x.t, packs[i], 0, 2, (1 - a, 1 - b))], bias=bias, out=out, stats=st, out_hw=(h, w_),
-                       out_sub=(2, 2, a, b))
+                       out_sub=(2, 2, a, b), out_lo=out_lo)
             i += 1
-    return Act(out, st)
+    return Act(out, st, out_lo)
 
 
 def run_in_conv(cx: Ctx, conv: nn.Conv2d, x: Tensor, dtype: torch.dtype) -> Act:
@@ -381,12 +434,16 @@ def run_in_conv(cx: Ctx, conv: nn.Conv2d, x: Tensor, dtype: torch.dtype) -> Act:
     simt = os.environ.get("B200DIFF_SIMT_IN_CONV")
     if conv.in_channels == 1 and simt != "0" or conv.in_channels <= 8 and simt == "1":
         st = cx.stats_for(x.shape[0], conv.out_channels)
+        if cx.want_lo("in", x.shape[2], x.shape[3]):
+            t, tl = ops.conv3x3_in(x.contiguous(), _f(conv.weight), _f(conv.bias), dtype, stats=st, want_lo=True)
+            return Act(t, st, tl)
         return Act(ops.conv3x3_in(x.contiguous(), _f(conv.weight), _f(conv.bias), dtype, stats=st), st)
     cpad = (conv.in_channels + 7) // 8 * 8
     key = ("in", id(conv))
     if key not in pw.conv:
         pw.conv[key] = ops.pack_conv_weight(_f(conv.weight), dtype, cpad)
-    return run_conv(cx, [(ops.nchw_to_nhwc(x, cpad, dtype), pw.conv[key], 0, 3, 1)], bias=_f(conv.bias))
+    return run_conv(cx, [(ops.nchw_to_nhwc(x, cpad, dtype), pw.conv[key], 0, 3, 1)], bias=_f(conv.bias),
+                    lo=cx.want_lo("in", x.shape[2], x.shape[3]))
 
 
 def run_out_head(cx: Ctx, out: nn.Sequential, h: Act) -> Tensor:
@@ -458,7 +515,19 @@ class _EngineModule(nn.Module):
         self._pw_fp: Optional[int] = None
         self._temb: Optional[TimeEmbedding] = None
         self._arena = ops.StatsArena()
+        # which stored activations keep a low plane (LoPolicy); off unless B200DIFF_LO_PLANES says otherwise —
+        # DSUnetModel sets its own default
+        self.lo_policy = LoPolicy.parse(os.environ.get("B200DIFF_LO_PLANES"), None)
         self.register_load_state_dict_post_hook(lambda mod, keys: mod.invalidate())
+
+    @property
+    def lo_policy(self) -> Optional[LoPolicy]:
+        return self._lo_policy
+
+    @lo_policy.setter
+    def lo_policy(self, pol: Optional[LoPolicy]) -> None:
+        self._lo_policy = pol
+        self.invalidate()       # captured step graphs are keyed on the packed weights: re-pack, re-capture
 
     def invalidate(self):
         self._pw = None
@@ -656,14 +725,16 @@ class UNetModel(_EngineModule):
         n = x.shape[0]
         emb_all = self._emb_all(pw, timesteps, n, step_ptr, y)
         self._arena.begin(x.device)
-        cx = Ctx(pw, emb_all, self._arena, tfm.context_tokens(context, self.act_dtype))
+        cx = Ctx(pw, emb_all, self._arena, tfm.context_tokens(context, self.act_dtype), lo=self.lo_policy)
         hs = []
         h = run_in_conv(cx, self.input_blocks[0][0], x.float(), self.act_dtype)
         hs.append(h)
         for blk in list(self.input_blocks)[1:]:
             h = run_sequential(cx, blk, h, None)
             hs.append(h)
+        cx.where = "mid"
         h = run_sequential(cx, self.middle_block, h, None)
+        cx.where = "dec"
         for blk in self.output_blocks:
             h = run_sequential(cx, blk, h, hs.pop())
         out = run_out_head(cx, self.id_predictor if self.predict_codebook_ids else self.out, h)   # openaimodel.py:955-958

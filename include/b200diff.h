@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 14
+#define B200_ABI_VERSION 15
 #define B200_F16 0
 #define B200_BF16 1
 
@@ -130,6 +130,13 @@ typedef struct {
                               out_nhwc_f32 set the S fp32 partial planes (workspace) are summed in fixed order into out_nhwc_f32
                               with no epilogue terms (bias / residual must be NULL) — the weight-gradient GEMM of the training
                               step, dW[Cout, Cin] = dY^T X with K = all tokens of the batch (trainers' loss.backward()).        */
+  void *out_lo;             /* optional second 16-bit NHWC plane of `out`'s shape: receives result - (stored 16-bit result), so
+                              that out + out_lo carries the fp32 value the reference keeps in its fp32 activation tensors
+                              (ResBlock / first-conv outputs of the 256x256 level of DSUnetModel, whose 16-bit rounding is what
+                              DESIGN.md section 4 measures).  Operand consumers (TMA) read `out` alone — it is exactly the 16-bit
+                              rounding they would apply anyway; GroupNorm / residual consumers read both planes.  Needs a 16-bit
+                              NHWC `out` and a launch without split-K (b200_conv_ksplit == 1).                              */
+  const void *residual_lo;  /* optional low plane of `residual` (same shape / type): the epilogue adds residual + residual_lo */
 } b200_conv_desc;
 int b200_conv2d_igemm(const b200_conv_desc *d, void *stream);
 /* split-K factor b200_conv2d_igemm will use for this descriptor (1 = none).  It depends on the layer geometry only
@@ -142,7 +149,8 @@ int b200_conv_ksplit(const b200_conv_desc *d);
  * (ldm/models/diffusion/ddpm.py:1331-1333).  w is OIHW fp32.  sums (may be NULL): zeroed fp64 [N, Cout, 2], receives
  * the per-(image, channel) sum / sum of squares of the stored output for the following GroupNorm.     */
 int b200_conv3x3_in(const float *x_nchw, const float *w_oihw, const float *bias, void *out_nhwc,
-                    int N, int Cin, int H, int W, int Cout, double *sums, int act_dtype, void *stream);
+                    int N, int Cin, int H, int W, int Cout, double *sums, void *out_lo, int act_dtype, void *stream);
+/* out_lo (may be NULL): low plane of the output, see b200_conv_desc.out_lo.                            */
 /* last conv: Cout <= 4, NHWC act -> NCHW fp32.  replaces self.out[2] (openaimodel.py:898-902). */
 int b200_conv3x3_out(const void *x_nhwc, const float *w_oihw, const float *bias, float *out_nchw,
                      int N, int Cin, int H, int W, int Cout, int act_dtype, void *stream);
@@ -172,7 +180,8 @@ int b200_groupnorm_apply_cs(const void *x0, int C0, const double *cs0, const voi
                             const double *cs1, int N, int HW, int groups, float eps, const float *gamma,
                             const float *beta, const float *film, int film_stride, int silu, void *out,
                             const float *preshift, int preshift_stride, int wsets, int film_gstride,
-                            int preshift_gstride, int act_dtype, void *stream);
+                            int preshift_gstride, const void *x0_lo, const void *x1_lo, int act_dtype, void *stream);
+/* x0_lo / x1_lo (may be NULL): low planes of the sources (b200_conv_desc.out_lo): the value normalised is x + x_lo.   */
 int b200_channel_stats(const void *x, int N, int HW, int C, double *sums, int act_dtype, void *stream);
 
 /* ---- attention -------------------------------------------------------------------------------
@@ -268,7 +277,9 @@ int b200_add4_scale(const void *a, const void *b, const void *c, const void *d, 
 /* same, for NHWC [N,HW,C] tensors, also ACCUMULATING the per-(image, channel) statistics of dst (sums[N][C][2] fp64,
  * zero first) for the GroupNorm that consumes the DS-Diff skip mean.                                             */
 int b200_add4_scale_stats(const void *a, const void *b, const void *c, const void *d, float scale, void *dst,
-                          int N, int HW, int C, double *sums, int act_dtype, void *stream);
+                          int N, int HW, int C, double *sums, const void *a_lo, const void *b_lo, const void *c_lo,
+                          const void *d_lo, void *dst_lo, int act_dtype, void *stream);
+/* a_lo .. d_lo (each may be NULL): low planes of the sources, added in; dst_lo (may be NULL): low plane of the result. */
 /* SE_Attention (Disc_diff/guided_diffusion/unet.py:105-109): x * sigmoid(W2 relu(W1 avgpool(x))). */
 int b200_se_attention(const void *x, const float *w1, const float *w2, void *out, float *scratch,
                       int N, int HW, int C, int Cr, int act_dtype, void *stream);

@@ -178,48 +178,58 @@ def _cfg2_reference_deviation(r):
     return devs, pin
 
 
-# measured on B200 (profiles/r2_parity_cfg2.md): the reference's own TF32 path deviates 1.05e-3 .. 1.10e-3 from its fp32
-# output per step — north_star's 1e-3 is below what the reference's shipped GPU arithmetic achieves against itself
-REF_TF32_DEVIATION_MEASURED = 1.05e-3
+# measured on B200 (profiles/r2_parity_cfg2.json): the reference's own TF32 path deviates 1.0e-3 .. 1.25e-3 from its fp32
+# output per step — north_star's 1e-3 is below what the reference's shipped GPU arithmetic achieves against itself.
+# Used only when the compiled reference (oracle/_ref) is absent; otherwise the deviation is measured in the test.
+REF_TF32_DEVIATION_MEASURED = {1961: 1.0476e-3, 1561: 0.9973e-3, 961: 1.1191e-3, 361: 1.2390e-3, 1: 1.2472e-3}
 
 
-def test_cfg2_per_step_error_is_bounded_by_the_operand_and_storage_floor(loops):
-    """cfg2 per-step error, asserted at what the arithmetic can deliver: 10-bit-mantissa operands (fp16 here, TF32 in the
-    reference's own GPU path) cost 1.14e-3 on this network and the 16-bit STORAGE of every convolution output (north_star
-    itself specifies 16-bit storage) adds 0.80e-3 in quadrature -> 1.40e-3 at the first step (oracle simulation,
-    profiles/r2_store_attribution_cfg2.json; measured 1.39e-3), growing to 1.65e-3 late in the chain where x_t is nearly
-    noise-free (measured over DDIM-50 in both rounds).  Bound = the measured worst case + 15 %, and <= 1.7 x the reference's
-    own TF32 deviation measured in this test at the same step on this GPU.  The oracle is pinned to the reference's fp32
-    GPU output (2e-5).  Measurements are written to gpurun_out/parity_cfg2.json when that directory exists."""
+def test_cfg2_per_step_gate_1p25x_reference_deviation(loops):
+    """cfg2 per-step gate, stated against the REFERENCE ITSELF as the round-1 review asked: the network output of this path
+    deviates from the fp32 oracle by at most 1.25 x what the reference's own shipped GPU arithmetic (TF32 "high") deviates
+    from its own fp32 output — measured in this test, at the same probe steps, on the same GPU, weights and inputs.
+
+    How it is met (DESIGN.md section 4): 10-bit-mantissa operands (fp16 here, TF32 there) cost 1.08e-3 on this network;
+    storing EVERY activation as 16 bits added 0.8e-3 in quadrature (1.39e-3 = 1.33 x, the round-1 / early round-2 state).
+    DSUnetModel now keeps the first convolutions' outputs and the decoder's conv1 / ResBlock outputs of the 256x256 level as
+    hi + lo plane pairs (unet.LoPolicy, tools/store_sim.py): measured 1.16 .. 1.19 x over the DDIM-50 chain, for 3 % of
+    step time.  The oracle is pinned to the reference's fp32 GPU output at full size (<= 2e-5).  Measurements are written to
+    gpurun_out/parity_cfg2.json when that directory exists."""
     r = loops("cfg2")
-    worst = max(r["per_step"].values())
+    assert r["net"].lo_policy is not None and r["net"].lo_policy.min_pixels == 256 * 256      # the shipped default
     devs, pin = _cfg2_reference_deviation(r)
-    if os.path.isdir(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")):
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
         import json
-        with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_cfg2.json"),
-                  "w") as fh:
+        with open(os.path.join(out_dir, "parity_cfg2.json"), "w") as fh:
             json.dump({"b200_vs_fp32_oracle_rel_l2": {str(k): v for k, v in r["per_step"].items()},
                        "reference_tf32_as_shipped_vs_its_fp32": None if devs is None else {str(k): v for k, v in devs.items()},
-                       "reference_fp32_gpu_vs_cpu_oracle": None if pin is None else {str(k): v for k, v in pin.items()}}, fh,
-                      indent=1)
-    assert worst <= 1.9e-3, r["per_step"]
+                       "reference_fp32_gpu_vs_cpu_oracle": None if pin is None else {str(k): v for k, v in pin.items()},
+                       "lo_policy": sorted(r["net"].lo_policy.kinds)}, fh, indent=1)
     if devs is not None:
         assert max(pin.values()) <= 2e-5                                 # the oracle IS the reference at full size
-        for t in r["per_step"]:
-            assert r["per_step"][t] <= 1.7 * devs[t], (t, r["per_step"][t], devs[t])
-    else:
-        assert worst <= 1.7 * REF_TF32_DEVIATION_MEASURED, r["per_step"]
-
-
-@pytest.mark.xfail(strict=True, reason="KNOWN UNMET GATE: cfg2 per-step error is 1.39e-3 = 1.33 x the reference's own TF32 "
-                   "deviation (1.05e-3), above both north_star's 1e-3 and the 1.25 x reference-deviation gate; closing it "
-                   "needs 32-bit storage of the 256x256 activations (+8 % step time, DESIGN.md section 4)")
-def test_cfg2_per_step_gate_1p25x_reference_deviation(loops):
-    r = loops("cfg2")
-    devs, _ = _cfg2_reference_deviation(r)
     for t in r["per_step"]:
-        d = devs[t] if devs is not None else REF_TF32_DEVIATION_MEASURED
-        assert r["per_step"][t] <= max(1e-3, 1.25 * d), (t, r["per_step"][t], d)
+        d = devs[t] if devs is not None else REF_TF32_DEVIATION_MEASURED[t]
+        assert r["per_step"][t] <= 1.25 * d, (t, r["per_step"][t], d)
+
+
+def test_cfg2_sixteen_bit_storage_everywhere_is_what_the_low_planes_fix(loops):
+    """The same network with ``lo_policy = None`` (every stored activation 16-bit, B200DIFF_LO_PLANES=0): the first probe
+    step sits at 1.39e-3 — the figure the low planes were introduced against — and the default policy must beat it by at
+    least 8 %.  Guards against the planes silently not being used at full size."""
+    r = loops("cfg2")
+    net = r["net"]
+    t, (xc, ref) = max(r["probes"].items())
+    pol = net.lo_policy
+    try:
+        net.lo_policy = None
+        got = net(xc.cuda(), torch.full((1,), t, dtype=torch.long, device="cuda"))[0].cpu()
+    finally:
+        net.lo_policy = pol
+    plain = O.rel_err(got, ref)
+    print(f"\n[cfg2] t={t}: 16-bit storage everywhere {plain:.4e}, default low planes {r['per_step'][t]:.4e}")
+    assert 1.3e-3 <= plain <= 1.5e-3, plain
+    assert r["per_step"][t] <= 0.92 * plain, (r["per_step"][t], plain)
 
 
 # -------------------------------------------------------------------------------------------------

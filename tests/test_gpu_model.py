@@ -445,13 +445,15 @@ def test_full_size_network_forward_vs_oracle(workload):
     rel = O.rel_err(got, ref)
     # cfg1 (BASELINE configs[0]) meets north_star's 1e-3 outright at full size (measured 6.5e-4 .. 6.9e-4 over a whole
     # DDIM-50 run, profiles/r1_full_loop_parity_cfg1.json); the DS-Diff backbones sit at their 10-bit-operand floor (1.2e-3)
-    tol = 1e-3 if workload == "cfg1" else REL_TOL[torch.float16]
+    # cfg2 with its default low planes (unet.LoPolicy): measured 1.23e-3 .. 1.25e-3 at this step (1.39e-3 with 16-bit storage
+    # everywhere); the gate proper — 1.25 x the reference's own TF32 deviation — is tests/test_gpu_full_loop.py
+    tol = {"cfg1": 1e-3, "cfg2": 1.4e-3}.get(workload, REL_TOL[torch.float16])
     assert rel < tol, f"{workload} full-size rel err {rel:.3e}"
     if hasattr(net, "prepare_conditioning"):        # the step as the samplers run it: conditioning prefix hoisted
         assert net.prepare_conditioning([cond.cuda()])
         got_h = net(xc.cuda(), ts.cuda(), cond_cached=True)[0].cpu()
         rel_h = O.rel_err(got_h, ref)
-        assert rel_h < REL_TOL[torch.float16], f"{workload} full-size (hoisted) rel err {rel_h:.3e}"
+        assert rel_h < max(tol, 1.05 * rel), f"{workload} full-size (hoisted) rel err {rel_h:.3e}"
 
 
 def test_sample_volume_batch_split_independent_on_gpu():
