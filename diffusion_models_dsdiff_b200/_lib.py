@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200diff.so")
+# B200DIFF_LIB: another build of the same ABI (kernel A/B timing); default = the in-tree library next to this file
+LIB_PATH = os.environ.get("B200DIFF_LIB") or os.path.join(_HERE, "libb200diff.so")
 
 ABI_VERSION = 15        # must equal B200_ABI_VERSION of the header the library was built from
 F16, BF16 = 0, 1

@@ -103,12 +103,12 @@ colsum16_kernel(const T *__restrict__ x, float *__restrict__ out, int64_t R, int
   if (col < ncol && rl < lanes) {
     const T *base = x + col * 8;
     int64_t r = r_begin + rl;
-    for (; r + 3 * lanes < r_end; r += 4 * lanes) {
-      uint4 u[4];
+    for (; r + 7 * lanes < r_end; r += 8 * lanes) {
+      uint4 u[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = ld_stream(base + (r + (int64_t)k * lanes) * C);
+      for (int k = 0; k < 8; ++k) u[k] = ld_stream(base + (r + (int64_t)k * lanes) * C);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 8; ++k) {
         float f[8];
         unpack8<T>(u[k], f);
 #pragma unroll
@@ -129,8 +129,19 @@ colsum16_kernel(const T *__restrict__ x, float *__restrict__ out, int64_t R, int
     for (int l = 1; l < lanes; ++l)
 #pragma unroll
       for (int i = 0; i < 8; ++i) s[i] += red[(l * cpb + cl) * 8 + i];
+    // two 16-byte vector reductions per thread instead of eight scalar atomics: the same-address traffic at the L2 atomic
+    // units (blocks x 8 per column) was what bounded the narrow (C = 768) launches, not HBM
+    if ((reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + col * 8), "f"(s[0]), "f"(s[1]), "f"(s[2]),
+                   "f"(s[3])
+                   : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + col * 8 + 4), "f"(s[4]), "f"(s[5]), "f"(s[6]),
+                   "f"(s[7])
+                   : "memory");
+    } else {      // a bias-gradient view at an odd offset of the flat gradient arena
 #pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(out + col * 8 + i, s[i]);
+      for (int i = 0; i < 8; ++i) atomicAdd(out + col * 8 + i, s[i]);
+    }
   }
 }
 
@@ -179,25 +190,37 @@ gelu_fwd_kernel(const T *__restrict__ pre, T *__restrict__ out, int64_t nvec) {
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kMaxVec = 6;      // up to 6 * 32 * 8 = 1536 channels (NV = vectors per lane is a template parameter)
 
-template <typename T>
+template <typename T, int NV>
 __global__ void __launch_bounds__(256)
 gated_residual_kernel(const T *__restrict__ h_in, const T *__restrict__ f, const float *__restrict__ gate, int gate_stride,
                       T *__restrict__ h_out, int64_t rows, int L, int C) {
+  // persistent warps, one token row at a time: the 2 * NV 16-byte loads of a row are all in flight before the first use
+  const int lane = threadIdx.x & 31;
   const int nvec = C >> 3;
-  const int64_t total = rows * nvec;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / nvec;
-    const int v = (int)(i - r * nvec);
+  const int64_t stride = (int64_t)gridDim.x * 8;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += stride) {
     const int n = (int)(r / L);
-    float a[8], b[8];
-    unpack8<T>(ld_stream(h_in + r * C + v * 8), a);
-    unpack8<T>(ld_stream(f + r * C + v * 8), b);
-    const float4 g0 = *reinterpret_cast<const float4 *>(gate + (size_t)n * gate_stride + v * 8);
-    const float4 g1 = *reinterpret_cast<const float4 *>(gate + (size_t)n * gate_stride + v * 8 + 4);
-    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    uint4 ua[NV], ub[NV];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = fmaf(g[j], b[j], a[j]);
-    st_stream(h_out + r * C + v * 8, pack8<T>(a));
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nvec) { ua[k] = ld_stream(h_in + r * C + v * 8); ub[k] = ld_stream(f + r * C + v * 8); }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int v = lane + 32 * k;
+      if (v < nvec) {
+        float a[8], b[8];
+        unpack8<T>(ua[k], a);
+        unpack8<T>(ub[k], b);
+        const float4 g0 = __ldg(reinterpret_cast<const float4 *>(gate + (size_t)n * gate_stride + v * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4 *>(gate + (size_t)n * gate_stride + v * 8 + 4));
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = fmaf(g[j], b[j], a[j]);
+        st_stream(h_out + r * C + v * 8, pack8<T>(a));
+      }
+    }
   }
 }
 
@@ -222,20 +245,42 @@ gate_bwd_kernel(const T *__restrict__ dh, const T *__restrict__ f, const float *
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[k][j] = 0.f; g[k][j] = (v < nvec) ? gate[(size_t)n * gate_stride + v * 8 + j] : 0.f; }
   }
+  // the streaming loads / stores are ordered (asm volatile): the NEXT row is loaded before the current one is used and
+  // stored, so a warp always has a row in flight
+  uint4 ud[NV], uf[NV], nd[NV], nf[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int v = lane + 32 * k;
+    ud[k] = make_uint4(0, 0, 0, 0); uf[k] = ud[k]; nd[k] = ud[k]; nf[k] = ud[k];
+    if (v < nvec && t0 < t1) {
+      const size_t row0 = ((size_t)n * L + t0) * C;
+      ud[k] = ld_stream(dh + row0 + v * 8);
+      uf[k] = ld_stream(f + row0 + v * 8);
+    }
+  }
   for (int t = t0; t < t1; ++t) {
     const size_t row = ((size_t)n * L + t) * C;
+    if (t + 1 < t1) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int v = lane + 32 * k;
+        if (v < nvec) { nd[k] = ld_stream(dh + row + C + v * 8); nf[k] = ld_stream(f + row + C + v * 8); }
+      }
+    }
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int v = lane + 32 * k;
       if (v < nvec) {
         float d[8], ff[8];
-        unpack8<T>(ld_stream(dh + row + v * 8), d);
-        unpack8<T>(ld_stream(f + row + v * 8), ff);
+        unpack8<T>(ud[k], d);
+        unpack8<T>(uf[k], ff);
 #pragma unroll
         for (int j = 0; j < 8; ++j) { acc[k][j] = fmaf(d[j], ff[j], acc[k][j]); d[j] *= g[k][j]; }
         st_stream(df + row + v * 8, pack8<T>(d));
       }
     }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) { ud[k] = nd[k]; uf[k] = nf[k]; }
   }
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -260,8 +305,11 @@ gate_bwd_kernel(const T *__restrict__ dh, const T *__restrict__ f, const float *
 //   dx   = rstd * (g - mean_c(g) - nhat * mean_c(g * nhat))  (+ dres: the gradient arriving on the residual branch)
 //   dshift[n, c] += sum_t da ; dscale[n, c] += sum_t da * nhat
 // ------------------------------------------------------------------------------------------------------------------
+#ifndef B200_LN_BWD_MIN_CTAS
+#define B200_LN_BWD_MIN_CTAS ((NV <= 3) ? 2 : 1)
+#endif
 template <typename T, int NV>
-__global__ void __launch_bounds__(256, (NV <= 3) ? 2 : 1)
+__global__ void __launch_bounds__(256, B200_LN_BWD_MIN_CTAS)
 ln_mod_bwd_kernel(const T *__restrict__ x, const T *__restrict__ da, const float *__restrict__ scale, int mod_stride,
                   const T *__restrict__ dres, T *__restrict__ dx, float *__restrict__ dshift, float *__restrict__ dscale,
                   int dmod_stride, int N, int L, int C, float eps, int rows_per_warp) {
@@ -282,23 +330,39 @@ ln_mod_bwd_kernel(const T *__restrict__ x, const T *__restrict__ da, const float
   for (int k = 0; k < NV; ++k)
 #pragma unroll
     for (int j = 0; j < 8; ++j) { a_sh[k][j] = 0.f; a_sc[k][j] = 0.f; }
+  // streaming loads / stores are ordered (asm volatile): row t + 1 is loaded (raw) before row t goes through its three
+  // dependent reductions and its store, so the HBM latency of a row hides behind the arithmetic of the previous one
+  uint4 ux[NV], ug[NV], nx[NV], ng[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int v = lane + 32 * k;
+    ux[k] = make_uint4(0, 0, 0, 0); ug[k] = ux[k]; nx[k] = ux[k]; ng[k] = ux[k];
+    if (v < nvec && t0 < t1) {
+      const size_t row0 = ((size_t)n * L + t0) * C;
+      ux[k] = ld_stream(x + row0 + v * 8);
+      ug[k] = ld_stream(da + row0 + v * 8);
+    }
+  }
   for (int t = t0; t < t1; ++t) {
     const size_t row = ((size_t)n * L + t) * C;
+    if (t + 1 < t1) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int v = lane + 32 * k;
+        if (v < nvec) { nx[k] = ld_stream(x + row + C + v * 8); ng[k] = ld_stream(da + row + C + v * 8); }
+      }
+    }
     float xv[NV][8], gv[NV][8];
     float s = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      const int v = lane + 32 * k;
-      if (v < nvec) {
-        unpack8<T>(ld_stream(x + row + v * 8), xv[k]);
-        unpack8<T>(ld_stream(da + row + v * 8), gv[k]);
+      unpack8<T>(ux[k], xv[k]);      // lanes past the row hold zeros
+      unpack8<T>(ug[k], gv[k]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s += xv[k][j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { xv[k][j] = 0.f; gv[k][j] = 0.f; }
-      }
+      for (int j = 0; j < 8; ++j) s += xv[k][j];
     }
+    if (dres && lane < ((C * (int)sizeof(T) + 127) >> 7))      // this row's residual-branch gradient: pull it into L2 now
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(dres + row) + lane * 128));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s * invC;
@@ -355,6 +419,8 @@ ln_mod_bwd_kernel(const T *__restrict__ x, const T *__restrict__ da, const float
         st_stream(dx + row + v * 8, pack8<T>(o8));
       }
     }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) { ux[k] = nx[k]; ug[k] = ng[k]; }
   }
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
@@ -850,11 +916,20 @@ extern "C" int b200_transpose16(const void *src, void *dst, float *colsum, int64
 extern "C" int b200_colsum16(const void *x, float *out, int64_t R, int C, int act_dtype, void *stream) {
   B200_CHECK(x && out && R > 0 && C > 0 && C % 8 == 0, "colsum16: bad arguments");
   const int ncol = C / 8;
-  int cpb = 64;
-  while (cpb > ncol && cpb > 1) cpb >>= 1;               // power of two <= 64 (a partial last column block is masked)
+  // columns per block: the divisor of ncol in [16, 64] that keeps most of the 256 threads busy (C = 768: 32 columns x 8 row
+  // lanes instead of a full and a half-empty 64-column block); otherwise a power of two with a masked last block
+  int cpb = 0, best = 0;
+  for (int dcol = 64; dcol >= 16; --dcol)
+    if (ncol % dcol == 0 && dcol * (256 / dcol) > best) { best = dcol * (256 / dcol); cpb = dcol; }
+  if (cpb == 0) {
+    cpb = 64;
+    while (cpb > ncol && cpb > 1) cpb >>= 1;
+  }
   const int gx = cdiv(ncol, cpb);
   const int lanes = 256 / cpb;
-  int gy = std::max(1, std::min((int)cdiv64(R, (int64_t)lanes * 8), num_sms() * 4 / gx));
+  // six blocks per SM: measured best of 1 .. 16 on 32768 x {768, 2304, 3072} (tools/row_kernels_one.py); fewer starve the
+  // memory system, more only add same-address reductions
+  int gy = std::max(1, std::min((int)cdiv64(R, (int64_t)lanes * 8), std::max(1, num_sms() * 6 / gx)));
   const int rpb = (int)cdiv64(R, gy);
   gy = (int)cdiv64(R, rpb);
 #define L_(TT, ...) colsum16_kernel<TT><<<dim3(gx, gy), 256, 0, (cudaStream_t)stream>>>((const TT *)x, out, R, C, rpb, cpb)
@@ -884,34 +959,50 @@ extern "C" int b200_gelu_fwd(const void *pre, void *out, int64_t n, int act_dtyp
 
 extern "C" int b200_gated_residual(const void *h_in, const void *f, const float *gate, int gate_stride, void *h_out,
                                    int64_t rows, int L, int C, int act_dtype, void *stream) {
-  B200_CHECK(h_in && f && gate && h_out && rows > 0 && L > 0 && C % 8 == 0, "gated_residual: bad arguments");
-#define L_(TT, ...) gated_residual_kernel<TT><<<ew_blocks(rows * (C / 8)), 256, 0, (cudaStream_t)stream>>>( \
-      (const TT *)h_in, (const TT *)f, gate, gate_stride, (TT *)h_out, rows, L, C)
+  B200_CHECK(h_in && f && gate && h_out && rows > 0 && L > 0 && C % 8 == 0 && C <= kMaxVec * 256,
+             "gated_residual: bad arguments (C <= %d)", kMaxVec * 256);
+  B200_CHECK(gate_stride % 4 == 0 && ((uintptr_t)gate & 15) == 0, "gated_residual: gate rows must be 16-byte aligned");
+  const int nv = cdiv(C / 8, 32);
+  const int blocks = (int)std::min<int64_t>(cdiv64(rows, 8), (int64_t)num_sms() * 8);
+#define L2_(TT, NV)                                                                                      \
+  gated_residual_kernel<TT, NV><<<blocks, 256, 0, (cudaStream_t)stream>>>((const TT *)h_in, (const TT *)f, gate, \
+                                                                          gate_stride, (TT *)h_out, rows, L, C)
+#define L_(TT, ...)                                                                         \
+  switch (nv) {                                                                             \
+    case 1: L2_(TT, 1); break; case 2: L2_(TT, 2); break; case 3: L2_(TT, 3); break;        \
+    case 4: L2_(TT, 4); break; case 5: L2_(TT, 5); break; default: L2_(TT, 6); break;       \
+  }
   B200_ACT_DISPATCH(L_, 0);
 #undef L_
+#undef L2_
   B200_LAUNCH_CHECK();
   return 0;
 }
 
-static int rows_per_warp_for(int N, int L) {
-  // enough warps to fill the GPU, but long enough runs that the per-(sample, channel) atomics stay cheap
-  int rpw = 32;
-  while (rpw > 4 && (int64_t)N * cdiv(L, 8 * rpw) < (int64_t)num_sms() * 3) rpw >>= 1;
-  return rpw;
+static int rows_per_warp_for(int N, int L, int blocks_per_sm) {
+  // ONE resident wave: a block (8 warps) walks rows of one sample, so the grid is N x (blocks per sample) with as many blocks
+  // per sample as fit the GPU's resident slots — 512 blocks on 296 slots (DiT-B/2, batch 32) ran 1.73 waves, i.e. the time
+  // of two; long runs also keep the per-(sample, channel) atomics cheap
+  const int slots = std::max(1, num_sms() * std::max(1, blocks_per_sm));
+  const int bps = std::max(1, std::min(slots / std::max(N, 1), cdiv(L, 8)));
+  return std::max(1, cdiv(L, 8 * bps));
 }
 
 extern "C" int b200_gate_bwd(const void *dh, const void *f, const float *gate, int gate_stride, void *df, float *dgate,
                              int dgate_stride, int N, int L, int C, int act_dtype, void *stream) {
   B200_CHECK(dh && f && gate && df && dgate && N > 0 && L > 0 && C % 8 == 0 && C <= kMaxVec * 256,
              "gate_bwd: bad arguments (C <= %d)", kMaxVec * 256);
-  const int rpw = rows_per_warp_for(N, L);
-  const int blocks = N * cdiv(L, 8 * rpw);
   const int nv = cdiv(C / 8, 32);
 #define L2_(TT, NV)                                                                                                  \
   do {                                                                                                               \
     const size_t smem_ = (size_t)8 * C * sizeof(float);                                                              \
     if (smem_ > 48 * 1024)                                                                                           \
       B200_CUDA(cudaFuncSetAttribute(gate_bwd_kernel<TT, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_)); \
+    static int per_sm_ = 0;           /* per (type, NV) instantiation (first C seen sizes the wave) */           \
+    if (per_sm_ == 0)                                                                                                \
+      B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_, gate_bwd_kernel<TT, NV>, 256, smem_));         \
+    const int rpw = rows_per_warp_for(N, L, per_sm_);                                                                \
+    const int blocks = N * cdiv(L, 8 * rpw);                                                                         \
     gate_bwd_kernel<TT, NV><<<blocks, 256, smem_, (cudaStream_t)stream>>>((const TT *)dh, (const TT *)f, gate,       \
         gate_stride, (TT *)df, dgate, dgate_stride, N, L, C, rpw);                                                    \
   } while (0)
@@ -932,14 +1023,17 @@ extern "C" int b200_ln_mod_bwd(const void *x, const void *da, const float *scale
                                void *stream) {
   B200_CHECK(x && da && scale && dx && dshift && dscale && N > 0 && L > 0 && C % 8 == 0 && C <= kMaxVec * 256,
              "ln_mod_bwd: bad arguments (C <= %d)", kMaxVec * 256);
-  const int rpw = rows_per_warp_for(N, L);
-  const int blocks = N * cdiv(L, 8 * rpw);
   const int nv = cdiv(C / 8, 32);
 #define L2_(TT, NV)                                                                                                  \
   do {                                                                                                               \
     const size_t smem_ = (size_t)17 * C * sizeof(float);                                                             \
     if (smem_ > 48 * 1024)                                                                                           \
       B200_CUDA(cudaFuncSetAttribute(ln_mod_bwd_kernel<TT, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_)); \
+    static int per_sm_ = 0;           /* per (type, NV) instantiation (first C seen sizes the wave) */           \
+    if (per_sm_ == 0)                                                                                                \
+      B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_, ln_mod_bwd_kernel<TT, NV>, 256, smem_));       \
+    const int rpw = rows_per_warp_for(N, L, per_sm_);                                                                \
+    const int blocks = N * cdiv(L, 8 * rpw);                                                                         \
     ln_mod_bwd_kernel<TT, NV><<<blocks, 256, smem_, (cudaStream_t)stream>>>((const TT *)x, (const TT *)da, scale,    \
         mod_stride, (const TT *)dres, (TT *)dx, dshift, dscale, dmod_stride, N, L, C, eps, rpw);                      \
   } while (0)

@@ -114,6 +114,8 @@ class DiTTrainer:
         self.graph_warmup = 2
         self._graphs: dict = {}
         self._graph_seen: dict = {}
+        self.graph_kernels = 0          # kernels in the last captured step graph
+        self.replayed_kernels = 0       # kernels launched through graph replays so far (the C-side counter only sees eager launches)
 
     # -- helpers -------------------------------------------------------------------------------
     def _grad_view(self, name: str, shape) -> Tensor:
@@ -202,6 +204,7 @@ class DiTTrainer:
         self.step_count += 1
         st["hyper"].copy_(torch.tensor(T.adamw_hyper(self.lr, self.betas, self.step_count), dtype=torch.float32))
         st["graph"].replay()
+        self.replayed_kernels += st["kernels"]
         self.model.invalidate()
         self.last_terms = st["terms"]
         return st["out"]
@@ -215,10 +218,13 @@ class DiTTrainer:
             dist.barrier(self.group)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
+        n0 = L.launch_count()
         with torch.cuda.graph(g):
             st["out"] = self._step(st["x"], st["cond"], st["noise"], st["coef"], st["t_model"], True, st["hyper"])
             st["terms"] = self.last_terms
         st["graph"] = g
+        st["kernels"] = L.launch_count() - n0          # libb200diff launches captured in (= replayed by) this graph
+        self.graph_kernels = st["kernels"]
         self._graphs[key] = st
         return st
 

@@ -193,4 +193,6 @@ def test_dsunet_with_low_planes_matches_the_oracle(kinds):
     cond = x[:, 1:].cuda()
     assert net.prepare_conditioning([cond])
     y2, _ = net(x.cuda(), t.cuda(), cond_cached=True)
-    assert O.rel_err(y2.cpu(), y1.cpu()) < 1e-3
+    # the cached conv1 output is rounded BEFORE the bias + timestep term is added (inside the next GroupNorm): a different
+    # rounding point, the same bound (tests/test_gpu_model.py::test_hoisted_conditioning_prefix...)
+    assert O.rel_err(y2.cpu(), ref) < 2e-3 and O.rel_err(y2.cpu(), y1.cpu()) < 2e-3
