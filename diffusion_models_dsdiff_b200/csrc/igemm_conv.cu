@@ -472,7 +472,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + acc * kAccCols;
 
       // residual for one 16-column chunk, issued one chunk ahead so its latency hides behind the previous chunk's math
-      auto load_res = [&](int c, uint4 (&q)[2]) {
+      auto load_res = [&](int c, uint4 (&q)[2], uint4 (&ql)[2]) {
         const int co = n_tile * p.BN + c;
         q[0] = make_uint4(0, 0, 0, 0);
         q[1] = q[0];
@@ -484,8 +484,11 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
             if (co + 8 < p.Cout) q[1] = *reinterpret_cast<const uint4 *>(res + pix * p.Cout + co + 8);
           }
         }
+        if constexpr (kFast) {      // the residual's low plane travels one chunk ahead like the residual itself
+          if (res_lo) ld_global_256(res_lo + pix * p.Cout + co, ql[0], ql[1]);
+        }
       };
-      auto process = [&](const uint32_t (&r)[16], const uint4 (&rq)[2], int c) {
+      auto process = [&](const uint32_t (&r)[16], const uint4 (&rq)[2], const uint4 (&lq)[2], int c) {
         const int co = n_tile * p.BN + c;
         float v[16];
         uint4 packed[2];
@@ -521,9 +524,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
               v[2 * j + 1] = fmaf(p.res_scale, f.y, v[2 * j + 1]);
             }
           }
-          if (res_lo) {      // low plane of the residual (prefetched into L2 above; loaded here to keep the register budget)
-            uint4 lq[2];
-            ld_global_256(res_lo + pix * p.Cout + co, lq[0], lq[1]);
+          if (res_lo) {      // low plane of the residual
             const uint32_t *lw = reinterpret_cast<const uint32_t *>(lq);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -684,29 +685,29 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       };
 
       uint32_t ra[16], rb[16];
-      uint4 qa[2], qb[2];
+      uint4 qa[2], qb[2], la[2], lb[2];
       int ci = g;
       if (ci < nch) {
         tmem_ld16(taddr + ci * 16, ra);
-        load_res(ci * 16, qa);
+        load_res(ci * 16, qa, la);
       }
       while (ci < nch) {
         tmem_ld_wait_dep(ra);
         int cn = ci + 2;
         if (cn < nch) {
           tmem_ld16(taddr + cn * 16, rb);
-          load_res(cn * 16, qb);
+          load_res(cn * 16, qb, lb);
         }
-        process(ra, qa, ci * 16);
+        process(ra, qa, la, ci * 16);
         ci = cn;
         if (ci >= nch) break;
         tmem_ld_wait_dep(rb);
         cn = ci + 2;
         if (cn < nch) {
           tmem_ld16(taddr + cn * 16, ra);
-          load_res(cn * 16, qa);
+          load_res(cn * 16, qa, la);
         }
-        process(rb, qb, ci * 16);
+        process(rb, qb, lb, ci * 16);
         ci = cn;
       }
       tc_fence_before();

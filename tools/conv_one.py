@@ -1,6 +1,7 @@
 """One conv shape, a few launches (ncu --set full target).
 
-    python tools/conv_one.py N H W Cin Cout [k] [flags: s=fused GN statistics, r=residual, b=timestep row bias]
+    python tools/conv_one.py N H W Cin Cout [k] [flags: s=fused GN statistics, r=residual, b=timestep row bias,
+                                                        l=write the low plane (out_lo), L=residual low plane]
 """
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -21,6 +22,10 @@ if "r" in flags:
     kw["residual"] = torch.randn(n, h, w, co, device=dev).half()
 if "b" in flags:
     kw["rowbias"] = torch.randn(n, co, device=dev)
+if "l" in flags:
+    kw["out_lo"] = torch.empty_like(out)
+if "L" in flags:
+    kw["residual_lo"] = (torch.randn(n, h, w, co, device=dev) * 1e-3).half()
 run = lambda: ops.conv2d([(x, wt, 0, k, k // 2)], bias=b, out=out, **kw)
 for _ in range(6):
     run()
