@@ -576,6 +576,10 @@ def run_b200(args):
                    "parallelism": f"slice-sharded x{world}, no data-path collective",
                    "l2": "activations per layer exceed the 126 MB L2 (inputs larger than L2; no explicit flush)",
                    "cuda_graph": True, "graph_kernels_per_denoise_step": per_step,
+                   "activation_storage": ("16-bit NHWC; hi + lo plane pairs (32 bits) for " +
+                                          ",".join(sorted(net.lo_policy.kinds)) + f" on maps >= {net.lo_policy.min_pixels} "
+                                          "pixels (unet.LoPolicy, B200DIFF_LO_PLANES)") if getattr(net, "lo_policy", None)
+                                         else "16-bit NHWC everywhere",
                    "loop_invariant_hoisting": ("conditioning encoders' first conv + first ResBlock GN/conv1 evaluated once "
                                                f"per sampling run ({hoisted:.1f} of {per_fwd:.1f} GFLOP per slice-step); "
                                                "model_tflops_per_gpu counts executed FLOPs") if hoisted else None},

@@ -118,7 +118,7 @@ def loops():
 def _reference_network(name):
     """The reference's OWN module for this workload (byte-compiled oracle/_ref on the GPU box), random-init."""
     _ref_import.install()
-    if name == "cfg2":
+    if name in ("cfg2", "cfg2p"):
         from UNet_DS_Diff.model import DSUnetModel as Ref
     else:
         from ldm.modules.diffusionmodules.openaimodel import UNetModel as Ref
@@ -230,6 +230,46 @@ def test_cfg2_sixteen_bit_storage_everywhere_is_what_the_low_planes_fix(loops):
     print(f"\n[cfg2] t={t}: 16-bit storage everywhere {plain:.4e}, default low planes {r['per_step'][t]:.4e}")
     assert 1.3e-3 <= plain <= 1.5e-3, plain
     assert r["per_step"][t] <= 0.92 * plain, (r["per_step"][t], plain)
+
+
+def test_cfg2p_shipped_inference_network_vs_reference_deviation():
+    """cfg2' — the 96-channel learned-sigma FiLM DS-Diff that inference_config.yaml really runs — one network evaluation at
+    256 x 256 (t = 961) against the fp32 oracle, next to the reference's own modules on this GPU (TF32 "high" as shipped vs
+    their strict fp32).  Measured: reference deviation 1.25e-3; this path 1.56e-3 = 1.25 x with the default low planes
+    (1.68e-3 = 1.34 x with 16-bit storage everywhere, 1.36e-3 = 1.08 x with every >= 128 x 128 tensor kept as a pair:
+    tools/lo_policy_probe.py).  This narrow network is HBM-bound, so the default policy is the one tuned on the benchmarked
+    320-channel model; the assert is the measured ratio + 4 %."""
+    wl, net, sd = _build("cfg2p")
+    cond, x_T = bench.synth_inputs(1, wl["cond_ch"], 256, 0)
+    xc = torch.cat([x_T, cond], 1)
+    ts = torch.tensor([961])
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = O.dsunet_forward(sd, wl["hp"], xc, ts)[0]
+    got = net(xc.cuda(), ts.cuda())[0].cpu()
+    rel = O.rel_err(got, ref)
+    dev_ref = 1.2521e-3          # measured (above); re-measured below when the compiled reference travelled to the box
+    if _ref_import.available():
+        ref_net = _reference_network("cfg2p")
+        ref_net.load_state_dict(sd, strict=True)
+        ref_net = ref_net.cuda()
+        try:
+            with torch.no_grad():
+                torch.backends.cuda.matmul.allow_tf32 = False
+                torch.backends.cudnn.allow_tf32 = False
+                torch.set_float32_matmul_precision("highest")
+                strict = ref_net(xc.cuda(), ts.cuda())[0].float().cpu()
+                torch.backends.cudnn.allow_tf32 = True
+                torch.set_float32_matmul_precision("high")
+                shipped = ref_net(xc.cuda(), ts.cuda())[0].float().cpu()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            torch.set_float32_matmul_precision("highest")
+        assert O.rel_err(strict, ref) <= 2e-5
+        dev_ref = O.rel_err(shipped, strict)
+    print(f"\n[cfg2p] t=961: this path {rel:.4e}, reference TF32 as shipped vs its own fp32 {dev_ref:.4e} ({rel / dev_ref:.3f} x)")
+    assert rel <= 1.30 * dev_ref, (rel, dev_ref)
 
 
 # -------------------------------------------------------------------------------------------------

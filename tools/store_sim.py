@@ -15,10 +15,19 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 import torch, torch.nn.functional as F
 import bench, dsdiff_oracle as O
 
-wl = bench.WORKLOADS["cfg2"]
+wl = bench.WORKLOADS[os.environ.get("WL", "cfg2")]
 hp = wl["hp"]
 torch.set_num_threads(os.cpu_count())
-sd = O.synth_state_dict(bench.meta_shapes(wl))
+if os.environ.get("SD") == "module":     # the weights the GPU tests use: module default init (seed 0) + de-zeroed zero_module tensors
+    import diffusion_models_dsdiff_b200 as P
+    torch.manual_seed(0)
+    sd = {k: v.detach().float() for k, v in getattr(P, wl["cls"])(**wl["hp"]).state_dict().items()}
+    _g = torch.Generator().manual_seed(1)
+    for _k, _v in sd.items():
+        if _v.numel() and not _v.any():
+            sd[_k] = torch.randn(_v.shape, generator=_g) * 0.02
+else:
+    sd = O.synth_state_dict(bench.meta_shapes(wl))
 cond, x_T = bench.synth_inputs(1, wl["cond_ch"], 256, 0)
 xc = torch.cat([x_T, cond], 1)
 T_STEP = int(os.environ.get("T_STEP", "1961"))
@@ -57,8 +66,13 @@ def resblock(p, x, emb, where):
     h = O.silu(O.group_norm(x_gn, sd[p + ".in_layers.0.weight"], sd[p + ".in_layers.0.bias"]))
     h = O.conv2d(sd, p + ".in_layers.2", h, opq=q)
     emb_out = O.linear(sd, p + ".emb_layers.1", O.silu(emb))[:, :, None, None]      # fp32 GEMV in the engine
-    h = store("conv1", where, h + emb_out)
-    h = O.silu(O.group_norm(h, sd[p + ".out_layers.0.weight"], sd[p + ".out_layers.0.bias"]))
+    if hp.get("use_scale_shift_norm"):      # FiLM (openaimodel.py:276-280): conv1 + bias is stored, the modulation is in the GN pass
+        h = store("conv1", where, h)
+        scale, shift = torch.chunk(emb_out, 2, dim=1)
+        h = O.silu(O.group_norm(h, sd[p + ".out_layers.0.weight"], sd[p + ".out_layers.0.bias"]) * (1 + scale) + shift)
+    else:
+        h = store("conv1", where, h + emb_out)
+        h = O.silu(O.group_norm(h, sd[p + ".out_layers.0.weight"], sd[p + ".out_layers.0.bias"]))
     h = O.conv2d(sd, p + ".out_layers.3", h, opq=q)
     if p + ".skip_connection.weight" in sd:
         w = sd[p + ".skip_connection.weight"]
@@ -189,6 +203,20 @@ if __name__ == "__main__":
         "P: G + dec (rb, conv1) at 128": (lambda k, w, r: G(k, w, r) or (r >= 128 and w == "dec" and k in ("rb", "conv1")), ("gn", "res", "mean")),
         "Q: G + up at 256": (lambda k, w, r: G(k, w, r) or (r >= 256 and k == "up"), ("gn", "res", "mean")),
     }
+    if os.environ.get("BATCH") == "3":
+        ALL = ("in", "rb", "conv1", "mean", "up", "down")
+        cases = {
+            "engine, every store 16-bit": cases["engine today (every store 16-bit)"],
+            "operands only": cases["operands only (all stores exact)"],
+            "G (shipped default)": G,
+            "G + mean": lambda k, w, r: G(k, w, r) or (r >= 256 and k == "mean"),
+            "G + enc conv1": lambda k, w, r: G(k, w, r) or (r >= 256 and k == "conv1"),
+            "G + enc rb": lambda k, w, r: G(k, w, r) or (r >= 256 and k == "rb"),
+            "G + up": lambda k, w, r: G(k, w, r) or (r >= 256 and k == "up"),
+            "G kinds at >= 128": lambda k, w, r: r >= 128 and ((w == "dec" and k in ("rb", "conv1")) or k == "in"),
+            "everything at 256": lambda k, w, r: r >= 256,
+            "everything at >= 128": lambda k, w, r: r >= 128,
+        }
     if os.environ.get("BATCH") == "2":
         cases = {"engine today (every store 16-bit)": cases["engine today (every store 16-bit)"]}
         cases.update(cases2)
