@@ -10,10 +10,10 @@ import torch
 import torch.nn.functional as F
 
 import dsdiff_oracle as O
-from _util import golden, maxabs, synth_sd
+from _util import golden, maxabs, rel_tol, synth_sd
 
 pytestmark = pytest.mark.gpu
-REL_TOL = {torch.float16: 3e-3, torch.bfloat16: 2.5e-2}
+# relative-L2 bounds: rel_tol(fixture, dtype) = measured on a B200 x 1.2 (tests/_util.py MEASURED_REL)
 
 
 def _pkg():
@@ -76,16 +76,17 @@ def test_autoencoder_kl_matches_reference(dtype):
     g = golden("ae_small")
     post = ae.encode(g["x"].cuda())
     assert post.parameters.shape == g["moments"].shape
-    assert O.rel_err(post.parameters.cpu(), g["moments"]) < REL_TOL[dtype]
+    assert O.rel_err(post.parameters.cpu(), g["moments"]) < rel_tol("ae_small.moments", dtype)
     # against the oracle with operands rounded at the same places
     momq = O.ae_encode_moments(sd, g["x"], opq=lambda v: v.to(dtype).float())
-    assert O.rel_err(post.parameters.cpu(), momq) < REL_TOL[dtype]
+    assert O.rel_err(post.parameters.cpu(), momq) < rel_tol("ae_small.moments_sameq", dtype)
     z = post.sample(noise=g["noise"].cuda())
     assert maxabs(z.cpu(), O.ae_posterior_sample(post.parameters.cpu(), g["noise"])) < 1e-5
     dec = ae.decode(g["z"].cuda())
     assert dec.shape == g["dec"].shape and dec.dtype == torch.float32
-    assert O.rel_err(dec.cpu(), g["dec"]) < REL_TOL[dtype]
-    assert maxabs(dec.cpu(), g["dec"]) < (1e-2 if dtype == torch.float16 else 8e-2) * max(1.0, float(g["dec"].abs().max()))
+    assert O.rel_err(dec.cpu(), g["dec"]) < rel_tol("ae_small.dec", dtype)
+    # max-abs of the decoded image: measured 3.1e-3 (fp16) / 2.6e-2 (bf16) x 1.25
+    assert maxabs(dec.cpu(), g["dec"]) < (4e-3 if dtype == torch.float16 else 3.3e-2) * max(1.0, float(g["dec"].abs().max()))
 
 
 def test_autoencoder_cpu_raises():
@@ -146,9 +147,9 @@ def test_cross_attention_unet_matches_reference(case, dtype):
     g = golden(case)
     y = net(g["x"].cuda(), g["t"].cuda(), context=g["context"].cuda()).cpu()
     assert y.shape == g["y"].shape
-    assert O.rel_err(y, g["y"]) < REL_TOL[dtype], f"{case}: {O.rel_err(y, g['y']):.3e}"
+    assert O.rel_err(y, g["y"]) < rel_tol(case, dtype), f"{case}: {O.rel_err(y, g['y']):.3e}"
     yq = O.unet_forward(sd, hp, g["x"], g["t"], opq=lambda v: v.to(dtype).float(), context=g["context"])
-    assert O.rel_err(y, yq) < REL_TOL[dtype]
+    assert O.rel_err(y, yq) < rel_tol(case + ".sameq", dtype)
 
 
 def test_latent_diffusion_ancestral_loop_and_decode():
@@ -177,7 +178,8 @@ def test_latent_diffusion_ancestral_loop_and_decode():
     sch = O.LdmSchedule(timesteps=T)
     ref = O.ldm_ddpm_loop(lambda xc, ts: O.unet_forward(sd, hp, xc, ts, context=ctx), sch, x_T, None, noises,
                           parameterization="eps", clip_denoised=False)
-    assert maxabs(out.cpu(), ref) < 2e-2 * max(1.0, float(ref.abs().max()))
+    # 6-step ancestral chain in latent space: measured 6.1e-4 (bound = x 1.5: a chain compounds run-to-run rounding differences)
+    assert maxabs(out.cpu(), ref) < 9.2e-4 * max(1.0, float(ref.abs().max()))
     # graph path: same torch seed => same noise draws as the eager loop
     outs = []
     for use_graph in (False, True):
@@ -188,7 +190,7 @@ def test_latent_diffusion_ancestral_loop_and_decode():
     img = ld.decode_first_stage(out)
     ref_img = O.ae_decode(asd, ref / 0.5)
     assert img.shape == (2, 1, 32, 32)
-    assert maxabs(img.cpu(), ref_img) < 3e-2 * max(1.0, float(ref_img.abs().max()))
+    assert maxabs(img.cpu(), ref_img) < 3.4e-3 * max(1.0, float(ref_img.abs().max()))       # decoded: measured 2.24e-3 x 1.5
     with pytest.raises(NotImplementedError):      # LatentDiffusion.p_mean_variance has no v branch (ddpm.py:941-946)
         ld.parameterization = "v"
         ld.sample({"c_crossattn": [ctx.cuda()]}, batch_size=2, shape=(2, 3, 16, 16))
@@ -212,13 +214,11 @@ def test_dit_forward_matches_reference_golden(case, dtype):
     cond = g["cond"].cuda() if "cond" in g else None
     y = net(g["x"].cuda(), g["t"].cuda(), y=labels, cond=cond).cpu()
     assert y.shape == g["y_out"].shape and y.dtype == torch.float32
-    # tolerance: same operand-rounding floor as the UNet tests (tests/test_gpu_model.py REL_TOL)
-    tol = {torch.float16: 2e-3, torch.bfloat16: 1.6e-2}[dtype]
-    rel = O.rel_err(y, g["y_out"])
-    assert rel < tol, f"{case} {dtype}: rel err {rel:.3e}"
+    rel = O.rel_err(y, g["y_out"])              # fp16: 6.2e-4 .. 7.2e-4 measured, i.e. inside north_star's 1e-3 with the margin
+    assert rel < rel_tol(case, dtype), f"{case} {dtype}: rel err {rel:.3e}"
     sd["pos_embed"] = g["pos_embed"]
     yq = O.dit_forward(sd, hp, g["x"], g["t"], y=g.get("labels"), cond=g.get("cond"), opq=lambda v: v.to(dtype).float())
-    assert O.rel_err(y, yq) < tol
+    assert O.rel_err(y, yq) < rel_tol(case + ".sameq", dtype)
 
 
 def test_dit_head_padding_and_step_table():
@@ -236,7 +236,7 @@ def test_dit_head_padding_and_step_table():
     t = torch.tensor([11.0, 11.0])
     y = net(x.cuda(), t.cuda()).cpu()
     ref = O.dit_forward(sd, hp, x, t)
-    assert O.rel_err(y, ref) < 2e-3
+    assert O.rel_err(y, ref) < rel_tol("dit_small.padded_head")
     table = torch.tensor([500.0, 11.0, 3.0]).cuda()
     step = torch.tensor([1], dtype=torch.int32).cuda()
     y2 = net(x.cuda(), table, step_ptr=step).cpu()
@@ -267,7 +267,7 @@ def test_dit_in_guided_diffusion_ddim_loop_matches_oracle():
     sch = O.GdSchedule(steps=1000, timestep_respacing="4", rescale_timesteps=True)
     ref = O.gd_loop(lambda xc, ts: O.dit_forward(sd, hp, xc, ts), sch, x_T, cond, noises, mode="ddim", eta=0.0,
                     parameterization="v", learn_sigma=True)
-    assert maxabs(out.cpu(), ref) < 1e-2
+    assert maxabs(out.cpu(), ref) < 3.5e-3                 # north_star 1e-2; measured 2.35e-3 x 1.5
     out_graph = d.ddim_sample_loop(wrap, (2, 1, 32, 32), noise=x_T.cuda(), clip_denoised=True,
                                    model_kwargs={"c_concat": [cond.cuda()]}, eta=0.0)
     assert maxabs(out_graph, out) < 1e-6
@@ -302,16 +302,16 @@ def test_latent_get_input_and_concat_conditioning_glue():
     z, c = ld.get_input(batch, "pet", cond_key="image", noise=nz[0].cuda())
     assert z.shape == (3, 3, 16, 16) and torch.equal(c.cpu(), image)
     zr = ref_latent(target, nz[0])
-    assert O.rel_err(z.cpu(), zr) < REL_TOL[torch.float16]
+    assert O.rel_err(z.cpu(), zr) < rel_tol("latent_glue.encode")
     z2, c2, x, xrec = ld.get_input(batch, "pet", cond_key="image", bs=2, return_first_stage_outputs=True, noise=nz[0][:2].cuda())
     assert z2.shape[0] == 2 and c2.shape[0] == 2 and x.shape == (2, 1, 32, 32) and xrec.shape == (2, 1, 32, 32)
     assert torch.equal(z2, z[:2])
     # a 3-contrast conditioning image is 3 channels: the reference only splits when C > 3 (:157-158) — then ONE encode ...
     one = ld.get_concat_conditioning(image[:, :1], n_keys=1, noises=[nz[1]])["c_concat"][0]
-    assert O.rel_err(one.cpu(), ref_latent(contrasts[0], nz[1])) < REL_TOL[torch.float16]
+    assert O.rel_err(one.cpu(), ref_latent(contrasts[0], nz[1])) < rel_tol("latent_glue.one")
     # ... while 4+ channels are chunked into len(keys) images, each encoded on its own and concatenated along C
     four = torch.cat(contrasts + [target], 1)
     got = ld.get_concat_conditioning(four, n_keys=4, noises=nz)["c_concat"][0]
     assert got.shape == (3, 12, 16, 16)
     want = torch.cat([ref_latent(v, n_) for v, n_ in zip(contrasts + [target], nz)], 1)
-    assert O.rel_err(got.cpu(), want) < REL_TOL[torch.float16]
+    assert O.rel_err(got.cpu(), want) < rel_tol("latent_glue.concat")

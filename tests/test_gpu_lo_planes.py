@@ -166,7 +166,7 @@ def test_dsunet_with_low_planes_matches_the_oracle(kinds):
     import diffusion_models_dsdiff_b200 as P
     from diffusion_models_dsdiff_b200 import ops
     from diffusion_models_dsdiff_b200.unet import LoPolicy
-    from _util import synth_sd
+    from _util import rel_tol, synth_sd
     hp, sd = synth_sd("ds_small")
     net = P.DSUnetModel(**hp).cuda().eval()
     net.load_state_dict(sd, strict=True)
@@ -187,7 +187,7 @@ def test_dsunet_with_low_planes_matches_the_oracle(kinds):
     details = [d for _, _, _, _, _, d in timer.records if d]
     assert any(d.endswith("+lo") for d in details), "no launch wrote / read a low plane"
     e0, e1 = O.rel_err(y0.cpu(), ref), O.rel_err(y1.cpu(), ref)
-    assert e1 < 2e-3 and e0 < 2e-3, (e0, e1)
+    assert e1 < rel_tol("ds_small.lo_planes") and e0 < rel_tol("ds_small.lo_planes"), (e0, e1)   # measured x 1.2
     assert e1 <= e0 * 1.1, (e0, e1)         # extra stored precision never costs accuracy
     # hoisted conditioning prefix (persistent first-conv planes) gives the same function
     cond = x[:, 1:].cuda()
@@ -195,4 +195,4 @@ def test_dsunet_with_low_planes_matches_the_oracle(kinds):
     y2, _ = net(x.cuda(), t.cuda(), cond_cached=True)
     # the cached conv1 output is rounded BEFORE the bias + timestep term is added (inside the next GroupNorm): a different
     # rounding point, the same bound (tests/test_gpu_model.py::test_hoisted_conditioning_prefix...)
-    assert O.rel_err(y2.cpu(), ref) < 2e-3 and O.rel_err(y2.cpu(), y1.cpu()) < 2e-3
+    assert O.rel_err(y2.cpu(), ref) < rel_tol("ds_small.lo_planes_hoisted") and O.rel_err(y2.cpu(), y1.cpu()) < rel_tol("ds_small.lo_planes_hoisted")

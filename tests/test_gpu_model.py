@@ -13,19 +13,18 @@ import pytest
 import torch
 
 import dsdiff_oracle as O
-from _util import golden, maxabs, synth_sd
+from _util import golden, maxabs, rel_tol, synth_sd
 
 pytestmark = pytest.mark.gpu
 
-# vs the pure-fp32 reference.  Operand rounding ALONE (exact fp32 everywhere else, measured with the oracle's
-# opq hook on these fixtures) already costs 0.93e-3 (fp16) / 7.8e-3 (bf16) relative, i.e. north_star's 1e-3
-# sits at the unit-roundoff floor of a 10-bit-mantissa operand format (the reference's own TF32 GPU path
-# has the same mantissa); the bound here is that floor plus the 16-bit activation stores.
-REL_TOL = {torch.float16: 2e-3, torch.bfloat16: 1.6e-2}
-# vs the oracle evaluated with matmul operands rounded at the same places (isolates kernel correctness: a wrong
-# kernel is off by >1e-2).  The remainder is the 16-bit STORE of every conv output (the residual stream lives in
-# HBM as 16-bit; the opq hook keeps it fp32): measured 1.06e-3..1.22e-3 (fp16) on these fixtures.
-REL_TOL_SAMEQ = {torch.float16: 1.5e-3, torch.bfloat16: 1.2e-2}
+# Every relative-L2 bound below is `rel_tol(fixture, dtype)` = the value MEASURED for that fixture on a B200 x 1.2
+# (tests/_util.py MEASURED_REL, profiles/r2_parity_measured.md), not a round number.
+# vs the pure-fp32 reference: operand rounding ALONE (exact fp32 everywhere else, measured with the oracle's opq hook on
+# these fixtures) already costs 0.93e-3 (fp16) / 7.8e-3 (bf16) relative, i.e. north_star's 1e-3 sits at the unit-roundoff
+# floor of a 10-bit-mantissa operand format (the reference's own TF32 GPU path has the same mantissa); the measured values
+# are that floor plus the 16-bit activation stores.
+# "<fixture>.sameq" = vs the oracle evaluated with matmul operands rounded at the same places (isolates kernel correctness:
+# a wrong kernel is off by > 1e-2); the remainder is the 16-bit STORE of every conv output.
 
 
 def _pkg():
@@ -51,10 +50,10 @@ def test_unet_forward_matches_reference_golden(case, dtype):
     y = net(g["x"].cuda(), g["t"].cuda()).cpu()
     assert y.shape == g["y"].shape and y.dtype == torch.float32
     rel = O.rel_err(y, g["y"])
-    assert rel < REL_TOL[dtype], f"{case} {dtype}: rel err {rel:.3e}"
+    assert rel < rel_tol(case, dtype), f"{case} {dtype}: rel err {rel:.3e}"
     # and against the oracle with operands rounded at the same places: isolates kernel bugs from precision
     yq = O.unet_forward(sd, hp, g["x"], g["t"], opq=lambda v: v.to(dtype).float())
-    assert O.rel_err(y, yq) < REL_TOL_SAMEQ[dtype]
+    assert O.rel_err(y, yq) < rel_tol(case + ".sameq", dtype)
 
 
 def test_unet_forward_is_deterministic_and_batch_independent():
@@ -117,14 +116,14 @@ def test_v1_ddim_loop_matches_reference(param, eta, dtype):
     out, inter = smp.sample(g["S"], g["x_T"].shape[0], tuple(g["x_T"].shape[1:]), g["cond"].cuda(), eta=eta,
                             x_T=g["x_T"].cuda(), verbose=False, noises=list(g["noises"]), record=rec)
     rel0 = O.rel_err(rec[0]["model_out"].cpu(), g["model_out"][0])
-    assert rel0 < REL_TOL[dtype], f"step-0 eps rel err {rel0:.3e}"
+    assert rel0 < rel_tol("v1_ddim.step0", dtype), f"step-0 eps rel err {rel0:.3e}"
     err = maxabs(out.cpu(), g["final"])
     if dtype == torch.float16 and param == "v":      # north_star: final slice within 1e-2 max-abs on [-1, 1]
         assert err < 1e-2, err
-    elif dtype == torch.float16:    # eps-param at T=2000 divides by sqrt(alpha_t) ~ 0.03 in the first step: a 2e-3
-        # relative error of eps becomes up to 2e-3 / 0.03 = 7e-2 of x0 before the clamp (ill-conditioned);
-        # measured 5e-2 .. 7e-2 depending on fp32 summation order
-        assert err < 1e-1, err
+    elif dtype == torch.float16:    # eps-param at T=2000 divides by sqrt(alpha_t) ~ 0.03 in the first step: a 1.5e-3
+        # relative error of eps becomes up to 1.5e-3 / 0.03 = 5e-2 of x0 before the clamp (ill-conditioned);
+        # measured 4.5e-2 (5e-2 .. 7e-2 with other fp32 summation orders during development): bound = worst seen x 1.15
+        assert err < 8e-2, err
     elif param == "v":              # eps-param divides by sqrt(alpha_t) ~ 0.03 at t=1961: bf16 noise is amplified
         assert err < 8e-2, err
     assert len(inter["x_inter"]) >= 2
@@ -191,13 +190,13 @@ def test_dsunet_forward_and_feature_dict_match_reference(dtype):
     hp, sd, net = _net("ds_small", dtype, _pkg().DSUnetModel)
     g = golden("ds_small")
     y, f = net(g["x"].cuda(), g["t"].cuda())
-    assert O.rel_err(y.cpu(), g["y"]) < REL_TOL[dtype]
+    assert O.rel_err(y.cpu(), g["y"]) < rel_tol("ds_small", dtype)
     assert set(f) == {"style", "content", "anatomy", "lesion", "n_style_content"}
     assert [len(f[k]) for k in ("style", "content", "anatomy", "lesion", "n_style_content")] == [3, 3, 2, 2, 4]
     for got, ref in ((f["style"][0], "style0"), (f["content"][2], "content2"), (f["anatomy"][1], "anatomy1"),
                      (f["lesion"][0], "lesion0")) + tuple((f["n_style_content"][i], f"nsc{i}") for i in range(4)):
         assert got.shape == g[ref].shape
-        assert O.rel_err(got.cpu(), g[ref]) < REL_TOL[dtype] * 1.5, ref
+        assert O.rel_err(got.cpu(), g[ref]) < rel_tol("ds_small.features", dtype), ref
 
 
 def test_dsunet_two_channel_input():
@@ -206,8 +205,8 @@ def test_dsunet_two_channel_input():
     y, _ = net(g["x"].cuda(), g["t"].cuda())
     # two of the four encoders see an all-zero stream (UNet_DS_Diff/model.py:654-658): their feature maps are spatially
     # CONSTANT, so every 16-bit rounding is the same at all pixels and adds coherently through the 3x3 convs instead of
-    # averaging out (measured 3.9e-3; the oracle with fp16-rounded operands alone is already at 1.4e-3).
-    assert O.rel_err(y.cpu(), g["y"]) < 6e-3
+    # averaging out (measured 3.87e-3; the oracle with fp16-rounded operands alone is already at 1.4e-3).
+    assert O.rel_err(y.cpu(), g["y"]) < rel_tol("ds_small_2ch")
 
 
 @pytest.mark.parametrize("mode,eta", [("ddim", 0.0), ("ddim", 0.5), ("ddpm", 0.0)])
@@ -330,7 +329,7 @@ def test_dpm_solver_sampler_matches_reference():
         g = golden(f"dpmpp_v_S{steps}")
         rec = []
         out, _ = DPMSolverSampler(m).sample(steps, 2, (1, 32, 32), g["cond"].cuda(), x_T=g["x_T"].cuda(), record=rec)
-        assert O.rel_err(rec[0]["model_out"].cpu(), g["model_out"][0]) < REL_TOL[torch.float16]
+        assert O.rel_err(rec[0]["model_out"].cpu(), g["model_out"][0]) < rel_tol("dpmpp.step0")
         assert maxabs(out.cpu(), g["final"]) < 1e-2          # north_star: final slice, [-1, 1] scale
         # CUDA-graph path (no record): same result as the eager loop
         out_g, _ = DPMSolverSampler(m).sample(steps, 2, (1, 32, 32), g["cond"].cuda(), x_T=g["x_T"].cuda())
@@ -447,7 +446,7 @@ def test_full_size_network_forward_vs_oracle(workload):
     # DDIM-50 run, profiles/r1_full_loop_parity_cfg1.json); the DS-Diff backbones sit at their 10-bit-operand floor (1.2e-3)
     # cfg2 with its default low planes (unet.LoPolicy): measured 1.23e-3 .. 1.25e-3 at this step (1.39e-3 with 16-bit storage
     # everywhere); the gate proper — 1.25 x the reference's own TF32 deviation — is tests/test_gpu_full_loop.py
-    tol = {"cfg1": 1e-3, "cfg2": 1.4e-3}.get(workload, REL_TOL[torch.float16])
+    tol = 1e-3 if workload == "cfg1" else rel_tol(workload + ".full_size", margin=1.15)     # cfg1: north_star verbatim
     assert rel < tol, f"{workload} full-size rel err {rel:.3e}"
     if hasattr(net, "prepare_conditioning"):        # the step as the samplers run it: conditioning prefix hoisted
         assert net.prepare_conditioning([cond.cuda()])
@@ -483,10 +482,10 @@ def test_ddim_classifier_free_guidance_matches_reference():
                                      unconditional_conditioning=g["uncond"].cuda())
     u, c = g["model_out2"][0].chunk(2)
     # guidance amplifies the network's rounding noise: out = s*c - (s-1)*u carries up to (2s - 1) = 5x the error of one
-    # evaluation; the 1e-2 final-slice gate of the unguided loops scales accordingly (measured 1.5e-2 at s = 3)
-    amp = 2 * g["scale"] - 1
-    assert O.rel_err(rec[0]["model_out"].cpu(), u + g["scale"] * (c - u)) < amp * REL_TOL[torch.float16]
-    assert maxabs(out.cpu(), g["final"]) < 1e-2 * amp
+    # evaluation; the 1e-2 final-slice gate of the unguided loops scales accordingly (measured 1.57e-2 at s = 3; the bound is
+    # that x 1.25; the guided step-0 output itself: measured 2.16e-3 x 1.2)
+    assert O.rel_err(rec[0]["model_out"].cpu(), u + g["scale"] * (c - u)) < rel_tol("cfg_guided.step0")
+    assert maxabs(out.cpu(), g["final"]) < 2e-2
     out_g, _ = S.DDIMSampler(m).sample(g["S"], 2, (1, 32, 32), g["cond"].cuda(), eta=0.0, x_T=g["x_T"].cuda(), verbose=False,
                                        unconditional_guidance_scale=g["scale"], unconditional_conditioning=g["uncond"].cuda())
     assert maxabs(out_g, out) < 1e-6        # CUDA-graph path == eager path (eta = 0: the drawn noise is multiplied by 0)
@@ -512,19 +511,19 @@ def test_dsdiff_loop_invariant_conditioning_prefix(case):
     n0 = P.launch_count(); net(x, t_table, step_ptr=step, return_features=False); n_full = P.launch_count() - n0
     n0 = P.launch_count(); net(x, t_table, step_ptr=step, return_features=False, cond_cached=True); n_h = P.launch_count() - n0
     assert n_h <= n_full - 6                                   # 3 streams x (first conv, GN, conv1) fewer launches
-    assert O.rel_err(hoisted, full) < REL_TOL[torch.float16]
+    assert O.rel_err(hoisted, full) < rel_tol(case + ".hoisted_vs_full")
     if case == "ds_small":                                     # accuracy vs the reference's fp32 output is unchanged
         g = golden("ds_small")
         net.prepare_conditioning([g["x"][:, 1:].cuda()])
         y_h, _ = net(g["x"].cuda(), g["t"].cuda(), return_features=False, cond_cached=True)
         y_f, _ = net(g["x"].cuda(), g["t"].cuda(), return_features=False)
         e_h, e_f = O.rel_err(y_h.cpu(), g["y"]), O.rel_err(y_f.cpu(), g["y"])
-        assert e_h < REL_TOL[torch.float16] and e_h < 1.15 * e_f
+        assert e_h < rel_tol("ds_small.hoisted") and e_h < 1.15 * e_f
     other = x.clone(); other[:, 1:] = x[:, 1:].flip(0) * 0.7   # a different conditioning re-arms the same buffers
     assert net.prepare_conditioning([other[:, 1:]])
     ref2, _ = net(other, t_table, step_ptr=step, return_features=False)
     got2, _ = net(other, t_table, step_ptr=step, return_features=False, cond_cached=True)
-    assert O.rel_err(got2, ref2) < REL_TOL[torch.float16]
+    assert O.rel_err(got2, ref2) < rel_tol(case + ".hoisted_step")
 
 
 @pytest.mark.parametrize("workload", ["cfg1", "cfg2"])
@@ -562,7 +561,7 @@ def test_resblock_updown_and_label_embedding_match_reference(case):
     g = golden(case)
     y = net(g["x"].cuda(), g["t"].cuda(), y=g["labels"].cuda()).cpu()
     rel = O.rel_err(y, g["y"])
-    assert rel < REL_TOL[torch.float16], f"{case}: rel err {rel:.3e}"
+    assert rel < rel_tol(case), f"{case}: rel err {rel:.3e}"
     with pytest.raises(AssertionError):
         net(g["x"].cuda(), g["t"].cuda())          # class-conditional model without y
 
@@ -575,7 +574,7 @@ def test_codebook_id_head_matches_reference():
     y = net(g["x"].cuda(), g["t"].cuda()).cpu()
     assert y.shape == g["y"].shape and y.dtype == torch.float32
     rel = O.rel_err(y, g["y"])
-    assert rel < REL_TOL[torch.float16], f"rel err {rel:.3e}"
+    assert rel < rel_tol("unet_codebook"), f"rel err {rel:.3e}"
 
 
 @pytest.mark.parametrize("param", ["v", "eps"])

@@ -7,7 +7,7 @@ import torch
 import torch.nn.functional as F
 
 import dsdiff_oracle as O
-from _util import synth_sd
+from _util import rel_tol, synth_sd
 
 pytestmark = pytest.mark.gpu
 
@@ -287,11 +287,12 @@ def test_grouped_encoders_match_separate_launches(n, streams):
     y_g, f_g = net(x.cuda(), t.cuda())
     net.group_max_pixels = 0
     y_s, f_s = net(x.cuda(), t.cuda())
-    assert O.rel_err(y_g.cpu(), ref) < 2e-3 and O.rel_err(y_s.cpu(), ref) < 2e-3
-    assert O.rel_err(y_g.cpu(), y_s.cpu()) < 2e-3
+    tol = rel_tol("ds_small.grouped")            # measured x 1.2 (tests/_util.py MEASURED_REL)
+    assert O.rel_err(y_g.cpu(), ref) < tol and O.rel_err(y_s.cpu(), ref) < tol
+    assert O.rel_err(y_g.cpu(), y_s.cpu()) < rel_tol("ds_small.grouped_vs_separate")
     for k in f_g:
         for a, b in zip(f_g[k], f_s[k]):
-            assert a.shape == b.shape and O.rel_err(a.cpu(), b.cpu()) < 4e-3, k
+            assert a.shape == b.shape and O.rel_err(a.cpu(), b.cpu()) < rel_tol("ds_small.grouped_features_vs_separate"), k
 
 
 def test_grouped_encoders_are_batch_independent():
