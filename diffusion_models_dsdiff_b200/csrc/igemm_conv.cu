@@ -40,7 +40,7 @@ struct ConvKParams {
   int seg_cin[3], seg_coff[3], seg_ks[3], seg_pad[3];
   int seg_padw[3];          // W padding (== seg_pad except for the 2x2 sub-pixel convolutions of a folded Upsample)
   int out_sy, out_sx, out_oy, out_ox;   // output pixel (h, w) is stored at (h*out_sy + out_oy, w*out_sx + out_ox); 1,1,0,0 = dense
-  int seg_halo[3];          // 3x3 stride-1 segment staged as 3 column-shifted (TH+2)-row boxes reused by the 3 tap rows
+  int seg_halo[3];          // k x k stride-1 segment (k = 3 pad 1, or k = 2) staged as k column-shifted (TH+k-1)-row boxes, each reused by its k tap rows
   const float *bias;
   const float *rowbias;
   int rowbias_stride;
@@ -200,7 +200,6 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
   const uint32_t b_bytes = (uint32_t)(p.BN / kCtas) * 128u;       // this CTA's share of a weight tile
   const uint32_t a_bytes = (uint32_t)p.a_bytes;
   const uint32_t stage_bytes = (uint32_t)p.stage_bytes;           // [activation box | up to 3 weight tiles]
-  const uint32_t halo_bytes = (uint32_t)(p.TH + 2) * p.TW * 128u;
   const int tile0 = blockIdx.x / kCtas, tile_step = gridDim.x / kCtas;
 
   if (threadIdx.x == 0) {
@@ -235,11 +234,12 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
   }
 
   // A pipeline stage is a GROUP of work, identical for the producer and the MMA issuer, per tile and segment:
-  //   halo segment : for c0 (64-channel chunk) / for sx (column shift): ONE activation box of (TH+2) rows + the THREE
-  //                  weight tiles of taps (r, sx), r = 0..2 — tap row r multiplies box rows [r*TW, r*TW+128): 12 MMAs;
+  //   halo segment : (k x k taps, k = 3 or 2) for c0 (64-channel chunk) / for sx (column shift): ONE activation box of
+  //                  (TH+k-1) rows + the k weight tiles of taps (r, sx), r = 0..k-1 — tap row r multiplies box rows
+  //                  [r*TW, r*TW+128): 4k MMAs;
   //   otherwise    : for tap / for c0: one 128-pixel activation box + one weight tile: 4 MMAs.
   // One full barrier (expect_tx = all bytes of the group) and one empty barrier per stage: the single-thread issue loops
-  // do one wait per 12 MMAs instead of one per 4.
+  // do one wait per 12 (8) MMAs instead of one per 4, and L2 -> SM bytes per MMA drop to 0.71 (0.78) of the per-tap schedule.
   if (warp == 0) {
     // ===================== TMA producer (one per CTA; whole warp runs the loop, one elected lane issues) ==========
     int st = 0;
@@ -287,10 +287,12 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
         const int ks = p.seg_ks[s], pad = p.seg_pad[s], cin = p.seg_cin[s];
         const int tbase = wset * ks * ks;                    // weight sets are stacked along the tap axis of the TMA map
         if (p.seg_halo[s]) {
+          // ks column shifts; each stages ONE (TH + ks - 1)-row box and the ks weight tiles of that column's taps
+          const uint32_t halo_bytes = (uint32_t)(p.TH + ks - 1) * p.TW * 128u;
           for (int c0 = 0; c0 < cin; c0 += kBK)
-            for (int sx = 0; sx < 3; ++sx, ++gi)
+            for (int sx = 0; sx < ks; ++sx, ++gi)
               if (gi >= g_begin && gi < g_end)
-                load_group(s, c0, n_tile, tbase + sx, 3, 3, halo_bytes, w0 + sx - 1, h0 - 1, n0);
+                load_group(s, c0, n_tile, tbase + sx, ks, ks, halo_bytes, w0 + sx - p.seg_padw[s], h0 - pad, n0);
         } else {
           for (int tap = 0; tap < ks * ks; ++tap) {
             const int r = tap / ks, sx = tap - r * ks;
@@ -345,9 +347,10 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
           const int taps = p.seg_ks[s] * p.seg_ks[s], cin = p.seg_cin[s];
           if (p.seg_halo[s]) {
             // tap row r = the 128 box rows starting r*TW pixels (r*TW*128 B, a multiple of the 1024-B swizzle atom)
+            const int ks = p.seg_ks[s];
             for (int c0 = 0; c0 < cin; c0 += kBK)
-              for (int sx = 0; sx < 3; ++sx, ++gi)
-                if (gi >= g_begin && gi < g_end) mma_group(3, (uint32_t)p.TW * 128u, (min(kBK, cin - c0) + 15) >> 4);
+              for (int sx = 0; sx < ks; ++sx, ++gi)
+                if (gi >= g_begin && gi < g_end) mma_group(ks, (uint32_t)p.TW * 128u, (min(kBK, cin - c0) + 15) >> 4);
           } else {
             for (int tap = 0; tap < taps; ++tap)
               for (int c0 = 0; c0 < cin; c0 += kBK, ++gi)
@@ -819,6 +822,12 @@ static void choose_tiling(const b200_conv_desc *d, int *ctas, int *bn) {
 // 1/S of the K groups and writes an fp32 partial tile (plain stores: deterministic); the finalize kernel adds the S
 // partials IN ORDER, applies bias / timestep bias / residual, stores 16-bit and accumulates the GroupNorm sums.
 // S depends on the layer geometry only (never on N), so an image's result does not depend on its batch.
+// halo staging of a segment: 3x3 pad-1 convolutions and the 2x2 sub-pixel convolutions of a folded Upsample (any padding)
+static bool seg_is_halo(const b200_conv_seg &g) {
+  static const bool no_k2 = getenv("B200DIFF_NO_HALO_K2") != nullptr;
+  return (g.ksize == 3 && g.pad == 1 && g.pad_w1 == 0) || (g.ksize == 2 && !no_k2);
+}
+
 static int conv_groups_total(const b200_conv_desc *d) {
   int TW = 1, TH = 1, TN = 1;
   pick_box(d->Hout, d->Wout, &TW, &TH, &TN);
@@ -826,7 +835,7 @@ static int conv_groups_total(const b200_conv_desc *d) {
   int g = 0;
   for (int s = 0; s < d->nseg; ++s) {
     const int chunks = cdiv(d->seg[s].cin, kBK);
-    g += (halo_ok && d->seg[s].ksize == 3 && d->seg[s].pad == 1 && d->seg[s].pad_w1 == 0) ? chunks * 3 : chunks * d->seg[s].ksize * d->seg[s].ksize;
+    g += (halo_ok && seg_is_halo(d->seg[s])) ? chunks * d->seg[s].ksize : chunks * d->seg[s].ksize * d->seg[s].ksize;
   }
   return g;
 }
@@ -967,14 +976,14 @@ static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t
   }
   // halo staging: 3x3 stride-1 pad-1 segments whose 128-pixel box lies in one image and is >= 8 pixels wide
   const bool halo_ok = d->stride == 1 && p.TN == 1 && p.TW >= 8 && !getenv("B200DIFF_NO_HALO");
-  bool any_halo = false;
+  int halo_taps = 1;        // weight tiles per stage = tap rows sharing one activation box (3, 2, or 1 without halo segments)
   for (int s = 0; s < d->nseg; ++s) {
-    p.seg_halo[s] = halo_ok && d->seg[s].ksize == 3 && d->seg[s].pad == 1 && d->seg[s].pad_w1 == 0;
-    any_halo |= p.seg_halo[s] != 0;
+    p.seg_halo[s] = halo_ok && seg_is_halo(d->seg[s]);
+    if (p.seg_halo[s]) halo_taps = std::max(halo_taps, d->seg[s].ksize);
   }
-  p.a_bytes = any_halo ? kABytes + 2 * p.TW * 128 : kABytes;
+  p.a_bytes = kABytes + (halo_taps - 1) * p.TW * 128;
   const size_t b_bytes = (size_t)(p.BN / kCtas) * 128;
-  p.stage_bytes = p.a_bytes + (any_halo ? 3 : 1) * (int)b_bytes;
+  p.stage_bytes = p.a_bytes + halo_taps * (int)b_bytes;
   p.stages = (int)std::min<size_t>(kMaxStages, (226 * 1024 - 1536 - kStatSmem) / p.stage_bytes);
   B200_CHECK(p.stages >= 2, "conv: tile too large for shared memory");
 
@@ -991,7 +1000,7 @@ static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t
       uint64_t str[3] = {(uint64_t)g.cin * 2, (uint64_t)d->Win * g.cin * 2,
                          (uint64_t)d->Hin * d->Win * g.cin * 2};
       uint32_t box[4] = {kBK, (uint32_t)(p.TW * d->stride), (uint32_t)(p.TH * d->stride), (uint32_t)p.TN};
-      if (p.seg_halo[s]) box[2] = (uint32_t)(p.TH + 2);
+      if (p.seg_halo[s]) box[2] = (uint32_t)(p.TH + g.ksize - 1);
       uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
       if (int rc = cached_tmap(&maps.a[s], g.src, 4, dims, str, box, es)) return rc;
     }

@@ -28,7 +28,9 @@ if "l" in flags:
     kw["out_lo"] = torch.empty_like(out)
 if "L" in flags:
     kw["residual_lo"] = (torch.randn(n, h, w, co, device=dev) * 1e-3).half()
-run = lambda: ops.conv2d([(x, wt, 0, k, k // 2)], stride=st, bias=b, out=out, **kw)
+if k == 2:      # one parity class of a folded Upsample: 2x2 taps, rows / columns {i - 1, i}, dense output of the input's size
+    kw["out_hw"] = (h, w)
+run = lambda: ops.conv2d([(x, wt, 0, k, (1, 1) if k == 2 else k // 2)], stride=st, bias=b, out=out, **kw)
 for _ in range(6):
     run()
 torch.cuda.synchronize()
