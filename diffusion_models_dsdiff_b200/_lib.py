@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # B200DIFF_LIB: another build of the same ABI (kernel A/B timing); default = the in-tree library next to this file
 LIB_PATH = os.environ.get("B200DIFF_LIB") or os.path.join(_HERE, "libb200diff.so")
 
-ABI_VERSION = 15        # must equal B200_ABI_VERSION of the header the library was built from
+ABI_VERSION = 16        # must equal B200_ABI_VERSION of the header the library was built from
 F16, BF16 = 0, 1
 SAMPLER_LDM_DDIM, SAMPLER_LDM_DDPM, SAMPLER_GD_DDIM, SAMPLER_GD_DDPM, SAMPLER_DPMPP_2M = 0, 1, 2, 3, 4
 SAMPLER_NCOEF = 16
@@ -93,6 +93,7 @@ SIGNATURES = {
     "b200_gather_row_f32": [_P, _P, _P, _I, _P],
     "b200_upsample_nearest2x": [_P, _P, _I, _I, _I, _I, _I, _P],
     "b200_avgpool2x": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "b200_head_gather9": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "b200_add4_scale": [_P, _P, _P, _P, _F, _P, _L, _I, _I, _P],
     "b200_add4_scale_stats": [_P, _P, _P, _P, _F, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _I, _P],
     "b200_se_attention": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],

@@ -660,6 +660,20 @@ def upsample_nearest2x(x: Tensor) -> Tensor:
     return out
 
 
+def head_gather9(taps: Tensor, bias: Optional[Tensor], channels: int) -> Tensor:
+    """Second half of a tap-split 3x3 network head (``unet.run_out_head``): ``taps`` is the fp32 NHWC result of the 1x1
+    convolution to 9 * channels tap channels (rows may be padded); returns fp32 NCHW [N, channels, H, W]."""
+    _dev(taps)
+    n, h, w, ldp = taps.shape
+    if taps.dtype != torch.float32 or not taps.is_contiguous() or not 1 <= channels <= 3 or ldp < 9 * channels:
+        raise L.B200Error("head_gather9: needs contiguous fp32 NHWC taps of >= 9 * channels columns, 1..3 channels")
+    out = torch.empty((n, channels, h, w), device=taps.device, dtype=torch.float32)
+    _timed("head_gather9", 0.0, 4.0 * (n * h * w * 9 * channels + out.numel()),
+           lambda: L.check(L.lib().b200_head_gather9(_p(taps), _p(_f32(bias)) if bias is not None else None, _p(out), n, h, w,
+                                                     channels, ldp, _stream()), "head_gather9"))
+    return out
+
+
 def avg_pool2x(x: Tensor) -> Tensor:
     """nn.AvgPool2d(2, 2) on an NHWC activation."""
     _dev(x)

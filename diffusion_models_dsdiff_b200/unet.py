@@ -387,6 +387,7 @@ def run_sequential(cx: Ctx, seq: nn.Sequential, x0: Act, x1: Optional[Act], conv
 
 
 _FOLD_UPSAMPLE = os.environ.get("B200DIFF_NO_UPSAMPLE_FOLD", "0") != "1"
+_SPLIT_HEAD = os.environ.get("B200DIFF_NO_SPLIT_HEAD", "0") != "1"       # 3x3 head as 1x1 tap channels + 9-point gather
 
 
 def run_upsample_conv(cx: Ctx, conv: nn.Conv2d, x: Act) -> Act:
@@ -452,6 +453,20 @@ def run_out_head(cx: Ctx, out: nn.Sequential, h: Act) -> Tensor:
     pw = cx.pw
     gn, conv = out[0], out[-1]
     a = run_gn(cx, gn, h, silu=len(out) == 3)
+    if _SPLIT_HEAD and conv.kernel_size[0] == 3 and conv.padding[0] == 1 and conv.out_channels <= 3:
+        # 3x3 head with 1..3 output channels: a 16-wide N tile would spend 9 taps x the MMAs (and 3.75 x the L2 -> SM bytes)
+        # of a 1x1 convolution on the same useful FLOPs.  Instead ONE 1x1 convolution to the 9 * C tap channels
+        # P[pixel, (3r + s) * C + co] = sum_ci h[pixel, ci] W[co, ci, r, s] (fp32 NHWC out of the accumulators) and a 9-point
+        # gather out[h, w] = bias + sum_{r,s} P[h + r - 1, w + s - 1, tap] (b200_head_gather9): same products, fp32 sums.
+        key = ("out9", id(conv))
+        c = conv.out_channels
+        if key not in pw.conv:
+            cpad = (9 * c + 15) // 16 * 16
+            w = torch.zeros((cpad, conv.in_channels, 1, 1), device=a.device)
+            w[:9 * c, :, 0, 0] = conv.weight.detach().float().permute(2, 3, 0, 1).reshape(9 * c, conv.in_channels)
+            pw.conv[key] = (ops.pack_conv_weight(w, a.dtype), conv.bias.detach().float().contiguous())
+        wp, bias = pw.conv[key]
+        return ops.head_gather9(ops.conv2d([(a, wp, 0, 1, 0)], out_f32=True), bias, c)
     # tensor-core path with the output channels zero-padded to whole 16-wide N tiles; the epilogue writes fp32 NCHW
     key = ("out", id(conv))
     if key not in pw.conv:

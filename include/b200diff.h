@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B200_ABI_VERSION 15
+#define B200_ABI_VERSION 16
 #define B200_F16 0
 #define B200_BF16 1
 
@@ -267,6 +267,12 @@ int b200_gather_row_f32(const float *table, const int *step_ptr, float *out, int
  * nearest x2 upsample (Upsample.forward F.interpolate, openaimodel.py:113-117), NHWC.          */
 int b200_upsample_nearest2x(const void *src, void *dst, int N, int H, int W, int C, int act_dtype,
                             void *stream);
+/* Second half of a 3x3 network head with C = 1..3 output channels (self.out[-1], openaimodel.py:898-902; UNet_DS_Diff/model.py
+ * `self.out`) evaluated as a 1x1 convolution to 9*C tap channels (b200_conv2d_igemm, fp32 NHWC rows of `ldp` floats,
+ * tap-major: element (3r+s)*C + co) plus this gather: out[n,co,h,w] = bias[co] + sum_{r,s} taps[n,h+r-1,w+s-1,(3r+s)*C+co],
+ * zero outside the image.  `out` is fp32 NCHW [N,C,H,W]; bias may be NULL.                                          */
+int b200_head_gather9(const float *taps_nhwc, const float *bias, float *out_nchw, int N, int H, int W, int C, int ldp,
+                      void *stream);
 /* nn.AvgPool2d(2, 2) on NHWC act: Downsample(use_conv=False) and the h_upd / x_upd of ResBlock(down=True)
  * (openaimodel.py:158-160, 216-218, 265-270).  H, W even.                                                     */
 int b200_avgpool2x(const void *src_nhwc, void *dst_nhwc, int N, int H, int W, int C, int act_dtype, void *stream);

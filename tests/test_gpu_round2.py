@@ -339,3 +339,50 @@ def test_folded_upsample_conv_matches_interpolate_then_conv(shape, dt):
     yf = got.t.float()
     exact = torch.stack([yf.double().sum((1, 2)), (yf.double() ** 2).sum((1, 2))], -1)
     assert torch.allclose(got.cs, exact, rtol=1e-5, atol=1e-3)
+
+
+# -------------------------------------------------------------------------------------------------
+# 3x3 network head with 1..3 output channels = 1x1 convolution to 9*C tap channels + 9-point gather (b200_head_gather9)
+# -------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64, 1), (1, 24, 40, 96, 2), (3, 8, 8, 32, 3), (1, 64, 64, 320, 1)])
+def test_split_head_matches_conv3x3_and_the_unsplit_path(shape, dt):
+    """self.out = GroupNorm, SiLU, conv3x3 (openaimodel.py:898-902): the tap-split form equals F.conv2d on the same 16-bit
+    operand (fp32 sums in another order) and the padded-N-tile 3x3 form it replaces."""
+    import torch.nn as nn
+    from diffusion_models_dsdiff_b200 import unet as U
+    ops = _ops()
+    n, h, w, ci, co = shape
+    x = rnd(80, n, ci, h, w)
+    head = nn.Sequential(nn.GroupNorm(32, ci), nn.SiLU(), nn.Conv2d(ci, co, 3, padding=1))
+    with torch.no_grad():
+        head[0].weight.copy_(1.0 + rnd(81, ci, scale=0.2))
+        head[0].bias.copy_(rnd(82, ci, scale=0.2))
+        head[2].weight.copy_(rnd(83, co, ci, 3, 3, scale=1.0 / math.sqrt(9 * ci)))
+        head[2].bias.copy_(rnd(84, co, scale=0.1))
+    head = head.cuda()
+
+    def run(split):
+        class PW:
+            conv = {}
+        arena = ops.StatsArena()
+        arena.begin(torch.device("cuda"))
+        old, U._SPLIT_HEAD = U._SPLIT_HEAD, split
+        try:
+            return U.run_out_head(U.Ctx(PW(), None, arena), head, U.Act(nhwc(x, dt)))
+        finally:
+            U._SPLIT_HEAD = old
+
+    n0 = ops.L.lib().b200_launch_count()
+    got = run(True)
+    assert ops.L.lib().b200_launch_count() - n0 >= 3          # GroupNorm (+ statistics), 1x1 convolution, gather
+    assert got.shape == (n, co, h, w) and got.dtype == torch.float32
+    unsplit = run(False)
+    # the conv operand both forms read: the 16-bit GroupNorm + SiLU output
+    a = ops.group_norm(nhwc(x, dt), head[0].weight.float(), head[0].bias.float())
+    ref = F.conv2d(nchw(a), q(head[2].weight.detach().cpu(), dt), head[2].bias.detach().cpu(), padding=1)
+    scale = max(1.0, ref.abs().max().item())
+    # same GroupNorm launch, same operands, fp32 sums in another order: the two forms agree to fp32 roundoff
+    assert (got.cpu() - unsplit.cpu()).abs().max().item() < 2e-5 * scale
+    # vs torch on the operand of a separately launched GroupNorm (its statistics pass may round an element the other way)
+    close(got.cpu(), ref, dt, f"split head {shape}")

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/b200diff.h but not exported"
     assert set(L.SIGNATURES) == set(syms), "ctypes table and header disagree"
-    assert L.lib().b200_abi_version() == L.ABI_VERSION == 15
+    assert L.lib().b200_abi_version() == L.ABI_VERSION == 16
     assert L.lib().b200_launch_count() == 0 or True
 
 
