@@ -447,6 +447,13 @@ def run_in_conv(cx: Ctx, conv: nn.Conv2d, x: Tensor, dtype: torch.dtype) -> Act:
                     lo=cx.want_lo("in", x.shape[2], x.shape[3]))
 
 
+def split_head_weight(w: Tensor) -> Tensor:
+    """[C, Cin, 3, 3] -> [9 * C, Cin]: row (3 r + s) * C + co holds W[co, :, r, s] — the 1x1 "tap channel" weights of the
+    tap-split network head (``run_out_head``; gather: ``b200_head_gather9``)."""
+    c, cin = w.shape[0], w.shape[1]
+    return w.permute(2, 3, 0, 1).reshape(9 * c, cin)
+
+
 def run_out_head(cx: Ctx, out: nn.Sequential, h: Act) -> Tensor:
     """self.out = GN, SiLU, conv3x3 (openaimodel.py:898-902) or id_predictor = GN, conv1x1 (:903-907):
     NHWC 16-bit -> NCHW fp32."""
@@ -463,7 +470,7 @@ def run_out_head(cx: Ctx, out: nn.Sequential, h: Act) -> Tensor:
         if key not in pw.conv:
             cpad = (9 * c + 15) // 16 * 16
             w = torch.zeros((cpad, conv.in_channels, 1, 1), device=a.device)
-            w[:9 * c, :, 0, 0] = conv.weight.detach().float().permute(2, 3, 0, 1).reshape(9 * c, conv.in_channels)
+            w[:9 * c, :, 0, 0] = split_head_weight(conv.weight.detach().float())
             pw.conv[key] = (ops.pack_conv_weight(w, a.dtype), conv.bias.detach().float().contiguous())
         wp, bias = pw.conv[key]
         return ops.head_gather9(ops.conv2d([(a, wp, 0, 1, 0)], out_f32=True), bias, c)

@@ -372,3 +372,22 @@ def test_every_runtime_switch_is_documented():
     design = open(os.path.join(root, "DESIGN.md")).read()
     missing = sorted(v for v in found if v not in design)
     assert not missing, missing
+
+
+def test_split_head_weight_layout_reproduces_conv3x3():
+    """unet.split_head_weight + the 9-point gather b200_head_gather9 performs (restated in torch) == F.conv2d(pad 1)."""
+    import torch.nn.functional as F
+    from diffusion_models_dsdiff_b200.unet import split_head_weight
+    g = torch.Generator().manual_seed(4)
+    for c, cin, h, w in ((1, 8, 5, 7), (2, 16, 6, 6), (3, 8, 4, 9)):
+        x = torch.randn(2, cin, h, w, generator=g, dtype=torch.float64)
+        wt = torch.randn(c, cin, 3, 3, generator=g, dtype=torch.float64)
+        b = torch.randn(c, generator=g, dtype=torch.float64)
+        taps = F.conv2d(x, split_head_weight(wt)[:, :, None, None])               # [N, 9C, H, W]: the 1x1 convolution
+        tp = F.pad(taps, (1, 1, 1, 1))
+        out = b.view(1, c, 1, 1).expand(2, c, h, w).clone()
+        for r in range(3):
+            for s in range(3):
+                t = r * 3 + s
+                out += tp[:, t * c:(t + 1) * c, r:r + h, s:s + w]                # P[n, h + r - 1, w + s - 1, tap * C + co]
+        assert torch.allclose(out, F.conv2d(x, wt, b, padding=1), atol=1e-12)
