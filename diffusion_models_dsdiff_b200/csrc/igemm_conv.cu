@@ -41,6 +41,8 @@ struct ConvKParams {
   int seg_padw[3];          // W padding (== seg_pad except for the 2x2 sub-pixel convolutions of a folded Upsample)
   int out_sy, out_sx, out_oy, out_ox;   // output pixel (h, w) is stored at (h*out_sy + out_oy, w*out_sx + out_ox); 1,1,0,0 = dense
   int seg_halo[3];          // k x k stride-1 segment (k = 3 pad 1, or k = 2) staged as k column-shifted (TH+k-1)-row boxes, each reused by its k tap rows
+  int seg_s2[3];            // 3x3 stride-2 segment on the 5-D parity-plane view of its input: per column shift ONE (TH+1)-row box of
+                            // the row-parity plane that tap rows 0 and 2 share + one box of tap row 1's plane (see launch code)
   const float *bias;
   const float *rowbias;
   int rowbias_stride;
@@ -155,6 +157,22 @@ __device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const void *tmap,
       "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst), "l"(tmap), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// 5-D loads: the parity-plane view of a stride-2 convolution's input (launch code below)
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const void *tmap, uint32_t bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const void *tmap, uint32_t bar_cluster, int c0, int c1, int c2,
+                                                 int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst), "l"(tmap), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "r"(c4)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -267,6 +285,33 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       __syncwarp();
       if (++st == p.stages) { st = 0; ph ^= 1; }
     };
+    // stride-2 3x3 group: two (TH+1)-row boxes of the parity-plane view (planes pya / pyb, first plane rows ia / ib, plane
+    // column j0, channel coordinate ca = c0 + px * cin) + the three weight tiles of column shift sx
+    auto load_group_s2 = [&](int s, int c0, int n_tile, int tap0, uint32_t box_bytes, int ca, int j0, int pya, int ia, int pyb,
+                             int ib, int n0) {
+      mbar_wait(smem_u32(&empty_bar[st]), ph ^ 1);
+      const uint32_t fb_local = smem_u32(&full_bar[st]);
+      const uint32_t sa = smem_base + st * stage_bytes;
+      const int brow = n_tile * p.BN + (int)rank * (p.BN / kCtas);
+      if (elect_one()) {
+        if (kCtas == 2) {
+          const uint32_t fb = mapa_u32(fb_local, 0);
+          mbar_arrive_expect_tx_cluster(fb, 2 * box_bytes + 3 * b_bytes);
+          tma_load_5d_pair(sa, &maps.a[s], fb, ca, j0, pya, ia, n0);
+          tma_load_5d_pair(sa + box_bytes, &maps.a[s], fb, ca, j0, pyb, ib, n0);
+          for (int j = 0; j < 3; ++j)
+            tma_load_3d_pair(sa + a_bytes + j * b_bytes, &maps.b[s], fb, p.seg_coff[s] + c0, brow, tap0 + j * 3);
+        } else {
+          mbar_arrive_expect_tx(fb_local, 2 * box_bytes + 3 * b_bytes);
+          tma_load_5d(sa, &maps.a[s], fb_local, ca, j0, pya, ia, n0);
+          tma_load_5d(sa + box_bytes, &maps.a[s], fb_local, ca, j0, pyb, ib, n0);
+          for (int j = 0; j < 3; ++j)
+            tma_load_3d(sa + a_bytes + j * b_bytes, &maps.b[s], fb_local, p.seg_coff[s] + c0, brow, tap0 + j * 3);
+        }
+      }
+      __syncwarp();
+      if (++st == p.stages) { st = 0; ph ^= 1; }
+    };
     for (int item = tile0; item < p.num_tiles * p.ksplit; item += tile_step) {
       const int tile = item / p.ksplit, split = item - tile * p.ksplit;
       const int g_begin = (int)((long long)split * p.groups_total / p.ksplit);
@@ -293,6 +338,19 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
             for (int sx = 0; sx < ks; ++sx, ++gi)
               if (gi >= g_begin && gi < g_end)
                 load_group(s, c0, n_tile, tbase + sx, ks, ks, halo_bytes, w0 + sx - p.seg_padw[s], h0 - pad, n0);
+        } else if (p.seg_s2[s]) {
+          // input row of output row h, tap row r: 2 h + (r - pad) = plane (r - pad) & 1, plane row h + floor((r - pad) / 2);
+          // tap rows 0 and 2 lie in the same plane one plane row apart: ONE (TH+1)-row box serves both
+          const uint32_t box_bytes = (uint32_t)(p.TH + 1) * p.TW * 128u;
+          const int cy0 = -pad, cy1 = 1 - pad;
+          const int py0 = cy0 & 1, py1 = cy1 & 1;
+          const int i0 = h0 + ((cy0 - py0) >> 1), i1 = h0 + ((cy1 - py1) >> 1);
+          for (int c0 = 0; c0 < cin; c0 += kBK)
+            for (int sx = 0; sx < 3; ++sx, ++gi)
+              if (gi >= g_begin && gi < g_end) {
+                const int cx = sx - p.seg_padw[s], px = cx & 1;
+                load_group_s2(s, c0, n_tile, tbase + sx, box_bytes, c0 + px * cin, w0 + ((cx - px) >> 1), py0, i0, py1, i1, n0);
+              }
         } else {
           for (int tap = 0; tap < ks * ks; ++tap) {
             const int r = tap / ks, sx = tap - r * ks;
@@ -322,13 +380,15 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
         const uint32_t tmem_d = tmem_base + acc * kAccCols;
         uint32_t accumulate = 0;
         // nb weight tiles of the stage; tile j multiplies the activation rows starting j*a_step bytes into the box
-        auto mma_group = [&](int nb, uint32_t a_step, int nk) {
+        // a_off1 / a_off2: byte offsets of weight tiles 1 / 2's activation rows inside the stage (default j * a_step)
+        auto mma_group = [&](int nb, uint32_t a_step, int nk, uint32_t a_off1 = 0xffffffffu, uint32_t a_off2 = 0u) {
           mbar_wait(smem_u32(&full_bar[st]), ph);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t sa = smem_base + st * stage_bytes;
             for (int j = 0; j < nb; ++j) {
-              const uint64_t da = umma_desc_sw128(sa + j * a_step);
+              const uint32_t aoff = a_off1 == 0xffffffffu ? j * a_step : (j == 0 ? 0u : (j == 1 ? a_off1 : a_off2));
+              const uint64_t da = umma_desc_sw128(sa + aoff);
               const uint64_t db = umma_desc_sw128(sa + a_bytes + j * b_bytes);
               for (int k = 0; k < nk; ++k) {
                 // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in >>4 units
@@ -351,6 +411,13 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
             for (int c0 = 0; c0 < cin; c0 += kBK)
               for (int sx = 0; sx < ks; ++sx, ++gi)
                 if (gi >= g_begin && gi < g_end) mma_group(ks, (uint32_t)p.TW * 128u, (min(kBK, cin - c0) + 15) >> 4);
+          } else if (p.seg_s2[s]) {
+            // weight tile j = tap row j: rows 0 and 2 read the first box (one plane row apart), row 1 the second box
+            const uint32_t box_bytes = (uint32_t)(p.TH + 1) * p.TW * 128u;
+            for (int c0 = 0; c0 < cin; c0 += kBK)
+              for (int sx = 0; sx < 3; ++sx, ++gi)
+                if (gi >= g_begin && gi < g_end)
+                  mma_group(3, 0u, (min(kBK, cin - c0) + 15) >> 4, box_bytes, (uint32_t)p.TW * 128u);
           } else {
             for (int tap = 0; tap < taps; ++tap)
               for (int c0 = 0; c0 < cin; c0 += kBK, ++gi)
@@ -828,6 +895,14 @@ static bool seg_is_halo(const b200_conv_seg &g) {
   return (g.ksize == 3 && g.pad == 1 && g.pad_w1 == 0) || (g.ksize == 2 && !no_k2);
 }
 
+// row-pair staging of a 3x3 stride-2 segment on the parity-plane view of its input (even H, W; K steps of 16 channels must
+// not leave a plane's channel range)
+static bool seg_is_s2(const b200_conv_desc *d, const b200_conv_seg &g, int TW, int TN) {
+  static const bool off = getenv("B200DIFF_NO_S2_HALO") != nullptr;
+  return !off && d->stride == 2 && TN == 1 && TW >= 8 && d->Hin % 2 == 0 && d->Win % 2 == 0 && g.ksize == 3 && g.pad_w1 == 0 &&
+         (g.pad == 0 || g.pad == 1) && g.cin % 16 == 0;
+}
+
 static int conv_groups_total(const b200_conv_desc *d) {
   int TW = 1, TH = 1, TN = 1;
   pick_box(d->Hout, d->Wout, &TW, &TH, &TN);
@@ -835,6 +910,7 @@ static int conv_groups_total(const b200_conv_desc *d) {
   int g = 0;
   for (int s = 0; s < d->nseg; ++s) {
     const int chunks = cdiv(d->seg[s].cin, kBK);
+    if (seg_is_s2(d, d->seg[s], TW, TN)) { g += chunks * 3; continue; }
     g += (halo_ok && seg_is_halo(d->seg[s])) ? chunks * d->seg[s].ksize : chunks * d->seg[s].ksize * d->seg[s].ksize;
   }
   return g;
@@ -982,6 +1058,13 @@ static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t
     if (p.seg_halo[s]) halo_taps = std::max(halo_taps, d->seg[s].ksize);
   }
   p.a_bytes = kABytes + (halo_taps - 1) * p.TW * 128;
+  for (int s = 0; s < d->nseg; ++s) {
+    p.seg_s2[s] = seg_is_s2(d, d->seg[s], p.TW, p.TN);
+    if (p.seg_s2[s]) {
+      halo_taps = 3;
+      p.a_bytes = std::max(p.a_bytes, 2 * (p.TH + 1) * p.TW * 128);
+    }
+  }
   const size_t b_bytes = (size_t)(p.BN / kCtas) * 128;
   p.stage_bytes = p.a_bytes + halo_taps * (int)b_bytes;
   p.stages = (int)std::min<size_t>(kMaxStages, (226 * 1024 - 1536 - kStatSmem) / p.stage_bytes);
@@ -995,7 +1078,17 @@ static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t
     B200_CHECK(((uintptr_t)g.src & 15) == 0 && ((uintptr_t)g.weight & 15) == 0, "conv: unaligned pointer");
     p.seg_cin[s] = g.cin; p.seg_coff[s] = g.coff; p.seg_ks[s] = g.ksize; p.seg_pad[s] = g.pad;
     p.seg_padw[s] = g.pad_w1 > 0 ? g.pad_w1 - 1 : g.pad;
-    {  // activations: (C, W, H, N)
+    if (p.seg_s2[s]) {
+      // stride 2 without element strides: pixel (2 i + py, 2 j + px), channel c of the NHWC map is element
+      // (px * C + c, j, py, i, n) of a 5-D view; a tap reads a DENSE box of one parity plane, out-of-bounds j / i are the
+      // zero padding.  Box = (TH+1) plane rows: tap rows 0 and 2 share it (igemm kernel, seg_s2)
+      uint64_t dims[5] = {(uint64_t)g.cin * 2, (uint64_t)d->Win / 2, 2, (uint64_t)d->Hin / 2, (uint64_t)d->N};
+      uint64_t str[4] = {(uint64_t)g.cin * 4, (uint64_t)d->Win * g.cin * 2, (uint64_t)d->Win * g.cin * 4,
+                         (uint64_t)d->Hin * d->Win * g.cin * 2};
+      uint32_t box[5] = {kBK, (uint32_t)p.TW, 1, (uint32_t)(p.TH + 1), 1};
+      uint32_t es[5] = {1, 1, 1, 1, 1};
+      if (int rc = cached_tmap(&maps.a[s], g.src, 5, dims, str, box, es)) return rc;
+    } else {  // activations: (C, W, H, N)
       uint64_t dims[4] = {(uint64_t)g.cin, (uint64_t)d->Win, (uint64_t)d->Hin, (uint64_t)d->N};
       uint64_t str[3] = {(uint64_t)g.cin * 2, (uint64_t)d->Win * g.cin * 2,
                          (uint64_t)d->Hin * d->Win * g.cin * 2};
