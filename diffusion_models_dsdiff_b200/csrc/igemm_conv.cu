@@ -41,6 +41,7 @@ struct ConvKParams {
   int seg_padw[3];          // W padding (== seg_pad except for the 2x2 sub-pixel convolutions of a folded Upsample)
   int out_sy, out_sx, out_oy, out_ox;   // output pixel (h, w) is stored at (h*out_sy + out_oy, w*out_sx + out_ox); 1,1,0,0 = dense
   int seg_halo[3];          // k x k stride-1 segment (k = 3 pad 1, or k = 2) staged as k column-shifted (TH+k-1)-row boxes, each reused by its k tap rows
+  int seg_kgroup[3];        // K chunks (64 channels each) per pipeline stage of a per-tap segment: 2 for 1x1 segments, else 1
   int seg_s2[3];            // 3x3 stride-2 segment on the 5-D parity-plane view of its input: per column shift ONE (TH+1)-row box of
                             // the row-parity plane that tap rows 0 and 2 share + one box of tap row 1's plane (see launch code)
   const float *bias;
@@ -285,6 +286,31 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
       __syncwarp();
       if (++st == p.stages) { st = 0; ph ^= 1; }
     };
+    // nc consecutive 64-channel chunks of ONE tap in one stage (1x1 segments): nc activation boxes + nc weight tiles
+    auto load_group_k = [&](int s, int c0, int nc, int n_tile, int tap, int win, int hin, int n0) {
+      mbar_wait(smem_u32(&empty_bar[st]), ph ^ 1);
+      const uint32_t fb_local = smem_u32(&full_bar[st]);
+      const uint32_t sa = smem_base + st * stage_bytes;
+      const int brow = n_tile * p.BN + (int)rank * (p.BN / kCtas);
+      if (elect_one()) {
+        if (kCtas == 2) {
+          const uint32_t fb = mapa_u32(fb_local, 0);
+          mbar_arrive_expect_tx_cluster(fb, nc * ((uint32_t)kABytes + b_bytes));
+          for (int j = 0; j < nc; ++j) {
+            tma_load_4d_pair(sa + j * kABytes, &maps.a[s], fb, c0 + j * kBK, win, hin, n0);
+            tma_load_3d_pair(sa + a_bytes + j * b_bytes, &maps.b[s], fb, p.seg_coff[s] + c0 + j * kBK, brow, tap);
+          }
+        } else {
+          mbar_arrive_expect_tx(fb_local, nc * ((uint32_t)kABytes + b_bytes));
+          for (int j = 0; j < nc; ++j) {
+            tma_load_4d(sa + j * kABytes, &maps.a[s], fb_local, c0 + j * kBK, win, hin, n0);
+            tma_load_3d(sa + a_bytes + j * b_bytes, &maps.b[s], fb_local, p.seg_coff[s] + c0 + j * kBK, brow, tap);
+          }
+        }
+      }
+      __syncwarp();
+      if (++st == p.stages) { st = 0; ph ^= 1; }
+    };
     // stride-2 3x3 group: two (TH+1)-row boxes of the parity-plane view (planes pya / pyb, first plane rows ia / ib, plane
     // column j0, channel coordinate ca = c0 + px * cin) + the three weight tiles of column shift sx
     auto load_group_s2 = [&](int s, int c0, int n_tile, int tap0, uint32_t box_bytes, int ca, int j0, int pya, int ia, int pyb,
@@ -352,12 +378,18 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
                 load_group_s2(s, c0, n_tile, tbase + sx, box_bytes, c0 + px * cin, w0 + ((cx - px) >> 1), py0, i0, py1, i1, n0);
               }
         } else {
+          const int kg = p.seg_kgroup[s];
           for (int tap = 0; tap < ks * ks; ++tap) {
             const int r = tap / ks, sx = tap - r * ks;
-            for (int c0 = 0; c0 < cin; c0 += kBK, ++gi)
-              if (gi >= g_begin && gi < g_end)
-                load_group(s, c0, n_tile, tbase + tap, 0, 1, (uint32_t)kABytes, w0 * p.stride + sx - p.seg_padw[s],
-                           h0 * p.stride + r - pad, n0);
+            for (int c0 = 0; c0 < cin; c0 += kBK * kg, ++gi)
+              if (gi >= g_begin && gi < g_end) {
+                if (kg == 1)
+                  load_group(s, c0, n_tile, tbase + tap, 0, 1, (uint32_t)kABytes, w0 * p.stride + sx - p.seg_padw[s],
+                             h0 * p.stride + r - pad, n0);
+                else
+                  load_group_k(s, c0, min(kg, (cin - c0 + kBK - 1) / kBK), n_tile, tbase + tap,
+                               w0 * p.stride + sx - p.seg_padw[s], h0 * p.stride + r - pad, n0);
+              }
           }
         }
       }
@@ -381,7 +413,9 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
         uint32_t accumulate = 0;
         // nb weight tiles of the stage; tile j multiplies the activation rows starting j*a_step bytes into the box
         // a_off1 / a_off2: byte offsets of weight tiles 1 / 2's activation rows inside the stage (default j * a_step)
-        auto mma_group = [&](int nb, uint32_t a_step, int nk, uint32_t a_off1 = 0xffffffffu, uint32_t a_off2 = 0u) {
+        // k_left >= 0: tile j covers channels [j * 64, ...) of the k_left channels left in the segment (its own K step count)
+        auto mma_group = [&](int nb, uint32_t a_step, int nk, uint32_t a_off1 = 0xffffffffu, uint32_t a_off2 = 0u,
+                             int k_left = -1) {
           mbar_wait(smem_u32(&full_bar[st]), ph);
           tc_fence_after();
           if (elect_one()) {
@@ -390,6 +424,7 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
               const uint32_t aoff = a_off1 == 0xffffffffu ? j * a_step : (j == 0 ? 0u : (j == 1 ? a_off1 : a_off2));
               const uint64_t da = umma_desc_sw128(sa + aoff);
               const uint64_t db = umma_desc_sw128(sa + a_bytes + j * b_bytes);
+              if (k_left >= 0) nk = (min(kBK, k_left - j * kBK) + 15) >> 4;
               for (int k = 0; k < nk; ++k) {
                 // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in >>4 units
                 const uint32_t accf = accumulate | (uint32_t)(j | k);
@@ -419,9 +454,13 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
                 if (gi >= g_begin && gi < g_end)
                   mma_group(3, 0u, (min(kBK, cin - c0) + 15) >> 4, box_bytes, (uint32_t)p.TW * 128u);
           } else {
+            const int kg = p.seg_kgroup[s];
             for (int tap = 0; tap < taps; ++tap)
-              for (int c0 = 0; c0 < cin; c0 += kBK, ++gi)
-                if (gi >= g_begin && gi < g_end) mma_group(1, 0u, (min(kBK, cin - c0) + 15) >> 4);
+              for (int c0 = 0; c0 < cin; c0 += kBK * kg, ++gi)
+                if (gi >= g_begin && gi < g_end) {
+                  if (kg == 1) mma_group(1, 0u, (min(kBK, cin - c0) + 15) >> 4);
+                  else mma_group(min(kg, (cin - c0 + kBK - 1) / kBK), (uint32_t)kABytes, 0, 0xffffffffu, 0u, cin - c0);
+                }
           }
         }
         if (elect_one()) {
@@ -903,7 +942,13 @@ static bool seg_is_s2(const b200_conv_desc *d, const b200_conv_seg &g, int TW, i
          (g.pad == 0 || g.pad == 1) && g.cin % 16 == 0;
 }
 
-static int conv_groups_total(const b200_conv_desc *d) {
+// K chunks per stage of a per-tap segment: 1x1 segments (and plain GEMMs) stage two 64-channel chunks per barrier round trip
+static int seg_kgroup(const b200_conv_seg &g) {
+  static const bool off = getenv("B200DIFF_NO_KGROUP") != nullptr;
+  return (g.ksize == 1 && !off) ? 2 : 1;
+}
+
+static int conv_groups_total(const b200_conv_desc *d, bool raw = false) {
   int TW = 1, TH = 1, TN = 1;
   pick_box(d->Hout, d->Wout, &TW, &TH, &TN);
   const bool halo_ok = d->stride == 1 && TN == 1 && TW >= 8 && !getenv("B200DIFF_NO_HALO");
@@ -911,7 +956,8 @@ static int conv_groups_total(const b200_conv_desc *d) {
   for (int s = 0; s < d->nseg; ++s) {
     const int chunks = cdiv(d->seg[s].cin, kBK);
     if (seg_is_s2(d, d->seg[s], TW, TN)) { g += chunks * 3; continue; }
-    g += (halo_ok && seg_is_halo(d->seg[s])) ? chunks * d->seg[s].ksize : chunks * d->seg[s].ksize * d->seg[s].ksize;
+    g += (halo_ok && seg_is_halo(d->seg[s])) ? chunks * d->seg[s].ksize
+                                             : cdiv(chunks, raw ? 1 : seg_kgroup(d->seg[s])) * d->seg[s].ksize * d->seg[s].ksize;
   }
   return g;
 }
@@ -924,13 +970,14 @@ static int conv_ksplit(const b200_conv_desc *d) {
   // measured inside a CUDA graph (tools/graph_probe.py): 8x8 3x3 960->960 48.6 -> 33.4 us with S = 9, but 1x1 layers
   // (G = 15) and 16x16 maps (S = 2) lose to the extra finalize launch, so only long-K layers on <= 8x8 maps split
   if ((long)d->Hout * d->Wout > 64 || d->Cout % 8) return 1;
-  const int G = conv_groups_total(d);
+  const int G = conv_groups_total(d, /*raw=*/true);      // 64-channel K chunks (the thresholds were measured in these units)
   if (G < 36) return 1;
   // work items a NOMINAL batch of 8 images would give without splitting (geometry only)
   const long tiles8 = (long)std::max(1, d->wsets) * cdiv(8 * d->Hout * d->Wout, 2 * kBM) * cdiv(d->Cout, pick_bn(d->Cout));
   const int pairs = num_sms() / 2;
   int S = (int)((pairs + tiles8 / 2) / tiles8);
   S = std::min(S, std::min(16, G / 4));
+  S = std::min(S, conv_groups_total(d));
   return S < 4 ? 1 : S;
 }
 
@@ -1059,6 +1106,11 @@ static int launch_conv(const b200_conv_desc *d, int bn, int ksplit, cudaStream_t
   }
   p.a_bytes = kABytes + (halo_taps - 1) * p.TW * 128;
   for (int s = 0; s < d->nseg; ++s) {
+    p.seg_kgroup[s] = seg_kgroup(d->seg[s]);
+    if (p.seg_kgroup[s] > 1) {
+      halo_taps = std::max(halo_taps, p.seg_kgroup[s]);
+      p.a_bytes = std::max(p.a_bytes, p.seg_kgroup[s] * kABytes);
+    }
     p.seg_s2[s] = seg_is_s2(d, d->seg[s], p.TW, p.TN);
     if (p.seg_s2[s]) {
       halo_taps = 3;
