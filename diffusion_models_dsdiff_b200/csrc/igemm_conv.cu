@@ -550,18 +550,24 @@ conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const ConvKParams p) {
                                                  (size_t)(n - ws_thr * p.n_per_set) * p.rowscale_stride : nullptr;
       if (staged_bias) {
         __syncwarp();
-        for (int slot = lane; slot < 128; slot += 32) {
+        // all (up to 8) loads of the warp's 128 columns are issued before the first add: ONE exposed L2 latency per tile
+        // instead of four (this staging is on the critical path of short-K GEMMs, whose epilogue outlasts the mainloop)
+        float bb[4], rb[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int slot = lane + 32 * q;
           const int chunk = (slot >> 4) * 2 + g;
           const int co = n_tile * p.BN + chunk * 16 + (slot & 15);
-          float b = 0.f;
+          bb[q] = 0.f; rb[q] = 0.f;
           if (chunk * 16 < p.BN && co < p.Cout) {
-            if (p.bias) b = __ldg(p.bias + (size_t)ws_warp * p.Cout + co);
+            if (p.bias) bb[q] = __ldg(p.bias + (size_t)ws_warp * p.Cout + co);
             if (p.rowbias && n_warp < p.N)
-              b += __ldg(p.rowbias + (size_t)ws_warp * p.rowbias_gstride +
-                         (size_t)(n_warp - ws_warp * p.n_per_set) * p.rowbias_stride + co);
+              rb[q] = __ldg(p.rowbias + (size_t)ws_warp * p.rowbias_gstride +
+                            (size_t)(n_warp - ws_warp * p.n_per_set) * p.rowbias_stride + co);
           }
-          bs[slot] = b;
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bs[lane + 32 * q] = bb[q] + rb[q];
         __syncwarp();
       }
       float amax = 0.f;          // largest |result| this thread stores in this tile (fp16 range guard)
